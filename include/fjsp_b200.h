@@ -1,0 +1,181 @@
+/*
+ * fjsp_b200.h — C ABI of the B200-native batched FJSP environment (libfjsp_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of FARIDKH/Multi-agent-RL-for-FJSP: the
+ * environment step.  The reference has no FFI; its boundary is the Python class
+ * FJSPParallelEnv (FJSPParallelEnvWrapper.py:9-136) over FJSPSimulation (FJSPSimulation.py:27-430).
+ * Each entry point below names the reference interface it replaces.  The Python host side
+ * (multi_agent_rl_for_fjsp_b200/env.py, FJSPParallelEnvWrapper.py) binds these with ctypes and
+ * passes torch tensors' data_ptr(); no torch type appears here.
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (fjsp_last_error() gives the
+ * thread-local message).  No exceptions cross the ABI.  Device pointers are caller-owned.  Calls
+ * that take a `stream` enqueue work on that cudaStream_t (passed as void*) and do not synchronise
+ * the host unless stated.  A handle belongs to one device and is not thread-safe.
+ */
+#ifndef FJSP_B200_H
+#define FJSP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FJSP_ABI_VERSION 1
+
+/* ---- fixed shape of the problem (reference: 8 agents, FJSPSimulation.py:62-82) ---- */
+#define FJSP_NUM_AGENTS 8          /* pickup_station, agv, small_machine, big_machine, packaging_blue_1, _blue_2, _red, _green */
+#define FJSP_OBS_DIM 38            /* a2c._flatten_obs order, SURVEY.md §8a-R9 (a2c.py:137-151) */
+#define FJSP_MASK_DIM 32           /* 29 used: 3 + 8 + 6*3, padded to 32 */
+#define FJSP_MASK_USED 29
+#define FJSP_FLAG_DIM 4            /* terminated, truncated, fault, was_reset */
+#define FJSP_INFO_DIM 4            /* current_step, orders_completed, total_products_packaged, reserved */
+#define FJSP_MAX_ORDERS 32         /* reference reset default is 30 (FJSPSimulation.py:316) */
+#define FJSP_MAX_ORDER_PRODUCTS 9  /* np.random.randint(1,10) (FJSPSimulation.py:107) */
+#define FJSP_NUM_LOCATIONS 5       /* LocationType order: PICKUP, BIG_MACHINE, SMALL_MACHINE, STORAGE, PACKAGING */
+#define FJSP_TRAY_CAPACITY 5       /* constants.py:22; the mask hard-codes the global (PickupStationAgent.py:125) */
+#define FJSP_POOL_SLOTS 64         /* trays in transit per env (bound: 1 + max_episode_steps/4 = 51) */
+#define FJSP_STATE_WORDS 128       /* packed state: 128 x u32 = 512 B per env */
+#define FJSP_TILE_ENVS 64          /* envs per HBM tile (array-of-tiles, each tile word-major [128][64]) */
+
+/* fault codes (flags[2]); the reference has no equivalent — see DESIGN.md "faults" */
+#define FJSP_FAULT_NONE 0
+#define FJSP_FAULT_PKG_RESTART_WITH_WAITERS 1 /* reference raises ValueError out of env.run (SURVEY R-PKG-cap-b) */
+#define FJSP_FAULT_POOL_EXHAUSTED 2           /* >64 trays in transit: impossible when max_episode_steps <= 252 */
+
+/* Mirrors constants.py:5-32 (LOCATION_POSITIONS, PROCESSING_TIMES, CONFIG). */
+typedef struct FjspConfig {
+    int32_t struct_size;                   /* sizeof(FjspConfig), for ABI checking */
+    int32_t pos[FJSP_NUM_LOCATIONS][2];    /* (row, col) per LocationType, constants.py:5-11 */
+    int32_t grid_rows, grid_cols;          /* constants.py:26-27 (observation-space bounds only) */
+    int32_t proc_small, proc_big, proc_pack; /* constants.py:14-18, sim time units; multiples of step_size */
+    int32_t step_size;                     /* constants.py:29 */
+    int32_t agv_speed;                     /* constants.py:28 */
+    int32_t max_episode_steps;             /* constants.py:31; <= 252 */
+    int32_t storage_capacity;              /* FJSPSimulation.py:87 default 100 */
+    int32_t pack_capacity;                 /* PackagingAgent.py:46 simpy.Resource(capacity=20); <= 31 */
+    int32_t tray_capacity;                 /* must be 5 */
+    int32_t num_trays;                     /* constants.py:21; min(num_trays,1000) reach the pickup station (FJSPSimulation.py:96) */
+} FjspConfig;
+
+/* One order as the reference generates it (FJSPSimulation.py:101-131): all products of an order
+ * share type and colour.  Packed u32: n | type<<8 | colour<<16. */
+typedef uint32_t FjspOrderRec;
+#define FJSP_ORDER_REC(n, type, colour) ((uint32_t)(n) | ((uint32_t)(type) << 8) | ((uint32_t)(colour) << 16))
+
+/* ---- canonical integer state S: the record both sides export for bit-exact diff ----
+ * tray entry  = tray_id | order<<16 | first_product_idx<<22 | count<<26      (-1 = none)
+ * product id  = order*100 + idx  (FJSPSimulation.py:115)                     (-1 = none)            */
+#define FJSP_CANON_MAXQ 64
+#define FJSP_CANON_PS_READY 256
+#define FJSP_CANON_MAXPQ 256
+#define FJSP_TRAY_ENTRY(id, order, first, count) ((int32_t)((id) | ((order) << 16) | ((first) << 22) | ((count) << 26)))
+
+typedef struct FjspCanonMachine {
+    int32_t is_busy, current_tray, progress_done;
+    int32_t queue_n, queue[FJSP_CANON_MAXQ];
+    int32_t ready_n, ready[FJSP_CANON_MAXQ];
+} FjspCanonMachine;
+
+typedef struct FjspCanonPack {
+    int32_t is_busy, current_product, progress_L, products_completed, users;
+    int32_t queue_n, queue[FJSP_CANON_MAXPQ];
+} FjspCanonPack;
+
+typedef struct FjspCanonState {
+    int32_t current_step, num_orders, fault;
+    int32_t agv_row, agv_col, agv_carry, agv_is_moving;
+    int32_t ps_order_queue_len, ps_current_order, ps_product_idx, ps_current_tray, ps_trays_at_station;
+    int32_t ps_ready_n, ps_ready[FJSP_CANON_PS_READY];
+    FjspCanonMachine machine[2];           /* 0 = small_machine, 1 = big_machine */
+    int32_t storage_n, storage[FJSP_CANON_MAXQ];
+    FjspCanonPack pack[4];                 /* blue_1, blue_2, red, green */
+    int32_t processed_mask[FJSP_MAX_ORDERS];  /* bit i = products[i].is_processed */
+    int32_t packaged_mask[FJSP_MAX_ORDERS];   /* bit i = products[i].is_packaged */
+    int32_t order_complete[FJSP_MAX_ORDERS];
+    int32_t order_completion_step[FJSP_MAX_ORDERS]; /* completion_time / step_size - 1, or -1 */
+    int32_t total_products_packaged, completed_orders;
+} FjspCanonState;
+
+typedef struct FjspHandle FjspHandle;
+
+/* Per-rollout counters written by fjsp_rollout_random (device memory, 8 x u64). */
+#define FJSP_STATS_WORDS 8 /* env_steps, episodes, orders_completed, products_packaged, faults, reward_sum_x40, 0, 0 */
+
+const char* fjsp_last_error(void);
+int fjsp_abi_version(void);
+
+/* constants.py:5-32 defaults. */
+int fjsp_default_config(FjspConfig* cfg);
+
+/* FJSPParallelEnv.__init__ (FJSPParallelEnvWrapper.py:27-33) for `num_envs` independent shops on
+ * CUDA device `device`.  `first_env` is the global index of env 0 of this handle (multi-GPU
+ * sharding: Philox counters use first_env + local index, so results do not depend on the shard map). */
+int fjsp_create(const FjspConfig* cfg, int64_t num_envs, int64_t first_env, int device, FjspHandle** out);
+int fjsp_destroy(FjspHandle* h);
+int64_t fjsp_num_envs(const FjspHandle* h);
+size_t fjsp_state_bytes(const FjspHandle* h);   /* packed HBM bytes per env (512) */
+void* fjsp_state_ptr(FjspHandle* h);            /* device pointer of the packed state (tiles) */
+
+/* FJSPParallelEnv.reset (FJSPParallelEnvWrapper.py:43-54) -> FJSPSimulation.reset (:286-323).
+ *   env_mask  : device u8[N] (non-zero = reset that env) or NULL = all
+ *   orders    : device FjspOrderRec[N][FJSP_MAX_ORDERS] explicit order tables, or NULL = draw
+ *               n~U{1..9}, type~U{1..3}, colour~U{1..3} from Philox4x32-10(key=seed,
+ *               counter=(global env, episode, order, 0)) — replayable on the host
+ *   num_orders: 0..32 (reference default 30)
+ *   obs/masks : device float[N][38] / int8[N][32] initial observations (may be NULL)            */
+int fjsp_reset(FjspHandle* h, const uint8_t* env_mask, uint64_t seed, const FjspOrderRec* orders,
+               int num_orders, float* obs, int8_t* masks, void* stream);
+
+/* FJSPParallelEnv.step (FJSPParallelEnvWrapper.py:56-69) -> FJSPSimulation.step (:144-242) for all
+ * N envs in lockstep; ONE kernel launch.
+ *   actions : device u8[N][8], agent order = FJSPSimulation.py:76-82
+ *   obs     : device float[N][38]    masks: device int8[N][32]    rewards: device float[N][8]
+ *   flags   : device u8[N][4] = terminated, truncated, fault, was_reset
+ *   results : device u8[N][8] per-agent action_result bit-fields, or NULL   (see FJSP_RES_*)
+ *   infos   : device int32[N][4] = current_step, orders_completed, total_products_packaged, 0, or NULL
+ *   autoreset: non-zero = envs that end (terminated|truncated|fault) are re-initialised inside the
+ *              step (episode counter + 1, fresh Philox orders) and return the post-reset observation */
+int fjsp_step(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, float* rewards,
+              uint8_t* flags, uint8_t* results, int32_t* infos, int autoreset, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): H2D actions, step, D2H outputs, stream
+ * synchronised on return.  This is the end-to-end path bench.py reports as `e2e`. */
+int fjsp_step_host(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, float* rewards,
+                   uint8_t* flags, int autoreset, void* stream);
+
+/* a_i ~ U{0..n_i-1}, n = (3,8,3,3,3,3,3,3), Philox4x32-10(key=seed, counter=(global env, t, 0, 1)). */
+int fjsp_random_actions(FjspHandle* h, uint64_t seed, uint64_t t, uint8_t* actions, void* stream);
+
+/* `steps` lockstep steps with in-kernel random actions (same stream as fjsp_random_actions with
+ * t = t0 .. t0+steps-1) and autoreset, state kept on-chip between steps; adds to stats[8] (device u64). */
+int fjsp_rollout_random(FjspHandle* h, int steps, uint64_t seed, uint64_t t0, uint64_t* stats, void* stream);
+
+/* Canonical record S of one env, decoded on the host (synchronises). Diagnostic / parity path. */
+int fjsp_export_state(FjspHandle* h, int64_t env, FjspCanonState* out);
+/* Raw packed words of one env (128 x u32) copied to the host (synchronises). */
+int fjsp_export_packed(FjspHandle* h, int64_t env, uint32_t* out_words);
+
+/* Number of kernels this library has launched since the handle was created. */
+int64_t fjsp_launch_count(const FjspHandle* h);
+
+/* action_result bit-fields (results[N][8]); reference dict keys in comments */
+#define FJSP_RES_SUCCESS 0x01        /* 'success' */
+#define FJSP_RES_PS_LOADED 0x02      /* 'product_loaded'    PickupStationAgent.py:197 */
+#define FJSP_RES_PS_TRAY_DONE 0x04   /* 'tray_completed'    PickupStationAgent.py:207,215 */
+#define FJSP_RES_PS_IDLE_ORDERS 0x08 /* 'idle_with_orders'  PickupStationAgent.py:163 */
+#define FJSP_RES_AGV_INVALID 0x02    /* 'invalid_action'    AGVAgent.py:211 */
+#define FJSP_RES_AGV_MOVED 0x04      /* 'moved'             AGVAgent.py:240 */
+#define FJSP_RES_AGV_PICKUP 0x08     /* 'pickup_success'    AGVAgent.py:288 */
+#define FJSP_RES_AGV_DROP 0x10       /* 'drop_success'      AGVAgent.py:366 */
+#define FJSP_RES_AGV_TO_PACK 0x20    /* 'delivered_to_packaging' AGVAgent.py:357 */
+#define FJSP_RES_M_STARTED 0x02      /* 'started_processing' / 'started_packaging' */
+#define FJSP_RES_M_COMPLETED 0x04    /* 'completed_processing' / 'completed_packaging' */
+#define FJSP_RES_M_IDLE_QUEUE 0x08   /* 'idle_with_queue' */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FJSP_B200_H */

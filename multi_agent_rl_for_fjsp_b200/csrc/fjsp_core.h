@@ -1,0 +1,776 @@
+// fjsp_core.h — packed per-env state (128 x u32 = 512 B) and the lockstep step function.
+//
+// This is the device code of the hot path (FJSPSimulation.step, /root/reference/FJSPSimulation.py:144-242,
+// and everything it calls in agents/*.py, models/*.py, utils/RewardModel.py).  It is written against an
+// abstract word accessor S { u32 ld(int w); void st(int w, u32 v); } so the same source runs
+//   * in the CUDA kernels with S = one column of a shared-memory tile  (fjsp_kernels.cu), and
+//   * in tests/host_harness (g++ build, tests only) with S = a plain array,
+// which lets the CPU-only test suite exercise the packed-state logic against the oracle.  The product
+// library has no CPU execution path: libfjsp_b200.so only ever launches the kernels.
+//
+// The algorithm is NOT a translation of the reference's SimPy object graph; it is an integer tick model:
+//   - orders live in one u32 each (n, type, colour, tray-cut mask, packaged mask),
+//   - trays waiting at the pickup station are implicit (a cursor over the cut masks),
+//   - trays in transit live in a 64-slot pool of u32 records linked into FIFOs by 6-bit next indices,
+//   - SimPy timers become start/finish step stamps resolved in the run phase of the step they fire in
+//     (rule R0 of SURVEY.md §8a: a timeout of T time units started in step k fires in step k + T/step_size).
+#ifndef FJSP_CORE_H
+#define FJSP_CORE_H
+
+#include <stdint.h>
+
+#include "../../include/fjsp_b200.h"
+
+#if defined(__CUDACC__)
+#define FJSP_HD __host__ __device__ __forceinline__
+#else
+#define FJSP_HD inline
+#endif
+
+namespace fjsp {
+
+typedef uint32_t u32;
+
+// ---------------------------------------------------------------------------------------------
+// Derived configuration, passed by value to every kernel (constants.py:5-32 after validation).
+// ---------------------------------------------------------------------------------------------
+struct Params {
+    int32_t pos_row[FJSP_NUM_LOCATIONS], pos_col[FJSP_NUM_LOCATIONS];
+    int32_t dist[FJSP_NUM_LOCATIONS][FJSP_NUM_LOCATIONS];   // Manhattan distance (AGVAgent.py:229)
+    int32_t delay[FJSP_NUM_LOCATIONS][FJSP_NUM_LOCATIONS];  // floor(d / (agv_speed*step_size)) steps until arrival
+    int32_t small_steps, big_steps, pack_steps;             // PROCESSING_TIMES / step_size
+    int32_t max_episode_steps, storage_capacity, pack_capacity, trays_total, num_trays;
+    int32_t step_size;
+    double time_reward;                                     // TIME_PENALTY * step_size (RewardModel.py:42)
+    float progress_tab[256];                                // float32((1/L)*100) (PackagingAgent.py:117)
+};
+
+// location indices = LocationType order (enums/LocationType.py:3-8)
+enum { LOC_PICKUP = 0, LOC_BIG = 1, LOC_SMALL = 2, LOC_STORAGE = 3, LOC_PACKAGING = 4 };
+enum { TYPE_SMALL = 1, TYPE_MEDIUM = 2, TYPE_BIG = 3 };
+enum { COL_RED = 1, COL_BLUE = 2, COL_GREEN = 3 };
+
+// ---------------------------------------------------------------------------------------------
+// Word map of the packed state.
+// ---------------------------------------------------------------------------------------------
+enum {
+    W_CTRL = 0,     // step16 | num_orders6<<16 | fault2<<22 | completed_orders6<<24
+    W_PS = 1,       // total_packaged9 | next_order6<<9 | cur_order6<<15 (63=none) | prod_idx4<<21 | cur_tray_count3<<25
+    W_PSQ = 2,      // alloc_count8 | ready_count8<<8 | ready_order6<<16 | ready_idx4<<22
+    W_AGV = 3,      // loc3 | moving1<<3 | target3<<4 | arrive16<<7 | carry7<<23 (slot+1, 0 = none)
+    W_FREE_LO = 4,  // pool free bitmap, slots 0..31 (1 = free)
+    W_FREE_HI = 5,  // slots 32..63
+    W_EPISODE = 6,  // Philox episode counter
+    W_STORAGE = 7,  // head6 | tail6<<6 | len8<<12
+    W_MACH = 8,     // 2 machines x 2 words (small, big)
+                    //   A: busy1 | has_cur1<<1 | cur6<<2 | start16<<8 | prog1<<24 | qlen6<<25
+                    //   B: qhead6 | qtail6<<6 | rhead6<<12 | rtail6<<18 | rlen6<<24
+    W_PACK = 12,    // 4 stations x 3 words (blue_1, blue_2, red, green)
+                    //   A: qhead6 | qtail6<<6 | qrec6<<12 | fhead6<<18 | ftail6<<24
+                    //   B: frec6 | users5<<6 | busy1<<11 | waiters1<<12 | hascur1<<13 | curprod9<<14 | qcount8<<23
+                    //   C: completed8 | progL8<<8
+    W_CSTEP = 24,   // 32 x u8 completion step + 1 (0 = not complete), 4 per word
+    W_ORDER = 32,   // 32 x order word: n4 | type2<<4 | colour2<<6 | cut8<<8 | packaged9<<16
+    W_POOL = 64,    // 64 x tray record: order5 | first4<<5 | count3<<9 | processed1<<12 | next6<<13 | stamp8<<19 | lost1<<27
+    W_TOTAL = 128
+};
+static_assert(W_TOTAL == FJSP_STATE_WORDS, "state size");
+
+// order word
+FJSP_HD int ord_n(u32 w) { return (int)(w & 15u); }
+FJSP_HD int ord_type(u32 w) { return (int)((w >> 4) & 3u); }
+FJSP_HD int ord_colour(u32 w) { return (int)((w >> 6) & 3u); }
+FJSP_HD u32 ord_cut(u32 w) { return (w >> 8) & 0xffu; }
+FJSP_HD u32 ord_packaged(u32 w) { return (w >> 16) & 0x1ffu; }
+FJSP_HD u32 make_order(int n, int type, int colour) { return (u32)n | ((u32)type << 4) | ((u32)colour << 6); }
+
+// tray record
+FJSP_HD int rec_order(u32 r) { return (int)(r & 31u); }
+FJSP_HD int rec_first(u32 r) { return (int)((r >> 5) & 15u); }
+FJSP_HD int rec_count(u32 r) { return (int)((r >> 9) & 7u); }
+FJSP_HD int rec_processed(u32 r) { return (int)((r >> 12) & 1u); }
+FJSP_HD int rec_next(u32 r) { return (int)((r >> 13) & 63u); }
+FJSP_HD int rec_stamp(u32 r) { return (int)((r >> 19) & 255u); }
+FJSP_HD int rec_lost(u32 r) { return (int)((r >> 27) & 1u); }
+FJSP_HD u32 make_rec(int order, int first, int count, int processed) {
+    return (u32)order | ((u32)first << 5) | ((u32)count << 9) | ((u32)processed << 12);
+}
+FJSP_HD u32 rec_with_next(u32 r, int next) { return (r & ~(63u << 13)) | ((u32)next << 13); }
+FJSP_HD u32 rec_with_stamp(u32 r, int stamp) { return (r & ~(255u << 19)) | ((u32)(stamp & 255) << 19); }
+
+FJSP_HD int ctz32(u32 x) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+FJSP_HD int popc32(u32 x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// Unpacked hot scalars (words 0..23).  Loaded once per step, kept in registers, stored once.
+// ---------------------------------------------------------------------------------------------
+struct Fifo {
+    int head, tail, len;
+};
+struct Mach {
+    int busy, has_cur, cur, start, prog;
+    Fifo q, r;
+};
+struct Pack {
+    Fifo q, f;  // queued tray records, in-flight tray records (len = record count)
+    int users, busy, waiters, hascur, curprod, qcount, completed, progL;
+};
+struct Hot {
+    int step, num_orders, fault, completed_orders;
+    int total_packaged, next_order, cur_order, prod_idx, cur_tray_count;
+    int alloc_count, ready_count, ready_order, ready_idx;
+    int agv_loc, agv_moving, agv_target, agv_arrive, carry;
+    u32 free_lo, free_hi, episode;
+    Fifo storage;
+    Mach m[2];
+    Pack p[4];
+};
+
+template <class S>
+FJSP_HD void load_hot(S& s, Hot& h) {
+    u32 w = s.ld(W_CTRL);
+    h.step = (int)(w & 0xffffu), h.num_orders = (int)((w >> 16) & 63u), h.fault = (int)((w >> 22) & 3u);
+    h.completed_orders = (int)((w >> 24) & 63u);
+    w = s.ld(W_PS);
+    h.total_packaged = (int)(w & 511u), h.next_order = (int)((w >> 9) & 63u), h.cur_order = (int)((w >> 15) & 63u);
+    h.prod_idx = (int)((w >> 21) & 15u), h.cur_tray_count = (int)((w >> 25) & 7u);
+    w = s.ld(W_PSQ);
+    h.alloc_count = (int)(w & 255u), h.ready_count = (int)((w >> 8) & 255u), h.ready_order = (int)((w >> 16) & 63u);
+    h.ready_idx = (int)((w >> 22) & 15u);
+    w = s.ld(W_AGV);
+    h.agv_loc = (int)(w & 7u), h.agv_moving = (int)((w >> 3) & 1u), h.agv_target = (int)((w >> 4) & 7u);
+    h.agv_arrive = (int)((w >> 7) & 0xffffu), h.carry = (int)((w >> 23) & 127u);
+    h.free_lo = s.ld(W_FREE_LO), h.free_hi = s.ld(W_FREE_HI), h.episode = s.ld(W_EPISODE);
+    w = s.ld(W_STORAGE);
+    h.storage.head = (int)(w & 63u), h.storage.tail = (int)((w >> 6) & 63u), h.storage.len = (int)((w >> 12) & 255u);
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        Mach& m = h.m[i];
+        w = s.ld(W_MACH + 2 * i);
+        m.busy = (int)(w & 1u), m.has_cur = (int)((w >> 1) & 1u), m.cur = (int)((w >> 2) & 63u);
+        m.start = (int)((w >> 8) & 0xffffu), m.prog = (int)((w >> 24) & 1u), m.q.len = (int)((w >> 25) & 63u);
+        w = s.ld(W_MACH + 2 * i + 1);
+        m.q.head = (int)(w & 63u), m.q.tail = (int)((w >> 6) & 63u), m.r.head = (int)((w >> 12) & 63u);
+        m.r.tail = (int)((w >> 18) & 63u), m.r.len = (int)((w >> 24) & 63u);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        Pack& p = h.p[i];
+        w = s.ld(W_PACK + 3 * i);
+        p.q.head = (int)(w & 63u), p.q.tail = (int)((w >> 6) & 63u), p.q.len = (int)((w >> 12) & 63u);
+        p.f.head = (int)((w >> 18) & 63u), p.f.tail = (int)((w >> 24) & 63u);
+        w = s.ld(W_PACK + 3 * i + 1);
+        p.f.len = (int)(w & 63u), p.users = (int)((w >> 6) & 31u), p.busy = (int)((w >> 11) & 1u);
+        p.waiters = (int)((w >> 12) & 1u), p.hascur = (int)((w >> 13) & 1u), p.curprod = (int)((w >> 14) & 511u);
+        p.qcount = (int)((w >> 23) & 255u);
+        w = s.ld(W_PACK + 3 * i + 2);
+        p.completed = (int)(w & 255u), p.progL = (int)((w >> 8) & 255u);
+    }
+}
+
+template <class S>
+FJSP_HD void store_hot(S& s, const Hot& h) {
+    s.st(W_CTRL, (u32)h.step | ((u32)h.num_orders << 16) | ((u32)h.fault << 22) | ((u32)h.completed_orders << 24));
+    s.st(W_PS, (u32)h.total_packaged | ((u32)h.next_order << 9) | ((u32)h.cur_order << 15) | ((u32)h.prod_idx << 21) |
+                   ((u32)h.cur_tray_count << 25));
+    s.st(W_PSQ, (u32)h.alloc_count | ((u32)h.ready_count << 8) | ((u32)h.ready_order << 16) | ((u32)h.ready_idx << 22));
+    s.st(W_AGV, (u32)h.agv_loc | ((u32)h.agv_moving << 3) | ((u32)h.agv_target << 4) | ((u32)h.agv_arrive << 7) |
+                    ((u32)h.carry << 23));
+    s.st(W_FREE_LO, h.free_lo), s.st(W_FREE_HI, h.free_hi), s.st(W_EPISODE, h.episode);
+    s.st(W_STORAGE, (u32)h.storage.head | ((u32)h.storage.tail << 6) | ((u32)h.storage.len << 12));
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const Mach& m = h.m[i];
+        s.st(W_MACH + 2 * i, (u32)m.busy | ((u32)m.has_cur << 1) | ((u32)m.cur << 2) | ((u32)m.start << 8) |
+                                 ((u32)m.prog << 24) | ((u32)m.q.len << 25));
+        s.st(W_MACH + 2 * i + 1, (u32)m.q.head | ((u32)m.q.tail << 6) | ((u32)m.r.head << 12) | ((u32)m.r.tail << 18) |
+                                     ((u32)m.r.len << 24));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const Pack& p = h.p[i];
+        s.st(W_PACK + 3 * i, (u32)p.q.head | ((u32)p.q.tail << 6) | ((u32)p.q.len << 12) | ((u32)p.f.head << 18) |
+                                 ((u32)p.f.tail << 24));
+        s.st(W_PACK + 3 * i + 1, (u32)p.f.len | ((u32)p.users << 6) | ((u32)p.busy << 11) | ((u32)p.waiters << 12) |
+                                     ((u32)p.hascur << 13) | ((u32)p.curprod << 14) | ((u32)p.qcount << 23));
+        s.st(W_PACK + 3 * i + 2, (u32)p.completed | ((u32)p.progL << 8));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pool + FIFO primitives
+// ---------------------------------------------------------------------------------------------
+FJSP_HD int pool_alloc(Hot& h) {
+    if (h.free_lo) {
+        int b = ctz32(h.free_lo);
+        h.free_lo &= h.free_lo - 1u;
+        return b;
+    }
+    if (h.free_hi) {
+        int b = ctz32(h.free_hi);
+        h.free_hi &= h.free_hi - 1u;
+        return 32 + b;
+    }
+    return -1;
+}
+FJSP_HD void pool_free(Hot& h, int slot) {
+    if (slot < 32) h.free_lo |= 1u << slot;
+    else h.free_hi |= 1u << (slot - 32);
+}
+template <class S>
+FJSP_HD void fifo_push(S& s, Fifo& f, int slot) {
+    if (f.len == 0) {
+        f.head = slot;
+    } else {
+        u32 r = s.ld(W_POOL + f.tail);
+        s.st(W_POOL + f.tail, rec_with_next(r, slot));
+    }
+    f.tail = slot;
+    f.len++;
+}
+template <class S>
+FJSP_HD int fifo_pop(S& s, Fifo& f) {  // caller checks len > 0
+    int slot = f.head;
+    f.head = rec_next(s.ld(W_POOL + slot));
+    f.len--;
+    return slot;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (counter-based; replayable on the host).  Streams:
+//   orders : counter = (global env, episode, order index, 0) -> n = 1+mulhi(r0,9), type = 1+mulhi(r1,3), colour = 1+mulhi(r2,3)
+//   actions: counter = (global env, t_lo, t_hi, 1)           -> a_j = (u16_j * n_j) >> 16
+// ---------------------------------------------------------------------------------------------
+FJSP_HD u32 mulhi_u32(u32 a, u32 b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (u32)(((uint64_t)a * b) >> 32);
+#endif
+}
+FJSP_HD void philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1, u32 out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        u32 hi0 = mulhi_u32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        u32 hi1 = mulhi_u32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        u32 n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0, c1 = lo1, c2 = n2, c3 = lo0;
+        k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
+    }
+    out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
+}
+FJSP_HD u32 philox_order(uint64_t seed, uint64_t genv, u32 episode, int o) {
+    u32 r[4];
+    philox4x32_10((u32)genv, episode, (u32)o, 0u, (u32)seed, (u32)(seed >> 32), r);
+    return make_order(1 + (int)mulhi_u32(r[0], 9u), 1 + (int)mulhi_u32(r[1], 3u), 1 + (int)mulhi_u32(r[2], 3u));
+}
+FJSP_HD void philox_actions(uint64_t seed, uint64_t genv, uint64_t t, int a[8]) {
+    u32 r[4];
+    philox4x32_10((u32)genv, (u32)t, (u32)(t >> 32), 1u, (u32)seed, (u32)(seed >> 32), r);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        u32 hw = (j & 1) ? (r[j >> 1] >> 16) : (r[j >> 1] & 0xffffu);
+        a[j] = (int)((hw * (j == 1 ? 8u : 3u)) >> 16);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reset: FJSPSimulation.reset (FJSPSimulation.py:286-323).  `orders` = FjspOrderRec[32] (n | type<<8 | colour<<16)
+// or nullptr -> Philox.
+// ---------------------------------------------------------------------------------------------
+template <class S>
+FJSP_HD void reset_env(S& s, const Params& P, int num_orders, const FjspOrderRec* orders, uint64_t seed, uint64_t genv,
+                       u32 episode) {
+    (void)P;
+#pragma unroll 8
+    for (int w = 0; w < W_ORDER; w++) s.st(w, 0u);
+    for (int o = 0; o < FJSP_MAX_ORDERS; o++) {
+        u32 ow = 0u;
+        if (o < num_orders) {
+            if (orders) {
+                u32 r = orders[o];
+                ow = make_order((int)(r & 0xffu), (int)((r >> 8) & 0xffu), (int)((r >> 16) & 0xffu));
+            } else {
+                ow = philox_order(seed, genv, episode, o);
+            }
+        }
+        s.st(W_ORDER + o, ow);
+    }
+#pragma unroll 8
+    for (int w = W_POOL; w < W_TOTAL; w++) s.st(w, 0u);
+    s.st(W_CTRL, (u32)num_orders << 16);
+    s.st(W_PS, 63u << 15);  // cur_order = none
+    s.st(W_AGV, (u32)LOC_PICKUP);  // AGVAgent.py:41
+    s.st(W_FREE_LO, 0xffffffffu), s.st(W_FREE_HI, 0xffffffffu);
+    s.st(W_EPISODE, episode);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Observation (layout O, 38 floats) + masks (29 bytes in 8 words).  SURVEY.md §8a-R9.
+// ---------------------------------------------------------------------------------------------
+struct StepOut {
+    float obs[FJSP_OBS_DIM];
+    u32 mask[FJSP_MASK_DIM / 4];
+    float reward[FJSP_NUM_AGENTS];
+    u32 flags;      // terminated | truncated<<8 | fault<<16 | was_reset<<24
+    u32 results[2]; // 8 x u8 action_result bit-fields
+    int32_t info[4];
+};
+
+FJSP_HD void mask_set(u32* mw, int idx, int v) { mw[idx >> 2] |= (u32)(v & 1) << ((idx & 3) * 8); }
+
+template <class S>
+FJSP_HD void observe(S& s, const Params& P, const Hot& h, float* obs, u32* mw) {
+#pragma unroll
+    for (int i = 0; i < FJSP_MASK_DIM / 4; i++) mw[i] = 0u;
+    // ---- pickup station: PickupStationAgent.get_observation (:58-98) / get_action_mask (:100-142)
+    int has_cur_order = h.cur_order != 63;
+    int order_size = 0, remaining = 0, o_type = 0, o_colour = 0;
+    if (has_cur_order) {
+        u32 ow = s.ld(W_ORDER + h.cur_order);
+        order_size = ord_n(ow), remaining = order_size - h.prod_idx;
+        o_type = ord_type(ow), o_colour = ord_colour(ow);
+    }
+    int tcount = h.cur_tray_count;
+    obs[0] = (float)(tcount > 0 ? o_colour : 0);
+    obs[1] = (float)tcount;
+    obs[2] = (float)(tcount > 0 ? o_type : 0);
+    obs[3] = (float)(remaining > 0 ? o_colour : 0);
+    obs[4] = (float)(remaining > 0 ? o_type : 0);
+    obs[5] = (float)order_size;
+    obs[6] = (float)remaining;
+    {
+        int queue_len = h.num_orders - h.next_order;
+        int has_order = has_cur_order || queue_len > 0;
+        int has_tray = tcount > 0 || (P.trays_total - h.alloc_count) > 0;
+        int tray_not_full = tcount < FJSP_TRAY_CAPACITY;
+        int prem = has_cur_order ? (remaining > 0) : (queue_len > 0);
+        mask_set(mw, 0, 1);
+        mask_set(mw, 1, has_order && has_tray && tray_not_full && prem);
+        mask_set(mw, 2, tcount > 0);
+    }
+    // ---- AGV: AGVAgent.get_observation (:53-76) / get_action_mask (:79-178)
+    int carrying = h.carry != 0;
+    int c_count = 0, c_type = 0, c_proc = 0;
+    if (carrying) {
+        u32 r = s.ld(W_POOL + h.carry - 1);
+        c_count = rec_count(r), c_proc = rec_processed(r);
+        c_type = ord_type(s.ld(W_ORDER + rec_order(r)));
+    }
+    obs[7] = (float)h.m[1].busy;
+    obs[8] = (float)h.m[1].r.len;
+    obs[9] = (float)carrying;
+    obs[10] = (float)h.ready_count;
+    obs[11] = (float)P.pos_row[h.agv_loc];
+    obs[12] = (float)P.pos_col[h.agv_loc];
+    obs[13] = (float)h.m[0].busy;
+    obs[14] = (float)h.m[0].r.len;
+    obs[15] = (float)h.storage.len;
+    obs[16] = (float)carrying;                 // a carried tray is never packaged (delivered trays vanish)
+    obs[17] = (float)(carrying && !c_proc);
+    obs[18] = (float)c_count;
+    obs[19] = (float)c_type;
+    mask_set(mw, 3, 1);
+    if (!h.agv_moving) {
+        int loc = h.agv_loc;
+        mask_set(mw, 4, loc != LOC_PICKUP);
+        mask_set(mw, 5, loc != LOC_SMALL);
+        mask_set(mw, 6, loc != LOC_BIG);
+        mask_set(mw, 7, loc != LOC_STORAGE);
+        mask_set(mw, 8, loc != LOC_PACKAGING);
+        if (!carrying) {
+            int avail = loc == LOC_PICKUP ? h.ready_count
+                        : loc == LOC_SMALL ? h.m[0].r.len
+                        : loc == LOC_BIG ? h.m[1].r.len
+                        : loc == LOC_STORAGE ? h.storage.len : 0;
+            mask_set(mw, 9, avail > 0);
+        } else {
+            int ok = 0;
+            if (loc == LOC_SMALL) ok = !c_proc && (c_type == TYPE_SMALL || c_type == TYPE_MEDIUM);
+            else if (loc == LOC_BIG) ok = !c_proc && (c_type == TYPE_BIG || c_type == TYPE_MEDIUM);
+            else if (loc == LOC_PACKAGING) ok = c_proc;
+            else if (loc == LOC_STORAGE) ok = 1;
+            mask_set(mw, 10, ok);  // PICKUP: only an empty tray, never the case
+        }
+    }
+    // ---- machines: MachineAgent.get_observation (:62-70) / get_action_mask (:72-97)
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const Mach& m = h.m[i];
+        obs[20 + 3 * i] = (float)m.busy;
+        obs[21 + 3 * i] = m.prog ? 1.0f : 0.0f;
+        obs[22 + 3 * i] = (float)m.q.len;
+        mask_set(mw, 11 + 3 * i, 1);
+        mask_set(mw, 12 + 3 * i, m.q.len > 0 && !m.busy);
+        mask_set(mw, 13 + 3 * i, !m.busy && m.has_cur);
+    }
+    // ---- packaging: PackagingAgent.get_observation (:54-62) / get_action_mask (:64-89)
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const Pack& p = h.p[i];
+        obs[26 + 3 * i] = (float)p.busy;
+        obs[27 + 3 * i] = P.progress_tab[p.progL];
+        obs[28 + 3 * i] = (float)(int)(int8_t)p.qcount;  // dtype=np.int8 (PackagingAgent.py:59)
+        mask_set(mw, 17 + 3 * i, 1);
+        mask_set(mw, 18 + 3 * i, p.qcount > 0 && !p.busy && p.users < P.pack_capacity);
+        mask_set(mw, 19 + 3 * i, !p.busy && p.hascur);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Packaging helpers
+// ---------------------------------------------------------------------------------------------
+// Move the first `g` queued products of station p into flight (grant events, PackagingAgent.py:138-141).
+template <class S>
+FJSP_HD void pack_grant(S& s, Hot& h, Pack& p, int g, int stamp) {
+    while (g > 0 && p.q.len > 0) {
+        int slot = p.q.head;
+        u32 r = s.ld(W_POOL + slot);
+        int cnt = rec_count(r);
+        int fslot;
+        int last_idx;
+        if (cnt <= g) {
+            fifo_pop(s, p.q);
+            fslot = slot;
+            last_idx = rec_first(r) + cnt - 1;
+            g -= cnt, p.qcount -= cnt;
+        } else {  // capacity split: the first g products start, the rest keeps waiting (R-PKG-cap-a)
+            fslot = pool_alloc(h);
+            if (fslot < 0) {
+                h.fault = FJSP_FAULT_POOL_EXHAUSTED;
+                return;
+            }
+            u32 started = make_rec(rec_order(r), rec_first(r), g, 1);
+            u32 rest = (r & ~((15u << 5) | (7u << 9))) | ((u32)(rec_first(r) + g) << 5) | ((u32)(cnt - g) << 9);
+            s.st(W_POOL + slot, rest);
+            r = started;
+            last_idx = rec_first(r) + g - 1;
+            p.qcount -= g;
+            g = 0;
+        }
+        s.st(W_POOL + fslot, rec_with_stamp(r, stamp));
+        fifo_push(s, p.f, fslot);
+        p.busy = 1, p.hascur = 1;
+        p.curprod = rec_order(r) | (last_idx << 5);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One environment step.  Returns through `out`.  `actions` = 8 bytes.
+// ---------------------------------------------------------------------------------------------
+template <class S>
+FJSP_HD void step_env(S& s, const Params& P, const int a[8], StepOut& out) {
+    Hot h;
+    load_hot(s, h);
+    const int k = h.step;
+    const int orders_before = h.completed_orders, products_before = h.total_packaged;
+    double local[8];
+    u32 res[8];
+
+    // ===== action phase, agents in dict order (FJSPSimulation.py:172-174, :76-82) =====
+    // ---- R1 pickup station (PickupStationAgent.py:146-232)
+    {
+        int loaded = 0, tray_done = 0, idle_orders = 0, success = 0;
+        if (a[0] == 0) {
+            idle_orders = (h.num_orders - h.next_order) > 0 || h.cur_order != 63;
+            success = 1;
+        } else if (a[0] == 1) {
+            int ok = 1;
+            if (h.cur_order == 63) {
+                if (h.next_order < h.num_orders) h.cur_order = h.next_order++, h.prod_idx = 0;
+                else ok = 0;
+            }
+            if (ok && h.cur_tray_count == 0) {
+                if (h.alloc_count < P.trays_total) h.alloc_count++;  // trays_at_station.pop(0)
+                else ok = 0;
+            }
+            if (ok) {
+                u32 ow = s.ld(W_ORDER + h.cur_order);
+                h.cur_tray_count++, h.prod_idx++;
+                loaded = 1, success = 1;
+                if (h.prod_idx >= ord_n(ow)) {          // order exhausted: tray released (:201-208)
+                    h.cur_order = 63, h.prod_idx = 0;
+                    h.cur_tray_count = 0, h.ready_count++;
+                    tray_done = 1;
+                } else if (h.cur_tray_count >= FJSP_TRAY_CAPACITY) {  // tray full (:211-216)
+                    s.st(W_ORDER + h.cur_order, ow | (1u << (8 + h.prod_idx - 1)));  // cut after the last loaded product
+                    h.cur_tray_count = 0, h.ready_count++;
+                    tray_done = 1;
+                }
+            }
+        } else if (a[0] == 2) {
+            if (h.cur_tray_count > 0) {                 // SIGNAL (:226-230): the order is not exhausted here
+                u32 ow = s.ld(W_ORDER + h.cur_order);
+                s.st(W_ORDER + h.cur_order, ow | (1u << (8 + h.prod_idx - 1)));
+                h.cur_tray_count = 0, h.ready_count++;
+                success = 1;
+            }
+        }
+        res[0] = (success ? FJSP_RES_SUCCESS : 0) | (loaded ? FJSP_RES_PS_LOADED : 0) | (tray_done ? FJSP_RES_PS_TRAY_DONE : 0) |
+                 (idle_orders ? FJSP_RES_PS_IDLE_ORDERS : 0);
+        double r = 0.0;  // RewardModel.py:53-60
+        if (loaded) r += 1.0;
+        if (tray_done) r += 5.0;
+        if (a[0] == 0 && idle_orders) r += -1.0;
+        local[0] = r;
+    }
+    // ---- R2-R4 AGV (AGVAgent.py:180-368)
+    {
+        int invalid = 0, moved = 0, pick = 0, drop = 0, to_pack = 0, success = 0;
+        const int act = a[1];
+        if (h.agv_moving) {
+            invalid = 1;
+        } else if (act == 0) {
+            success = 1;
+        } else if (act <= 5) {
+            const int tl = act == 1 ? LOC_PICKUP : act == 2 ? LOC_SMALL : act == 3 ? LOC_BIG : act == 4 ? LOC_STORAGE : LOC_PACKAGING;
+            success = 1;
+            if (P.dist[h.agv_loc][tl] != 0) {
+                moved = 1;
+                h.agv_moving = 1, h.agv_target = tl;        // resolved in the run phase below
+                h.agv_arrive = k + P.delay[h.agv_loc][tl];
+            }
+        } else if (act == 6) {
+            const int loc = h.agv_loc;
+            if (h.carry != 0 || loc == LOC_PACKAGING) {
+                invalid = 1;
+            } else if (loc == LOC_PICKUP) {
+                if (h.ready_count > 0) {
+                    int slot = pool_alloc(h);
+                    if (slot < 0) {
+                        h.fault = FJSP_FAULT_POOL_EXHAUSTED, invalid = 1;
+                    } else {
+                        // head ready tray = products [ready_idx, next cut] of order ready_order
+                        u32 ow = s.ld(W_ORDER + h.ready_order);
+                        u32 cuts = ord_cut(ow) >> h.ready_idx;
+                        int cnt = cuts ? ctz32(cuts) + 1 : ord_n(ow) - h.ready_idx;
+                        s.st(W_POOL + slot, make_rec(h.ready_order, h.ready_idx, cnt, 0));
+                        h.ready_idx += cnt;
+                        if (h.ready_idx >= ord_n(ow)) h.ready_order++, h.ready_idx = 0;
+                        h.ready_count--;
+                        h.carry = slot + 1, pick = 1;
+                    }
+                } else invalid = 1;
+            } else {
+                Fifo& f = loc == LOC_SMALL ? h.m[0].r : loc == LOC_BIG ? h.m[1].r : h.storage;
+                if (f.len > 0) h.carry = fifo_pop(s, f) + 1, pick = 1;
+                else invalid = 1;
+            }
+            success = pick;
+        } else if (act == 7) {
+            const int loc = h.agv_loc;
+            if (h.carry == 0 || loc == LOC_PICKUP) {
+                invalid = 1;  // empty-handed, or a non-empty tray at PICKUP (:310-317)
+            } else {
+                const int slot = h.carry - 1;
+                u32 r = s.ld(W_POOL + slot);
+                u32 ow = s.ld(W_ORDER + rec_order(r));
+                const int ty = ord_type(ow), proc = rec_processed(r);
+                if (loc == LOC_SMALL || loc == LOC_BIG) {
+                    int compat = loc == LOC_SMALL ? (ty == TYPE_SMALL || ty == TYPE_MEDIUM) : (ty == TYPE_BIG || ty == TYPE_MEDIUM);
+                    if (!proc && compat) {
+                        if (loc == LOC_SMALL) fifo_push(s, h.m[0].q, slot);
+                        else fifo_push(s, h.m[1].q, slot);
+                        drop = 1;
+                    } else invalid = 1;
+                } else if (loc == LOC_STORAGE) {
+                    if (h.storage.len < P.storage_capacity) fifo_push(s, h.storage, slot);
+                    else s.st(W_POOL + slot, r | (1u << 27));  // Storage.add_tray False ignored: tray vanishes (Storage.py:18-22)
+                    drop = 1;
+                } else {  // PACKAGING (:352-360) -> add_tray_to_packaging (FJSPSimulation.py:402-430)
+                    if (proc) {
+                        const int col = ord_colour(ow), cnt = rec_count(r);
+                        int st = -1;
+                        if (col == COL_BLUE) st = h.p[0].users < P.pack_capacity ? 0 : (h.p[1].users < P.pack_capacity ? 1 : -1);
+                        else if (col == COL_RED) st = h.p[2].users < P.pack_capacity ? 2 : -1;
+                        else st = h.p[3].users < P.pack_capacity ? 3 : -1;
+                        if (st == 0) fifo_push(s, h.p[0].q, slot), h.p[0].qcount += cnt;
+                        else if (st == 1) fifo_push(s, h.p[1].q, slot), h.p[1].qcount += cnt;
+                        else if (st == 2) fifo_push(s, h.p[2].q, slot), h.p[2].qcount += cnt;
+                        else if (st == 3) fifo_push(s, h.p[3].q, slot), h.p[3].qcount += cnt;
+                        else s.st(W_POOL + slot, r | (1u << 27));  // no station with capacity: products dropped (:426-427)
+                        drop = 1, to_pack = 1;
+                    } else invalid = 1;
+                }
+                if (drop) h.carry = 0, success = 1;
+            }
+        } else {
+            invalid = 1;
+        }
+        res[1] = (success ? FJSP_RES_SUCCESS : 0) | (invalid ? FJSP_RES_AGV_INVALID : 0) | (moved ? FJSP_RES_AGV_MOVED : 0) |
+                 (pick ? FJSP_RES_AGV_PICKUP : 0) | (drop ? FJSP_RES_AGV_DROP : 0) | (to_pack ? FJSP_RES_AGV_TO_PACK : 0);
+        double r = 0.0;  // RewardModel.py:62-77
+        if (pick) r += 2.0;
+        if (drop) r += 2.0;
+        if (to_pack) r += 10.0;
+        if (moved) r += -0.1;
+        if (invalid) r += -5.0;
+        local[1] = r;
+    }
+    // ---- R5 machines (MachineAgent.py:99-169).  START takes effect in this step's run phase, but no later
+    //      agent reads machine state inside the action phase, so it is applied here.
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        Mach& m = h.m[i];
+        const int act = a[2 + i];
+        int started = 0, completed = 0, idle_q = 0, success = 0;
+        if (act == 0) {
+            idle_q = m.q.len > 0 && !m.busy;
+            success = 1;
+        } else if (act == 1) {
+            if (m.q.len > 0 && !m.busy) {
+                int slot = fifo_pop(s, m.q);
+                if (m.has_cur) {  // unsignalled finished tray is overwritten and lost (:160)
+                    u32 old = s.ld(W_POOL + m.cur);
+                    s.st(W_POOL + m.cur, old | (1u << 27));
+                }
+                m.busy = 1, m.has_cur = 1, m.cur = slot, m.start = k;
+                started = 1, success = 1;
+            }
+        } else if (act == 2) {
+            if (!m.busy && m.has_cur) {
+                fifo_push(s, m.r, m.cur);
+                m.has_cur = 0, m.cur = 0;
+                completed = 1, success = 1;
+            }
+        }
+        res[2 + i] = (success ? FJSP_RES_SUCCESS : 0) | (started ? FJSP_RES_M_STARTED : 0) | (completed ? FJSP_RES_M_COMPLETED : 0) |
+                     (idle_q ? FJSP_RES_M_IDLE_QUEUE : 0);
+        double r = 0.0;  // RewardModel.py:79-86
+        if (started) r += 1.0;
+        if (completed) r += 5.0;
+        if (act == 0 && idle_q) r += -2.0;
+        local[2 + i] = r;
+    }
+    // ---- R6 packaging (PackagingAgent.py:91-125)
+    int pk_start[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        Pack& p = h.p[i];
+        const int act = a[4 + i];
+        int started = 0, completed = 0, idle_q = 0, success = 0;
+        pk_start[i] = 0;
+        if (act == 0) {
+            idle_q = p.qcount > 0 && !p.busy;
+            success = 1;
+        } else if (act == 1) {
+            if (p.qcount > 0) {  // no busy/capacity check (:111-118)
+                started = 1, success = 1;
+                p.progL = p.qcount;
+                if (p.waiters) h.fault = FJSP_FAULT_PKG_RESTART_WITH_WAITERS;  // reference raises (R-PKG-cap-b)
+                else pk_start[i] = p.qcount;
+            }
+        } else if (act == 2) {
+            if (!p.busy && p.hascur) completed = 1;  // success stays False (:120-123)
+        }
+        res[4 + i] = (success ? FJSP_RES_SUCCESS : 0) | (started ? FJSP_RES_M_STARTED : 0) | (completed ? FJSP_RES_M_COMPLETED : 0) |
+                     (idle_q ? FJSP_RES_M_IDLE_QUEUE : 0);
+        double r = 0.0;  // RewardModel.py:88-95
+        if (started) r += 2.0;
+        if (completed) r += 20.0;
+        if (act == 0 && idle_q) r += -1.0;
+        local[4 + i] = r;
+    }
+
+    // ===== run phase: env.run(until = now + step_size) (FJSPSimulation.py:183-184), rule R0 =====
+    // AGV arrival (AGVAgent.py:387-396)
+    if (h.agv_moving && h.agv_arrive == k) h.agv_loc = h.agv_target, h.agv_moving = 0;
+    // machines: product i (1-based) is flagged in step start + P*i; the tray finishes at start + P*n
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        Mach& m = h.m[i];
+        if (m.busy) {
+            u32 r = s.ld(W_POOL + m.cur);
+            const int per = i == 0 ? P.small_steps : P.big_steps;
+            if (k == m.start + per * rec_count(r)) {
+                s.st(W_POOL + m.cur, r | (1u << 12));
+                m.busy = 0, m.prog = 1;
+            }
+        }
+    }
+    // packaging stations, event order inside the run:
+    //   URGENT Initialize of this step's requests (grant while users < capacity, users counted BEFORE finishes)
+    //   -> NORMAL timeouts due at the boundary (finish, release) -> grants -> releases grant waiters FIFO.
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        Pack& p = h.p[i];
+        int g = 0;
+        if (pk_start[i] > 0) {
+            int room = P.pack_capacity - p.users;
+            g = pk_start[i] < room ? pk_start[i] : room;
+            if (g < pk_start[i]) p.waiters = 1;
+            p.users += g;
+        }
+        int released = 0;
+        while (p.f.len > 0) {
+            int slot = p.f.head;
+            u32 r = s.ld(W_POOL + slot);
+            if (rec_stamp(r) != (k & 255)) break;
+            fifo_pop(s, p.f);
+            pool_free(h, slot);
+            const int o = rec_order(r), cnt = rec_count(r);
+            u32 ow = s.ld(W_ORDER + o);
+            ow |= (((1u << cnt) - 1u) << rec_first(r)) << 16;   // is_packaged (:143)
+            s.st(W_ORDER + o, ow);
+            p.completed += cnt, h.total_packaged += cnt, p.users -= cnt, released += cnt;
+            p.busy = 0;
+            if (ord_packaged(ow) == (1u << ord_n(ow)) - 1u) {    // _check_order_completions (FJSPSimulation.py:245-258)
+                h.completed_orders++;
+                u32 cw = s.ld(W_CSTEP + (o >> 2));
+                s.st(W_CSTEP + (o >> 2), cw | ((u32)((k + 1) & 255) << ((o & 3) * 8)));
+            }
+        }
+        const int stamp = (k + P.pack_steps) & 255;
+        if (g > 0) pack_grant(s, h, p, g, stamp);
+        if (p.waiters && released > 0) {
+            int wgrant = released < p.qcount ? released : p.qcount;
+            int room = P.pack_capacity - p.users;
+            if (wgrant > room) wgrant = room;
+            p.users += wgrant;
+            pack_grant(s, h, p, wgrant, stamp);
+            if (p.qcount == 0) p.waiters = 0;
+        }
+    }
+
+    // ===== rewards (FJSPSimulation.py:190-209, RewardModel.py:34-44,99-110), double like the reference =====
+    {
+        double g = 100.0 * (double)(h.completed_orders - orders_before);
+        g += 10.0 * (double)(h.total_packaged - products_before);
+        g += P.time_reward;
+#pragma unroll
+        for (int i = 0; i < 8; i++) out.reward[i] = (float)(g / 8.0 + local[i]);
+    }
+    // ===== termination / truncation (FJSPSimulation.py:216-224), pre-increment step =====
+    const int all_done = h.completed_orders == h.num_orders && h.num_orders > 0 && h.next_order == h.num_orders;
+    const int truncated = k >= P.max_episode_steps;
+    out.flags = (u32)all_done | ((u32)truncated << 8) | ((u32)h.fault << 16);
+    out.results[0] = res[0] | (res[1] << 8) | (res[2] << 16) | (res[3] << 24);
+    out.results[1] = res[4] | (res[5] << 8) | (res[6] << 16) | (res[7] << 24);
+    h.step = k + 1;
+    out.info[0] = h.step, out.info[1] = h.completed_orders, out.info[2] = h.total_packaged, out.info[3] = 0;
+    observe(s, P, h, out.obs, out.mask);
+    store_hot(s, h);
+}
+
+// observation of the current state without stepping (reset path)
+template <class S>
+FJSP_HD void observe_env(S& s, const Params& P, float* obs, u32* mw) {
+    Hot h;
+    load_hot(s, h);
+    observe(s, P, h, obs, mw);
+}
+
+}  // namespace fjsp
+#endif  // FJSP_CORE_H

@@ -1,0 +1,95 @@
+"""ctypes binding of the TEST-ONLY host build of the device step function (see harness.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from oracle.canon import CANON_DT
+from oracle.fjsp_oracle import FjspConfig, default_config, order_rec
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libfjsp_hostharness.so")
+_CSRC = os.path.join(_HERE, "..", "..", "multi_agent_rl_for_fjsp_b200", "csrc")
+
+
+def build():
+    srcs = [os.path.join(_HERE, "harness.cpp"), os.path.join(_CSRC, "fjsp_core.h"), os.path.join(_CSRC, "fjsp_host.h"),
+            os.path.join(_HERE, "..", "..", "include", "fjsp_b200.h")]
+    if (not os.path.exists(_SO)) or any(os.path.getmtime(p) > os.path.getmtime(_SO) for p in srcs):
+        os.makedirs(os.path.dirname(_SO), exist_ok=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas", "-o", _SO, srcs[0]], check=True)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        L.hh_create.restype = C.c_void_p
+        L.hh_create.argtypes = [C.c_void_p]
+        L.hh_check_config.restype = C.c_char_p
+        L.hh_check_config.argtypes = [C.c_void_p]
+        L.hh_destroy.argtypes = [C.c_void_p]
+        L.hh_observe.argtypes = [C.c_void_p] * 3
+        L.hh_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32]
+        L.hh_step.argtypes = [C.c_void_p] * 8
+        L.hh_export.argtypes = [C.c_void_p, C.c_void_p]
+        L.hh_words.argtypes = [C.c_void_p, C.c_void_p]
+        L.hh_philox_actions.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.hh_philox.argtypes = [C.c_void_p] * 3
+        _lib = L
+    return _lib
+
+
+class HostEnv:
+    def __init__(self, cfg: FjspConfig | None = None):
+        self._L = lib()
+        self.cfg = cfg if cfg is not None else default_config()
+        self._h = self._L.hh_create(C.addressof(self.cfg))
+        if not self._h:
+            raise ValueError(self._L.hh_check_config(C.addressof(self.cfg)).decode())
+        self.obs = np.zeros(38, np.float32)
+        self.masks = np.zeros(32, np.int8)
+        self.rewards = np.zeros(8, np.float32)
+        self.flags = np.zeros(4, np.uint8)
+        self.results = np.zeros(8, np.uint8)
+        self.infos = np.zeros(4, np.int32)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.hh_destroy(h)
+
+    def reset(self, orders=None, num_orders=None, seed=0, genv=0, episode=0):
+        if orders is not None:
+            arr = np.asarray(orders)
+            if arr.ndim == 2:
+                arr = np.array([order_rec(*o) for o in arr], dtype=np.uint32)
+            arr = np.ascontiguousarray(arr, dtype=np.uint32)
+            buf = np.zeros(32, np.uint32)
+            buf[:arr.shape[0]] = arr
+            self._L.hh_reset(self._h, buf.ctypes.data, int(arr.shape[0]), 0, 0, 0)
+        else:
+            self._L.hh_reset(self._h, None, int(num_orders), seed, genv, episode)
+        self._L.hh_observe(self._h, self.obs.ctypes.data, self.masks.ctypes.data)
+        return self.obs.copy(), self.masks.copy()
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.uint8)
+        self._L.hh_step(self._h, a.ctypes.data, self.obs.ctypes.data, self.masks.ctypes.data, self.rewards.ctypes.data,
+                        self.flags.ctypes.data, self.results.ctypes.data, self.infos.ctypes.data)
+        return self.obs.copy(), self.masks.copy(), self.rewards.copy(), self.flags.copy()
+
+    def export(self):
+        s = np.zeros((), dtype=CANON_DT)
+        self._L.hh_export(self._h, s.ctypes.data)
+        return s
+
+    def words(self):
+        w = np.zeros(128, np.uint32)
+        self._L.hh_words(self._h, w.ctypes.data)
+        return w

@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — env agent-steps/sec of the batched FJSP environment step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs E]
+
+Workload (config.workload): BASELINE.json configs[3] — default layout (constants.py), 2^20 envs PER GPU,
+30 Philox orders per env, uniform-random actions (Philox), auto-reset; one "step" = one lockstep env step of
+every env = ONE launch of fjsp_step_kernel.  1 env-step = 8 agent-steps.  Weak scaling: per-GPU work is fixed,
+ranks own disjoint global env ranges, there is no collective in the step.
+
+value      device-timed (CUDA events on the launching stream), inputs resident in HBM: the K action buffers are
+           generated before the timed region; every step reads a fresh 8 MiB action buffer and the 512 MiB state,
+           so the working set exceeds the 126 MB L2 without a flush.
+e2e        the same metric through the host-buffer C-ABI call fjsp_step_host: pinned host actions in, pinned host
+           obs/masks/rewards/flags out, H2D + D2H copies inside the timed region.
+roofline   algorithmic bytes per launch = envs x (8 + 152 + 32 + 32 + 4 + 2 x 512) = envs x 1252 B,
+           divided by the mean launch duration, against MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline / --impl reference
+           the reference is pure Python + SimPy and cannot travel to the GPU box, so the CPU arm is the C port of it
+           (oracle/fjsp_oracle.c, kind "port") on all host threads, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "env_agent_steps_per_sec"
+UNIT = "agent-steps/s"
+BYTES_IO = 8 + 152 + 32 + 32 + 4
+STATE_BYTES = 512
+BYTES_PER_ENV_STEP = BYTES_IO + 2 * STATE_BYTES  # 1252
+SEED = 20261018
+NUM_ORDERS = 30
+
+
+def workload_name(envs):
+    return ("configs[3]: default layout, %d envs per GPU (2^20 default), 30 Philox orders/env, Philox uniform-random "
+            "actions, autoreset; 1 step = 1 lockstep env step of all envs" % envs)
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                clk, mxc = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            mx = mxc
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than one sample: use everything we saw
+            for ts, line in self.rows:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1]))
+                except Exception:
+                    pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_port_rate(sample_envs, steps_per_call, calls, threads, warm_calls=1):
+    """Times the C port of the reference (oracle/fjsp_oracle.c) on `threads` host threads.  Returns
+    (agent-steps/s, seconds, env-steps)."""
+    from oracle.fjsp_oracle import OracleBatch
+
+    b = OracleBatch(sample_envs, SEED, NUM_ORDERS)
+    for _ in range(warm_calls):
+        b.rollout(steps_per_call, nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(calls):
+        b.rollout(steps_per_call, nthreads=threads)
+    dt = time.perf_counter() - t0
+    env_steps = sample_envs * steps_per_call * calls
+    return env_steps * 8 / dt, dt, env_steps
+
+
+def cpu_baseline_block(target_seconds=12.0):
+    threads = os.cpu_count() or 1
+    sample_envs = 8192
+    rate, dt, _ = cpu_port_rate(sample_envs, 20, 1, threads, warm_calls=1)  # calibrate
+    steps = max(20, min(2000, int(target_seconds * rate / 8 / sample_envs)))
+    rate, dt, env_steps = cpu_port_rate(sample_envs, steps, 1, threads, warm_calls=0)
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d envs x %d lockstep steps (%.1f s) of the same workload, C port of the reference "
+                      "(oracle/fjsp_oracle.c), %d pthreads" % (sample_envs, steps, dt, threads)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is Python+SimPy and does not
+    exist on the GPU box, so this is the C port on all host threads; each step = one lockstep step of a bounded
+    sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    # one reference "step" = INNER consecutive steps of each of sample_envs envs, env-major, which is the CPU's best
+    # mode (an env's 82 KB object graph stays in cache); agent-steps are counted the same way on both arms.
+    sample_envs, inner = 4096, 64
+    from oracle.fjsp_oracle import OracleBatch
+
+    b = OracleBatch(sample_envs, SEED, NUM_ORDERS)
+    for _ in range(args.warmup):
+        b.rollout(inner, nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        b.rollout(inner, nthreads=threads)
+    dt = time.perf_counter() - t0
+    value = sample_envs * inner * 8 * args.steps / dt
+    sample = ("per step: %d envs x %d consecutive env steps (bounded sample of the 2^20-env workload, env-major), "
+              "C port oracle/fjsp_oracle.c, %d pthreads" % (sample_envs, inner, threads))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.envs), "sample_envs": sample_envs, "inner_steps": inner},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the environment step exists only as sm_100a kernels (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    E, K, W = args.envs, args.steps, args.warmup
+    env = BatchedFJSPEnv(E, device=dev, first_env=rank * E, seed=SEED, num_orders=NUM_ORDERS, autoreset=True)
+    env.reset()
+    # inputs resident in HBM: one action buffer per step, generated by the Philox policy stand-in
+    nbuf = min(W + K, args.max_action_buffers)
+    acts = torch.empty((nbuf, E, 8), dtype=torch.uint8, device=dev)
+    for t in range(nbuf):
+        env.random_actions(t, out=acts[t])
+    torch.cuda.synchronize()
+
+    for t in range(W):
+        env.step(acts[t % nbuf])
+    launches0 = env.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    wall0 = time.time()
+    ev0.record()
+    for t in range(W, W + K):
+        env.step(acts[t % nbuf])
+    ev1.record()
+    barrier()
+    wall1 = time.time()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = env.launch_count - launches0
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    ms_per_step = ms / K
+    value = world * E * 8 * K / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer entry point
+    Ke = max(3, min(K, args.e2e_steps))
+    host_actions = [acts[i % nbuf].cpu().numpy() for i in range(min(4, nbuf))]
+    for i in range(2):
+        env.step_host(host_actions[i % len(host_actions)])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        env.step_host(host_actions[i % len(host_actions)])
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * E * 8 * Ke / e2e_s
+
+    # ---- small-batch point (BASELINE configs[1]: 4096 envs, launch-latency bound), device-timed, reported as extra
+    small = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        es = BatchedFJSPEnv(4096, device=dev, seed=SEED, autoreset=True)
+        es.reset()
+        sa = [es.random_actions(t, out=torch.empty((4096, 8), dtype=torch.uint8, device=dev)) for t in range(64)]
+        for t in range(50):
+            es.step(sa[t % 64])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for t in range(2000):
+            es.step(sa[t % 64])
+        e1.record()
+        torch.cuda.synchronize()
+        sms = e0.elapsed_time(e1)
+        st = es.rollout_random(50)
+        torch.cuda.synchronize()
+        e0.record()
+        es.rollout_random(2000)
+        e1.record()
+        torch.cuda.synchronize()
+        rms = e0.elapsed_time(e1)
+        small = {"envs": 4096, "step_launch_us": sms / 2000 * 1e3, "agent_steps_per_s_stepwise": 4096 * 8 * 2000 / (sms * 1e-3),
+                 "agent_steps_per_s_rollout_2000_steps_per_launch": 4096 * 8 * 2000 / (rms * 1e-3),
+                 "note": "configs[1]; L2-resident, launch-latency bound; not the headline"}
+        # K-steps-per-launch variant on the full batch (state stays on-chip between steps; not the headline)
+        e0.record()
+        env.rollout_random(32)
+        e1.record()
+        torch.cuda.synchronize()
+        small["rollout32_full_batch_agent_steps_per_s"] = E * 8 * 32 / (e0.elapsed_time(e1) * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = E * BYTES_PER_ENV_STEP / (ms_per_step * 1e-3) / 1e9  # GB/s per GPU
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload_name(E), "envs_per_gpu": E, "num_orders": NUM_ORDERS,
+                       "state_bytes_per_env": STATE_BYTES, "parallelism": "env-sharded x%d, no collective in the step" % world,
+                       "l2": "no flush: each step streams the 512 MiB state and a fresh 8 MiB action buffer (> 126 MB L2)",
+                       "action_buffers": nbuf},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": args.ncu_traffic_bytes, "peak_source": peak_src, "kernel": "fjsp_step_kernel",
+                         "algorithmic_bytes_per_launch": E * BYTES_PER_ENV_STEP},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 8, "d2h_bytes_per_step": E * (152 + 32 + 32 + 4),
+                    "steps": Ke, "api": "fjsp_step_host (pinned host buffers)"},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_block()
+        if small:
+            line["extra"] = small
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--max-action-buffers", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--ncu-traffic-bytes", type=float, default=None,
+                    help="dram bytes read+written per launch of fjsp_step_kernel from the committed ncu capture")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

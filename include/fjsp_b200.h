@@ -158,6 +158,12 @@ int fjsp_export_state(FjspHandle* h, int64_t env, FjspCanonState* out);
 /* Raw packed words of one env (128 x u32) copied to the host (synchronises). */
 int fjsp_export_packed(FjspHandle* h, int64_t env, uint32_t* out_words);
 
+/* Snapshot / restore of the whole packed state (num_tiles * 32 KB, see fjsp_state_total_bytes) to / from a
+ * caller-owned DEVICE buffer: env checkpointing, and bit-for-bit comparison of two handles. */
+size_t fjsp_state_total_bytes(const FjspHandle* h);
+int fjsp_state_save(FjspHandle* h, void* dst_device, size_t bytes, void* stream);
+int fjsp_state_load(FjspHandle* h, const void* src_device, size_t bytes, void* stream);
+
 /* Number of kernels this library has launched since the handle was created. */
 int64_t fjsp_launch_count(const FjspHandle* h);
 

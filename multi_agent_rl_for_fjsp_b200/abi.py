@@ -1,0 +1,166 @@
+"""ctypes binding of the C ABI declared in include/fjsp_b200.h (libfjsp_b200.so).
+
+The library is built in-tree by ``build()`` (``nvcc -gencode arch=compute_100a,code=sm_100a``) and is the
+only implementation of the step: if it is missing, ``lib()`` raises — there is no fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_REPO = os.path.dirname(_PKG)
+SO_PATH = os.path.join(_PKG, "lib", "libfjsp_b200.so")
+SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("fjsp_api.cu", "fjsp_kernels.cuh", "fjsp_core.h", "fjsp_host.h")]
+HEADER = os.path.join(_REPO, "include", "fjsp_b200.h")
+
+NUM_AGENTS, OBS_DIM, MASK_DIM, FLAG_DIM, INFO_DIM, MAX_ORDERS = 8, 38, 32, 4, 4, 32
+STATE_WORDS, TILE_ENVS = 128, 64
+CANON_MAXQ, CANON_PS_READY, CANON_MAXPQ = 64, 256, 256
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+class FjspConfig(C.Structure):
+    """Mirror of ``FjspConfig`` (constants.py:5-32 of the reference)."""
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("pos", (C.c_int32 * 2) * 5),
+        ("grid_rows", C.c_int32), ("grid_cols", C.c_int32),
+        ("proc_small", C.c_int32), ("proc_big", C.c_int32), ("proc_pack", C.c_int32),
+        ("step_size", C.c_int32), ("agv_speed", C.c_int32), ("max_episode_steps", C.c_int32),
+        ("storage_capacity", C.c_int32), ("pack_capacity", C.c_int32),
+        ("tray_capacity", C.c_int32), ("num_trays", C.c_int32),
+    ]
+
+
+_MACHINE_DT = np.dtype([
+    ("is_busy", "<i4"), ("current_tray", "<i4"), ("progress_done", "<i4"),
+    ("queue_n", "<i4"), ("queue", "<i4", (CANON_MAXQ,)), ("ready_n", "<i4"), ("ready", "<i4", (CANON_MAXQ,))])
+_PACK_DT = np.dtype([
+    ("is_busy", "<i4"), ("current_product", "<i4"), ("progress_L", "<i4"), ("products_completed", "<i4"),
+    ("users", "<i4"), ("queue_n", "<i4"), ("queue", "<i4", (CANON_MAXPQ,))])
+CANON_DT = np.dtype([
+    ("current_step", "<i4"), ("num_orders", "<i4"), ("fault", "<i4"),
+    ("agv_row", "<i4"), ("agv_col", "<i4"), ("agv_carry", "<i4"), ("agv_is_moving", "<i4"),
+    ("ps_order_queue_len", "<i4"), ("ps_current_order", "<i4"), ("ps_product_idx", "<i4"),
+    ("ps_current_tray", "<i4"), ("ps_trays_at_station", "<i4"),
+    ("ps_ready_n", "<i4"), ("ps_ready", "<i4", (CANON_PS_READY,)),
+    ("machine", _MACHINE_DT, (2,)), ("storage_n", "<i4"), ("storage", "<i4", (CANON_MAXQ,)),
+    ("pack", _PACK_DT, (4,)),
+    ("processed_mask", "<i4", (MAX_ORDERS,)), ("packaged_mask", "<i4", (MAX_ORDERS,)),
+    ("order_complete", "<i4", (MAX_ORDERS,)), ("order_completion_step", "<i4", (MAX_ORDERS,)),
+    ("total_products_packaged", "<i4"), ("completed_orders", "<i4")])
+
+EXPORTS = [
+    "fjsp_last_error", "fjsp_abi_version", "fjsp_default_config", "fjsp_create", "fjsp_destroy", "fjsp_num_envs",
+    "fjsp_state_bytes", "fjsp_state_ptr", "fjsp_reset", "fjsp_step", "fjsp_step_host", "fjsp_random_actions",
+    "fjsp_rollout_random", "fjsp_export_state", "fjsp_export_packed", "fjsp_launch_count",
+    "fjsp_state_total_bytes", "fjsp_state_save", "fjsp_state_load",
+]
+
+
+def find_nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; cannot build libfjsp_b200.so")
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a.  Cross-compiles without a GPU."""
+    deps = SOURCES + [HEADER]
+    stale = (not os.path.exists(SO_PATH)) or any(os.path.getmtime(p) > os.path.getmtime(SO_PATH) for p in deps)
+    if force or stale:
+        os.makedirs(os.path.dirname(SO_PATH), exist_ok=True)
+        cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, SOURCES[0]]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose:
+            print(proc.stderr)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    return SO_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libfjsp_b200.so (raises if it has not been built: there is no CPU fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError(
+            "libfjsp_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`python -m multi_agent_rl_for_fjsp_b200.abi`. This package has no CPU fallback." % SO_PATH)
+    L = C.CDLL(SO_PATH)
+    vp, i64, u64 = C.c_void_p, C.c_int64, C.c_uint64
+    L.fjsp_last_error.restype = C.c_char_p
+    L.fjsp_abi_version.restype = C.c_int
+    L.fjsp_default_config.argtypes = [C.POINTER(FjspConfig)]
+    L.fjsp_create.argtypes = [C.POINTER(FjspConfig), i64, i64, C.c_int, C.POINTER(vp)]
+    L.fjsp_destroy.argtypes = [vp]
+    L.fjsp_num_envs.restype, L.fjsp_num_envs.argtypes = i64, [vp]
+    L.fjsp_state_bytes.restype, L.fjsp_state_bytes.argtypes = C.c_size_t, [vp]
+    L.fjsp_state_ptr.restype, L.fjsp_state_ptr.argtypes = vp, [vp]
+    L.fjsp_launch_count.restype, L.fjsp_launch_count.argtypes = i64, [vp]
+    L.fjsp_reset.argtypes = [vp, vp, u64, vp, C.c_int, vp, vp, vp]
+    L.fjsp_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp]
+    L.fjsp_step_host.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int, vp]
+    L.fjsp_random_actions.argtypes = [vp, u64, u64, vp, vp]
+    L.fjsp_rollout_random.argtypes = [vp, C.c_int, u64, u64, vp, vp]
+    L.fjsp_state_total_bytes.restype, L.fjsp_state_total_bytes.argtypes = C.c_size_t, [vp]
+    L.fjsp_state_save.argtypes = [vp, vp, C.c_size_t, vp]
+    L.fjsp_state_load.argtypes = [vp, vp, C.c_size_t, vp]
+    L.fjsp_export_state.argtypes = [vp, i64, vp]
+    L.fjsp_export_packed.argtypes = [vp, i64, vp]
+    if L.fjsp_abi_version() != 1:
+        raise RuntimeError("libfjsp_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RuntimeError("libfjsp_b200: " + lib().fjsp_last_error().decode())
+
+
+def default_config() -> FjspConfig:
+    cfg = FjspConfig()
+    check(lib().fjsp_default_config(C.byref(cfg)))
+    return cfg
+
+
+def config_from_dict(d: dict | None) -> FjspConfig:
+    """Build an FjspConfig from a reference-style CONFIG dict (constants.py:20-32); unknown keys are ignored,
+    ``positions`` / ``processing_times`` may carry LOCATION_POSITIONS / PROCESSING_TIMES overrides."""
+    cfg = default_config()
+    if not d:
+        return cfg
+    for k in ("grid_rows", "grid_cols", "step_size", "agv_speed", "max_episode_steps", "storage_capacity",
+              "pack_capacity", "tray_capacity", "num_trays", "proc_small", "proc_big", "proc_pack"):
+        if k in d:
+            setattr(cfg, k, int(d[k]))
+    pt = d.get("processing_times") or {}
+    for k, f in (("small_machine", "proc_small"), ("big_machine", "proc_big"), ("packaging", "proc_pack")):
+        if k in pt:
+            setattr(cfg, f, int(pt[k]))
+    pos = d.get("positions") or d.get("pos")
+    if pos is not None:
+        for i, (r, c) in enumerate(pos):
+            cfg.pos[i][0], cfg.pos[i][1] = int(r), int(c)
+    return cfg
+
+
+def order_rec(n: int, ptype: int, colour: int) -> int:
+    return int(n) | (int(ptype) << 8) | (int(colour) << 16)
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

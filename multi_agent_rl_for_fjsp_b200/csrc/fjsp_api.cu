@@ -1,0 +1,260 @@
+// fjsp_api.cu — the C ABI of libfjsp_b200.so (declared in include/fjsp_b200.h).
+// Host-side glue only: argument checks, launches, copies.  There is no CPU implementation of the step here;
+// every entry point that advances the simulation launches a kernel from fjsp_kernels.cuh.
+#include <cuda_runtime.h>
+
+#include <new>
+#include <string>
+
+#include "fjsp_host.h"
+#include "fjsp_kernels.cuh"
+
+using namespace fjsp;
+
+struct FjspHandle {
+    FjspConfig cfg;
+    Params P;
+    int device;
+    int64_t num_envs, first_env, num_tiles;
+    u32* state;  // num_tiles * 32 KB
+    uint64_t seed;
+    int num_orders;
+    int64_t launches;
+    // device staging for the host-buffer entry point (allocated on first use)
+    uint8_t* d_actions;
+    float* d_obs;
+    int8_t* d_masks;
+    float* d_rewards;
+    uint8_t* d_flags;
+};
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) {
+    g_err = m;
+    return 1;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return 2;
+}
+#define CK(call)                                        \
+    do {                                                \
+        cudaError_t e__ = (call);                       \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int dev) : prev(-1), ok(true) {
+        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+        else if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+extern "C" {
+
+const char* fjsp_last_error(void) { return g_err.c_str(); }
+int fjsp_abi_version(void) { return FJSP_ABI_VERSION; }
+
+int fjsp_default_config(FjspConfig* cfg) {
+    if (!cfg) return fail("cfg is NULL");
+    default_config(cfg);
+    return 0;
+}
+
+int fjsp_create(const FjspConfig* cfg, int64_t num_envs, int64_t first_env, int device, FjspHandle** out) {
+    if (!out) return fail("out is NULL");
+    *out = nullptr;
+    if (num_envs <= 0) return fail("num_envs must be positive");
+    if (first_env < 0 || first_env + num_envs > 0xffffffffLL) return fail("global env index must fit 32 bits (Philox counter word)");
+    FjspConfig c;
+    if (cfg) c = *cfg; else default_config(&c);
+    Params P;
+    if (const char* m = make_params(c, &P)) return fail(m);
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail("no such CUDA device (this library has no CPU path)");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 9) return fail("device lacks bulk async copies (needs sm_90+; built for sm_100a)");
+    DeviceGuard g(device);
+    if (!g.ok) return fail("cudaSetDevice failed");
+    FjspHandle* h = new (std::nothrow) FjspHandle();
+    if (!h) return fail("out of host memory");
+    h->cfg = c, h->P = P, h->device = device;
+    h->num_envs = num_envs, h->first_env = first_env;
+    h->num_tiles = (num_envs + TILE - 1) / TILE;
+    h->seed = 0, h->num_orders = 30, h->launches = 0;
+    cudaError_t e = cudaMalloc(&h->state, (size_t)h->num_tiles * TILE_BYTES);
+    if (e != cudaSuccess) {
+        delete h;
+        return cuda_fail(e, "cudaMalloc(state)");
+    }
+    e = cudaFuncSetAttribute(fjsp_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fjsp_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 16);
+    if (e != cudaSuccess) {
+        cudaFree(h->state);
+        delete h;
+        return cuda_fail(e, "cudaFuncSetAttribute (is this an sm_100a device?)");
+    }
+    // all envs start as freshly reset, empty shops (num_orders = 0) until fjsp_reset is called
+    fjsp_reset_kernel<<<(unsigned)h->num_tiles, TILE>>>(h->P, h->state, nullptr, nullptr, 0, 0ull, h->num_envs, h->first_env, nullptr,
+                                                        nullptr);
+    h->launches++;
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        cudaFree(h->state);
+        delete h;
+        return cuda_fail(e, "initial reset kernel");
+    }
+    *out = h;
+    return 0;
+}
+
+int fjsp_destroy(FjspHandle* h) {
+    if (!h) return 0;
+    DeviceGuard g(h->device);
+    cudaFree(h->state);
+    cudaFree(h->d_actions), cudaFree(h->d_obs), cudaFree(h->d_masks), cudaFree(h->d_rewards), cudaFree(h->d_flags);
+    delete h;
+    return 0;
+}
+
+int64_t fjsp_num_envs(const FjspHandle* h) { return h ? h->num_envs : 0; }
+size_t fjsp_state_bytes(const FjspHandle* h) {
+    (void)h;
+    return (size_t)FJSP_STATE_WORDS * 4;
+}
+void* fjsp_state_ptr(FjspHandle* h) { return h ? h->state : nullptr; }
+int64_t fjsp_launch_count(const FjspHandle* h) { return h ? h->launches : 0; }
+
+int fjsp_reset(FjspHandle* h, const uint8_t* env_mask, uint64_t seed, const FjspOrderRec* orders, int num_orders, float* obs,
+               int8_t* masks, void* stream) {
+    if (!h) return fail("handle is NULL");
+    if (num_orders < 0 || num_orders > FJSP_MAX_ORDERS) return fail("num_orders must be in 0..32");
+    if ((obs == nullptr) != (masks == nullptr)) return fail("obs and masks must both be given or both be NULL");
+    DeviceGuard g(h->device);
+    h->seed = seed, h->num_orders = num_orders;
+    fjsp_reset_kernel<<<(unsigned)h->num_tiles, TILE, 0, (cudaStream_t)stream>>>(h->P, h->state, env_mask, orders, num_orders, seed,
+                                                                                h->num_envs, h->first_env, obs, masks);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int fjsp_step(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, float* rewards, uint8_t* flags, uint8_t* results,
+              int32_t* infos, int autoreset, void* stream) {
+    if (!h) return fail("handle is NULL");
+    if (!actions || !obs || !masks || !rewards || !flags) return fail("actions/obs/masks/rewards/flags must be device pointers");
+    if ((reinterpret_cast<uintptr_t>(actions) & 7) || (reinterpret_cast<uintptr_t>(masks) & 15) ||
+        (reinterpret_cast<uintptr_t>(rewards) & 15) || (reinterpret_cast<uintptr_t>(flags) & 3) || (reinterpret_cast<uintptr_t>(obs) & 3) ||
+        (results && (reinterpret_cast<uintptr_t>(results) & 7)) || (infos && (reinterpret_cast<uintptr_t>(infos) & 15)))
+        return fail("buffer alignment: actions/results 8 B, masks/rewards/infos 16 B, flags/obs 4 B (obs 16 B for the bulk-store path)");
+    DeviceGuard g(h->device);
+    StepArgs A;
+    A.state = h->state, A.actions = actions, A.obs = obs, A.masks = masks, A.rewards = rewards, A.flags = flags;
+    A.results = results, A.infos = infos, A.num_envs = h->num_envs, A.first_env = h->first_env, A.seed = h->seed;
+    A.num_orders = h->num_orders, A.autoreset = autoreset;
+    fjsp_step_kernel<<<(unsigned)h->num_tiles, TILE, STEP_SMEM_BYTES, (cudaStream_t)stream>>>(h->P, A);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int ensure_staging(FjspHandle* h) {
+    if (h->d_actions) return 0;
+    const size_t n = (size_t)h->num_envs;
+    CK(cudaMalloc(&h->d_actions, n * FJSP_NUM_AGENTS));
+    CK(cudaMalloc(&h->d_obs, n * FJSP_OBS_DIM * sizeof(float)));
+    CK(cudaMalloc(&h->d_masks, n * FJSP_MASK_DIM));
+    CK(cudaMalloc(&h->d_rewards, n * FJSP_NUM_AGENTS * sizeof(float)));
+    CK(cudaMalloc(&h->d_flags, n * FJSP_FLAG_DIM));
+    return 0;
+}
+
+int fjsp_step_host(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, float* rewards, uint8_t* flags, int autoreset,
+                   void* stream) {
+    if (!h) return fail("handle is NULL");
+    if (!actions || !obs || !masks || !rewards || !flags) return fail("host buffers must not be NULL");
+    DeviceGuard g(h->device);
+    if (int rc = ensure_staging(h)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)h->num_envs;
+    CK(cudaMemcpyAsync(h->d_actions, actions, n * FJSP_NUM_AGENTS, cudaMemcpyHostToDevice, st));
+    if (int rc = fjsp_step(h, h->d_actions, h->d_obs, h->d_masks, h->d_rewards, h->d_flags, nullptr, nullptr, autoreset, stream)) return rc;
+    CK(cudaMemcpyAsync(obs, h->d_obs, n * FJSP_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(masks, h->d_masks, n * FJSP_MASK_DIM, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(rewards, h->d_rewards, n * FJSP_NUM_AGENTS * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(flags, h->d_flags, n * FJSP_FLAG_DIM, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int fjsp_random_actions(FjspHandle* h, uint64_t seed, uint64_t t, uint8_t* actions, void* stream) {
+    if (!h) return fail("handle is NULL");
+    if (!actions || (reinterpret_cast<uintptr_t>(actions) & 7)) return fail("actions must be an 8-byte aligned device pointer");
+    DeviceGuard g(h->device);
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((h->num_envs + threads - 1) / threads);
+    fjsp_random_actions_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(actions, h->num_envs, h->first_env, seed, t);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int fjsp_rollout_random(FjspHandle* h, int steps, uint64_t seed, uint64_t t0, uint64_t* stats, void* stream) {
+    if (!h) return fail("handle is NULL");
+    if (steps < 1) return fail("steps must be >= 1");
+    if (!stats || (reinterpret_cast<uintptr_t>(stats) & 7)) return fail("stats must be an 8-byte aligned device pointer (8 x u64)");
+    if (seed != h->seed) return fail("rollout seed must equal the seed of the last fjsp_reset (one Philox key per handle)");
+    DeviceGuard g(h->device);
+    fjsp_rollout_kernel<<<(unsigned)h->num_tiles, TILE, TILE_BYTES + 16, (cudaStream_t)stream>>>(
+        h->P, h->state, h->num_envs, h->first_env, seed, t0, steps, h->num_orders, reinterpret_cast<unsigned long long*>(stats));
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+size_t fjsp_state_total_bytes(const FjspHandle* h) { return h ? (size_t)h->num_tiles * TILE_BYTES : 0; }
+
+int fjsp_state_save(FjspHandle* h, void* dst_device, size_t bytes, void* stream) {
+    if (!h || !dst_device) return fail("NULL argument");
+    if (bytes != fjsp_state_total_bytes(h)) return fail("bytes must equal fjsp_state_total_bytes()");
+    DeviceGuard g(h->device);
+    CK(cudaMemcpyAsync(dst_device, h->state, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+int fjsp_state_load(FjspHandle* h, const void* src_device, size_t bytes, void* stream) {
+    if (!h || !src_device) return fail("NULL argument");
+    if (bytes != fjsp_state_total_bytes(h)) return fail("bytes must equal fjsp_state_total_bytes()");
+    DeviceGuard g(h->device);
+    CK(cudaMemcpyAsync(h->state, src_device, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+int fjsp_export_packed(FjspHandle* h, int64_t env, uint32_t* out_words) {
+    if (!h || !out_words) return fail("NULL argument");
+    if (env < 0 || env >= h->num_envs) return fail("env index out of range");
+    DeviceGuard g(h->device);
+    CK(cudaDeviceSynchronize());
+    const u32* src = h->state + (env / TILE) * TILE_WORDS + (env % TILE);
+    // word w of this env sits TILE words after word w-1: a strided gather of 128 x 4 bytes
+    CK(cudaMemcpy2D(out_words, sizeof(u32), src, TILE * sizeof(u32), sizeof(u32), FJSP_STATE_WORDS, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int fjsp_export_state(FjspHandle* h, int64_t env, FjspCanonState* out) {
+    if (!out) return fail("out is NULL");
+    u32 words[FJSP_STATE_WORDS];
+    if (int rc = fjsp_export_packed(h, env, words)) return rc;
+    export_canon(words, h->P, out);
+    return 0;
+}
+
+}  // extern "C"

@@ -321,12 +321,13 @@ FJSP_HD void reset_env(S& s, const Params& P, int num_orders, const FjspOrderRec
 // Observation (layout O, 38 floats) + masks (29 bytes in 8 words).  SURVEY.md §8a-R9.
 // ---------------------------------------------------------------------------------------------
 struct StepOut {
-    float obs[FJSP_OBS_DIM];
+    float* obs;     // 38 floats, written in place (a shared-memory staging row on the device)
     u32 mask[FJSP_MASK_DIM / 4];
     float reward[FJSP_NUM_AGENTS];
     u32 flags;      // terminated | truncated<<8 | fault<<16 | was_reset<<24
     u32 results[2]; // 8 x u8 action_result bit-fields
     int32_t info[4];
+    long long reward40;  // sum over the 8 agents of round(40 * reward): exact integer statistic for rollouts
 };
 
 FJSP_HD void mask_set(u32* mw, int idx, int v) { mw[idx >> 2] |= (u32)(v & 1) << ((idx & 3) * 8); }
@@ -470,7 +471,7 @@ FJSP_HD void pack_grant(S& s, Hot& h, Pack& p, int g, int stamp) {
 // ---------------------------------------------------------------------------------------------
 // One environment step.  Returns through `out`.  `actions` = 8 bytes.
 // ---------------------------------------------------------------------------------------------
-template <class S>
+template <bool WITH_OBS, class S>
 FJSP_HD void step_env(S& s, const Params& P, const int a[8], StepOut& out) {
     Hot h;
     load_hot(s, h);
@@ -749,8 +750,18 @@ FJSP_HD void step_env(S& s, const Params& P, const int a[8], StepOut& out) {
         double g = 100.0 * (double)(h.completed_orders - orders_before);
         g += 10.0 * (double)(h.total_packaged - products_before);
         g += P.time_reward;
+        long long r40 = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) out.reward[i] = (float)(g / 8.0 + local[i]);
+        for (int i = 0; i < 8; i++) {
+            double r = g / 8.0 + local[i];
+            out.reward[i] = (float)r;
+#if defined(__CUDA_ARCH__)
+            r40 += __double2ll_rn(r * 40.0);
+#else
+            r40 += (long long)__builtin_llrint(r * 40.0);
+#endif
+        }
+        out.reward40 = r40;
     }
     // ===== termination / truncation (FJSPSimulation.py:216-224), pre-increment step =====
     const int all_done = h.completed_orders == h.num_orders && h.num_orders > 0 && h.next_order == h.num_orders;
@@ -760,7 +771,7 @@ FJSP_HD void step_env(S& s, const Params& P, const int a[8], StepOut& out) {
     out.results[1] = res[4] | (res[5] << 8) | (res[6] << 16) | (res[7] << 24);
     h.step = k + 1;
     out.info[0] = h.step, out.info[1] = h.completed_orders, out.info[2] = h.total_packaged, out.info[3] = 0;
-    observe(s, P, h, out.obs, out.mask);
+    if (WITH_OBS) observe(s, P, h, out.obs, out.mask);
     store_hot(s, h);
 }
 

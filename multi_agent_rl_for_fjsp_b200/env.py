@@ -1,0 +1,195 @@
+"""BatchedFJSPEnv — tensor API over N independent shop floors stepped in lockstep on one B200.
+
+Host-side mirror of the reference's env surface for the batched case: the same reset/step meaning as
+``FJSPParallelEnv.reset/step`` (/root/reference/FJSPParallelEnvWrapper.py:43-69), with the 8 agents'
+dicts replaced by dense tensors in the canonical agent order (FJSPSimulation.py:76-82):
+
+    actions  uint8 [N, 8]      obs  float32 [N, 38] (a2c._flatten_obs order)      masks int8 [N, 32] (29 used)
+    rewards  float32 [N, 8]    flags uint8 [N, 4] = terminated, truncated, fault, was_reset
+
+PyTorch is plumbing here (device memory + the current stream); every simulation step is one launch of
+the sm_100a kernel behind ``fjsp_step`` in libfjsp_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import abi
+
+AGENT_IDS = [
+    "pickup_station", "agv", "small_machine", "big_machine",
+    "packaging_blue_1", "packaging_blue_2", "packaging_red", "packaging_green",
+]
+N_ACTIONS = (3, 8, 3, 3, 3, 3, 3, 3)
+OBS_DIM, MASK_DIM = abi.OBS_DIM, abi.MASK_DIM
+OBS_SLICES = [(0, 7), (7, 20), (20, 23), (23, 26), (26, 29), (29, 32), (32, 35), (35, 38)]
+MASK_OFFSETS = [0, 3, 11, 14, 17, 20, 23, 26, 29]
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BatchedFJSPEnv:
+    def __init__(self, num_envs: int, config=None, device="cuda:0", first_env: int = 0, seed: int = 0,
+                 num_orders: int = 30, autoreset: bool = True, with_infos: bool = False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedFJSPEnv needs a CUDA device: the environment step exists only as sm_100a kernels")
+        self._L = abi.lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("BatchedFJSPEnv runs on CUDA devices only (got %s)" % device)
+        self.cfg = config if isinstance(config, abi.FjspConfig) else abi.config_from_dict(config)
+        self.num_envs, self.first_env = int(num_envs), int(first_env)
+        self.seed, self.num_orders, self.autoreset = int(seed), int(num_orders), bool(autoreset)
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        torch.cuda.init()
+        with torch.cuda.device(dev_index):
+            torch.zeros(1, device=self.device)  # make sure the primary context exists before the library uses it
+            h = C.c_void_p()
+            abi.check(self._L.fjsp_create(C.byref(self.cfg), self.num_envs, self.first_env, dev_index, C.byref(h)))
+        self._h = h
+        n = self.num_envs
+        kw = dict(device=self.device)
+        self.obs = torch.zeros((n, OBS_DIM), dtype=torch.float32, **kw)
+        self.masks = torch.zeros((n, MASK_DIM), dtype=torch.int8, **kw)
+        self.rewards = torch.zeros((n, 8), dtype=torch.float32, **kw)
+        self.flags = torch.zeros((n, 4), dtype=torch.uint8, **kw)
+        self.results = torch.zeros((n, 8), dtype=torch.uint8, **kw) if with_infos else None
+        self.infos = torch.zeros((n, 4), dtype=torch.int32, **kw) if with_infos else None
+        self._actions = torch.zeros((n, 8), dtype=torch.uint8, **kw)
+        self._stats = torch.zeros(8, dtype=torch.int64, **kw)
+        self._t = 0
+        self._host = None
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.fjsp_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.fjsp_launch_count(self._h))
+
+    @property
+    def state_bytes_per_env(self) -> int:
+        return int(self._L.fjsp_state_bytes(self._h))
+
+    # ------------------------------------------------------------------ reset / step
+    def reset(self, seed: int | None = None, num_orders: int | None = None, orders=None, env_mask=None):
+        """FJSPParallelEnv.reset for all (or the masked) envs.
+
+        orders: optional explicit order tables, uint32 tensor/array [N, 32] packed n | type<<8 | colour<<16
+        (``abi.order_rec``) or int array [N, num_orders, 3]; default: Philox stream (seed, global env, episode 0).
+        """
+        if seed is not None:
+            self.seed = int(seed)
+        if num_orders is not None:
+            self.num_orders = int(num_orders)
+        d_orders = None
+        if orders is not None:
+            d_orders = self._pack_orders(orders)
+        d_mask = None
+        if env_mask is not None:
+            d_mask = torch.as_tensor(env_mask, device=self.device).to(torch.uint8).contiguous()
+            assert d_mask.numel() == self.num_envs
+        abi.check(self._L.fjsp_reset(self._h, _ptr(d_mask), self.seed, _ptr(d_orders), self.num_orders, _ptr(self.obs),
+                                     _ptr(self.masks), self._stream()))
+        self._keep = (d_orders, d_mask)  # keep the buffers alive until the stream has consumed them
+        return self.obs, self.masks
+
+    def _pack_orders(self, orders):
+        arr = orders.detach().cpu().numpy() if isinstance(orders, torch.Tensor) else np.asarray(orders)
+        if arr.ndim == 3:  # [N, k, 3] -> packed [N, 32]
+            n, k, _ = arr.shape
+            packed = np.zeros((n, abi.MAX_ORDERS), dtype=np.uint32)
+            packed[:, :k] = (arr[..., 0].astype(np.uint32) | (arr[..., 1].astype(np.uint32) << 8) |
+                             (arr[..., 2].astype(np.uint32) << 16))
+            if self.num_orders != k:
+                self.num_orders = k
+            arr = packed
+        arr = np.ascontiguousarray(arr, dtype=np.uint32)
+        assert arr.shape == (self.num_envs, abi.MAX_ORDERS), arr.shape
+        return torch.from_numpy(arr.view(np.int32)).to(self.device)
+
+    def step(self, actions: torch.Tensor):
+        """One lockstep step of all envs: ONE kernel launch.  Returns views of the env's output tensors."""
+        a = actions
+        if a.dtype != torch.uint8 or a.device != self.device or not a.is_contiguous():
+            a = a.to(device=self.device, dtype=torch.uint8).contiguous()
+        assert a.shape == (self.num_envs, 8), a.shape
+        abi.check(self._L.fjsp_step(self._h, _ptr(a), _ptr(self.obs), _ptr(self.masks), _ptr(self.rewards), _ptr(self.flags),
+                                    _ptr(self.results), _ptr(self.infos), int(self.autoreset), self._stream()))
+        self._t += 1
+        return self.obs, self.rewards, self.flags[:, 0], self.flags[:, 1], self.masks
+
+    def random_actions(self, t: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+        """a_i ~ U{0..n_i-1} from the Philox action stream at time index t (default: the env's step counter)."""
+        out = self._actions if out is None else out
+        abi.check(self._L.fjsp_random_actions(self._h, self.seed, self._t if t is None else int(t), _ptr(out), self._stream()))
+        return out
+
+    def rollout_random(self, steps: int, t0: int | None = None) -> torch.Tensor:
+        """`steps` steps per launch with in-kernel random actions and auto-reset; returns the cumulative stats tensor
+        (env_steps, episodes, orders_completed, products_packaged, faults, sum round(40*reward), 0, 0)."""
+        t0 = self._t if t0 is None else int(t0)
+        abi.check(self._L.fjsp_rollout_random(self._h, int(steps), self.seed, t0, _ptr(self._stats), self._stream()))
+        self._t = t0 + int(steps)
+        return self._stats
+
+    # ------------------------------------------------------------------ host-buffer path (end-to-end)
+    def step_host(self, actions: np.ndarray):
+        """Same step through HOST buffers: H2D actions, kernel, D2H obs/masks/rewards/flags (pinned), synchronised."""
+        if self._host is None:
+            n = self.num_envs
+            self._host = dict(
+                actions=torch.zeros((n, 8), dtype=torch.uint8).pin_memory(),
+                obs=torch.zeros((n, OBS_DIM), dtype=torch.float32).pin_memory(),
+                masks=torch.zeros((n, MASK_DIM), dtype=torch.int8).pin_memory(),
+                rewards=torch.zeros((n, 8), dtype=torch.float32).pin_memory(),
+                flags=torch.zeros((n, 4), dtype=torch.uint8).pin_memory())
+        hb = self._host
+        if actions is not None:
+            hb["actions"].numpy()[...] = actions
+        abi.check(self._L.fjsp_step_host(self._h, _ptr(hb["actions"]), _ptr(hb["obs"]), _ptr(hb["masks"]), _ptr(hb["rewards"]),
+                                         _ptr(hb["flags"]), int(self.autoreset), self._stream()))
+        self._t += 1
+        return hb["obs"].numpy(), hb["masks"].numpy(), hb["rewards"].numpy(), hb["flags"].numpy()
+
+    # ------------------------------------------------------------------ snapshot / restore
+    def save_state(self) -> torch.Tensor:
+        """Copy of the whole packed state (int32 tensor on the env's device)."""
+        nbytes = int(self._L.fjsp_state_total_bytes(self._h))
+        buf = torch.empty(nbytes // 4, dtype=torch.int32, device=self.device)
+        abi.check(self._L.fjsp_state_save(self._h, _ptr(buf), nbytes, self._stream()))
+        return buf
+
+    def load_state(self, buf: torch.Tensor):
+        nbytes = int(self._L.fjsp_state_total_bytes(self._h))
+        assert buf.device == self.device and buf.is_contiguous() and buf.numel() * buf.element_size() == nbytes
+        abi.check(self._L.fjsp_state_load(self._h, _ptr(buf), nbytes, self._stream()))
+
+    # ------------------------------------------------------------------ diagnostics
+    def export_state(self, env: int) -> np.ndarray:
+        """Canonical integer record S of one env (synchronises)."""
+        s = np.zeros((), dtype=abi.CANON_DT)
+        abi.check(self._L.fjsp_export_state(self._h, int(env), C.c_void_p(s.ctypes.data)))
+        return s
+
+    def export_packed(self, env: int) -> np.ndarray:
+        w = np.zeros(abi.STATE_WORDS, dtype=np.uint32)
+        abi.check(self._L.fjsp_export_packed(self._h, int(env), C.c_void_p(w.ctypes.data)))
+        return w

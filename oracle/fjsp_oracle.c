@@ -35,8 +35,8 @@
 #include "../include/fjsp_b200.h"
 
 #define MAX_PRODUCTS (FJSP_MAX_ORDERS * FJSP_MAX_ORDER_PRODUCTS)
-#define MAX_TRAYS 1024
-#define LIST_CAP 512
+#define MAX_TRAYS 256 /* one tray per LOAD at most, episodes are <= 253 steps */
+#define LIST_CAP 320
 
 enum { LOC_PICKUP = 0, LOC_BIG = 1, LOC_SMALL = 2, LOC_STORAGE = 3, LOC_PACKAGING = 4, LOC_NONE = -1 };
 enum { TYPE_SMALL = 1, TYPE_MEDIUM = 2, TYPE_BIG = 3 };
@@ -200,13 +200,7 @@ void fjsp_oracle_reset(OracleEnv* e, const FjspOrderRec* orders, int num_orders)
     e->pack[0].colour = COL_BLUE, e->pack[1].colour = COL_BLUE; /* FJSPSimulation.py:68-73 */
     e->pack[2].colour = COL_RED, e->pack[3].colour = COL_GREEN;
     /* _init_trays (:89-98): ids 0..num_trays-1, popped from the END into trays_at_station, at most 1000 */
-    e->ntrays_total = cfg.num_trays < 1000 ? cfg.num_trays : 1000;
-    if (e->ntrays_total > MAX_TRAYS) e->ntrays_total = MAX_TRAYS;
-    for (int i = 0; i < e->ntrays_total; i++) {
-        e->trays[i].id = cfg.num_trays - 1 - i; /* allocation order: highest id first */
-        e->trays[i].n = 0;
-        e->trays[i].order_id = -1;
-    }
+    e->ntrays_total = cfg.num_trays < 1000 ? cfg.num_trays : 1000; /* tray i (allocation order) has id num_trays-1-i */
     /* generate_order x num_orders (:101-131, :315-318) */
     if (num_orders > FJSP_MAX_ORDERS) num_orders = FJSP_MAX_ORDERS;
     for (int o = 0; o < num_orders; o++) {
@@ -344,7 +338,10 @@ static double act_pickup(OracleEnv* e, int action, uint8_t* res) {
             }
             if (!e->current_tray) {
                 if (trays_at_station(e) > 0) {
-                    e->current_tray = &e->trays[e->trays_next++]; /* trays_at_station.pop(0), :176 */
+                    int ti = e->trays_next++; /* trays_at_station.pop(0), :176 */
+                    e->current_tray = &e->trays[ti % MAX_TRAYS];
+                    e->current_tray->id = e->cfg.num_trays - 1 - ti;
+                    e->current_tray->n = 0;
                     e->current_tray->order_id = e->current_order->id;
                 } else break;
             }
@@ -795,6 +792,8 @@ typedef struct RolloutJob {
 
 static void* rollout_worker(void* arg) {
     RolloutJob* j = (RolloutJob*)arg;
+    uint64_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; /* thread-local: the job structs share cache lines */
+    int64_t rsum = 0;
     for (int64_t i = j->lo; i < j->hi; i++) {
         OracleEnv* e = j->envs[i];
         uint64_t genv = (uint64_t)(j->first_env + i);
@@ -802,24 +801,28 @@ static void* rollout_worker(void* arg) {
         int8_t masks[FJSP_MASK_DIM];
         double rew[8];
         uint8_t flags[4], act[8];
+        uint32_t episode = j->episodes[i];
         for (int k = 0; k < j->steps; k++) {
             int before_o = e->completed_orders, before_p = e->total_products_packaged;
             fjsp_oracle_philox_actions(j->seed, genv, j->t0 + (uint64_t)k, act);
             fjsp_oracle_step(e, act, obs, masks, rew, flags, NULL);
-            j->acc[0] += 1;
-            j->acc[2] += (uint64_t)(e->completed_orders - before_o);
-            j->acc[3] += (uint64_t)(e->total_products_packaged - before_p);
-            for (int a = 0; a < 8; a++) j->rsum += (int64_t)llround(rew[a] * 40.0);
+            acc[0] += 1;
+            acc[2] += (uint64_t)(e->completed_orders - before_o);
+            acc[3] += (uint64_t)(e->total_products_packaged - before_p);
+            for (int a = 0; a < 8; a++) rsum += (int64_t)llround(rew[a] * 40.0);
             if (flags[0] | flags[1] | flags[2]) {
                 FjspOrderRec orders[FJSP_MAX_ORDERS];
-                j->acc[1] += 1;
-                j->acc[4] += flags[2] ? 1 : 0;
-                j->episodes[i] += 1;
-                fjsp_oracle_philox_orders(j->seed, genv, j->episodes[i], j->num_orders, orders);
+                acc[1] += 1;
+                acc[4] += flags[2] ? 1 : 0;
+                episode += 1;
+                fjsp_oracle_philox_orders(j->seed, genv, episode, j->num_orders, orders);
                 fjsp_oracle_reset(e, orders, j->num_orders);
             }
         }
+        j->episodes[i] = episode;
     }
+    for (int k = 0; k < 8; k++) j->acc[k] = acc[k];
+    j->rsum = rsum;
     return NULL;
 }
 

@@ -59,8 +59,8 @@ void hh_step(void* p, const uint8_t* actions, float* obs, int8_t* masks, float* 
     int a[8];
     for (int i = 0; i < 8; i++) a[i] = actions[i];
     StepOut out;
-    step_env(s, e->P, a, out);
-    for (int i = 0; i < FJSP_OBS_DIM; i++) obs[i] = out.obs[i];
+    out.obs = obs;
+    step_env<true>(s, e->P, a, out);
     unpack_masks(out.mask, masks);
     for (int i = 0; i < 8; i++) rewards[i] = out.reward[i];
     flags[0] = out.flags & 0xff, flags[1] = (out.flags >> 8) & 0xff, flags[2] = (out.flags >> 16) & 0xff, flags[3] = 0;

@@ -1,0 +1,236 @@
+"""Parity of the CUDA path (through the C ABI, libfjsp_b200.so) against the oracle and the golden vectors.
+
+Bar (BASELINE.json north_star): integer state, observations' integer fields, masks and flags bit-exact;
+rewards / float observations within 1e-6 relative (tests/util.py REL_TOL).  Nothing here reads
+/root/reference: the goldens were recorded from it in the build container (oracle/gen_golden.py).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import canon
+from oracle.fjsp_oracle import OracleBatch, OracleEnv, philox_actions, philox_orders
+from tests.util import GOLDEN_FILES, REL_TOL, cfg_from_dict, load_golden, replay_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _abi_cfg(ocfg):
+    """oracle FjspConfig -> package FjspConfig (same C layout)."""
+    import ctypes as C
+
+    from multi_agent_rl_for_fjsp_b200 import abi
+
+    cfg = abi.FjspConfig()
+    C.memmove(C.addressof(cfg), C.addressof(ocfg), C.sizeof(cfg))
+    return cfg
+
+
+class GpuSingle:
+    """Adapter: one CUDA env behind the replay interface of tests/util.py."""
+
+    def __init__(self, ocfg):
+        from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+
+        self.env = BatchedFJSPEnv(1, config=_abi_cfg(ocfg), autoreset=False)
+
+    def reset(self, orders):
+        orders = np.asarray(orders)
+        obs, masks = self.env.reset(orders=orders[None, :, :])
+        return obs[0].cpu().numpy(), masks[0].cpu().numpy()
+
+    def step(self, actions):
+        a = torch.as_tensor(np.asarray(actions, dtype=np.uint8)[None, :], device=self.env.device)
+        obs, rew, term, trunc, masks = self.env.step(a)
+        return obs[0].cpu().numpy(), masks[0].cpu().numpy(), rew[0].cpu().numpy(), self.env.flags[0].cpu().numpy()
+
+    def export(self):
+        return self.env.export_state(0)
+
+
+@pytest.mark.parametrize("name", GOLDEN_FILES)
+def test_gpu_replays_golden(name):
+    """Every golden trajectory of the reference, step by step, through fjsp_reset/fjsp_step/fjsp_export_state."""
+    steps = replay_golden(name, lambda cfg: GpuSingle(cfg), max_steps=2500)
+    assert steps > 0
+
+
+def test_gpu_golden_episodes_in_one_batch():
+    """All episodes of the heuristic golden file as ONE batch (one env per episode) stepped in lockstep."""
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+
+    g, cfgd = load_golden("default_heuristic")
+    starts = g["ep_start"].tolist() + [g["actions"].shape[0]]
+    E = len(starts) - 1
+    lens = [starts[i + 1] - starts[i] for i in range(E)]
+    env = BatchedFJSPEnv(E, config=_abi_cfg(cfg_from_dict(cfgd)), autoreset=False)
+    orders = np.zeros((E, 32), dtype=np.uint32)
+    for e in range(E):
+        no = int(g["ep_norders"][e])
+        t = g["ep_orders"][e][:no]
+        orders[e, :no] = t[:, 0] | (t[:, 1] << 8) | (t[:, 2] << 16)
+    # per-env num_orders differs: reset each group of equal num_orders with a mask
+    for no in sorted(set(int(x) for x in g["ep_norders"])):
+        mask = (g["ep_norders"] == no).astype(np.uint8)
+        env.reset(num_orders=no, orders=orders, env_mask=mask)
+    for k in range(max(lens)):
+        acts = np.zeros((E, 8), dtype=np.uint8)
+        live = [e for e in range(E) if k < lens[e]]
+        for e in live:
+            acts[e] = g["actions"][starts[e] + k]
+        obs, rew, term, trunc, masks = env.step(torch.as_tensor(acts, device=env.device))
+        obs, rew, masks, flags = obs.cpu().numpy(), rew.cpu().numpy(), masks.cpu().numpy(), env.flags.cpu().numpy()
+        for e in live:
+            t = starts[e] + k
+            assert np.array_equal(obs[e], g["obs"][t]), (e, k)
+            assert np.array_equal(masks[e], g["masks"][t]), (e, k)
+            assert np.all(np.abs(rew[e] - g["rewards"][t]) <= REL_TOL * np.abs(g["rewards"][t])), (e, k)
+            assert tuple(flags[e][:2]) == tuple(g["flags"][t]) and flags[e][2] == 0, (e, k)
+
+
+@pytest.mark.parametrize("n_envs,first_env", [(1, 0), (63, 5), (64, 0), (1000, 123456), (4096, 0)])
+def test_gpu_vs_oracle_random_batch(n_envs, first_env):
+    """Philox orders + Philox actions + auto-reset: sampled envs are followed by the oracle step by step
+    (ragged sizes exercise the partial last tile and the non-bulk observation store)."""
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+
+    seed, num_orders, steps = 0xC0FFEE1234, 30, 430
+    env = BatchedFJSPEnv(n_envs, first_env=first_env, seed=seed, num_orders=num_orders, autoreset=True, with_infos=True)
+    obs0, masks0 = env.reset()
+    rs = np.random.RandomState(n_envs)
+    sample = sorted(set([0, n_envs - 1] + rs.randint(0, n_envs, size=min(24, n_envs)).tolist()))
+    oracles, episodes = {}, {}
+    obs0, masks0 = obs0.cpu().numpy(), masks0.cpu().numpy()
+    for i in sample:
+        o = OracleEnv()
+        oo, om = o.reset(philox_orders(seed, first_env + i, 0, num_orders))
+        assert np.array_equal(oo, obs0[i]) and np.array_equal(om, masks0[i])
+        oracles[i], episodes[i] = o, 0
+    for t in range(steps):
+        acts = env.random_actions(t)
+        acts_h = acts.cpu().numpy()
+        obs, rew, term, trunc, masks = env.step(acts)
+        obs, rew, masks, flags, infos = (x.cpu().numpy() for x in (obs, rew, masks, env.flags, env.infos))
+        for i in sample:
+            o = oracles[i]
+            assert np.array_equal(acts_h[i], philox_actions(seed, first_env + i, t)), "action stream"
+            oo, om, orw, of = o.step(acts_h[i])
+            assert tuple(of[:3]) == tuple(flags[i][:3]), (i, t, of, flags[i])
+            assert np.all(np.abs(rew[i] - orw) <= REL_TOL * np.abs(orw)), (i, t, rew[i], orw)
+            assert np.array_equal(o.results, env.results[i].cpu().numpy()), (i, t)
+            if of[0] or of[1] or of[2]:
+                assert flags[i][3] == 1
+                episodes[i] += 1
+                oo, om = o.reset(philox_orders(seed, first_env + i, episodes[i], num_orders))
+            else:
+                assert flags[i][3] == 0
+                assert infos[i][0] == int(o.export()["current_step"])
+            assert np.array_equal(oo, obs[i]), (i, t, oo, obs[i])
+            assert np.array_equal(om, masks[i]), (i, t)
+    for i in sample:
+        d = canon.diff(oracles[i].export(), env.export_state(i))
+        assert not d, (i, d[:5])
+
+
+def test_gpu_rollout_matches_stepwise_and_oracle():
+    """K-steps-per-launch kernel == single-step kernel (whole packed state, bit for bit) == oracle statistics."""
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+
+    n, seed, num_orders, steps = 2048 + 17, 99, 30, 260
+    a = BatchedFJSPEnv(n, seed=seed, num_orders=num_orders, autoreset=True)
+    b = BatchedFJSPEnv(n, seed=seed, num_orders=num_orders, autoreset=True)
+    a.reset(), b.reset()
+    for t in range(steps):
+        a.step(a.random_actions(t))
+    stats = b.rollout_random(100, t0=0)
+    stats = b.rollout_random(steps - 100, t0=100).cpu().numpy()
+    assert torch.equal(a.save_state(), b.save_state())
+    ob = OracleBatch(n, seed, num_orders)
+    ostats = ob.rollout(steps, nthreads=4)
+    assert stats[:6].tolist() == ostats[:6].astype(np.int64).tolist(), (stats, ostats)
+    for i in (0, 1, 63, 64, n - 1):
+        d = canon.diff(ob.export(i), b.export_state(i))
+        assert not d, (i, d[:5])
+
+
+def test_gpu_full_size_properties():
+    """BASELINE config 4 size (2^20 envs): size-independent properties.
+    (1) step path and rollout path agree bit for bit on the whole 512 MB state; (2) sampled envs agree with the
+    oracle; (3) the shard map does not matter: env g of a full batch == env g-first_env of a shard."""
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+
+    n, seed, steps = 1 << 20, 2026, 48
+    a = BatchedFJSPEnv(n, seed=seed, autoreset=True)
+    a.reset()
+    b = BatchedFJSPEnv(n, seed=seed, autoreset=True)
+    b.reset()
+    for t in range(steps):
+        a.step(a.random_actions(t))
+    stats = b.rollout_random(steps, t0=0).cpu().numpy()
+    assert stats[0] == n * steps
+    assert torch.equal(a.save_state(), b.save_state())
+    first = (n // 2) + 777
+    shard = BatchedFJSPEnv(4096, first_env=first, seed=seed, autoreset=True)
+    shard.reset()
+    shard.rollout_random(steps, t0=0)
+    for g in (first, first + 1, first + 4095):
+        assert np.array_equal(b.export_packed(g), shard.export_packed(g - first))
+    for g in (0, 12345, n - 1):
+        o = OracleEnv()
+        o.reset(philox_orders(seed, g, 0, 30))
+        for t in range(steps):
+            o.step(philox_actions(seed, g, t))
+        d = canon.diff(o.export(), a.export_state(g))
+        assert not d, (g, d[:5])
+
+
+def test_gpu_host_buffer_step_matches_device_step():
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+
+    n, seed = 777, 5
+    a = BatchedFJSPEnv(n, seed=seed)
+    b = BatchedFJSPEnv(n, seed=seed)
+    a.reset(), b.reset()
+    for t in range(40):
+        acts = a.random_actions(t)
+        obs, rew, term, trunc, masks = a.step(acts)
+        hobs, hmasks, hrew, hflags = b.step_host(acts.cpu().numpy())
+        assert np.array_equal(obs.cpu().numpy(), hobs) and np.array_equal(masks.cpu().numpy(), hmasks)
+        assert np.array_equal(rew.cpu().numpy(), hrew) and np.array_equal(a.flags.cpu().numpy(), hflags)
+
+
+def test_gpu_fault_flag_on_restart_with_waiters():
+    """R-PKG-cap-b: a packaging START while requests still wait (where the reference raises ValueError) sets
+    the fault flag on both sides in the same step."""
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+    from tests.test_known_answers import drive_to_pack_overflow
+
+    ocfg = cfg_from_dict(dict(load_golden("pack_cap3")[1]))
+    o = OracleEnv(ocfg)
+    g = GpuSingle(ocfg)
+    acts = drive_to_pack_overflow()
+    orders = [(5, 1, 1)] * 4
+    o.reset(orders), g.reset(orders)
+    seen = False
+    for a in acts:
+        _, _, _, of = o.step(a)
+        _, _, _, gf = g.step(a)
+        assert tuple(of[:3]) == tuple(gf[:3])
+        seen = seen or of[2] == 1
+        if seen:
+            break
+    assert seen
+
+
+def test_no_cpu_fallback_in_product():
+    """The package must not route through the oracle or any host build of the step."""
+    import multi_agent_rl_for_fjsp_b200 as pkg
+    import os
+
+    root = os.path.dirname(pkg.__file__)
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("no oracle", "") or f == "README.md", (dp, f)
+                assert "host_harness" not in src

@@ -131,8 +131,8 @@ def cpu_port_rate(sample_envs, steps_per_call, calls, threads, warm_calls=1):
 def cpu_baseline_block(target_seconds=12.0):
     threads = os.cpu_count() or 1
     sample_envs = 8192
-    rate, dt, _ = cpu_port_rate(sample_envs, 20, 1, threads, warm_calls=1)  # calibrate
-    steps = max(20, min(2000, int(target_seconds * rate / 8 / sample_envs)))
+    rate, dt, _ = cpu_port_rate(sample_envs, 200, 1, threads, warm_calls=1)  # calibrate
+    steps = max(200, min(200000, int(target_seconds * rate / 8 / sample_envs)))
     rate, dt, env_steps = cpu_port_rate(sample_envs, steps, 1, threads, warm_calls=0)
     return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": "%d envs x %d lockstep steps (%.1f s) of the same workload, C port of the reference "

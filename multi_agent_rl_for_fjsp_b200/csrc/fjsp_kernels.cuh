@@ -143,17 +143,18 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
     }
     mbar_wait(bar, 0);
 
-    SmemColumn s{s_state + tid};
-    StepOut out;
-    out.obs = s_obs + tid * FJSP_OBS_DIM;
-    step_env<true>(s, P, a, out);
-    if (A.autoreset && (out.flags & 0x00ffffffu)) {
-        const u32 episode = s.ld(W_EPISODE) + 1u;
-        reset_env(s, P, valid ? A.num_orders : 0, nullptr, A.seed, (uint64_t)(A.first_env + env), episode);
-        observe_env(s, P, out.obs, out.mask);
-        out.flags |= 1u << 24;
-    }
+    // padding lanes of a ragged last tile are inert: their columns travel through shared memory unchanged
     if (valid) {
+        SmemColumn s{s_state + tid};
+        StepOut out;
+        out.obs = s_obs + tid * FJSP_OBS_DIM;
+        step_env<true>(s, P, a, out);
+        if (A.autoreset && (out.flags & 0x00ffffffu)) {
+            const u32 episode = s.ld(W_EPISODE) + 1u;
+            reset_env(s, P, A.num_orders, nullptr, A.seed, (uint64_t)(A.first_env + env), episode);
+            observe_env(s, P, out.obs, out.mask);
+            out.flags |= 1u << 24;
+        }
         uint4* m4 = reinterpret_cast<uint4*>(A.masks + env * FJSP_MASK_DIM);
         m4[0] = make_uint4(out.mask[0], out.mask[1], out.mask[2], out.mask[3]);
         m4[1] = make_uint4(out.mask[4], out.mask[5], out.mask[6], out.mask[7]);

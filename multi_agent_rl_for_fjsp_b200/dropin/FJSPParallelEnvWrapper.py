@@ -1,0 +1,289 @@
+"""Drop-in ``FJSPParallelEnvWrapper`` module: ``from FJSPParallelEnvWrapper import FJSPParallelEnv`` (train.py:20).
+
+Same PettingZoo-style surface as the reference class (/root/reference/FJSPParallelEnvWrapper.py:9-136) — dict
+``reset()`` / ``step(actions)``, ``possible_agents`` / ``agents``, ``observation_space`` / ``action_space``, ``state()``,
+``render()``, ``unwrapped.simulation`` — but the simulation is env 0 of a ``BatchedFJSPEnv`` of size 1: every
+``step`` is one launch of the sm_100a step kernel through the C ABI.  There is no Python or CPU simulation here.
+
+Order generation in ``reset`` performs the reference's three draws per order from the global legacy NumPy RNG
+(FJSPSimulation.py:107-112), so ``np.random.seed(s)`` / ``reset(seed=s)`` produce the reference's order stream.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from multi_agent_rl_for_fjsp_b200 import abi, spaces as _spaces
+from multi_agent_rl_for_fjsp_b200.env import AGENT_IDS, MASK_OFFSETS, N_ACTIONS, BatchedFJSPEnv
+
+try:  # the reference subclasses pettingzoo.ParallelEnv; keep isinstance() working when it is installed
+    from pettingzoo import ParallelEnv as _Base  # type: ignore
+except Exception:  # noqa: BLE001
+    class _Base:  # minimal stand-in (see compat/pettingzoo)
+        @property
+        def unwrapped(self):
+            return self
+
+# reference CONFIG defaults (constants.py:20-32) that the facade itself needs
+_DEFAULTS = dict(num_trays=1000, tray_capacity=5, grid_rows=4, grid_cols=6, agv_speed=1, step_size=10, max_episode_steps=200)
+
+_PS_KEYS = ["current_tray_color", "current_tray_count", "current_tray_type", "next_product_color", "next_product_type",
+            "order_size", "products_remaining"]
+_AGV_KEYS = ["big_machine_busy", "big_machine_ready", "carrying_tray", "pickup_ready_trays", None, None,
+             "small_machine_busy", "small_machine_ready", "storage_tray_count", "tray_needs_packaging",
+             "tray_needs_processing", "tray_product_count", "tray_type"]
+_RESULT_KEYS = {
+    "pickup_station": [("success", 0x01), ("product_loaded", 0x02), ("tray_completed", 0x04), ("idle_with_orders", 0x08)],
+    "agv": [("success", 0x01), ("invalid_action", 0x02), ("moved", 0x04), ("pickup_success", 0x08), ("drop_success", 0x10),
+            ("delivered_to_packaging", 0x20)],
+    "machine": [("success", 0x01), ("started_processing", 0x02), ("completed_processing", 0x04), ("idle_with_queue", 0x08)],
+    "packaging": [("success", 0x01), ("started_packaging", 0x02), ("completed_packaging", 0x04), ("idle_with_queue", 0x08)],
+}
+
+
+def draw_reference_orders(n):
+    """The reference's three draws per order from the GLOBAL legacy NumPy RNG, in its order
+    (FJSPSimulation.py:107-112): randint(1, 10), choice over the 3 product types, choice over the 3 colours.
+    ``np.random.choice`` over a 3-element list consumes the stream identically for enum members and ints."""
+    out = []
+    for _ in range(n):
+        k = int(np.random.randint(1, 10))
+        t = int(np.random.choice([1, 2, 3]))
+        c = int(np.random.choice([1, 2, 3]))
+        out.append((k, t, c))
+    return out
+
+
+class _Obj:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class SimulationView:
+    """Read-only stand-in for ``env.unwrapped.simulation`` built lazily from the exported canonical state.
+
+    Provides what a2c.py reads: ``current_step``, ``get_order_progress()`` (a2c.py:353-354), ``agv.position`` /
+    ``agv.carrying_tray`` (a2c.py:298-306), ``total_products_packaged``, ``completed_orders``, ``orders``."""
+
+    def __init__(self, facade):
+        self._f = facade
+
+    def _s(self):
+        return self._f._canon()
+
+    @property
+    def current_step(self):
+        return int(self._s()["current_step"])
+
+    @property
+    def total_products_packaged(self):
+        return int(self._s()["total_products_packaged"])
+
+    @property
+    def config(self):
+        return self._f.config
+
+    @property
+    def orders(self):
+        s, out = self._s(), []
+        for o in range(int(s["num_orders"])):
+            n, t, c = self._f._orders[o]
+            prods = [_Obj(id=o * 100 + i, order_id=o, product_type=_Obj(name=("", "SMALL", "MEDIUM", "BIG")[t], value=t),
+                          packaging_color=_Obj(name=("", "RED", "BLUE", "GREEN")[c], value=c),
+                          is_processed=bool((int(s["processed_mask"][o]) >> i) & 1),
+                          is_packaged=bool((int(s["packaged_mask"][o]) >> i) & 1)) for i in range(n)]
+            cs = int(s["order_completion_step"][o])
+            out.append(_Obj(id=o, products=prods, is_complete=bool(s["order_complete"][o]),
+                            completion_time=None if cs < 0 else float((cs + 1) * self._f.config["step_size"])))
+        return out
+
+    @property
+    def completed_orders(self):
+        done = [o for o in self.orders if o.is_complete]
+        return sorted(done, key=lambda o: (o.completion_time, o.id))
+
+    @property
+    def agv(self):
+        s = self._s()
+        carry = int(s["agv_carry"])
+        tray = None
+        if carry >= 0:
+            tray = _Obj(id=carry & 0xffff, order_id=(carry >> 16) & 63, first=(carry >> 22) & 15, count=(carry >> 26) & 7)
+        return _Obj(position=(int(s["agv_row"]), int(s["agv_col"])), carrying_tray=tray, is_moving=bool(s["agv_is_moving"]))
+
+    def get_order_progress(self):  # FJSPSimulation.py:260-284
+        orders = self.orders
+        return {
+            "total_orders": len(orders),
+            "completed_orders": sum(1 for o in orders if o.is_complete),
+            "total_products": sum(len(o.products) for o in orders),
+            "products_processed": sum(sum(1 for p in o.products if p.is_processed) for o in orders),
+            "products_packaged": self.total_products_packaged,
+            "orders_detail": [{"order_id": o.id, "total_products": len(o.products),
+                               "processed": sum(1 for p in o.products if p.is_processed),
+                               "packaged": sum(1 for p in o.products if p.is_packaged),
+                               "is_complete": o.is_complete} for o in orders],
+        }
+
+
+class FJSPParallelEnv(_Base):
+    metadata = {"name": "fjsp_v1", "render_modes": ["human", "rgb_array"], "is_parallelizable": True}
+
+    def __init__(self, config=None, render_mode=None, device="cuda:0"):
+        self.config = dict(_DEFAULTS)
+        if config:
+            self.config.update(config)
+        self.render_mode = render_mode
+        self._env = BatchedFJSPEnv(1, config=abi.config_from_dict(self.config), device=device, autoreset=False,
+                                   with_infos=True)
+        self.possible_agents = list(AGENT_IDS)
+        self.agents = self.possible_agents.copy()
+        self._orders = []
+        self._cache = None
+        self.simulation = SimulationView(self)
+        self._obs_spaces = {
+            "pickup_station": _spaces.pickup_station(),
+            "agv": _spaces.agv(self.config["grid_rows"], self.config["grid_cols"], self.config["tray_capacity"]),
+            "small_machine": _spaces.machine(), "big_machine": _spaces.machine(),
+        }
+        for a in AGENT_IDS[4:]:
+            self._obs_spaces[a] = _spaces.packaging()
+        self._env.reset(orders=self._order_table())  # no orders (and no RNG draws) until reset(), as in the reference
+
+    # ---- spaces
+    def observation_space(self, agent):
+        return self._obs_spaces[agent]
+
+    def action_space(self, agent):
+        return _spaces.action_space(agent)
+
+    # ---- reset / step
+    def _gen_orders(self, n):
+        self._orders = draw_reference_orders(n)
+
+    def _order_table(self):
+        if len(self._orders) > abi.MAX_ORDERS:
+            raise ValueError("num_orders > %d is not supported by the packed state" % abi.MAX_ORDERS)
+        tab = np.zeros((1, abi.MAX_ORDERS), dtype=np.uint32)
+        for i, (k, t, c) in enumerate(self._orders):
+            tab[0, i] = abi.order_rec(k, t, c)
+        self._env.num_orders = len(self._orders)
+        return tab
+
+    def reset(self, seed=None, options=None):
+        self.agents = self.possible_agents.copy()
+        num_orders = options.get("num_orders") if options else None
+        if seed is not None:
+            np.random.seed(seed)
+        self._gen_orders(num_orders if num_orders is not None else 30)
+        obs, masks = self._env.reset(orders=self._order_table())
+        self._cache = None
+        observations = self._obs_dicts(obs[0].cpu().numpy(), masks[0].cpu().numpy())
+        return observations, {a: {} for a in self.possible_agents}
+
+    def step(self, actions):
+        a = np.zeros((1, 8), dtype=np.uint8)
+        present = []
+        for i, aid in enumerate(AGENT_IDS):
+            if aid in actions:
+                v = int(actions[aid])
+                # out-of-range actions: AGV -> invalid_action (AGVAgent.py:249-250), others -> silently nothing
+                a[0, i] = v if 0 <= v < 255 else 255
+                present.append(aid)
+            # a missing agent is not executed and is rewarded as action 0 (FJSPSimulation.py:172-174,201):
+            # for every agent action 0 has exactly that effect, except that its idle penalty must not apply.
+        e = self._env
+        obs, rew, term, trunc, masks = e.step(torch.from_numpy(a))
+        self._cache = None
+        out = torch.cat([obs[0], rew[0], e.flags[0].float(), e.infos[0].float(), e.results[0].float(),
+                         masks[0].float()]).cpu().numpy()
+        o, r = out[:38], out[38:46]
+        flags, infos, results, m = out[46:50].astype(np.int64), out[50:54].astype(np.int64), out[54:62].astype(np.int64), out[62:94]
+        observations = self._obs_dicts(o, m.astype(np.int8))
+        rewards = {aid: float(r[i]) for i, aid in enumerate(AGENT_IDS)}
+        for i, aid in enumerate(AGENT_IDS):
+            if aid not in actions:  # undo the idle penalty of the implicit action 0
+                res = int(results[i])
+                if aid == "pickup_station" and res & 0x08:
+                    rewards[aid] += 1.0
+                elif aid in ("small_machine", "big_machine") and res & 0x08:
+                    rewards[aid] += 2.0
+                elif aid.startswith("packaging") and res & 0x08:
+                    rewards[aid] += 1.0
+                elif aid == "agv" and res & 0x02:  # implicit IDLE while moving is not an invalid action
+                    rewards[aid] += 5.0
+        if flags[2]:
+            raise ValueError("list.remove(x): x not in list  [packaging START while requests were still waiting; "
+                             "the reference raises here too (SURVEY R-PKG-cap-b)]")
+        terminated, truncated = bool(flags[0]), bool(flags[1])
+        terminations = {aid: terminated for aid in AGENT_IDS}
+        truncations = {aid: truncated for aid in AGENT_IDS}
+        sim_time = float(int(infos[0]) * self.config["step_size"])
+        infos_d = {}
+        for i, aid in enumerate(AGENT_IDS):
+            kind = aid if aid in ("pickup_station", "agv") else ("machine" if "machine" in aid else "packaging")
+            if aid in actions:
+                ar = {"action": int(actions[aid])}
+                ar.update({k: bool(int(results[i]) & bit) for k, bit in _RESULT_KEYS[kind]})
+            else:
+                ar = {}
+            infos_d[aid] = {"action_result": ar, "sim_time": sim_time, "orders_completed": int(infos[1]),
+                            "total_products_packaged": int(infos[2])}
+        if terminated or truncated:
+            self.agents = []
+        return observations, rewards, terminations, truncations, infos_d
+
+    # ---- observation dicts with the reference's dtypes (AGVAgent.py:60-75, MachineAgent.py:64-69, ...)
+    def _obs_dicts(self, o, m):
+        i32 = lambda v: np.array(int(v), dtype=np.int32)  # noqa: E731
+        i8 = lambda v: np.array(int(v), dtype=np.int8)  # noqa: E731
+        obs = {}
+        ps = {k: i32(o[i]) for i, k in enumerate(_PS_KEYS)}
+        ps["action_mask"] = m[0:3].astype(np.int8)
+        obs["pickup_station"] = ps
+        agv = {k: i32(o[7 + i]) for i, k in enumerate(_AGV_KEYS) if k is not None}
+        agv["position"] = np.array([int(o[11]), int(o[12])], dtype=np.int32)
+        agv["action_mask"] = m[3:11].astype(np.int8)
+        obs["agv"] = agv
+        for j, aid in enumerate(AGENT_IDS[2:]):
+            b = 20 + 3 * j
+            obs[aid] = {"is_busy": i8(o[b]), "processing_progress": np.array(o[b + 1], dtype=np.float32),
+                        "queue_length": i8(o[b + 2]),
+                        "action_mask": m[MASK_OFFSETS[2 + j]:MASK_OFFSETS[2 + j] + 3].astype(np.int8)}
+        return obs
+
+    def _canon(self):
+        if self._cache is None:
+            self._cache = self._env.export_state(0)
+        return self._cache
+
+    # ---- misc surface
+    def render(self):
+        if self.render_mode == "human":
+            s = self._canon()
+            print("Step %d | orders %d/%d | packaged %d | AGV (%d,%d) carrying=%s" % (
+                s["current_step"], s["completed_orders"], s["num_orders"], s["total_products_packaged"], s["agv_row"],
+                s["agv_col"], "yes" if s["agv_carry"] >= 0 else "no"))
+        elif self.render_mode == "rgb_array":
+            grid = np.ones((self.config["grid_rows"], self.config["grid_cols"], 3), dtype=np.uint8) * 255
+            s = self._canon()
+            grid[int(s["agv_row"]), int(s["agv_col"])] = [0, 0, 0]
+            return grid
+
+    def close(self):
+        self._env.close()
+
+    def state(self):
+        """71-float64 global state (FJSPParallelEnvWrapper.py:119-136): per agent sorted keys incl. action_mask,
+        then [len(orders), len(completed_orders), total_products_packaged, env.now]."""
+        e = self._env
+        o, m = e.obs[0].cpu().numpy(), e.masks[0].cpu().numpy()
+        d = self._obs_dicts(o, m)
+        parts = []
+        for aid in self.possible_agents:
+            for key in sorted(d[aid].keys()):
+                parts.append(np.asarray(d[aid][key]).flatten())
+        s = self._canon()
+        parts.append(np.array([s["num_orders"], s["completed_orders"], s["total_products_packaged"],
+                               float(int(s["current_step"]) * self.config["step_size"])], dtype=np.float32))
+        return np.concatenate(parts)

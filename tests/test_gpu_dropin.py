@@ -1,0 +1,55 @@
+"""The drop-in facade (dropin/FJSPParallelEnvWrapper.py) on the real device, against the oracle, driven the way
+a2c.py drives the reference env (reset(options), `while env.agents:` with dict actions, unwrapped.simulation)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import canon
+from oracle.fjsp_oracle import OracleEnv
+
+pytestmark = pytest.mark.gpu
+DROPIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "multi_agent_rl_for_fjsp_b200", "dropin")
+
+
+@pytest.fixture
+def FJSPParallelEnv(monkeypatch):
+    monkeypatch.syspath_prepend(DROPIN)
+    sys.modules.pop("FJSPParallelEnvWrapper", None)
+    mod = importlib.import_module("FJSPParallelEnvWrapper")
+    yield mod.FJSPParallelEnv
+    sys.modules.pop("FJSPParallelEnvWrapper", None)
+
+
+def test_dict_api_episode_matches_oracle(FJSPParallelEnv):
+    env = FJSPParallelEnv()
+    rs = np.random.RandomState(9)
+    for ep, no in enumerate((25, 5)):
+        obs, infos = env.reset(seed=40 + ep, options={"num_orders": no})
+        orc = OracleEnv()
+        o_o, m_o = orc.reset(env._orders)
+        of, mf = canon.flatten_reference_obs(obs)
+        assert np.array_equal(of, o_o) and np.array_equal(mf, m_o)
+        steps = 0
+        while env.agents:
+            a = np.array([rs.randint(n) for n in (3, 8, 3, 3, 3, 3, 3, 3)])
+            obs, rew, te, tr, inf = env.step({aid: int(a[i]) for i, aid in enumerate(env.possible_agents)})
+            o_o, m_o, r_o, f_o = orc.step(a)
+            of, mf = canon.flatten_reference_obs(obs)
+            assert np.array_equal(of, o_o) and np.array_equal(mf, m_o)
+            assert np.allclose([rew[x] for x in env.possible_agents], r_o, rtol=1e-6, atol=0)
+            assert te["agv"] == bool(f_o[0]) and tr["agv"] == bool(f_o[1])
+            assert inf["agv"]["sim_time"] == 10.0 * (steps + 1)
+            steps += 1
+        sim = env.unwrapped.simulation
+        assert sim.current_step == steps == 201
+        s = orc.export()
+        prog = sim.get_order_progress()
+        assert prog["completed_orders"] == int(s["completed_orders"]) and prog["total_orders"] == no
+        assert prog["products_packaged"] == int(s["total_products_packaged"])
+        assert sim.agv.position == (int(s["agv_row"]), int(s["agv_col"]))
+        assert (sim.agv.carrying_tray is not None) == (int(s["agv_carry"]) >= 0)
+    assert env.state().shape == (71,)
+    env.close()

@@ -49,57 +49,82 @@ def workload_name(envs):
 
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons DURING the timed region: NVML polled from a thread every ~2 ms
+    (nvidia_ml_py), falling back to one `nvidia-smi` query loop when NVML is not importable."""
+
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.gpu, self._stop, self.mode = [], gpu_index, False, None
+        self.max_mhz = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.mode = "nvml"
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.mode = None
+        try:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            self.mode = "smi"
+            self.t = threading.Thread(target=self._read_smi, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.mode = None
 
-    def _read(self):
+    def _poll_nvml(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                clk = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.time(), clk, {n for n, b in self.REASONS if bits & b}))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _read_smi(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+            f = [x.strip() for x in line.split(",")]
+            try:
+                clk, self.max_mhz = float(f[0]), float(f[1])
+            except Exception:
+                continue
+            names = ("hw_slowdown", "sw_thermal_slowdown", "hw_thermal_slowdown", "sw_power_cap")
+            self.rows.append((time.time(), clk, {n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")}))
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for ts, line in self.rows:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                clk, mxc = float(f[1]), float(f[2])
-            except ValueError:
-                continue
-            mx = mxc
-            if t0 - 0.05 <= ts <= t1 + 0.15:
-                sm.append(clk)
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        if not sm:  # region shorter than one sample: use everything we saw
-            for ts, line in self.rows:
-                f = [x.strip() for x in line.split(",")]
-                try:
-                    sm.append(float(f[1]))
-                except Exception:
-                    pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self._stop = True
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        if self.mode == "smi":
+            time.sleep(0.05)
+            self.proc.terminate()
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        if not inside:  # region shorter than the sampling period: take the samples closest to it
+            inside = sorted(self.rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t1)))[:3]
+        sm = sorted(r[1] for r in inside)
+        reasons = set()
+        for r in inside:
+            reasons |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+                "samples": len(inside), "source": self.mode}
 
 
 def measured_peak():
@@ -220,7 +245,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
+        time.sleep(0.05)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     wall0 = time.time()

@@ -1,0 +1,282 @@
+"""Batched CTDE multi-agent A2C on the tensor API (BASELINE.json configs[2] and [4]).
+
+The caller of the hot path, rebuilt for N-env lockstep rollouts.  Same algorithm as the reference's trainer
+(/root/reference/a2c.py:24-116,168-252,647-731, networks.py:22-61, transition_memory.py:45-105), per-sample loops replaced
+by batched tensor ops:
+
+  * 8 actors (obs_i -> 256 -> 256 -> A_i, softmax) and one centralised critic (38 -> 256 -> 256 -> 128 -> 1),
+    654,366 fp32 parameters, nn.Linear default init.  The six 3->256->256->3 actors run as one ``torch.bmm`` chain.
+  * action selection: probs * action_mask, renormalise, uniform-over-valid fallback, Categorical sample (a2c.py:217-247);
+  * returns and GAE per agent with the SHARED critic value, bootstrap V(s_T) when a rollout is cut, 0.0 when the episode
+    ended — including time-limit truncation (a2c.py:325-332,357; transition_memory.py:83-105);
+  * actor loss  -(norm_adv * logp).mean() - entropy_coef * H(unmasked probs + 1e-10), advantages normalised per agent
+    with the unbiased std (a2c.py:694-731); critic loss = MSE of the value against every agent's returns (a2c.py:675-692);
+  * clip_grad_norm 0.5 per network, one Adam per network (lr 3e-4 actors / 1e-3 critic).
+
+GEMMs are library calls (cuBLAS through torch): at these sizes they are launch-latency bound, not tensor-core bound.
+Data parallelism: every rank owns an env shard; ONE flat all-reduce (654,366 fp32 = 2.62 MB, NCCL over NVLink) of the
+gradients per update, plus one tiny all-reduce of the advantage moments so normalisation is over the GLOBAL batch.
+The env step is one kernel launch per step that writes observations straight into the rollout buffer (``step_into``).
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from .env import MASK_OFFSETS, N_ACTIONS, OBS_SLICES
+
+HID = 256
+
+
+def _linear_init(out_f, in_f, lead=(), device=None, gen=None):
+    """nn.Linear's default init (kaiming_uniform(a=sqrt(5)) -> U(-1/sqrt(in), 1/sqrt(in)) for weight and bias)."""
+    bound = 1.0 / math.sqrt(in_f)
+    w = (torch.rand(*lead, in_f, out_f, device=device, generator=gen) * 2 - 1) * bound  # stored [in, out] for x @ w
+    b = (torch.rand(*lead, 1, out_f, device=device, generator=gen) * 2 - 1) * bound
+    return torch.nn.Parameter(w), torch.nn.Parameter(b)
+
+
+class ActorCritic(torch.nn.Module):
+    """The reference's 8 ActorNetworks + CentralizedCriticNetwork as batched parameter groups."""
+
+    def __init__(self, device=None, seed: int | None = None):
+        super().__init__()
+        gen = None
+        if seed is not None:
+            gen = torch.Generator(device=device)
+            gen.manual_seed(seed)
+        mk = lambda o, i, lead=(): _linear_init(o, i, lead, device, gen)  # noqa: E731
+        # pickup_station (7 -> 3), agv (13 -> 8): networks.py:22-38
+        self.ps = torch.nn.ParameterList([p for pair in (mk(HID, 7), mk(HID, HID), mk(3, HID)) for p in pair])
+        self.agv = torch.nn.ParameterList([p for pair in (mk(HID, 13), mk(HID, HID), mk(8, HID)) for p in pair])
+        # small/big machine + 4 packaging stations: six identical 3 -> 256 -> 256 -> 3 actors, one bmm chain
+        self.six = torch.nn.ParameterList([p for pair in (mk(HID, 3, (6,)), mk(HID, HID, (6,)), mk(3, HID, (6,))) for p in pair])
+        # centralised critic 38 -> 256 -> 256 -> 128 -> 1: networks.py:41-61
+        self.critic = torch.nn.ParameterList(
+            [p for pair in (mk(HID, 38), mk(HID, HID), mk(HID // 2, HID), mk(1, HID // 2)) for p in pair])
+
+    @staticmethod
+    def _mlp(x, params, last_act=None):
+        n = len(params) // 2
+        for i in range(n):
+            w, b = params[2 * i], params[2 * i + 1]
+            x = torch.baddbmm(b, x, w) if w.dim() == 3 else torch.addmm(b[0], x, w)
+            if i < n - 1:
+                x = torch.relu(x)
+        return x
+
+    def actor_probs(self, obs):
+        """obs [B,38] -> list of 8 prob tensors (softmax over each agent's actions), unmasked."""
+        p_ps = torch.softmax(self._mlp(obs[:, 0:7], self.ps), dim=-1)
+        p_agv = torch.softmax(self._mlp(obs[:, 7:20], self.agv), dim=-1)
+        x6 = obs[:, 20:38].reshape(-1, 6, 3).transpose(0, 1)  # [6,B,3]
+        p_six = torch.softmax(self._mlp(x6, self.six), dim=-1)  # [6,B,3]
+        return [p_ps, p_agv] + [p_six[i] for i in range(6)]
+
+    def probs32(self, obs):
+        """[B,32] layout of the env's mask block (3 | 8 | 6x3 | 3 zero pad)."""
+        pr = self.actor_probs(obs)
+        pad = torch.zeros(obs.shape[0], 3, device=obs.device, dtype=obs.dtype)
+        return torch.cat(pr + [pad], dim=1)
+
+    def value(self, obs):
+        return self._mlp(obs, self.critic).squeeze(-1)
+
+    def networks(self):
+        """(name, parameter list, per-agent leading dim or None) for per-network clipping / optimisers."""
+        return [("pickup_station", list(self.ps), None), ("agv", list(self.agv), None), ("six", list(self.six), 6),
+                ("critic", list(self.critic), None)]
+
+    def num_parameters(self):
+        return sum(p.numel() for p in self.parameters())
+
+
+_SEG = [(MASK_OFFSETS[i], N_ACTIONS[i]) for i in range(8)]
+
+
+def masked_policy(probs32, masks):
+    """probs * mask, renormalised per agent; uniform over valid actions when the masked mass is 0 (a2c.py:217-231).
+    Returns q [B,32] with each agent's segment summing to 1."""
+    m = masks.to(probs32.dtype)
+    pm = probs32 * m
+    out = torch.zeros_like(pm)
+    for off, n in _SEG:
+        seg, mseg = pm[:, off:off + n], m[:, off:off + n]
+        s = seg.sum(-1, keepdim=True)
+        uni = mseg / mseg.sum(-1, keepdim=True).clamp_min(1.0)
+        out[:, off:off + n] = torch.where(s > 0, seg / s.clamp_min(1e-38), uni)
+    return out
+
+
+def sample_actions(q, generator=None):
+    """Categorical sample per agent from q [B,32] -> uint8 [B,8] (inverse CDF on one uniform per agent)."""
+    B = q.shape[0]
+    u = torch.rand(B, 8, device=q.device, generator=generator)
+    acts = torch.empty(B, 8, dtype=torch.uint8, device=q.device)
+    for i, (off, n) in enumerate(_SEG):
+        cdf = q[:, off:off + n].cumsum(-1)
+        a = (u[:, i:i + 1] * cdf[:, -1:] >= cdf).sum(-1).clamp_max(n - 1)
+        # never pick a zero-probability action because of rounding at the end of the cdf
+        valid = q[:, off:off + n] > 0
+        a = torch.where(valid.gather(1, a[:, None])[:, 0], a, valid.float().argmax(-1))
+        acts[:, i] = a.to(torch.uint8)
+    return acts
+
+
+def log_prob_of(q, actions):
+    """log q[a] per agent, with Categorical's probability clamp (torch.distributions: eps = finfo.eps)."""
+    eps = torch.finfo(q.dtype).eps
+    idx = actions.long() + torch.tensor([o for o, _ in _SEG], device=q.device)
+    return torch.log(q.gather(1, idx).clamp(eps, 1 - eps))
+
+
+def entropy_unmasked(probs32):
+    """-sum p log(p + 1e-10) per agent over the UNMASKED probabilities (a2c.py:694-710) -> [B,8]."""
+    e = -(probs32 * torch.log(probs32 + 1e-10))
+    return torch.stack([e[:, off:off + n].sum(-1) for off, n in _SEG], dim=1)
+
+
+def gae_and_returns(rewards, values, dones, gamma, lamb):
+    """rewards [T,N,8], values [T+1,N] (values[T] = bootstrap), dones [T,N] bool -> (returns, advantages) [T,N,8].
+    Reverse scan of transition_memory.py:83-105; an episode end zeroes the bootstrap and restarts the accumulators."""
+    T = rewards.shape[0]
+    ret = values[T].unsqueeze(-1).expand_as(rewards[0]).clone()
+    nxt = values[T].unsqueeze(-1).expand_as(rewards[0]).clone()
+    gae = torch.zeros_like(rewards[0])
+    returns, advs = torch.empty_like(rewards), torch.empty_like(rewards)
+    for t in range(T - 1, -1, -1):
+        nd = (~dones[t]).to(rewards.dtype).unsqueeze(-1)
+        v = values[t].unsqueeze(-1)
+        ret = rewards[t] + gamma * ret * nd
+        td = rewards[t] + gamma * nxt * nd - v
+        gae = td + gamma * lamb * gae * nd
+        returns[t], advs[t] = ret, gae
+        nxt = v.expand_as(gae)
+    return returns, advs
+
+
+class BatchedA2C:
+    def __init__(self, env, rollout_len=32, gamma=0.99, lamb=0.95, lr_actor=3e-4, lr_critic=1e-3, entropy_coef=0.01,
+                 max_grad_norm=0.5, seed=0, global_adv_norm=True):
+        self.env, self.T = env, int(rollout_len)
+        self.gamma, self.lamb, self.entropy_coef, self.max_grad_norm = gamma, lamb, entropy_coef, max_grad_norm
+        self.device = env.device
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.global_adv_norm = global_adv_norm
+        self.net = ActorCritic(device=self.device, seed=seed)  # same seed on every rank -> identical replicas
+        groups = self.net.networks()
+        fused = self.device.type == "cuda"
+        self.opt = torch.optim.Adam(
+            [{"params": g[1], "lr": lr_critic if g[0] == "critic" else lr_actor} for g in groups], fused=fused)
+        N, T, dev = env.num_envs, self.T, self.device
+        self.obs = torch.zeros(T + 1, N, 38, device=dev)
+        self.masks = torch.zeros(T + 1, N, 32, dtype=torch.int8, device=dev)
+        self.actions = torch.zeros(T, N, 8, dtype=torch.uint8, device=dev)
+        self.rewards = torch.zeros(T, N, 8, device=dev)
+        self.flags = torch.zeros(T, N, 4, dtype=torch.uint8, device=dev)
+        self.values = torch.zeros(T + 1, N, device=dev)
+        self.gen = torch.Generator(device=dev)
+        self.gen.manual_seed(seed * 1000003 + (dist.get_rank() if self.world > 1 else 0))
+        self._flat = None
+        self.frames = 0
+        self.stats = {}
+        o, m = env.reset()
+        self.obs[0].copy_(o), self.masks[0].copy_(m)
+
+    # ------------------------------------------------------------------ rollout
+    @torch.no_grad()
+    def rollout(self):
+        T = self.T
+        for t in range(T):
+            o, m = self.obs[t], self.masks[t]
+            q = masked_policy(self.net.probs32(o), m)
+            self.values[t] = self.net.value(o)
+            self.actions[t] = sample_actions(q, self.gen)
+            # the step kernel writes the next observation / mask straight into the rollout buffer
+            self.env.step_into(self.actions[t], self.obs[t + 1], self.masks[t + 1], self.rewards[t], self.flags[t])
+        self.values[T] = self.net.value(self.obs[T])
+        self.frames += T * self.env.num_envs
+
+    # ------------------------------------------------------------------ update
+    def _allreduce_(self, t):
+        if self.world > 1:
+            dist.all_reduce(t)
+        return t
+
+    def update(self):
+        T, N = self.T, self.env.num_envs
+        dones = (self.flags[:, :, 0:3] != 0).any(-1)
+        returns, advs = gae_and_returns(self.rewards, self.values, dones, self.gamma, self.lamb)
+        B = T * N
+        obs, masks = self.obs[:T].reshape(B, 38), self.masks[:T].reshape(B, 32)
+        acts, returns, advs = self.actions.reshape(B, 8), returns.reshape(B, 8), advs.reshape(B, 8)
+        # advantage normalisation per agent over the (global) batch, unbiased std (a2c.py:727-729)
+        mom = torch.stack([torch.full((8,), float(B), device=self.device), advs.sum(0), (advs * advs).sum(0)])
+        if self.global_adv_norm:
+            self._allreduce_(mom)
+        cnt, mean = mom[0], mom[1] / mom[0]
+        var = (mom[2] - cnt * mean * mean) / (cnt - 1).clamp_min(1.0)
+        adv_n = (advs - mean) / (var.clamp_min(0).sqrt() + 1e-8)
+
+        probs = self.net.probs32(obs)
+        q = masked_policy(probs, masks)
+        logp = log_prob_of(q, acts)
+        ent = entropy_unmasked(probs).mean(0)
+        actor_loss = -(adv_n * logp).mean(0) - self.entropy_coef * ent  # [8], one loss per agent (separate networks)
+        v = self.net.value(obs)
+        critic_loss = F.mse_loss(v.unsqueeze(-1).expand_as(returns), returns)
+        self.opt.zero_grad(set_to_none=False)
+        (actor_loss.sum() + critic_loss).backward()
+        if self.world > 1:  # ONE flat all-reduce of all gradients (2.62 MB), then the mean over ranks
+            grads = [p.grad for p in self.net.parameters()]
+            flat = torch.cat([g.reshape(-1) for g in grads])
+            dist.all_reduce(flat)
+            flat /= self.world
+            off = 0
+            for g in grads:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+        self._clip()
+        self.opt.step()
+        self.stats = {"actor_loss": actor_loss.detach(), "critic_loss": critic_loss.detach(), "entropy": ent.detach()}
+
+    def _clip(self):
+        """clip_grad_norm_(max_grad_norm) per NETWORK: each of the 8 actors and the critic separately (a2c.py:668,686)."""
+        for _, params, lead in self.net.networks():
+            if lead is None:
+                torch.nn.utils.clip_grad_norm_(params, self.max_grad_norm)
+            else:
+                sq = sum((p.grad.reshape(lead, -1) ** 2).sum(-1) for p in params)
+                scale = (self.max_grad_norm / (sq.sqrt() + 1e-6)).clamp_max(1.0)
+                for p in params:
+                    p.grad.mul_(scale.view(lead, *([1] * (p.grad.dim() - 1))))
+
+    # ------------------------------------------------------------------ driver
+    def train(self, updates: int):
+        """`updates` x (rollout of T steps + one update).  Returns frames/s of this rank (device-timed when on CUDA)."""
+        cuda = self.device.type == "cuda"
+        if cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(self.device)
+            e0.record()
+        t0 = time.perf_counter()
+        f0 = self.frames
+        for _ in range(updates):
+            self.rollout()
+            self.update()
+            # next rollout continues from the last observation
+            self.obs[0].copy_(self.obs[self.T]), self.masks[0].copy_(self.masks[self.T])
+        if cuda:
+            e1.record()
+            torch.cuda.synchronize(self.device)
+            secs = e0.elapsed_time(e1) * 1e-3
+        else:
+            secs = time.perf_counter() - t0
+        return (self.frames - f0) / secs, secs
+
+    def mean_reward(self):
+        return float(self.rewards.sum(-1).mean())

@@ -136,6 +136,20 @@ class BatchedFJSPEnv:
         self._t += 1
         return self.obs, self.rewards, self.flags[:, 0], self.flags[:, 1], self.masks
 
+    def step_into(self, actions: torch.Tensor, obs: torch.Tensor, masks: torch.Tensor, rewards: torch.Tensor,
+                  flags: torch.Tensor):
+        """Same launch, but the kernel writes straight into caller-owned tensors (e.g. slices of a rollout buffer,
+        so the policy's input needs no copy).  Shapes/dtypes as the env's own output tensors; contiguous."""
+        n = self.num_envs
+        assert actions.dtype == torch.uint8 and actions.is_contiguous() and actions.shape == (n, 8)
+        assert obs.dtype == torch.float32 and obs.is_contiguous() and obs.shape == (n, OBS_DIM)
+        assert masks.dtype == torch.int8 and masks.is_contiguous() and masks.shape == (n, MASK_DIM)
+        assert rewards.dtype == torch.float32 and rewards.is_contiguous() and rewards.shape == (n, 8)
+        assert flags.dtype == torch.uint8 and flags.is_contiguous() and flags.shape == (n, 4)
+        abi.check(self._L.fjsp_step(self._h, _ptr(actions), _ptr(obs), _ptr(masks), _ptr(rewards), _ptr(flags), None, None,
+                                    int(self.autoreset), self._stream()))
+        self._t += 1
+
     def random_actions(self, t: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
         """a_i ~ U{0..n_i-1} from the Philox action stream at time index t (default: the env's step counter)."""
         out = self._actions if out is None else out

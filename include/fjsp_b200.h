@@ -167,6 +167,21 @@ int fjsp_state_load(FjspHandle* h, const void* src_device, size_t bytes, void* s
 /* Number of kernels this library has launched since the handle was created. */
 int64_t fjsp_launch_count(const FjspHandle* h);
 
+/* ---- fused device ops for a batched A2C trainer, the caller of the path.  Stateless. ----
+ * fjsp_a2c_sample: per row, for each of the 8 agents: softmax(logits segment) * mask, renormalise (uniform over valid
+ *   actions when the masked mass is 0), Categorical sample, log-prob of the sample (a2c.py:214-247).
+ *   logits float[rows][32] and masks int8[rows][32] use the env's mask layout (3 | 8 | 6x3 | pad); actions u8[rows][8];
+ *   logp float[rows][8] or NULL.  Uniforms: Philox4x32-10(key=seed, counter=(first_row+row, t_lo, t_hi, 2|3)) with
+ *   t = counter[0] + t_off (counter: device u64 or NULL = 0), so a captured CUDA graph draws fresh numbers each replay.
+ * fjsp_a2c_gae: returns and GAE per (env, agent) over T steps with the shared critic value
+ *   (transition_memory.py:83-105): rewards float[T][N][8], values float[T+1][N] (values[T] = bootstrap),
+ *   flags u8[T][N][4] as written by fjsp_step (terminated|truncated|fault ends the episode: bootstrap 0). */
+int fjsp_a2c_sample(const float* logits, const int8_t* masks, uint8_t* actions, float* logp, int64_t rows, int64_t first_row,
+                    uint64_t seed, const uint64_t* counter, uint64_t t_off, void* stream);
+int fjsp_a2c_counter_add(uint64_t* counter, uint64_t inc, void* stream);
+int fjsp_a2c_gae(const float* rewards, const float* values, const uint8_t* flags, float* returns, float* advantages, int T, int64_t N,
+                 float gamma, float lamb, void* stream);
+
 /* action_result bit-fields (results[N][8]); reference dict keys in comments */
 #define FJSP_RES_SUCCESS 0x01        /* 'success' */
 #define FJSP_RES_PS_LOADED 0x02      /* 'product_loaded'    PickupStationAgent.py:197 */

@@ -69,19 +69,25 @@ class ActorCritic(torch.nn.Module):
                 x = torch.relu(x)
         return x
 
-    def actor_probs(self, obs):
-        """obs [B,38] -> list of 8 prob tensors (softmax over each agent's actions), unmasked."""
-        p_ps = torch.softmax(self._mlp(obs[:, 0:7], self.ps), dim=-1)
-        p_agv = torch.softmax(self._mlp(obs[:, 7:20], self.agv), dim=-1)
+    def actor_logits(self, obs):
+        """obs [B,38] -> (pickup [B,3], agv [B,8], six [6,B,3]) pre-softmax outputs of the 8 actors."""
+        z_ps = self._mlp(obs[:, 0:7], self.ps)
+        z_agv = self._mlp(obs[:, 7:20], self.agv)
         x6 = obs[:, 20:38].reshape(-1, 6, 3).transpose(0, 1)  # [6,B,3]
-        p_six = torch.softmax(self._mlp(x6, self.six), dim=-1)  # [6,B,3]
-        return [p_ps, p_agv] + [p_six[i] for i in range(6)]
+        return z_ps, z_agv, self._mlp(x6, self.six)
+
+    def logits32(self, obs):
+        """Pre-softmax logits in the [B,32] layout of the env's mask block (3 | 8 | 6x3 | 3 zero pad)."""
+        z_ps, z_agv, z6 = self.actor_logits(obs)
+        pad = torch.zeros(obs.shape[0], 3, device=obs.device, dtype=obs.dtype)
+        return torch.cat([z_ps, z_agv, z6.transpose(0, 1).reshape(-1, 18), pad], dim=1).contiguous()
 
     def probs32(self, obs):
-        """[B,32] layout of the env's mask block (3 | 8 | 6x3 | 3 zero pad)."""
-        pr = self.actor_probs(obs)
+        """Softmax per agent (networks.py:33), same layout."""
+        z_ps, z_agv, z6 = self.actor_logits(obs)
         pad = torch.zeros(obs.shape[0], 3, device=obs.device, dtype=obs.dtype)
-        return torch.cat(pr + [pad], dim=1)
+        return torch.cat([torch.softmax(z_ps, -1), torch.softmax(z_agv, -1),
+                          torch.softmax(z6, -1).transpose(0, 1).reshape(-1, 18), pad], dim=1)
 
     def value(self, obs):
         return self._mlp(obs, self.critic).squeeze(-1)
@@ -159,10 +165,17 @@ def gae_and_returns(rewards, values, dones, gamma, lamb):
     return returns, advs
 
 
+def _ptr(t):
+    import ctypes
+
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
 class BatchedA2C:
     def __init__(self, env, rollout_len=32, gamma=0.99, lamb=0.95, lr_actor=3e-4, lr_critic=1e-3, entropy_coef=0.01,
-                 max_grad_norm=0.5, seed=0, global_adv_norm=True):
+                 max_grad_norm=0.5, seed=0, global_adv_norm=True, use_cuda_graph=True, fused_ops=True):
         self.env, self.T = env, int(rollout_len)
+        self.seed = int(seed)
         self.gamma, self.lamb, self.entropy_coef, self.max_grad_norm = gamma, lamb, entropy_coef, max_grad_norm
         self.device = env.device
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
@@ -181,25 +194,68 @@ class BatchedA2C:
         self.values = torch.zeros(T + 1, N, device=dev)
         self.gen = torch.Generator(device=dev)
         self.gen.manual_seed(seed * 1000003 + (dist.get_rank() if self.world > 1 else 0))
-        self._flat = None
+        # fused CUDA ops (libfjsp_b200.so: fjsp_a2c_sample / fjsp_a2c_gae) and CUDA-graph replay of the rollout
+        self.fused = bool(fused_ops) and self.device.type == "cuda"
+        self.use_graph = bool(use_cuda_graph) and self.fused
+        self._graph = None
+        if self.fused:
+            from . import abi
+
+            self._L = abi.lib()
+            self._ctr = torch.zeros(1, dtype=torch.int64, device=dev)  # Philox time counter, advanced on the device
+            self._ret = torch.zeros(T, N, 8, device=dev)
+            self._adv = torch.zeros(T, N, 8, device=dev)
         self.frames = 0
         self.stats = {}
         o, m = env.reset()
         self.obs[0].copy_(o), self.masks[0].copy_(m)
 
     # ------------------------------------------------------------------ rollout
-    @torch.no_grad()
-    def rollout(self):
-        T = self.T
+    def _stream(self):
+        import ctypes
+
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _rollout_steps(self):
+        """T x (policy forward, masked Categorical sample, ONE env-step launch).  Static buffers: capturable."""
+        T, env = self.T, self.env
         for t in range(T):
             o, m = self.obs[t], self.masks[t]
-            q = masked_policy(self.net.probs32(o), m)
-            self.values[t] = self.net.value(o)
-            self.actions[t] = sample_actions(q, self.gen)
+            self.values[t].copy_(self.net.value(o))
+            if self.fused:
+                z = self.net.logits32(o)
+                rc = self._L.fjsp_a2c_sample(_ptr(z), _ptr(m), _ptr(self.actions[t]), None, env.num_envs, env.first_env,
+                                             self.seed, _ptr(self._ctr), t, self._stream())
+                assert rc == 0, self._L.fjsp_last_error()
+            else:
+                q = masked_policy(self.net.probs32(o), m)
+                self.actions[t] = sample_actions(q, self.gen)
             # the step kernel writes the next observation / mask straight into the rollout buffer
-            self.env.step_into(self.actions[t], self.obs[t + 1], self.masks[t + 1], self.rewards[t], self.flags[t])
-        self.values[T] = self.net.value(self.obs[T])
-        self.frames += T * self.env.num_envs
+            env.step_into(self.actions[t], self.obs[t + 1], self.masks[t + 1], self.rewards[t], self.flags[t])
+        self.values[T].copy_(self.net.value(self.obs[T]))
+        if self.fused:
+            rc = self._L.fjsp_a2c_counter_add(_ptr(self._ctr), T, self._stream())
+            assert rc == 0
+
+    @torch.no_grad()
+    def rollout(self):
+        if self.use_graph:
+            if self._graph is None:
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):  # warm-up on a side stream (cuBLAS workspaces, lazy init) before capture
+                    self._rollout_steps()
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                torch.cuda.synchronize(self.device)
+                self.obs[0].copy_(self.obs[self.T]), self.masks[0].copy_(self.masks[self.T])
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph):
+                    self._rollout_steps()
+            else:
+                self._graph.replay()
+        else:
+            self._rollout_steps()
+        self.frames += self.T * self.env.num_envs
 
     # ------------------------------------------------------------------ update
     def _allreduce_(self, t):
@@ -209,8 +265,14 @@ class BatchedA2C:
 
     def update(self):
         T, N = self.T, self.env.num_envs
-        dones = (self.flags[:, :, 0:3] != 0).any(-1)
-        returns, advs = gae_and_returns(self.rewards, self.values, dones, self.gamma, self.lamb)
+        if self.fused:
+            rc = self._L.fjsp_a2c_gae(_ptr(self.rewards), _ptr(self.values), _ptr(self.flags), _ptr(self._ret), _ptr(self._adv),
+                                      T, N, self.gamma, self.lamb, self._stream())
+            assert rc == 0, self._L.fjsp_last_error()
+            returns, advs = self._ret, self._adv
+        else:
+            dones = (self.flags[:, :, 0:3] != 0).any(-1)
+            returns, advs = gae_and_returns(self.rewards, self.values, dones, self.gamma, self.lamb)
         B = T * N
         obs, masks = self.obs[:T].reshape(B, 38), self.masks[:T].reshape(B, 32)
         acts, returns, advs = self.actions.reshape(B, 8), returns.reshape(B, 8), advs.reshape(B, 8)

@@ -15,7 +15,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_PKG)
 SO_PATH = os.path.join(_PKG, "lib", "libfjsp_b200.so")
-SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("fjsp_api.cu", "fjsp_kernels.cuh", "fjsp_core.h", "fjsp_host.h")]
+SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("fjsp_api.cu", "fjsp_kernels.cuh", "fjsp_a2c.cuh", "fjsp_core.h", "fjsp_host.h")]
 HEADER = os.path.join(_REPO, "include", "fjsp_b200.h")
 
 NUM_AGENTS, OBS_DIM, MASK_DIM, FLAG_DIM, INFO_DIM, MAX_ORDERS = 8, 38, 32, 4, 4, 32
@@ -62,6 +62,7 @@ EXPORTS = [
     "fjsp_state_bytes", "fjsp_state_ptr", "fjsp_reset", "fjsp_step", "fjsp_step_host", "fjsp_random_actions",
     "fjsp_rollout_random", "fjsp_export_state", "fjsp_export_packed", "fjsp_launch_count",
     "fjsp_state_total_bytes", "fjsp_state_save", "fjsp_state_load",
+    "fjsp_a2c_sample", "fjsp_a2c_counter_add", "fjsp_a2c_gae",
 ]
 
 
@@ -118,6 +119,9 @@ def lib() -> C.CDLL:
     L.fjsp_state_total_bytes.restype, L.fjsp_state_total_bytes.argtypes = C.c_size_t, [vp]
     L.fjsp_state_save.argtypes = [vp, vp, C.c_size_t, vp]
     L.fjsp_state_load.argtypes = [vp, vp, C.c_size_t, vp]
+    L.fjsp_a2c_sample.argtypes = [vp, vp, vp, vp, i64, i64, u64, vp, u64, vp]
+    L.fjsp_a2c_counter_add.argtypes = [vp, u64, vp]
+    L.fjsp_a2c_gae.argtypes = [vp, vp, vp, vp, vp, C.c_int, i64, C.c_float, C.c_float, vp]
     L.fjsp_export_state.argtypes = [vp, i64, vp]
     L.fjsp_export_packed.argtypes = [vp, i64, vp]
     if L.fjsp_abi_version() != 1:

@@ -8,6 +8,7 @@
 
 #include "fjsp_host.h"
 #include "fjsp_kernels.cuh"
+#include "fjsp_a2c.cuh"
 
 using namespace fjsp;
 
@@ -254,6 +255,37 @@ int fjsp_export_state(FjspHandle* h, int64_t env, FjspCanonState* out) {
     u32 words[FJSP_STATE_WORDS];
     if (int rc = fjsp_export_packed(h, env, words)) return rc;
     export_canon(words, h->P, out);
+    return 0;
+}
+
+// ---- fused ops of the batched A2C trainer (stateless; run on the current device) ----
+int fjsp_a2c_sample(const float* logits, const int8_t* masks, uint8_t* actions, float* logp, int64_t rows, int64_t first_row,
+                    uint64_t seed, const uint64_t* counter, uint64_t t_off, void* stream) {
+    if (!logits || !masks || !actions) return fail("logits/masks/actions must be device pointers");
+    if ((reinterpret_cast<uintptr_t>(logits) & 15) || (reinterpret_cast<uintptr_t>(masks) & 15) ||
+        (reinterpret_cast<uintptr_t>(actions) & 7) || (logp && (reinterpret_cast<uintptr_t>(logp) & 15)))
+        return fail("alignment: logits/masks/logp 16 B, actions 8 B");
+    if (rows <= 0) return 0;
+    fjsp_policy_sample_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        logits, masks, actions, logp, rows, first_row, seed, reinterpret_cast<const unsigned long long*>(counter), t_off);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int fjsp_a2c_counter_add(uint64_t* counter, uint64_t inc, void* stream) {
+    if (!counter) return fail("counter is NULL");
+    fjsp_counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(counter), inc);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int fjsp_a2c_gae(const float* rewards, const float* values, const uint8_t* flags, float* returns, float* advantages, int T, int64_t N,
+                 float gamma, float lamb, void* stream) {
+    if (!rewards || !values || !flags || !returns || !advantages) return fail("NULL argument");
+    if (T <= 0 || N <= 0) return fail("T and N must be positive");
+    fjsp_gae_kernel<<<(unsigned)((N * 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rewards, values, flags, returns, advantages, T, N,
+                                                                                   gamma, lamb);
+    CK(cudaGetLastError());
     return 0;
 }
 

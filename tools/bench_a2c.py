@@ -1,0 +1,37 @@
+"""A2C frames/sec (BASELINE.json configs[2] / [4]): batched CTDE A2C on E envs per GPU, rollout length T.
+1 frame = 1 env step consumed by training (rollout + update amortised).  Run plain for 1 GPU or under torchrun.
+Prints one JSON line on rank 0."""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv, dist as fdist
+from multi_agent_rl_for_fjsp_b200.a2c_batched import BatchedA2C
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--envs", type=int, default=4096)
+ap.add_argument("--rollout", type=int, default=32)
+ap.add_argument("--updates", type=int, default=20)
+ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--num-orders", type=int, default=25)
+args = ap.parse_args()
+rank, local_rank, world = fdist.world_info()
+torch.cuda.set_device(local_rank)
+dev = torch.device("cuda", local_rank)
+fdist.init(device=dev)
+env = BatchedFJSPEnv(args.envs, device=dev, first_env=rank * args.envs, seed=11, num_orders=args.num_orders, autoreset=True)
+tr = BatchedA2C(env, rollout_len=args.rollout, seed=1)
+tr.train(args.warmup)
+l0 = env.launch_count
+fdist.barrier(dev)
+fps, secs = tr.train(args.updates)
+secs = fdist.max_over_ranks(secs, dev)
+frames = world * args.envs * args.rollout * args.updates
+if rank == 0:
+    print(json.dumps({"metric": "a2c_frames_per_sec", "value": frames / secs, "unit": "frames/s", "n_gpus": world,
+                      "envs_per_gpu": args.envs, "rollout_len": args.rollout, "updates": args.updates,
+                      "ms_per_update": secs / args.updates * 1e3, "env_step_launches": env.launch_count - l0,
+                      "mean_step_reward": tr.mean_reward(), "params": tr.net.num_parameters(),
+                      "critic_loss": float(tr.stats["critic_loss"])}))
+if world > 1:
+    dist.destroy_process_group()

@@ -247,10 +247,13 @@ class BatchedA2C:
                     self._rollout_steps()
                 torch.cuda.current_stream(self.device).wait_stream(side)
                 torch.cuda.synchronize(self.device)
-                self.obs[0].copy_(self.obs[self.T]), self.masks[0].copy_(self.masks[self.T])
+                # that eager pass IS this call's rollout (its buffers are consistent); capturing executes nothing, it only
+                # records the same launch sequence over the same static buffers for every later call
+                state, ctr = self.env.save_state(), self._ctr.clone()
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph):
                     self._rollout_steps()
+                self.env.load_state(state), self._ctr.copy_(ctr)  # capture must not have side effects
             else:
                 self._graph.replay()
         else:

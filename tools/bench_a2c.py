@@ -14,13 +14,16 @@ ap.add_argument("--rollout", type=int, default=32)
 ap.add_argument("--updates", type=int, default=20)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--num-orders", type=int, default=25)
+ap.add_argument("--tf32", action="store_true", help="TF32 tensor-core GEMMs (fp32 storage/accumulate); default is full fp32")
+ap.add_argument("--no-graph", action="store_true")
 args = ap.parse_args()
+torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
 rank, local_rank, world = fdist.world_info()
 torch.cuda.set_device(local_rank)
 dev = torch.device("cuda", local_rank)
 fdist.init(device=dev)
 env = BatchedFJSPEnv(args.envs, device=dev, first_env=rank * args.envs, seed=11, num_orders=args.num_orders, autoreset=True)
-tr = BatchedA2C(env, rollout_len=args.rollout, seed=1)
+tr = BatchedA2C(env, rollout_len=args.rollout, seed=1, use_cuda_graph=not args.no_graph)
 tr.train(args.warmup)
 l0 = env.launch_count
 fdist.barrier(dev)
@@ -30,8 +33,8 @@ frames = world * args.envs * args.rollout * args.updates
 if rank == 0:
     print(json.dumps({"metric": "a2c_frames_per_sec", "value": frames / secs, "unit": "frames/s", "n_gpus": world,
                       "envs_per_gpu": args.envs, "rollout_len": args.rollout, "updates": args.updates,
-                      "ms_per_update": secs / args.updates * 1e3, "env_step_launches": env.launch_count - l0,
-                      "mean_step_reward": tr.mean_reward(), "params": tr.net.num_parameters(),
+                      "ms_per_update": secs / args.updates * 1e3, "env_step_launches": args.rollout * args.updates,
+                      "mean_step_reward": tr.mean_reward(), "params": tr.net.num_parameters(), "gemm_precision": "tf32" if args.tf32 else "fp32", "cuda_graph_rollout": not args.no_graph,
                       "critic_loss": float(tr.stats["critic_loss"])}))
 if world > 1:
     dist.destroy_process_group()

@@ -38,6 +38,9 @@ UNIT = "agent-steps/s"
 BYTES_IO = 8 + 152 + 32 + 32 + 4
 STATE_BYTES = 512
 BYTES_PER_ENV_STEP = BYTES_IO + 2 * STATE_BYTES  # 1252
+# dram__bytes_read.sum + dram__bytes_write.sum of one fjsp_step_kernel launch at 2^20 envs, from the committed
+# `ncu --set full` capture profiles/r01_step_kernel_full_raw.csv (545.3 MB + 716.5 MB); only valid for the default size
+NCU_TRAFFIC_BYTES_2P20 = 545.323776e6 + 716.455680e6
 SEED = 20261018
 NUM_ORDERS = 30
 
@@ -319,7 +322,7 @@ def run_ours(args):
                        "l2": "no flush: each step streams the 512 MiB state and a fresh 8 MiB action buffer (> 126 MB L2)",
                        "action_buffers": nbuf},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": args.ncu_traffic_bytes, "peak_source": peak_src, "kernel": "fjsp_step_kernel",
+                         "traffic": args.ncu_traffic_bytes if E == (1 << 20) else None, "peak_source": peak_src, "kernel": "fjsp_step_kernel",
                          "algorithmic_bytes_per_launch": E * BYTES_PER_ENV_STEP},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 8, "d2h_bytes_per_step": E * (152 + 32 + 32 + 4),
                     "steps": Ke, "api": "fjsp_step_host (pinned host buffers)"},
@@ -346,7 +349,7 @@ def main():
     ap.add_argument("--max-action-buffers", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--ncu-traffic-bytes", type=float, default=None,
+    ap.add_argument("--ncu-traffic-bytes", type=float, default=NCU_TRAFFIC_BYTES_2P20,
                     help="dram bytes read+written per launch of fjsp_step_kernel from the committed ncu capture")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -97,9 +97,12 @@ def lib() -> C.CDLL:
     if _lib is not None:
         return _lib
     if not os.path.exists(SO_PATH):
-        raise RuntimeError(
-            "libfjsp_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` or "
-            "`python -m multi_agent_rl_for_fjsp_b200.abi`. This package has no CPU fallback." % SO_PATH)
+        try:  # fresh checkout: compile in-tree once (needs nvcc); there is no other implementation to fall back to
+            build()
+        except Exception as e:  # noqa: BLE001
+            raise RuntimeError(
+                "libfjsp_b200.so is not built (%s) and could not be compiled here: %s. Run "
+                "`python -c 'import __graft_entry__ as g; g.build()'`. This package has no CPU fallback." % (SO_PATH, e))
     L = C.CDLL(SO_PATH)
     vp, i64, u64 = C.c_void_p, C.c_int64, C.c_uint64
     L.fjsp_last_error.restype = C.c_char_p

@@ -102,14 +102,73 @@ class SimulationView:
         done = [o for o in self.orders if o.is_complete]
         return sorted(done, key=lambda o: (o.completion_time, o.id))
 
+    # ---- object-graph views read by the reference's heuristic policy and visualiser (a2c.py:407-535)
+    def _tray(self, entry):
+        """Tray view from a canonical tray entry (tray_id | order<<16 | first<<22 | count<<26)."""
+        entry = int(entry)
+        if entry < 0:
+            return None
+        s = self._s()
+        o, first, cnt = (entry >> 16) & 63, (entry >> 22) & 15, (entry >> 26) & 7
+        n, t, c = self._f._orders[o]
+        bits = ((1 << cnt) - 1) << first
+        prods = [_Obj(id=o * 100 + i, order_id=o, is_processed=bool((int(s["processed_mask"][o]) >> i) & 1),
+                      is_packaged=bool((int(s["packaged_mask"][o]) >> i) & 1)) for i in range(first, first + cnt)]
+        return _Obj(id=entry & 0xffff, order_id=o, products=prods, capacity=5,
+                    tray_type=("", "SMALL", "MEDIUM", "BIG")[t], tray_color=("", "RED", "BLUE", "GREEN")[c],
+                    needs_processing=(int(s["processed_mask"][o]) & bits) != bits,
+                    needs_packaging=(int(s["packaged_mask"][o]) & bits) != bits)
+
+    def _trays(self, arr, n):
+        return [self._tray(e) for e in arr[:int(n)]]
+
     @property
     def agv(self):
         s = self._s()
-        carry = int(s["agv_carry"])
-        tray = None
-        if carry >= 0:
-            tray = _Obj(id=carry & 0xffff, order_id=(carry >> 16) & 63, first=(carry >> 22) & 15, count=(carry >> 26) & 7)
-        return _Obj(position=(int(s["agv_row"]), int(s["agv_col"])), carrying_tray=tray, is_moving=bool(s["agv_is_moving"]))
+        return _Obj(position=(int(s["agv_row"]), int(s["agv_col"])), carrying_tray=self._tray(s["agv_carry"]),
+                    is_moving=bool(s["agv_is_moving"]))
+
+    @property
+    def pickup_station(self):
+        s = self._s()
+        orders = self.orders
+        n = int(s["num_orders"])
+        cur = int(s["ps_current_order"])
+        return _Obj(order_queue=orders[n - int(s["ps_order_queue_len"]):], current_order=orders[cur] if cur >= 0 else None,
+                    current_order_product_idx=int(s["ps_product_idx"]), current_tray=self._tray(s["ps_current_tray"]),
+                    ready_trays=self._trays(s["ps_ready"], s["ps_ready_n"]),
+                    trays_at_station=[None] * int(s["ps_trays_at_station"]))
+
+    def _machine(self, i):
+        m = self._s()["machine"][i]
+        return _Obj(is_busy=bool(m["is_busy"]), current_tray=self._tray(m["current_tray"]),
+                    processing_progress=float(m["progress_done"]), tray_queue=self._trays(m["queue"], m["queue_n"]),
+                    ready_trays=self._trays(m["ready"], m["ready_n"]))
+
+    @property
+    def small_machine(self):
+        return self._machine(0)
+
+    @property
+    def big_machine(self):
+        return self._machine(1)
+
+    @property
+    def storage(self):
+        s = self._s()
+        return _Obj(trays=self._trays(s["storage"], s["storage_n"]), capacity=self._f.config.get("storage_capacity", 100))
+
+    @property
+    def packaging_stations(self):
+        s, out = self._s(), {}
+        for i, name in enumerate(AGENT_IDS[4:]):
+            p = s["pack"][i]
+            cp = int(p["current_product"])
+            out[name] = _Obj(is_busy=bool(p["is_busy"]), products_completed=int(p["products_completed"]),
+                             product_queue=[_Obj(id=int(x), order_id=int(x) // 100) for x in p["queue"][:int(p["queue_n"])]],
+                             current_product=_Obj(id=cp, order_id=cp // 100) if cp >= 0 else None,
+                             processing_progress=(100.0 / int(p["progress_L"])) if int(p["progress_L"]) else 0.0)
+        return out
 
     def get_order_progress(self):  # FJSPSimulation.py:260-284
         orders = self.orders

@@ -52,13 +52,19 @@ def _missing(mod: str) -> bool:
 def load_reference():
     """Import the reference modules; returns a namespace with FJSPParallelEnv, FJSPSimulation, enums."""
     if _loaded:
+        for p in _loaded["paths"]:  # a test fixture may have restored sys.path since the first load
+            if p not in sys.path:
+                sys.path.insert(0, p)
         return _loaded["ns"]
     if not reference_available():
         raise RuntimeError("reference sources not found under %s" % REFERENCE_ROOT)
+    paths = [REFERENCE_ROOT]
     if _missing("simpy"):
         sys.path.insert(0, _SHIMS)
+        paths.append(_SHIMS)
     if _missing("gymnasium") or _missing("pettingzoo") or _missing("matplotlib"):
         sys.path.insert(0, _COMPAT)
+        paths.append(_COMPAT)
     for pkg in ("agents", "models", "utils", "enums"):
         m = types.ModuleType(pkg)
         m.__path__ = [os.path.join(REFERENCE_ROOT, pkg)]
@@ -78,6 +84,7 @@ def load_reference():
     ns.Product = importlib.import_module("models.Product").Product
     ns.Order = importlib.import_module("models.Order").Order
     _loaded["ns"] = ns
+    _loaded["paths"] = paths
     return ns
 
 

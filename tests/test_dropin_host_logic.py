@@ -119,3 +119,31 @@ def test_reference_train_py_runs_unchanged_on_facade(tmp_path):
     proc = subprocess.run([sys.executable, "-c", code], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-3000:]
     assert "Training complete" in proc.stdout
+
+
+@pytest.mark.reference
+def test_reference_heuristic_policy_drives_facade_like_reference(facade_cls):
+    """a2c.MultiAgentA2C._get_heuristic_actions (a2c.py:390-537) reads the simulation OBJECT GRAPH; the facade's
+    SimulationView must present the same graph: both envs follow the same trajectory under that policy."""
+    import importlib
+
+    ns = refload.load_reference()
+    sys.modules.setdefault("visualization", type(sys)("visualization")).GridVisualizer = object
+    a2c_ref = importlib.import_module("a2c")
+    ref = ns.FJSPParallelEnv()
+    env = facade_cls()
+    pol = a2c_ref.MultiAgentA2C._get_heuristic_actions
+    with refload.quiet():
+        np.random.seed(21); ref.reset(options={"num_orders": 6})
+        np.random.seed(21); env.reset(options={"num_orders": 6})
+        total_ref = total = 0.0
+        steps = 0
+        while ref.agents and steps < 400:
+            a1 = pol(None, ref.unwrapped.simulation)
+            a2 = pol(None, env.unwrapped.simulation)
+            assert a1 == a2, (steps, a1, a2)
+            _, r1, te1, tr1, i1 = ref.step(a1)
+            _, r2, te2, tr2, i2 = env.step(a2)
+            assert r2 == pytest.approx(r1, rel=1e-6) and te1 == te2 and tr1 == tr2
+            total_ref += sum(r1.values()); total += sum(r2.values()); steps += 1
+        assert not env.agents and i1["agv"]["orders_completed"] == i2["agv"]["orders_completed"] >= 1

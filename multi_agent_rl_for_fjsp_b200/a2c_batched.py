@@ -100,6 +100,67 @@ class ActorCritic(torch.nn.Module):
     def num_parameters(self):
         return sum(p.numel() for p in self.parameters())
 
+    # ---- checkpoint compatibility with the reference (a2c.py:733-775): same dict layout, nn.Sequential key names
+    def _groups(self):
+        from .env import AGENT_IDS
+
+        return [(AGENT_IDS[0], self.ps, None), (AGENT_IDS[1], self.agv, None)] + [(AGENT_IDS[2 + i], self.six, i) for i in range(6)]
+
+    @staticmethod
+    def _to_state_dict(params, idx):
+        sd = {}
+        for k in range(len(params) // 2):
+            w, b = params[2 * k].detach(), params[2 * k + 1].detach()
+            if idx is not None:
+                w, b = w[idx], b[idx]
+            sd["net.%d.weight" % (2 * k)] = w.t().contiguous().cpu().clone()  # nn.Linear stores [out, in]
+            sd["net.%d.bias" % (2 * k)] = b.reshape(-1).cpu().clone()
+        return sd
+
+    @staticmethod
+    def _from_state_dict(params, idx, sd):
+        with torch.no_grad():
+            for k in range(len(params) // 2):
+                w = torch.as_tensor(sd["net.%d.weight" % (2 * k)]).t()
+                b = torch.as_tensor(sd["net.%d.bias" % (2 * k)]).reshape(1, -1)
+                (params[2 * k] if idx is None else params[2 * k][idx]).copy_(w)
+                (params[2 * k + 1] if idx is None else params[2 * k + 1][idx]).copy_(b)
+
+    def reference_checkpoint(self):
+        """The dict ``MultiAgentA2C.save_model`` writes (a2c.py:745-752), with plain-int dims."""
+        from .env import AGENT_IDS, N_ACTIONS, OBS_SLICES
+
+        return {
+            "actor_nets": {name: self._to_state_dict(list(p), i) for name, p, i in self._groups()},
+            "critic_net": self._to_state_dict(list(self.critic), None),
+            "obs_dims": {a: int(hi - lo) for a, (lo, hi) in zip(AGENT_IDS, OBS_SLICES)},
+            "act_dims": {a: int(n) for a, n in zip(AGENT_IDS, N_ACTIONS)},
+            "global_obs_dim": 38,
+            "possible_agents": list(AGENT_IDS),
+        }
+
+    def save_reference_checkpoint(self, path):
+        torch.save(self.reference_checkpoint(), path)
+
+    def load_reference_checkpoint(self, path_or_dict):
+        """Load a checkpoint in the reference's layout.  Files are unpickled with ``weights_only=True`` plus an allow-list
+        for the NumPy scalar types the reference's ``act_dims`` contain (a2c.py:80: ``act_space.n`` is ``np.int64``);
+        the file is third-party content, so nothing else is allowed to execute."""
+        ckpt = path_or_dict
+        if not isinstance(ckpt, dict):
+            import numpy as np
+
+            import numpy._core.multiarray as ma  # pickles written under NumPy 1.x name it numpy.core.multiarray
+
+            allow = [np.dtype, np.int64, np.ndarray, type(np.dtype(np.int64)), ma.scalar, ma._reconstruct,
+                     (ma.scalar, "numpy.core.multiarray.scalar"), (ma._reconstruct, "numpy.core.multiarray._reconstruct")]
+            with torch.serialization.safe_globals(allow):
+                ckpt = torch.load(path_or_dict, weights_only=True, map_location="cpu")
+        for name, params, idx in self._groups():
+            self._from_state_dict(list(params), idx, ckpt["actor_nets"][name])
+        self._from_state_dict(list(self.critic), None, ckpt["critic_net"])
+        return ckpt
+
 
 _SEG = [(MASK_OFFSETS[i], N_ACTIONS[i]) for i in range(8)]
 

@@ -215,3 +215,42 @@ def test_two_rank_data_parallel_update_equals_single_process_on_joint_batch():
     pj = torch.cat([p.detach().reshape(-1) for p in tr.net.parameters()])
     # one Adam step moves a parameter by ~lr = 3e-4; summation-order noise on near-zero gradients stays far below that
     assert torch.allclose(pj, p0, rtol=1e-4, atol=2e-5), float((pj - p0).abs().max())
+
+
+def test_checkpoint_roundtrip_in_reference_layout(tmp_path):
+    a, b = A.ActorCritic(seed=1), A.ActorCritic(seed=2)
+    a.save_reference_checkpoint(str(tmp_path / "m.pt"))
+    ck = b.load_reference_checkpoint(str(tmp_path / "m.pt"))
+    assert ck["global_obs_dim"] == 38 and ck["obs_dims"]["agv"] == 13 and ck["act_dims"]["agv"] == 8
+    o = torch.randn(7, 38)
+    assert torch.equal(a.probs32(o), b.probs32(o)) and torch.equal(a.value(o), b.value(o))
+    assert set(ck["actor_nets"]["agv"]) == {"net.0.weight", "net.0.bias", "net.2.weight", "net.2.bias", "net.4.weight", "net.4.bias"}
+    assert ck["actor_nets"]["agv"]["net.0.weight"].shape == (256, 13)
+
+
+@pytest.mark.reference
+def test_loads_reference_checkpoint_and_matches_reference_networks():
+    """checkpoints/model.pt of the reference (654,366 fp32 params) loads with weights_only=True and the batched
+    networks reproduce the reference's nn.Sequential outputs."""
+    import importlib
+    import sys
+
+    from oracle import refload
+
+    refload.load_reference()
+    networks = importlib.import_module("networks")
+    path = refload.REFERENCE_ROOT + "/checkpoints/model.pt"
+    net = A.ActorCritic(seed=0)
+    ck = net.load_reference_checkpoint(path)
+    assert list(ck["possible_agents"])[1] == "agv" and int(ck["global_obs_dim"]) == 38
+    o = torch.rand(16, 38) * 3
+    pr = net.probs32(o)
+    agv = networks.ActorNetwork(13, 8)
+    agv.load_state_dict(ck["actor_nets"]["agv"])
+    red = networks.ActorNetwork(3, 3)
+    red.load_state_dict(ck["actor_nets"]["packaging_red"])
+    crit = networks.CentralizedCriticNetwork(38)
+    crit.load_state_dict(ck["critic_net"])
+    assert torch.allclose(pr[:, 3:11], agv(o[:, 7:20]), atol=1e-6)
+    assert torch.allclose(pr[:, 23:26], red(o[:, 32:35]), atol=1e-6)
+    assert torch.allclose(net.value(o), crit(o).squeeze(-1), atol=1e-5)

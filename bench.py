@@ -303,12 +303,52 @@ def run_ours(args):
         small = {"envs": 4096, "step_launch_us": sms / 2000 * 1e3, "agent_steps_per_s_stepwise": 4096 * 8 * 2000 / (sms * 1e-3),
                  "agent_steps_per_s_rollout_2000_steps_per_launch": 4096 * 8 * 2000 / (rms * 1e-3),
                  "note": "configs[1]; L2-resident, launch-latency bound; not the headline"}
+        # the same 4096-env stepping replayed from a CUDA graph of 64 captured step launches (no per-launch host work)
+        gs = torch.cuda.Stream(device=dev)
+        gs.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(gs):
+            es.step(sa[0])
+        torch.cuda.current_stream(dev).wait_stream(gs)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for t in range(64):
+                es.step(sa[t])
+        for _ in range(3):
+            graph.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(32):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        small["agent_steps_per_s_cuda_graph_64_steps"] = 4096 * 8 * 64 * 32 / (e0.elapsed_time(e1) * 1e-3)
+        small["cuda_graph_step_us"] = e0.elapsed_time(e1) / (64 * 32) * 1e3
         # K-steps-per-launch variant on the full batch (state stays on-chip between steps; not the headline)
         e0.record()
         env.rollout_random(32)
         e1.record()
         torch.cuda.synchronize()
         small["rollout32_full_batch_agent_steps_per_s"] = E * 8 * 32 / (e0.elapsed_time(e1) * 1e-3)
+
+    # ---- A2C frames/s (second half of BASELINE.json's metric; configs[2]): 4096 envs per GPU, rollout 32, fp32 GEMMs,
+    #      CUDA-graph rollout, ONE flat NCCL all-reduce of the gradients per update when N > 1.  All ranks take part.
+    a2c = None
+    if not args.no_extras:
+        from multi_agent_rl_for_fjsp_b200.a2c_batched import BatchedA2C
+
+        ea = BatchedFJSPEnv(4096, device=dev, first_env=rank * 4096, seed=SEED + 1, num_orders=25, autoreset=True)
+        tr = BatchedA2C(ea, rollout_len=32, seed=1)
+        tr.train(3)
+        barrier()
+        fps, secs = tr.train(20)
+        secs = max_over_ranks(secs)
+        a2c = {"metric": "a2c_frames_per_sec", "value": world * 4096 * 32 * 20 / secs, "unit": "frames/s",
+               "envs_per_gpu": 4096, "rollout_len": 32, "updates": 20, "ms_per_update": secs / 20 * 1e3,
+               "params": tr.net.num_parameters(), "gemm_precision": "fp32", "cuda_graph_rollout": True,
+               "gradient_allreduce": "nccl, one flat 2.62 MB bucket" if world > 1 else "none (1 GPU)",
+               "note": "1 frame = 1 env step consumed by training (rollout + update); reference CPU: 17-33 frames/s (BASELINE.md)"}
+        del tr, ea
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -332,6 +372,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline_block()
         if small:
             line["extra"] = small
+        if a2c:
+            line["a2c"] = a2c
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -163,8 +163,8 @@ def cpu_baseline_block(target_seconds=12.0):
     steps = max(200, min(200000, int(target_seconds * rate / 8 / sample_envs)))
     rate, dt, env_steps = cpu_port_rate(sample_envs, steps, 1, threads, warm_calls=0)
     return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d envs x %d lockstep steps (%.1f s) of the same workload, C port of the reference "
-                      "(oracle/fjsp_oracle.c), %d pthreads" % (sample_envs, steps, dt, threads)}
+            "sample": "%d envs x %d consecutive steps each, env-major (%.1f s), same workload (Philox orders/actions, "
+                      "autoreset), C port of the reference (oracle/fjsp_oracle.c), %d pthreads" % (sample_envs, steps, dt, threads)}
 
 
 def run_reference(args):

@@ -43,7 +43,7 @@ extern "C" {
 /* fault codes (flags[2]); the reference has no equivalent — see DESIGN.md "faults" */
 #define FJSP_FAULT_NONE 0
 #define FJSP_FAULT_PKG_RESTART_WITH_WAITERS 1 /* reference raises ValueError out of env.run (SURVEY R-PKG-cap-b) */
-#define FJSP_FAULT_POOL_EXHAUSTED 2           /* >64 trays in transit: impossible when max_episode_steps <= 252 */
+#define FJSP_FAULT_POOL_EXHAUSTED 2           /* >64 trays in transit: impossible when max_episode_steps <= 240 */
 
 /* Mirrors constants.py:5-32 (LOCATION_POSITIONS, PROCESSING_TIMES, CONFIG). */
 typedef struct FjspConfig {
@@ -53,7 +53,7 @@ typedef struct FjspConfig {
     int32_t proc_small, proc_big, proc_pack; /* constants.py:14-18, sim time units; multiples of step_size */
     int32_t step_size;                     /* constants.py:29 */
     int32_t agv_speed;                     /* constants.py:28 */
-    int32_t max_episode_steps;             /* constants.py:31; <= 252 */
+    int32_t max_episode_steps;             /* constants.py:31; <= 240 */
     int32_t storage_capacity;              /* FJSPSimulation.py:87 default 100 */
     int32_t pack_capacity;                 /* PackagingAgent.py:46 simpy.Resource(capacity=20); <= 31 */
     int32_t tray_capacity;                 /* must be 5 */

@@ -38,7 +38,7 @@ inline const char* make_params(const FjspConfig& c, Params* P) {
             return "processing times must be positive multiples of step_size (timers are resolved on step boundaries)";
     if (c.proc_pack / c.step_size > 200) return "proc_pack too long";
     if (c.tray_capacity != FJSP_TRAY_CAPACITY) return "tray_capacity must be 5 (the reference's mask hard-codes CONFIG['tray_capacity'])";
-    if (c.max_episode_steps < 1 || c.max_episode_steps > 252) return "max_episode_steps must be in 1..252";
+    if (c.max_episode_steps < 1 || c.max_episode_steps > 240) return "max_episode_steps must be in 1..240 (bounds the 64-slot tray pool and the 6/8-bit queue counters)";
     if (c.pack_capacity < 1 || c.pack_capacity > 31) return "pack_capacity must be in 1..31";
     if (c.storage_capacity < 0) return "storage_capacity must be >= 0";
     if (c.num_trays < 0 || c.num_trays > 65535) return "num_trays must be in 0..65535";

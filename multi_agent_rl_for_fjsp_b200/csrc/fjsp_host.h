@@ -74,8 +74,8 @@ inline const char* make_params(const FjspConfig& c, Params* P) {
 
 struct ArrayState {
     u32* w;
-    u32 ld(int i) const { return w[i]; }
-    void st(int i, u32 v) { w[i] = v; }
+    FJSP_HD u32 ld(int i) const { return w[i]; }
+    FJSP_HD void st(int i, u32 v) { w[i] = v; }
 };
 
 // ---- canonical record S from packed words ----

@@ -27,6 +27,8 @@ struct FjspHandle {
     int8_t* d_masks;
     float* d_rewards;
     uint8_t* d_flags;
+    cudaStream_t hs[2];      // the two streams the host-buffer path alternates its chunks on
+    cudaEvent_t hev[2], hin;
 };
 
 static thread_local std::string g_err;
@@ -122,6 +124,11 @@ int fjsp_destroy(FjspHandle* h) {
     DeviceGuard g(h->device);
     cudaFree(h->state);
     cudaFree(h->d_actions), cudaFree(h->d_obs), cudaFree(h->d_masks), cudaFree(h->d_rewards), cudaFree(h->d_flags);
+    for (int i = 0; i < 2; i++) {
+        if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
+        if (h->hev[i]) cudaEventDestroy(h->hev[i]);
+    }
+    if (h->hin) cudaEventDestroy(h->hin);
     delete h;
     return 0;
 }
@@ -160,7 +167,7 @@ int fjsp_step(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, 
     StepArgs A;
     A.state = h->state, A.actions = actions, A.obs = obs, A.masks = masks, A.rewards = rewards, A.flags = flags;
     A.results = results, A.infos = infos, A.num_envs = h->num_envs, A.first_env = h->first_env, A.seed = h->seed;
-    A.num_orders = h->num_orders, A.autoreset = autoreset;
+    A.num_orders = h->num_orders, A.autoreset = autoreset, A.tile_begin = 0;
     fjsp_step_kernel<<<(unsigned)h->num_tiles, TILE, STEP_SMEM_BYTES, (cudaStream_t)stream>>>(h->P, A);
     h->launches++;
     CK(cudaGetLastError());
@@ -175,24 +182,57 @@ static int ensure_staging(FjspHandle* h) {
     CK(cudaMalloc(&h->d_masks, n * FJSP_MASK_DIM));
     CK(cudaMalloc(&h->d_rewards, n * FJSP_NUM_AGENTS * sizeof(float)));
     CK(cudaMalloc(&h->d_flags, n * FJSP_FLAG_DIM));
+    for (int i = 0; i < 2; i++) {
+        CK(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->hev[i], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&h->hin, cudaEventDisableTiming));
     return 0;
 }
 
+// Host-buffer step.  The batch is cut into tile-aligned chunks that alternate between two internal streams, so the
+// H2D of chunk c+1 and the kernel of chunk c+1 overlap the (PCIe-bound) D2H of chunk c; envs are independent, so
+// chunks may run in any order.  Ordered after prior work on `stream`, and `stream` is ordered after it on return.
 int fjsp_step_host(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, float* rewards, uint8_t* flags, int autoreset,
                    void* stream) {
     if (!h) return fail("handle is NULL");
     if (!actions || !obs || !masks || !rewards || !flags) return fail("host buffers must not be NULL");
     DeviceGuard g(h->device);
     if (int rc = ensure_staging(h)) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    const size_t n = (size_t)h->num_envs;
-    CK(cudaMemcpyAsync(h->d_actions, actions, n * FJSP_NUM_AGENTS, cudaMemcpyHostToDevice, st));
-    if (int rc = fjsp_step(h, h->d_actions, h->d_obs, h->d_masks, h->d_rewards, h->d_flags, nullptr, nullptr, autoreset, stream)) return rc;
-    CK(cudaMemcpyAsync(obs, h->d_obs, n * FJSP_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(masks, h->d_masks, n * FJSP_MASK_DIM, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(rewards, h->d_rewards, n * FJSP_NUM_AGENTS * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(flags, h->d_flags, n * FJSP_FLAG_DIM, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    cudaStream_t user = (cudaStream_t)stream;
+    CK(cudaEventRecord(h->hin, user));
+    for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(h->hs[i], h->hin, 0));
+    const int64_t tiles = h->num_tiles;
+    int64_t nchunks = tiles >= 64 ? 8 : (tiles >= 2 ? 2 : 1);
+    const int64_t per = (tiles + nchunks - 1) / nchunks;
+    StepArgs A;
+    A.state = h->state, A.actions = h->d_actions, A.obs = h->d_obs, A.masks = h->d_masks, A.rewards = h->d_rewards;
+    A.flags = h->d_flags, A.results = nullptr, A.infos = nullptr, A.num_envs = h->num_envs, A.first_env = h->first_env;
+    A.seed = h->seed, A.num_orders = h->num_orders, A.autoreset = autoreset;
+    int c = 0;
+    for (int64_t t0 = 0; t0 < tiles; t0 += per, c++) {
+        cudaStream_t st = h->hs[c & 1];
+        const int64_t t1 = t0 + per < tiles ? t0 + per : tiles;
+        const int64_t e0 = t0 * TILE, e1 = t1 * TILE < h->num_envs ? t1 * TILE : h->num_envs;
+        const size_t n = (size_t)(e1 - e0);
+        CK(cudaMemcpyAsync(h->d_actions + e0 * FJSP_NUM_AGENTS, actions + e0 * FJSP_NUM_AGENTS, n * FJSP_NUM_AGENTS,
+                           cudaMemcpyHostToDevice, st));
+        A.tile_begin = t0;
+        fjsp_step_kernel<<<(unsigned)(t1 - t0), TILE, STEP_SMEM_BYTES, st>>>(h->P, A);
+        h->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(obs + e0 * FJSP_OBS_DIM, h->d_obs + e0 * FJSP_OBS_DIM, n * FJSP_OBS_DIM * sizeof(float),
+                           cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(masks + e0 * FJSP_MASK_DIM, h->d_masks + e0 * FJSP_MASK_DIM, n * FJSP_MASK_DIM, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(rewards + e0 * FJSP_NUM_AGENTS, h->d_rewards + e0 * FJSP_NUM_AGENTS, n * FJSP_NUM_AGENTS * sizeof(float),
+                           cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(flags + e0 * FJSP_FLAG_DIM, h->d_flags + e0 * FJSP_FLAG_DIM, n * FJSP_FLAG_DIM, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < 2; i++) {
+        CK(cudaEventRecord(h->hev[i], h->hs[i]));
+        CK(cudaStreamWaitEvent(user, h->hev[i], 0));
+    }
+    for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(h->hs[i]));
     return 0;
 }
 

@@ -83,6 +83,7 @@ struct StepArgs {
     uint8_t* results;        // [N][8] or null
     int32_t* infos;          // [N][4] or null
     int64_t num_envs, first_env;
+    int64_t tile_begin;      // first tile of this launch (host-buffer path steps the batch in pipelined chunks)
     uint64_t seed;
     int32_t num_orders, autoreset;
 };
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + TILE_BYTES + OBS_TILE_BYTES);
 
     const int tid = threadIdx.x;
-    const int64_t tile = blockIdx.x;
+    const int64_t tile = A.tile_begin + blockIdx.x;
     const int64_t env = tile * TILE + tid;
     const bool valid = env < A.num_envs;
     u32* g_tile = A.state + tile * TILE_WORDS;

@@ -266,7 +266,7 @@ def run_ours(args):
 
     # ---- end to end through the host-buffer entry point
     Ke = max(3, min(K, args.e2e_steps))
-    host_actions = [acts[i % nbuf].cpu().numpy() for i in range(min(4, nbuf))]
+    host_actions = [acts[i % nbuf].cpu().pin_memory() for i in range(min(4, nbuf))]  # inputs in pinned host memory
     for i in range(2):
         env.step_host(host_actions[i % len(host_actions)])
     barrier()

@@ -165,8 +165,8 @@ class BatchedFJSPEnv:
         return self._stats
 
     # ------------------------------------------------------------------ host-buffer path (end-to-end)
-    def step_host(self, actions: np.ndarray):
-        """Same step through HOST buffers: H2D actions, kernel, D2H obs/masks/rewards/flags (pinned), synchronised."""
+    def host_buffers(self):
+        """The pinned host tensors `step_host` reads actions from and writes results to (allocated on first use)."""
         if self._host is None:
             n = self.num_envs
             self._host = dict(
@@ -175,10 +175,23 @@ class BatchedFJSPEnv:
                 masks=torch.zeros((n, MASK_DIM), dtype=torch.int8).pin_memory(),
                 rewards=torch.zeros((n, 8), dtype=torch.float32).pin_memory(),
                 flags=torch.zeros((n, 4), dtype=torch.uint8).pin_memory())
-        hb = self._host
+        return self._host
+
+    def step_host(self, actions=None):
+        """Same step through HOST buffers: H2D actions, kernel, D2H obs/masks/rewards/flags, synchronised on return.
+
+        actions: None (use what the caller wrote into ``host_buffers()["actions"]``), a pinned uint8 CPU tensor [N,8]
+        (read in place, no staging copy) or any array-like (copied into the pinned buffer first).
+        Returns NumPy views of the pinned result buffers."""
+        hb = self.host_buffers()
+        src = hb["actions"]
         if actions is not None:
-            hb["actions"].numpy()[...] = actions
-        abi.check(self._L.fjsp_step_host(self._h, _ptr(hb["actions"]), _ptr(hb["obs"]), _ptr(hb["masks"]), _ptr(hb["rewards"]),
+            if (isinstance(actions, torch.Tensor) and actions.device.type == "cpu" and actions.dtype == torch.uint8
+                    and actions.is_contiguous() and actions.is_pinned() and tuple(actions.shape) == (self.num_envs, 8)):
+                src = actions
+            else:
+                hb["actions"].numpy()[...] = np.asarray(actions, dtype=np.uint8)
+        abi.check(self._L.fjsp_step_host(self._h, _ptr(src), _ptr(hb["obs"]), _ptr(hb["masks"]), _ptr(hb["rewards"]),
                                          _ptr(hb["flags"]), int(self.autoreset), self._stream()))
         self._t += 1
         return hb["obs"].numpy(), hb["masks"].numpy(), hb["rewards"].numpy(), hb["flags"].numpy()

@@ -276,6 +276,16 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * E * 8 * Ke / e2e_s
+    # the e2e path's own roofline: this box's pinned D2H bandwidth on the result payload (220 B/env)
+    hb = env.host_buffers()
+    for _ in range(2):
+        hb["obs"].copy_(env.obs, non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        hb["obs"].copy_(env.obs, non_blocking=True)
+    torch.cuda.synchronize()
+    d2h_gbs = E * 152 * 5 / (time.perf_counter() - t0) / 1e9
 
     # ---- small-batch point (BASELINE configs[1]: 4096 envs, launch-latency bound), device-timed, reported as extra
     small = None
@@ -365,7 +375,8 @@ def run_ours(args):
                          "traffic": args.ncu_traffic_bytes if E == (1 << 20) else None, "peak_source": peak_src, "kernel": "fjsp_step_kernel",
                          "algorithmic_bytes_per_launch": E * BYTES_PER_ENV_STEP},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 8, "d2h_bytes_per_step": E * (152 + 32 + 32 + 4),
-                    "steps": Ke, "api": "fjsp_step_host (pinned host buffers)"},
+                    "steps": Ke, "api": "fjsp_step_host (pinned host buffers)", "pcie_d2h_gbs_measured": d2h_gbs,
+                    "pcie_bound_frac": (E * 220 / (d2h_gbs * 1e9)) / (e2e_s / Ke)},
             "gpu_launches": launches, "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

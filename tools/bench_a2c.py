@@ -35,6 +35,7 @@ if rank == 0:
                       "envs_per_gpu": args.envs, "rollout_len": args.rollout, "updates": args.updates,
                       "ms_per_update": secs / args.updates * 1e3, "env_step_launches": args.rollout * args.updates,
                       "mean_step_reward": tr.mean_reward(), "params": tr.net.num_parameters(), "gemm_precision": "tf32" if args.tf32 else "fp32", "cuda_graph_rollout": not args.no_graph,
-                      "critic_loss": float(tr.stats["critic_loss"])}))
+                      "critic_loss": float(tr.stats["critic_loss"]), "update_graph": tr._ugraph is not None,
+                      "update_graph_error": tr.update_graph_error}))
 if world > 1:
     dist.destroy_process_group()

@@ -224,10 +224,21 @@ def sample_actions(q, generator=None):
     return acts
 
 
+_SEG_OFF = {}
+
+
+def _seg_offsets(device):
+    """Cached [8] tensor of the agents' segment offsets (built once per device: no H2D copy inside graph capture)."""
+    key = str(device)
+    if key not in _SEG_OFF:
+        _SEG_OFF[key] = torch.tensor([o for o, _ in _SEG], device=device)
+    return _SEG_OFF[key]
+
+
 def log_prob_of(q, actions):
     """log q[a] per agent, with Categorical's probability clamp (torch.distributions: eps = finfo.eps)."""
     eps = torch.finfo(q.dtype).eps
-    idx = actions.long() + torch.tensor([o for o, _ in _SEG], device=q.device)
+    idx = actions.long() + _seg_offsets(q.device)
     return torch.log(q.gather(1, idx).clamp(eps, 1 - eps))
 
 
@@ -291,6 +302,7 @@ class BatchedA2C:
         self.use_graph = bool(use_cuda_graph) and self.fused
         self._graph = None
         self._ugraph, self._ugraph_tries = None, 0
+        _seg_offsets(self.device)
         self.use_update_graph = self.use_graph
         self.update_graph_error = None
         if self.fused:

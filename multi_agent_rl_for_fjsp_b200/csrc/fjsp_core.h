@@ -41,7 +41,7 @@ struct Params {
     int32_t small_steps, big_steps, pack_steps;             // PROCESSING_TIMES / step_size
     int32_t max_episode_steps, storage_capacity, pack_capacity, trays_total, num_trays;
     int32_t step_size;
-    double time_reward;                                     // TIME_PENALTY * step_size (RewardModel.py:42)
+    float reward_scale;                                     // 1/80: rewards are exact multiples of 1/80 (see step_env)
     float progress_tab[256];                                // float32((1/L)*100) (PackagingAgent.py:117)
 };
 
@@ -477,7 +477,7 @@ FJSP_HD void step_env(S& s, const Params& P, const int a[8], StepOut& out) {
     load_hot(s, h);
     const int k = h.step;
     const int orders_before = h.completed_orders, products_before = h.total_packaged;
-    double local[8];
+    int local10[8];  // local rewards in tenths: every RewardModel constant is a multiple of 0.1 (RewardModel.py:12-32)
     u32 res[8];
 
     // ===== action phase, agents in dict order (FJSPSimulation.py:172-174, :76-82) =====
@@ -521,11 +521,8 @@ FJSP_HD void step_env(S& s, const Params& P, const int a[8], StepOut& out) {
         }
         res[0] = (success ? FJSP_RES_SUCCESS : 0) | (loaded ? FJSP_RES_PS_LOADED : 0) | (tray_done ? FJSP_RES_PS_TRAY_DONE : 0) |
                  (idle_orders ? FJSP_RES_PS_IDLE_ORDERS : 0);
-        double r = 0.0;  // RewardModel.py:53-60
-        if (loaded) r += 1.0;
-        if (tray_done) r += 5.0;
-        if (a[0] == 0 && idle_orders) r += -1.0;
-        local[0] = r;
+        // RewardModel.py:53-60: +1 load, +5 tray completed, -1 idle with orders
+        local10[0] = (loaded ? 10 : 0) + (tray_done ? 50 : 0) - ((a[0] == 0 && idle_orders) ? 10 : 0);
     }
     // ---- R2-R4 AGV (AGVAgent.py:180-368)
     {
@@ -612,13 +609,8 @@ FJSP_HD void step_env(S& s, const Params& P, const int a[8], StepOut& out) {
         }
         res[1] = (success ? FJSP_RES_SUCCESS : 0) | (invalid ? FJSP_RES_AGV_INVALID : 0) | (moved ? FJSP_RES_AGV_MOVED : 0) |
                  (pick ? FJSP_RES_AGV_PICKUP : 0) | (drop ? FJSP_RES_AGV_DROP : 0) | (to_pack ? FJSP_RES_AGV_TO_PACK : 0);
-        double r = 0.0;  // RewardModel.py:62-77
-        if (pick) r += 2.0;
-        if (drop) r += 2.0;
-        if (to_pack) r += 10.0;
-        if (moved) r += -0.1;
-        if (invalid) r += -5.0;
-        local[1] = r;
+        // RewardModel.py:62-77: +2 pickup, +2 drop, +10 delivered to packaging, -0.1 move, -5 invalid
+        local10[1] = (pick ? 20 : 0) + (drop ? 20 : 0) + (to_pack ? 100 : 0) - (moved ? 1 : 0) - (invalid ? 50 : 0);
     }
     // ---- R5 machines (MachineAgent.py:99-169).  START takes effect in this step's run phase, but no later
     //      agent reads machine state inside the action phase, so it is applied here.
@@ -649,11 +641,8 @@ FJSP_HD void step_env(S& s, const Params& P, const int a[8], StepOut& out) {
         }
         res[2 + i] = (success ? FJSP_RES_SUCCESS : 0) | (started ? FJSP_RES_M_STARTED : 0) | (completed ? FJSP_RES_M_COMPLETED : 0) |
                      (idle_q ? FJSP_RES_M_IDLE_QUEUE : 0);
-        double r = 0.0;  // RewardModel.py:79-86
-        if (started) r += 1.0;
-        if (completed) r += 5.0;
-        if (act == 0 && idle_q) r += -2.0;
-        local[2 + i] = r;
+        // RewardModel.py:79-86: +1 start, +5 signal complete, -2 idle with queue
+        local10[2 + i] = (started ? 10 : 0) + (completed ? 50 : 0) - ((act == 0 && idle_q) ? 20 : 0);
     }
     // ---- R6 packaging (PackagingAgent.py:91-125)
     int pk_start[4];
@@ -678,11 +667,8 @@ FJSP_HD void step_env(S& s, const Params& P, const int a[8], StepOut& out) {
         }
         res[4 + i] = (success ? FJSP_RES_SUCCESS : 0) | (started ? FJSP_RES_M_STARTED : 0) | (completed ? FJSP_RES_M_COMPLETED : 0) |
                      (idle_q ? FJSP_RES_M_IDLE_QUEUE : 0);
-        double r = 0.0;  // RewardModel.py:88-95
-        if (started) r += 2.0;
-        if (completed) r += 20.0;
-        if (act == 0 && idle_q) r += -1.0;
-        local[4 + i] = r;
+        // RewardModel.py:88-95: +2 start, +20 signal complete, -1 idle with queue
+        local10[4 + i] = (started ? 20 : 0) + (completed ? 200 : 0) - ((act == 0 && idle_q) ? 10 : 0);
     }
 
     // ===== run phase: env.run(until = now + step_size) (FJSPSimulation.py:183-184), rule R0 =====
@@ -745,21 +731,19 @@ FJSP_HD void step_env(S& s, const Params& P, const int a[8], StepOut& out) {
         }
     }
 
-    // ===== rewards (FJSPSimulation.py:190-209, RewardModel.py:34-44,99-110), double like the reference =====
+    // ===== rewards (FJSPSimulation.py:190-209, RewardModel.py:34-44,99-110) =====
+    // r_i = g/8 + local_i with g = 100*orders + 10*products - 0.1*step_size is an exact multiple of 1/80:
+    //   80*r_i = 10*(100*orders + 10*products) - step_size + 8*(10*local_i).
+    // One correctly rounded fp32 division of that integer reproduces the fp32 rounding of the reference's float64 value
+    // (no FP64 in the kernel; a non-dyadic k/80 is never within double-rounding distance of an fp32 midpoint).
     {
-        double g = 100.0 * (double)(h.completed_orders - orders_before);
-        g += 10.0 * (double)(h.total_packaged - products_before);
-        g += P.time_reward;
+        const int g80 = 10 * (100 * (h.completed_orders - orders_before) + 10 * (h.total_packaged - products_before)) - P.step_size;
         long long r40 = 0;
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            double r = g / 8.0 + local[i];
-            out.reward[i] = (float)r;
-#if defined(__CUDA_ARCH__)
-            r40 += __double2ll_rn(r * 40.0);
-#else
-            r40 += (long long)__builtin_llrint(r * 40.0);
-#endif
+            const int r80 = g80 + 8 * local10[i];
+            out.reward[i] = (float)r80 / 80.0f;
+            r40 += r80 >= 0 ? (r80 + 1) / 2 : -((1 - r80) / 2);  // round(40 r), halves away from zero
         }
         out.reward40 = r40;
     }

@@ -189,6 +189,9 @@ SCENARIOS = [
     ("few_trays", dict(num_trays=6), "heuristic", 1200, [30, 8], 1008),
     ("step5_short", dict(step_size=5, proc_small=15, proc_big=25, proc_pack=10, max_episode_steps=120), "heuristic", 2500,
      [30, 20], 1009),
+    ("speed2_far_step20", dict(pos=[[0, 0], [0, 29], [14, 11], [33, 2], [25, 40]], grid_rows=34, grid_cols=41, agv_speed=2,
+                               step_size=20, proc_small=40, proc_big=80, proc_pack=20, max_episode_steps=150), "heuristic",
+     2000, [16, 9], 1010),
 ]
 
 if __name__ == "__main__":

@@ -83,3 +83,41 @@ def test_config_validation_messages():
                 dict(pos=[(0, 0), (0, 0), (2, 3), (3, 0), (3, 5)])):
         with pytest.raises(ValueError):
             HostEnv(_cfg(**bad))
+
+
+def test_random_config_fuzz():
+    """Random (valid) configurations: layouts, timings, capacities, episode lengths.  The packed-state step function
+    and the C restatement must agree on every one of them (both are generic in FjspConfig)."""
+    rs = np.random.RandomState(2026)
+    total = 0
+    for trial in range(14):
+        step = int(rs.choice([5, 10, 20]))
+        cells = set()
+        while len(cells) < 5:
+            cells.add((int(rs.randint(0, 12)), int(rs.randint(0, 30))))
+        kw = dict(pos=list(cells), step_size=step, proc_small=step * int(rs.randint(1, 8)), proc_big=step * int(rs.randint(1, 13)),
+                  proc_pack=step * int(rs.randint(1, 5)), agv_speed=int(rs.randint(1, 3)), max_episode_steps=int(rs.randint(40, 241)),
+                  storage_capacity=int(rs.randint(0, 6)), pack_capacity=int(rs.randint(1, 32)), num_trays=int(rs.choice([3, 40, 1000])))
+        orc, hh = OracleEnv(_cfg(**kw)), HostEnv(_cfg(**kw))
+        pos = kw["pos"]
+        move_cell = {1: tuple(pos[0]), 2: tuple(pos[2]), 3: tuple(pos[1]), 4: tuple(pos[3]), 5: tuple(pos[4])}
+        for ep in range(3):
+            orders = policies.random_orders(rs, int(rs.randint(1, 33)))
+            o1, m1 = orc.reset(orders)
+            o2, m2 = hh.reset(orders)
+            assert np.array_equal(o1, o2) and np.array_equal(m1, m2), kw
+            while True:
+                a = (policies.heuristic(rs, o1, m1, noise=0.2, move_cell=move_cell) if ep else policies.masked_random(rs, o1, m1))
+                o1, m1, r1, f1 = orc.step(a)
+                o2, m2, r2, f2 = hh.step(a)
+                total += 1
+                assert np.array_equal(f1, f2), (kw, f1, f2)
+                if f1[2]:
+                    break
+                assert np.array_equal(o1, o2) and np.array_equal(m1, m2), kw
+                assert np.array_equal(r1.astype(np.float32), r2), (kw, r1, r2)
+                if f1[0] or f1[1]:
+                    d = canon.diff(orc.export(), hh.export())
+                    assert not d, (kw, d[:4])
+                    break
+    assert total > 2000

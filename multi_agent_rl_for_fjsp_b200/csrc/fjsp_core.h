@@ -290,12 +290,25 @@ FJSP_HD void philox_actions(uint64_t seed, uint64_t genv, uint64_t t, int a[8]) 
 // Reset: FJSPSimulation.reset (FJSPSimulation.py:286-323).  `orders` = FjspOrderRec[32] (n | type<<8 | colour<<16)
 // or nullptr -> Philox.
 // ---------------------------------------------------------------------------------------------
+// Everything of a fresh env except the 32 order words (the kernels fill those warp-cooperatively, one order per lane).
+template <class S>
+FJSP_HD void reset_env_base(S& s, int num_orders, u32 episode) {
+#pragma unroll 8
+    for (int w = 0; w < W_ORDER; w++) s.st(w, 0u);
+#pragma unroll 8
+    for (int w = W_POOL; w < W_TOTAL; w++) s.st(w, 0u);
+    s.st(W_CTRL, (u32)num_orders << 16);
+    s.st(W_PS, 63u << 15);         // cur_order = none
+    s.st(W_AGV, (u32)LOC_PICKUP);  // AGVAgent.py:41
+    s.st(W_FREE_LO, 0xffffffffu), s.st(W_FREE_HI, 0xffffffffu);
+    s.st(W_EPISODE, episode);
+}
+
 template <class S>
 FJSP_HD void reset_env(S& s, const Params& P, int num_orders, const FjspOrderRec* orders, uint64_t seed, uint64_t genv,
                        u32 episode) {
     (void)P;
-#pragma unroll 8
-    for (int w = 0; w < W_ORDER; w++) s.st(w, 0u);
+    reset_env_base(s, num_orders, episode);
     for (int o = 0; o < FJSP_MAX_ORDERS; o++) {
         u32 ow = 0u;
         if (o < num_orders) {
@@ -308,13 +321,6 @@ FJSP_HD void reset_env(S& s, const Params& P, int num_orders, const FjspOrderRec
         }
         s.st(W_ORDER + o, ow);
     }
-#pragma unroll 8
-    for (int w = W_POOL; w < W_TOTAL; w++) s.st(w, 0u);
-    s.st(W_CTRL, (u32)num_orders << 16);
-    s.st(W_PS, 63u << 15);  // cur_order = none
-    s.st(W_AGV, (u32)LOC_PICKUP);  // AGVAgent.py:41
-    s.st(W_FREE_LO, 0xffffffffu), s.st(W_FREE_HI, 0xffffffffu);
-    s.st(W_EPISODE, episode);
 }
 
 // ---------------------------------------------------------------------------------------------

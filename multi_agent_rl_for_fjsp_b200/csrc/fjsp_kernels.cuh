@@ -73,6 +73,34 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Warp-cooperative auto-reset.  FJSP_MAX_ORDERS == 32 == warp size: for every lane whose episode just ended (ballot),
+// the 32 lanes draw that env's 32 Philox orders in parallel (one order per lane, counter = (global env, episode, lane))
+// and store them into the ending lane's shared-memory column; the ending lane itself re-initialises its scalars.
+// A per-lane reset would make the whole warp wait for 32 sequential Philox calls whenever ANY of its envs ends.
+// Must be called by all 32 lanes of the warp.  Returns true for lanes that were reset.
+__device__ __forceinline__ bool warp_autoreset(u32* s_state, int tid, bool do_reset, int num_orders, uint64_t seed,
+                                               uint64_t genv_lane0) {
+    const unsigned need = __ballot_sync(0xffffffffu, do_reset);
+    if (need == 0u) return false;
+    const int lane = tid & 31, wbase = tid & ~31;
+    SmemColumn s{s_state + tid};
+    u32 episode = 0u;
+    if (do_reset) {
+        episode = s.ld(W_EPISODE) + 1u;
+        reset_env_base(s, num_orders, episode);
+    }
+    unsigned rem = need;
+    while (rem) {
+        const int src = __ffs((int)rem) - 1;
+        rem &= rem - 1u;
+        const u32 ep = __shfl_sync(0xffffffffu, episode, src);
+        const u32 ow = lane < num_orders ? philox_order(seed, genv_lane0 + (uint64_t)src, ep, lane) : 0u;
+        s_state[(W_ORDER + lane) * TILE + wbase + src] = ow;
+    }
+    __syncwarp();
+    return do_reset;
+}
+
 struct StepArgs {
     u32* state;              // tiles
     const uint8_t* actions;  // [N][8]
@@ -145,17 +173,17 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
     mbar_wait(bar, 0);
 
     // padding lanes of a ragged last tile are inert: their columns travel through shared memory unchanged
+    SmemColumn s{s_state + tid};
+    StepOut out;
+    out.obs = s_obs + tid * FJSP_OBS_DIM;
+    out.flags = 0u;
+    if (valid) step_env<true>(s, P, a, out);
+    const bool ended = valid && A.autoreset && (out.flags & 0x00ffffffu);
+    if (warp_autoreset(s_state, tid, ended, A.num_orders, A.seed, (uint64_t)(A.first_env + env - (tid & 31)))) {
+        observe_env(s, P, out.obs, out.mask);  // the observation returned with an ended episode is the new episode's first
+        out.flags |= 1u << 24;
+    }
     if (valid) {
-        SmemColumn s{s_state + tid};
-        StepOut out;
-        out.obs = s_obs + tid * FJSP_OBS_DIM;
-        step_env<true>(s, P, a, out);
-        if (A.autoreset && (out.flags & 0x00ffffffu)) {
-            const u32 episode = s.ld(W_EPISODE) + 1u;
-            reset_env(s, P, A.num_orders, nullptr, A.seed, (uint64_t)(A.first_env + env), episode);
-            observe_env(s, P, out.obs, out.mask);
-            out.flags |= 1u << 24;
-        }
         uint4* m4 = reinterpret_cast<uint4*>(A.masks + env * FJSP_MASK_DIM);
         m4[0] = make_uint4(out.mask[0], out.mask[1], out.mask[2], out.mask[3]);
         m4[1] = make_uint4(out.mask[4], out.mask[5], out.mask[6], out.mask[7]);
@@ -225,9 +253,10 @@ __global__ void __launch_bounds__(TILE) fjsp_rollout_kernel(const __grid_constan
     SmemColumn s{s_state + tid};
     unsigned long long n_steps = 0, n_eps = 0, n_orders = 0, n_prod = 0, n_fault = 0;
     long long r40 = 0;
-    if (valid) {
-        const uint64_t genv = (uint64_t)(first_env + env);
-        for (int k = 0; k < steps; k++) {
+    const uint64_t genv = (uint64_t)(first_env + env);
+    for (int k = 0; k < steps; k++) {  // uniform trip count: all lanes stay together for the cooperative reset
+        bool ended = false;
+        if (valid) {
             int a[8];
             philox_actions(seed, genv, t0 + (uint64_t)k, a);
             StepOut out;
@@ -239,12 +268,12 @@ __global__ void __launch_bounds__(TILE) fjsp_rollout_kernel(const __grid_constan
             n_prod += (unsigned long long)(out.info[2] - (int)(before_ps & 511u));
             r40 += out.reward40;
             if (out.flags & 0x00ffffffu) {
+                ended = true;
                 n_eps += 1;
                 n_fault += (out.flags >> 16) & 0xffu ? 1 : 0;
-                const u32 episode = s.ld(W_EPISODE) + 1u;
-                reset_env(s, P, num_orders, nullptr, seed, genv, episode);
             }
         }
+        warp_autoreset(s_state, tid, ended, num_orders, seed, genv - (uint64_t)(tid & 31));
     }
     // warp shuffle reduce, then one shared atomic per warp, one global atomic per CTA and counter
     unsigned long long v[6] = {n_steps, n_eps, n_orders, n_prod, n_fault, (unsigned long long)r40};

@@ -41,7 +41,6 @@ struct Params {
     int32_t small_steps, big_steps, pack_steps;             // PROCESSING_TIMES / step_size
     int32_t max_episode_steps, storage_capacity, pack_capacity, trays_total, num_trays;
     int32_t step_size;
-    float reward_scale;                                     // 1/80: rewards are exact multiples of 1/80 (see step_env)
     float progress_tab[256];                                // float32((1/L)*100) (PackagingAgent.py:117)
 };
 

@@ -66,7 +66,6 @@ inline const char* make_params(const FjspConfig& c, Params* P) {
     P->trays_total = c.num_trays < 1000 ? c.num_trays : 1000;  // FJSPSimulation.py:96
     if (P->trays_total > 255) P->trays_total = 255;            // an episode of <= 253 steps allocates <= 253 trays
     P->step_size = c.step_size;
-    P->reward_scale = 1.0f / 80.0f;
     P->progress_tab[0] = 0.0f;
     for (int L = 1; L < 256; L++) P->progress_tab[L] = (float)((1.0 / (double)L) * 100.0);
     return nullptr;

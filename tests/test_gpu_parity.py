@@ -234,3 +234,71 @@ def test_no_cpu_fallback_in_product():
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("no oracle", "") or f == "README.md", (dp, f)
                 assert "host_harness" not in src
+
+
+def _torch_heuristic(obs, masks, gen, noise=0.1):
+    """Vectorised competent policy on device tensors (same spirit as oracle/policies.heuristic): completes orders, so
+    packaging, terminations and DESYNCHRONISED auto-resets happen at scale."""
+    n = obs.shape[0]
+    dev = obs.device
+    m = masks != 0
+    a = torch.zeros(n, 8, dtype=torch.long, device=dev)
+    a[:, 0] = m[:, 1].long()
+    for i, off in ((2, 11), (3, 14)):
+        a[:, i] = torch.where(m[:, off + 2], 2, torch.where(m[:, off + 1], 1, 0))
+    for i, off in ((4, 17), (5, 20), (6, 23), (7, 26)):
+        a[:, i] = m[:, off + 1].long()
+    row, col = obs[:, 11].long(), obs[:, 12].long()
+    cells = {1: (0, 0), 2: (2, 3), 3: (0, 3), 4: (3, 0), 5: (3, 5)}
+    carrying, needs_proc, ttype = obs[:, 9] > 0, obs[:, 17] > 0, obs[:, 19].long()
+    tgt_c = torch.where(needs_proc, torch.where(ttype == 1, 2, torch.where(ttype == 3, 3, torch.where(obs[:, 22] <= obs[:, 25], 2, 3))), 5)
+    tgt_e = torch.where(obs[:, 14] > 0, 2, torch.where(obs[:, 8] > 0, 3, torch.where(obs[:, 10] > 0, 1, torch.where(obs[:, 15] > 0, 4, 1))))
+    tgt = torch.where(carrying, tgt_c, tgt_e)
+    at = torch.zeros(n, dtype=torch.bool, device=dev)
+    for k, (r, c) in cells.items():
+        at |= (tgt == k) & (row == r) & (col == c)
+    manip = torch.where(carrying, 7, 6)
+    manip_ok = torch.where(carrying, m[:, 10], m[:, 9])
+    a[:, 1] = torch.where(at, torch.where(manip_ok, manip, 0), tgt)
+    rnd = torch.rand(n, 8, device=dev, generator=gen)
+    nact = torch.tensor([3, 8, 3, 3, 3, 3, 3, 3], device=dev)
+    noise_a = (torch.rand(n, 8, device=dev, generator=gen) * nact).long().clamp_max(7)
+    return torch.where(rnd < noise, noise_a, a).to(torch.uint8)
+
+
+def test_gpu_heuristic_batch_with_desynchronised_resets():
+    """Few orders per env + a competent policy: episodes TERMINATE at different steps in different lanes of a warp, so
+    the warp-cooperative reset runs with partial ballots; packaging/termination paths are exercised on 3000 envs."""
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+
+    n, seed, num_orders, steps = 3000, 424242, 3, 420
+    env = BatchedFJSPEnv(n, seed=seed, num_orders=num_orders, autoreset=True)
+    obs, masks = env.reset()
+    gen = torch.Generator(device=env.device).manual_seed(5)
+    sample = sorted(set([0, 31, 32, 63, 64, n - 1] + np.random.RandomState(1).randint(0, n, size=40).tolist()))
+    oracles, episodes = {}, {}
+    for i in sample:
+        o = OracleEnv()
+        o.reset(philox_orders(seed, i, 0, num_orders))
+        oracles[i], episodes[i] = o, 0
+    terminated, reset_steps = 0, set()
+    for t in range(steps):
+        acts = _torch_heuristic(obs, masks, gen)
+        obs, rew, term, trunc, masks = env.step(acts)
+        h_act, h_obs, h_rew, h_masks, h_flags = (x.cpu().numpy() for x in (acts, obs, rew, masks, env.flags))
+        terminated += int(h_flags[:, 0].sum())
+        for i in sample:
+            o = oracles[i]
+            oo, om, orw, of = o.step(h_act[i])
+            assert tuple(of[:3]) == tuple(h_flags[i][:3]), (i, t, of, h_flags[i])
+            assert np.all(np.abs(h_rew[i] - orw) <= REL_TOL * np.abs(orw)), (i, t)
+            if of[0] or of[1]:
+                episodes[i] += 1
+                reset_steps.add(t)
+                oo, om = o.reset(philox_orders(seed, i, episodes[i], num_orders))
+            assert np.array_equal(oo, h_obs[i]) and np.array_equal(om, h_masks[i]), (i, t)
+    assert terminated > n, "the policy should finish most episodes by completing all orders"
+    assert len(reset_steps) > 20, "resets must be spread over many different steps (partial ballots)"
+    for i in sample:
+        d = canon.diff(oracles[i].export(), env.export_state(i))
+        assert not d, (i, d[:5])

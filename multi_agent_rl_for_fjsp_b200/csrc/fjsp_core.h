@@ -476,10 +476,10 @@ FJSP_HD void pack_grant(S& s, Hot& h, Pack& p, int g, int stamp) {
 // ---------------------------------------------------------------------------------------------
 // One environment step.  Returns through `out`.  `actions` = 8 bytes.
 // ---------------------------------------------------------------------------------------------
+// `h` holds the unpacked hot words (0..23) of the env; the caller loads/stores them (once per step in the step kernel,
+// once per LAUNCH in the K-steps-per-launch kernel, which keeps them in registers between steps).
 template <bool WITH_OBS, class S>
-FJSP_HD void step_env(S& s, const Params& P, const int a[8], StepOut& out) {
-    Hot h;
-    load_hot(s, h);
+FJSP_HD void step_env_hot(S& s, const Params& P, Hot& h, const int a[8], StepOut& out) {
     const int k = h.step;
     const int orders_before = h.completed_orders, products_before = h.total_packaged;
     int local10[8];  // local rewards in tenths: every RewardModel constant is a multiple of 0.1 (RewardModel.py:12-32)
@@ -761,6 +761,13 @@ FJSP_HD void step_env(S& s, const Params& P, const int a[8], StepOut& out) {
     h.step = k + 1;
     out.info[0] = h.step, out.info[1] = h.completed_orders, out.info[2] = h.total_packaged, out.info[3] = 0;
     if (WITH_OBS) observe(s, P, h, out.obs, out.mask);
+}
+
+template <bool WITH_OBS, class S>
+FJSP_HD void step_env(S& s, const Params& P, const int a[8], StepOut& out) {
+    Hot h;
+    load_hot(s, h);
+    step_env_hot<WITH_OBS>(s, P, h, a, out);
     store_hot(s, h);
 }
 

@@ -254,6 +254,8 @@ __global__ void __launch_bounds__(TILE) fjsp_rollout_kernel(const __grid_constan
     unsigned long long n_steps = 0, n_eps = 0, n_orders = 0, n_prod = 0, n_fault = 0;
     long long r40 = 0;
     const uint64_t genv = (uint64_t)(first_env + env);
+    Hot h;  // hot words live in registers for the whole launch; shared memory only sees them around a reset
+    load_hot(s, h);
     for (int k = 0; k < steps; k++) {  // uniform trip count: all lanes stay together for the cooperative reset
         bool ended = false;
         if (valid) {
@@ -261,20 +263,22 @@ __global__ void __launch_bounds__(TILE) fjsp_rollout_kernel(const __grid_constan
             philox_actions(seed, genv, t0 + (uint64_t)k, a);
             StepOut out;
             out.obs = nullptr;
-            const u32 before = s.ld(W_CTRL), before_ps = s.ld(W_PS);
-            step_env<false>(s, P, a, out);
+            const int before_o = h.completed_orders, before_p = h.total_packaged;
+            step_env_hot<false>(s, P, h, a, out);
             n_steps += 1;
-            n_orders += (unsigned long long)(out.info[1] - (int)((before >> 24) & 63u));
-            n_prod += (unsigned long long)(out.info[2] - (int)(before_ps & 511u));
+            n_orders += (unsigned long long)(h.completed_orders - before_o);
+            n_prod += (unsigned long long)(h.total_packaged - before_p);
             r40 += out.reward40;
             if (out.flags & 0x00ffffffu) {
                 ended = true;
                 n_eps += 1;
                 n_fault += (out.flags >> 16) & 0xffu ? 1 : 0;
+                s.st(W_EPISODE, h.episode);  // the only hot word the reset reads
             }
         }
-        warp_autoreset(s_state, tid, ended, num_orders, seed, genv - (uint64_t)(tid & 31));
+        if (warp_autoreset(s_state, tid, ended, num_orders, seed, genv - (uint64_t)(tid & 31))) load_hot(s, h);
     }
+    store_hot(s, h);
     // warp shuffle reduce, then one shared atomic per warp, one global atomic per CTA and counter
     unsigned long long v[6] = {n_steps, n_eps, n_orders, n_prod, n_fault, (unsigned long long)r40};
 #pragma unroll

@@ -99,7 +99,7 @@ int fjsp_create(const FjspConfig* cfg, int64_t num_envs, int64_t first_env, int 
         return cuda_fail(e, "cudaMalloc(state)");
     }
     e = cudaFuncSetAttribute(fjsp_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(fjsp_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_BYTES + 16);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fjsp_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ROLLOUT_SMEM_BYTES);
     if (e != cudaSuccess) {
         cudaFree(h->state);
         delete h;
@@ -254,7 +254,7 @@ int fjsp_rollout_random(FjspHandle* h, int steps, uint64_t seed, uint64_t t0, ui
     if (!stats || (reinterpret_cast<uintptr_t>(stats) & 7)) return fail("stats must be an 8-byte aligned device pointer (8 x u64)");
     if (seed != h->seed) return fail("rollout seed must equal the seed of the last fjsp_reset (one Philox key per handle)");
     DeviceGuard g(h->device);
-    fjsp_rollout_kernel<<<(unsigned)h->num_tiles, TILE, TILE_BYTES + 16, (cudaStream_t)stream>>>(
+    fjsp_rollout_kernel<<<(unsigned)h->num_tiles, TILE, ROLLOUT_SMEM_BYTES, (cudaStream_t)stream>>>(
         h->P, h->state, h->num_envs, h->first_env, seed, t0, steps, h->num_orders, reinterpret_cast<unsigned long long*>(stats));
     h->launches++;
     CK(cudaGetLastError());

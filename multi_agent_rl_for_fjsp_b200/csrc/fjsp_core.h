@@ -2,7 +2,9 @@
 //
 // This is the device code of the hot path (FJSPSimulation.step, /root/reference/FJSPSimulation.py:144-242,
 // and everything it calls in agents/*.py, models/*.py, utils/RewardModel.py).  It is written against an
-// abstract word accessor S { u32 ld(int w); void st(int w, u32 v); } so the same source runs
+// abstract word accessor S { u32 ld(int w); void st(int w, u32 v); u32 ld_hot(int w); void st_hot(int w, u32 v); }
+// (ld/st: the dynamically indexed words 24..127 — completion steps, orders, tray pool; ld_hot/st_hot: the 24 hot words,
+// always addressed with compile-time indices) so the same source runs
 //   * in the CUDA kernels with S = one column of a shared-memory tile  (fjsp_kernels.cu), and
 //   * in tests/host_harness (g++ build, tests only) with S = a plain array,
 // which lets the CPU-only test suite exercise the packed-state logic against the oracle.  The product
@@ -139,72 +141,72 @@ struct Hot {
 
 template <class S>
 FJSP_HD void load_hot(S& s, Hot& h) {
-    u32 w = s.ld(W_CTRL);
+    u32 w = s.ld_hot(W_CTRL);
     h.step = (int)(w & 0xffffu), h.num_orders = (int)((w >> 16) & 63u), h.fault = (int)((w >> 22) & 3u);
     h.completed_orders = (int)((w >> 24) & 63u);
-    w = s.ld(W_PS);
+    w = s.ld_hot(W_PS);
     h.total_packaged = (int)(w & 511u), h.next_order = (int)((w >> 9) & 63u), h.cur_order = (int)((w >> 15) & 63u);
     h.prod_idx = (int)((w >> 21) & 15u), h.cur_tray_count = (int)((w >> 25) & 7u);
-    w = s.ld(W_PSQ);
+    w = s.ld_hot(W_PSQ);
     h.alloc_count = (int)(w & 255u), h.ready_count = (int)((w >> 8) & 255u), h.ready_order = (int)((w >> 16) & 63u);
     h.ready_idx = (int)((w >> 22) & 15u);
-    w = s.ld(W_AGV);
+    w = s.ld_hot(W_AGV);
     h.agv_loc = (int)(w & 7u), h.agv_moving = (int)((w >> 3) & 1u), h.agv_target = (int)((w >> 4) & 7u);
     h.agv_arrive = (int)((w >> 7) & 0xffffu), h.carry = (int)((w >> 23) & 127u);
-    h.free_lo = s.ld(W_FREE_LO), h.free_hi = s.ld(W_FREE_HI), h.episode = s.ld(W_EPISODE);
-    w = s.ld(W_STORAGE);
+    h.free_lo = s.ld_hot(W_FREE_LO), h.free_hi = s.ld_hot(W_FREE_HI), h.episode = s.ld_hot(W_EPISODE);
+    w = s.ld_hot(W_STORAGE);
     h.storage.head = (int)(w & 63u), h.storage.tail = (int)((w >> 6) & 63u), h.storage.len = (int)((w >> 12) & 255u);
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         Mach& m = h.m[i];
-        w = s.ld(W_MACH + 2 * i);
+        w = s.ld_hot(W_MACH + 2 * i);
         m.busy = (int)(w & 1u), m.has_cur = (int)((w >> 1) & 1u), m.cur = (int)((w >> 2) & 63u);
         m.start = (int)((w >> 8) & 0xffffu), m.prog = (int)((w >> 24) & 1u), m.q.len = (int)((w >> 25) & 63u);
-        w = s.ld(W_MACH + 2 * i + 1);
+        w = s.ld_hot(W_MACH + 2 * i + 1);
         m.q.head = (int)(w & 63u), m.q.tail = (int)((w >> 6) & 63u), m.r.head = (int)((w >> 12) & 63u);
         m.r.tail = (int)((w >> 18) & 63u), m.r.len = (int)((w >> 24) & 63u);
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         Pack& p = h.p[i];
-        w = s.ld(W_PACK + 3 * i);
+        w = s.ld_hot(W_PACK + 3 * i);
         p.q.head = (int)(w & 63u), p.q.tail = (int)((w >> 6) & 63u), p.q.len = (int)((w >> 12) & 63u);
         p.f.head = (int)((w >> 18) & 63u), p.f.tail = (int)((w >> 24) & 63u);
-        w = s.ld(W_PACK + 3 * i + 1);
+        w = s.ld_hot(W_PACK + 3 * i + 1);
         p.f.len = (int)(w & 63u), p.users = (int)((w >> 6) & 31u), p.busy = (int)((w >> 11) & 1u);
         p.waiters = (int)((w >> 12) & 1u), p.hascur = (int)((w >> 13) & 1u), p.curprod = (int)((w >> 14) & 511u);
         p.qcount = (int)((w >> 23) & 255u);
-        w = s.ld(W_PACK + 3 * i + 2);
+        w = s.ld_hot(W_PACK + 3 * i + 2);
         p.completed = (int)(w & 255u), p.progL = (int)((w >> 8) & 255u);
     }
 }
 
 template <class S>
 FJSP_HD void store_hot(S& s, const Hot& h) {
-    s.st(W_CTRL, (u32)h.step | ((u32)h.num_orders << 16) | ((u32)h.fault << 22) | ((u32)h.completed_orders << 24));
-    s.st(W_PS, (u32)h.total_packaged | ((u32)h.next_order << 9) | ((u32)h.cur_order << 15) | ((u32)h.prod_idx << 21) |
+    s.st_hot(W_CTRL, (u32)h.step | ((u32)h.num_orders << 16) | ((u32)h.fault << 22) | ((u32)h.completed_orders << 24));
+    s.st_hot(W_PS, (u32)h.total_packaged | ((u32)h.next_order << 9) | ((u32)h.cur_order << 15) | ((u32)h.prod_idx << 21) |
                    ((u32)h.cur_tray_count << 25));
-    s.st(W_PSQ, (u32)h.alloc_count | ((u32)h.ready_count << 8) | ((u32)h.ready_order << 16) | ((u32)h.ready_idx << 22));
-    s.st(W_AGV, (u32)h.agv_loc | ((u32)h.agv_moving << 3) | ((u32)h.agv_target << 4) | ((u32)h.agv_arrive << 7) |
+    s.st_hot(W_PSQ, (u32)h.alloc_count | ((u32)h.ready_count << 8) | ((u32)h.ready_order << 16) | ((u32)h.ready_idx << 22));
+    s.st_hot(W_AGV, (u32)h.agv_loc | ((u32)h.agv_moving << 3) | ((u32)h.agv_target << 4) | ((u32)h.agv_arrive << 7) |
                     ((u32)h.carry << 23));
-    s.st(W_FREE_LO, h.free_lo), s.st(W_FREE_HI, h.free_hi), s.st(W_EPISODE, h.episode);
-    s.st(W_STORAGE, (u32)h.storage.head | ((u32)h.storage.tail << 6) | ((u32)h.storage.len << 12));
+    s.st_hot(W_FREE_LO, h.free_lo), s.st_hot(W_FREE_HI, h.free_hi), s.st_hot(W_EPISODE, h.episode);
+    s.st_hot(W_STORAGE, (u32)h.storage.head | ((u32)h.storage.tail << 6) | ((u32)h.storage.len << 12));
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         const Mach& m = h.m[i];
-        s.st(W_MACH + 2 * i, (u32)m.busy | ((u32)m.has_cur << 1) | ((u32)m.cur << 2) | ((u32)m.start << 8) |
+        s.st_hot(W_MACH + 2 * i, (u32)m.busy | ((u32)m.has_cur << 1) | ((u32)m.cur << 2) | ((u32)m.start << 8) |
                                  ((u32)m.prog << 24) | ((u32)m.q.len << 25));
-        s.st(W_MACH + 2 * i + 1, (u32)m.q.head | ((u32)m.q.tail << 6) | ((u32)m.r.head << 12) | ((u32)m.r.tail << 18) |
+        s.st_hot(W_MACH + 2 * i + 1, (u32)m.q.head | ((u32)m.q.tail << 6) | ((u32)m.r.head << 12) | ((u32)m.r.tail << 18) |
                                      ((u32)m.r.len << 24));
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const Pack& p = h.p[i];
-        s.st(W_PACK + 3 * i, (u32)p.q.head | ((u32)p.q.tail << 6) | ((u32)p.q.len << 12) | ((u32)p.f.head << 18) |
+        s.st_hot(W_PACK + 3 * i, (u32)p.q.head | ((u32)p.q.tail << 6) | ((u32)p.q.len << 12) | ((u32)p.f.head << 18) |
                                  ((u32)p.f.tail << 24));
-        s.st(W_PACK + 3 * i + 1, (u32)p.f.len | ((u32)p.users << 6) | ((u32)p.busy << 11) | ((u32)p.waiters << 12) |
+        s.st_hot(W_PACK + 3 * i + 1, (u32)p.f.len | ((u32)p.users << 6) | ((u32)p.busy << 11) | ((u32)p.waiters << 12) |
                                      ((u32)p.hascur << 13) | ((u32)p.curprod << 14) | ((u32)p.qcount << 23));
-        s.st(W_PACK + 3 * i + 2, (u32)p.completed | ((u32)p.progL << 8));
+        s.st_hot(W_PACK + 3 * i + 2, (u32)p.completed | ((u32)p.progL << 8));
     }
 }
 
@@ -292,15 +294,17 @@ FJSP_HD void philox_actions(uint64_t seed, uint64_t genv, uint64_t t, int a[8]) 
 // Everything of a fresh env except the 32 order words (the kernels fill those warp-cooperatively, one order per lane).
 template <class S>
 FJSP_HD void reset_env_base(S& s, int num_orders, u32 episode) {
-#pragma unroll 8
-    for (int w = 0; w < W_ORDER; w++) s.st(w, 0u);
+#pragma unroll
+    for (int w = 0; w < W_CSTEP; w++) s.st_hot(w, 0u);
+#pragma unroll
+    for (int w = W_CSTEP; w < W_ORDER; w++) s.st(w, 0u);
 #pragma unroll 8
     for (int w = W_POOL; w < W_TOTAL; w++) s.st(w, 0u);
-    s.st(W_CTRL, (u32)num_orders << 16);
-    s.st(W_PS, 63u << 15);         // cur_order = none
-    s.st(W_AGV, (u32)LOC_PICKUP);  // AGVAgent.py:41
-    s.st(W_FREE_LO, 0xffffffffu), s.st(W_FREE_HI, 0xffffffffu);
-    s.st(W_EPISODE, episode);
+    s.st_hot(W_CTRL, (u32)num_orders << 16);
+    s.st_hot(W_PS, 63u << 15);         // cur_order = none
+    s.st_hot(W_AGV, (u32)LOC_PICKUP);  // AGVAgent.py:41
+    s.st_hot(W_FREE_LO, 0xffffffffu), s.st_hot(W_FREE_HI, 0xffffffffu);
+    s.st_hot(W_EPISODE, episode);
 }
 
 template <class S>

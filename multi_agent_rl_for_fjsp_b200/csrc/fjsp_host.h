@@ -75,6 +75,8 @@ struct ArrayState {
     u32* w;
     FJSP_HD u32 ld(int i) const { return w[i]; }
     FJSP_HD void st(int i, u32 v) { w[i] = v; }
+    FJSP_HD u32 ld_hot(int i) const { return w[i]; }
+    FJSP_HD void st_hot(int i, u32 v) { w[i] = v; }
 };
 
 // ---- canonical record S from packed words ----

@@ -2,14 +2,16 @@
 //
 // HBM layout: the packed state is an ARRAY OF TILES.  One tile = 64 envs x 128 words, stored
 // word-major  tile[w][lane]  (u32), i.e. 32 KB that are contiguous in HBM.  A CTA owns one tile per step:
-//   1. one elected thread issues ONE bulk async copy (TMA engine, cp.async.bulk, SASS UBLKCP) of the 32 KB tile
-//      into shared memory and arms an mbarrier with the byte count; the other threads meanwhile fetch the
-//      8 action bytes of their env with a coalesced 64-bit load;
-//   2. every thread steps its own env out of shared memory (thread t owns column t of the [128][64] tile, so all
-//      accesses of a warp hit 32 distinct banks regardless of the word index each lane follows — the FIFO
-//      pointer chasing is conflict-free by construction);
+//   1. one elected thread issues ONE bulk async copy (TMA engine, cp.async.bulk, SASS UBLKCP) of the tile's 26 KB of
+//      dynamically indexed words (24..127: completion steps, orders, tray pool) into shared memory and arms an
+//      mbarrier with the byte count; all threads meanwhile fetch their 24 hot words (coalesced 32-bit loads: a warp
+//      reads 128 consecutive bytes per word) and the 8 action bytes of their env (coalesced 64-bit load);
+//   2. every thread steps its own env: hot words in registers, the rest out of shared memory (thread t owns column t
+//      of the [104][64] sub-tile, so all accesses of a warp hit 32 distinct banks regardless of the word index each
+//      lane follows — the FIFO pointer chasing is conflict-free by construction);
 //   3. observations are staged row-major in shared memory; masks / rewards / flags leave as 128-bit stores;
-//   4. after a proxy fence + barrier the elected thread issues two bulk async stores (state tile, observation rows).
+//   4. hot words go back with coalesced 32-bit stores; after a proxy fence + barrier the elected thread issues two bulk
+//      async stores (the 26 KB sub-tile, the observation rows).
 // Nothing but the step's own inputs and outputs crosses HBM: 512 B state in, 512 B state out, 8 + 152 + 32 + 32 + 4
 // bytes of I/O per env-step.
 #pragma once
@@ -23,21 +25,32 @@ namespace fjsp {
 constexpr int TILE = FJSP_TILE_ENVS;                       // 64 envs per tile
 constexpr int TILE_WORDS = FJSP_STATE_WORDS * TILE;        // 8192 u32
 constexpr int TILE_BYTES = TILE_WORDS * 4;                 // 32768
+constexpr int HOT_BYTES = W_CSTEP * TILE * 4;              // 6144: words 0..23, through registers (coalesced LDG/STG)
+constexpr int DYN_WORDS = (W_TOTAL - W_CSTEP) * TILE;      // words 24..127, through shared memory (one bulk copy)
+constexpr int DYN_BYTES = DYN_WORDS * 4;                   // 26624
 constexpr int OBS_ROW_BYTES = FJSP_OBS_DIM * 4;            // 152
 constexpr int OBS_TILE_BYTES = OBS_ROW_BYTES * TILE;       // 9728
-constexpr int STEP_SMEM_BYTES = TILE_BYTES + OBS_TILE_BYTES + 16;
+constexpr int STEP_SMEM_BYTES = DYN_BYTES + OBS_TILE_BYTES + 16;
+constexpr int ROLLOUT_SMEM_BYTES = DYN_BYTES + 16;
 
-// One column of a shared-memory tile: word w of this thread's env.
-struct SmemColumn {
-    u32* base;  // &tile[0][lane]
-    __device__ __forceinline__ u32 ld(int w) const { return base[w * TILE]; }
-    __device__ __forceinline__ void st(int w, u32 v) { base[w * TILE] = v; }
+// One env of a tile inside a kernel: the dynamically indexed words (24..127) live in shared memory, column `lane` of
+// the [104][64] sub-tile; the 24 hot words are read/written straight from/to the HBM tile with compile-time indices
+// (a warp touches 128 consecutive bytes per word: coalesced) and otherwise live in registers (struct Hot).
+struct TileColumn {
+    u32* dyn;  // &s_dyn[0][lane] - W_CSTEP * TILE, so dyn[w * TILE] is word w
+    u32* hot;  // &g_tile[0][lane]
+    __device__ __forceinline__ u32 ld(int w) const { return dyn[w * TILE]; }
+    __device__ __forceinline__ void st(int w, u32 v) { dyn[w * TILE] = v; }
+    __device__ __forceinline__ u32 ld_hot(int w) const { return hot[w * TILE]; }
+    __device__ __forceinline__ void st_hot(int w, u32 v) { hot[w * TILE] = v; }
 };
-// Same column addressed directly in HBM (reset / export paths, not hot).
+// Whole column addressed directly in HBM (reset / export paths, not hot).
 struct GmemColumn {
     u32* base;
     __device__ __forceinline__ u32 ld(int w) const { return base[w * TILE]; }
     __device__ __forceinline__ void st(int w, u32 v) { base[w * TILE] = v; }
+    __device__ __forceinline__ u32 ld_hot(int w) const { return base[w * TILE]; }
+    __device__ __forceinline__ void st_hot(int w, u32 v) { base[w * TILE] = v; }
 };
 
 // ---- PTX wrappers (mbarrier + bulk async copy; see /opt/skills/guides/blackwell_cuda_programming.md) ----
@@ -78,16 +91,15 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // and store them into the ending lane's shared-memory column; the ending lane itself re-initialises its scalars.
 // A per-lane reset would make the whole warp wait for 32 sequential Philox calls whenever ANY of its envs ends.
 // Must be called by all 32 lanes of the warp.  Returns true for lanes that were reset.
-__device__ __forceinline__ bool warp_autoreset(u32* s_state, int tid, bool do_reset, int num_orders, uint64_t seed,
-                                               uint64_t genv_lane0) {
+__device__ __forceinline__ bool warp_autoreset(TileColumn s, u32* s_dyn, int tid, bool do_reset, u32 cur_episode,
+                                               int num_orders, uint64_t seed, uint64_t genv_lane0) {
     const unsigned need = __ballot_sync(0xffffffffu, do_reset);
     if (need == 0u) return false;
     const int lane = tid & 31, wbase = tid & ~31;
-    SmemColumn s{s_state + tid};
     u32 episode = 0u;
     if (do_reset) {
-        episode = s.ld(W_EPISODE) + 1u;
-        reset_env_base(s, num_orders, episode);
+        episode = cur_episode + 1u;
+        reset_env_base(s, num_orders, episode);  // hot words go to the HBM tile; the caller reloads its registers
     }
     unsigned rem = need;
     while (rem) {
@@ -95,7 +107,7 @@ __device__ __forceinline__ bool warp_autoreset(u32* s_state, int tid, bool do_re
         rem &= rem - 1u;
         const u32 ep = __shfl_sync(0xffffffffu, episode, src);
         const u32 ow = lane < num_orders ? philox_order(seed, genv_lane0 + (uint64_t)src, ep, lane) : 0u;
-        s_state[(W_ORDER + lane) * TILE + wbase + src] = ow;
+        s_dyn[(W_ORDER - W_CSTEP + lane) * TILE + wbase + src] = ow;
     }
     __syncwarp();
     return do_reset;
@@ -146,9 +158,9 @@ __global__ void __launch_bounds__(TILE) fjsp_reset_kernel(const __grid_constant_
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__ Params P, const StepArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    u32* s_state = reinterpret_cast<u32*>(smem_raw);
-    float* s_obs = reinterpret_cast<float*>(smem_raw + TILE_BYTES);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + TILE_BYTES + OBS_TILE_BYTES);
+    u32* s_dyn = reinterpret_cast<u32*>(smem_raw);
+    float* s_obs = reinterpret_cast<float*>(smem_raw + DYN_BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + DYN_BYTES + OBS_TILE_BYTES);
 
     const int tid = threadIdx.x;
     const int64_t tile = A.tile_begin + blockIdx.x;
@@ -158,11 +170,14 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
 
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
-    if (tid == 0) {
-        mbar_expect_tx(bar, TILE_BYTES);
-        bulk_g2s(s_state, g_tile, TILE_BYTES, bar);
+    if (tid == 0) {  // ONE bulk async copy (TMA engine) for the 26 KB of dynamically indexed words of the tile
+        mbar_expect_tx(bar, DYN_BYTES);
+        bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, DYN_BYTES, bar);
     }
-    // coalesced 64-bit action fetch overlaps the tile copy
+    // meanwhile: the 24 hot words (coalesced 32-bit loads, straight into registers) and the 8 action bytes (64-bit load)
+    TileColumn s{s_dyn + tid - W_CSTEP * TILE, g_tile + tid};
+    Hot h;
+    load_hot(s, h);
     int a[8];
     {
         uint2 av = make_uint2(0u, 0u);
@@ -172,17 +187,18 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
     }
     mbar_wait(bar, 0);
 
-    // padding lanes of a ragged last tile are inert: their columns travel through shared memory unchanged
-    SmemColumn s{s_state + tid};
+    // padding lanes of a ragged last tile are inert: their words travel through unchanged
     StepOut out;
     out.obs = s_obs + tid * FJSP_OBS_DIM;
     out.flags = 0u;
-    if (valid) step_env<true>(s, P, a, out);
+    if (valid) step_env_hot<true>(s, P, h, a, out);
     const bool ended = valid && A.autoreset && (out.flags & 0x00ffffffu);
-    if (warp_autoreset(s_state, tid, ended, A.num_orders, A.seed, (uint64_t)(A.first_env + env - (tid & 31)))) {
-        observe_env(s, P, out.obs, out.mask);  // the observation returned with an ended episode is the new episode's first
+    if (warp_autoreset(s, s_dyn, tid, ended, h.episode, A.num_orders, A.seed, (uint64_t)(A.first_env + env - (tid & 31)))) {
+        load_hot(s, h);
+        observe(s, P, h, out.obs, out.mask);  // the observation returned with an ended episode is the new episode's first
         out.flags |= 1u << 24;
     }
+    store_hot(s, h);
     if (valid) {
         uint4* m4 = reinterpret_cast<uint4*>(A.masks + env * FJSP_MASK_DIM);
         m4[0] = make_uint4(out.mask[0], out.mask[1], out.mask[2], out.mask[3]);
@@ -201,7 +217,7 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
     const int nvalid = remaining >= TILE ? TILE : (int)remaining;
     const bool obs_bulk = ((nvalid * OBS_ROW_BYTES) & 15) == 0 && ((reinterpret_cast<uintptr_t>(A.obs) & 15) == 0);
     if (tid == 0) {
-        bulk_s2g(g_tile, s_state, TILE_BYTES);
+        bulk_s2g(g_tile + W_CSTEP * TILE, s_dyn, DYN_BYTES);
         if (obs_bulk) bulk_s2g(A.obs + tile * TILE * FJSP_OBS_DIM, s_obs, (uint32_t)(nvalid * OBS_ROW_BYTES));
         bulk_commit();
     }
@@ -234,8 +250,8 @@ __global__ void __launch_bounds__(TILE) fjsp_rollout_kernel(const __grid_constan
                                                              int64_t first_env, uint64_t seed, uint64_t t0, int steps,
                                                              int num_orders, unsigned long long* stats) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    u32* s_state = reinterpret_cast<u32*>(smem_raw);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + TILE_BYTES);
+    u32* s_dyn = reinterpret_cast<u32*>(smem_raw);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + DYN_BYTES);
     __shared__ unsigned long long s_acc[6];
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
@@ -246,16 +262,16 @@ __global__ void __launch_bounds__(TILE) fjsp_rollout_kernel(const __grid_constan
     if (tid < 6) s_acc[tid] = 0ull;
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(bar, TILE_BYTES);
-        bulk_g2s(s_state, g_tile, TILE_BYTES, bar);
+        mbar_expect_tx(bar, DYN_BYTES);
+        bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, DYN_BYTES, bar);
     }
+    TileColumn s{s_dyn + tid - W_CSTEP * TILE, g_tile + tid};
+    Hot h;  // hot words live in registers for the whole launch
+    load_hot(s, h);
     mbar_wait(bar, 0);
-    SmemColumn s{s_state + tid};
     unsigned long long n_steps = 0, n_eps = 0, n_orders = 0, n_prod = 0, n_fault = 0;
     long long r40 = 0;
     const uint64_t genv = (uint64_t)(first_env + env);
-    Hot h;  // hot words live in registers for the whole launch; shared memory only sees them around a reset
-    load_hot(s, h);
     for (int k = 0; k < steps; k++) {  // uniform trip count: all lanes stay together for the cooperative reset
         bool ended = false;
         if (valid) {
@@ -273,10 +289,9 @@ __global__ void __launch_bounds__(TILE) fjsp_rollout_kernel(const __grid_constan
                 ended = true;
                 n_eps += 1;
                 n_fault += (out.flags >> 16) & 0xffu ? 1 : 0;
-                s.st(W_EPISODE, h.episode);  // the only hot word the reset reads
             }
         }
-        if (warp_autoreset(s_state, tid, ended, num_orders, seed, genv - (uint64_t)(tid & 31))) load_hot(s, h);
+        if (warp_autoreset(s, s_dyn, tid, ended, h.episode, num_orders, seed, genv - (uint64_t)(tid & 31))) load_hot(s, h);
     }
     store_hot(s, h);
     // warp shuffle reduce, then one shared atomic per warp, one global atomic per CTA and counter
@@ -291,7 +306,7 @@ __global__ void __launch_bounds__(TILE) fjsp_rollout_kernel(const __grid_constan
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
-        bulk_s2g(g_tile, s_state, TILE_BYTES);
+        bulk_s2g(g_tile + W_CSTEP * TILE, s_dyn, DYN_BYTES);
         bulk_commit();
     }
     if (tid < 6) atomicAdd(&stats[tid], s_acc[tid]);

@@ -39,8 +39,8 @@ BYTES_IO = 8 + 152 + 32 + 32 + 4
 STATE_BYTES = 512
 BYTES_PER_ENV_STEP = BYTES_IO + 2 * STATE_BYTES  # 1252
 # dram__bytes_read.sum + dram__bytes_write.sum of one fjsp_step_kernel launch at 2^20 envs, from the committed
-# `ncu --set full` capture profiles/r01_step_kernel_full_raw.csv (545.3 MB + 715.6 MB); only valid for the default size
-NCU_TRAFFIC_BYTES_2P20 = 545.326592e6 + 715.646720e6
+# `ncu --set full` capture profiles/r01_step_kernel_full_raw.csv (545.4 MB + 714.2 MB); only valid for the default size
+NCU_TRAFFIC_BYTES_2P20 = 545.384192e6 + 714.157056e6
 SEED = 20261018
 NUM_ORDERS = 30
 

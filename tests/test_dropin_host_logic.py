@@ -147,3 +147,32 @@ def test_reference_heuristic_policy_drives_facade_like_reference(facade_cls):
             assert r2 == pytest.approx(r1, rel=1e-6) and te1 == te2 and tr1 == tr2
             total_ref += sum(r1.values()); total += sum(r2.values()); steps += 1
         assert not env.agents and i1["agv"]["orders_completed"] == i2["agv"]["orders_completed"] >= 1
+
+
+@pytest.mark.reference
+def test_reference_cli_heuristic_test_run_prints_the_same_summary(tmp_path):
+    """`train.py --test_only --heuristic --load_path checkpoints/model.pt` (the reference's CLI, its own load_model and
+    heuristic test loop) prints the same TEST COMPLETE summary on the facade as on the reference's own env."""
+    args = "['--test_only', '--heuristic', '--load_path', %r, '--test_orders', '5', '--max_steps', '400']" % (
+        refload.REFERENCE_ROOT + "/checkpoints/model.pt")
+    ours = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import tests.fake_device_env as f\n"
+        "import multi_agent_rl_for_fjsp_b200.env as e\n"
+        "e.BatchedFJSPEnv = f.FakeBatchedFJSPEnv\n"
+        "from multi_agent_rl_for_fjsp_b200 import run_reference_caller as r\n"
+        "r.main([%r, 'train.py'] + %s)\n") % (REPO, refload.REFERENCE_ROOT, args)
+    theirs = (
+        "import sys, runpy; sys.path.insert(0, %r)\n"
+        "from oracle import refload\n"
+        "refload.load_reference()\n"
+        "sys.argv = [%r] + %s\n"
+        "runpy.run_path(%r, run_name='__main__')\n") % (REPO, refload.REFERENCE_ROOT + "/train.py", args,
+                                                        refload.REFERENCE_ROOT + "/train.py")
+    outs = []
+    for code in (ours, theirs):
+        p = subprocess.run([sys.executable, "-c", code], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        tail = p.stdout[p.stdout.index("TEST COMPLETE"):]
+        outs.append([ln.strip() for ln in tail.splitlines() if ":" in ln])
+    assert outs[0] == outs[1] and any("Orders completed" in ln for ln in outs[0]), outs

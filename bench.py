@@ -217,6 +217,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the environment step exists only as sm_100a kernels (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from multi_agent_rl_for_fjsp_b200.dist import bind_to_gpu_numa
+
+    numa_cpus = bind_to_gpu_numa(local_rank)  # before any pinned allocation: first touch on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -375,7 +378,7 @@ def run_ours(args):
                          "traffic": args.ncu_traffic_bytes if E == (1 << 20) else None, "peak_source": peak_src, "kernel": "fjsp_step_kernel",
                          "algorithmic_bytes_per_launch": E * BYTES_PER_ENV_STEP},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 8, "d2h_bytes_per_step": E * (152 + 32 + 32 + 4),
-                    "steps": Ke, "api": "fjsp_step_host (pinned host buffers)", "pcie_d2h_gbs_measured": d2h_gbs,
+                    "steps": Ke, "api": "fjsp_step_host (pinned host buffers)", "pcie_d2h_gbs_measured": d2h_gbs, "host_cpus_bound": len(numa_cpus),
                     "pcie_bound_frac": (E * 220 / (d2h_gbs * 1e9)) / (e2e_s / Ke)},
             "gpu_launches": launches, "clocks": clocks,
         }

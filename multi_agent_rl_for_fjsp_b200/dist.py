@@ -24,6 +24,27 @@ def shard_range(total_envs: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def bind_to_gpu_numa(gpu_index: int) -> list:
+    """Pin this process to the CPUs NVML reports as local to `gpu_index`, so pinned host buffers allocated afterwards
+    are first-touched on the GPU's own NUMA node (matters when 8 ranks stream results to the host at once).
+    Returns the CPU list it bound to ([] if NVML or the affinity call is unavailable)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:  # noqa: BLE001
+        return []
+
+
 def init(backend: str | None = None, device: torch.device | None = None):
     rank, local_rank, world = world_info()
     if world > 1 and not dist.is_initialized():

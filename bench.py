@@ -362,6 +362,20 @@ def run_ours(args):
                "gradient_allreduce": "nccl, one flat 2.62 MB bucket" if world > 1 else "none (1 GPU)",
                "note": "1 frame = 1 env step consumed by training (rollout + update); reference CPU: 17-33 frames/s (BASELINE.md)"}
         del tr, ea
+        # same run with TF32 tensor-core GEMMs (fp32 storage and accumulation), reported separately, never as the headline
+        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            eb = BatchedFJSPEnv(4096, device=dev, first_env=rank * 4096, seed=SEED + 1, num_orders=25, autoreset=True)
+            tb = BatchedA2C(eb, rollout_len=32, seed=1)
+            tb.train(3)
+            barrier()
+            _, secs_tf = tb.train(20)
+            secs_tf = max_over_ranks(secs_tf)
+            a2c["tf32_variant_frames_per_sec"] = world * 4096 * 32 * 20 / secs_tf
+            del tb, eb
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev_tf32
 
     if rank == 0:
         peak, peak_src = measured_peak()

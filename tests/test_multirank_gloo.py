@@ -75,3 +75,14 @@ def test_shard_range_properties():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         fdist.shard_range(10, 2, 2)
+
+
+def test_numa_binding_helper_is_safe_without_a_gpu():
+    import os
+
+    before = os.sched_getaffinity(0)
+    cpus = fdist.bind_to_gpu_numa(0)  # no NVML device here: must return [] and leave the affinity alone
+    assert isinstance(cpus, list)
+    if not cpus:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)

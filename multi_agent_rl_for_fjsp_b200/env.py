@@ -60,10 +60,16 @@ class BatchedFJSPEnv:
         self.flags = torch.zeros((n, 4), dtype=torch.uint8, **kw)
         self.results = torch.zeros((n, 8), dtype=torch.uint8, **kw) if with_infos else None
         self.infos = torch.zeros((n, 4), dtype=torch.int32, **kw) if with_infos else None
+        self._term, self._trunc = self.flags[:, 0], self.flags[:, 1]
         self._actions = torch.zeros((n, 8), dtype=torch.uint8, **kw)
         self._stats = torch.zeros(8, dtype=torch.int64, **kw)
         self._t = 0
         self._host = None
+        # constant argument block of fjsp_step for the env's own output tensors (built once: the eager call path is
+        # launch-latency bound at small batch sizes, so per-call Python work matters)
+        self._out_ptrs = (_ptr(self.obs), _ptr(self.masks), _ptr(self.rewards), _ptr(self.flags), _ptr(self.results),
+                          _ptr(self.infos))
+        self._fjsp_step = self._L.fjsp_step
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -131,10 +137,13 @@ class BatchedFJSPEnv:
         if a.dtype != torch.uint8 or a.device != self.device or not a.is_contiguous():
             a = a.to(device=self.device, dtype=torch.uint8).contiguous()
         assert a.shape == (self.num_envs, 8), a.shape
-        abi.check(self._L.fjsp_step(self._h, _ptr(a), _ptr(self.obs), _ptr(self.masks), _ptr(self.rewards), _ptr(self.flags),
-                                    _ptr(self.results), _ptr(self.infos), int(self.autoreset), self._stream()))
+        o = self._out_ptrs
+        rc = self._fjsp_step(self._h, a.data_ptr(), o[0], o[1], o[2], o[3], o[4], o[5], self.autoreset,
+                             torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            abi.check(rc)
         self._t += 1
-        return self.obs, self.rewards, self.flags[:, 0], self.flags[:, 1], self.masks
+        return self.obs, self.rewards, self._term, self._trunc, self.masks
 
     def step_into(self, actions: torch.Tensor, obs: torch.Tensor, masks: torch.Tensor, rewards: torch.Tensor,
                   flags: torch.Tensor):

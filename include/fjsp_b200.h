@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define FJSP_ABI_VERSION 1
+#define FJSP_ABI_VERSION 2
 
 /* ---- fixed shape of the problem (reference: 8 agents, FJSPSimulation.py:62-82) ---- */
 #define FJSP_NUM_AGENTS 8          /* pickup_station, agv, small_machine, big_machine, packaging_blue_1, _blue_2, _red, _green */
@@ -38,7 +38,19 @@ extern "C" {
 #define FJSP_TRAY_CAPACITY 5       /* constants.py:22; the mask hard-codes the global (PickupStationAgent.py:125) */
 #define FJSP_POOL_SLOTS 64         /* trays in transit per env (bound: 1 + max_episode_steps/4 = 51) */
 #define FJSP_STATE_WORDS 128       /* packed state: 128 x u32 = 512 B per env */
-#define FJSP_TILE_ENVS 64          /* envs per HBM tile (array-of-tiles, each tile word-major [128][64]) */
+#define FJSP_TILE_ENVS 64          /* envs per HBM tile (array-of-tiles, each tile word-major [words][64]) */
+
+/* ---- scaled shop (BASELINE configs[4], builder-defined extension): K = num_cells "cells", each with its
+ * own AGV, small machine, big machine, four packaging stations, storage and tray pool, sharing ONE pickup station /
+ * order stream and its single dock.  K = 1 is the reference shop, bit for bit.  Agents (and the action / reward /
+ * result columns): pickup_station, then per cell: agv, small_machine, big_machine, packaging_blue_1, _blue_2, _red,
+ * _green.  Row widths below; K = 1 gives the reference's 8 / 38 / 32. */
+#define FJSP_MAX_CELLS 4
+#define FJSP_AGENTS_K(k) (1 + 7 * (k))
+#define FJSP_ACT_DIM_K(k) ((FJSP_AGENTS_K(k) + 7) / 8 * 8)      /* actions u8, rewards f32, results u8 per env */
+#define FJSP_OBS_DIM_K(k) (7 + 31 * (k))
+#define FJSP_MASK_DIM_K(k) ((3 + 26 * (k) + 31) / 32 * 32)
+#define FJSP_STATE_WORDS_K(k) (64 + 64 * (k) + 20 * ((k) - 1))  /* 128 words for K = 1, 380 for K = 4 */
 
 /* fault codes (flags[2]); the reference has no equivalent — see DESIGN.md "faults" */
 #define FJSP_FAULT_NONE 0
@@ -58,6 +70,7 @@ typedef struct FjspConfig {
     int32_t pack_capacity;                 /* PackagingAgent.py:46 simpy.Resource(capacity=20); <= 31 */
     int32_t tray_capacity;                 /* must be 5 */
     int32_t num_trays;                     /* constants.py:21; min(num_trays,1000) reach the pickup station (FJSPSimulation.py:96) */
+    int32_t num_cells;                     /* 1 = the reference shop; 2..4 = scaled shop (see above) */
 } FjspConfig;
 
 /* One order as the reference generates it (FJSPSimulation.py:101-131): all products of an order
@@ -153,8 +166,11 @@ int fjsp_random_actions(FjspHandle* h, uint64_t seed, uint64_t t, uint8_t* actio
  * t = t0 .. t0+steps-1) and autoreset, state kept on-chip between steps; adds to stats[8] (device u64). */
 int fjsp_rollout_random(FjspHandle* h, int steps, uint64_t seed, uint64_t t0, uint64_t* stats, void* stream);
 
-/* Canonical record S of one env, decoded on the host (synchronises). Diagnostic / parity path. */
+/* Canonical record S of one env, decoded on the host (synchronises). Diagnostic / parity path.
+ * For a scaled shop the record describes ONE cell (AGV, machines, storage, packaging) plus the shared pickup station
+ * and order table; fjsp_export_state is cell 0. */
 int fjsp_export_state(FjspHandle* h, int64_t env, FjspCanonState* out);
+int fjsp_export_state_cell(FjspHandle* h, int64_t env, int cell, FjspCanonState* out);
 /* Raw packed words of one env (128 x u32) copied to the host (synchronises). */
 int fjsp_export_packed(FjspHandle* h, int64_t env, uint32_t* out_words);
 

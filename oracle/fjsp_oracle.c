@@ -99,6 +99,19 @@ typedef struct Pack {
     int ncreated;
 } Pack;
 
+typedef struct Cell {
+    /* agv */
+    int agv_row, agv_col;
+    Tray* carrying;
+    int is_moving;
+    int move_created_now, move_target_loc, move_arrive_step;
+    int holds_dock; /* scaled shop: this AGV occupies (or has been granted) the single dock of the pickup station */
+    /* machines, storage, packaging */
+    Machine machine[2]; /* 0 small, 1 big */
+    TrayList storage;
+    Pack pack[4];
+} Cell;
+
 typedef struct OracleEnv {
     FjspConfig cfg;
     int small_steps, big_steps, pack_steps;
@@ -115,15 +128,9 @@ typedef struct OracleEnv {
     int trays_next; /* trays_at_station = ids (ntrays_total-1-trays_next) downwards */
     Tray* current_tray;
     TrayList ps_ready;
-    /* agv */
-    int agv_row, agv_col;
-    Tray* carrying;
-    int is_moving;
-    int move_created_now, move_target_loc, move_arrive_step;
-    /* machines, storage, packaging */
-    Machine machine[2]; /* 0 small, 1 big */
-    TrayList storage;
-    Pack pack[4];
+    /* cells: each has its AGV, machines, storage and packaging stations (one cell = the reference shop) */
+    struct Cell cells[FJSP_MAX_CELLS];
+    int ncells;
     /* tracking */
     int current_step, completed_orders, total_products_packaged, fault;
 } OracleEnv;
@@ -153,9 +160,9 @@ static int tray_needs_packaging(const Tray* t) {
 static int tray_type(const Tray* t) { return t->n ? t->products[0]->type : 0; }
 
 /* AGVAgent._get_current_location (AGVAgent.py:398-403): first LocationType whose cell matches */
-static int agv_location(const OracleEnv* e) {
+static int agv_location(const OracleEnv* e, const Cell* c) {
     for (int l = 0; l < FJSP_NUM_LOCATIONS; l++)
-        if (e->cfg.pos[l][0] == e->agv_row && e->cfg.pos[l][1] == e->agv_col) return l;
+        if (e->cfg.pos[l][0] == c->agv_row && e->cfg.pos[l][1] == c->agv_col) return l;
     return LOC_NONE;
 }
 
@@ -172,6 +179,7 @@ int fjsp_oracle_default_config(FjspConfig* c) {
     c->proc_small = 60, c->proc_big = 120, c->proc_pack = 30; /* constants.py:14-18 */
     c->step_size = 10, c->agv_speed = 1, c->max_episode_steps = 200;
     c->storage_capacity = 100, c->pack_capacity = 20, c->tray_capacity = 5, c->num_trays = 1000;
+    c->num_cells = 1;
     return 0;
 }
 
@@ -193,12 +201,19 @@ void fjsp_oracle_reset(OracleEnv* e, const FjspOrderRec* orders, int num_orders)
     int ss = e->small_steps, bs = e->big_steps, ps = e->pack_steps;
     memset(e, 0, sizeof(*e));
     e->cfg = cfg, e->small_steps = ss, e->big_steps = bs, e->pack_steps = ps;
-    /* _init_agents (:62-82) */
-    e->agv_row = cfg.pos[LOC_PICKUP][0], e->agv_col = cfg.pos[LOC_PICKUP][1]; /* AGVAgent.py:41 */
-    e->machine[0].proc_steps = ss;
-    e->machine[1].proc_steps = bs;
-    e->pack[0].colour = COL_BLUE, e->pack[1].colour = COL_BLUE; /* FJSPSimulation.py:68-73 */
-    e->pack[2].colour = COL_RED, e->pack[3].colour = COL_GREEN;
+    /* _init_agents (:62-82), once per cell */
+    e->ncells = cfg.num_cells < 1 ? 1 : (cfg.num_cells > FJSP_MAX_CELLS ? FJSP_MAX_CELLS : cfg.num_cells);
+    for (int ci = 0; ci < e->ncells; ci++) {
+        Cell* c = &e->cells[ci];
+        /* AGVAgent.py:41: the AGV starts at PICKUP; the dock holds one AGV, so AGVs of further cells start at STORAGE */
+        const int start = ci == 0 ? LOC_PICKUP : LOC_STORAGE;
+        c->agv_row = cfg.pos[start][0], c->agv_col = cfg.pos[start][1];
+        c->holds_dock = ci == 0;
+        c->machine[0].proc_steps = ss;
+        c->machine[1].proc_steps = bs;
+        c->pack[0].colour = COL_BLUE, c->pack[1].colour = COL_BLUE; /* FJSPSimulation.py:68-73 */
+        c->pack[2].colour = COL_RED, c->pack[3].colour = COL_GREEN;
+    }
     /* _init_trays (:89-98): ids 0..num_trays-1, popped from the END into trays_at_station, at most 1000 */
     e->ntrays_total = cfg.num_trays < 1000 ? cfg.num_trays : 1000; /* tray i (allocation order) has id num_trays-1-i */
     /* generate_order x num_orders (:101-131, :315-318) */
@@ -224,8 +239,84 @@ static int order_queue_len(const OracleEnv* e) { return e->norders - e->order_qu
 static int trays_at_station(const OracleEnv* e) { return e->ntrays_total - e->trays_next; }
 static int pack_has_capacity(const OracleEnv* e, const Pack* p) { return p->users < e->cfg.pack_capacity; } /* PackagingAgent.py:149-153 */
 
+/* scaled shop: the pickup station has ONE dock; another cell's AGV standing there or under way to it blocks it */
+static int dock_blocked_for(const OracleEnv* e, const Cell* c) {
+    for (int ci = 0; ci < e->ncells; ci++)
+        if (&e->cells[ci] != c && e->cells[ci].holds_dock) return 1;
+    return 0;
+}
+
+/* one cell's block of the observation: AGV (13) + small/big machine (3 + 3) + four packaging stations (12) = 31 floats,
+ * and of the masks: 8 + 3 + 3 + 12 = 26 bytes */
+static void observe_cell(const OracleEnv* e, const Cell* c, float* obs, int8_t* masks) {
+    /* --- AGV: AGVAgent.get_observation (:53-76), keys sorted --- */
+    const Machine* sm = &c->machine[0];
+    const Machine* bm = &c->machine[1];
+    const Tray* tr = c->carrying;
+    obs[0] = (float)bm->is_busy;
+    obs[1] = (float)bm->ready.n;
+    obs[2] = (float)(tr ? 1 : 0);
+    obs[3] = (float)e->ps_ready.n;
+    obs[4] = (float)c->agv_row, obs[5] = (float)c->agv_col;
+    obs[6] = (float)sm->is_busy;
+    obs[7] = (float)sm->ready.n;
+    obs[8] = (float)c->storage.n;
+    obs[9] = (float)(tr && tray_needs_packaging(tr));
+    obs[10] = (float)(tr && tray_needs_processing(tr));
+    obs[11] = (float)(tr ? tr->n : 0);
+    obs[12] = (float)(tr ? tray_type(tr) : 0);
+    /* get_action_mask (:79-178) */
+    {
+        int8_t* m = masks;
+        m[0] = 1;
+        if (!c->is_moving) {
+            int loc = agv_location(e, c);
+            static const int move_loc[6] = {-1, LOC_PICKUP, LOC_SMALL, LOC_BIG, LOC_STORAGE, LOC_PACKAGING};
+            for (int a = 1; a <= 5; a++) m[a] = (int8_t)(loc != move_loc[a]);
+            if (m[1] && dock_blocked_for(e, c)) m[1] = 0; /* scaled shop only: the dock is taken */
+            if (tr == NULL && loc != LOC_NONE) {
+                if (loc == LOC_PICKUP) m[6] = (int8_t)(e->ps_ready.n > 0);
+                else if (loc == LOC_SMALL) m[6] = (int8_t)(sm->ready.n > 0);
+                else if (loc == LOC_BIG) m[6] = (int8_t)(bm->ready.n > 0);
+                else if (loc == LOC_STORAGE) m[6] = (int8_t)(c->storage.n > 0);
+            } else if (tr != NULL && loc != LOC_NONE) {
+                int ty = tray_type(tr);
+                if (loc == LOC_PICKUP) m[7] = (int8_t)(tr->n == 0);
+                else if (loc == LOC_SMALL) m[7] = (int8_t)(tray_needs_processing(tr) && (ty == TYPE_SMALL || ty == TYPE_MEDIUM));
+                else if (loc == LOC_BIG) m[7] = (int8_t)(tray_needs_processing(tr) && (ty == TYPE_BIG || ty == TYPE_MEDIUM));
+                else if (loc == LOC_PACKAGING) m[7] = (int8_t)(tray_needs_packaging(tr) && !tray_needs_processing(tr));
+                else if (loc == LOC_STORAGE) m[7] = 1;
+            }
+        }
+    }
+    /* --- machines: MachineAgent.get_observation (:62-70), get_action_mask (:72-97) --- */
+    for (int i = 0; i < 2; i++) {
+        const Machine* m = &c->machine[i];
+        float* o = obs + 13 + 3 * i;
+        int8_t* k = masks + 8 + 3 * i;
+        o[0] = (float)m->is_busy;
+        o[1] = m->progress_done ? 1.0f : 0.0f;
+        o[2] = (float)(int8_t)m->queue.n; /* dtype=np.int8, :67 */
+        k[0] = 1;
+        k[1] = (int8_t)(m->queue.n > 0 && !m->is_busy);
+        k[2] = (int8_t)(!m->is_busy && m->current_tray != NULL);
+    }
+    /* --- packaging: PackagingAgent.get_observation (:54-62), get_action_mask (:64-89) --- */
+    for (int i = 0; i < 4; i++) {
+        const Pack* p = &c->pack[i];
+        float* o = obs + 19 + 3 * i;
+        int8_t* k = masks + 14 + 3 * i;
+        o[0] = (float)p->is_busy;
+        o[1] = (float)p->progress; /* np.array(double, dtype=np.float32) */
+        o[2] = (float)(int8_t)p->qn;
+        k[0] = 1;
+        k[1] = (int8_t)(p->qn > 0 && !p->is_busy && pack_has_capacity(e, p));
+        k[2] = (int8_t)(!p->is_busy && p->current_product != NULL);
+    }
+}
+
 void fjsp_oracle_observe(const OracleEnv* e, float* obs, int8_t* masks) {
-    memset(masks, 0, FJSP_MASK_DIM);
+    memset(masks, 0, (size_t)FJSP_MASK_DIM_K(e->ncells));
     /* --- pickup station: PickupStationAgent.get_observation (:58-98), keys sorted --- */
     int order_size = 0, remaining = 0, next_type = 0, next_colour = 0;
     if (e->current_order) {
@@ -256,69 +347,7 @@ void fjsp_oracle_observe(const OracleEnv* e, float* obs, int8_t* masks) {
         masks[1] = (int8_t)(has_order && has_tray && tray_not_full && prem);
         masks[2] = (int8_t)(e->current_tray && e->current_tray->n > 0);
     }
-    /* --- AGV: AGVAgent.get_observation (:53-76), keys sorted --- */
-    const Machine* sm = &e->machine[0];
-    const Machine* bm = &e->machine[1];
-    const Tray* c = e->carrying;
-    obs[7] = (float)bm->is_busy;
-    obs[8] = (float)bm->ready.n;
-    obs[9] = (float)(c ? 1 : 0);
-    obs[10] = (float)e->ps_ready.n;
-    obs[11] = (float)e->agv_row, obs[12] = (float)e->agv_col;
-    obs[13] = (float)sm->is_busy;
-    obs[14] = (float)sm->ready.n;
-    obs[15] = (float)e->storage.n;
-    obs[16] = (float)(c && tray_needs_packaging(c));
-    obs[17] = (float)(c && tray_needs_processing(c));
-    obs[18] = (float)(c ? c->n : 0);
-    obs[19] = (float)(c ? tray_type(c) : 0);
-    /* get_action_mask (:79-178) */
-    {
-        int8_t* m = masks + 3;
-        m[0] = 1;
-        if (!e->is_moving) {
-            int loc = agv_location(e);
-            static const int move_loc[6] = {-1, LOC_PICKUP, LOC_SMALL, LOC_BIG, LOC_STORAGE, LOC_PACKAGING};
-            for (int a = 1; a <= 5; a++) m[a] = (int8_t)(loc != move_loc[a]);
-            if (c == NULL && loc != LOC_NONE) {
-                if (loc == LOC_PICKUP) m[6] = (int8_t)(e->ps_ready.n > 0);
-                else if (loc == LOC_SMALL) m[6] = (int8_t)(sm->ready.n > 0);
-                else if (loc == LOC_BIG) m[6] = (int8_t)(bm->ready.n > 0);
-                else if (loc == LOC_STORAGE) m[6] = (int8_t)(e->storage.n > 0);
-            } else if (c != NULL && loc != LOC_NONE) {
-                int ty = tray_type(c);
-                if (loc == LOC_PICKUP) m[7] = (int8_t)(c->n == 0);
-                else if (loc == LOC_SMALL) m[7] = (int8_t)(tray_needs_processing(c) && (ty == TYPE_SMALL || ty == TYPE_MEDIUM));
-                else if (loc == LOC_BIG) m[7] = (int8_t)(tray_needs_processing(c) && (ty == TYPE_BIG || ty == TYPE_MEDIUM));
-                else if (loc == LOC_PACKAGING) m[7] = (int8_t)(tray_needs_packaging(c) && !tray_needs_processing(c));
-                else if (loc == LOC_STORAGE) m[7] = 1;
-            }
-        }
-    }
-    /* --- machines: MachineAgent.get_observation (:62-70), get_action_mask (:72-97) --- */
-    for (int i = 0; i < 2; i++) {
-        const Machine* m = &e->machine[i];
-        float* o = obs + 20 + 3 * i;
-        int8_t* k = masks + 11 + 3 * i;
-        o[0] = (float)m->is_busy;
-        o[1] = m->progress_done ? 1.0f : 0.0f;
-        o[2] = (float)(int8_t)m->queue.n; /* dtype=np.int8, :67 */
-        k[0] = 1;
-        k[1] = (int8_t)(m->queue.n > 0 && !m->is_busy);
-        k[2] = (int8_t)(!m->is_busy && m->current_tray != NULL);
-    }
-    /* --- packaging: PackagingAgent.get_observation (:54-62), get_action_mask (:64-89) --- */
-    for (int i = 0; i < 4; i++) {
-        const Pack* p = &e->pack[i];
-        float* o = obs + 26 + 3 * i;
-        int8_t* k = masks + 17 + 3 * i;
-        o[0] = (float)p->is_busy;
-        o[1] = (float)p->progress; /* np.array(double, dtype=np.float32) */
-        o[2] = (float)(int8_t)p->qn;
-        k[0] = 1;
-        k[1] = (int8_t)(p->qn > 0 && !p->is_busy && pack_has_capacity(e, p));
-        k[2] = (int8_t)(!p->is_busy && p->current_product != NULL);
-    }
+    for (int ci = 0; ci < e->ncells; ci++) observe_cell(e, &e->cells[ci], obs + 7 + 31 * ci, masks + 3 + 26 * ci);
 }
 
 /* ------------------------------------------------------------------ action phase */
@@ -393,12 +422,12 @@ static double act_pickup(OracleEnv* e, int action, uint8_t* res) {
 }
 
 /* FJSPSimulation.add_tray_to_packaging (:402-430) + PackagingAgent.add_tray (:127-131) */
-static void add_tray_to_packaging(OracleEnv* e, Tray* t) {
+static void add_tray_to_packaging(OracleEnv* e, Cell* c, Tray* t) {
     static const char* station_colour_name[4] = {"blue", "blue", "red", "green"};
     static const char* colour_name[4] = {"", "red", "blue", "green"};
     int colour = t->products[0]->colour;
     for (int s = 0; s < 4; s++) {
-        Pack* p = &e->pack[s];
+        Pack* p = &c->pack[s];
         /* `packaging_color.name.lower() in station.color.name.lower()` — substring test, equal names here */
         if (strstr(station_colour_name[s], colour_name[colour]) && pack_has_capacity(e, p)) {
             for (int i = 0; i < t->n; i++)
@@ -410,41 +439,46 @@ static void add_tray_to_packaging(OracleEnv* e, Tray* t) {
 }
 
 /* AGVAgent.execute_action (:180-252), _execute_pickup (:254-293), _execute_drop (:295-368) */
-static double act_agv(OracleEnv* e, int action, uint8_t* res) {
+static double act_agv(OracleEnv* e, Cell* c, int action, uint8_t* res) {
     int invalid = 0, moved = 0, pickup_ok = 0, drop_ok = 0, to_pack = 0, success = 0;
-    if (e->is_moving) {
+    if (c->is_moving) {
         invalid = 1; /* :210-212 */
     } else if (action == 0) {
         success = 1;
     } else if (action >= 1 && action <= 5) {
         static const int move_loc[6] = {-1, LOC_PICKUP, LOC_SMALL, LOC_BIG, LOC_STORAGE, LOC_PACKAGING}; /* :218-224 */
         int tl = move_loc[action];
-        int d = abs(e->agv_row - e->cfg.pos[tl][0]) + abs(e->agv_col - e->cfg.pos[tl][1]);
+        int d = abs(c->agv_row - e->cfg.pos[tl][0]) + abs(c->agv_col - e->cfg.pos[tl][1]);
+        if (tl == LOC_PICKUP && d != 0 && dock_blocked_for(e, c)) {
+            invalid = 1; /* scaled shop only: the single dock of the pickup station is taken by another cell's AGV */
+        } else {
         success = 1;
         if (d != 0) {
+            if (tl == LOC_PICKUP) c->holds_dock = 1; /* granted now: later AGVs of this step already see it */
             /* env.process(_move_process) (:236): Initialize is URGENT in this step's run */
-            e->move_created_now = 1;
-            e->move_target_loc = tl;
+            c->move_created_now = 1;
+            c->move_target_loc = tl;
             /* timeout(d / agv_speed) from t = step*step_size fires in the run of step + floor(d/(speed*step_size)) (R0) */
-            e->move_arrive_step = e->current_step + d / (e->cfg.agv_speed * e->cfg.step_size);
+            c->move_arrive_step = e->current_step + d / (e->cfg.agv_speed * e->cfg.step_size);
             moved = 1;
         }
+        }
     } else if (action == 6) {
-        int loc = agv_location(e);
-        if (e->carrying != NULL || loc == LOC_NONE || loc == LOC_PACKAGING) {
+        int loc = agv_location(e, c);
+        if (c->carrying != NULL || loc == LOC_NONE || loc == LOC_PACKAGING) {
             invalid = 1;
         } else {
             Tray* t = NULL;
             if (loc == LOC_PICKUP) t = tl_pop0(&e->ps_ready);
-            else if (loc == LOC_SMALL) t = tl_pop0(&e->machine[0].ready);
-            else if (loc == LOC_BIG) t = tl_pop0(&e->machine[1].ready);
-            else if (loc == LOC_STORAGE) t = tl_pop0(&e->storage);
-            if (t) e->carrying = t, success = 1, pickup_ok = 1;
+            else if (loc == LOC_SMALL) t = tl_pop0(&c->machine[0].ready);
+            else if (loc == LOC_BIG) t = tl_pop0(&c->machine[1].ready);
+            else if (loc == LOC_STORAGE) t = tl_pop0(&c->storage);
+            if (t) c->carrying = t, success = 1, pickup_ok = 1;
             else invalid = 1;
         }
     } else if (action == 7) {
-        int loc = agv_location(e);
-        Tray* t = e->carrying;
+        int loc = agv_location(e, c);
+        Tray* t = c->carrying;
         if (t == NULL || loc == LOC_NONE) {
             invalid = 1;
         } else if (loc == LOC_PICKUP) {
@@ -455,19 +489,19 @@ static double act_agv(OracleEnv* e, int action, uint8_t* res) {
             int ty = tray_type(t);
             int compatible = (loc == LOC_SMALL) ? (ty == TYPE_SMALL || ty == TYPE_MEDIUM) : (ty == TYPE_BIG || ty == TYPE_MEDIUM);
             if (tray_needs_processing(t) && compatible) {
-                tl_push(&e->machine[loc == LOC_SMALL ? 0 : 1].queue, t); /* add_tray, MachineAgent.py:141-143 */
+                tl_push(&c->machine[loc == LOC_SMALL ? 0 : 1].queue, t); /* add_tray, MachineAgent.py:141-143 */
                 drop_ok = 1;
             } else invalid = 1;
         } else if (loc == LOC_STORAGE) {
-            if (e->storage.n < e->cfg.storage_capacity) tl_push(&e->storage, t); /* Storage.add_tray (:16-22); False ignored */
+            if (c->storage.n < e->cfg.storage_capacity) tl_push(&c->storage, t); /* Storage.add_tray (:16-22); False ignored */
             drop_ok = 1;
         } else if (loc == LOC_PACKAGING) {
             if (tray_needs_packaging(t) && !tray_needs_processing(t)) {
-                add_tray_to_packaging(e, t);
+                add_tray_to_packaging(e, c, t);
                 drop_ok = 1, to_pack = 1;
             } else invalid = 1;
         }
-        if (drop_ok) e->carrying = NULL, success = 1;
+        if (drop_ok) c->carrying = NULL, success = 1;
     } else {
         invalid = 1; /* :249-250 */
     }
@@ -626,37 +660,48 @@ static void run_machine(OracleEnv* e, Machine* m) {
     }
 }
 
-static void run_agv(OracleEnv* e) {
-    if (e->move_created_now) { /* _move_process (:387-396) starts: is_moving = True */
-        e->move_created_now = 0;
-        e->is_moving = 1;
+static void run_agv(OracleEnv* e, Cell* c) {
+    if (c->move_created_now) { /* _move_process (:387-396) starts: is_moving = True */
+        c->move_created_now = 0;
+        c->is_moving = 1;
     }
-    if (e->is_moving && e->move_arrive_step == e->current_step) {
-        e->agv_row = e->cfg.pos[e->move_target_loc][0];
-        e->agv_col = e->cfg.pos[e->move_target_loc][1];
-        e->is_moving = 0;
+    if (c->is_moving && c->move_arrive_step == e->current_step) {
+        c->agv_row = e->cfg.pos[c->move_target_loc][0];
+        c->agv_col = e->cfg.pos[c->move_target_loc][1];
+        c->is_moving = 0;
     }
+    /* the dock is held while standing at PICKUP or under way to it; it is freed when the AGV starts to leave */
+    c->holds_dock = c->is_moving ? (c->move_target_loc == LOC_PICKUP) : (agv_location(e, c) == LOC_PICKUP);
 }
 
 /* ------------------------------------------------------------------ step */
 void fjsp_oracle_step(OracleEnv* e, const uint8_t* actions, float* obs, int8_t* masks, double* rewards,
                       uint8_t* flags, uint8_t* results) {
-    uint8_t res_local[8];
+    uint8_t res_local[FJSP_ACT_DIM_K(FJSP_MAX_CELLS)];
     uint8_t* res = results ? results : res_local;
+    const int K = e->ncells, A = FJSP_AGENTS_K(K);
     int orders_before = e->completed_orders;
     int products_before = e->total_products_packaged;
-    double local[8];
-    /* 1. actions in dict order (FJSPSimulation.py:172-174, :76-82) */
+    double local[FJSP_ACT_DIM_K(FJSP_MAX_CELLS)];
+    /* 1. actions in dict order (FJSPSimulation.py:172-174, :76-82): pickup station, then cell by cell agv, small
+     *    machine, big machine, four packaging stations (one cell = the reference's order) */
     local[0] = act_pickup(e, actions[0], &res[0]);
-    local[1] = act_agv(e, actions[1], &res[1]);
-    local[2] = act_machine(e, &e->machine[0], actions[2], &res[2]);
-    local[3] = act_machine(e, &e->machine[1], actions[3], &res[3]);
-    for (int i = 0; i < 4; i++) local[4 + i] = act_pack(e, &e->pack[i], actions[4 + i], &res[4 + i]);
+    for (int ci = 0; ci < K; ci++) {
+        Cell* c = &e->cells[ci];
+        const int b = 1 + 7 * ci;
+        local[b] = act_agv(e, c, actions[b], &res[b]);
+        local[b + 1] = act_machine(e, &c->machine[0], actions[b + 1], &res[b + 1]);
+        local[b + 2] = act_machine(e, &c->machine[1], actions[b + 2], &res[b + 2]);
+        for (int i = 0; i < 4; i++) local[b + 3 + i] = act_pack(e, &c->pack[i], actions[b + 3 + i], &res[b + 3 + i]);
+    }
     /* 2. env.run(until=now+step_size) (:183-184). Stations do not interact inside a run. */
-    run_agv(e);
-    run_machine(e, &e->machine[0]);
-    run_machine(e, &e->machine[1]);
-    for (int i = 0; i < 4; i++) run_pack(e, &e->pack[i]);
+    for (int ci = 0; ci < K; ci++) {
+        Cell* c = &e->cells[ci];
+        run_agv(e, c);
+        run_machine(e, &c->machine[0]);
+        run_machine(e, &c->machine[1]);
+        for (int i = 0; i < 4; i++) run_pack(e, &c->pack[i]);
+    }
     /* 3. _check_order_completions (:245-258) */
     for (int o = 0; o < e->norders; o++) {
         Order* od = &e->orders[o];
@@ -670,13 +715,13 @@ void fjsp_oracle_step(OracleEnv* e, const uint8_t* actions, float* obs, int8_t* 
             }
         }
     }
-    /* 4. rewards (:190-209, RewardModel.py:34-44,99-110), same double arithmetic order */
+    /* 4. rewards (:190-209, RewardModel.py:34-44,99-110), same double arithmetic order; num_agents = 1 + 7K */
     int oc = e->completed_orders - orders_before;
     int pp = e->total_products_packaged - products_before;
     double g = 100.0 * (double)oc;
     g += 10.0 * (double)pp;
     g += -0.1 * (double)e->cfg.step_size;
-    for (int i = 0; i < 8; i++) rewards[i] = g / 8.0 + local[i];
+    for (int i = 0; i < A; i++) rewards[i] = g / (double)A + local[i];
     /* 5. observations */
     if (obs && masks) fjsp_oracle_observe(e, obs, masks);
     /* 6. termination / truncation (:216-224), pre-increment current_step */
@@ -698,10 +743,11 @@ static int fill_trays(int32_t* dst, int cap, const TrayList* l) {
     return l->n;
 }
 
-void fjsp_oracle_export(const OracleEnv* e, FjspCanonState* s) {
+void fjsp_oracle_export_cell(const OracleEnv* e, int cell, FjspCanonState* s) {
+    const Cell* c = &e->cells[cell];
     memset(s, 0, sizeof(*s));
     s->current_step = e->current_step, s->num_orders = e->norders, s->fault = e->fault;
-    s->agv_row = e->agv_row, s->agv_col = e->agv_col, s->agv_carry = tray_entry(e->carrying), s->agv_is_moving = e->is_moving;
+    s->agv_row = c->agv_row, s->agv_col = c->agv_col, s->agv_carry = tray_entry(c->carrying), s->agv_is_moving = c->is_moving;
     s->ps_order_queue_len = order_queue_len(e);
     s->ps_current_order = e->current_order ? e->current_order->id : -1;
     s->ps_product_idx = e->current_order_product_idx;
@@ -709,16 +755,16 @@ void fjsp_oracle_export(const OracleEnv* e, FjspCanonState* s) {
     s->ps_trays_at_station = trays_at_station(e);
     s->ps_ready_n = fill_trays(s->ps_ready, FJSP_CANON_PS_READY, &e->ps_ready);
     for (int i = 0; i < 2; i++) {
-        const Machine* m = &e->machine[i];
+        const Machine* m = &c->machine[i];
         s->machine[i].is_busy = m->is_busy;
         s->machine[i].current_tray = tray_entry(m->current_tray);
         s->machine[i].progress_done = m->progress_done;
         s->machine[i].queue_n = fill_trays(s->machine[i].queue, FJSP_CANON_MAXQ, &m->queue);
         s->machine[i].ready_n = fill_trays(s->machine[i].ready, FJSP_CANON_MAXQ, &m->ready);
     }
-    s->storage_n = fill_trays(s->storage, FJSP_CANON_MAXQ, &e->storage);
+    s->storage_n = fill_trays(s->storage, FJSP_CANON_MAXQ, &c->storage);
     for (int i = 0; i < 4; i++) {
-        const Pack* p = &e->pack[i];
+        const Pack* p = &c->pack[i];
         s->pack[i].is_busy = p->is_busy;
         s->pack[i].current_product = p->current_product ? p->current_product->id : -1;
         s->pack[i].progress_L = p->progress != 0.0 ? (int32_t)lround(100.0 / p->progress) : 0;
@@ -738,6 +784,7 @@ void fjsp_oracle_export(const OracleEnv* e, FjspCanonState* s) {
     s->total_products_packaged = e->total_products_packaged;
     s->completed_orders = e->completed_orders;
 }
+void fjsp_oracle_export(const OracleEnv* e, FjspCanonState* s) { fjsp_oracle_export_cell(e, 0, s); }
 
 /* ------------------------------------------------------------------ Philox4x32-10 streams (replayable) */
 static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
@@ -774,10 +821,23 @@ void fjsp_oracle_philox_actions(uint64_t seed, uint64_t genv, uint64_t t, uint8_
     }
 }
 
+/* scaled shop: cell c draws its 8 values with counter word 3 = 1 + 16c; cell 0 also supplies the pickup station */
+void fjsp_oracle_philox_actions_k(uint64_t seed, uint64_t genv, uint64_t t, int K, uint8_t* a) {
+    static const uint32_t nact[8] = {3, 8, 3, 3, 3, 3, 3, 3};
+    for (int c = 0; c < K; c++) {
+        uint32_t r[4];
+        philox4x32_10((uint32_t)genv, (uint32_t)t, (uint32_t)(t >> 32), 1u + 16u * (uint32_t)c, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        for (int j = (c == 0 ? 0 : 1); j < 8; j++) {
+            uint32_t h = (j & 1) ? (r[j >> 1] >> 16) : (r[j >> 1] & 0xffffu);
+            a[7 * c + j] = (uint8_t)((h * nact[j]) >> 16);
+        }
+    }
+}
+
 /* ------------------------------------------------------------------ batch rollout (CPU baseline + full-size statistics parity)
  * n_envs independent envs, `steps` lockstep steps, Philox actions at t = t0.., Philox orders, auto-reset on
  * terminated|truncated|fault.  stats[8] += {env_steps, episodes, orders_completed, products_packaged, faults,
- * sum(round(40*reward)) over all agents, 0, 0}.  Env state persists in `envs` (array of n_envs OracleEnv*). */
+ * sum(round(10*A*reward)) over all A = 1+7K agents (80*reward for the reference shop: rewards are multiples of 1/(10A)), 0, 0}.  Env state persists in `envs` (array of n_envs OracleEnv*). */
 int64_t fjsp_oracle_env_size(void) { return (int64_t)sizeof(OracleEnv); }
 
 typedef struct RolloutJob {
@@ -797,19 +857,20 @@ static void* rollout_worker(void* arg) {
     for (int64_t i = j->lo; i < j->hi; i++) {
         OracleEnv* e = j->envs[i];
         uint64_t genv = (uint64_t)(j->first_env + i);
-        float obs[FJSP_OBS_DIM];
-        int8_t masks[FJSP_MASK_DIM];
-        double rew[8];
-        uint8_t flags[4], act[8];
+        float obs[FJSP_OBS_DIM_K(FJSP_MAX_CELLS)];
+        int8_t masks[FJSP_MASK_DIM_K(FJSP_MAX_CELLS)];
+        double rew[FJSP_ACT_DIM_K(FJSP_MAX_CELLS)];
+        uint8_t flags[4], act[FJSP_ACT_DIM_K(FJSP_MAX_CELLS)];
         uint32_t episode = j->episodes[i];
+        const int K = e->ncells, A = FJSP_AGENTS_K(K);
         for (int k = 0; k < j->steps; k++) {
             int before_o = e->completed_orders, before_p = e->total_products_packaged;
-            fjsp_oracle_philox_actions(j->seed, genv, j->t0 + (uint64_t)k, act);
+            fjsp_oracle_philox_actions_k(j->seed, genv, j->t0 + (uint64_t)k, K, act);
             fjsp_oracle_step(e, act, obs, masks, rew, flags, NULL);
             acc[0] += 1;
             acc[2] += (uint64_t)(e->completed_orders - before_o);
             acc[3] += (uint64_t)(e->total_products_packaged - before_p);
-            for (int a = 0; a < 8; a++) rsum += (int64_t)llround(rew[a] * 40.0);
+            for (int a = 0; a < A; a++) rsum += (int64_t)llround(rew[a] * 10.0 * (double)A);
             if (flags[0] | flags[1] | flags[2]) {
                 FjspOrderRec orders[FJSP_MAX_ORDERS];
                 acc[1] += 1;

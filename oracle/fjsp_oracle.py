@@ -30,7 +30,7 @@ class FjspConfig(C.Structure):
         ("proc_small", C.c_int32), ("proc_big", C.c_int32), ("proc_pack", C.c_int32),
         ("step_size", C.c_int32), ("agv_speed", C.c_int32), ("max_episode_steps", C.c_int32),
         ("storage_capacity", C.c_int32), ("pack_capacity", C.c_int32),
-        ("tray_capacity", C.c_int32), ("num_trays", C.c_int32),
+        ("tray_capacity", C.c_int32), ("num_trays", C.c_int32), ("num_cells", C.c_int32),
     ]
 
 
@@ -65,6 +65,8 @@ def lib():
         L.fjsp_oracle_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.fjsp_oracle_philox_orders.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
         L.fjsp_oracle_philox_actions.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.fjsp_oracle_philox_actions_k.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+        L.fjsp_oracle_export_cell.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.fjsp_oracle_env_size.restype = C.c_int64
         L.fjsp_oracle_rollout_random.argtypes = [
             C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
@@ -97,10 +99,16 @@ def philox_orders(seed: int, genv: int, episode: int, num_orders: int) -> np.nda
     return out[:num_orders]
 
 
-def philox_actions(seed: int, genv: int, t: int) -> np.ndarray:
-    out = np.zeros(8, dtype=np.uint8)
-    lib().fjsp_oracle_philox_actions(seed, genv, t, out.ctypes.data)
+def philox_actions(seed: int, genv: int, t: int, cells: int = 1) -> np.ndarray:
+    out = np.zeros(dims(cells)["act"], dtype=np.uint8)
+    lib().fjsp_oracle_philox_actions_k(seed, genv, t, cells, out.ctypes.data)
     return out
+
+
+def dims(cells: int = 1) -> dict:
+    """Row widths of a K-cell shop (include/fjsp_b200.h FJSP_*_K); K = 1 is the reference shop."""
+    agents = 1 + 7 * cells
+    return {"agents": agents, "act": (agents + 7) // 8 * 8, "obs": 7 + 31 * cells, "mask": (3 + 26 * cells + 31) // 32 * 32}
 
 
 class OracleEnv:
@@ -112,11 +120,13 @@ class OracleEnv:
         self._h = self._L.fjsp_oracle_create(C.byref(self.cfg))
         if not self._h:
             raise MemoryError("fjsp_oracle_create failed")
-        self.obs = np.zeros(38, dtype=np.float32)
-        self.masks = np.zeros(32, dtype=np.int8)
-        self.rewards = np.zeros(8, dtype=np.float64)
+        self.cells = max(1, int(self.cfg.num_cells))
+        d = dims(self.cells)
+        self.obs = np.zeros(d["obs"], dtype=np.float32)
+        self.masks = np.zeros(d["mask"], dtype=np.int8)
+        self.rewards = np.zeros(d["act"], dtype=np.float64)
         self.flags = np.zeros(4, dtype=np.uint8)
-        self.results = np.zeros(8, dtype=np.uint8)
+        self.results = np.zeros(d["act"], dtype=np.uint8)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -139,9 +149,9 @@ class OracleEnv:
                                  self.rewards.ctypes.data, self.flags.ctypes.data, self.results.ctypes.data)
         return self.obs.copy(), self.masks.copy(), self.rewards.copy(), self.flags.copy()
 
-    def export(self) -> np.ndarray:
+    def export(self, cell: int = 0) -> np.ndarray:
         s = np.zeros((), dtype=CANON_DT)
-        self._L.fjsp_oracle_export(self._h, s.ctypes.data)
+        self._L.fjsp_oracle_export_cell(self._h, int(cell), s.ctypes.data)
         return s
 
 

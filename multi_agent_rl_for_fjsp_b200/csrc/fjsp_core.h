@@ -52,12 +52,17 @@ enum { TYPE_SMALL = 1, TYPE_MEDIUM = 2, TYPE_BIG = 3 };
 enum { COL_RED = 1, COL_BLUE = 2, COL_GREEN = 3 };
 
 // ---------------------------------------------------------------------------------------------
-// Word map of the packed state.
+// Word map of the packed state of a K-cell shop (K = 1: the reference shop, 128 words).
+//   words 0..23      hot words of the pickup station (shared) and of cell 0
+//   words 24..31     order completion steps (u8 each)
+//   words 32..63     order words
+//   words 64+64c ..  tray pool of cell c (64 records)                      -> words 24 .. 64+64K are "dynamic"
+//   words 64+64K ..  hot words of cells 1..K-1, 20 each (AGV, free bitmap x2, storage, 2 machines x 2, 4 stations x 3)
 // ---------------------------------------------------------------------------------------------
 enum {
     W_CTRL = 0,     // step16 | num_orders6<<16 | fault2<<22 | completed_orders6<<24
     W_PS = 1,       // total_packaged9 | next_order6<<9 | cur_order6<<15 (63=none) | prod_idx4<<21 | cur_tray_count3<<25
-    W_PSQ = 2,      // alloc_count8 | ready_count8<<8 | ready_order6<<16 | ready_idx4<<22
+    W_PSQ = 2,      // alloc_count8 | ready_count8<<8 | ready_order6<<16 | ready_idx4<<22 | dock_mask4<<26
     W_AGV = 3,      // loc3 | moving1<<3 | target3<<4 | arrive16<<7 | carry7<<23 (slot+1, 0 = none)
     W_FREE_LO = 4,  // pool free bitmap, slots 0..31 (1 = free)
     W_FREE_HI = 5,  // slots 32..63
@@ -72,10 +77,24 @@ enum {
                     //   C: completed8 | progL8<<8
     W_CSTEP = 24,   // 32 x u8 completion step + 1 (0 = not complete), 4 per word
     W_ORDER = 32,   // 32 x order word: n4 | type2<<4 | colour2<<6 | cut8<<8 | packaged9<<16
-    W_POOL = 64,    // 64 x tray record: order5 | first4<<5 | count3<<9 | processed1<<12 | next6<<13 | stamp8<<19 | lost1<<27
-    W_TOTAL = 128
+    W_POOL = 64,    // 64 x tray record per cell: order5 | first4<<5 | count3<<9 | processed1<<12 | next6<<13 | stamp8<<19 | lost1<<27
+    W_TOTAL = 128,  // K = 1
+    CELL_HOT_WORDS = 20
 };
 static_assert(W_TOTAL == FJSP_STATE_WORDS, "state size");
+
+template <int K>
+struct Lay {
+    static constexpr int DYN_END = 64 + 64 * K;                     // hot | dynamic (24..DYN_END) | hot words of cells >= 1
+    static constexpr int TOTAL = FJSP_STATE_WORDS_K(K);
+    static constexpr int AGENTS = FJSP_AGENTS_K(K), ACT = FJSP_ACT_DIM_K(K), OBS = FJSP_OBS_DIM_K(K), MASK = FJSP_MASK_DIM_K(K);
+};
+// word index of hot word `which` (0 AGV, 1 FREE_LO, 2 FREE_HI, 3 STORAGE, 4..7 MACH, 8..19 PACK) of cell c
+FJSP_HD constexpr int cell_word(int K, int c, int which) {
+    return c == 0 ? (which < 3 ? W_AGV + which : which == 3 ? W_STORAGE : which < 8 ? W_MACH + (which - 4) : W_PACK + (which - 8))
+                  : 64 + 64 * K + CELL_HOT_WORDS * (c - 1) + which;
+}
+FJSP_HD constexpr int pool_base(int c) { return W_POOL + 64 * c; }
 
 // order word
 FJSP_HD int ord_n(u32 w) { return (int)(w & 15u); }
@@ -115,7 +134,7 @@ FJSP_HD int popc32(u32 x) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Unpacked hot scalars (words 0..23).  Loaded once per step, kept in registers, stored once.
+// Unpacked hot scalars.  Shared (pickup station, counters) + one struct per cell.  Kept in registers.
 // ---------------------------------------------------------------------------------------------
 struct Fifo {
     int head, tail, len;
@@ -128,12 +147,15 @@ struct Pack {
     Fifo q, f;  // queued tray records, in-flight tray records (len = record count)
     int users, busy, waiters, hascur, curprod, qcount, completed, progL;
 };
-struct Hot {
+struct Hot {  // shared part
     int step, num_orders, fault, completed_orders;
     int total_packaged, next_order, cur_order, prod_idx, cur_tray_count;
-    int alloc_count, ready_count, ready_order, ready_idx;
+    int alloc_count, ready_count, ready_order, ready_idx, dock_mask;
+    u32 episode;
+};
+struct HotCell {
     int agv_loc, agv_moving, agv_target, agv_arrive, carry;
-    u32 free_lo, free_hi, episode;
+    u32 free_lo, free_hi;
     Fifo storage;
     Mach m[2];
     Pack p[4];
@@ -149,71 +171,79 @@ FJSP_HD void load_hot(S& s, Hot& h) {
     h.prod_idx = (int)((w >> 21) & 15u), h.cur_tray_count = (int)((w >> 25) & 7u);
     w = s.ld_hot(W_PSQ);
     h.alloc_count = (int)(w & 255u), h.ready_count = (int)((w >> 8) & 255u), h.ready_order = (int)((w >> 16) & 63u);
-    h.ready_idx = (int)((w >> 22) & 15u);
-    w = s.ld_hot(W_AGV);
+    h.ready_idx = (int)((w >> 22) & 15u), h.dock_mask = (int)((w >> 26) & 15u);
+    h.episode = s.ld_hot(W_EPISODE);
+}
+template <class S>
+FJSP_HD void store_hot(S& s, const Hot& h) {
+    s.st_hot(W_CTRL, (u32)h.step | ((u32)h.num_orders << 16) | ((u32)h.fault << 22) | ((u32)h.completed_orders << 24));
+    s.st_hot(W_PS, (u32)h.total_packaged | ((u32)h.next_order << 9) | ((u32)h.cur_order << 15) | ((u32)h.prod_idx << 21) |
+                       ((u32)h.cur_tray_count << 25));
+    s.st_hot(W_PSQ, (u32)h.alloc_count | ((u32)h.ready_count << 8) | ((u32)h.ready_order << 16) | ((u32)h.ready_idx << 22) |
+                        ((u32)h.dock_mask << 26));
+    s.st_hot(W_EPISODE, h.episode);
+}
+template <int K, class S>
+FJSP_HD void load_cell(S& s, int c, HotCell& h) {
+    u32 w = s.ld_hot(cell_word(K, c, 0));
     h.agv_loc = (int)(w & 7u), h.agv_moving = (int)((w >> 3) & 1u), h.agv_target = (int)((w >> 4) & 7u);
     h.agv_arrive = (int)((w >> 7) & 0xffffu), h.carry = (int)((w >> 23) & 127u);
-    h.free_lo = s.ld_hot(W_FREE_LO), h.free_hi = s.ld_hot(W_FREE_HI), h.episode = s.ld_hot(W_EPISODE);
-    w = s.ld_hot(W_STORAGE);
+    h.free_lo = s.ld_hot(cell_word(K, c, 1)), h.free_hi = s.ld_hot(cell_word(K, c, 2));
+    w = s.ld_hot(cell_word(K, c, 3));
     h.storage.head = (int)(w & 63u), h.storage.tail = (int)((w >> 6) & 63u), h.storage.len = (int)((w >> 12) & 255u);
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         Mach& m = h.m[i];
-        w = s.ld_hot(W_MACH + 2 * i);
+        w = s.ld_hot(cell_word(K, c, 4 + 2 * i));
         m.busy = (int)(w & 1u), m.has_cur = (int)((w >> 1) & 1u), m.cur = (int)((w >> 2) & 63u);
         m.start = (int)((w >> 8) & 0xffffu), m.prog = (int)((w >> 24) & 1u), m.q.len = (int)((w >> 25) & 63u);
-        w = s.ld_hot(W_MACH + 2 * i + 1);
+        w = s.ld_hot(cell_word(K, c, 5 + 2 * i));
         m.q.head = (int)(w & 63u), m.q.tail = (int)((w >> 6) & 63u), m.r.head = (int)((w >> 12) & 63u);
         m.r.tail = (int)((w >> 18) & 63u), m.r.len = (int)((w >> 24) & 63u);
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         Pack& p = h.p[i];
-        w = s.ld_hot(W_PACK + 3 * i);
+        w = s.ld_hot(cell_word(K, c, 8 + 3 * i));
         p.q.head = (int)(w & 63u), p.q.tail = (int)((w >> 6) & 63u), p.q.len = (int)((w >> 12) & 63u);
         p.f.head = (int)((w >> 18) & 63u), p.f.tail = (int)((w >> 24) & 63u);
-        w = s.ld_hot(W_PACK + 3 * i + 1);
+        w = s.ld_hot(cell_word(K, c, 9 + 3 * i));
         p.f.len = (int)(w & 63u), p.users = (int)((w >> 6) & 31u), p.busy = (int)((w >> 11) & 1u);
         p.waiters = (int)((w >> 12) & 1u), p.hascur = (int)((w >> 13) & 1u), p.curprod = (int)((w >> 14) & 511u);
         p.qcount = (int)((w >> 23) & 255u);
-        w = s.ld_hot(W_PACK + 3 * i + 2);
+        w = s.ld_hot(cell_word(K, c, 10 + 3 * i));
         p.completed = (int)(w & 255u), p.progL = (int)((w >> 8) & 255u);
     }
 }
-
-template <class S>
-FJSP_HD void store_hot(S& s, const Hot& h) {
-    s.st_hot(W_CTRL, (u32)h.step | ((u32)h.num_orders << 16) | ((u32)h.fault << 22) | ((u32)h.completed_orders << 24));
-    s.st_hot(W_PS, (u32)h.total_packaged | ((u32)h.next_order << 9) | ((u32)h.cur_order << 15) | ((u32)h.prod_idx << 21) |
-                   ((u32)h.cur_tray_count << 25));
-    s.st_hot(W_PSQ, (u32)h.alloc_count | ((u32)h.ready_count << 8) | ((u32)h.ready_order << 16) | ((u32)h.ready_idx << 22));
-    s.st_hot(W_AGV, (u32)h.agv_loc | ((u32)h.agv_moving << 3) | ((u32)h.agv_target << 4) | ((u32)h.agv_arrive << 7) |
-                    ((u32)h.carry << 23));
-    s.st_hot(W_FREE_LO, h.free_lo), s.st_hot(W_FREE_HI, h.free_hi), s.st_hot(W_EPISODE, h.episode);
-    s.st_hot(W_STORAGE, (u32)h.storage.head | ((u32)h.storage.tail << 6) | ((u32)h.storage.len << 12));
+template <int K, class S>
+FJSP_HD void store_cell(S& s, int c, const HotCell& h) {
+    s.st_hot(cell_word(K, c, 0), (u32)h.agv_loc | ((u32)h.agv_moving << 3) | ((u32)h.agv_target << 4) | ((u32)h.agv_arrive << 7) |
+                                     ((u32)h.carry << 23));
+    s.st_hot(cell_word(K, c, 1), h.free_lo), s.st_hot(cell_word(K, c, 2), h.free_hi);
+    s.st_hot(cell_word(K, c, 3), (u32)h.storage.head | ((u32)h.storage.tail << 6) | ((u32)h.storage.len << 12));
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         const Mach& m = h.m[i];
-        s.st_hot(W_MACH + 2 * i, (u32)m.busy | ((u32)m.has_cur << 1) | ((u32)m.cur << 2) | ((u32)m.start << 8) |
-                                 ((u32)m.prog << 24) | ((u32)m.q.len << 25));
-        s.st_hot(W_MACH + 2 * i + 1, (u32)m.q.head | ((u32)m.q.tail << 6) | ((u32)m.r.head << 12) | ((u32)m.r.tail << 18) |
-                                     ((u32)m.r.len << 24));
+        s.st_hot(cell_word(K, c, 4 + 2 * i), (u32)m.busy | ((u32)m.has_cur << 1) | ((u32)m.cur << 2) | ((u32)m.start << 8) |
+                                                 ((u32)m.prog << 24) | ((u32)m.q.len << 25));
+        s.st_hot(cell_word(K, c, 5 + 2 * i), (u32)m.q.head | ((u32)m.q.tail << 6) | ((u32)m.r.head << 12) | ((u32)m.r.tail << 18) |
+                                                 ((u32)m.r.len << 24));
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const Pack& p = h.p[i];
-        s.st_hot(W_PACK + 3 * i, (u32)p.q.head | ((u32)p.q.tail << 6) | ((u32)p.q.len << 12) | ((u32)p.f.head << 18) |
-                                 ((u32)p.f.tail << 24));
-        s.st_hot(W_PACK + 3 * i + 1, (u32)p.f.len | ((u32)p.users << 6) | ((u32)p.busy << 11) | ((u32)p.waiters << 12) |
-                                     ((u32)p.hascur << 13) | ((u32)p.curprod << 14) | ((u32)p.qcount << 23));
-        s.st_hot(W_PACK + 3 * i + 2, (u32)p.completed | ((u32)p.progL << 8));
+        s.st_hot(cell_word(K, c, 8 + 3 * i), (u32)p.q.head | ((u32)p.q.tail << 6) | ((u32)p.q.len << 12) | ((u32)p.f.head << 18) |
+                                                 ((u32)p.f.tail << 24));
+        s.st_hot(cell_word(K, c, 9 + 3 * i), (u32)p.f.len | ((u32)p.users << 6) | ((u32)p.busy << 11) | ((u32)p.waiters << 12) |
+                                                 ((u32)p.hascur << 13) | ((u32)p.curprod << 14) | ((u32)p.qcount << 23));
+        s.st_hot(cell_word(K, c, 10 + 3 * i), (u32)p.completed | ((u32)p.progL << 8));
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pool + FIFO primitives
+// Pool + FIFO primitives (pb = first pool word of the cell)
 // ---------------------------------------------------------------------------------------------
-FJSP_HD int pool_alloc(Hot& h) {
+FJSP_HD int pool_alloc(HotCell& h) {
     if (h.free_lo) {
         int b = ctz32(h.free_lo);
         h.free_lo &= h.free_lo - 1u;
@@ -226,25 +256,25 @@ FJSP_HD int pool_alloc(Hot& h) {
     }
     return -1;
 }
-FJSP_HD void pool_free(Hot& h, int slot) {
+FJSP_HD void pool_free(HotCell& h, int slot) {
     if (slot < 32) h.free_lo |= 1u << slot;
     else h.free_hi |= 1u << (slot - 32);
 }
 template <class S>
-FJSP_HD void fifo_push(S& s, Fifo& f, int slot) {
+FJSP_HD void fifo_push(S& s, int pb, Fifo& f, int slot) {
     if (f.len == 0) {
         f.head = slot;
     } else {
-        u32 r = s.ld(W_POOL + f.tail);
-        s.st(W_POOL + f.tail, rec_with_next(r, slot));
+        u32 r = s.ld(pb + f.tail);
+        s.st(pb + f.tail, rec_with_next(r, slot));
     }
     f.tail = slot;
     f.len++;
 }
 template <class S>
-FJSP_HD int fifo_pop(S& s, Fifo& f) {  // caller checks len > 0
+FJSP_HD int fifo_pop(S& s, int pb, Fifo& f) {  // caller checks len > 0
     int slot = f.head;
-    f.head = rec_next(s.ld(W_POOL + slot));
+    f.head = rec_next(s.ld(pb + slot));
     f.len--;
     return slot;
 }
@@ -287,31 +317,54 @@ FJSP_HD void philox_actions(uint64_t seed, uint64_t genv, uint64_t t, int a[8]) 
     }
 }
 
+// scaled shop: cell c draws its 8 values with counter word 3 = 1 + 16c; cell 0 also supplies the pickup station's
+template <int K>
+FJSP_HD void philox_actions_k(uint64_t seed, uint64_t genv, uint64_t t, int* a) {
+#pragma unroll
+    for (int c = 0; c < K; c++) {
+        u32 r[4];
+        philox4x32_10((u32)genv, (u32)t, (u32)(t >> 32), 1u + 16u * (u32)c, (u32)seed, (u32)(seed >> 32), r);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (c > 0 && j == 0) continue;
+            u32 hw = (j & 1) ? (r[j >> 1] >> 16) : (r[j >> 1] & 0xffffu);
+            a[7 * c + j] = (int)((hw * (j == 1 ? 8u : 3u)) >> 16);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Reset: FJSPSimulation.reset (FJSPSimulation.py:286-323).  `orders` = FjspOrderRec[32] (n | type<<8 | colour<<16)
 // or nullptr -> Philox.
 // ---------------------------------------------------------------------------------------------
 // Everything of a fresh env except the 32 order words (the kernels fill those warp-cooperatively, one order per lane).
-template <class S>
+template <int K, class S>
 FJSP_HD void reset_env_base(S& s, int num_orders, u32 episode) {
 #pragma unroll
     for (int w = 0; w < W_CSTEP; w++) s.st_hot(w, 0u);
 #pragma unroll
     for (int w = W_CSTEP; w < W_ORDER; w++) s.st(w, 0u);
 #pragma unroll 8
-    for (int w = W_POOL; w < W_TOTAL; w++) s.st(w, 0u);
+    for (int w = W_POOL; w < Lay<K>::DYN_END; w++) s.st(w, 0u);
+#pragma unroll
+    for (int w = Lay<K>::DYN_END; w < Lay<K>::TOTAL; w++) s.st_hot(w, 0u);
     s.st_hot(W_CTRL, (u32)num_orders << 16);
-    s.st_hot(W_PS, 63u << 15);         // cur_order = none
-    s.st_hot(W_AGV, (u32)LOC_PICKUP);  // AGVAgent.py:41
-    s.st_hot(W_FREE_LO, 0xffffffffu), s.st_hot(W_FREE_HI, 0xffffffffu);
+    s.st_hot(W_PS, 63u << 15);   // cur_order = none
+    s.st_hot(W_PSQ, 1u << 26);   // the dock of the pickup station is held by cell 0's AGV
     s.st_hot(W_EPISODE, episode);
+#pragma unroll
+    for (int c = 0; c < K; c++) {
+        // AGVAgent.py:41: the AGV starts at PICKUP; further cells' AGVs start at STORAGE (one dock)
+        s.st_hot(cell_word(K, c, 0), (u32)(c == 0 ? LOC_PICKUP : LOC_STORAGE));
+        s.st_hot(cell_word(K, c, 1), 0xffffffffu), s.st_hot(cell_word(K, c, 2), 0xffffffffu);
+    }
 }
 
-template <class S>
+template <int K, class S>
 FJSP_HD void reset_env(S& s, const Params& P, int num_orders, const FjspOrderRec* orders, uint64_t seed, uint64_t genv,
                        u32 episode) {
     (void)P;
-    reset_env_base(s, num_orders, episode);
+    reset_env_base<K>(s, num_orders, episode);
     for (int o = 0; o < FJSP_MAX_ORDERS; o++) {
         u32 ow = 0u;
         if (o < num_orders) {
@@ -327,24 +380,23 @@ FJSP_HD void reset_env(S& s, const Params& P, int num_orders, const FjspOrderRec
 }
 
 // ---------------------------------------------------------------------------------------------
-// Observation (layout O, 38 floats) + masks (29 bytes in 8 words).  SURVEY.md §8a-R9.
+// Observation (layout O: 7 + 31K floats) + masks (3 + 26K bytes).  SURVEY.md §8a-R9; K = 1: 38 / 29.
 // ---------------------------------------------------------------------------------------------
+template <int K>
 struct StepOut {
-    float* obs;     // 38 floats, written in place (a shared-memory staging row on the device)
-    u32 mask[FJSP_MASK_DIM / 4];
-    float reward[FJSP_NUM_AGENTS];
+    float* obs;     // 7 + 31K floats, written in place (a shared-memory staging row on the device)
+    u32 mask[Lay<K>::MASK / 4];
+    float reward[Lay<K>::ACT];
     u32 flags;      // terminated | truncated<<8 | fault<<16 | was_reset<<24
-    u32 results[2]; // 8 x u8 action_result bit-fields
+    u32 results[Lay<K>::ACT / 4];  // u8 action_result bit-fields per agent
     int32_t info[4];
-    long long reward40;  // sum over the 8 agents of round(40 * reward): exact integer statistic for rollouts
+    long long reward_units;  // sum over the agents of 10*A*reward (exact integers): statistic for rollouts
 };
 
 FJSP_HD void mask_set(u32* mw, int idx, int v) { mw[idx >> 2] |= (u32)(v & 1) << ((idx & 3) * 8); }
 
 template <class S>
-FJSP_HD void observe(S& s, const Params& P, const Hot& h, float* obs, u32* mw) {
-#pragma unroll
-    for (int i = 0; i < FJSP_MASK_DIM / 4; i++) mw[i] = 0u;
+FJSP_HD void observe_shared(S& s, const Params& P, const Hot& h, float* obs, u32* mw) {
     // ---- pickup station: PickupStationAgent.get_observation (:58-98) / get_action_mask (:100-142)
     int has_cur_order = h.cur_order != 63;
     int order_size = 0, remaining = 0, o_type = 0, o_colour = 0;
@@ -361,81 +413,100 @@ FJSP_HD void observe(S& s, const Params& P, const Hot& h, float* obs, u32* mw) {
     obs[4] = (float)(remaining > 0 ? o_type : 0);
     obs[5] = (float)order_size;
     obs[6] = (float)remaining;
-    {
-        int queue_len = h.num_orders - h.next_order;
-        int has_order = has_cur_order || queue_len > 0;
-        int has_tray = tcount > 0 || (P.trays_total - h.alloc_count) > 0;
-        int tray_not_full = tcount < FJSP_TRAY_CAPACITY;
-        int prem = has_cur_order ? (remaining > 0) : (queue_len > 0);
-        mask_set(mw, 0, 1);
-        mask_set(mw, 1, has_order && has_tray && tray_not_full && prem);
-        mask_set(mw, 2, tcount > 0);
-    }
+    int queue_len = h.num_orders - h.next_order;
+    int has_order = has_cur_order || queue_len > 0;
+    int has_tray = tcount > 0 || (P.trays_total - h.alloc_count) > 0;
+    int tray_not_full = tcount < FJSP_TRAY_CAPACITY;
+    int prem = has_cur_order ? (remaining > 0) : (queue_len > 0);
+    mask_set(mw, 0, 1);
+    mask_set(mw, 1, has_order && has_tray && tray_not_full && prem);
+    mask_set(mw, 2, tcount > 0);
+}
+
+// one cell: AGV (13) + small/big machine (3 + 3) + four packaging stations (12) = 31 floats; 26 mask bytes from `mo`
+template <class S>
+FJSP_HD void observe_cell(S& s, const Params& P, const Hot& h, const HotCell& hc, int c, float* obs, u32* mw, int mo) {
+    const int pb = pool_base(c);
     // ---- AGV: AGVAgent.get_observation (:53-76) / get_action_mask (:79-178)
-    int carrying = h.carry != 0;
+    int carrying = hc.carry != 0;
     int c_count = 0, c_type = 0, c_proc = 0;
     if (carrying) {
-        u32 r = s.ld(W_POOL + h.carry - 1);
+        u32 r = s.ld(pb + hc.carry - 1);
         c_count = rec_count(r), c_proc = rec_processed(r);
         c_type = ord_type(s.ld(W_ORDER + rec_order(r)));
     }
-    obs[7] = (float)h.m[1].busy;
-    obs[8] = (float)h.m[1].r.len;
-    obs[9] = (float)carrying;
-    obs[10] = (float)h.ready_count;
-    obs[11] = (float)P.pos_row[h.agv_loc];
-    obs[12] = (float)P.pos_col[h.agv_loc];
-    obs[13] = (float)h.m[0].busy;
-    obs[14] = (float)h.m[0].r.len;
-    obs[15] = (float)h.storage.len;
-    obs[16] = (float)carrying;                 // a carried tray is never packaged (delivered trays vanish)
-    obs[17] = (float)(carrying && !c_proc);
-    obs[18] = (float)c_count;
-    obs[19] = (float)c_type;
-    mask_set(mw, 3, 1);
-    if (!h.agv_moving) {
-        int loc = h.agv_loc;
-        mask_set(mw, 4, loc != LOC_PICKUP);
-        mask_set(mw, 5, loc != LOC_SMALL);
-        mask_set(mw, 6, loc != LOC_BIG);
-        mask_set(mw, 7, loc != LOC_STORAGE);
-        mask_set(mw, 8, loc != LOC_PACKAGING);
+    obs[0] = (float)hc.m[1].busy;
+    obs[1] = (float)hc.m[1].r.len;
+    obs[2] = (float)carrying;
+    obs[3] = (float)h.ready_count;
+    obs[4] = (float)P.pos_row[hc.agv_loc];
+    obs[5] = (float)P.pos_col[hc.agv_loc];
+    obs[6] = (float)hc.m[0].busy;
+    obs[7] = (float)hc.m[0].r.len;
+    obs[8] = (float)hc.storage.len;
+    obs[9] = (float)carrying;                 // a carried tray is never packaged (delivered trays vanish)
+    obs[10] = (float)(carrying && !c_proc);
+    obs[11] = (float)c_count;
+    obs[12] = (float)c_type;
+    mask_set(mw, mo + 0, 1);
+    if (!hc.agv_moving) {
+        int loc = hc.agv_loc;
+        mask_set(mw, mo + 1, loc != LOC_PICKUP && (h.dock_mask & ~(1 << c)) == 0);  // one dock (scaled shop)
+        mask_set(mw, mo + 2, loc != LOC_SMALL);
+        mask_set(mw, mo + 3, loc != LOC_BIG);
+        mask_set(mw, mo + 4, loc != LOC_STORAGE);
+        mask_set(mw, mo + 5, loc != LOC_PACKAGING);
         if (!carrying) {
             int avail = loc == LOC_PICKUP ? h.ready_count
-                        : loc == LOC_SMALL ? h.m[0].r.len
-                        : loc == LOC_BIG ? h.m[1].r.len
-                        : loc == LOC_STORAGE ? h.storage.len : 0;
-            mask_set(mw, 9, avail > 0);
+                        : loc == LOC_SMALL ? hc.m[0].r.len
+                        : loc == LOC_BIG ? hc.m[1].r.len
+                        : loc == LOC_STORAGE ? hc.storage.len : 0;
+            mask_set(mw, mo + 6, avail > 0);
         } else {
             int ok = 0;
             if (loc == LOC_SMALL) ok = !c_proc && (c_type == TYPE_SMALL || c_type == TYPE_MEDIUM);
             else if (loc == LOC_BIG) ok = !c_proc && (c_type == TYPE_BIG || c_type == TYPE_MEDIUM);
             else if (loc == LOC_PACKAGING) ok = c_proc;
             else if (loc == LOC_STORAGE) ok = 1;
-            mask_set(mw, 10, ok);  // PICKUP: only an empty tray, never the case
+            mask_set(mw, mo + 7, ok);  // PICKUP: only an empty tray, never the case
         }
     }
     // ---- machines: MachineAgent.get_observation (:62-70) / get_action_mask (:72-97)
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        const Mach& m = h.m[i];
-        obs[20 + 3 * i] = (float)m.busy;
-        obs[21 + 3 * i] = m.prog ? 1.0f : 0.0f;
-        obs[22 + 3 * i] = (float)m.q.len;
-        mask_set(mw, 11 + 3 * i, 1);
-        mask_set(mw, 12 + 3 * i, m.q.len > 0 && !m.busy);
-        mask_set(mw, 13 + 3 * i, !m.busy && m.has_cur);
+        const Mach& m = hc.m[i];
+        obs[13 + 3 * i] = (float)m.busy;
+        obs[14 + 3 * i] = m.prog ? 1.0f : 0.0f;
+        obs[15 + 3 * i] = (float)m.q.len;
+        mask_set(mw, mo + 8 + 3 * i, 1);
+        mask_set(mw, mo + 9 + 3 * i, m.q.len > 0 && !m.busy);
+        mask_set(mw, mo + 10 + 3 * i, !m.busy && m.has_cur);
     }
     // ---- packaging: PackagingAgent.get_observation (:54-62) / get_action_mask (:64-89)
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const Pack& p = h.p[i];
-        obs[26 + 3 * i] = (float)p.busy;
-        obs[27 + 3 * i] = P.progress_tab[p.progL];
-        obs[28 + 3 * i] = (float)(int)(int8_t)p.qcount;  // dtype=np.int8 (PackagingAgent.py:59)
-        mask_set(mw, 17 + 3 * i, 1);
-        mask_set(mw, 18 + 3 * i, p.qcount > 0 && !p.busy && p.users < P.pack_capacity);
-        mask_set(mw, 19 + 3 * i, !p.busy && p.hascur);
+        const Pack& p = hc.p[i];
+        obs[19 + 3 * i] = (float)p.busy;
+        obs[20 + 3 * i] = P.progress_tab[p.progL];
+        obs[21 + 3 * i] = (float)(int)(int8_t)p.qcount;  // dtype=np.int8 (PackagingAgent.py:59)
+        mask_set(mw, mo + 14 + 3 * i, 1);
+        mask_set(mw, mo + 15 + 3 * i, p.qcount > 0 && !p.busy && p.users < P.pack_capacity);
+        mask_set(mw, mo + 16 + 3 * i, !p.busy && p.hascur);
+    }
+}
+
+// whole observation; cell 0's hot words are the caller's registers, further cells are re-read
+template <int K, class S>
+FJSP_HD void observe(S& s, const Params& P, const Hot& h, const HotCell& c0, float* obs, u32* mw) {
+#pragma unroll
+    for (int i = 0; i < Lay<K>::MASK / 4; i++) mw[i] = 0u;
+    observe_shared(s, P, h, obs, mw);
+    observe_cell(s, P, h, c0, 0, obs + 7, mw, 3);
+#pragma unroll
+    for (int c = 1; c < K; c++) {
+        HotCell hc;
+        load_cell<K>(s, c, hc);
+        observe_cell(s, P, h, hc, c, obs + 7 + 31 * c, mw, 3 + 26 * c);
     }
 }
 
@@ -444,118 +515,121 @@ FJSP_HD void observe(S& s, const Params& P, const Hot& h, float* obs, u32* mw) {
 // ---------------------------------------------------------------------------------------------
 // Move the first `g` queued products of station p into flight (grant events, PackagingAgent.py:138-141).
 template <class S>
-FJSP_HD void pack_grant(S& s, Hot& h, Pack& p, int g, int stamp) {
+FJSP_HD void pack_grant(S& s, int pb, Hot& h, HotCell& hc, Pack& p, int g, int stamp) {
     while (g > 0 && p.q.len > 0) {
         int slot = p.q.head;
-        u32 r = s.ld(W_POOL + slot);
+        u32 r = s.ld(pb + slot);
         int cnt = rec_count(r);
         int fslot;
         int last_idx;
         if (cnt <= g) {
-            fifo_pop(s, p.q);
+            fifo_pop(s, pb, p.q);
             fslot = slot;
             last_idx = rec_first(r) + cnt - 1;
             g -= cnt, p.qcount -= cnt;
         } else {  // capacity split: the first g products start, the rest keeps waiting (R-PKG-cap-a)
-            fslot = pool_alloc(h);
+            fslot = pool_alloc(hc);
             if (fslot < 0) {
                 h.fault = FJSP_FAULT_POOL_EXHAUSTED;
                 return;
             }
             u32 started = make_rec(rec_order(r), rec_first(r), g, 1);
             u32 rest = (r & ~((15u << 5) | (7u << 9))) | ((u32)(rec_first(r) + g) << 5) | ((u32)(cnt - g) << 9);
-            s.st(W_POOL + slot, rest);
+            s.st(pb + slot, rest);
             r = started;
             last_idx = rec_first(r) + g - 1;
             p.qcount -= g;
             g = 0;
         }
-        s.st(W_POOL + fslot, rec_with_stamp(r, stamp));
-        fifo_push(s, p.f, fslot);
+        s.st(pb + fslot, rec_with_stamp(r, stamp));
+        fifo_push(s, pb, p.f, fslot);
         p.busy = 1, p.hascur = 1;
         p.curprod = rec_order(r) | (last_idx << 5);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// One environment step.  Returns through `out`.  `actions` = 8 bytes.
+// Action phase
 // ---------------------------------------------------------------------------------------------
-// `h` holds the unpacked hot words (0..23) of the env; the caller loads/stores them (once per step in the step kernel,
-// once per LAUNCH in the K-steps-per-launch kernel, which keeps them in registers between steps).
-template <bool WITH_OBS, class S>
-FJSP_HD void step_env_hot(S& s, const Params& P, Hot& h, const int a[8], StepOut& out) {
-    const int k = h.step;
-    const int orders_before = h.completed_orders, products_before = h.total_packaged;
-    int local10[8];  // local rewards in tenths: every RewardModel constant is a multiple of 0.1 (RewardModel.py:12-32)
-    u32 res[8];
-
-    // ===== action phase, agents in dict order (FJSPSimulation.py:172-174, :76-82) =====
-    // ---- R1 pickup station (PickupStationAgent.py:146-232)
-    {
-        int loaded = 0, tray_done = 0, idle_orders = 0, success = 0;
-        if (a[0] == 0) {
-            idle_orders = (h.num_orders - h.next_order) > 0 || h.cur_order != 63;
-            success = 1;
-        } else if (a[0] == 1) {
-            int ok = 1;
-            if (h.cur_order == 63) {
-                if (h.next_order < h.num_orders) h.cur_order = h.next_order++, h.prod_idx = 0;
-                else ok = 0;
-            }
-            if (ok && h.cur_tray_count == 0) {
-                if (h.alloc_count < P.trays_total) h.alloc_count++;  // trays_at_station.pop(0)
-                else ok = 0;
-            }
-            if (ok) {
-                u32 ow = s.ld(W_ORDER + h.cur_order);
-                h.cur_tray_count++, h.prod_idx++;
-                loaded = 1, success = 1;
-                if (h.prod_idx >= ord_n(ow)) {          // order exhausted: tray released (:201-208)
-                    h.cur_order = 63, h.prod_idx = 0;
-                    h.cur_tray_count = 0, h.ready_count++;
-                    tray_done = 1;
-                } else if (h.cur_tray_count >= FJSP_TRAY_CAPACITY) {  // tray full (:211-216)
-                    s.st(W_ORDER + h.cur_order, ow | (1u << (8 + h.prod_idx - 1)));  // cut after the last loaded product
-                    h.cur_tray_count = 0, h.ready_count++;
-                    tray_done = 1;
-                }
-            }
-        } else if (a[0] == 2) {
-            if (h.cur_tray_count > 0) {                 // SIGNAL (:226-230): the order is not exhausted here
-                u32 ow = s.ld(W_ORDER + h.cur_order);
-                s.st(W_ORDER + h.cur_order, ow | (1u << (8 + h.prod_idx - 1)));
+// R1 pickup station (PickupStationAgent.py:146-232)
+template <class S>
+FJSP_HD void act_pickup(S& s, const Params& P, Hot& h, int a0, int& local10, u32& res) {
+    int loaded = 0, tray_done = 0, idle_orders = 0, success = 0;
+    if (a0 == 0) {
+        idle_orders = (h.num_orders - h.next_order) > 0 || h.cur_order != 63;
+        success = 1;
+    } else if (a0 == 1) {
+        int ok = 1;
+        if (h.cur_order == 63) {
+            if (h.next_order < h.num_orders) h.cur_order = h.next_order++, h.prod_idx = 0;
+            else ok = 0;
+        }
+        if (ok && h.cur_tray_count == 0) {
+            if (h.alloc_count < P.trays_total) h.alloc_count++;  // trays_at_station.pop(0)
+            else ok = 0;
+        }
+        if (ok) {
+            u32 ow = s.ld(W_ORDER + h.cur_order);
+            h.cur_tray_count++, h.prod_idx++;
+            loaded = 1, success = 1;
+            if (h.prod_idx >= ord_n(ow)) {          // order exhausted: tray released (:201-208)
+                h.cur_order = 63, h.prod_idx = 0;
                 h.cur_tray_count = 0, h.ready_count++;
-                success = 1;
+                tray_done = 1;
+            } else if (h.cur_tray_count >= FJSP_TRAY_CAPACITY) {  // tray full (:211-216)
+                s.st(W_ORDER + h.cur_order, ow | (1u << (8 + h.prod_idx - 1)));  // cut after the last loaded product
+                h.cur_tray_count = 0, h.ready_count++;
+                tray_done = 1;
             }
         }
-        res[0] = (success ? FJSP_RES_SUCCESS : 0) | (loaded ? FJSP_RES_PS_LOADED : 0) | (tray_done ? FJSP_RES_PS_TRAY_DONE : 0) |
-                 (idle_orders ? FJSP_RES_PS_IDLE_ORDERS : 0);
-        // RewardModel.py:53-60: +1 load, +5 tray completed, -1 idle with orders
-        local10[0] = (loaded ? 10 : 0) + (tray_done ? 50 : 0) - ((a[0] == 0 && idle_orders) ? 10 : 0);
+    } else if (a0 == 2) {
+        if (h.cur_tray_count > 0) {                 // SIGNAL (:226-230): the order is not exhausted here
+            u32 ow = s.ld(W_ORDER + h.cur_order);
+            s.st(W_ORDER + h.cur_order, ow | (1u << (8 + h.prod_idx - 1)));
+            h.cur_tray_count = 0, h.ready_count++;
+            success = 1;
+        }
     }
+    res = (success ? FJSP_RES_SUCCESS : 0) | (loaded ? FJSP_RES_PS_LOADED : 0) | (tray_done ? FJSP_RES_PS_TRAY_DONE : 0) |
+          (idle_orders ? FJSP_RES_PS_IDLE_ORDERS : 0);
+    // RewardModel.py:53-60: +1 load, +5 tray completed, -1 idle with orders
+    local10 = (loaded ? 10 : 0) + (tray_done ? 50 : 0) - ((a0 == 0 && idle_orders) ? 10 : 0);
+}
+
+// one cell's seven agents: agv, small machine, big machine, four packaging stations.  a/local10/res point at the cell's
+// first column.  pk_start[i] = products whose packaging processes START creates in this step (resolved in run_cell).
+template <class S>
+FJSP_HD void act_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, const int* a, int* local10, u32* res, int* pk_start) {
+    const int pb = pool_base(c);
     // ---- R2-R4 AGV (AGVAgent.py:180-368)
     {
         int invalid = 0, moved = 0, pick = 0, drop = 0, to_pack = 0, success = 0;
-        const int act = a[1];
-        if (h.agv_moving) {
+        const int act = a[0];
+        if (hc.agv_moving) {
             invalid = 1;
         } else if (act == 0) {
             success = 1;
         } else if (act <= 5) {
             const int tl = act == 1 ? LOC_PICKUP : act == 2 ? LOC_SMALL : act == 3 ? LOC_BIG : act == 4 ? LOC_STORAGE : LOC_PACKAGING;
-            success = 1;
-            if (P.dist[h.agv_loc][tl] != 0) {
-                moved = 1;
-                h.agv_moving = 1, h.agv_target = tl;        // resolved in the run phase below
-                h.agv_arrive = k + P.delay[h.agv_loc][tl];
+            const int d = P.dist[hc.agv_loc][tl];
+            if (tl == LOC_PICKUP && d != 0 && (h.dock_mask & ~(1 << c)) != 0) {
+                invalid = 1;  // scaled shop only: the single dock is taken by another cell's AGV
+            } else {
+                success = 1;
+                if (d != 0) {
+                    if (tl == LOC_PICKUP) h.dock_mask |= 1 << c;  // granted now: later AGVs of this step already see it
+                    moved = 1;
+                    hc.agv_moving = 1, hc.agv_target = tl;        // resolved in the run phase
+                    hc.agv_arrive = k + P.delay[hc.agv_loc][tl];
+                }
             }
         } else if (act == 6) {
-            const int loc = h.agv_loc;
-            if (h.carry != 0 || loc == LOC_PACKAGING) {
+            const int loc = hc.agv_loc;
+            if (hc.carry != 0 || loc == LOC_PACKAGING) {
                 invalid = 1;
             } else if (loc == LOC_PICKUP) {
                 if (h.ready_count > 0) {
-                    int slot = pool_alloc(h);
+                    int slot = pool_alloc(hc);
                     if (slot < 0) {
                         h.fault = FJSP_FAULT_POOL_EXHAUSTED, invalid = 1;
                     } else {
@@ -563,102 +637,101 @@ FJSP_HD void step_env_hot(S& s, const Params& P, Hot& h, const int a[8], StepOut
                         u32 ow = s.ld(W_ORDER + h.ready_order);
                         u32 cuts = ord_cut(ow) >> h.ready_idx;
                         int cnt = cuts ? ctz32(cuts) + 1 : ord_n(ow) - h.ready_idx;
-                        s.st(W_POOL + slot, make_rec(h.ready_order, h.ready_idx, cnt, 0));
+                        s.st(pb + slot, make_rec(h.ready_order, h.ready_idx, cnt, 0));
                         h.ready_idx += cnt;
                         if (h.ready_idx >= ord_n(ow)) h.ready_order++, h.ready_idx = 0;
                         h.ready_count--;
-                        h.carry = slot + 1, pick = 1;
+                        hc.carry = slot + 1, pick = 1;
                     }
                 } else invalid = 1;
             } else {
-                Fifo& f = loc == LOC_SMALL ? h.m[0].r : loc == LOC_BIG ? h.m[1].r : h.storage;
-                if (f.len > 0) h.carry = fifo_pop(s, f) + 1, pick = 1;
+                Fifo& f = loc == LOC_SMALL ? hc.m[0].r : loc == LOC_BIG ? hc.m[1].r : hc.storage;
+                if (f.len > 0) hc.carry = fifo_pop(s, pb, f) + 1, pick = 1;
                 else invalid = 1;
             }
             success = pick;
         } else if (act == 7) {
-            const int loc = h.agv_loc;
-            if (h.carry == 0 || loc == LOC_PICKUP) {
+            const int loc = hc.agv_loc;
+            if (hc.carry == 0 || loc == LOC_PICKUP) {
                 invalid = 1;  // empty-handed, or a non-empty tray at PICKUP (:310-317)
             } else {
-                const int slot = h.carry - 1;
-                u32 r = s.ld(W_POOL + slot);
+                const int slot = hc.carry - 1;
+                u32 r = s.ld(pb + slot);
                 u32 ow = s.ld(W_ORDER + rec_order(r));
                 const int ty = ord_type(ow), proc = rec_processed(r);
                 if (loc == LOC_SMALL || loc == LOC_BIG) {
                     int compat = loc == LOC_SMALL ? (ty == TYPE_SMALL || ty == TYPE_MEDIUM) : (ty == TYPE_BIG || ty == TYPE_MEDIUM);
                     if (!proc && compat) {
-                        if (loc == LOC_SMALL) fifo_push(s, h.m[0].q, slot);
-                        else fifo_push(s, h.m[1].q, slot);
+                        if (loc == LOC_SMALL) fifo_push(s, pb, hc.m[0].q, slot);
+                        else fifo_push(s, pb, hc.m[1].q, slot);
                         drop = 1;
                     } else invalid = 1;
                 } else if (loc == LOC_STORAGE) {
-                    if (h.storage.len < P.storage_capacity) fifo_push(s, h.storage, slot);
-                    else s.st(W_POOL + slot, r | (1u << 27));  // Storage.add_tray False ignored: tray vanishes (Storage.py:18-22)
+                    if (hc.storage.len < P.storage_capacity) fifo_push(s, pb, hc.storage, slot);
+                    else s.st(pb + slot, r | (1u << 27));  // Storage.add_tray False ignored: tray vanishes (Storage.py:18-22)
                     drop = 1;
                 } else {  // PACKAGING (:352-360) -> add_tray_to_packaging (FJSPSimulation.py:402-430)
                     if (proc) {
                         const int col = ord_colour(ow), cnt = rec_count(r);
                         int st = -1;
-                        if (col == COL_BLUE) st = h.p[0].users < P.pack_capacity ? 0 : (h.p[1].users < P.pack_capacity ? 1 : -1);
-                        else if (col == COL_RED) st = h.p[2].users < P.pack_capacity ? 2 : -1;
-                        else st = h.p[3].users < P.pack_capacity ? 3 : -1;
-                        if (st == 0) fifo_push(s, h.p[0].q, slot), h.p[0].qcount += cnt;
-                        else if (st == 1) fifo_push(s, h.p[1].q, slot), h.p[1].qcount += cnt;
-                        else if (st == 2) fifo_push(s, h.p[2].q, slot), h.p[2].qcount += cnt;
-                        else if (st == 3) fifo_push(s, h.p[3].q, slot), h.p[3].qcount += cnt;
-                        else s.st(W_POOL + slot, r | (1u << 27));  // no station with capacity: products dropped (:426-427)
+                        if (col == COL_BLUE) st = hc.p[0].users < P.pack_capacity ? 0 : (hc.p[1].users < P.pack_capacity ? 1 : -1);
+                        else if (col == COL_RED) st = hc.p[2].users < P.pack_capacity ? 2 : -1;
+                        else st = hc.p[3].users < P.pack_capacity ? 3 : -1;
+                        if (st == 0) fifo_push(s, pb, hc.p[0].q, slot), hc.p[0].qcount += cnt;
+                        else if (st == 1) fifo_push(s, pb, hc.p[1].q, slot), hc.p[1].qcount += cnt;
+                        else if (st == 2) fifo_push(s, pb, hc.p[2].q, slot), hc.p[2].qcount += cnt;
+                        else if (st == 3) fifo_push(s, pb, hc.p[3].q, slot), hc.p[3].qcount += cnt;
+                        else s.st(pb + slot, r | (1u << 27));  // no station with capacity: products dropped (:426-427)
                         drop = 1, to_pack = 1;
                     } else invalid = 1;
                 }
-                if (drop) h.carry = 0, success = 1;
+                if (drop) hc.carry = 0, success = 1;
             }
         } else {
             invalid = 1;
         }
-        res[1] = (success ? FJSP_RES_SUCCESS : 0) | (invalid ? FJSP_RES_AGV_INVALID : 0) | (moved ? FJSP_RES_AGV_MOVED : 0) |
+        res[0] = (success ? FJSP_RES_SUCCESS : 0) | (invalid ? FJSP_RES_AGV_INVALID : 0) | (moved ? FJSP_RES_AGV_MOVED : 0) |
                  (pick ? FJSP_RES_AGV_PICKUP : 0) | (drop ? FJSP_RES_AGV_DROP : 0) | (to_pack ? FJSP_RES_AGV_TO_PACK : 0);
         // RewardModel.py:62-77: +2 pickup, +2 drop, +10 delivered to packaging, -0.1 move, -5 invalid
-        local10[1] = (pick ? 20 : 0) + (drop ? 20 : 0) + (to_pack ? 100 : 0) - (moved ? 1 : 0) - (invalid ? 50 : 0);
+        local10[0] = (pick ? 20 : 0) + (drop ? 20 : 0) + (to_pack ? 100 : 0) - (moved ? 1 : 0) - (invalid ? 50 : 0);
     }
     // ---- R5 machines (MachineAgent.py:99-169).  START takes effect in this step's run phase, but no later
     //      agent reads machine state inside the action phase, so it is applied here.
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        Mach& m = h.m[i];
-        const int act = a[2 + i];
+        Mach& m = hc.m[i];
+        const int act = a[1 + i];
         int started = 0, completed = 0, idle_q = 0, success = 0;
         if (act == 0) {
             idle_q = m.q.len > 0 && !m.busy;
             success = 1;
         } else if (act == 1) {
             if (m.q.len > 0 && !m.busy) {
-                int slot = fifo_pop(s, m.q);
+                int slot = fifo_pop(s, pb, m.q);
                 if (m.has_cur) {  // unsignalled finished tray is overwritten and lost (:160)
-                    u32 old = s.ld(W_POOL + m.cur);
-                    s.st(W_POOL + m.cur, old | (1u << 27));
+                    u32 old = s.ld(pb + m.cur);
+                    s.st(pb + m.cur, old | (1u << 27));
                 }
                 m.busy = 1, m.has_cur = 1, m.cur = slot, m.start = k;
                 started = 1, success = 1;
             }
         } else if (act == 2) {
             if (!m.busy && m.has_cur) {
-                fifo_push(s, m.r, m.cur);
+                fifo_push(s, pb, m.r, m.cur);
                 m.has_cur = 0, m.cur = 0;
                 completed = 1, success = 1;
             }
         }
-        res[2 + i] = (success ? FJSP_RES_SUCCESS : 0) | (started ? FJSP_RES_M_STARTED : 0) | (completed ? FJSP_RES_M_COMPLETED : 0) |
+        res[1 + i] = (success ? FJSP_RES_SUCCESS : 0) | (started ? FJSP_RES_M_STARTED : 0) | (completed ? FJSP_RES_M_COMPLETED : 0) |
                      (idle_q ? FJSP_RES_M_IDLE_QUEUE : 0);
         // RewardModel.py:79-86: +1 start, +5 signal complete, -2 idle with queue
-        local10[2 + i] = (started ? 10 : 0) + (completed ? 50 : 0) - ((act == 0 && idle_q) ? 20 : 0);
+        local10[1 + i] = (started ? 10 : 0) + (completed ? 50 : 0) - ((act == 0 && idle_q) ? 20 : 0);
     }
     // ---- R6 packaging (PackagingAgent.py:91-125)
-    int pk_start[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        Pack& p = h.p[i];
-        const int act = a[4 + i];
+        Pack& p = hc.p[i];
+        const int act = a[3 + i];
         int started = 0, completed = 0, idle_q = 0, success = 0;
         pk_start[i] = 0;
         if (act == 0) {
@@ -674,24 +747,33 @@ FJSP_HD void step_env_hot(S& s, const Params& P, Hot& h, const int a[8], StepOut
         } else if (act == 2) {
             if (!p.busy && p.hascur) completed = 1;  // success stays False (:120-123)
         }
-        res[4 + i] = (success ? FJSP_RES_SUCCESS : 0) | (started ? FJSP_RES_M_STARTED : 0) | (completed ? FJSP_RES_M_COMPLETED : 0) |
+        res[3 + i] = (success ? FJSP_RES_SUCCESS : 0) | (started ? FJSP_RES_M_STARTED : 0) | (completed ? FJSP_RES_M_COMPLETED : 0) |
                      (idle_q ? FJSP_RES_M_IDLE_QUEUE : 0);
         // RewardModel.py:88-95: +2 start, +20 signal complete, -1 idle with queue
-        local10[4 + i] = (started ? 20 : 0) + (completed ? 200 : 0) - ((act == 0 && idle_q) ? 10 : 0);
+        local10[3 + i] = (started ? 20 : 0) + (completed ? 200 : 0) - ((act == 0 && idle_q) ? 10 : 0);
     }
+}
 
-    // ===== run phase: env.run(until = now + step_size) (FJSPSimulation.py:183-184), rule R0 =====
-    // AGV arrival (AGVAgent.py:387-396)
-    if (h.agv_moving && h.agv_arrive == k) h.agv_loc = h.agv_target, h.agv_moving = 0;
+// ---------------------------------------------------------------------------------------------
+// Run phase of one cell: env.run(until = now + step_size) (FJSPSimulation.py:183-184), rule R0
+// ---------------------------------------------------------------------------------------------
+// `dock_after` collects who holds the dock once the run phase is over; h.dock_mask itself keeps its action-phase meaning
+// until every cell has acted (cells are processed one after the other here, but all actions precede all runs).
+template <class S>
+FJSP_HD void run_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, const int* pk_start, int& dock_after) {
+    const int pb = pool_base(c);
+    // AGV arrival (AGVAgent.py:387-396); the dock is held while standing at PICKUP or under way to it
+    if (hc.agv_moving && hc.agv_arrive == k) hc.agv_loc = hc.agv_target, hc.agv_moving = 0;
+    dock_after |= (hc.agv_moving ? (hc.agv_target == LOC_PICKUP) : (hc.agv_loc == LOC_PICKUP)) << c;
     // machines: product i (1-based) is flagged in step start + P*i; the tray finishes at start + P*n
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        Mach& m = h.m[i];
+        Mach& m = hc.m[i];
         if (m.busy) {
-            u32 r = s.ld(W_POOL + m.cur);
+            u32 r = s.ld(pb + m.cur);
             const int per = i == 0 ? P.small_steps : P.big_steps;
             if (k == m.start + per * rec_count(r)) {
-                s.st(W_POOL + m.cur, r | (1u << 12));
+                s.st(pb + m.cur, r | (1u << 12));
                 m.busy = 0, m.prog = 1;
             }
         }
@@ -701,7 +783,7 @@ FJSP_HD void step_env_hot(S& s, const Params& P, Hot& h, const int a[8], StepOut
     //   -> NORMAL timeouts due at the boundary (finish, release) -> grants -> releases grant waiters FIFO.
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        Pack& p = h.p[i];
+        Pack& p = hc.p[i];
         int g = 0;
         if (pk_start[i] > 0) {
             int room = P.pack_capacity - p.users;
@@ -712,10 +794,10 @@ FJSP_HD void step_env_hot(S& s, const Params& P, Hot& h, const int a[8], StepOut
         int released = 0;
         while (p.f.len > 0) {
             int slot = p.f.head;
-            u32 r = s.ld(W_POOL + slot);
+            u32 r = s.ld(pb + slot);
             if (rec_stamp(r) != (k & 255)) break;
-            fifo_pop(s, p.f);
-            pool_free(h, slot);
+            fifo_pop(s, pb, p.f);
+            pool_free(hc, slot);
             const int o = rec_order(r), cnt = rec_count(r);
             u32 ow = s.ld(W_ORDER + o);
             ow |= (((1u << cnt) - 1u) << rec_first(r)) << 16;   // is_packaged (:143)
@@ -729,58 +811,103 @@ FJSP_HD void step_env_hot(S& s, const Params& P, Hot& h, const int a[8], StepOut
             }
         }
         const int stamp = (k + P.pack_steps) & 255;
-        if (g > 0) pack_grant(s, h, p, g, stamp);
+        if (g > 0) pack_grant(s, pb, h, hc, p, g, stamp);
         if (p.waiters && released > 0) {
             int wgrant = released < p.qcount ? released : p.qcount;
             int room = P.pack_capacity - p.users;
             if (wgrant > room) wgrant = room;
             p.users += wgrant;
-            pack_grant(s, h, p, wgrant, stamp);
+            pack_grant(s, pb, h, hc, p, wgrant, stamp);
             if (p.qcount == 0) p.waiters = 0;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One environment step of a K-cell shop.  `h` = shared hot words and `c0` = cell 0's hot words live with the caller
+// (registers: loaded/stored once per step in the step kernel, once per LAUNCH in the K-steps-per-launch kernel);
+// cells 1..K-1 are loaded and stored here, one at a time.  Agent order: pickup station, then cell by cell agv, small
+// machine, big machine, four packaging stations (FJSPSimulation.py:76-82,172-174 for K = 1).
+// ---------------------------------------------------------------------------------------------
+template <int K, bool WITH_OBS, class S>
+FJSP_HD void step_env_hot(S& s, const Params& P, Hot& h, HotCell& c0, const int* a, StepOut<K>& out) {
+    constexpr int A = Lay<K>::AGENTS;
+    const int k = h.step;
+    const int orders_before = h.completed_orders, products_before = h.total_packaged;
+    int local10[Lay<K>::ACT];  // local rewards in tenths: every RewardModel constant is a multiple of 0.1 (RewardModel.py:12-32)
+    u32 res[Lay<K>::ACT];
+#pragma unroll
+    for (int i = A; i < Lay<K>::ACT; i++) local10[i] = 0, res[i] = 0u;
+
+    act_pickup(s, P, h, a[0], local10[0], res[0]);
+    int dock_after = 0;
+    {
+        int pk_start[4];
+        act_cell(s, P, h, c0, 0, k, a + 1, local10 + 1, res + 1, pk_start);
+        run_cell(s, P, h, c0, 0, k, pk_start, dock_after);
+    }
+#pragma unroll
+    for (int c = 1; c < K; c++) {
+        HotCell hc;
+        int pk_start[4];
+        load_cell<K>(s, c, hc);
+        act_cell(s, P, h, hc, c, k, a + 1 + 7 * c, local10 + 1 + 7 * c, res + 1 + 7 * c, pk_start);
+        run_cell(s, P, h, hc, c, k, pk_start, dock_after);
+        store_cell<K>(s, c, hc);
+    }
+    h.dock_mask = dock_after;
 
     // ===== rewards (FJSPSimulation.py:190-209, RewardModel.py:34-44,99-110) =====
-    // r_i = g/8 + local_i with g = 100*orders + 10*products - 0.1*step_size is an exact multiple of 1/80:
-    //   80*r_i = 10*(100*orders + 10*products) - step_size + 8*(10*local_i).
+    // r_i = g/A + local_i with g = 100*orders + 10*products - 0.1*step_size and A = 1 + 7K agents is an exact multiple of
+    // 1/(10A):  10A*r_i = 10*(100*orders + 10*products) - step_size + A*(10*local_i)   (A = 8: multiples of 1/80).
     // One correctly rounded fp32 division of that integer reproduces the fp32 rounding of the reference's float64 value
-    // (no FP64 in the kernel; a non-dyadic k/80 is never within double-rounding distance of an fp32 midpoint).
+    // (no FP64 in the kernel; a non-dyadic k/(10A) is never within double-rounding distance of an fp32 midpoint).
     {
-        const int g80 = 10 * (100 * (h.completed_orders - orders_before) + 10 * (h.total_packaged - products_before)) - P.step_size;
-        long long r40 = 0;
+        const int g = 10 * (100 * (h.completed_orders - orders_before) + 10 * (h.total_packaged - products_before)) - P.step_size;
+        long long units = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int r80 = g80 + 8 * local10[i];
-            out.reward[i] = (float)r80 / 80.0f;
-            r40 += r80 >= 0 ? (r80 + 1) / 2 : -((1 - r80) / 2);  // round(40 r), halves away from zero
+        for (int i = 0; i < Lay<K>::ACT; i++) {
+            if (i < A) {
+                const int n = g + A * local10[i];
+                out.reward[i] = (float)n / (float)(10 * A);
+                units += n;
+            } else {
+                out.reward[i] = 0.0f;
+            }
         }
-        out.reward40 = r40;
+        out.reward_units = units;
     }
     // ===== termination / truncation (FJSPSimulation.py:216-224), pre-increment step =====
     const int all_done = h.completed_orders == h.num_orders && h.num_orders > 0 && h.next_order == h.num_orders;
     const int truncated = k >= P.max_episode_steps;
     out.flags = (u32)all_done | ((u32)truncated << 8) | ((u32)h.fault << 16);
-    out.results[0] = res[0] | (res[1] << 8) | (res[2] << 16) | (res[3] << 24);
-    out.results[1] = res[4] | (res[5] << 8) | (res[6] << 16) | (res[7] << 24);
+#pragma unroll
+    for (int i = 0; i < Lay<K>::ACT / 4; i++)
+        out.results[i] = res[4 * i] | (res[4 * i + 1] << 8) | (res[4 * i + 2] << 16) | (res[4 * i + 3] << 24);
     h.step = k + 1;
     out.info[0] = h.step, out.info[1] = h.completed_orders, out.info[2] = h.total_packaged, out.info[3] = 0;
-    if (WITH_OBS) observe(s, P, h, out.obs, out.mask);
+    if (WITH_OBS) observe<K>(s, P, h, c0, out.obs, out.mask);
 }
 
-template <bool WITH_OBS, class S>
-FJSP_HD void step_env(S& s, const Params& P, const int a[8], StepOut& out) {
+template <int K, bool WITH_OBS, class S>
+FJSP_HD void step_env(S& s, const Params& P, const int* a, StepOut<K>& out) {
     Hot h;
+    HotCell c0;
     load_hot(s, h);
-    step_env_hot<WITH_OBS>(s, P, h, a, out);
+    load_cell<K>(s, 0, c0);
+    step_env_hot<K, WITH_OBS>(s, P, h, c0, a, out);
     store_hot(s, h);
+    store_cell<K>(s, 0, c0);
 }
 
 // observation of the current state without stepping (reset path)
-template <class S>
+template <int K, class S>
 FJSP_HD void observe_env(S& s, const Params& P, float* obs, u32* mw) {
     Hot h;
+    HotCell c0;
     load_hot(s, h);
-    observe(s, P, h, obs, mw);
+    load_cell<K>(s, 0, c0);
+    observe<K>(s, P, h, c0, obs, mw);
 }
 
 }  // namespace fjsp

@@ -25,6 +25,7 @@ inline void default_config(FjspConfig* c) {
     c->proc_small = 60, c->proc_big = 120, c->proc_pack = 30;  // constants.py:14-18
     c->step_size = 10, c->agv_speed = 1, c->max_episode_steps = 200;
     c->storage_capacity = 100, c->pack_capacity = 20, c->tray_capacity = 5, c->num_trays = 1000;
+    c->num_cells = 1;
 }
 
 // Returns nullptr if ok, else a static message.
@@ -42,6 +43,7 @@ inline const char* make_params(const FjspConfig& c, Params* P) {
     if (c.pack_capacity < 1 || c.pack_capacity > 31) return "pack_capacity must be in 1..31";
     if (c.storage_capacity < 0) return "storage_capacity must be >= 0";
     if (c.num_trays < 0 || c.num_trays > 65535) return "num_trays must be in 0..65535";
+    if (c.num_cells < 1 || c.num_cells > FJSP_MAX_CELLS) return "num_cells must be in 1..4";
     for (int a = 0; a < FJSP_NUM_LOCATIONS; a++)
         for (int b = a + 1; b < FJSP_NUM_LOCATIONS; b++)
             if (c.pos[a][0] == c.pos[b][0] && c.pos[a][1] == c.pos[b][1]) return "station positions must be distinct";
@@ -79,11 +81,15 @@ struct ArrayState {
     FJSP_HD void st_hot(int i, u32 v) { w[i] = v; }
 };
 
-// ---- canonical record S from packed words ----
-inline void export_canon(const u32* words, const Params& P, FjspCanonState* out) {
+// ---- canonical record S from packed words: shared pickup station / orders + the given cell ----
+template <int K>
+inline void export_canon_k(const u32* words, const Params& P, int cell, FjspCanonState* out) {
     ArrayState s{const_cast<u32*>(words)};
     Hot h;
+    HotCell hc;
     load_hot(s, h);
+    load_cell<K>(s, cell, hc);
+    const int pb = pool_base(cell);
     FjspCanonState& c = *out;
     memset(&c, 0, sizeof(c));
     auto order_word = [&](int o) { return words[W_ORDER + o]; };
@@ -101,16 +107,16 @@ inline void export_canon(const u32* words, const Params& P, FjspCanonState* out)
         for (int i = 0; i < cap; i++) dst[i] = -1;
         int slot = f.head;
         for (int i = 0; i < f.len && i < cap; i++) {
-            u32 r = words[W_POOL + slot];
+            u32 r = words[pb + slot];
             dst[i] = rec_entry(r);
             slot = rec_next(r);
         }
         return f.len;
     };
     c.current_step = h.step, c.num_orders = h.num_orders, c.fault = h.fault;
-    c.agv_row = P.pos_row[h.agv_loc], c.agv_col = P.pos_col[h.agv_loc];
-    c.agv_carry = h.carry ? rec_entry(words[W_POOL + h.carry - 1]) : -1;
-    c.agv_is_moving = h.agv_moving;
+    c.agv_row = P.pos_row[hc.agv_loc], c.agv_col = P.pos_col[hc.agv_loc];
+    c.agv_carry = hc.carry ? rec_entry(words[pb + hc.carry - 1]) : -1;
+    c.agv_is_moving = hc.agv_moving;
     c.ps_order_queue_len = h.num_orders - h.next_order;
     c.ps_current_order = h.cur_order == 63 ? -1 : h.cur_order;
     c.ps_product_idx = h.prod_idx;
@@ -129,28 +135,17 @@ inline void export_canon(const u32* words, const Params& P, FjspCanonState* out)
         }
         c.ps_ready_n = h.ready_count;
     }
-    int partial_order[2] = {-1, -1};
-    u32 partial_mask[2] = {0, 0};
     for (int i = 0; i < 2; i++) {
-        const Mach& m = h.m[i];
+        const Mach& m = hc.m[i];
         c.machine[i].is_busy = m.busy;
-        c.machine[i].current_tray = m.has_cur ? rec_entry(words[W_POOL + m.cur]) : -1;
+        c.machine[i].current_tray = m.has_cur ? rec_entry(words[pb + m.cur]) : -1;
         c.machine[i].progress_done = m.prog;
         c.machine[i].queue_n = walk(m.q, c.machine[i].queue, FJSP_CANON_MAXQ);
         c.machine[i].ready_n = walk(m.r, c.machine[i].ready, FJSP_CANON_MAXQ);
-        if (m.busy) {  // products flagged so far: i <= (last executed step - start) / per
-            u32 r = words[W_POOL + m.cur];
-            int per = i == 0 ? P.small_steps : P.big_steps;
-            int done = (h.step - 1 - m.start) / per;
-            if (done > rec_count(r)) done = rec_count(r);
-            if (done < 0) done = 0;
-            partial_order[i] = rec_order(r);
-            partial_mask[i] = ((1u << done) - 1u) << rec_first(r);
-        }
     }
-    c.storage_n = walk(h.storage, c.storage, FJSP_CANON_MAXQ);
+    c.storage_n = walk(hc.storage, c.storage, FJSP_CANON_MAXQ);
     for (int i = 0; i < 4; i++) {
-        const Pack& p = h.p[i];
+        const Pack& p = hc.p[i];
         c.pack[i].is_busy = p.busy;
         c.pack[i].current_product = p.hascur ? (p.curprod & 31) * 100 + (p.curprod >> 5) : -1;
         c.pack[i].progress_L = p.progL;
@@ -159,7 +154,7 @@ inline void export_canon(const u32* words, const Params& P, FjspCanonState* out)
         for (int k = 0; k < FJSP_CANON_MAXPQ; k++) c.pack[i].queue[k] = -1;
         int slot = p.q.head, n = 0;
         for (int k = 0; k < p.q.len; k++) {
-            u32 r = words[W_POOL + slot];
+            u32 r = words[pb + slot];
             for (int j = 0; j < rec_count(r) && n < FJSP_CANON_MAXPQ; j++) c.pack[i].queue[n++] = rec_order(r) * 100 + rec_first(r) + j;
             slot = rec_next(r);
         }
@@ -173,16 +168,39 @@ inline void export_canon(const u32* words, const Params& P, FjspCanonState* out)
         c.order_complete[o] = cs != 0;
         c.order_completion_step[o] = cs - 1;
     }
-    uint64_t free_bits = (uint64_t)h.free_lo | ((uint64_t)h.free_hi << 32);
-    for (int slot = 0; slot < FJSP_POOL_SLOTS; slot++) {
-        if ((free_bits >> slot) & 1u) continue;
-        u32 r = words[W_POOL + slot];
-        if (rec_processed(r)) c.processed_mask[rec_order(r)] |= (int32_t)(((1u << rec_count(r)) - 1u) << rec_first(r));
+    // is_processed is a property of the products, whatever cell their tray is in: scan every cell's pool and machines
+    for (int cc = 0; cc < K; cc++) {
+        HotCell x;
+        load_cell<K>(s, cc, x);
+        const int xb = pool_base(cc);
+        uint64_t free_bits = (uint64_t)x.free_lo | ((uint64_t)x.free_hi << 32);
+        for (int slot = 0; slot < FJSP_POOL_SLOTS; slot++) {
+            if ((free_bits >> slot) & 1u) continue;
+            u32 r = words[xb + slot];
+            if (rec_processed(r)) c.processed_mask[rec_order(r)] |= (int32_t)(((1u << rec_count(r)) - 1u) << rec_first(r));
+        }
+        for (int i = 0; i < 2; i++) {
+            const Mach& m = x.m[i];
+            if (!m.busy) continue;  // products flagged so far: i <= (last executed step - start) / per
+            u32 r = words[xb + m.cur];
+            int per = i == 0 ? P.small_steps : P.big_steps;
+            int done = (h.step - 1 - m.start) / per;
+            if (done > rec_count(r)) done = rec_count(r);
+            if (done < 0) done = 0;
+            c.processed_mask[rec_order(r)] |= (int32_t)(((1u << done) - 1u) << rec_first(r));
+        }
     }
-    for (int i = 0; i < 2; i++)
-        if (partial_order[i] >= 0) c.processed_mask[partial_order[i]] |= (int32_t)partial_mask[i];
     c.total_products_packaged = h.total_packaged;
     c.completed_orders = h.completed_orders;
+}
+
+inline void export_canon(const u32* words, const Params& P, int cells, int cell, FjspCanonState* out) {
+    switch (cells) {
+        case 1: export_canon_k<1>(words, P, cell, out); break;
+        case 2: export_canon_k<2>(words, P, cell, out); break;
+        case 3: export_canon_k<3>(words, P, cell, out); break;
+        default: export_canon_k<4>(words, P, cell, out); break;
+    }
 }
 
 }  // namespace fjsp

@@ -12,8 +12,17 @@ using namespace fjsp;
 
 struct HostEnv {
     Params P;
-    u32 words[W_TOTAL];
+    int cells;
+    u32 words[FJSP_STATE_WORDS_K(FJSP_MAX_CELLS)];
 };
+
+#define DISPATCH_K(e, ...)                                  \
+    switch ((e)->cells) {                                   \
+        case 1: { constexpr int K = 1; __VA_ARGS__; } break;  \
+        case 2: { constexpr int K = 2; __VA_ARGS__; } break;  \
+        case 3: { constexpr int K = 3; __VA_ARGS__; } break;  \
+        default: { constexpr int K = 4; __VA_ARGS__; } break; \
+    }
 
 extern "C" {
 
@@ -25,6 +34,7 @@ void* hh_create(const FjspConfig* cfg) {
         free(e);
         return nullptr;
     }
+    e->cells = c.num_cells;
     return e;
 }
 const char* hh_check_config(const FjspConfig* cfg) {
@@ -34,52 +44,60 @@ const char* hh_check_config(const FjspConfig* cfg) {
 }
 void hh_destroy(void* p) { free(p); }
 
-static void unpack_masks(const u32* mw, int8_t* masks) {
-    for (int i = 0; i < FJSP_MASK_DIM; i++) masks[i] = (int8_t)((mw[i >> 2] >> ((i & 3) * 8)) & 0xff);
+static void unpack_bytes(const u32* w, int n, uint8_t* dst) {
+    for (int i = 0; i < n; i++) dst[i] = (uint8_t)((w[i >> 2] >> ((i & 3) * 8)) & 0xff);
 }
 
 void hh_observe(void* p, float* obs, int8_t* masks) {
     HostEnv* e = (HostEnv*)p;
     ArrayState s{e->words};
-    u32 mw[FJSP_MASK_DIM / 4];
-    observe_env(s, e->P, obs, mw);
-    unpack_masks(mw, masks);
+    DISPATCH_K(e, {
+        u32 mw[Lay<K>::MASK / 4];
+        observe_env<K>(s, e->P, obs, mw);
+        unpack_bytes(mw, Lay<K>::MASK, (uint8_t*)masks);
+    })
 }
 
 void hh_reset(void* p, const FjspOrderRec* orders, int num_orders, uint64_t seed, uint64_t genv, uint32_t episode) {
     HostEnv* e = (HostEnv*)p;
     ArrayState s{e->words};
-    reset_env(s, e->P, num_orders, orders, seed, genv, episode);
+    DISPATCH_K(e, reset_env<K>(s, e->P, num_orders, orders, seed, genv, episode))
 }
 
 void hh_step(void* p, const uint8_t* actions, float* obs, int8_t* masks, float* rewards, uint8_t* flags, uint8_t* results,
              int32_t* infos) {
     HostEnv* e = (HostEnv*)p;
     ArrayState s{e->words};
-    int a[8];
-    for (int i = 0; i < 8; i++) a[i] = actions[i];
-    StepOut out;
-    out.obs = obs;
-    step_env<true>(s, e->P, a, out);
-    unpack_masks(out.mask, masks);
-    for (int i = 0; i < 8; i++) rewards[i] = out.reward[i];
-    flags[0] = out.flags & 0xff, flags[1] = (out.flags >> 8) & 0xff, flags[2] = (out.flags >> 16) & 0xff, flags[3] = 0;
-    if (results)
-        for (int i = 0; i < 8; i++) results[i] = (uint8_t)((out.results[i >> 2] >> ((i & 3) * 8)) & 0xff);
-    if (infos)
-        for (int i = 0; i < 4; i++) infos[i] = out.info[i];
+    DISPATCH_K(e, {
+        int a[Lay<K>::ACT];
+        for (int i = 0; i < Lay<K>::ACT; i++) a[i] = actions[i];
+        StepOut<K> out;
+        out.obs = obs;
+        step_env<K, true>(s, e->P, a, out);
+        unpack_bytes(out.mask, Lay<K>::MASK, (uint8_t*)masks);
+        for (int i = 0; i < Lay<K>::ACT; i++) rewards[i] = out.reward[i];
+        flags[0] = out.flags & 0xff, flags[1] = (out.flags >> 8) & 0xff, flags[2] = (out.flags >> 16) & 0xff, flags[3] = 0;
+        if (results) unpack_bytes(out.results, Lay<K>::ACT, results);
+        if (infos)
+            for (int i = 0; i < 4; i++) infos[i] = out.info[i];
+    })
 }
 
-void hh_export(void* p, FjspCanonState* out) {
+void hh_export(void* p, int cell, FjspCanonState* out) {
     HostEnv* e = (HostEnv*)p;
-    export_canon(e->words, e->P, out);
+    export_canon(e->words, e->P, e->cells, cell, out);
 }
-void hh_words(void* p, uint32_t* out) { memcpy(out, ((HostEnv*)p)->words, sizeof(u32) * W_TOTAL); }
+void hh_words(void* p, uint32_t* out) { memcpy(out, ((HostEnv*)p)->words, sizeof(u32) * FJSP_STATE_WORDS_K(((HostEnv*)p)->cells)); }
 
-void hh_philox_actions(uint64_t seed, uint64_t genv, uint64_t t, uint8_t* out) {
-    int a[8];
-    philox_actions(seed, genv, t, a);
-    for (int i = 0; i < 8; i++) out[i] = (uint8_t)a[i];
+void hh_philox_actions(uint64_t seed, uint64_t genv, uint64_t t, int cells, uint8_t* out) {
+    int a[FJSP_ACT_DIM_K(FJSP_MAX_CELLS)] = {0};
+    switch (cells) {
+        case 1: philox_actions_k<1>(seed, genv, t, a); break;
+        case 2: philox_actions_k<2>(seed, genv, t, a); break;
+        case 3: philox_actions_k<3>(seed, genv, t, a); break;
+        default: philox_actions_k<4>(seed, genv, t, a); break;
+    }
+    for (int i = 0; i < FJSP_ACT_DIM_K(cells); i++) out[i] = (uint8_t)a[i];
 }
 void hh_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out); }
 }

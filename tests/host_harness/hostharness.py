@@ -6,7 +6,7 @@ import subprocess
 import numpy as np
 
 from oracle.canon import CANON_DT
-from oracle.fjsp_oracle import FjspConfig, default_config, order_rec
+from oracle.fjsp_oracle import FjspConfig, default_config, dims, order_rec
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libfjsp_hostharness.so")
@@ -37,9 +37,9 @@ def lib():
         L.hh_observe.argtypes = [C.c_void_p] * 3
         L.hh_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32]
         L.hh_step.argtypes = [C.c_void_p] * 8
-        L.hh_export.argtypes = [C.c_void_p, C.c_void_p]
+        L.hh_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.hh_words.argtypes = [C.c_void_p, C.c_void_p]
-        L.hh_philox_actions.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.hh_philox_actions.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
         L.hh_philox.argtypes = [C.c_void_p] * 3
         _lib = L
     return _lib
@@ -52,11 +52,13 @@ class HostEnv:
         self._h = self._L.hh_create(C.addressof(self.cfg))
         if not self._h:
             raise ValueError(self._L.hh_check_config(C.addressof(self.cfg)).decode())
-        self.obs = np.zeros(38, np.float32)
-        self.masks = np.zeros(32, np.int8)
-        self.rewards = np.zeros(8, np.float32)
+        self.cells = max(1, int(self.cfg.num_cells))
+        d = dims(self.cells)
+        self.obs = np.zeros(d["obs"], np.float32)
+        self.masks = np.zeros(d["mask"], np.int8)
+        self.rewards = np.zeros(d["act"], np.float32)
         self.flags = np.zeros(4, np.uint8)
-        self.results = np.zeros(8, np.uint8)
+        self.results = np.zeros(d["act"], np.uint8)
         self.infos = np.zeros(4, np.int32)
 
     def __del__(self):
@@ -84,12 +86,12 @@ class HostEnv:
                         self.flags.ctypes.data, self.results.ctypes.data, self.infos.ctypes.data)
         return self.obs.copy(), self.masks.copy(), self.rewards.copy(), self.flags.copy()
 
-    def export(self):
+    def export(self, cell=0):
         s = np.zeros((), dtype=CANON_DT)
-        self._L.hh_export(self._h, s.ctypes.data)
+        self._L.hh_export(self._h, int(cell), s.ctypes.data)
         return s
 
     def words(self):
-        w = np.zeros(128, np.uint32)
+        w = np.zeros(64 + 64 * self.cells + 20 * (self.cells - 1), np.uint32)
         self._L.hh_words(self._h, w.ctypes.data)
         return w

@@ -54,7 +54,7 @@ def test_streams_agree_and_are_in_range():
         want = [((int(r[j >> 1]) >> 16 if j & 1 else int(r[j >> 1]) & 0xffff) * nact[j]) >> 16 for j in range(8)]
         a = fjsp_oracle.philox_actions(seed, genv, t)
         b = np.zeros(8, np.uint8)
-        hostharness.lib().hh_philox_actions(seed, genv, t, b.ctypes.data)
+        hostharness.lib().hh_philox_actions(seed, genv, t, 1, b.ctypes.data)
         assert a.tolist() == want and b.tolist() == want
         for j in range(8):
             counts[j, want[j]] += 1

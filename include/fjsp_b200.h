@@ -129,7 +129,8 @@ int fjsp_default_config(FjspConfig* cfg);
 int fjsp_create(const FjspConfig* cfg, int64_t num_envs, int64_t first_env, int device, FjspHandle** out);
 int fjsp_destroy(FjspHandle* h);
 int64_t fjsp_num_envs(const FjspHandle* h);
-size_t fjsp_state_bytes(const FjspHandle* h);   /* packed HBM bytes per env (512) */
+int fjsp_num_cells(const FjspHandle* h);        /* K of the handle's config (1 = the reference shop) */
+size_t fjsp_state_bytes(const FjspHandle* h);   /* packed HBM bytes per env (512 for K = 1, 4 * FJSP_STATE_WORDS_K(K)) */
 void* fjsp_state_ptr(FjspHandle* h);            /* device pointer of the packed state (tiles) */
 
 /* FJSPParallelEnv.reset (FJSPParallelEnvWrapper.py:43-54) -> FJSPSimulation.reset (:286-323).
@@ -171,7 +172,7 @@ int fjsp_rollout_random(FjspHandle* h, int steps, uint64_t seed, uint64_t t0, ui
  * and order table; fjsp_export_state is cell 0. */
 int fjsp_export_state(FjspHandle* h, int64_t env, FjspCanonState* out);
 int fjsp_export_state_cell(FjspHandle* h, int64_t env, int cell, FjspCanonState* out);
-/* Raw packed words of one env (128 x u32) copied to the host (synchronises). */
+/* Raw packed words of one env (FJSP_STATE_WORDS_K(K) x u32; 128 for K = 1) copied to the host (synchronises). */
 int fjsp_export_packed(FjspHandle* h, int64_t env, uint32_t* out_words);
 
 /* Snapshot / restore of the whole packed state (num_tiles * 32 KB, see fjsp_state_total_bytes) to / from a

@@ -20,6 +20,16 @@ HEADER = os.path.join(_REPO, "include", "fjsp_b200.h")
 
 NUM_AGENTS, OBS_DIM, MASK_DIM, FLAG_DIM, INFO_DIM, MAX_ORDERS = 8, 38, 32, 4, 4, 32
 STATE_WORDS, TILE_ENVS = 128, 64
+MAX_CELLS = 4
+ABI_VERSION = 2
+
+
+def dims(cells: int = 1) -> dict:
+    """Row widths of a K-cell shop (include/fjsp_b200.h FJSP_*_K); K = 1 is the reference shop (8 / 38 / 32 / 128)."""
+    agents = 1 + 7 * cells
+    return {"agents": agents, "act": (agents + 7) // 8 * 8, "obs": 7 + 31 * cells, "mask": (3 + 26 * cells + 31) // 32 * 32,
+            "mask_used": 3 + 26 * cells, "state_words": 64 + 64 * cells + 20 * (cells - 1)}
+
 CANON_MAXQ, CANON_PS_READY, CANON_MAXPQ = 64, 256, 256
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -35,7 +45,7 @@ class FjspConfig(C.Structure):
         ("proc_small", C.c_int32), ("proc_big", C.c_int32), ("proc_pack", C.c_int32),
         ("step_size", C.c_int32), ("agv_speed", C.c_int32), ("max_episode_steps", C.c_int32),
         ("storage_capacity", C.c_int32), ("pack_capacity", C.c_int32),
-        ("tray_capacity", C.c_int32), ("num_trays", C.c_int32),
+        ("tray_capacity", C.c_int32), ("num_trays", C.c_int32), ("num_cells", C.c_int32),
     ]
 
 
@@ -60,7 +70,8 @@ CANON_DT = np.dtype([
 EXPORTS = [
     "fjsp_last_error", "fjsp_abi_version", "fjsp_default_config", "fjsp_create", "fjsp_destroy", "fjsp_num_envs",
     "fjsp_state_bytes", "fjsp_state_ptr", "fjsp_reset", "fjsp_step", "fjsp_step_host", "fjsp_random_actions",
-    "fjsp_rollout_random", "fjsp_export_state", "fjsp_export_packed", "fjsp_launch_count",
+    "fjsp_rollout_random", "fjsp_export_state", "fjsp_export_state_cell", "fjsp_export_packed", "fjsp_launch_count",
+    "fjsp_num_cells",
     "fjsp_state_total_bytes", "fjsp_state_save", "fjsp_state_load",
     "fjsp_a2c_sample", "fjsp_a2c_counter_add", "fjsp_a2c_gae",
 ]
@@ -126,8 +137,10 @@ def lib() -> C.CDLL:
     L.fjsp_a2c_counter_add.argtypes = [vp, u64, vp]
     L.fjsp_a2c_gae.argtypes = [vp, vp, vp, vp, vp, C.c_int, i64, C.c_float, C.c_float, vp]
     L.fjsp_export_state.argtypes = [vp, i64, vp]
+    L.fjsp_export_state_cell.argtypes = [vp, i64, C.c_int, vp]
     L.fjsp_export_packed.argtypes = [vp, i64, vp]
-    if L.fjsp_abi_version() != 1:
+    L.fjsp_num_cells.restype, L.fjsp_num_cells.argtypes = C.c_int, [vp]
+    if L.fjsp_abi_version() != ABI_VERSION:
         raise RuntimeError("libfjsp_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -151,7 +164,7 @@ def config_from_dict(d: dict | None) -> FjspConfig:
     if not d:
         return cfg
     for k in ("grid_rows", "grid_cols", "step_size", "agv_speed", "max_episode_steps", "storage_capacity",
-              "pack_capacity", "tray_capacity", "num_trays", "proc_small", "proc_big", "proc_pack"):
+              "pack_capacity", "tray_capacity", "num_trays", "proc_small", "proc_big", "proc_pack", "num_cells"):
         if k in d:
             setattr(cfg, k, int(d[k]))
     pt = d.get("processing_times") or {}

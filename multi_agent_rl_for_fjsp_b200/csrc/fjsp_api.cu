@@ -16,8 +16,11 @@ struct FjspHandle {
     FjspConfig cfg;
     Params P;
     int device;
+    int cells;               // K: 1 = the reference shop, 2..4 = scaled shop
+    int act, obs, mask;      // row widths of the I/O tensors (FJSP_*_DIM_K)
+    size_t tile_bytes;       // 64 envs x FJSP_STATE_WORDS_K words
     int64_t num_envs, first_env, num_tiles;
-    u32* state;  // num_tiles * 32 KB
+    u32* state;  // num_tiles * tile_bytes
     uint64_t seed;
     int num_orders;
     int64_t launches;
@@ -59,6 +62,23 @@ struct DeviceGuard {
     }
 };
 
+// The kernels are templated on the number of cells K; one switch per launch site.
+#define DISPATCH_K(cells, ...)                                 \
+    switch (cells) {                                           \
+        case 1: { constexpr int K = 1; __VA_ARGS__; } break;   \
+        case 2: { constexpr int K = 2; __VA_ARGS__; } break;   \
+        case 3: { constexpr int K = 3; __VA_ARGS__; } break;   \
+        default: { constexpr int K = 4; __VA_ARGS__; } break;  \
+    }
+
+template <int K>
+static cudaError_t set_smem_attrs() {
+    cudaError_t e = cudaFuncSetAttribute(fjsp_step_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::STEP_SMEM_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(fjsp_rollout_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::ROLLOUT_SMEM_BYTES);
+    return e;
+}
+
 extern "C" {
 
 const char* fjsp_last_error(void) { return g_err.c_str(); }
@@ -91,23 +111,25 @@ int fjsp_create(const FjspConfig* cfg, int64_t num_envs, int64_t first_env, int 
     if (!h) return fail("out of host memory");
     h->cfg = c, h->P = P, h->device = device;
     h->num_envs = num_envs, h->first_env = first_env;
+    h->cells = c.num_cells;
+    h->act = FJSP_ACT_DIM_K(h->cells), h->obs = FJSP_OBS_DIM_K(h->cells), h->mask = FJSP_MASK_DIM_K(h->cells);
+    h->tile_bytes = (size_t)FJSP_STATE_WORDS_K(h->cells) * TILE * sizeof(u32);
     h->num_tiles = (num_envs + TILE - 1) / TILE;
     h->seed = 0, h->num_orders = 30, h->launches = 0;
-    cudaError_t e = cudaMalloc(&h->state, (size_t)h->num_tiles * TILE_BYTES);
+    cudaError_t e = cudaMalloc(&h->state, (size_t)h->num_tiles * h->tile_bytes);
     if (e != cudaSuccess) {
         delete h;
         return cuda_fail(e, "cudaMalloc(state)");
     }
-    e = cudaFuncSetAttribute(fjsp_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEP_SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(fjsp_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ROLLOUT_SMEM_BYTES);
+    DISPATCH_K(h->cells, e = set_smem_attrs<K>())
     if (e != cudaSuccess) {
         cudaFree(h->state);
         delete h;
         return cuda_fail(e, "cudaFuncSetAttribute (is this an sm_100a device?)");
     }
     // all envs start as freshly reset, empty shops (num_orders = 0) until fjsp_reset is called
-    fjsp_reset_kernel<<<(unsigned)h->num_tiles, TILE>>>(h->P, h->state, nullptr, nullptr, 0, 0ull, h->num_envs, h->first_env, nullptr,
-                                                        nullptr);
+    DISPATCH_K(h->cells, fjsp_reset_kernel<K><<<(unsigned)h->num_tiles, TILE>>>(h->P, h->state, nullptr, nullptr, 0, 0ull, h->num_envs,
+                                                                                h->first_env, nullptr, nullptr))
     h->launches++;
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -134,10 +156,8 @@ int fjsp_destroy(FjspHandle* h) {
 }
 
 int64_t fjsp_num_envs(const FjspHandle* h) { return h ? h->num_envs : 0; }
-size_t fjsp_state_bytes(const FjspHandle* h) {
-    (void)h;
-    return (size_t)FJSP_STATE_WORDS * 4;
-}
+int fjsp_num_cells(const FjspHandle* h) { return h ? h->cells : 0; }
+size_t fjsp_state_bytes(const FjspHandle* h) { return h ? (size_t)FJSP_STATE_WORDS_K(h->cells) * 4 : 0; }
 void* fjsp_state_ptr(FjspHandle* h) { return h ? h->state : nullptr; }
 int64_t fjsp_launch_count(const FjspHandle* h) { return h ? h->launches : 0; }
 
@@ -148,8 +168,8 @@ int fjsp_reset(FjspHandle* h, const uint8_t* env_mask, uint64_t seed, const Fjsp
     if ((obs == nullptr) != (masks == nullptr)) return fail("obs and masks must both be given or both be NULL");
     DeviceGuard g(h->device);
     h->seed = seed, h->num_orders = num_orders;
-    fjsp_reset_kernel<<<(unsigned)h->num_tiles, TILE, 0, (cudaStream_t)stream>>>(h->P, h->state, env_mask, orders, num_orders, seed,
-                                                                                h->num_envs, h->first_env, obs, masks);
+    DISPATCH_K(h->cells, fjsp_reset_kernel<K><<<(unsigned)h->num_tiles, TILE, 0, (cudaStream_t)stream>>>(
+                             h->P, h->state, env_mask, orders, num_orders, seed, h->num_envs, h->first_env, obs, masks))
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -168,7 +188,7 @@ int fjsp_step(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, 
     A.state = h->state, A.actions = actions, A.obs = obs, A.masks = masks, A.rewards = rewards, A.flags = flags;
     A.results = results, A.infos = infos, A.num_envs = h->num_envs, A.first_env = h->first_env, A.seed = h->seed;
     A.num_orders = h->num_orders, A.autoreset = autoreset, A.tile_begin = 0;
-    fjsp_step_kernel<<<(unsigned)h->num_tiles, TILE, STEP_SMEM_BYTES, (cudaStream_t)stream>>>(h->P, A);
+    DISPATCH_K(h->cells, fjsp_step_kernel<K><<<(unsigned)h->num_tiles, TILE, Geo<K>::STEP_SMEM_BYTES, (cudaStream_t)stream>>>(h->P, A))
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -177,10 +197,10 @@ int fjsp_step(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, 
 static int ensure_staging(FjspHandle* h) {
     if (h->d_actions) return 0;
     const size_t n = (size_t)h->num_envs;
-    CK(cudaMalloc(&h->d_actions, n * FJSP_NUM_AGENTS));
-    CK(cudaMalloc(&h->d_obs, n * FJSP_OBS_DIM * sizeof(float)));
-    CK(cudaMalloc(&h->d_masks, n * FJSP_MASK_DIM));
-    CK(cudaMalloc(&h->d_rewards, n * FJSP_NUM_AGENTS * sizeof(float)));
+    CK(cudaMalloc(&h->d_actions, n * h->act));
+    CK(cudaMalloc(&h->d_obs, n * h->obs * sizeof(float)));
+    CK(cudaMalloc(&h->d_masks, n * h->mask));
+    CK(cudaMalloc(&h->d_rewards, n * h->act * sizeof(float)));
     CK(cudaMalloc(&h->d_flags, n * FJSP_FLAG_DIM));
     for (int i = 0; i < 2; i++) {
         CK(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
@@ -215,17 +235,15 @@ int fjsp_step_host(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* ma
         const int64_t t1 = t0 + per < tiles ? t0 + per : tiles;
         const int64_t e0 = t0 * TILE, e1 = t1 * TILE < h->num_envs ? t1 * TILE : h->num_envs;
         const size_t n = (size_t)(e1 - e0);
-        CK(cudaMemcpyAsync(h->d_actions + e0 * FJSP_NUM_AGENTS, actions + e0 * FJSP_NUM_AGENTS, n * FJSP_NUM_AGENTS,
-                           cudaMemcpyHostToDevice, st));
+        const int64_t na = h->act, no = h->obs, nm = h->mask;
+        CK(cudaMemcpyAsync(h->d_actions + e0 * na, actions + e0 * na, n * na, cudaMemcpyHostToDevice, st));
         A.tile_begin = t0;
-        fjsp_step_kernel<<<(unsigned)(t1 - t0), TILE, STEP_SMEM_BYTES, st>>>(h->P, A);
+        DISPATCH_K(h->cells, fjsp_step_kernel<K><<<(unsigned)(t1 - t0), TILE, Geo<K>::STEP_SMEM_BYTES, st>>>(h->P, A))
         h->launches++;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(obs + e0 * FJSP_OBS_DIM, h->d_obs + e0 * FJSP_OBS_DIM, n * FJSP_OBS_DIM * sizeof(float),
-                           cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(masks + e0 * FJSP_MASK_DIM, h->d_masks + e0 * FJSP_MASK_DIM, n * FJSP_MASK_DIM, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(rewards + e0 * FJSP_NUM_AGENTS, h->d_rewards + e0 * FJSP_NUM_AGENTS, n * FJSP_NUM_AGENTS * sizeof(float),
-                           cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(obs + e0 * no, h->d_obs + e0 * no, n * no * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(masks + e0 * nm, h->d_masks + e0 * nm, n * nm, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(rewards + e0 * na, h->d_rewards + e0 * na, n * na * sizeof(float), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(flags + e0 * FJSP_FLAG_DIM, h->d_flags + e0 * FJSP_FLAG_DIM, n * FJSP_FLAG_DIM, cudaMemcpyDeviceToHost, st));
     }
     for (int i = 0; i < 2; i++) {
@@ -242,7 +260,7 @@ int fjsp_random_actions(FjspHandle* h, uint64_t seed, uint64_t t, uint8_t* actio
     DeviceGuard g(h->device);
     const int threads = 256;
     const unsigned blocks = (unsigned)((h->num_envs + threads - 1) / threads);
-    fjsp_random_actions_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(actions, h->num_envs, h->first_env, seed, t);
+    DISPATCH_K(h->cells, fjsp_random_actions_kernel<K><<<blocks, threads, 0, (cudaStream_t)stream>>>(actions, h->num_envs, h->first_env, seed, t))
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -254,14 +272,15 @@ int fjsp_rollout_random(FjspHandle* h, int steps, uint64_t seed, uint64_t t0, ui
     if (!stats || (reinterpret_cast<uintptr_t>(stats) & 7)) return fail("stats must be an 8-byte aligned device pointer (8 x u64)");
     if (seed != h->seed) return fail("rollout seed must equal the seed of the last fjsp_reset (one Philox key per handle)");
     DeviceGuard g(h->device);
-    fjsp_rollout_kernel<<<(unsigned)h->num_tiles, TILE, ROLLOUT_SMEM_BYTES, (cudaStream_t)stream>>>(
-        h->P, h->state, h->num_envs, h->first_env, seed, t0, steps, h->num_orders, reinterpret_cast<unsigned long long*>(stats));
+    DISPATCH_K(h->cells, fjsp_rollout_kernel<K><<<(unsigned)h->num_tiles, TILE, Geo<K>::ROLLOUT_SMEM_BYTES, (cudaStream_t)stream>>>(
+                             h->P, h->state, h->num_envs, h->first_env, seed, t0, steps, h->num_orders,
+                             reinterpret_cast<unsigned long long*>(stats)))
     h->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 
-size_t fjsp_state_total_bytes(const FjspHandle* h) { return h ? (size_t)h->num_tiles * TILE_BYTES : 0; }
+size_t fjsp_state_total_bytes(const FjspHandle* h) { return h ? (size_t)h->num_tiles * h->tile_bytes : 0; }
 
 int fjsp_state_save(FjspHandle* h, void* dst_device, size_t bytes, void* stream) {
     if (!h || !dst_device) return fail("NULL argument");
@@ -284,19 +303,23 @@ int fjsp_export_packed(FjspHandle* h, int64_t env, uint32_t* out_words) {
     if (env < 0 || env >= h->num_envs) return fail("env index out of range");
     DeviceGuard g(h->device);
     CK(cudaDeviceSynchronize());
-    const u32* src = h->state + (env / TILE) * TILE_WORDS + (env % TILE);
-    // word w of this env sits TILE words after word w-1: a strided gather of 128 x 4 bytes
-    CK(cudaMemcpy2D(out_words, sizeof(u32), src, TILE * sizeof(u32), sizeof(u32), FJSP_STATE_WORDS, cudaMemcpyDeviceToHost));
+    const int words = FJSP_STATE_WORDS_K(h->cells);
+    const u32* src = h->state + (env / TILE) * (int64_t)words * TILE + (env % TILE);
+    // word w of this env sits TILE words after word w-1: a strided gather of `words` x 4 bytes
+    CK(cudaMemcpy2D(out_words, sizeof(u32), src, TILE * sizeof(u32), sizeof(u32), (size_t)words, cudaMemcpyDeviceToHost));
     return 0;
 }
 
-int fjsp_export_state(FjspHandle* h, int64_t env, FjspCanonState* out) {
+int fjsp_export_state_cell(FjspHandle* h, int64_t env, int cell, FjspCanonState* out) {
     if (!out) return fail("out is NULL");
-    u32 words[FJSP_STATE_WORDS];
+    if (h && (cell < 0 || cell >= h->cells)) return fail("cell index out of range");
+    u32 words[FJSP_STATE_WORDS_K(FJSP_MAX_CELLS)];
     if (int rc = fjsp_export_packed(h, env, words)) return rc;
-    export_canon(words, h->P, out);
+    export_canon(words, h->P, h->cells, cell, out);
     return 0;
 }
+
+int fjsp_export_state(FjspHandle* h, int64_t env, FjspCanonState* out) { return fjsp_export_state_cell(h, env, 0, out); }
 
 // ---- fused ops of the batched A2C trainer (stateless; run on the current device) ----
 int fjsp_a2c_sample(const float* logits, const int8_t* masks, uint8_t* actions, float* logp, int64_t rows, int64_t first_row,

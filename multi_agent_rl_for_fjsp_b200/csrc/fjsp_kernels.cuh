@@ -1,19 +1,20 @@
-// fjsp_kernels.cuh — sm_100a kernels of the batched FJSP environment.
+// fjsp_kernels.cuh — sm_100a kernels of the batched FJSP environment (templated on K, the number of cells of the shop;
+// K = 1 is the reference shop, K = 2..4 the scaled shop of DESIGN.md §10).
 //
-// HBM layout: the packed state is an ARRAY OF TILES.  One tile = 64 envs x 128 words, stored
-// word-major  tile[w][lane]  (u32), i.e. 32 KB that are contiguous in HBM.  A CTA owns one tile per step:
-//   1. one elected thread issues ONE bulk async copy (TMA engine, cp.async.bulk, SASS UBLKCP) of the tile's 26 KB of
-//      dynamically indexed words (24..127: completion steps, orders, tray pool) into shared memory and arms an
-//      mbarrier with the byte count; all threads meanwhile fetch their 24 hot words (coalesced 32-bit loads: a warp
-//      reads 128 consecutive bytes per word) and the 8 action bytes of their env (coalesced 64-bit load);
+// HBM layout: the packed state is an ARRAY OF TILES.  One tile = 64 envs x W words (W = 128 for K = 1),
+// stored word-major  tile[w][lane]  (u32), contiguous in HBM.  A CTA owns one tile per step:
+//   1. one elected thread issues ONE bulk async copy (TMA engine, cp.async.bulk, SASS UBLKCP) of the tile's
+//      dynamically indexed words (24 .. 64+64K: completion steps, orders, tray pools; 26 KB for K = 1) into shared memory
+//      and arms an mbarrier with the byte count; all threads meanwhile fetch their hot words (coalesced 32-bit loads: a
+//      warp reads 128 consecutive bytes per word) and the action bytes of their env;
 //   2. every thread steps its own env: hot words in registers, the rest out of shared memory (thread t owns column t
-//      of the [104][64] sub-tile, so all accesses of a warp hit 32 distinct banks regardless of the word index each
-//      lane follows — the FIFO pointer chasing is conflict-free by construction);
+//      of the sub-tile, so all accesses of a warp hit 32 distinct banks regardless of the word index each lane follows —
+//      the FIFO pointer chasing is conflict-free by construction);
 //   3. observations are staged row-major in shared memory; masks / rewards / flags leave as 128-bit stores;
 //   4. hot words go back with coalesced 32-bit stores; after a proxy fence + barrier the elected thread issues two bulk
-//      async stores (the 26 KB sub-tile, the observation rows).
-// Nothing but the step's own inputs and outputs crosses HBM: 512 B state in, 512 B state out, 8 + 152 + 32 + 32 + 4
-// bytes of I/O per env-step.
+//      async stores (the sub-tile, the observation rows).
+// Nothing but the step's own inputs and outputs crosses HBM: for K = 1, 512 B state in, 512 B state out,
+// 8 + 152 + 32 + 32 + 4 bytes of I/O per env-step.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -22,20 +23,24 @@
 
 namespace fjsp {
 
-constexpr int TILE = FJSP_TILE_ENVS;                       // 64 envs per tile
-constexpr int TILE_WORDS = FJSP_STATE_WORDS * TILE;        // 8192 u32
-constexpr int TILE_BYTES = TILE_WORDS * 4;                 // 32768
-constexpr int HOT_BYTES = W_CSTEP * TILE * 4;              // 6144: words 0..23, through registers (coalesced LDG/STG)
-constexpr int DYN_WORDS = (W_TOTAL - W_CSTEP) * TILE;      // words 24..127, through shared memory (one bulk copy)
-constexpr int DYN_BYTES = DYN_WORDS * 4;                   // 26624
-constexpr int OBS_ROW_BYTES = FJSP_OBS_DIM * 4;            // 152
-constexpr int OBS_TILE_BYTES = OBS_ROW_BYTES * TILE;       // 9728
-constexpr int STEP_SMEM_BYTES = DYN_BYTES + OBS_TILE_BYTES + 16;
-constexpr int ROLLOUT_SMEM_BYTES = DYN_BYTES + 16;
+constexpr int TILE = FJSP_TILE_ENVS;  // 64 envs per tile
 
-// One env of a tile inside a kernel: the dynamically indexed words (24..127) live in shared memory, column `lane` of
-// the [104][64] sub-tile; the 24 hot words are read/written straight from/to the HBM tile with compile-time indices
-// (a warp touches 128 consecutive bytes per word: coalesced) and otherwise live in registers (struct Hot).
+template <int K>
+struct Geo {
+    static constexpr int WORDS = Lay<K>::TOTAL;                     // u32 per env (128 / 380)
+    static constexpr int TILE_WORDS = WORDS * TILE;
+    static constexpr int TILE_BYTES = TILE_WORDS * 4;               // 32768 / 97280
+    static constexpr int DYN_WORDS = (Lay<K>::DYN_END - W_CSTEP) * TILE;
+    static constexpr int DYN_BYTES = DYN_WORDS * 4;                 // 26624 / 75776: through shared memory (one bulk copy)
+    static constexpr int OBS_ROW_BYTES = Lay<K>::OBS * 4;           // 152 / 524
+    static constexpr int OBS_TILE_BYTES = OBS_ROW_BYTES * TILE;     // 9728 / 33536
+    static constexpr int STEP_SMEM_BYTES = DYN_BYTES + OBS_TILE_BYTES + 16;
+    static constexpr int ROLLOUT_SMEM_BYTES = DYN_BYTES + 16;
+};
+
+// One env of a tile inside a kernel: the dynamically indexed words live in shared memory, column `lane` of the
+// sub-tile; the hot words are read/written straight from/to the HBM tile with compile-time indices (a warp touches 128
+// consecutive bytes per word: coalesced) and otherwise live in registers (struct Hot / HotCell).
 struct TileColumn {
     u32* dyn;  // &s_dyn[0][lane] - W_CSTEP * TILE, so dyn[w * TILE] is word w
     u32* hot;  // &g_tile[0][lane]
@@ -91,6 +96,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // and store them into the ending lane's shared-memory column; the ending lane itself re-initialises its scalars.
 // A per-lane reset would make the whole warp wait for 32 sequential Philox calls whenever ANY of its envs ends.
 // Must be called by all 32 lanes of the warp.  Returns true for lanes that were reset.
+template <int K>
 __device__ __forceinline__ bool warp_autoreset(TileColumn s, u32* s_dyn, int tid, bool do_reset, u32 cur_episode,
                                                int num_orders, uint64_t seed, uint64_t genv_lane0) {
     const unsigned need = __ballot_sync(0xffffffffu, do_reset);
@@ -99,7 +105,7 @@ __device__ __forceinline__ bool warp_autoreset(TileColumn s, u32* s_dyn, int tid
     u32 episode = 0u;
     if (do_reset) {
         episode = cur_episode + 1u;
-        reset_env_base(s, num_orders, episode);  // hot words go to the HBM tile; the caller reloads its registers
+        reset_env_base<K>(s, num_orders, episode);  // hot words go to the HBM tile; the caller reloads its registers
     }
     unsigned rem = need;
     while (rem) {
@@ -115,12 +121,12 @@ __device__ __forceinline__ bool warp_autoreset(TileColumn s, u32* s_dyn, int tid
 
 struct StepArgs {
     u32* state;              // tiles
-    const uint8_t* actions;  // [N][8]
-    float* obs;              // [N][38]
-    int8_t* masks;           // [N][32]
-    float* rewards;          // [N][8]
+    const uint8_t* actions;  // [N][ACT]
+    float* obs;              // [N][OBS]
+    int8_t* masks;           // [N][MASK]
+    float* rewards;          // [N][ACT]
     uint8_t* flags;          // [N][4]
-    uint8_t* results;        // [N][8] or null
+    uint8_t* results;        // [N][ACT] or null
     int32_t* infos;          // [N][4] or null
     int64_t num_envs, first_env;
     int64_t tile_begin;      // first tile of this launch (host-buffer path steps the batch in pipelined chunks)
@@ -131,83 +137,103 @@ struct StepArgs {
 // ---------------------------------------------------------------------------------------------
 // Reset: FJSPSimulation.reset for the masked envs.  Thread per env, state addressed in place.
 // ---------------------------------------------------------------------------------------------
+template <int K>
 __global__ void __launch_bounds__(TILE) fjsp_reset_kernel(const __grid_constant__ Params P, u32* state, const uint8_t* env_mask,
                                                            const FjspOrderRec* orders, int num_orders, uint64_t seed,
                                                            int64_t num_envs, int64_t first_env, float* obs, int8_t* masks) {
     const int64_t env = (int64_t)blockIdx.x * TILE + threadIdx.x;
     const bool pad = env >= num_envs;
     if (!pad && env_mask && env_mask[env] == 0) return;
-    GmemColumn s{state + (int64_t)blockIdx.x * TILE_WORDS + threadIdx.x};
-    reset_env(s, P, pad ? 0 : num_orders, (pad || !orders) ? nullptr : orders + env * FJSP_MAX_ORDERS, seed,
-              (uint64_t)(first_env + env), 0u);
+    GmemColumn s{state + (int64_t)blockIdx.x * Geo<K>::TILE_WORDS + threadIdx.x};
+    reset_env<K>(s, P, pad ? 0 : num_orders, (pad || !orders) ? nullptr : orders + env * FJSP_MAX_ORDERS, seed,
+                 (uint64_t)(first_env + env), 0u);
     if (pad) return;
     if (obs && masks) {
-        float o[FJSP_OBS_DIM];
-        u32 mw[FJSP_MASK_DIM / 4];
-        observe_env(s, P, o, mw);
+        float o[Lay<K>::OBS];
+        u32 mw[Lay<K>::MASK / 4];
+        observe_env<K>(s, P, o, mw);
 #pragma unroll
-        for (int i = 0; i < FJSP_OBS_DIM; i++) obs[env * FJSP_OBS_DIM + i] = o[i];
-        uint4* m4 = reinterpret_cast<uint4*>(masks + env * FJSP_MASK_DIM);
-        m4[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-        m4[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+        for (int i = 0; i < Lay<K>::OBS; i++) obs[env * Lay<K>::OBS + i] = o[i];
+        uint4* m4 = reinterpret_cast<uint4*>(masks + env * Lay<K>::MASK);
+#pragma unroll
+        for (int i = 0; i < Lay<K>::MASK / 16; i++) m4[i] = make_uint4(mw[4 * i], mw[4 * i + 1], mw[4 * i + 2], mw[4 * i + 3]);
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void load_actions(const uint8_t* actions, int64_t env, bool valid, int* a) {
+    const u32* src = reinterpret_cast<const u32*>(actions + env * Lay<K>::ACT);
+#pragma unroll
+    for (int i = 0; i < Lay<K>::ACT / 4; i++) {
+        const u32 v = valid ? __ldg(src + i) : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) a[4 * i + j] = (int)((v >> (8 * j)) & 0xffu);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Step: one CTA = one tile of 64 envs; one launch = one lockstep step of all envs.
 // ---------------------------------------------------------------------------------------------
+template <int K>
 __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__ Params P, const StepArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u32* s_dyn = reinterpret_cast<u32*>(smem_raw);
-    float* s_obs = reinterpret_cast<float*>(smem_raw + DYN_BYTES);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + DYN_BYTES + OBS_TILE_BYTES);
+    float* s_obs = reinterpret_cast<float*>(smem_raw + Geo<K>::DYN_BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + Geo<K>::DYN_BYTES + Geo<K>::OBS_TILE_BYTES);
 
     const int tid = threadIdx.x;
     const int64_t tile = A.tile_begin + blockIdx.x;
     const int64_t env = tile * TILE + tid;
     const bool valid = env < A.num_envs;
-    u32* g_tile = A.state + tile * TILE_WORDS;
+    u32* g_tile = A.state + tile * Geo<K>::TILE_WORDS;
 
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
-    if (tid == 0) {  // ONE bulk async copy (TMA engine) for the 26 KB of dynamically indexed words of the tile
-        mbar_expect_tx(bar, DYN_BYTES);
-        bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, DYN_BYTES, bar);
+    if (tid == 0) {  // ONE bulk async copy (TMA engine) for the dynamically indexed words of the tile
+        mbar_expect_tx(bar, Geo<K>::DYN_BYTES);
+        bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, Geo<K>::DYN_BYTES, bar);
     }
-    // meanwhile: the 24 hot words (coalesced 32-bit loads, straight into registers) and the 8 action bytes (64-bit load)
+    // meanwhile: the hot words of the pickup station and of cell 0 (coalesced 32-bit loads, straight into registers)
+    // and the action bytes
     TileColumn s{s_dyn + tid - W_CSTEP * TILE, g_tile + tid};
     Hot h;
+    HotCell c0;
     load_hot(s, h);
-    int a[8];
-    {
-        uint2 av = make_uint2(0u, 0u);
-        if (valid) av = __ldg(reinterpret_cast<const uint2*>(A.actions) + env);
-#pragma unroll
-        for (int i = 0; i < 4; i++) a[i] = (int)((av.x >> (8 * i)) & 0xffu), a[4 + i] = (int)((av.y >> (8 * i)) & 0xffu);
-    }
+    load_cell<K>(s, 0, c0);
+    int a[Lay<K>::ACT];
+    load_actions<K>(A.actions, env, valid, a);
     mbar_wait(bar, 0);
 
     // padding lanes of a ragged last tile are inert: their words travel through unchanged
-    StepOut out;
-    out.obs = s_obs + tid * FJSP_OBS_DIM;
+    StepOut<K> out;
+    out.obs = s_obs + tid * Lay<K>::OBS;
     out.flags = 0u;
-    if (valid) step_env_hot<true>(s, P, h, a, out);
+    if (valid) step_env_hot<K, true>(s, P, h, c0, a, out);
     const bool ended = valid && A.autoreset && (out.flags & 0x00ffffffu);
-    if (warp_autoreset(s, s_dyn, tid, ended, h.episode, A.num_orders, A.seed, (uint64_t)(A.first_env + env - (tid & 31)))) {
+    if (ended && K > 1) store_cell<K>(s, 0, c0);  // (kept simple: the reset below rewrites every hot word anyway)
+    if (warp_autoreset<K>(s, s_dyn, tid, ended, h.episode, A.num_orders, A.seed, (uint64_t)(A.first_env + env - (tid & 31)))) {
         load_hot(s, h);
-        observe(s, P, h, out.obs, out.mask);  // the observation returned with an ended episode is the new episode's first
+        load_cell<K>(s, 0, c0);
+        observe<K>(s, P, h, c0, out.obs, out.mask);  // the observation returned with an ended episode is the new episode's first
         out.flags |= 1u << 24;
     }
     store_hot(s, h);
+    store_cell<K>(s, 0, c0);
     if (valid) {
-        uint4* m4 = reinterpret_cast<uint4*>(A.masks + env * FJSP_MASK_DIM);
-        m4[0] = make_uint4(out.mask[0], out.mask[1], out.mask[2], out.mask[3]);
-        m4[1] = make_uint4(out.mask[4], out.mask[5], out.mask[6], out.mask[7]);
-        float4* r4 = reinterpret_cast<float4*>(A.rewards + env * FJSP_NUM_AGENTS);
-        r4[0] = make_float4(out.reward[0], out.reward[1], out.reward[2], out.reward[3]);
-        r4[1] = make_float4(out.reward[4], out.reward[5], out.reward[6], out.reward[7]);
+        uint4* m4 = reinterpret_cast<uint4*>(A.masks + env * Lay<K>::MASK);
+#pragma unroll
+        for (int i = 0; i < Lay<K>::MASK / 16; i++)
+            m4[i] = make_uint4(out.mask[4 * i], out.mask[4 * i + 1], out.mask[4 * i + 2], out.mask[4 * i + 3]);
+        float4* r4 = reinterpret_cast<float4*>(A.rewards + env * Lay<K>::ACT);
+#pragma unroll
+        for (int i = 0; i < Lay<K>::ACT / 4; i++)
+            r4[i] = make_float4(out.reward[4 * i], out.reward[4 * i + 1], out.reward[4 * i + 2], out.reward[4 * i + 3]);
         reinterpret_cast<u32*>(A.flags)[env] = out.flags;
-        if (A.results) reinterpret_cast<uint2*>(A.results)[env] = make_uint2(out.results[0], out.results[1]);
+        if (A.results) {
+            u32* rs = reinterpret_cast<u32*>(A.results + env * Lay<K>::ACT);
+#pragma unroll
+            for (int i = 0; i < Lay<K>::ACT / 4; i++) rs[i] = out.results[i];
+        }
         if (A.infos) reinterpret_cast<int4*>(A.infos)[env] = make_int4(out.info[0], out.info[1], out.info[2], out.info[3]);
     }
     // generic-proxy writes to shared memory must be visible to the async proxy before the bulk stores
@@ -215,15 +241,15 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
     __syncthreads();
     const int64_t remaining = A.num_envs - tile * TILE;
     const int nvalid = remaining >= TILE ? TILE : (int)remaining;
-    const bool obs_bulk = ((nvalid * OBS_ROW_BYTES) & 15) == 0 && ((reinterpret_cast<uintptr_t>(A.obs) & 15) == 0);
+    const bool obs_bulk = ((nvalid * Geo<K>::OBS_ROW_BYTES) & 15) == 0 && ((reinterpret_cast<uintptr_t>(A.obs) & 15) == 0);
     if (tid == 0) {
-        bulk_s2g(g_tile + W_CSTEP * TILE, s_dyn, DYN_BYTES);
-        if (obs_bulk) bulk_s2g(A.obs + tile * TILE * FJSP_OBS_DIM, s_obs, (uint32_t)(nvalid * OBS_ROW_BYTES));
+        bulk_s2g(g_tile + W_CSTEP * TILE, s_dyn, Geo<K>::DYN_BYTES);
+        if (obs_bulk) bulk_s2g(A.obs + tile * TILE * Lay<K>::OBS, s_obs, (uint32_t)(nvalid * Geo<K>::OBS_ROW_BYTES));
         bulk_commit();
     }
     if (!obs_bulk) {  // ragged last tile or unaligned caller buffer: cooperative coalesced 32-bit stores
-        float* dst = A.obs + tile * TILE * FJSP_OBS_DIM;
-        for (int i = tid; i < nvalid * FJSP_OBS_DIM; i += TILE) dst[i] = s_obs[i];
+        float* dst = A.obs + tile * TILE * Lay<K>::OBS;
+        for (int i = tid; i < nvalid * Lay<K>::OBS; i += TILE) dst[i] = s_obs[i];
     }
     if (tid == 0) bulk_wait_read0();  // shared memory must stay allocated until the TMA engine has read it
 }
@@ -231,71 +257,81 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 // Uniform-random policy stand-in (BASELINE.json configs 1/2/4): a_i ~ U{0..n_i-1} from Philox.
 // ---------------------------------------------------------------------------------------------
+template <int K>
 __global__ void fjsp_random_actions_kernel(uint8_t* actions, int64_t num_envs, int64_t first_env, uint64_t seed, uint64_t t) {
     const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= num_envs) return;
-    int a[8];
-    philox_actions(seed, (uint64_t)(first_env + env), t, a);
-    uint2 v;
-    v.x = (u32)a[0] | ((u32)a[1] << 8) | ((u32)a[2] << 16) | ((u32)a[3] << 24);
-    v.y = (u32)a[4] | ((u32)a[5] << 8) | ((u32)a[6] << 16) | ((u32)a[7] << 24);
-    reinterpret_cast<uint2*>(actions)[env] = v;
+    int a[Lay<K>::ACT];
+#pragma unroll
+    for (int i = 0; i < Lay<K>::ACT; i++) a[i] = 0;
+    philox_actions_k<K>(seed, (uint64_t)(first_env + env), t, a);
+    u32* dst = reinterpret_cast<u32*>(actions + env * Lay<K>::ACT);
+#pragma unroll
+    for (int i = 0; i < Lay<K>::ACT / 4; i++)
+        dst[i] = (u32)a[4 * i] | ((u32)a[4 * i + 1] << 8) | ((u32)a[4 * i + 2] << 16) | ((u32)a[4 * i + 3] << 24);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Rollout: `steps` lockstep steps per launch with in-kernel Philox actions and auto-reset; the tile stays in
 // shared memory between steps, so HBM sees the state once per `steps` steps.  Accumulates exact integer stats.
 // ---------------------------------------------------------------------------------------------
+template <int K>
 __global__ void __launch_bounds__(TILE) fjsp_rollout_kernel(const __grid_constant__ Params P, u32* state, int64_t num_envs,
                                                              int64_t first_env, uint64_t seed, uint64_t t0, int steps,
                                                              int num_orders, unsigned long long* stats) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u32* s_dyn = reinterpret_cast<u32*>(smem_raw);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + DYN_BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + Geo<K>::DYN_BYTES);
     __shared__ unsigned long long s_acc[6];
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
     const int64_t env = tile * TILE + tid;
     const bool valid = env < num_envs;
-    u32* g_tile = state + tile * TILE_WORDS;
+    u32* g_tile = state + tile * Geo<K>::TILE_WORDS;
     if (tid == 0) mbar_init(bar, 1);
     if (tid < 6) s_acc[tid] = 0ull;
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(bar, DYN_BYTES);
-        bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, DYN_BYTES, bar);
+        mbar_expect_tx(bar, Geo<K>::DYN_BYTES);
+        bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, Geo<K>::DYN_BYTES, bar);
     }
     TileColumn s{s_dyn + tid - W_CSTEP * TILE, g_tile + tid};
-    Hot h;  // hot words live in registers for the whole launch
+    Hot h;  // hot words of the pickup station and of cell 0 live in registers for the whole launch
+    HotCell c0;
     load_hot(s, h);
+    load_cell<K>(s, 0, c0);
     mbar_wait(bar, 0);
     unsigned long long n_steps = 0, n_eps = 0, n_orders = 0, n_prod = 0, n_fault = 0;
-    long long r40 = 0;
+    long long units = 0;
     const uint64_t genv = (uint64_t)(first_env + env);
     for (int k = 0; k < steps; k++) {  // uniform trip count: all lanes stay together for the cooperative reset
         bool ended = false;
         if (valid) {
-            int a[8];
-            philox_actions(seed, genv, t0 + (uint64_t)k, a);
-            StepOut out;
+            int a[Lay<K>::ACT];
+            philox_actions_k<K>(seed, genv, t0 + (uint64_t)k, a);
+            StepOut<K> out;
             out.obs = nullptr;
             const int before_o = h.completed_orders, before_p = h.total_packaged;
-            step_env_hot<false>(s, P, h, a, out);
+            step_env_hot<K, false>(s, P, h, c0, a, out);
             n_steps += 1;
             n_orders += (unsigned long long)(h.completed_orders - before_o);
             n_prod += (unsigned long long)(h.total_packaged - before_p);
-            r40 += out.reward40;
+            units += out.reward_units;
             if (out.flags & 0x00ffffffu) {
                 ended = true;
                 n_eps += 1;
                 n_fault += (out.flags >> 16) & 0xffu ? 1 : 0;
             }
         }
-        if (warp_autoreset(s, s_dyn, tid, ended, h.episode, num_orders, seed, genv - (uint64_t)(tid & 31))) load_hot(s, h);
+        if (warp_autoreset<K>(s, s_dyn, tid, ended, h.episode, num_orders, seed, genv - (uint64_t)(tid & 31))) {
+            load_hot(s, h);
+            load_cell<K>(s, 0, c0);
+        }
     }
     store_hot(s, h);
+    store_cell<K>(s, 0, c0);
     // warp shuffle reduce, then one shared atomic per warp, one global atomic per CTA and counter
-    unsigned long long v[6] = {n_steps, n_eps, n_orders, n_prod, n_fault, (unsigned long long)r40};
+    unsigned long long v[6] = {n_steps, n_eps, n_orders, n_prod, n_fault, (unsigned long long)units};
 #pragma unroll
     for (int j = 0; j < 6; j++) {
         unsigned long long x = v[j];
@@ -306,7 +342,7 @@ __global__ void __launch_bounds__(TILE) fjsp_rollout_kernel(const __grid_constan
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
-        bulk_s2g(g_tile + W_CSTEP * TILE, s_dyn, DYN_BYTES);
+        bulk_s2g(g_tile + W_CSTEP * TILE, s_dyn, Geo<K>::DYN_BYTES);
         bulk_commit();
     }
     if (tid < 6) atomicAdd(&stats[tid], s_acc[tid]);

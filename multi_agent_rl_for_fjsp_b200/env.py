@@ -7,6 +7,10 @@ dicts replaced by dense tensors in the canonical agent order (FJSPSimulation.py:
     actions  uint8 [N, 8]      obs  float32 [N, 38] (a2c._flatten_obs order)      masks int8 [N, 32] (29 used)
     rewards  float32 [N, 8]    flags uint8 [N, 4] = terminated, truncated, fault, was_reset
 
+A scaled shop (``num_cells`` = K in 2..4, include/fjsp_b200.h) has 1 + 7K agents: the row widths become
+``abi.dims(K)`` (K = 4: actions/rewards 32, obs 131, masks 128) and ``agent_ids`` / ``n_actions`` / ``obs_slices`` /
+``mask_offsets`` describe the columns.
+
 PyTorch is plumbing here (device memory + the current stream); every simulation step is one launch of
 the sm_100a kernel behind ``fjsp_step`` in libfjsp_b200.so.
 """
@@ -29,6 +33,24 @@ OBS_SLICES = [(0, 7), (7, 20), (20, 23), (23, 26), (26, 29), (29, 32), (32, 35),
 MASK_OFFSETS = [0, 3, 11, 14, 17, 20, 23, 26, 29]
 
 
+_CELL_AGENTS = AGENT_IDS[1:]
+
+
+def agent_layout(cells: int = 1):
+    """(agent_ids, n_actions, obs_slices, mask_offsets) of a K-cell shop; K = 1 gives the module constants."""
+    if cells == 1:
+        return list(AGENT_IDS), tuple(N_ACTIONS), list(OBS_SLICES), list(MASK_OFFSETS)
+    ids, nact, obs_sl, mask_off = ["pickup_station"], [3], [(0, 7)], [0, 3]
+    for c in range(cells):
+        for j, name in enumerate(_CELL_AGENTS):
+            ids.append("%s_c%d" % (name, c))
+            nact.append(N_ACTIONS[1 + j])
+            lo, hi = OBS_SLICES[1 + j]
+            obs_sl.append((lo + 31 * c, hi + 31 * c))
+            mask_off.append(mask_off[-1] + N_ACTIONS[1 + j])
+    return ids, tuple(nact), obs_sl, mask_off
+
+
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -44,6 +66,12 @@ class BatchedFJSPEnv:
             raise RuntimeError("BatchedFJSPEnv runs on CUDA devices only (got %s)" % device)
         self.cfg = config if isinstance(config, abi.FjspConfig) else abi.config_from_dict(config)
         self.num_envs, self.first_env = int(num_envs), int(first_env)
+        self.cells = int(self.cfg.num_cells)
+        if not 1 <= self.cells <= abi.MAX_CELLS:
+            raise ValueError("num_cells must be in 1..%d" % abi.MAX_CELLS)
+        self.dims = abi.dims(self.cells)
+        self.agent_ids, self.n_actions, self.obs_slices, self.mask_offsets = agent_layout(self.cells)
+        self.act_dim, self.obs_dim, self.mask_dim = self.dims["act"], self.dims["obs"], self.dims["mask"]
         self.seed, self.num_orders, self.autoreset = int(seed), int(num_orders), bool(autoreset)
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         torch.cuda.init()
@@ -54,14 +82,14 @@ class BatchedFJSPEnv:
         self._h = h
         n = self.num_envs
         kw = dict(device=self.device)
-        self.obs = torch.zeros((n, OBS_DIM), dtype=torch.float32, **kw)
-        self.masks = torch.zeros((n, MASK_DIM), dtype=torch.int8, **kw)
-        self.rewards = torch.zeros((n, 8), dtype=torch.float32, **kw)
+        self.obs = torch.zeros((n, self.obs_dim), dtype=torch.float32, **kw)
+        self.masks = torch.zeros((n, self.mask_dim), dtype=torch.int8, **kw)
+        self.rewards = torch.zeros((n, self.act_dim), dtype=torch.float32, **kw)
         self.flags = torch.zeros((n, 4), dtype=torch.uint8, **kw)
-        self.results = torch.zeros((n, 8), dtype=torch.uint8, **kw) if with_infos else None
+        self.results = torch.zeros((n, self.act_dim), dtype=torch.uint8, **kw) if with_infos else None
         self.infos = torch.zeros((n, 4), dtype=torch.int32, **kw) if with_infos else None
         self._term, self._trunc = self.flags[:, 0], self.flags[:, 1]
-        self._actions = torch.zeros((n, 8), dtype=torch.uint8, **kw)
+        self._actions = torch.zeros((n, self.act_dim), dtype=torch.uint8, **kw)
         self._stats = torch.zeros(8, dtype=torch.int64, **kw)
         self._t = 0
         self._host = None
@@ -136,7 +164,7 @@ class BatchedFJSPEnv:
         a = actions
         if a.dtype != torch.uint8 or a.device != self.device or not a.is_contiguous():
             a = a.to(device=self.device, dtype=torch.uint8).contiguous()
-        assert a.shape == (self.num_envs, 8), a.shape
+        assert a.shape == (self.num_envs, self.act_dim), a.shape
         o = self._out_ptrs
         rc = self._fjsp_step(self._h, a.data_ptr(), o[0], o[1], o[2], o[3], o[4], o[5], self.autoreset,
                              torch.cuda.current_stream(self.device).cuda_stream)
@@ -150,10 +178,10 @@ class BatchedFJSPEnv:
         """Same launch, but the kernel writes straight into caller-owned tensors (e.g. slices of a rollout buffer,
         so the policy's input needs no copy).  Shapes/dtypes as the env's own output tensors; contiguous."""
         n = self.num_envs
-        assert actions.dtype == torch.uint8 and actions.is_contiguous() and actions.shape == (n, 8)
-        assert obs.dtype == torch.float32 and obs.is_contiguous() and obs.shape == (n, OBS_DIM)
-        assert masks.dtype == torch.int8 and masks.is_contiguous() and masks.shape == (n, MASK_DIM)
-        assert rewards.dtype == torch.float32 and rewards.is_contiguous() and rewards.shape == (n, 8)
+        assert actions.dtype == torch.uint8 and actions.is_contiguous() and actions.shape == (n, self.act_dim)
+        assert obs.dtype == torch.float32 and obs.is_contiguous() and obs.shape == (n, self.obs_dim)
+        assert masks.dtype == torch.int8 and masks.is_contiguous() and masks.shape == (n, self.mask_dim)
+        assert rewards.dtype == torch.float32 and rewards.is_contiguous() and rewards.shape == (n, self.act_dim)
         assert flags.dtype == torch.uint8 and flags.is_contiguous() and flags.shape == (n, 4)
         abi.check(self._L.fjsp_step(self._h, _ptr(actions), _ptr(obs), _ptr(masks), _ptr(rewards), _ptr(flags), None, None,
                                     int(self.autoreset), self._stream()))
@@ -179,10 +207,10 @@ class BatchedFJSPEnv:
         if self._host is None:
             n = self.num_envs
             self._host = dict(
-                actions=torch.zeros((n, 8), dtype=torch.uint8).pin_memory(),
-                obs=torch.zeros((n, OBS_DIM), dtype=torch.float32).pin_memory(),
-                masks=torch.zeros((n, MASK_DIM), dtype=torch.int8).pin_memory(),
-                rewards=torch.zeros((n, 8), dtype=torch.float32).pin_memory(),
+                actions=torch.zeros((n, self.act_dim), dtype=torch.uint8).pin_memory(),
+                obs=torch.zeros((n, self.obs_dim), dtype=torch.float32).pin_memory(),
+                masks=torch.zeros((n, self.mask_dim), dtype=torch.int8).pin_memory(),
+                rewards=torch.zeros((n, self.act_dim), dtype=torch.float32).pin_memory(),
                 flags=torch.zeros((n, 4), dtype=torch.uint8).pin_memory())
         return self._host
 
@@ -196,7 +224,8 @@ class BatchedFJSPEnv:
         src = hb["actions"]
         if actions is not None:
             if (isinstance(actions, torch.Tensor) and actions.device.type == "cpu" and actions.dtype == torch.uint8
-                    and actions.is_contiguous() and actions.is_pinned() and tuple(actions.shape) == (self.num_envs, 8)):
+                    and actions.is_contiguous() and actions.is_pinned()
+                    and tuple(actions.shape) == (self.num_envs, self.act_dim)):
                 src = actions
             else:
                 hb["actions"].numpy()[...] = np.asarray(actions, dtype=np.uint8)
@@ -219,13 +248,13 @@ class BatchedFJSPEnv:
         abi.check(self._L.fjsp_state_load(self._h, _ptr(buf), nbytes, self._stream()))
 
     # ------------------------------------------------------------------ diagnostics
-    def export_state(self, env: int) -> np.ndarray:
-        """Canonical integer record S of one env (synchronises)."""
+    def export_state(self, env: int, cell: int = 0) -> np.ndarray:
+        """Canonical integer record S of one env (synchronises); for a scaled shop: the shared part + the given cell."""
         s = np.zeros((), dtype=abi.CANON_DT)
-        abi.check(self._L.fjsp_export_state(self._h, int(env), C.c_void_p(s.ctypes.data)))
+        abi.check(self._L.fjsp_export_state_cell(self._h, int(env), int(cell), C.c_void_p(s.ctypes.data)))
         return s
 
     def export_packed(self, env: int) -> np.ndarray:
-        w = np.zeros(abi.STATE_WORDS, dtype=np.uint32)
+        w = np.zeros(self.dims["state_words"], dtype=np.uint32)
         abi.check(self._L.fjsp_export_packed(self._h, int(env), C.c_void_p(w.ctypes.data)))
         return w

@@ -1,0 +1,173 @@
+"""Scaled shop (K = 2..4 cells, include/fjsp_b200.h) on the CUDA path, through the C ABI, against the C restatement.
+
+The reference has no K-cell shop, so the anchors are the ones of tests/test_scaled_shop.py: K = 1 is the reference shop
+bit for bit (every other GPU test), the packed-state core == the oracle for K = 2..4 on the CPU, and here the kernels ==
+the oracle on the same seeded Philox streams (observations, masks, flags, action results, canonical state of every cell
+bit-exact; rewards within REL_TOL), the K-steps-per-launch kernel == the step kernel on the whole packed state, and the
+host-buffer path == the device path.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import canon
+from oracle.fjsp_oracle import OracleBatch, OracleEnv, default_config, dims, philox_actions, philox_orders
+from tests.test_gpu_parity import _abi_cfg
+from tests.util import REL_TOL
+
+pytestmark = pytest.mark.gpu
+
+
+def ocfg_k(k, **kw):
+    c = default_config()
+    c.num_cells = k
+    for key, v in kw.items():
+        setattr(c, key, v)
+    return c
+
+
+@pytest.mark.parametrize("k,n_envs,first_env", [(2, 200, 7), (3, 129, 0), (4, 64, 0), (4, 1000, 999)])
+def test_gpu_scaled_vs_oracle_random_batch(k, n_envs, first_env):
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+
+    seed, num_orders, steps = 0xABCDEF + k, 30, 420
+    ocfg = ocfg_k(k)
+    env = BatchedFJSPEnv(n_envs, config=_abi_cfg(ocfg), first_env=first_env, seed=seed, num_orders=num_orders, autoreset=True,
+                         with_infos=True)
+    d = dims(k)
+    assert (env.act_dim, env.obs_dim, env.mask_dim) == (d["act"], d["obs"], d["mask"])
+    assert env.state_bytes_per_env == 4 * (64 + 64 * k + 20 * (k - 1)) and len(env.agent_ids) == 1 + 7 * k
+    obs0, masks0 = env.reset()
+    obs0, masks0 = obs0.cpu().numpy(), masks0.cpu().numpy()
+    rs = np.random.RandomState(n_envs + k)
+    sample = sorted(set([0, n_envs - 1] + rs.randint(0, n_envs, size=12).tolist()))
+    oracles, episodes = {}, {}
+    for i in sample:
+        o = OracleEnv(ocfg)
+        oo, om = o.reset(philox_orders(seed, first_env + i, 0, num_orders))
+        assert np.array_equal(oo, obs0[i]) and np.array_equal(om, masks0[i])
+        oracles[i], episodes[i] = o, 0
+    for t in range(steps):
+        acts = env.random_actions(t)
+        obs, rew, term, trunc, masks = env.step(acts)
+        h_act, obs, rew, masks, flags, results = (x.cpu().numpy() for x in (acts, obs, rew, masks, env.flags, env.results))
+        for i in sample:
+            o = oracles[i]
+            assert np.array_equal(h_act[i], philox_actions(seed, first_env + i, t, cells=k)), "action stream"
+            oo, om, orw, of = o.step(h_act[i])
+            assert tuple(of[:3]) == tuple(flags[i][:3]), (i, t, of, flags[i])
+            assert np.all(np.abs(rew[i] - orw) <= REL_TOL * np.abs(orw)), (i, t, rew[i], orw)
+            assert np.array_equal(o.results, results[i]), (i, t)
+            if of[0] or of[1] or of[2]:
+                assert flags[i][3] == 1
+                episodes[i] += 1
+                oo, om = o.reset(philox_orders(seed, first_env + i, episodes[i], num_orders))
+            assert np.array_equal(oo, obs[i]), (i, t, np.flatnonzero(oo != obs[i]))
+            assert np.array_equal(om, masks[i]), (i, t, np.flatnonzero(om != masks[i]))
+        if t % 60 == 59:
+            for i in sample[:4]:
+                for c in range(k):
+                    df = canon.diff(oracles[i].export(c), env.export_state(i, c))
+                    assert not df, (i, t, c, df[:4])
+    assert max(episodes.values()) >= 2
+
+
+@pytest.mark.parametrize("k", [2, 4])
+def test_gpu_scaled_rollout_matches_stepwise_and_oracle(k):
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+
+    n, seed, num_orders, steps = 640 + 17, 31 + k, 30, 230
+    ocfg = ocfg_k(k)
+    a = BatchedFJSPEnv(n, config=_abi_cfg(ocfg), seed=seed, num_orders=num_orders, autoreset=True)
+    b = BatchedFJSPEnv(n, config=_abi_cfg(ocfg), seed=seed, num_orders=num_orders, autoreset=True)
+    a.reset(), b.reset()
+    for t in range(steps):
+        a.step(a.random_actions(t))
+    b.rollout_random(70, t0=0)
+    stats = b.rollout_random(steps - 70, t0=70).cpu().numpy()
+    assert torch.equal(a.save_state(), b.save_state())
+    ob = OracleBatch(n, seed, num_orders, cfg=ocfg)
+    ostats = ob.rollout(steps, nthreads=4)
+    assert stats[:6].tolist() == ostats[:6].astype(np.int64).tolist(), (stats, ostats)
+
+
+def test_gpu_scaled_heuristic_cells_complete_orders():
+    """A competent per-cell policy on the device tensors: trays flow through every cell, orders complete, episodes
+    terminate at different steps (partial-ballot cooperative resets) — sampled envs followed by the oracle."""
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+    from tests.test_gpu_parity import _torch_heuristic
+
+    k, n, seed, num_orders, steps = 4, 700, 2468, 6, 300
+    ocfg = ocfg_k(k)
+    env = BatchedFJSPEnv(n, config=_abi_cfg(ocfg), seed=seed, num_orders=num_orders, autoreset=True)
+    obs, masks = env.reset()
+    gen = torch.Generator(device=env.device).manual_seed(11)
+    sample = sorted(set([0, 31, 32, 63, 64, n - 1] + np.random.RandomState(2).randint(0, n, size=20).tolist()))
+    oracles, episodes = {}, {}
+    for i in sample:
+        o = OracleEnv(ocfg)
+        o.reset(philox_orders(seed, i, 0, num_orders))
+        oracles[i], episodes[i] = o, 0
+    terminated = 0
+    for t in range(steps):
+        acts = torch.zeros(n, env.act_dim, dtype=torch.uint8, device=env.device)
+        for c in range(k):  # the single-shop policy applied to each cell's view (pickup station + the cell's 7 agents)
+            o_c = torch.cat([obs[:, :7], obs[:, 7 + 31 * c:38 + 31 * c]], dim=1)
+            m_c = torch.zeros(n, 32, dtype=torch.int8, device=env.device)
+            m_c[:, :3], m_c[:, 3:29] = masks[:, :3], masks[:, 3 + 26 * c:29 + 26 * c]
+            a_c = _torch_heuristic(o_c, m_c, gen)
+            if c == 0:
+                acts[:, 0] = a_c[:, 0]
+            acts[:, 1 + 7 * c:8 + 7 * c] = a_c[:, 1:]
+        obs, rew, term, trunc, masks = env.step(acts)
+        h_act, h_obs, h_rew, h_masks, h_flags = (x.cpu().numpy() for x in (acts, obs, rew, masks, env.flags))
+        terminated += int(h_flags[:, 0].sum())
+        for i in sample:
+            o = oracles[i]
+            oo, om, orw, of = o.step(h_act[i])
+            assert tuple(of[:3]) == tuple(h_flags[i][:3]), (i, t, of, h_flags[i])
+            assert np.all(np.abs(h_rew[i] - orw) <= REL_TOL * np.abs(orw)), (i, t)
+            if of[0] or of[1] or of[2]:
+                episodes[i] += 1
+                oo, om = o.reset(philox_orders(seed, i, episodes[i], num_orders))
+            assert np.array_equal(oo, h_obs[i]) and np.array_equal(om, h_masks[i]), (i, t)
+    assert terminated > n // 2, terminated
+    for i in sample:
+        for c in range(k):
+            df = canon.diff(oracles[i].export(c), env.export_state(i, c))
+            assert not df, (i, c, df[:4])
+
+
+def test_gpu_scaled_host_buffer_step_matches_device_step():
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+
+    k, n, seed = 3, 333, 5
+    cfg = _abi_cfg(ocfg_k(k))
+    a = BatchedFJSPEnv(n, config=cfg, seed=seed)
+    b = BatchedFJSPEnv(n, config=cfg, seed=seed)
+    a.reset(), b.reset()
+    for t in range(30):
+        acts = a.random_actions(t)
+        obs, rew, term, trunc, masks = a.step(acts)
+        hobs, hmasks, hrew, hflags = b.step_host(acts.cpu().numpy())
+        assert np.array_equal(obs.cpu().numpy(), hobs) and np.array_equal(masks.cpu().numpy(), hmasks)
+        assert np.array_equal(rew.cpu().numpy(), hrew) and np.array_equal(a.flags.cpu().numpy(), hflags)
+
+
+def test_gpu_scaled_shard_map_invariance_at_size():
+    """2^17 four-cell shops (190 MB of state): env g of the full batch == env g - first of a shard created with first_env."""
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+
+    k, n, seed, steps = 4, 1 << 17, 77, 40
+    cfg = _abi_cfg(ocfg_k(k))
+    full = BatchedFJSPEnv(n, config=cfg, seed=seed)
+    full.reset()
+    stats = full.rollout_random(steps, t0=0).cpu().numpy()
+    assert stats[0] == n * steps
+    first = n // 2 + 321
+    shard = BatchedFJSPEnv(512, config=cfg, first_env=first, seed=seed)
+    shard.reset()
+    for t in range(steps):
+        shard.step(shard.random_actions(t))
+    for g in (first, first + 77, first + 511):
+        assert np.array_equal(full.export_packed(g), shard.export_packed(g - first))

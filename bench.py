@@ -12,7 +12,9 @@ value      device-timed (CUDA events on the launching stream), inputs resident i
            generated before the timed region; every step reads a fresh 8 MiB action buffer and the 512 MiB state,
            so the working set exceeds the 126 MB L2 without a flush.
 e2e        the same metric through the host-buffer C-ABI call fjsp_step_host: pinned host actions in, pinned host
-           obs/masks/rewards/flags out, H2D + D2H copies inside the timed region.
+           float32 obs / int8 masks / float32 rewards / u8 flags out, H2D + D2H copies inside the timed region.  The
+           results cross PCIe as 72-byte wire rows (include/fjsp_b200.h) and are decoded into the caller's tensors
+           by the library's host threads, pipelined with the copies; d2h_bytes_per_step counts the bytes that cross.
 roofline   algorithmic bytes per launch = envs x (8 + 152 + 32 + 32 + 4 + 2 x 512) = envs x 1252 B,
            divided by the mean launch duration, against MEASURED_PEAKS.json hbm_gbs.
 cpu_baseline / --impl reference
@@ -279,7 +281,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * E * 8 * Ke / e2e_s
-    # the e2e path's own roofline: this box's pinned D2H bandwidth on the result payload (220 B/env)
+    wire_row = 4 * env.dims["wire_words"]
+    # the e2e path's own roofline: this box's pinned D2H bandwidth on the wire rows (72 B/env)
     hb = env.host_buffers()
     for _ in range(2):
         hb["obs"].copy_(env.obs, non_blocking=True)
@@ -391,9 +394,12 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": args.ncu_traffic_bytes if E == (1 << 20) else None, "peak_source": peak_src, "kernel": "fjsp_step_kernel",
                          "algorithmic_bytes_per_launch": E * BYTES_PER_ENV_STEP},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 8, "d2h_bytes_per_step": E * (152 + 32 + 32 + 4),
-                    "steps": Ke, "api": "fjsp_step_host (pinned host buffers)", "pcie_d2h_gbs_measured": d2h_gbs, "host_cpus_bound": len(numa_cpus),
-                    "pcie_bound_frac": (E * 220 / (d2h_gbs * 1e9)) / (e2e_s / Ke)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 8, "d2h_bytes_per_step": E * wire_row,
+                    "steps": Ke, "ms_per_step": e2e_s / Ke * 1e3,
+                    "api": "fjsp_step_host (pinned host buffers; float32 obs/rewards, int8 masks, u8 flags delivered)",
+                    "wire_row_bytes": wire_row, "decoded_bytes_per_step": E * (152 + 32 + 32 + 4),
+                    "decode_threads": len(os.sched_getaffinity(0)), "pcie_d2h_gbs_measured": d2h_gbs, "host_cpus_bound": len(numa_cpus),
+                    "pcie_bound_frac": (E * wire_row / (d2h_gbs * 1e9)) / (e2e_s / Ke)},
             "gpu_launches": launches, "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

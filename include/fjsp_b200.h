@@ -52,6 +52,20 @@ extern "C" {
 #define FJSP_MASK_DIM_K(k) ((3 + 26 * (k) + 31) / 32 * 32)
 #define FJSP_STATE_WORDS_K(k) (64 + 64 * (k) + 20 * ((k) - 1))  /* 128 words for K = 1, 380 for K = 4 */
 
+/* ---- wire rows: the compact form in which a step's results cross PCIe on the host-buffer path (fjsp_step_host) and
+ * which fjsp_step_wire / fjsp_wire_decode expose.  Everything a step returns is a small integer, so one env's results
+ * are FJSP_WIRE_WORDS_K(K) u32 (72 B for K = 1, against 220 B of float32 tensors):
+ *   obs    : one byte per observation field, 4 per word: the field's integer value; a station index (LocationType
+ *            order) in BOTH AGV position fields (decoded through FjspConfig.pos); the table index L for a packaging
+ *            station's processing_progress (decoded to float32(100/L), 0 for L = 0); queue_length as the int8 it is
+ *   masks  : one bit per mask byte, 32 per word
+ *   reward : g (int32) then local_i (int16 per action column): reward_i = (g + A * local_i) / (10 * A), A = 1 + 7K —
+ *            the exact integer numerator of every reward (all RewardModel constants are multiples of 0.1)
+ *   flags  : terminated | truncated << 8 | fault << 16 | was_reset << 24
+ * fjsp_wire_decode turns rows back into exactly the tensors fjsp_step writes (bit for bit). */
+#define FJSP_WIRE_WORDS_K(k) \
+    ((((FJSP_OBS_DIM_K(k) + 3) / 4 + FJSP_MASK_DIM_K(k) / 32 + 1 + FJSP_ACT_DIM_K(k) / 2 + 1) + 1) / 2 * 2)
+
 /* fault codes (flags[2]); the reference has no equivalent — see DESIGN.md "faults" */
 #define FJSP_FAULT_NONE 0
 #define FJSP_FAULT_PKG_RESTART_WITH_WAITERS 1 /* reference raises ValueError out of env.run (SURVEY R-PKG-cap-b) */
@@ -156,9 +170,22 @@ int fjsp_step(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, 
               uint8_t* flags, uint8_t* results, int32_t* infos, int autoreset, void* stream);
 
 /* Same call with HOST buffers (pinned or pageable): H2D actions, step, D2H outputs, stream
- * synchronised on return.  This is the end-to-end path bench.py reports as `e2e`. */
+ * synchronised on return.  This is the end-to-end path bench.py reports as `e2e`.  The results cross PCIe as wire
+ * rows (see above) in pipelined chunks and are decoded into the caller's buffers by the library's host threads while
+ * later chunks are still in flight; what lands in obs/masks/rewards/flags is bit for bit what fjsp_step writes. */
 int fjsp_step_host(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, float* rewards,
                    uint8_t* flags, int autoreset, void* stream);
+
+/* fjsp_step with the results written as wire rows: wire = device u32[N][FJSP_WIRE_WORDS_K(K)] (16-byte aligned).
+ * results / infos as in fjsp_step (may be NULL).  ONE kernel launch. */
+int fjsp_step_wire(FjspHandle* h, const uint8_t* actions, uint32_t* wire, uint8_t* results, int32_t* infos, int autoreset,
+                   void* stream);
+/* HOST function (no GPU needed): decode n wire rows of a `cfg` shop into the tensors fjsp_step writes —
+ * obs float[n][OBS], masks int8[n][MASK], rewards float[n][ACT], flags u8[n][4]; any output may be NULL.
+ * `threads` <= 1 decodes on the calling thread, otherwise on that many short-lived threads. */
+int fjsp_wire_decode(const FjspConfig* cfg, const uint32_t* wire, int64_t n, float* obs, int8_t* masks, float* rewards,
+                     uint8_t* flags, int threads);
+size_t fjsp_wire_row_bytes(int num_cells);
 
 /* a_i ~ U{0..n_i-1}, n = (3,8,3,3,3,3,3,3), Philox4x32-10(key=seed, counter=(global env, t, 0, 1)). */
 int fjsp_random_actions(FjspHandle* h, uint64_t seed, uint64_t t, uint8_t* actions, void* stream);

@@ -15,7 +15,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_PKG)
 SO_PATH = os.path.join(_PKG, "lib", "libfjsp_b200.so")
-SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("fjsp_api.cu", "fjsp_kernels.cuh", "fjsp_a2c.cuh", "fjsp_core.h", "fjsp_host.h")]
+SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("fjsp_api.cu", "fjsp_wire.cpp", "fjsp_kernels.cuh", "fjsp_a2c.cuh", "fjsp_core.h", "fjsp_host.h", "fjsp_wire.h")]
 HEADER = os.path.join(_REPO, "include", "fjsp_b200.h")
 
 NUM_AGENTS, OBS_DIM, MASK_DIM, FLAG_DIM, INFO_DIM, MAX_ORDERS = 8, 38, 32, 4, 4, 32
@@ -28,7 +28,8 @@ def dims(cells: int = 1) -> dict:
     """Row widths of a K-cell shop (include/fjsp_b200.h FJSP_*_K); K = 1 is the reference shop (8 / 38 / 32 / 128)."""
     agents = 1 + 7 * cells
     return {"agents": agents, "act": (agents + 7) // 8 * 8, "obs": 7 + 31 * cells, "mask": (3 + 26 * cells + 31) // 32 * 32,
-            "mask_used": 3 + 26 * cells, "state_words": 64 + 64 * cells + 20 * (cells - 1)}
+            "mask_used": 3 + 26 * cells, "state_words": 64 + 64 * cells + 20 * (cells - 1),
+            "wire_words": ((7 + 31 * cells + 3) // 4 + (3 + 26 * cells + 31) // 32 + 1 + (agents + 7) // 8 * 4 + 1 + 1) // 2 * 2}
 
 CANON_MAXQ, CANON_PS_READY, CANON_MAXPQ = 64, 256, 256
 
@@ -71,7 +72,7 @@ EXPORTS = [
     "fjsp_last_error", "fjsp_abi_version", "fjsp_default_config", "fjsp_create", "fjsp_destroy", "fjsp_num_envs",
     "fjsp_state_bytes", "fjsp_state_ptr", "fjsp_reset", "fjsp_step", "fjsp_step_host", "fjsp_random_actions",
     "fjsp_rollout_random", "fjsp_export_state", "fjsp_export_state_cell", "fjsp_export_packed", "fjsp_launch_count",
-    "fjsp_num_cells",
+    "fjsp_num_cells", "fjsp_step_wire", "fjsp_wire_decode", "fjsp_wire_row_bytes",
     "fjsp_state_total_bytes", "fjsp_state_save", "fjsp_state_load",
     "fjsp_a2c_sample", "fjsp_a2c_counter_add", "fjsp_a2c_gae",
 ]
@@ -90,7 +91,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     stale = (not os.path.exists(SO_PATH)) or any(os.path.getmtime(p) > os.path.getmtime(SO_PATH) for p in deps)
     if force or stale:
         os.makedirs(os.path.dirname(SO_PATH), exist_ok=True)
-        cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, SOURCES[0]]
+        cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, SOURCES[0], SOURCES[1]]
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if verbose:
             print(proc.stderr)
@@ -140,6 +141,9 @@ def lib() -> C.CDLL:
     L.fjsp_export_state_cell.argtypes = [vp, i64, C.c_int, vp]
     L.fjsp_export_packed.argtypes = [vp, i64, vp]
     L.fjsp_num_cells.restype, L.fjsp_num_cells.argtypes = C.c_int, [vp]
+    L.fjsp_step_wire.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
+    L.fjsp_wire_decode.argtypes = [C.POINTER(FjspConfig), vp, i64, vp, vp, vp, vp, C.c_int]
+    L.fjsp_wire_row_bytes.restype, L.fjsp_wire_row_bytes.argtypes = C.c_size_t, [C.c_int]
     if L.fjsp_abi_version() != ABI_VERSION:
         raise RuntimeError("libfjsp_b200.so ABI version mismatch")
     _lib = L

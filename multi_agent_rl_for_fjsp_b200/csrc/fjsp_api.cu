@@ -8,9 +8,12 @@
 
 #include "fjsp_host.h"
 #include "fjsp_kernels.cuh"
+#include "fjsp_wire.h"
 #include "fjsp_a2c.cuh"
 
 using namespace fjsp;
+
+#define FJSP_HOST_MAX_CHUNKS 32
 
 struct FjspHandle {
     FjspConfig cfg;
@@ -26,12 +29,13 @@ struct FjspHandle {
     int64_t launches;
     // device staging for the host-buffer entry point (allocated on first use)
     uint8_t* d_actions;
-    float* d_obs;
-    int8_t* d_masks;
-    float* d_rewards;
-    uint8_t* d_flags;
+    u32* d_wire;             // device wire rows  [num_envs][wire_words]
+    u32* h_wire;             // pinned host copy of the same
+    int wire_words;
     cudaStream_t hs[2];      // the two streams the host-buffer path alternates its chunks on
     cudaEvent_t hev[2], hin;
+    cudaEvent_t cev[FJSP_HOST_MAX_CHUNKS];  // "chunk c has landed in h_wire"
+    DecodePool* pool;        // host threads turning wire rows into the caller's float32 / int8 tensors
 };
 
 static thread_local std::string g_err;
@@ -73,7 +77,9 @@ struct DeviceGuard {
 
 template <int K>
 static cudaError_t set_smem_attrs() {
-    cudaError_t e = cudaFuncSetAttribute(fjsp_step_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::STEP_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(fjsp_step_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::STEP_SMEM_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(fjsp_step_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::STEP_WIRE_SMEM_BYTES);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(fjsp_rollout_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::ROLLOUT_SMEM_BYTES);
     return e;
@@ -114,6 +120,7 @@ int fjsp_create(const FjspConfig* cfg, int64_t num_envs, int64_t first_env, int 
     h->cells = c.num_cells;
     h->act = FJSP_ACT_DIM_K(h->cells), h->obs = FJSP_OBS_DIM_K(h->cells), h->mask = FJSP_MASK_DIM_K(h->cells);
     h->tile_bytes = (size_t)FJSP_STATE_WORDS_K(h->cells) * TILE * sizeof(u32);
+    h->wire_words = FJSP_WIRE_WORDS_K(h->cells);
     h->num_tiles = (num_envs + TILE - 1) / TILE;
     h->seed = 0, h->num_orders = 30, h->launches = 0;
     cudaError_t e = cudaMalloc(&h->state, (size_t)h->num_tiles * h->tile_bytes);
@@ -145,11 +152,15 @@ int fjsp_destroy(FjspHandle* h) {
     if (!h) return 0;
     DeviceGuard g(h->device);
     cudaFree(h->state);
-    cudaFree(h->d_actions), cudaFree(h->d_obs), cudaFree(h->d_masks), cudaFree(h->d_rewards), cudaFree(h->d_flags);
+    delete h->pool;
+    cudaFree(h->d_actions), cudaFree(h->d_wire);
+    if (h->h_wire) cudaFreeHost(h->h_wire);
     for (int i = 0; i < 2; i++) {
         if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
         if (h->hev[i]) cudaEventDestroy(h->hev[i]);
     }
+    for (int i = 0; i < FJSP_HOST_MAX_CHUNKS; i++)
+        if (h->cev[i]) cudaEventDestroy(h->cev[i]);
     if (h->hin) cudaEventDestroy(h->hin);
     delete h;
     return 0;
@@ -187,10 +198,55 @@ int fjsp_step(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, 
     StepArgs A;
     A.state = h->state, A.actions = actions, A.obs = obs, A.masks = masks, A.rewards = rewards, A.flags = flags;
     A.results = results, A.infos = infos, A.num_envs = h->num_envs, A.first_env = h->first_env, A.seed = h->seed;
-    A.num_orders = h->num_orders, A.autoreset = autoreset, A.tile_begin = 0;
-    DISPATCH_K(h->cells, fjsp_step_kernel<K><<<(unsigned)h->num_tiles, TILE, Geo<K>::STEP_SMEM_BYTES, (cudaStream_t)stream>>>(h->P, A))
+    A.num_orders = h->num_orders, A.autoreset = autoreset, A.tile_begin = 0, A.wire = nullptr;
+    DISPATCH_K(h->cells, fjsp_step_kernel<K, false><<<(unsigned)h->num_tiles, TILE, Geo<K>::STEP_SMEM_BYTES, (cudaStream_t)stream>>>(h->P, A))
     h->launches++;
     CK(cudaGetLastError());
+    return 0;
+}
+
+static StepArgs wire_args(FjspHandle* h, const uint8_t* actions, u32* wire, uint8_t* results, int32_t* infos, int autoreset) {
+    StepArgs A;
+    A.state = h->state, A.actions = actions, A.obs = nullptr, A.masks = nullptr, A.rewards = nullptr, A.flags = nullptr;
+    A.results = results, A.infos = infos, A.wire = wire, A.num_envs = h->num_envs, A.first_env = h->first_env, A.seed = h->seed;
+    A.num_orders = h->num_orders, A.autoreset = autoreset, A.tile_begin = 0;
+    return A;
+}
+
+int fjsp_step_wire(FjspHandle* h, const uint8_t* actions, uint32_t* wire, uint8_t* results, int32_t* infos, int autoreset, void* stream) {
+    if (!h) return fail("handle is NULL");
+    if (!actions || !wire) return fail("actions/wire must be device pointers");
+    if ((reinterpret_cast<uintptr_t>(actions) & 7) || (reinterpret_cast<uintptr_t>(wire) & 15) ||
+        (results && (reinterpret_cast<uintptr_t>(results) & 7)) || (infos && (reinterpret_cast<uintptr_t>(infos) & 15)))
+        return fail("buffer alignment: actions/results 8 B, wire/infos 16 B");
+    DeviceGuard g(h->device);
+    const StepArgs A = wire_args(h, actions, wire, results, infos, autoreset);
+    DISPATCH_K(h->cells, fjsp_step_kernel<K, true><<<(unsigned)h->num_tiles, TILE, Geo<K>::STEP_WIRE_SMEM_BYTES, (cudaStream_t)stream>>>(h->P, A))
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+size_t fjsp_wire_row_bytes(int num_cells) {
+    return (num_cells >= 1 && num_cells <= FJSP_MAX_CELLS) ? (size_t)FJSP_WIRE_WORDS_K(num_cells) * 4 : 0;
+}
+
+int fjsp_wire_decode(const FjspConfig* cfg, const uint32_t* wire, int64_t n, float* obs, int8_t* masks, float* rewards, uint8_t* flags,
+                     int threads) {
+    if (!wire || n < 0) return fail("wire is NULL or n < 0");
+    FjspConfig c;
+    if (cfg) c = *cfg; else default_config(&c);
+    Params P;
+    if (const char* m = make_params(c, &P)) return fail(m);
+    if (threads > 64) threads = 64;
+    if (threads <= 1 || n < 2 * threads) {
+        wire_decode(c.num_cells, P, wire, 0, n, obs, masks, rewards, flags);
+        return 0;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++)
+        th.emplace_back([&, t] { wire_decode(c.num_cells, P, wire, n * t / threads, n * (t + 1) / threads, obs, masks, rewards, flags); });
+    for (auto& t : th) t.join();
     return 0;
 }
 
@@ -198,59 +254,76 @@ static int ensure_staging(FjspHandle* h) {
     if (h->d_actions) return 0;
     const size_t n = (size_t)h->num_envs;
     CK(cudaMalloc(&h->d_actions, n * h->act));
-    CK(cudaMalloc(&h->d_obs, n * h->obs * sizeof(float)));
-    CK(cudaMalloc(&h->d_masks, n * h->mask));
-    CK(cudaMalloc(&h->d_rewards, n * h->act * sizeof(float)));
-    CK(cudaMalloc(&h->d_flags, n * FJSP_FLAG_DIM));
+    CK(cudaMalloc(&h->d_wire, n * h->wire_words * sizeof(u32)));
+    CK(cudaMallocHost(&h->h_wire, n * h->wire_words * sizeof(u32)));
     for (int i = 0; i < 2; i++) {
         CK(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&h->hev[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < FJSP_HOST_MAX_CHUNKS; i++) CK(cudaEventCreateWithFlags(&h->cev[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->hin, cudaEventDisableTiming));
+    // decode workers: the CPUs this process may run on (bench.py binds each rank to its GPU's NUMA node), minus the caller
+    int workers = usable_cpus() - 1;
+    if (const char* e = getenv("FJSP_DECODE_THREADS")) workers = atoi(e) - 1;
+    if (workers > 31) workers = 31;
+    if (n < 4096 || workers < 0) workers = 0;  // small batches decode on the calling thread
+    h->pool = new (std::nothrow) DecodePool(workers);
+    if (!h->pool) return fail("out of host memory");
     return 0;
 }
 
-// Host-buffer step.  The batch is cut into tile-aligned chunks that alternate between two internal streams, so the
-// H2D of chunk c+1 and the kernel of chunk c+1 overlap the (PCIe-bound) D2H of chunk c; envs are independent, so
+// Host-buffer step.  The batch is cut into tile-aligned chunks that alternate between two internal streams: H2D of the
+// chunk's actions, the step kernel writing WIRE ROWS (72 B per env instead of 220 B of float tensors), D2H of the rows
+// into the handle's pinned staging.  As soon as a chunk has landed, the handle's host threads decode it into the
+// caller's obs/masks/rewards/flags while later chunks are still computing / crossing PCIe; envs are independent, so
 // chunks may run in any order.  Ordered after prior work on `stream`, and `stream` is ordered after it on return.
 int fjsp_step_host(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, float* rewards, uint8_t* flags, int autoreset,
                    void* stream) {
     if (!h) return fail("handle is NULL");
     if (!actions || !obs || !masks || !rewards || !flags) return fail("host buffers must not be NULL");
+    if (reinterpret_cast<uintptr_t>(masks) & 7) return fail("masks must be 8-byte aligned");
     DeviceGuard g(h->device);
     if (int rc = ensure_staging(h)) return rc;
     cudaStream_t user = (cudaStream_t)stream;
     CK(cudaEventRecord(h->hin, user));
     for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(h->hs[i], h->hin, 0));
     const int64_t tiles = h->num_tiles;
-    int64_t nchunks = tiles >= 64 ? 8 : (tiles >= 2 ? 2 : 1);
+    int64_t nchunks = tiles >= 2048 ? 16 : tiles >= 64 ? 8 : (tiles >= 2 ? 2 : 1);
     const int64_t per = (tiles + nchunks - 1) / nchunks;
-    StepArgs A;
-    A.state = h->state, A.actions = h->d_actions, A.obs = h->d_obs, A.masks = h->d_masks, A.rewards = h->d_rewards;
-    A.flags = h->d_flags, A.results = nullptr, A.infos = nullptr, A.num_envs = h->num_envs, A.first_env = h->first_env;
-    A.seed = h->seed, A.num_orders = h->num_orders, A.autoreset = autoreset;
+    StepArgs A = wire_args(h, h->d_actions, h->d_wire, nullptr, nullptr, autoreset);
+    const int64_t na = h->act, ww = h->wire_words;
     int c = 0;
     for (int64_t t0 = 0; t0 < tiles; t0 += per, c++) {
         cudaStream_t st = h->hs[c & 1];
         const int64_t t1 = t0 + per < tiles ? t0 + per : tiles;
         const int64_t e0 = t0 * TILE, e1 = t1 * TILE < h->num_envs ? t1 * TILE : h->num_envs;
         const size_t n = (size_t)(e1 - e0);
-        const int64_t na = h->act, no = h->obs, nm = h->mask;
         CK(cudaMemcpyAsync(h->d_actions + e0 * na, actions + e0 * na, n * na, cudaMemcpyHostToDevice, st));
         A.tile_begin = t0;
-        DISPATCH_K(h->cells, fjsp_step_kernel<K><<<(unsigned)(t1 - t0), TILE, Geo<K>::STEP_SMEM_BYTES, st>>>(h->P, A))
+        DISPATCH_K(h->cells, fjsp_step_kernel<K, true><<<(unsigned)(t1 - t0), TILE, Geo<K>::STEP_WIRE_SMEM_BYTES, st>>>(h->P, A))
         h->launches++;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(obs + e0 * no, h->d_obs + e0 * no, n * no * sizeof(float), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(masks + e0 * nm, h->d_masks + e0 * nm, n * nm, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(rewards + e0 * na, h->d_rewards + e0 * na, n * na * sizeof(float), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(flags + e0 * FJSP_FLAG_DIM, h->d_flags + e0 * FJSP_FLAG_DIM, n * FJSP_FLAG_DIM, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h->h_wire + e0 * ww, h->d_wire + e0 * ww, n * ww * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(h->cev[c], st));
     }
     for (int i = 0; i < 2; i++) {
         CK(cudaEventRecord(h->hev[i], h->hs[i]));
         CK(cudaStreamWaitEvent(user, h->hev[i], 0));
     }
-    for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(h->hs[i]));
+    const int64_t grain = h->pool->size() > 0 ? 2048 : (int64_t)1 << 40;
+    c = 0;
+    for (int64_t t0 = 0; t0 < tiles; t0 += per, c++) {
+        const int64_t t1 = t0 + per < tiles ? t0 + per : tiles;
+        const int64_t e0 = t0 * TILE, e1 = t1 * TILE < h->num_envs ? t1 * TILE : h->num_envs;
+        cudaError_t e = cudaEventSynchronize(h->cev[c]);
+        if (e != cudaSuccess) {
+            h->pool->wait();
+            return cuda_fail(e, "cudaEventSynchronize(chunk)");
+        }
+        DecodePool::Job j{h->cells, &h->P, h->h_wire, e0, e1, obs, masks, rewards, flags};
+        h->pool->submit(j, grain);
+    }
+    h->pool->wait();
     return 0;
 }
 

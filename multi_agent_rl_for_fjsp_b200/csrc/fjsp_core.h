@@ -382,11 +382,38 @@ FJSP_HD void reset_env(S& s, const Params& P, int num_orders, const FjspOrderRec
 // ---------------------------------------------------------------------------------------------
 // Observation (layout O: 7 + 31K floats) + masks (3 + 26K bytes).  SURVEY.md §8a-R9; K = 1: 38 / 29.
 // ---------------------------------------------------------------------------------------------
+// Where an observation goes.  FloatSink: the reference's float32 row (a2c._flatten_obs order).  WireSink: the compact
+// host wire format (include/fjsp_b200.h "wire rows"): one byte per field — a small integer, a station index for the
+// two AGV position fields, the table index L for a packaging progress — assembled in registers, 4 fields per u32.
+struct FloatSink {
+    float* o;
+    const Params& P;
+    FJSP_HD void set(int i, int v) { o[i] = (float)v; }
+    FJSP_HD void set_i8(int i, int v) { o[i] = (float)(int)(int8_t)v; }   // dtype=np.int8 (PackagingAgent.py:59)
+    FJSP_HD void set_loc(int i, int loc) { o[i] = (float)P.pos_row[loc], o[i + 1] = (float)P.pos_col[loc]; }
+    FJSP_HD void set_prog(int i, int L) { o[i] = P.progress_tab[L]; }
+    FJSP_HD FloatSink at(int off) const { return FloatSink{o + off, P}; }
+};
+struct WireSink {
+    u32* w;
+    int base;
+    FJSP_HD void put(int i, int v) { w[(base + i) >> 2] |= (u32)(v & 255) << (((base + i) & 3) * 8); }
+    FJSP_HD void set(int i, int v) { put(i, v); }
+    FJSP_HD void set_i8(int i, int v) { put(i, v); }
+    FJSP_HD void set_loc(int i, int loc) { put(i, loc), put(i + 1, loc); }
+    FJSP_HD void set_prog(int i, int L) { put(i, L); }
+    FJSP_HD WireSink at(int off) const { return WireSink{w, base + off}; }
+};
+enum { OBS_NONE = 0, OBS_FLOAT = 1, OBS_WIRE = 2 };
+
 template <int K>
 struct StepOut {
-    float* obs;     // 7 + 31K floats, written in place (a shared-memory staging row on the device)
+    float* obs;     // OBS_FLOAT: 7 + 31K floats, written in place (a shared-memory staging row on the device)
+    u32 wobs[(Lay<K>::OBS + 3) / 4];  // OBS_WIRE: the same fields, one byte each
     u32 mask[Lay<K>::MASK / 4];
     float reward[Lay<K>::ACT];
+    int reward_g;                     // 10A*r_i = reward_g + A*reward_local10[i]  (exact integers)
+    int reward_local10[Lay<K>::ACT];
     u32 flags;      // terminated | truncated<<8 | fault<<16 | was_reset<<24
     u32 results[Lay<K>::ACT / 4];  // u8 action_result bit-fields per agent
     int32_t info[4];
@@ -395,8 +422,8 @@ struct StepOut {
 
 FJSP_HD void mask_set(u32* mw, int idx, int v) { mw[idx >> 2] |= (u32)(v & 1) << ((idx & 3) * 8); }
 
-template <class S>
-FJSP_HD void observe_shared(S& s, const Params& P, const Hot& h, float* obs, u32* mw) {
+template <class S, class O>
+FJSP_HD void observe_shared(S& s, const Params& P, const Hot& h, O obs, u32* mw) {
     // ---- pickup station: PickupStationAgent.get_observation (:58-98) / get_action_mask (:100-142)
     int has_cur_order = h.cur_order != 63;
     int order_size = 0, remaining = 0, o_type = 0, o_colour = 0;
@@ -406,13 +433,13 @@ FJSP_HD void observe_shared(S& s, const Params& P, const Hot& h, float* obs, u32
         o_type = ord_type(ow), o_colour = ord_colour(ow);
     }
     int tcount = h.cur_tray_count;
-    obs[0] = (float)(tcount > 0 ? o_colour : 0);
-    obs[1] = (float)tcount;
-    obs[2] = (float)(tcount > 0 ? o_type : 0);
-    obs[3] = (float)(remaining > 0 ? o_colour : 0);
-    obs[4] = (float)(remaining > 0 ? o_type : 0);
-    obs[5] = (float)order_size;
-    obs[6] = (float)remaining;
+    obs.set(0, tcount > 0 ? o_colour : 0);
+    obs.set(1, tcount);
+    obs.set(2, tcount > 0 ? o_type : 0);
+    obs.set(3, remaining > 0 ? o_colour : 0);
+    obs.set(4, remaining > 0 ? o_type : 0);
+    obs.set(5, order_size);
+    obs.set(6, remaining);
     int queue_len = h.num_orders - h.next_order;
     int has_order = has_cur_order || queue_len > 0;
     int has_tray = tcount > 0 || (P.trays_total - h.alloc_count) > 0;
@@ -424,8 +451,8 @@ FJSP_HD void observe_shared(S& s, const Params& P, const Hot& h, float* obs, u32
 }
 
 // one cell: AGV (13) + small/big machine (3 + 3) + four packaging stations (12) = 31 floats; 26 mask bytes from `mo`
-template <class S>
-FJSP_HD void observe_cell(S& s, const Params& P, const Hot& h, const HotCell& hc, int c, float* obs, u32* mw, int mo) {
+template <class S, class O>
+FJSP_HD void observe_cell(S& s, const Params& P, const Hot& h, const HotCell& hc, int c, O obs, u32* mw, int mo) {
     const int pb = pool_base(c);
     // ---- AGV: AGVAgent.get_observation (:53-76) / get_action_mask (:79-178)
     int carrying = hc.carry != 0;
@@ -435,19 +462,18 @@ FJSP_HD void observe_cell(S& s, const Params& P, const Hot& h, const HotCell& hc
         c_count = rec_count(r), c_proc = rec_processed(r);
         c_type = ord_type(s.ld(W_ORDER + rec_order(r)));
     }
-    obs[0] = (float)hc.m[1].busy;
-    obs[1] = (float)hc.m[1].r.len;
-    obs[2] = (float)carrying;
-    obs[3] = (float)h.ready_count;
-    obs[4] = (float)P.pos_row[hc.agv_loc];
-    obs[5] = (float)P.pos_col[hc.agv_loc];
-    obs[6] = (float)hc.m[0].busy;
-    obs[7] = (float)hc.m[0].r.len;
-    obs[8] = (float)hc.storage.len;
-    obs[9] = (float)carrying;                 // a carried tray is never packaged (delivered trays vanish)
-    obs[10] = (float)(carrying && !c_proc);
-    obs[11] = (float)c_count;
-    obs[12] = (float)c_type;
+    obs.set(0, hc.m[1].busy);
+    obs.set(1, hc.m[1].r.len);
+    obs.set(2, carrying);
+    obs.set(3, h.ready_count);
+    obs.set_loc(4, hc.agv_loc);               // [4] = row, [5] = column of the AGV's station
+    obs.set(6, hc.m[0].busy);
+    obs.set(7, hc.m[0].r.len);
+    obs.set(8, hc.storage.len);
+    obs.set(9, carrying);                     // a carried tray is never packaged (delivered trays vanish)
+    obs.set(10, carrying && !c_proc);
+    obs.set(11, c_count);
+    obs.set(12, c_type);
     mask_set(mw, mo + 0, 1);
     if (!hc.agv_moving) {
         int loc = hc.agv_loc;
@@ -475,9 +501,9 @@ FJSP_HD void observe_cell(S& s, const Params& P, const Hot& h, const HotCell& hc
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         const Mach& m = hc.m[i];
-        obs[13 + 3 * i] = (float)m.busy;
-        obs[14 + 3 * i] = m.prog ? 1.0f : 0.0f;
-        obs[15 + 3 * i] = (float)m.q.len;
+        obs.set(13 + 3 * i, m.busy);
+        obs.set(14 + 3 * i, m.prog ? 1 : 0);
+        obs.set(15 + 3 * i, m.q.len);
         mask_set(mw, mo + 8 + 3 * i, 1);
         mask_set(mw, mo + 9 + 3 * i, m.q.len > 0 && !m.busy);
         mask_set(mw, mo + 10 + 3 * i, !m.busy && m.has_cur);
@@ -486,9 +512,9 @@ FJSP_HD void observe_cell(S& s, const Params& P, const Hot& h, const HotCell& hc
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const Pack& p = hc.p[i];
-        obs[19 + 3 * i] = (float)p.busy;
-        obs[20 + 3 * i] = P.progress_tab[p.progL];
-        obs[21 + 3 * i] = (float)(int)(int8_t)p.qcount;  // dtype=np.int8 (PackagingAgent.py:59)
+        obs.set(19 + 3 * i, p.busy);
+        obs.set_prog(20 + 3 * i, p.progL);
+        obs.set_i8(21 + 3 * i, p.qcount);
         mask_set(mw, mo + 14 + 3 * i, 1);
         mask_set(mw, mo + 15 + 3 * i, p.qcount > 0 && !p.busy && p.users < P.pack_capacity);
         mask_set(mw, mo + 16 + 3 * i, !p.busy && p.hascur);
@@ -496,17 +522,62 @@ FJSP_HD void observe_cell(S& s, const Params& P, const Hot& h, const HotCell& hc
 }
 
 // whole observation; cell 0's hot words are the caller's registers, further cells are re-read
-template <int K, class S>
-FJSP_HD void observe(S& s, const Params& P, const Hot& h, const HotCell& c0, float* obs, u32* mw) {
+template <int K, class S, class O>
+FJSP_HD void observe(S& s, const Params& P, const Hot& h, const HotCell& c0, O obs, u32* mw) {
 #pragma unroll
     for (int i = 0; i < Lay<K>::MASK / 4; i++) mw[i] = 0u;
     observe_shared(s, P, h, obs, mw);
-    observe_cell(s, P, h, c0, 0, obs + 7, mw, 3);
+    observe_cell(s, P, h, c0, 0, obs.at(7), mw, 3);
 #pragma unroll
     for (int c = 1; c < K; c++) {
         HotCell hc;
         load_cell<K>(s, c, hc);
-        observe_cell(s, P, h, hc, c, obs + 7 + 31 * c, mw, 3 + 26 * c);
+        observe_cell(s, P, h, hc, c, obs.at(7 + 31 * c), mw, 3 + 26 * c);
+    }
+}
+// ---------------------------------------------------------------------------------------------
+// Wire row (include/fjsp_b200.h FJSP_WIRE_WORDS_K): everything a step returns for one env, as small integers.
+//   [obs bytes, 4 per word][mask bits, 32 per word][reward_g i32][reward_local10 i16, 2 per word][flags u32][pad]
+// ---------------------------------------------------------------------------------------------
+template <int K>
+struct Wire {
+    static constexpr int OBSW = (Lay<K>::OBS + 3) / 4, MW = Lay<K>::MASK / 32;
+    static constexpr int OFF_MASK = OBSW, OFF_G = OBSW + MW, OFF_LOCAL = OFF_G + 1, OFF_FLAGS = OFF_LOCAL + Lay<K>::ACT / 2;
+    static constexpr int WORDS = FJSP_WIRE_WORDS_K(K);
+    static_assert(OFF_FLAGS + 1 <= WORDS && WORDS % 2 == 0, "wire row layout");
+};
+// four mask bytes (0/1 each) -> four bits
+FJSP_HD u32 mask_nibble(u32 bytes4) { return ((bytes4 & 0x01010101u) * 0x01020408u) >> 24; }
+
+template <int K>
+FJSP_HD void wire_row(const StepOut<K>& out, u32* row) {
+#pragma unroll
+    for (int i = 0; i < Wire<K>::OBSW; i++) row[i] = out.wobs[i];
+#pragma unroll
+    for (int i = 0; i < Wire<K>::MW; i++) {
+        u32 bits = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; j++) bits |= mask_nibble(out.mask[8 * i + j]) << (4 * j);
+        row[Wire<K>::OFF_MASK + i] = bits;
+    }
+    row[Wire<K>::OFF_G] = (u32)out.reward_g;
+#pragma unroll
+    for (int i = 0; i < Lay<K>::ACT / 2; i++)
+        row[Wire<K>::OFF_LOCAL + i] = ((u32)out.reward_local10[2 * i] & 0xffffu) | ((u32)out.reward_local10[2 * i + 1] << 16);
+    row[Wire<K>::OFF_FLAGS] = out.flags;
+#pragma unroll
+    for (int i = Wire<K>::OFF_FLAGS + 1; i < Wire<K>::WORDS; i++) row[i] = 0u;
+}
+
+// observation into the sink selected by MODE (OBS_FLOAT: out.obs, OBS_WIRE: out.wobs)
+template <int K, int MODE, class S>
+FJSP_HD void observe_out(S& s, const Params& P, const Hot& h, const HotCell& c0, StepOut<K>& out) {
+    if (MODE == OBS_FLOAT) {
+        observe<K>(s, P, h, c0, FloatSink{out.obs, P}, out.mask);
+    } else if (MODE == OBS_WIRE) {
+#pragma unroll
+        for (int i = 0; i < (Lay<K>::OBS + 3) / 4; i++) out.wobs[i] = 0u;
+        observe<K>(s, P, h, c0, WireSink{out.wobs, 0}, out.mask);
     }
 }
 
@@ -829,7 +900,7 @@ FJSP_HD void run_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, 
 // cells 1..K-1 are loaded and stored here, one at a time.  Agent order: pickup station, then cell by cell agv, small
 // machine, big machine, four packaging stations (FJSPSimulation.py:76-82,172-174 for K = 1).
 // ---------------------------------------------------------------------------------------------
-template <int K, bool WITH_OBS, class S>
+template <int K, int MODE, class S>
 FJSP_HD void step_env_hot(S& s, const Params& P, Hot& h, HotCell& c0, const int* a, StepOut<K>& out) {
     constexpr int A = Lay<K>::AGENTS;
     const int k = h.step;
@@ -865,8 +936,10 @@ FJSP_HD void step_env_hot(S& s, const Params& P, Hot& h, HotCell& c0, const int*
     {
         const int g = 10 * (100 * (h.completed_orders - orders_before) + 10 * (h.total_packaged - products_before)) - P.step_size;
         long long units = 0;
+        out.reward_g = g;
 #pragma unroll
         for (int i = 0; i < Lay<K>::ACT; i++) {
+            out.reward_local10[i] = local10[i];
             if (i < A) {
                 const int n = g + A * local10[i];
                 out.reward[i] = (float)n / (float)(10 * A);
@@ -886,16 +959,16 @@ FJSP_HD void step_env_hot(S& s, const Params& P, Hot& h, HotCell& c0, const int*
         out.results[i] = res[4 * i] | (res[4 * i + 1] << 8) | (res[4 * i + 2] << 16) | (res[4 * i + 3] << 24);
     h.step = k + 1;
     out.info[0] = h.step, out.info[1] = h.completed_orders, out.info[2] = h.total_packaged, out.info[3] = 0;
-    if (WITH_OBS) observe<K>(s, P, h, c0, out.obs, out.mask);
+    observe_out<K, MODE>(s, P, h, c0, out);
 }
 
-template <int K, bool WITH_OBS, class S>
+template <int K, int MODE, class S>
 FJSP_HD void step_env(S& s, const Params& P, const int* a, StepOut<K>& out) {
     Hot h;
     HotCell c0;
     load_hot(s, h);
     load_cell<K>(s, 0, c0);
-    step_env_hot<K, WITH_OBS>(s, P, h, c0, a, out);
+    step_env_hot<K, MODE>(s, P, h, c0, a, out);
     store_hot(s, h);
     store_cell<K>(s, 0, c0);
 }
@@ -907,7 +980,7 @@ FJSP_HD void observe_env(S& s, const Params& P, float* obs, u32* mw) {
     HotCell c0;
     load_hot(s, h);
     load_cell<K>(s, 0, c0);
-    observe<K>(s, P, h, c0, obs, mw);
+    observe<K>(s, P, h, c0, FloatSink{obs, P}, mw);
 }
 
 }  // namespace fjsp

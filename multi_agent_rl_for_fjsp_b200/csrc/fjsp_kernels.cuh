@@ -35,6 +35,9 @@ struct Geo {
     static constexpr int OBS_ROW_BYTES = Lay<K>::OBS * 4;           // 152 / 524
     static constexpr int OBS_TILE_BYTES = OBS_ROW_BYTES * TILE;     // 9728 / 33536
     static constexpr int STEP_SMEM_BYTES = DYN_BYTES + OBS_TILE_BYTES + 16;
+    static constexpr int WIRE_ROW_BYTES = Wire<K>::WORDS * 4;        // 72 / 224
+    static constexpr int WIRE_TILE_BYTES = WIRE_ROW_BYTES * TILE;    // 4608 / 14336
+    static constexpr int STEP_WIRE_SMEM_BYTES = DYN_BYTES + WIRE_TILE_BYTES + 16;
     static constexpr int ROLLOUT_SMEM_BYTES = DYN_BYTES + 16;
 };
 
@@ -128,6 +131,7 @@ struct StepArgs {
     uint8_t* flags;          // [N][4]
     uint8_t* results;        // [N][ACT] or null
     int32_t* infos;          // [N][4] or null
+    u32* wire;               // [N][Wire<K>::WORDS]: the WIRE instantiation writes this instead of obs/masks/rewards/flags
     int64_t num_envs, first_env;
     int64_t tile_begin;      // first tile of this launch (host-buffer path steps the batch in pipelined chunks)
     uint64_t seed;
@@ -174,12 +178,15 @@ __device__ __forceinline__ void load_actions(const uint8_t* actions, int64_t env
 // ---------------------------------------------------------------------------------------------
 // Step: one CTA = one tile of 64 envs; one launch = one lockstep step of all envs.
 // ---------------------------------------------------------------------------------------------
-template <int K>
+template <int K, bool WIRE>
 __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__ Params P, const StepArgs A) {
+    constexpr int OUT_ROW_BYTES = WIRE ? Geo<K>::WIRE_ROW_BYTES : Geo<K>::OBS_ROW_BYTES;   // staged row per env
+    constexpr int OUT_TILE_BYTES = OUT_ROW_BYTES * TILE;
+    constexpr int MODE = WIRE ? OBS_WIRE : OBS_FLOAT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u32* s_dyn = reinterpret_cast<u32*>(smem_raw);
-    float* s_obs = reinterpret_cast<float*>(smem_raw + Geo<K>::DYN_BYTES);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + Geo<K>::DYN_BYTES + Geo<K>::OBS_TILE_BYTES);
+    u32* s_out = reinterpret_cast<u32*>(smem_raw + Geo<K>::DYN_BYTES);  // float observations, or wire rows
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + Geo<K>::DYN_BYTES + OUT_TILE_BYTES);
 
     const int tid = threadIdx.x;
     const int64_t tile = A.tile_begin + blockIdx.x;
@@ -206,29 +213,37 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
 
     // padding lanes of a ragged last tile are inert: their words travel through unchanged
     StepOut<K> out;
-    out.obs = s_obs + tid * Lay<K>::OBS;
+    out.obs = reinterpret_cast<float*>(s_out) + tid * Lay<K>::OBS;
     out.flags = 0u;
-    if (valid) step_env_hot<K, true>(s, P, h, c0, a, out);
+    if (valid) step_env_hot<K, MODE>(s, P, h, c0, a, out);
     const bool ended = valid && A.autoreset && (out.flags & 0x00ffffffu);
     if (ended && K > 1) store_cell<K>(s, 0, c0);  // (kept simple: the reset below rewrites every hot word anyway)
     if (warp_autoreset<K>(s, s_dyn, tid, ended, h.episode, A.num_orders, A.seed, (uint64_t)(A.first_env + env - (tid & 31)))) {
         load_hot(s, h);
         load_cell<K>(s, 0, c0);
-        observe<K>(s, P, h, c0, out.obs, out.mask);  // the observation returned with an ended episode is the new episode's first
+        observe_out<K, MODE>(s, P, h, c0, out);  // the observation returned with an ended episode is the new episode's first
         out.flags |= 1u << 24;
     }
     store_hot(s, h);
     store_cell<K>(s, 0, c0);
     if (valid) {
-        uint4* m4 = reinterpret_cast<uint4*>(A.masks + env * Lay<K>::MASK);
+        if (WIRE) {
+            u32 row[Wire<K>::WORDS];
+            wire_row<K>(out, row);
+            uint2* dst = reinterpret_cast<uint2*>(s_out + tid * Wire<K>::WORDS);
 #pragma unroll
-        for (int i = 0; i < Lay<K>::MASK / 16; i++)
-            m4[i] = make_uint4(out.mask[4 * i], out.mask[4 * i + 1], out.mask[4 * i + 2], out.mask[4 * i + 3]);
-        float4* r4 = reinterpret_cast<float4*>(A.rewards + env * Lay<K>::ACT);
+            for (int i = 0; i < Wire<K>::WORDS / 2; i++) dst[i] = make_uint2(row[2 * i], row[2 * i + 1]);
+        } else {
+            uint4* m4 = reinterpret_cast<uint4*>(A.masks + env * Lay<K>::MASK);
 #pragma unroll
-        for (int i = 0; i < Lay<K>::ACT / 4; i++)
-            r4[i] = make_float4(out.reward[4 * i], out.reward[4 * i + 1], out.reward[4 * i + 2], out.reward[4 * i + 3]);
-        reinterpret_cast<u32*>(A.flags)[env] = out.flags;
+            for (int i = 0; i < Lay<K>::MASK / 16; i++)
+                m4[i] = make_uint4(out.mask[4 * i], out.mask[4 * i + 1], out.mask[4 * i + 2], out.mask[4 * i + 3]);
+            float4* r4 = reinterpret_cast<float4*>(A.rewards + env * Lay<K>::ACT);
+#pragma unroll
+            for (int i = 0; i < Lay<K>::ACT / 4; i++)
+                r4[i] = make_float4(out.reward[4 * i], out.reward[4 * i + 1], out.reward[4 * i + 2], out.reward[4 * i + 3]);
+            reinterpret_cast<u32*>(A.flags)[env] = out.flags;
+        }
         if (A.results) {
             u32* rs = reinterpret_cast<u32*>(A.results + env * Lay<K>::ACT);
 #pragma unroll
@@ -241,15 +256,15 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
     __syncthreads();
     const int64_t remaining = A.num_envs - tile * TILE;
     const int nvalid = remaining >= TILE ? TILE : (int)remaining;
-    const bool obs_bulk = ((nvalid * Geo<K>::OBS_ROW_BYTES) & 15) == 0 && ((reinterpret_cast<uintptr_t>(A.obs) & 15) == 0);
+    u32* g_out = WIRE ? A.wire + tile * TILE * Wire<K>::WORDS : reinterpret_cast<u32*>(A.obs + tile * TILE * Lay<K>::OBS);
+    const bool out_bulk = ((nvalid * OUT_ROW_BYTES) & 15) == 0 && ((reinterpret_cast<uintptr_t>(g_out) & 15) == 0);
     if (tid == 0) {
         bulk_s2g(g_tile + W_CSTEP * TILE, s_dyn, Geo<K>::DYN_BYTES);
-        if (obs_bulk) bulk_s2g(A.obs + tile * TILE * Lay<K>::OBS, s_obs, (uint32_t)(nvalid * Geo<K>::OBS_ROW_BYTES));
+        if (out_bulk) bulk_s2g(g_out, s_out, (uint32_t)(nvalid * OUT_ROW_BYTES));
         bulk_commit();
     }
-    if (!obs_bulk) {  // ragged last tile or unaligned caller buffer: cooperative coalesced 32-bit stores
-        float* dst = A.obs + tile * TILE * Lay<K>::OBS;
-        for (int i = tid; i < nvalid * Lay<K>::OBS; i += TILE) dst[i] = s_obs[i];
+    if (!out_bulk) {  // ragged last tile or unaligned caller buffer: cooperative coalesced 32-bit stores
+        for (int i = tid; i < nvalid * (OUT_ROW_BYTES / 4); i += TILE) g_out[i] = s_out[i];
     }
     if (tid == 0) bulk_wait_read0();  // shared memory must stay allocated until the TMA engine has read it
 }
@@ -312,7 +327,7 @@ __global__ void __launch_bounds__(TILE) fjsp_rollout_kernel(const __grid_constan
             StepOut<K> out;
             out.obs = nullptr;
             const int before_o = h.completed_orders, before_p = h.total_packaged;
-            step_env_hot<K, false>(s, P, h, c0, a, out);
+            step_env_hot<K, OBS_NONE>(s, P, h, c0, a, out);
             n_steps += 1;
             n_orders += (unsigned long long)(h.completed_orders - before_o);
             n_prod += (unsigned long long)(h.total_packaged - before_p);

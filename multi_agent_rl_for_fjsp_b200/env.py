@@ -187,6 +187,16 @@ class BatchedFJSPEnv:
                                     int(self.autoreset), self._stream()))
         self._t += 1
 
+    def step_wire(self, actions: torch.Tensor, wire: torch.Tensor):
+        """Same launch with the results written as wire rows (include/fjsp_b200.h): `wire` int32 [N, dims["wire_words"]]
+        on the env's device.  ``abi.lib().fjsp_wire_decode`` (host) turns rows into the tensors `step` returns."""
+        n = self.num_envs
+        assert actions.dtype == torch.uint8 and actions.is_contiguous() and actions.shape == (n, self.act_dim)
+        assert wire.dtype == torch.int32 and wire.is_contiguous() and wire.shape == (n, self.dims["wire_words"])
+        abi.check(self._L.fjsp_step_wire(self._h, _ptr(actions), _ptr(wire), _ptr(self.results), _ptr(self.infos),
+                                         int(self.autoreset), self._stream()))
+        self._t += 1
+
     def random_actions(self, t: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
         """a_i ~ U{0..n_i-1} from the Philox action stream at time index t (default: the env's step counter)."""
         out = self._actions if out is None else out

@@ -73,13 +73,29 @@ void hh_step(void* p, const uint8_t* actions, float* obs, int8_t* masks, float* 
         for (int i = 0; i < Lay<K>::ACT; i++) a[i] = actions[i];
         StepOut<K> out;
         out.obs = obs;
-        step_env<K, true>(s, e->P, a, out);
+        step_env<K, OBS_FLOAT>(s, e->P, a, out);
         unpack_bytes(out.mask, Lay<K>::MASK, (uint8_t*)masks);
         for (int i = 0; i < Lay<K>::ACT; i++) rewards[i] = out.reward[i];
         flags[0] = out.flags & 0xff, flags[1] = (out.flags >> 8) & 0xff, flags[2] = (out.flags >> 16) & 0xff, flags[3] = 0;
         if (results) unpack_bytes(out.results, Lay<K>::ACT, results);
         if (infos)
             for (int i = 0; i < 4; i++) infos[i] = out.info[i];
+    })
+}
+
+// the same step twice from the same state: once into float tensors, once into a wire row (state advanced once)
+void hh_step_wire(void* p, const uint8_t* actions, float* obs, int8_t* masks, float* rewards, uint8_t* flags, uint32_t* wire) {
+    HostEnv* e = (HostEnv*)p;
+    HostEnv copy = *e;
+    hh_step(p, actions, obs, masks, rewards, flags, nullptr, nullptr);
+    ArrayState s{copy.words};
+    DISPATCH_K(e, {
+        int a[Lay<K>::ACT];
+        for (int i = 0; i < Lay<K>::ACT; i++) a[i] = actions[i];
+        StepOut<K> out;
+        out.obs = nullptr;
+        step_env<K, OBS_WIRE>(s, copy.P, a, out);
+        wire_row<K>(out, wire);
     })
 }
 

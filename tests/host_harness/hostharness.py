@@ -37,6 +37,7 @@ def lib():
         L.hh_observe.argtypes = [C.c_void_p] * 3
         L.hh_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32]
         L.hh_step.argtypes = [C.c_void_p] * 8
+        L.hh_step_wire.argtypes = [C.c_void_p] * 7
         L.hh_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.hh_words.argtypes = [C.c_void_p, C.c_void_p]
         L.hh_philox_actions.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
@@ -85,6 +86,15 @@ class HostEnv:
         self._L.hh_step(self._h, a.ctypes.data, self.obs.ctypes.data, self.masks.ctypes.data, self.rewards.ctypes.data,
                         self.flags.ctypes.data, self.results.ctypes.data, self.infos.ctypes.data)
         return self.obs.copy(), self.masks.copy(), self.rewards.copy(), self.flags.copy()
+
+    def step_wire(self, actions):
+        """step() that also returns the wire row (include/fjsp_b200.h) of the same step."""
+        a = np.ascontiguousarray(actions, dtype=np.uint8)
+        words = ((7 + 31 * self.cells + 3) // 4 + len(self.masks) // 32 + 1 + len(self.rewards) // 2 + 1 + 1) // 2 * 2
+        wire = np.zeros(words, np.uint32)
+        self._L.hh_step_wire(self._h, a.ctypes.data, self.obs.ctypes.data, self.masks.ctypes.data, self.rewards.ctypes.data,
+                             self.flags.ctypes.data, wire.ctypes.data)
+        return self.obs.copy(), self.masks.copy(), self.rewards.copy(), self.flags.copy(), wire
 
     def export(self, cell=0):
         s = np.zeros((), dtype=CANON_DT)

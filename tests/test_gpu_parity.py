@@ -199,6 +199,34 @@ def test_gpu_host_buffer_step_matches_device_step():
         assert np.array_equal(rew.cpu().numpy(), hrew) and np.array_equal(a.flags.cpu().numpy(), hflags)
 
 
+def test_gpu_host_buffer_step_pipelined_chunks_and_decode_threads():
+    """Large enough for 8 pipelined chunks and the decode workers; also the wire-row device API + host decoder."""
+    import ctypes as C
+
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv, abi
+
+    n, seed = 70001, 6
+    a = BatchedFJSPEnv(n, seed=seed)
+    b = BatchedFJSPEnv(n, seed=seed)
+    c = BatchedFJSPEnv(n, seed=seed)
+    a.reset(), b.reset(), c.reset()
+    ww = a.dims["wire_words"]
+    wire = torch.zeros((n, ww), dtype=torch.int32, device=a.device)
+    for t in range(25):
+        acts = a.random_actions(t)
+        obs, rew, term, trunc, masks = a.step(acts)
+        hobs, hmasks, hrew, hflags = b.step_host(acts.cpu().numpy())
+        assert np.array_equal(obs.cpu().numpy(), hobs) and np.array_equal(masks.cpu().numpy(), hmasks)
+        assert np.array_equal(rew.cpu().numpy(), hrew) and np.array_equal(a.flags.cpu().numpy(), hflags)
+        c.step_wire(acts, wire)
+        rows = wire.cpu().numpy().view(np.uint32)
+        o2, m2, r2, f2 = (np.empty_like(x) for x in (hobs, hmasks, hrew, hflags))
+        abi.check(abi.lib().fjsp_wire_decode(C.byref(c.cfg), rows.ctypes.data, n, o2.ctypes.data, m2.ctypes.data, r2.ctypes.data,
+                                             f2.ctypes.data, 4))
+        assert np.array_equal(o2, hobs) and np.array_equal(m2, hmasks) and np.array_equal(r2, hrew) and np.array_equal(f2, hflags)
+    assert torch.equal(a.save_state(), b.save_state()) and torch.equal(a.save_state(), c.save_state())
+
+
 def test_gpu_fault_flag_on_restart_with_waiters():
     """R-PKG-cap-b: a packaging START while requests still wait (where the reference raises ValueError) sets
     the fault flag on both sides in the same step."""

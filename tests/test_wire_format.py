@@ -1,0 +1,90 @@
+"""Wire rows (include/fjsp_b200.h): the compact form in which a step's results cross PCIe on the host-buffer path.
+CPU-only: rows produced by the packed-state core (test-only host build of the device step function) are decoded by the
+product library's HOST function fjsp_wire_decode and must give bit for bit the float32 / int8 tensors of the same step —
+on the reference's own golden trajectories (so the decoded tensors are also checked against the reference) and on
+scaled shops under a policy that packages products (progress table, int8 queue lengths, negative rewards)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from multi_agent_rl_for_fjsp_b200 import abi
+from oracle import policies
+from oracle.fjsp_oracle import default_config, dims
+from tests.host_harness.hostharness import HostEnv
+from tests.util import cfg_from_dict, load_golden
+
+
+def _abi_cfg(ocfg):
+    cfg = abi.FjspConfig()
+    C.memmove(C.addressof(cfg), C.addressof(ocfg), C.sizeof(cfg))
+    return cfg
+
+
+def decode(cfg, rows, threads=1):
+    k = int(cfg.num_cells)
+    d = dims(k)
+    rows = np.ascontiguousarray(rows, dtype=np.uint32)
+    n = rows.shape[0]
+    assert rows.shape[1] * 4 == abi.lib().fjsp_wire_row_bytes(k) == 4 * abi.dims(k)["wire_words"]
+    obs = np.full((n, d["obs"]), -7, np.float32)
+    masks = np.full((n, d["mask"]), -7, np.int8)
+    rew = np.full((n, d["act"]), -7, np.float32)
+    flags = np.full((n, 4), 77, np.uint8)
+    abi.check(abi.lib().fjsp_wire_decode(C.byref(cfg), rows.ctypes.data, n, obs.ctypes.data, masks.ctypes.data, rew.ctypes.data,
+                                         flags.ctypes.data, threads))
+    return obs, masks, rew, flags
+
+
+@pytest.mark.parametrize("name", ["default_heuristic", "pack_cap3", "speed2_far_step20"])
+def test_wire_rows_decode_to_the_golden_tensors(name):
+    g, cfgd = load_golden(name)
+    ocfg = cfg_from_dict(cfgd)
+    starts = g["ep_start"].tolist() + [g["actions"].shape[0]]
+    e = HostEnv(ocfg)
+    rows, want = [], []
+    for ep in range(min(3, len(starts) - 1)):
+        no = int(g["ep_norders"][ep])
+        e.reset(g["ep_orders"][ep][:no])
+        for t in range(starts[ep], starts[ep + 1]):
+            o, m, r, f, w = e.step_wire(g["actions"][t])
+            assert np.array_equal(o, g["obs"][t]) and np.array_equal(m, g["masks"][t])
+            rows.append(w), want.append((o, m, r, f))
+    obs, masks, rew, flags = decode(_abi_cfg(ocfg), np.stack(rows), threads=3)
+    for i, (o, m, r, f) in enumerate(want):
+        assert np.array_equal(obs[i], o), (i, np.flatnonzero(obs[i] != o))
+        assert np.array_equal(masks[i], m) and np.array_equal(rew[i], r) and np.array_equal(flags[i][:3], f[:3]), i
+    assert np.abs(rew - g["rewards"][:len(want)].astype(np.float32)).max() <= 1e-6 * np.abs(g["rewards"]).max()
+
+
+@pytest.mark.parametrize("k", [1, 2, 4])
+def test_wire_rows_scaled_shop(k):
+    from tests.test_scaled_shop import cfg_k, policy_actions
+
+    ocfg = cfg_k(k)
+    e = HostEnv(ocfg)
+    rs = np.random.RandomState(k)
+    rows, want = [], []
+    for ep in range(4):
+        o, m = e.reset(policies.random_orders(rs, 30))
+        for t in range(201):
+            o, m, r, f, w = e.step_wire(policy_actions(rs, o, m, k, 2 if ep else 0))
+            rows.append(w), want.append((o, m, r, f))
+            if f[0] or f[1]:
+                break
+    obs, masks, rew, flags = decode(_abi_cfg(ocfg), np.stack(rows))
+    assert any(o[7 + 20] > 0 or o[7 + 23] > 0 or o[7 + 26] > 0 or o[7 + 29] > 0 for o, _, _, _ in want), "no packaging progress seen"
+    for i, (o, m, r, f) in enumerate(want):
+        assert np.array_equal(obs[i], o) and np.array_equal(masks[i], m) and np.array_equal(rew[i], r), i
+        assert np.array_equal(flags[i][:3], f[:3])
+
+
+def test_wire_decode_partial_outputs_and_errors():
+    cfg = abi.default_config()
+    rows = np.zeros((5, abi.dims(1)["wire_words"]), np.uint32)
+    L = abi.lib()
+    obs = np.ones((5, 38), np.float32)
+    assert L.fjsp_wire_decode(C.byref(cfg), rows.ctypes.data, 5, obs.ctypes.data, None, None, None, 1) == 0
+    assert (obs[:, :11] == 0).all()
+    assert L.fjsp_wire_decode(C.byref(cfg), None, 5, obs.ctypes.data, None, None, None, 1) != 0
+    assert L.fjsp_wire_row_bytes(0) == 0 and L.fjsp_wire_row_bytes(5) == 0 and L.fjsp_wire_row_bytes(1) == 72

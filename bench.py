@@ -238,7 +238,10 @@ def run_ours(args):
         return float(t.item())
 
     E, K, W = args.envs, args.steps, args.warmup
-    env = BatchedFJSPEnv(E, device=dev, first_env=rank * E, seed=SEED, num_orders=NUM_ORDERS, autoreset=True)
+    # the ranks of one host share its cores for the host-buffer path's decode
+    decode_threads = max(1, min(32, len(os.sched_getaffinity(0)) // world))
+    env = BatchedFJSPEnv(E, device=dev, first_env=rank * E, seed=SEED, num_orders=NUM_ORDERS, autoreset=True,
+                         decode_threads=decode_threads)
     env.reset()
     # inputs resident in HBM: one action buffer per step, generated by the Philox policy stand-in
     nbuf = min(W + K, args.max_action_buffers)
@@ -347,6 +350,38 @@ def run_ours(args):
         torch.cuda.synchronize()
         small["rollout32_full_batch_agent_steps_per_s"] = E * 8 * 32 / (e0.elapsed_time(e1) * 1e-3)
 
+    # ---- scaled shop (BASELINE configs[4]: K = 4 cells = 4 AGVs, 8 machines, 16 packaging stations, 29 agents), device-timed
+    scaled = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        from multi_agent_rl_for_fjsp_b200 import abi as _abi
+
+        cfg4 = _abi.default_config()
+        cfg4.num_cells = 4
+        n4 = 1 << 18
+        e4 = BatchedFJSPEnv(n4, config=cfg4, device=dev, seed=SEED, num_orders=32, autoreset=True)
+        e4.reset()
+        d4 = e4.dims
+        a4 = [e4.random_actions(t, out=torch.empty((n4, d4["act"]), dtype=torch.uint8, device=dev)) for t in range(16)]
+        for t in range(5):
+            e4.step(a4[t % 16])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for t in range(50):
+            e4.step(a4[t % 16])
+        e1.record()
+        torch.cuda.synchronize()
+        ms4 = e0.elapsed_time(e1) / 50
+        bytes4 = d4["act"] + 4 * d4["obs"] + d4["mask"] + 4 * d4["act"] + 4 + 2 * 4 * d4["state_words"]
+        peak4, _ = measured_peak()
+        scaled = {"workload": "configs[4] scaled shop: 4 cells (4 AGVs, 4 small + 4 big machines, 16 packaging stations, 29 agents), "
+                              "%d envs, 32 Philox orders/env, Philox uniform-random actions, autoreset" % n4,
+                  "envs": n4, "agents": d4["agents"], "ms_per_step": ms4, "agent_steps_per_s": n4 * d4["agents"] / (ms4 * 1e-3),
+                  "state_bytes_per_env": 4 * d4["state_words"], "algorithmic_bytes_per_env_step": bytes4,
+                  "achieved_gbs": n4 * bytes4 / (ms4 * 1e-3) / 1e9, "roofline_frac": n4 * bytes4 / (ms4 * 1e-3) / 1e9 / peak4,
+                  "kernel": "fjsp_step_kernel<4,false>"}
+        del e4, a4
+
     # ---- A2C frames/s (second half of BASELINE.json's metric; configs[2]): 4096 envs per GPU, rollout 32, fp32 GEMMs,
     #      CUDA-graph rollout, ONE flat NCCL all-reduce of the gradients per update when N > 1.  All ranks take part.
     a2c = None
@@ -398,7 +433,7 @@ def run_ours(args):
                     "steps": Ke, "ms_per_step": e2e_s / Ke * 1e3,
                     "api": "fjsp_step_host (pinned host buffers; float32 obs/rewards, int8 masks, u8 flags delivered)",
                     "wire_row_bytes": wire_row, "decoded_bytes_per_step": E * (152 + 32 + 32 + 4),
-                    "decode_threads": len(os.sched_getaffinity(0)), "pcie_d2h_gbs_measured": d2h_gbs, "host_cpus_bound": len(numa_cpus),
+                    "decode_threads": decode_threads, "pcie_d2h_gbs_measured": d2h_gbs, "host_cpus_bound": len(numa_cpus),
                     "pcie_bound_frac": (E * wire_row / (d2h_gbs * 1e9)) / (e2e_s / Ke)},
             "gpu_launches": launches, "clocks": clocks,
         }
@@ -406,6 +441,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline_block()
         if small:
             line["extra"] = small
+        if scaled:
+            line["scaled_shop"] = scaled
         if a2c:
             line["a2c"] = a2c
         print(json.dumps(line))

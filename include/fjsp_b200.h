@@ -176,6 +176,10 @@ int fjsp_step(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, 
 int fjsp_step_host(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, float* rewards,
                    uint8_t* flags, int autoreset, void* stream);
 
+/* Host threads fjsp_step_host may use for the decode (including the caller's); 0 = every CPU the process may run on
+ * (default).  Several handles / ranks on one host should share the cores out.  Call before the first fjsp_step_host. */
+int fjsp_set_decode_threads(FjspHandle* h, int threads);
+
 /* fjsp_step with the results written as wire rows: wire = device u32[N][FJSP_WIRE_WORDS_K(K)] (16-byte aligned).
  * results / infos as in fjsp_step (may be NULL).  ONE kernel launch. */
 int fjsp_step_wire(FjspHandle* h, const uint8_t* actions, uint32_t* wire, uint8_t* results, int32_t* infos, int autoreset,

@@ -3,6 +3,7 @@
 // every entry point that advances the simulation launches a kernel from fjsp_kernels.cuh.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <new>
 #include <string>
 
@@ -36,6 +37,7 @@ struct FjspHandle {
     cudaEvent_t hev[2], hin;
     cudaEvent_t cev[FJSP_HOST_MAX_CHUNKS];  // "chunk c has landed in h_wire"
     DecodePool* pool;        // host threads turning wire rows into the caller's float32 / int8 tensors
+    int decode_threads;      // 0 = every CPU this process may run on (fjsp_set_decode_threads)
 };
 
 static thread_local std::string g_err;
@@ -263,7 +265,7 @@ static int ensure_staging(FjspHandle* h) {
     for (int i = 0; i < FJSP_HOST_MAX_CHUNKS; i++) CK(cudaEventCreateWithFlags(&h->cev[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->hin, cudaEventDisableTiming));
     // decode workers: the CPUs this process may run on (bench.py binds each rank to its GPU's NUMA node), minus the caller
-    int workers = usable_cpus() - 1;
+    int workers = (h->decode_threads > 0 ? h->decode_threads : usable_cpus()) - 1;  // the calling thread decodes too
     if (const char* e = getenv("FJSP_DECODE_THREADS")) workers = atoi(e) - 1;
     if (workers > 31) workers = 31;
     if (n < 4096 || workers < 0) workers = 0;  // small batches decode on the calling thread
@@ -289,7 +291,14 @@ int fjsp_step_host(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* ma
     for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(h->hs[i], h->hin, 0));
     const int64_t tiles = h->num_tiles;
     int64_t nchunks = tiles >= 2048 ? 16 : tiles >= 64 ? 8 : (tiles >= 2 ? 2 : 1);
+    static const int env_chunks = getenv("FJSP_HOST_CHUNKS") ? atoi(getenv("FJSP_HOST_CHUNKS")) : 0;
+    static const int env_grain = getenv("FJSP_DECODE_GRAIN") ? atoi(getenv("FJSP_DECODE_GRAIN")) : 0;
+    static const bool timing = getenv("FJSP_HOST_TIMING") != nullptr;
+    if (env_chunks > 0 && env_chunks <= FJSP_HOST_MAX_CHUNKS && tiles >= env_chunks) nchunks = env_chunks;
     const int64_t per = (tiles + nchunks - 1) / nchunks;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_in = timing ? now() : 0.0;
+    double t_ev[FJSP_HOST_MAX_CHUNKS + 2] = {0};
     StepArgs A = wire_args(h, h->d_actions, h->d_wire, nullptr, nullptr, autoreset);
     const int64_t na = h->act, ww = h->wire_words;
     int c = 0;
@@ -310,7 +319,8 @@ int fjsp_step_host(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* ma
         CK(cudaEventRecord(h->hev[i], h->hs[i]));
         CK(cudaStreamWaitEvent(user, h->hev[i], 0));
     }
-    const int64_t grain = h->pool->size() > 0 ? 2048 : (int64_t)1 << 40;
+    const int64_t grain = h->pool->size() > 0 ? (env_grain > 0 ? env_grain : 2048) : (int64_t)1 << 40;
+    const double t_enq = timing ? now() : 0.0;
     c = 0;
     for (int64_t t0 = 0; t0 < tiles; t0 += per, c++) {
         const int64_t t1 = t0 + per < tiles ? t0 + per : tiles;
@@ -320,10 +330,24 @@ int fjsp_step_host(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* ma
             h->pool->wait();
             return cuda_fail(e, "cudaEventSynchronize(chunk)");
         }
+        if (timing) t_ev[c] = now();
         DecodePool::Job j{h->cells, &h->P, h->h_wire, e0, e1, obs, masks, rewards, flags};
         h->pool->submit(j, grain);
     }
     h->pool->wait();
+    if (timing) {
+        fprintf(stderr, "[fjsp_step_host] enqueue %.3f ms | chunk landed at", t_enq - t_in);
+        for (int i = 0; i < c; i++) fprintf(stderr, " %.2f", t_ev[i] - t_in);
+        fprintf(stderr, " | decoded at %.3f ms (%d workers, grain %lld)\n", now() - t_in, h->pool->size(), (long long)grain);
+    }
+    return 0;
+}
+
+int fjsp_set_decode_threads(FjspHandle* h, int threads) {
+    if (!h) return fail("handle is NULL");
+    if (threads < 0 || threads > 64) return fail("threads must be in 0..64 (0 = all CPUs of the process)");
+    if (h->pool) return fail("fjsp_set_decode_threads must be called before the first fjsp_step_host");
+    h->decode_threads = threads;
     return 0;
 }
 

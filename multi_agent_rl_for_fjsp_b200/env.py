@@ -57,7 +57,7 @@ def _ptr(t):
 
 class BatchedFJSPEnv:
     def __init__(self, num_envs: int, config=None, device="cuda:0", first_env: int = 0, seed: int = 0,
-                 num_orders: int = 30, autoreset: bool = True, with_infos: bool = False):
+                 num_orders: int = 30, autoreset: bool = True, with_infos: bool = False, decode_threads: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedFJSPEnv needs a CUDA device: the environment step exists only as sm_100a kernels")
         self._L = abi.lib()
@@ -80,6 +80,8 @@ class BatchedFJSPEnv:
             h = C.c_void_p()
             abi.check(self._L.fjsp_create(C.byref(self.cfg), self.num_envs, self.first_env, dev_index, C.byref(h)))
         self._h = h
+        if decode_threads:  # host threads of the step_host decode (0 = all CPUs of the process)
+            abi.check(self._L.fjsp_set_decode_threads(h, int(decode_threads)))
         n = self.num_envs
         kw = dict(device=self.device)
         self.obs = torch.zeros((n, self.obs_dim), dtype=torch.float32, **kw)

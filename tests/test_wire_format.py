@@ -21,16 +21,27 @@ def _abi_cfg(ocfg):
     return cfg
 
 
-def decode(cfg, rows, threads=1):
+def aligned(shape, dtype, fill, align=64, offset=0):
+    """Array whose data pointer is `offset` bytes past an `align`-byte boundary (32-byte alignment of all four outputs
+    selects the decoder's streaming-store path for blocks of 8 rows; anything else the plain-store path)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    raw = np.zeros(n + align + offset, np.uint8)
+    start = (-raw.ctypes.data) % align + offset
+    out = raw[start:start + n].view(dtype).reshape(shape)
+    out[...] = fill
+    return out
+
+
+def decode(cfg, rows, threads=1, offset=0):
     k = int(cfg.num_cells)
     d = dims(k)
     rows = np.ascontiguousarray(rows, dtype=np.uint32)
     n = rows.shape[0]
     assert rows.shape[1] * 4 == abi.lib().fjsp_wire_row_bytes(k) == 4 * abi.dims(k)["wire_words"]
-    obs = np.full((n, d["obs"]), -7, np.float32)
-    masks = np.full((n, d["mask"]), -7, np.int8)
-    rew = np.full((n, d["act"]), -7, np.float32)
-    flags = np.full((n, 4), 77, np.uint8)
+    obs = aligned((n, d["obs"]), np.float32, -7, offset=offset)
+    masks = aligned((n, d["mask"]), np.int8, -7, offset=offset)
+    rew = aligned((n, d["act"]), np.float32, -7, offset=offset)
+    flags = aligned((n, 4), np.uint8, 77, offset=offset)
     abi.check(abi.lib().fjsp_wire_decode(C.byref(cfg), rows.ctypes.data, n, obs.ctypes.data, masks.ctypes.data, rew.ctypes.data,
                                          flags.ctypes.data, threads))
     return obs, masks, rew, flags
@@ -72,7 +83,9 @@ def test_wire_rows_scaled_shop(k):
             rows.append(w), want.append((o, m, r, f))
             if f[0] or f[1]:
                 break
-    obs, masks, rew, flags = decode(_abi_cfg(ocfg), np.stack(rows))
+    obs, masks, rew, flags = decode(_abi_cfg(ocfg), np.stack(rows), threads=1 + k)
+    o2, m2, r2, f2 = decode(_abi_cfg(ocfg), np.stack(rows), threads=1, offset=8)   # unaligned outputs: plain stores
+    assert np.array_equal(obs, o2) and np.array_equal(masks, m2) and np.array_equal(rew, r2) and np.array_equal(flags, f2)
     assert any(o[7 + 20] > 0 or o[7 + 23] > 0 or o[7 + 26] > 0 or o[7 + 29] > 0 for o, _, _, _ in want), "no packaging progress seen"
     for i, (o, m, r, f) in enumerate(want):
         assert np.array_equal(obs[i], o) and np.array_equal(masks[i], m) and np.array_equal(rew[i], r), i

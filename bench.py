@@ -357,7 +357,7 @@ def run_ours(args):
 
         cfg4 = _abi.default_config()
         cfg4.num_cells = 4
-        n4 = 1 << 18
+        n4 = 1 << 19
         e4 = BatchedFJSPEnv(n4, config=cfg4, device=dev, seed=SEED, num_orders=32, autoreset=True)
         e4.reset()
         d4 = e4.dims
@@ -379,7 +379,7 @@ def run_ours(args):
                   "envs": n4, "agents": d4["agents"], "ms_per_step": ms4, "agent_steps_per_s": n4 * d4["agents"] / (ms4 * 1e-3),
                   "state_bytes_per_env": 4 * d4["state_words"], "algorithmic_bytes_per_env_step": bytes4,
                   "achieved_gbs": n4 * bytes4 / (ms4 * 1e-3) / 1e9, "roofline_frac": n4 * bytes4 / (ms4 * 1e-3) / 1e9 / peak4,
-                  "kernel": "fjsp_step_kernel<4,false>"}
+                  "kernel": "fjsp_step_cells_kernel<4,false> (one thread per (env, cell))"}
         del e4, a4
 
     # ---- A2C frames/s (second half of BASELINE.json's metric; configs[2]): 4096 envs per GPU, rollout 32, fp32 GEMMs,

@@ -84,7 +84,27 @@ static cudaError_t set_smem_attrs() {
         e = cudaFuncSetAttribute(fjsp_step_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::STEP_WIRE_SMEM_BYTES);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(fjsp_rollout_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::ROLLOUT_SMEM_BYTES);
+    if constexpr (K >= 2) {
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(fjsp_step_cells_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::CELLS_SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(fjsp_step_cells_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::CELLS_WIRE_SMEM_BYTES);
+    }
     return e;
+}
+
+// One lockstep step of `tiles` tiles starting at A.tile_begin.  K = 1: one thread per env.  K >= 2: one thread per
+// (env, cell) — unless FJSP_STEP_PER_ENV is set, which keeps the thread-per-env kernel for A/B measurements.
+template <int K, bool WIRE>
+static void launch_step(const FjspHandle* h, const StepArgs& A, unsigned tiles, cudaStream_t st) {
+    static const bool per_env = getenv("FJSP_STEP_PER_ENV") != nullptr;
+    if constexpr (K >= 2) {
+        if (!per_env) {
+            fjsp_step_cells_kernel<K, WIRE><<<tiles, TILE * K, WIRE ? Geo<K>::CELLS_WIRE_SMEM_BYTES : Geo<K>::CELLS_SMEM_BYTES, st>>>(h->P, A);
+            return;
+        }
+    }
+    fjsp_step_kernel<K, WIRE><<<tiles, TILE, WIRE ? Geo<K>::STEP_WIRE_SMEM_BYTES : Geo<K>::STEP_SMEM_BYTES, st>>>(h->P, A);
 }
 
 extern "C" {
@@ -201,7 +221,7 @@ int fjsp_step(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, 
     A.state = h->state, A.actions = actions, A.obs = obs, A.masks = masks, A.rewards = rewards, A.flags = flags;
     A.results = results, A.infos = infos, A.num_envs = h->num_envs, A.first_env = h->first_env, A.seed = h->seed;
     A.num_orders = h->num_orders, A.autoreset = autoreset, A.tile_begin = 0, A.wire = nullptr;
-    DISPATCH_K(h->cells, fjsp_step_kernel<K, false><<<(unsigned)h->num_tiles, TILE, Geo<K>::STEP_SMEM_BYTES, (cudaStream_t)stream>>>(h->P, A))
+    DISPATCH_K(h->cells, launch_step<K, false>(h, A, (unsigned)h->num_tiles, (cudaStream_t)stream))
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -223,7 +243,7 @@ int fjsp_step_wire(FjspHandle* h, const uint8_t* actions, uint32_t* wire, uint8_
         return fail("buffer alignment: actions/results 8 B, wire/infos 16 B");
     DeviceGuard g(h->device);
     const StepArgs A = wire_args(h, actions, wire, results, infos, autoreset);
-    DISPATCH_K(h->cells, fjsp_step_kernel<K, true><<<(unsigned)h->num_tiles, TILE, Geo<K>::STEP_WIRE_SMEM_BYTES, (cudaStream_t)stream>>>(h->P, A))
+    DISPATCH_K(h->cells, launch_step<K, true>(h, A, (unsigned)h->num_tiles, (cudaStream_t)stream))
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -309,7 +329,7 @@ int fjsp_step_host(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* ma
         const size_t n = (size_t)(e1 - e0);
         CK(cudaMemcpyAsync(h->d_actions + e0 * na, actions + e0 * na, n * na, cudaMemcpyHostToDevice, st));
         A.tile_begin = t0;
-        DISPATCH_K(h->cells, fjsp_step_kernel<K, true><<<(unsigned)(t1 - t0), TILE, Geo<K>::STEP_WIRE_SMEM_BYTES, st>>>(h->P, A))
+        DISPATCH_K(h->cells, launch_step<K, true>(h, A, (unsigned)(t1 - t0), st))
         h->launches++;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(h->h_wire + e0 * ww, h->d_wire + e0 * ww, n * ww * sizeof(u32), cudaMemcpyDeviceToHost, st));

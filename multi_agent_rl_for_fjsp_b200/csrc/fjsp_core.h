@@ -623,7 +623,8 @@ FJSP_HD void pack_grant(S& s, int pb, Hot& h, HotCell& hc, Pack& p, int g, int s
 // Action phase
 // ---------------------------------------------------------------------------------------------
 // R1 pickup station (PickupStationAgent.py:146-232)
-template <class S>
+// STORE = false: a lane that only mirrors the pickup station's registers (cell-parallel step): same arithmetic, no writes
+template <bool STORE = true, class S>
 FJSP_HD void act_pickup(S& s, const Params& P, Hot& h, int a0, int& local10, u32& res) {
     int loaded = 0, tray_done = 0, idle_orders = 0, success = 0;
     if (a0 == 0) {
@@ -648,15 +649,17 @@ FJSP_HD void act_pickup(S& s, const Params& P, Hot& h, int a0, int& local10, u32
                 h.cur_tray_count = 0, h.ready_count++;
                 tray_done = 1;
             } else if (h.cur_tray_count >= FJSP_TRAY_CAPACITY) {  // tray full (:211-216)
-                s.st(W_ORDER + h.cur_order, ow | (1u << (8 + h.prod_idx - 1)));  // cut after the last loaded product
+                if (STORE) s.st(W_ORDER + h.cur_order, ow | (1u << (8 + h.prod_idx - 1)));  // cut after the last loaded product
                 h.cur_tray_count = 0, h.ready_count++;
                 tray_done = 1;
             }
         }
     } else if (a0 == 2) {
         if (h.cur_tray_count > 0) {                 // SIGNAL (:226-230): the order is not exhausted here
-            u32 ow = s.ld(W_ORDER + h.cur_order);
-            s.st(W_ORDER + h.cur_order, ow | (1u << (8 + h.prod_idx - 1)));
+            if (STORE) {
+                u32 ow = s.ld(W_ORDER + h.cur_order);
+                s.st(W_ORDER + h.cur_order, ow | (1u << (8 + h.prod_idx - 1)));
+            }
             h.cur_tray_count = 0, h.ready_count++;
             success = 1;
         }
@@ -870,15 +873,17 @@ FJSP_HD void run_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, 
             fifo_pop(s, pb, p.f);
             pool_free(hc, slot);
             const int o = rec_order(r), cnt = rec_count(r);
-            u32 ow = s.ld(W_ORDER + o);
-            ow |= (((1u << cnt) - 1u) << rec_first(r)) << 16;   // is_packaged (:143)
-            s.st(W_ORDER + o, ow);
+            // or_word: a plain read-modify-write when one thread owns the env, an atomic OR when the cells of an env run
+            // on different threads (two cells may package products of the same order in the same step)
+            const u32 bits = (((1u << cnt) - 1u) << rec_first(r)) << 16;   // is_packaged (:143)
+            const u32 before = s.or_word(W_ORDER + o, bits);
+            const u32 ow = before | bits;
             p.completed += cnt, h.total_packaged += cnt, p.users -= cnt, released += cnt;
             p.busy = 0;
-            if (ord_packaged(ow) == (1u << ord_n(ow)) - 1u) {    // _check_order_completions (FJSPSimulation.py:245-258)
+            const u32 full = (1u << ord_n(ow)) - 1u;
+            if (ord_packaged(ow) == full && ord_packaged(before) != full) {  // _check_order_completions (FJSPSimulation.py:245-258)
                 h.completed_orders++;
-                u32 cw = s.ld(W_CSTEP + (o >> 2));
-                s.st(W_CSTEP + (o >> 2), cw | ((u32)((k + 1) & 255) << ((o & 3) * 8)));
+                s.or_word(W_CSTEP + (o >> 2), (u32)((k + 1) & 255) << ((o & 3) * 8));
             }
         }
         const int stamp = (k + P.pack_steps) & 255;
@@ -972,6 +977,144 @@ FJSP_HD void step_env(S& s, const Params& P, const int* a, StepOut<K>& out) {
     store_hot(s, h);
     store_cell<K>(s, 0, c0);
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Cell-parallel step (K >= 2): ONE THREAD PER (env, cell).  Same results as step_env_hot; the cells of an env meet at
+// three points only, through a small per-env exchange area X (a shared-memory column on the device):
+//   1. the pickup station acts first (every lane mirrors its registers, the lane of cell 0 writes the order words) and
+//      every AGV posts whether it asks for the single dock                                                  -> barrier
+//   2. each lane resolves the dock in agent order from the posted requests (an earlier AGV's grant blocks a later one),
+//      runs its cell's seven agents and its run phase; order words are updated with atomic ORs; it posts the ready-tray
+//      cursor if its AGV took a tray at the pickup station (only the dock holder can), its packaged / completed
+//      counts, its dock occupancy and a fault code                                                          -> barrier
+//   3. every lane rebuilds the same shared scalars from X, computes its agents' rewards and observation, posts the
+//      reward numerators and mask bits                                                                      -> barrier
+//   4. output rows are assembled in 32-byte pieces, one per lane.
+// X slots: X_RDF = dock requests (bits 0..3) | dock occupancy after the step (4..7) | fault code of cell c (8+2c..9+2c);
+// X_READY = ready cursor posted by the picking lane (bit 31 = valid); X_DELTA = completed orders << 16 | packaged
+// products; X_MASK.. = 3 mask bits of the pickup station, then 26 per cell; then one u16 per action column:
+// local reward (9-bit signed, tenths) | action_result << 9.
+// ---------------------------------------------------------------------------------------------
+enum { X_RDF = 0, X_READY = 1, X_DELTA = 2, X_MASK = 3 };
+template <int K>
+struct Xl {
+    static constexpr int LOCAL = X_MASK + 1 + K;  // first word of the u16 table
+    static constexpr int WORDS = LOCAL + Lay<K>::ACT / 2;
+};
+
+struct CellLane {
+    Hot h;
+    HotCell hc;
+    int c, k, fault_in, orders_in, packaged_in;
+    int local10[8];  // [0] pickup station (meaningful on the lane of cell 0), [1..7] the cell's agents
+    u32 res[8];
+    int g;           // after cells_finish: 10 * (100 * orders + 10 * products) - step_size
+    u32 flags;
+};
+
+template <int K, class S, class X>
+FJSP_HD void cells_begin(S& s, X& x, const Params& P, CellLane& L, int a0, const int* a7) {
+    L.k = L.h.step, L.fault_in = L.h.fault;
+    if (L.c == 0) act_pickup<true>(s, P, L.h, a0, L.local10[0], L.res[0]);
+    else act_pickup<false>(s, P, L.h, a0, L.local10[0], L.res[0]);
+    const int wants_dock = !L.hc.agv_moving && a7[0] == 1 && P.dist[L.hc.agv_loc][LOC_PICKUP] != 0;
+    if (wants_dock) x.atom_or(X_RDF, 1u << L.c);
+}
+
+template <int K, class S, class X>
+FJSP_HD void cells_act_run(S& s, X& x, const Params& P, CellLane& L, const int* a7) {
+    // the dock as this cell's AGV sees it: holders before the step + grants to earlier cells of this step
+    const u32 reqs = x.ld(X_RDF) & 15u;
+    int m = L.h.dock_mask;
+#pragma unroll
+    for (int j = 0; j < K - 1; j++)
+        if (j < L.c && ((reqs >> j) & 1u) && (m & ~(1 << j)) == 0) m |= 1 << j;
+    L.h.dock_mask = m;
+    const int rc = L.h.ready_count, ro = L.h.ready_order, ri = L.h.ready_idx;
+    L.orders_in = L.h.completed_orders, L.packaged_in = L.h.total_packaged;
+    L.h.completed_orders = 0, L.h.total_packaged = 0, L.h.fault = -1;
+    int pk_start[4];
+    act_cell(s, P, L.h, L.hc, L.c, L.k, a7, L.local10 + 1, L.res + 1, pk_start);
+    if (L.h.ready_count != rc || L.h.ready_order != ro || L.h.ready_idx != ri)
+        x.st(X_READY, (u32)L.h.ready_count | ((u32)L.h.ready_order << 8) | ((u32)L.h.ready_idx << 16) | (1u << 31));
+    int dock_after = 0;
+    run_cell(s, P, L.h, L.hc, L.c, L.k, pk_start, dock_after);
+    u32 post = (u32)dock_after << 4;
+    if (L.h.fault != -1) post |= (u32)(L.h.fault & 3) << (8 + 2 * L.c);
+    if (post) x.atom_or(X_RDF, post);
+    const u32 delta = ((u32)L.h.completed_orders << 16) | (u32)L.h.total_packaged;
+    if (delta) x.atom_add(X_DELTA, delta);
+}
+
+template <int K, class X>
+FJSP_HD void cells_finish(X& x, const Params& P, CellLane& L, int32_t* info) {
+    constexpr int A = Lay<K>::AGENTS;
+    const u32 rdf = x.ld(X_RDF), ready = x.ld(X_READY), delta = x.ld(X_DELTA);
+    Hot& h = L.h;
+    if (ready >> 31) h.ready_count = (int)(ready & 255u), h.ready_order = (int)((ready >> 8) & 63u), h.ready_idx = (int)((ready >> 16) & 15u);
+    const int d_orders = (int)(delta >> 16), d_products = (int)(delta & 0xffffu);
+    h.completed_orders = L.orders_in + d_orders, h.total_packaged = L.packaged_in + d_products;
+    h.dock_mask = (int)((rdf >> 4) & 15u);
+    h.fault = L.fault_in;
+#pragma unroll
+    for (int j = 0; j < K; j++) {  // the last cell that raised a fault wins, as in agent order
+        const int f = (int)((rdf >> (8 + 2 * j)) & 3u);
+        if (f) h.fault = f;
+    }
+    L.g = 10 * (100 * d_orders + 10 * d_products) - P.step_size;
+    const int all_done = h.completed_orders == h.num_orders && h.num_orders > 0 && h.next_order == h.num_orders;
+    const int truncated = L.k >= P.max_episode_steps;
+    L.flags = (u32)all_done | ((u32)truncated << 8) | ((u32)h.fault << 16);
+    h.step = L.k + 1;
+    info[0] = h.step, info[1] = h.completed_orders, info[2] = h.total_packaged, info[3] = 0;
+    // post this lane's columns: local reward (tenths, 9-bit signed) | action_result << 9
+    if (L.c == 0) x.st16(2 * Xl<K>::LOCAL, ((u32)L.local10[0] & 0x1ffu) | (L.res[0] << 9));
+#pragma unroll
+    for (int i = 1; i < 8; i++) x.st16(2 * Xl<K>::LOCAL + 7 * L.c + i, ((u32)L.local10[i] & 0x1ffu) | (L.res[i] << 9));
+    if (L.c == K - 1) {
+#pragma unroll
+        for (int i = A; i < Lay<K>::ACT; i++) x.st16(2 * Xl<K>::LOCAL + i, 0u);
+    }
+}
+
+// this lane's part of the observation: its cell (31 fields into `obs_cell`), plus the pickup station on the lane of
+// cell 0 (`obs_shared`); the mask bits are posted to X.
+template <int K, class S, class X, class O>
+FJSP_HD void cells_observe(S& s, X& x, const Params& P, const CellLane& L, O obs_shared, O obs_cell) {
+    u32 mw[8];
+    if (L.c == 0) {
+        mw[0] = 0u;
+        observe_shared(s, P, L.h, obs_shared, mw);
+        x.st(X_MASK, mask_nibble(mw[0]));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) mw[i] = 0u;
+    observe_cell(s, P, L.h, L.hc, L.c, obs_cell, mw, 0);
+    u32 bits = 0u;
+#pragma unroll
+    for (int i = 0; i < 7; i++) bits |= mask_nibble(mw[i]) << (4 * i);
+    x.st(X_MASK + 1 + L.c, bits & 0x3ffffffu);
+}
+
+// mask bits [32 * word, 32 * word + 32) of the env's mask row, from the posted pieces
+template <int K, class X>
+FJSP_HD u32 cells_mask_word(X& x, int word) {
+    uint64_t acc = (word == 0) ? (uint64_t)(x.ld(X_MASK) & 7u) : 0ull;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        const int rel = 3 + 26 * j - 32 * word;  // cell j's 26 bits land at [rel, rel + 26) of this word
+        if (rel > -26 && rel < 32) {
+            const uint64_t b = (uint64_t)x.ld(X_MASK + 1 + j);
+            acc |= rel >= 0 ? (b << rel) : (b >> (-rel));
+        }
+    }
+    return (u32)acc;
+}
+FJSP_HD int x_local10(u32 v16) { return (int)((v16 & 0x1ffu) ^ 0x100u) - 0x100; }  // 9-bit sign extension
+FJSP_HD u32 x_result(u32 v16) { return (v16 >> 9) & 0x7fu; }
+// four bits -> four mask bytes (inverse of mask_nibble)
+FJSP_HD u32 nibble_bytes(u32 n) { return ((n & 15u) * 0x00204081u) & 0x01010101u; }
 
 // observation of the current state without stepping (reset path)
 template <int K, class S>

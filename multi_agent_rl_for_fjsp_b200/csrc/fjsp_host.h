@@ -79,6 +79,21 @@ struct ArrayState {
     FJSP_HD void st(int i, u32 v) { w[i] = v; }
     FJSP_HD u32 ld_hot(int i) const { return w[i]; }
     FJSP_HD void st_hot(int i, u32 v) { w[i] = v; }
+    FJSP_HD u32 or_word(int i, u32 v) {
+        const u32 old = w[i];
+        w[i] = old | v;
+        return old;
+    }
+};
+// exchange area of the cell-parallel step, host emulation (lanes run one after the other)
+struct ArrayXchg {
+    u32* w;
+    FJSP_HD u32 ld(int i) const { return w[i]; }
+    FJSP_HD void st(int i, u32 v) { w[i] = v; }
+    FJSP_HD void atom_or(int i, u32 v) { w[i] |= v; }
+    FJSP_HD void atom_add(int i, u32 v) { w[i] += v; }
+    FJSP_HD void st16(int i16, u32 v) { reinterpret_cast<uint16_t*>(w)[i16] = (uint16_t)v; }
+    FJSP_HD u32 ld16(int i16) const { return reinterpret_cast<const uint16_t*>(w)[i16]; }
 };
 
 // ---- canonical record S from packed words: shared pickup station / orders + the given cell ----

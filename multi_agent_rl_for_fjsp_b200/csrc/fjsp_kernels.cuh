@@ -39,6 +39,11 @@ struct Geo {
     static constexpr int WIRE_TILE_BYTES = WIRE_ROW_BYTES * TILE;    // 4608 / 14336
     static constexpr int STEP_WIRE_SMEM_BYTES = DYN_BYTES + WIRE_TILE_BYTES + 16;
     static constexpr int ROLLOUT_SMEM_BYTES = DYN_BYTES + 16;
+    // cell-parallel step (K >= 2): TILE x K threads per CTA, + the exchange block
+    static constexpr int X_BYTES = Xl<K>::WORDS * TILE * 4;                       // 6144 for K = 4
+    static constexpr int CELLS_SMEM_BYTES = DYN_BYTES + OBS_TILE_BYTES + X_BYTES + 16;       // 115,472 for K = 4: 2 CTAs / SM
+    static constexpr int CELLS_WIRE_SMEM_BYTES = DYN_BYTES + WIRE_TILE_BYTES + X_BYTES + 16;
+    static constexpr int CELLS_CTAS_PER_SM = K == 2 ? 3 : 2;
 };
 
 // One env of a tile inside a kernel: the dynamically indexed words live in shared memory, column `lane` of the
@@ -51,6 +56,28 @@ struct TileColumn {
     __device__ __forceinline__ void st(int w, u32 v) { dyn[w * TILE] = v; }
     __device__ __forceinline__ u32 ld_hot(int w) const { return hot[w * TILE]; }
     __device__ __forceinline__ void st_hot(int w, u32 v) { hot[w * TILE] = v; }
+    __device__ __forceinline__ u32 or_word(int w, u32 v) {  // one thread owns the env: plain read-modify-write
+        const u32 old = dyn[w * TILE];
+        dyn[w * TILE] = old | v;
+        return old;
+    }
+};
+// The same column when the K cells of an env run on K threads (cell-parallel step): order words are shared.
+struct TileColumnShared : TileColumn {
+    __device__ __forceinline__ u32 or_word(int w, u32 v) { return atomicOr(&dyn[w * TILE], v); }
+};
+// Per-env exchange area of the cell-parallel step (fjsp_core.h "X slots"): column `lane` of a [Xl<K>::WORDS][TILE] block.
+struct XchgColumn {
+    u32* x;  // &s_x[0][lane]
+    __device__ __forceinline__ u32 ld(int i) const { return x[i * TILE]; }
+    __device__ __forceinline__ void st(int i, u32 v) { x[i * TILE] = v; }
+    __device__ __forceinline__ void atom_or(int i, u32 v) { atomicOr(&x[i * TILE], v); }
+    __device__ __forceinline__ void atom_add(int i, u32 v) { atomicAdd(&x[i * TILE], v); }
+    // u16 table: entry i16 lives in half (i16 & 1) of word i16 >> 1
+    __device__ __forceinline__ void st16(int i16, u32 v) {
+        reinterpret_cast<unsigned short*>(x + (i16 >> 1) * TILE)[i16 & 1] = (unsigned short)v;
+    }
+    __device__ __forceinline__ u32 ld16(int i16) const { return reinterpret_cast<const unsigned short*>(x + (i16 >> 1) * TILE)[i16 & 1]; }
 };
 // Whole column addressed directly in HBM (reset / export paths, not hot).
 struct GmemColumn {
@@ -59,6 +86,11 @@ struct GmemColumn {
     __device__ __forceinline__ void st(int w, u32 v) { base[w * TILE] = v; }
     __device__ __forceinline__ u32 ld_hot(int w) const { return base[w * TILE]; }
     __device__ __forceinline__ void st_hot(int w, u32 v) { base[w * TILE] = v; }
+    __device__ __forceinline__ u32 or_word(int w, u32 v) {
+        const u32 old = base[w * TILE];
+        base[w * TILE] = old | v;
+        return old;
+    }
 };
 
 // ---- PTX wrappers (mbarrier + bulk async copy; see /opt/skills/guides/blackwell_cuda_programming.md) ----
@@ -267,6 +299,146 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
         for (int i = tid; i < nvalid * (OUT_ROW_BYTES / 4); i += TILE) g_out[i] = s_out[i];
     }
     if (tid == 0) bulk_wait_read0();  // shared memory must stay allocated until the TMA engine has read it
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cell-parallel step (scaled shop, K >= 2): one CTA = one tile of 64 envs x K cells = 64K threads; thread (c, e) runs
+// cell c of env e (fjsp_core.h "cell-parallel step").  Warps are uniform in c, lanes of a warp are 32 consecutive envs,
+// so every shared-memory access stays on the conflict-free column layout and the hot words of cell c are coalesced
+// 32-bit loads.  The thread-per-env kernel above keeps 4 warps per SM resident at K = 4 (the tile's 76 KB of tray pools
+// set the limit) and is latency-bound at 0.27 of the HBM roofline; this one keeps 16.
+// ---------------------------------------------------------------------------------------------
+template <int K, bool WIRE>
+__global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_step_cells_kernel(const __grid_constant__ Params P, const StepArgs A) {
+    constexpr int NT = TILE * K;
+    constexpr int OUT_ROW_BYTES = WIRE ? Geo<K>::WIRE_ROW_BYTES : Geo<K>::OBS_ROW_BYTES;
+    constexpr int OUT_TILE_BYTES = OUT_ROW_BYTES * TILE;
+    constexpr int AG = Lay<K>::AGENTS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    u32* s_dyn = reinterpret_cast<u32*>(smem_raw);
+    u32* s_out = reinterpret_cast<u32*>(smem_raw + Geo<K>::DYN_BYTES);
+    u32* s_x = reinterpret_cast<u32*>(smem_raw + Geo<K>::DYN_BYTES + OUT_TILE_BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + Geo<K>::DYN_BYTES + OUT_TILE_BYTES + Geo<K>::X_BYTES);
+
+    const int tid = threadIdx.x;
+    const int c = tid / TILE, e = tid % TILE;  // c is uniform over a warp
+    const int64_t tile = A.tile_begin + blockIdx.x;
+    const int64_t env = tile * TILE + e;
+    const bool valid = env < A.num_envs;
+    u32* g_tile = A.state + tile * Geo<K>::TILE_WORDS;
+
+    if (tid == 0) mbar_init(bar, 1);
+    for (int i = tid; i < Xl<K>::WORDS * TILE; i += NT) s_x[i] = 0u;
+    if (WIRE)
+        for (int i = tid; i < OUT_TILE_BYTES / 4; i += NT) s_out[i] = 0u;  // wire rows are assembled with ORs
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bar, Geo<K>::DYN_BYTES);
+        bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, Geo<K>::DYN_BYTES, bar);
+    }
+    TileColumnShared s;
+    s.dyn = s_dyn + e - W_CSTEP * TILE, s.hot = g_tile + e;
+    XchgColumn x{s_x + e};
+    CellLane L;
+    L.c = c;
+    load_hot(s, L.h);            // every lane of an env mirrors the pickup station's words
+    load_cell<K>(s, c, L.hc);    // its own cell's 20 hot words (coalesced: a warp reads 128 consecutive bytes per word)
+    int a0 = 0, a7[7];
+    {
+        const uint8_t* arow = A.actions + env * Lay<K>::ACT;
+        if (valid) a0 = __ldg(arow);
+#pragma unroll
+        for (int i = 0; i < 7; i++) a7[i] = valid ? (int)__ldg(arow + 1 + 7 * c + i) : 0;
+    }
+    mbar_wait(bar, 0);
+
+    if (valid) cells_begin<K>(s, x, P, L, a0, a7);
+    __syncthreads();
+    if (valid) cells_act_run<K>(s, x, P, L, a7);
+    __syncthreads();
+    int32_t info[4] = {0, 0, 0, 0};
+    L.flags = 0u, L.g = 0;
+    if (valid) cells_finish<K>(x, P, L, info);
+    const bool ended = valid && A.autoreset && (L.flags & 0x00ffffffu);
+    if (__syncthreads_or(ended)) {
+        // the two warps of cell 0 reset the ended envs (all hot words of all cells go to the HBM tile, pools and orders
+        // to shared memory); every lane of a reset env then reloads its registers
+        if (c == 0) warp_autoreset<K>(s, s_dyn, tid, ended, L.h.episode, A.num_orders, A.seed, (uint64_t)(A.first_env + env - (tid & 31)));
+        __syncthreads();
+        if (ended) {
+            load_hot(s, L.h);
+            load_cell<K>(s, c, L.hc);
+            L.flags |= 1u << 24;
+        }
+    }
+    if (valid) {
+        if (WIRE) {  // the lane's 31 (+7) observation bytes, shifted to their place in the row and OR-ed in
+            u32 wc[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, wsh[2] = {0u, 0u};
+            cells_observe<K>(s, x, P, L, WireSink{wsh, 0}, WireSink{wc, 0});
+            u32* row = s_out + e * Wire<K>::WORDS;
+            const int off = 7 + 31 * c, w0 = off >> 2, sh = (off & 3) * 8;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                atomicOr(&row[w0 + i], wc[i] << sh);
+                if (sh) atomicOr(&row[w0 + i + 1], wc[i] >> (32 - sh));
+            }
+            if (c == 0) atomicOr(&row[0], wsh[0]), atomicOr(&row[1], wsh[1]);
+        } else {
+            float* orow = reinterpret_cast<float*>(s_out) + e * Lay<K>::OBS;
+            cells_observe<K>(s, x, P, L, FloatSink{orow, P}, FloatSink{orow + 7 + 31 * c, P});
+        }
+    }
+    if (c == 0) store_hot(s, L.h);
+    store_cell<K>(s, c, L.hc);
+    __syncthreads();
+    // ---- output rows, one 32-byte piece per lane: mask bytes [32c, 32c+32), action columns [8c, 8c+8)
+    if (valid) {
+        const u32 mbits = cells_mask_word<K>(x, c);
+        u32 v16[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v16[i] = x.ld16(2 * Xl<K>::LOCAL + 8 * c + i);
+        if (WIRE) {
+            u32* row = s_out + e * Wire<K>::WORDS;
+            row[Wire<K>::OFF_MASK + c] = mbits;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                row[Wire<K>::OFF_LOCAL + 4 * c + i] = ((u32)x_local10(v16[2 * i]) & 0xffffu) | ((u32)x_local10(v16[2 * i + 1]) << 16);
+            if (c == 0) row[Wire<K>::OFF_G] = (u32)L.g, row[Wire<K>::OFF_FLAGS] = L.flags;
+        } else {
+            uint4* m4 = reinterpret_cast<uint4*>(A.masks + env * Lay<K>::MASK + 32 * c);
+            m4[0] = make_uint4(nibble_bytes(mbits), nibble_bytes(mbits >> 4), nibble_bytes(mbits >> 8), nibble_bytes(mbits >> 12));
+            m4[1] = make_uint4(nibble_bytes(mbits >> 16), nibble_bytes(mbits >> 20), nibble_bytes(mbits >> 24), nibble_bytes(mbits >> 28));
+            float r[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) r[i] = (8 * c + i < AG) ? (float)(L.g + AG * x_local10(v16[i])) / (float)(10 * AG) : 0.0f;
+            float4* r4 = reinterpret_cast<float4*>(A.rewards + env * Lay<K>::ACT + 8 * c);
+            r4[0] = make_float4(r[0], r[1], r[2], r[3]);
+            r4[1] = make_float4(r[4], r[5], r[6], r[7]);
+            if (c == 0) reinterpret_cast<u32*>(A.flags)[env] = L.flags;
+        }
+        if (A.results) {
+            u32 lo = 0u, hi = 0u;
+#pragma unroll
+            for (int i = 0; i < 4; i++) lo |= x_result(v16[i]) << (8 * i), hi |= x_result(v16[4 + i]) << (8 * i);
+            *reinterpret_cast<uint2*>(A.results + env * Lay<K>::ACT + 8 * c) = make_uint2(lo, hi);
+        }
+        if (A.infos && c == 0) reinterpret_cast<int4*>(A.infos)[env] = make_int4(info[0], info[1], info[2], info[3]);
+    }
+    fence_async_smem();
+    __syncthreads();
+    const int64_t remaining = A.num_envs - tile * TILE;
+    const int nvalid = remaining >= TILE ? TILE : (int)remaining;
+    u32* g_out = WIRE ? A.wire + tile * TILE * Wire<K>::WORDS : reinterpret_cast<u32*>(A.obs + tile * TILE * Lay<K>::OBS);
+    const bool out_bulk = ((nvalid * OUT_ROW_BYTES) & 15) == 0 && ((reinterpret_cast<uintptr_t>(g_out) & 15) == 0);
+    if (tid == 0) {
+        bulk_s2g(g_tile + W_CSTEP * TILE, s_dyn, Geo<K>::DYN_BYTES);
+        if (out_bulk) bulk_s2g(g_out, s_out, (uint32_t)(nvalid * OUT_ROW_BYTES));
+        bulk_commit();
+    }
+    if (!out_bulk) {
+        for (int i = tid; i < nvalid * (OUT_ROW_BYTES / 4); i += NT) g_out[i] = s_out[i];
+    }
+    if (tid == 0) bulk_wait_read0();
 }
 
 // ---------------------------------------------------------------------------------------------

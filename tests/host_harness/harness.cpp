@@ -99,6 +99,59 @@ void hh_step_wire(void* p, const uint8_t* actions, float* obs, int8_t* masks, fl
     })
 }
 
+// Cell-parallel step (fjsp_core.h), host emulation: the K lanes of the env run one after the other inside each phase
+// (ascending or descending cell order: the result must not depend on it), "barriers" are the phase boundaries.
+int hh_step_cells(void* p, const uint8_t* actions, float* obs, int8_t* masks, float* rewards, uint8_t* flags, uint8_t* results,
+                  int32_t* infos, int reverse) {
+    HostEnv* e = (HostEnv*)p;
+    int done = 0;
+    DISPATCH_K(e, {
+        if constexpr (K >= 2) {
+            constexpr int AG = Lay<K>::AGENTS;
+            u32 xw[Xl<K>::WORDS];
+            for (int i = 0; i < Xl<K>::WORDS; i++) xw[i] = 0u;
+            ArrayXchg x{xw};
+            ArrayState s{e->words};
+            CellLane L[K];
+            int a7[K][7];
+            for (int c = 0; c < K; c++) {
+                L[c].c = c;
+                load_hot(s, L[c].h);
+                load_cell<K>(s, c, L[c].hc);
+                for (int i = 0; i < 7; i++) a7[c][i] = actions[1 + 7 * c + i];
+            }
+            int32_t info[K][4];
+            for (int i = 0; i < K; i++) { const int c = reverse ? K - 1 - i : i; cells_begin<K>(s, x, e->P, L[c], actions[0], a7[c]); }
+            for (int i = 0; i < K; i++) { const int c = reverse ? K - 1 - i : i; cells_act_run<K>(s, x, e->P, L[c], a7[c]); }
+            for (int i = 0; i < K; i++) { const int c = reverse ? K - 1 - i : i; cells_finish<K>(x, e->P, L[c], info[c]); }
+            for (int i = 0; i < K; i++) {
+                const int c = reverse ? K - 1 - i : i;
+                cells_observe<K>(s, x, e->P, L[c], FloatSink{obs, e->P}, FloatSink{obs + 7 + 31 * c, e->P});
+            }
+            store_hot(s, L[0].h);
+            for (int c = 0; c < K; c++) store_cell<K>(s, c, L[c].hc);
+            for (int c = 0; c < K; c++) {
+                const u32 mbits = cells_mask_word<K>(x, c);
+                for (int i = 0; i < 32; i++) masks[32 * c + i] = (int8_t)((mbits >> i) & 1u);
+                u32 nb[8];
+                for (int i = 0; i < 8; i++) nb[i] = nibble_bytes(mbits >> (4 * i));
+                if (memcmp(nb, masks + 32 * c, 32) != 0) return -1;  // nibble_bytes must be the same expansion
+                for (int i = 0; i < 8; i++) {
+                    const u32 v = x.ld16(2 * Xl<K>::LOCAL + 8 * c + i);
+                    rewards[8 * c + i] = (8 * c + i < AG) ? (float)(L[c].g + AG * x_local10(v)) / (float)(10 * AG) : 0.0f;
+                    if (results) results[8 * c + i] = (uint8_t)x_result(v);
+                }
+                if (L[c].flags != L[0].flags || L[c].g != L[0].g) return -2;  // every lane rebuilds the same shared scalars
+            }
+            flags[0] = L[0].flags & 0xff, flags[1] = (L[0].flags >> 8) & 0xff, flags[2] = (L[0].flags >> 16) & 0xff, flags[3] = 0;
+            if (infos)
+                for (int i = 0; i < 4; i++) infos[i] = info[0][i];
+            done = 1;
+        }
+    })
+    return done;
+}
+
 void hh_export(void* p, int cell, FjspCanonState* out) {
     HostEnv* e = (HostEnv*)p;
     export_canon(e->words, e->P, e->cells, cell, out);

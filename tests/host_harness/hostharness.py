@@ -38,6 +38,7 @@ def lib():
         L.hh_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32]
         L.hh_step.argtypes = [C.c_void_p] * 8
         L.hh_step_wire.argtypes = [C.c_void_p] * 7
+        L.hh_step_cells.argtypes = [C.c_void_p] * 8 + [C.c_int]
         L.hh_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.hh_words.argtypes = [C.c_void_p, C.c_void_p]
         L.hh_philox_actions.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
@@ -85,6 +86,14 @@ class HostEnv:
         a = np.ascontiguousarray(actions, dtype=np.uint8)
         self._L.hh_step(self._h, a.ctypes.data, self.obs.ctypes.data, self.masks.ctypes.data, self.rewards.ctypes.data,
                         self.flags.ctypes.data, self.results.ctypes.data, self.infos.ctypes.data)
+        return self.obs.copy(), self.masks.copy(), self.rewards.copy(), self.flags.copy()
+
+    def step_cells(self, actions, reverse=False):
+        """The same step through the cell-parallel phase functions (K >= 2), lanes emulated one after the other."""
+        a = np.ascontiguousarray(actions, dtype=np.uint8)
+        rc = self._L.hh_step_cells(self._h, a.ctypes.data, self.obs.ctypes.data, self.masks.ctypes.data, self.rewards.ctypes.data,
+                                   self.flags.ctypes.data, self.results.ctypes.data, self.infos.ctypes.data, int(reverse))
+        assert rc == 1, rc
         return self.obs.copy(), self.masks.copy(), self.rewards.copy(), self.flags.copy()
 
     def step_wire(self, actions):

@@ -138,3 +138,35 @@ def test_philox_action_stream_per_cell():
         hh_lib().hh_philox_actions(77, 123, 9, k, b.ctypes.data)
         assert np.array_equal(a, b) and a[:8].tolist() == philox_actions(77, 123, 9, cells=1).tolist()
         assert all(a[1 + 7 * c] < 8 and (a[2 + 7 * c:8 + 7 * c] < 3).all() for c in range(k))
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_cell_parallel_phases_equal_sequential_step(k):
+    """The cell-parallel decomposition (one lane per cell, exchange area, atomic ORs on order words) gives the packed
+    state and every output of the sequential step, whatever order the lanes of a phase run in."""
+    seq, par = HostEnv(cfg_k(k)), HostEnv(cfg_k(k))
+    rs = np.random.RandomState(500 + k)
+    steps = completed = contested = 0
+    for ep in range(18):
+        orders = policies.random_orders(rs, [30, 32, 8][ep % 3])
+        o1, m1 = seq.reset(orders)
+        o2, m2 = par.reset(orders)
+        assert np.array_equal(o1, o2) and np.array_equal(m1, m2)
+        while True:
+            a = policy_actions(rs, o1, m1, k, ep % 3)
+            if rs.rand() < 0.15:                      # several AGVs ask for the dock in the same step
+                a[[1 + 7 * c for c in range(k)]] = 1
+                contested += 1
+            o1, m1, r1, f1 = seq.step(a)
+            o2, m2, r2, f2 = par.step_cells(a, reverse=bool((steps + ep) & 1))
+            steps += 1
+            assert np.array_equal(f1, f2), (ep, steps, f1, f2)
+            assert np.array_equal(o1, o2), (ep, steps, np.flatnonzero(o1 != o2))
+            assert np.array_equal(m1, m2), (ep, steps, np.flatnonzero(m1 != m2))
+            assert np.array_equal(r1, r2), (ep, steps, r1, r2)
+            assert np.array_equal(seq.results, par.results) and np.array_equal(seq.infos, par.infos), (ep, steps)
+            assert np.array_equal(seq.words(), par.words()), (ep, steps, np.flatnonzero(seq.words() != par.words()))
+            if f1[0] or f1[1] or f1[2]:
+                break
+        completed += int(seq.export()["completed_orders"])
+    assert steps > 1500 and completed > 40 and contested > 100

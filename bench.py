@@ -13,7 +13,7 @@ value      device-timed (CUDA events on the launching stream), inputs resident i
            so the working set exceeds the 126 MB L2 without a flush.
 e2e        the same metric through the host-buffer C-ABI call fjsp_step_host: pinned host actions in, pinned host
            float32 obs / int8 masks / float32 rewards / u8 flags out, H2D + D2H copies inside the timed region.  The
-           results cross PCIe as 72-byte wire rows (include/fjsp_b200.h) and are decoded into the caller's tensors
+           results cross PCIe as 64-byte wire rows (include/fjsp_b200.h) and are decoded into the caller's tensors
            by the library's host threads, pipelined with the copies; d2h_bytes_per_step counts the bytes that cross.
 roofline   algorithmic bytes per launch = envs x (8 + 152 + 32 + 32 + 4 + 2 x 512) = envs x 1252 B,
            divided by the mean launch duration, against MEASURED_PEAKS.json hbm_gbs.
@@ -285,7 +285,7 @@ def run_ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * E * 8 * Ke / e2e_s
     wire_row = 4 * env.dims["wire_words"]
-    # the e2e path's own roofline: this box's pinned D2H bandwidth on the wire rows (72 B/env)
+    # the e2e path's own roofline: this box's pinned D2H bandwidth on the wire rows (64 B/env)
     hb = env.host_buffers()
     for _ in range(2):
         hb["obs"].copy_(env.obs, non_blocking=True)

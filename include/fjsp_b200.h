@@ -54,17 +54,17 @@ extern "C" {
 
 /* ---- wire rows: the compact form in which a step's results cross PCIe on the host-buffer path (fjsp_step_host) and
  * which fjsp_step_wire / fjsp_wire_decode expose.  Everything a step returns is a small integer, so one env's results
- * are FJSP_WIRE_WORDS_K(K) u32 (72 B for K = 1, against 220 B of float32 tensors):
+ * are FJSP_WIRE_WORDS_K(K) u32 (64 B for K = 1, against 220 B of float32 tensors):
  *   obs    : one byte per observation field, 4 per word: the field's integer value; a station index (LocationType
  *            order) in BOTH AGV position fields (decoded through FjspConfig.pos); the table index L for a packaging
  *            station's processing_progress (decoded to float32(100/L), 0 for L = 0); queue_length as the int8 it is
  *   masks  : one bit per mask byte, 32 per word
- *   reward : g (int32) then local_i (int16 per action column): reward_i = (g + A * local_i) / (10 * A), A = 1 + 7K —
- *            the exact integer numerator of every reward (all RewardModel constants are multiples of 0.1)
- *   flags  : terminated | truncated << 8 | fault << 16 | was_reset << 24
+ *   reward : one word = g (24-bit signed) | flag bits << 24 (terminated, truncated, fault x2, was_reset), then local_i
+ *            (int16 per action column): reward_i = (g + A * local_i) / (10 * A), A = 1 + 7K — the exact integer
+ *            numerator of every reward (all RewardModel constants are multiples of 0.1)
  * fjsp_wire_decode turns rows back into exactly the tensors fjsp_step writes (bit for bit). */
 #define FJSP_WIRE_WORDS_K(k) \
-    ((((FJSP_OBS_DIM_K(k) + 3) / 4 + FJSP_MASK_DIM_K(k) / 32 + 1 + FJSP_ACT_DIM_K(k) / 2 + 1) + 1) / 2 * 2)
+    ((((FJSP_OBS_DIM_K(k) + 3) / 4 + FJSP_MASK_DIM_K(k) / 32 + 1 + FJSP_ACT_DIM_K(k) / 2) + 1) / 2 * 2)
 
 /* fault codes (flags[2]); the reference has no equivalent — see DESIGN.md "faults" */
 #define FJSP_FAULT_NONE 0
@@ -229,6 +229,16 @@ int fjsp_a2c_sample(const float* logits, const int8_t* masks, uint8_t* actions, 
 int fjsp_a2c_counter_add(uint64_t* counter, uint64_t inc, void* stream);
 int fjsp_a2c_gae(const float* rewards, const float* values, const uint8_t* flags, float* returns, float* advantages, int T, int64_t N,
                  float gamma, float lamb, void* stream);
+
+/* Cell views of a scaled shop for a trainer that shares the reference's 8 networks between the cells: view row
+ * env * K + cell holds the reference's own layout — obs float[38] = pickup station's 7 fields + the cell's 31, masks
+ * int8[32] = 3 + the cell's 26 (+3 pad), rewards float[8] = pickup station's + the cell's 7, flags u8[4] (copied).  The
+ * pickup station acts through the row of cell 0; in the other rows its mask allows action 0 only.
+ * fjsp_cells_unpack_views: env tensors (as fjsp_step writes them) -> view tensors [num_envs * K][...].
+ * fjsp_cells_pack_actions: view actions u8[num_envs * K][8] -> env actions u8[num_envs][FJSP_ACT_DIM_K(K)].  Stateless. */
+int fjsp_cells_pack_actions(const uint8_t* view_actions, uint8_t* actions, int64_t num_envs, int num_cells, void* stream);
+int fjsp_cells_unpack_views(const float* obs, const int8_t* masks, const float* rewards, const uint8_t* flags, float* v_obs,
+                            int8_t* v_masks, float* v_rewards, uint8_t* v_flags, int64_t num_envs, int num_cells, void* stream);
 
 /* action_result bit-fields (results[N][8]); reference dict keys in comments */
 #define FJSP_RES_SUCCESS 0x01        /* 'success' */

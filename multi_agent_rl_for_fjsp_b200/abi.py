@@ -29,7 +29,7 @@ def dims(cells: int = 1) -> dict:
     agents = 1 + 7 * cells
     return {"agents": agents, "act": (agents + 7) // 8 * 8, "obs": 7 + 31 * cells, "mask": (3 + 26 * cells + 31) // 32 * 32,
             "mask_used": 3 + 26 * cells, "state_words": 64 + 64 * cells + 20 * (cells - 1),
-            "wire_words": ((7 + 31 * cells + 3) // 4 + (3 + 26 * cells + 31) // 32 + 1 + (agents + 7) // 8 * 4 + 1 + 1) // 2 * 2}
+            "wire_words": ((7 + 31 * cells + 3) // 4 + (3 + 26 * cells + 31) // 32 + 1 + (agents + 7) // 8 * 4 + 1) // 2 * 2}
 
 CANON_MAXQ, CANON_PS_READY, CANON_MAXPQ = 64, 256, 256
 
@@ -74,7 +74,7 @@ EXPORTS = [
     "fjsp_rollout_random", "fjsp_export_state", "fjsp_export_state_cell", "fjsp_export_packed", "fjsp_launch_count",
     "fjsp_num_cells", "fjsp_step_wire", "fjsp_wire_decode", "fjsp_wire_row_bytes", "fjsp_set_decode_threads",
     "fjsp_state_total_bytes", "fjsp_state_save", "fjsp_state_load",
-    "fjsp_a2c_sample", "fjsp_a2c_counter_add", "fjsp_a2c_gae",
+    "fjsp_a2c_sample", "fjsp_a2c_counter_add", "fjsp_a2c_gae", "fjsp_cells_pack_actions", "fjsp_cells_unpack_views",
 ]
 
 
@@ -137,6 +137,8 @@ def lib() -> C.CDLL:
     L.fjsp_a2c_sample.argtypes = [vp, vp, vp, vp, i64, i64, u64, vp, u64, vp]
     L.fjsp_a2c_counter_add.argtypes = [vp, u64, vp]
     L.fjsp_a2c_gae.argtypes = [vp, vp, vp, vp, vp, C.c_int, i64, C.c_float, C.c_float, vp]
+    L.fjsp_cells_pack_actions.argtypes = [vp, vp, i64, C.c_int, vp]
+    L.fjsp_cells_unpack_views.argtypes = [vp] * 8 + [i64, C.c_int, vp]
     L.fjsp_export_state.argtypes = [vp, i64, vp]
     L.fjsp_export_state_cell.argtypes = [vp, i64, C.c_int, vp]
     L.fjsp_export_packed.argtypes = [vp, i64, vp]

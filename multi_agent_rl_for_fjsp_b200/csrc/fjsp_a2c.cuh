@@ -127,4 +127,49 @@ __global__ void __launch_bounds__(256) fjsp_gae_kernel(const float* __restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cell views of a scaled shop (K cells): the batched trainer sees every (env, cell) as one row of the reference's own
+// 8-agent layout — the pickup station's 7 observation fields followed by the cell's 31, its 3 + 26 mask bytes, the
+// pickup station's reward followed by the cell's seven — so the reference's actor/critic networks are shared by the
+// cells.  View row = env * K + cell.  The pickup station acts through the row of cell 0; in the other rows its mask
+// allows action 0 only (its log-probability is then constant: no gradient).
+// ---------------------------------------------------------------------------------------------
+__global__ void fjsp_cells_pack_actions_kernel(const uint8_t* __restrict__ v_actions, uint8_t* __restrict__ actions, int64_t num_envs,
+                                               int K, int act_dim) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (env, action column)
+    if (i >= num_envs * act_dim) return;
+    const int64_t env = i / act_dim;
+    const int col = (int)(i % act_dim);
+    uint8_t a = 0;
+    if (col == 0) a = v_actions[env * K * 8];
+    else if (col < 1 + 7 * K) a = v_actions[(env * K + (col - 1) / 7) * 8 + 1 + (col - 1) % 7];
+    actions[i] = a;
+}
+
+__global__ void fjsp_cells_unpack_views_kernel(const float* __restrict__ obs, const int8_t* __restrict__ masks,
+                                               const float* __restrict__ rewards, const uint8_t* __restrict__ flags,
+                                               float* __restrict__ v_obs, int8_t* __restrict__ v_masks, float* __restrict__ v_rewards,
+                                               uint8_t* __restrict__ v_flags, int64_t num_envs, int K, int obs_dim, int mask_dim,
+                                               int act_dim) {
+    // one thread per (view row, 0..81): 38 observation floats, 32 mask bytes, 8 rewards, 4 flag bytes
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= num_envs * K * 82) return;
+    const int64_t row = i / 82, env = row / K;
+    const int j = (int)(i % 82), c = (int)(row % K);
+    if (j < 38) {
+        v_obs[row * 38 + j] = obs[env * obs_dim + (j < 7 ? j : 31 * c + j)];
+    } else if (j < 70) {
+        const int m = j - 38;
+        int8_t v = 0;
+        if (m < 3) v = c == 0 ? masks[env * mask_dim + m] : (int8_t)(m == 0);
+        else if (m < 29) v = masks[env * mask_dim + 26 * c + m];
+        v_masks[row * 32 + m] = v;
+    } else if (j < 78) {
+        const int a = j - 70;
+        v_rewards[row * 8 + a] = rewards[env * act_dim + (a == 0 ? 0 : 7 * c + a)];
+    } else {
+        v_flags[row * 4 + (j - 78)] = flags[env * 4 + (j - 78)];
+    }
+}
+
 }  // namespace fjsp

@@ -295,7 +295,7 @@ static int ensure_staging(FjspHandle* h) {
 }
 
 // Host-buffer step.  The batch is cut into tile-aligned chunks that alternate between two internal streams: H2D of the
-// chunk's actions, the step kernel writing WIRE ROWS (72 B per env instead of 220 B of float tensors), D2H of the rows
+// chunk's actions, the step kernel writing WIRE ROWS (64 B per env instead of 220 B of float tensors), D2H of the rows
 // into the handle's pinned staging.  As soon as a chunk has landed, the handle's host threads decode it into the
 // caller's obs/masks/rewards/flags while later chunks are still computing / crossing PCIe; envs are independent, so
 // chunks may run in any order.  Ordered after prior work on `stream`, and `stream` is ordered after it on return.
@@ -448,6 +448,28 @@ int fjsp_a2c_sample(const float* logits, const int8_t* masks, uint8_t* actions, 
     if (rows <= 0) return 0;
     fjsp_policy_sample_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         logits, masks, actions, logp, rows, first_row, seed, reinterpret_cast<const unsigned long long*>(counter), t_off);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int fjsp_cells_pack_actions(const uint8_t* view_actions, uint8_t* actions, int64_t num_envs, int num_cells, void* stream) {
+    if (!view_actions || !actions) return fail("NULL argument");
+    if (num_cells < 1 || num_cells > FJSP_MAX_CELLS || num_envs <= 0) return fail("num_cells must be in 1..4 and num_envs positive");
+    const int act = FJSP_ACT_DIM_K(num_cells);
+    const int64_t n = num_envs * act;
+    fjsp_cells_pack_actions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(view_actions, actions, num_envs, num_cells, act);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int fjsp_cells_unpack_views(const float* obs, const int8_t* masks, const float* rewards, const uint8_t* flags, float* v_obs,
+                            int8_t* v_masks, float* v_rewards, uint8_t* v_flags, int64_t num_envs, int num_cells, void* stream) {
+    if (!obs || !masks || !rewards || !flags || !v_obs || !v_masks || !v_rewards || !v_flags) return fail("NULL argument");
+    if (num_cells < 1 || num_cells > FJSP_MAX_CELLS || num_envs <= 0) return fail("num_cells must be in 1..4 and num_envs positive");
+    const int64_t n = num_envs * num_cells * 82;
+    fjsp_cells_unpack_views_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        obs, masks, rewards, flags, v_obs, v_masks, v_rewards, v_flags, num_envs, num_cells, FJSP_OBS_DIM_K(num_cells),
+        FJSP_MASK_DIM_K(num_cells), FJSP_ACT_DIM_K(num_cells));
     CK(cudaGetLastError());
     return 0;
 }

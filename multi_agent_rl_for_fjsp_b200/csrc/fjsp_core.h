@@ -537,15 +537,25 @@ FJSP_HD void observe(S& s, const Params& P, const Hot& h, const HotCell& c0, O o
 }
 // ---------------------------------------------------------------------------------------------
 // Wire row (include/fjsp_b200.h FJSP_WIRE_WORDS_K): everything a step returns for one env, as small integers.
-//   [obs bytes, 4 per word][mask bits, 32 per word][reward_g i32][reward_local10 i16, 2 per word][flags u32][pad]
+//   [obs bytes, 4 per word][mask bits, 32 per word][reward_g (24-bit signed) | flag bits << 24][reward_local10 i16, 2 per word][pad]
 // ---------------------------------------------------------------------------------------------
 template <int K>
 struct Wire {
     static constexpr int OBSW = (Lay<K>::OBS + 3) / 4, MW = Lay<K>::MASK / 32;
-    static constexpr int OFF_MASK = OBSW, OFF_G = OBSW + MW, OFF_LOCAL = OFF_G + 1, OFF_FLAGS = OFF_LOCAL + Lay<K>::ACT / 2;
+    static constexpr int OFF_MASK = OBSW, OFF_G = OBSW + MW, OFF_LOCAL = OFF_G + 1, END = OFF_LOCAL + Lay<K>::ACT / 2;
     static constexpr int WORDS = FJSP_WIRE_WORDS_K(K);
-    static_assert(OFF_FLAGS + 1 <= WORDS && WORDS % 2 == 0, "wire row layout");
+    static_assert(END <= WORDS && WORDS % 2 == 0, "wire row layout");
 };
+// flags word of fjsp_step (terminated | truncated << 8 | fault << 16 | was_reset << 24) <-> the 5 flag bits of a wire row
+FJSP_HD u32 wire_g_word(int g, u32 flags) {
+    const u32 fb = (flags & 1u) | ((flags >> 7) & 2u) | ((flags >> 14) & 12u) | ((flags >> 20) & 16u);
+    return ((u32)g & 0x00ffffffu) | (fb << 24);
+}
+FJSP_HD int wire_g(u32 w) { return (int)(w << 8) >> 8; }
+FJSP_HD u32 wire_flags(u32 w) {
+    const u32 fb = w >> 24;
+    return (fb & 1u) | ((fb & 2u) << 7) | ((fb & 12u) << 14) | ((fb & 16u) << 20);
+}
 // four mask bytes (0/1 each) -> four bits
 FJSP_HD u32 mask_nibble(u32 bytes4) { return ((bytes4 & 0x01010101u) * 0x01020408u) >> 24; }
 
@@ -560,13 +570,12 @@ FJSP_HD void wire_row(const StepOut<K>& out, u32* row) {
         for (int j = 0; j < 8; j++) bits |= mask_nibble(out.mask[8 * i + j]) << (4 * j);
         row[Wire<K>::OFF_MASK + i] = bits;
     }
-    row[Wire<K>::OFF_G] = (u32)out.reward_g;
+    row[Wire<K>::OFF_G] = wire_g_word(out.reward_g, out.flags);
 #pragma unroll
     for (int i = 0; i < Lay<K>::ACT / 2; i++)
         row[Wire<K>::OFF_LOCAL + i] = ((u32)out.reward_local10[2 * i] & 0xffffu) | ((u32)out.reward_local10[2 * i + 1] << 16);
-    row[Wire<K>::OFF_FLAGS] = out.flags;
 #pragma unroll
-    for (int i = Wire<K>::OFF_FLAGS + 1; i < Wire<K>::WORDS; i++) row[i] = 0u;
+    for (int i = Wire<K>::END; i < Wire<K>::WORDS; i++) row[i] = 0u;
 }
 
 // observation into the sink selected by MODE (OBS_FLOAT: out.obs, OBS_WIRE: out.wobs)

@@ -35,8 +35,8 @@ struct Geo {
     static constexpr int OBS_ROW_BYTES = Lay<K>::OBS * 4;           // 152 / 524
     static constexpr int OBS_TILE_BYTES = OBS_ROW_BYTES * TILE;     // 9728 / 33536
     static constexpr int STEP_SMEM_BYTES = DYN_BYTES + OBS_TILE_BYTES + 16;
-    static constexpr int WIRE_ROW_BYTES = Wire<K>::WORDS * 4;        // 72 / 224
-    static constexpr int WIRE_TILE_BYTES = WIRE_ROW_BYTES * TILE;    // 4608 / 14336
+    static constexpr int WIRE_ROW_BYTES = Wire<K>::WORDS * 4;        // 64 / 216
+    static constexpr int WIRE_TILE_BYTES = WIRE_ROW_BYTES * TILE;    // 4096 / 13824
     static constexpr int STEP_WIRE_SMEM_BYTES = DYN_BYTES + WIRE_TILE_BYTES + 16;
     static constexpr int ROLLOUT_SMEM_BYTES = DYN_BYTES + 16;
     // cell-parallel step (K >= 2): TILE x K threads per CTA, + the exchange block
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_step_
 #pragma unroll
             for (int i = 0; i < 4; i++)
                 row[Wire<K>::OFF_LOCAL + 4 * c + i] = ((u32)x_local10(v16[2 * i]) & 0xffffu) | ((u32)x_local10(v16[2 * i + 1]) << 16);
-            if (c == 0) row[Wire<K>::OFF_G] = (u32)L.g, row[Wire<K>::OFF_FLAGS] = L.flags;
+            if (c == 0) row[Wire<K>::OFF_G] = wire_g_word(L.g, L.flags);
         } else {
             uint4* m4 = reinterpret_cast<uint4*>(A.masks + env * Lay<K>::MASK + 32 * c);
             m4[0] = make_uint4(nibble_bytes(mbits), nibble_bytes(mbits >> 4), nibble_bytes(mbits >> 8), nibble_bytes(mbits >> 12));

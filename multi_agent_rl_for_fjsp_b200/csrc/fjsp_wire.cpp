@@ -56,12 +56,15 @@ static void decode_generic(const Params& P, const u32* wire, int64_t lo, int64_t
             }
         }
         if (rewards) {
-            const int g = (int)row[Wire<K>::OFF_G];
+            const int g = wire_g(row[Wire<K>::OFF_G]);
             const int16_t* l = reinterpret_cast<const int16_t*>(row + Wire<K>::OFF_LOCAL);
             float* r = rewards + e * ACT;
             for (int i = 0; i < ACT; i++) r[i] = i < A ? (float)(g + A * (int)l[i]) / denom : 0.0f;
         }
-        if (flags) memcpy(flags + e * FJSP_FLAG_DIM, row + Wire<K>::OFF_FLAGS, 4);
+        if (flags) {
+            const u32 f = wire_flags(row[Wire<K>::OFF_G]);
+            memcpy(flags + e * FJSP_FLAG_DIM, &f, 4);
+        }
     }
 }
 
@@ -109,7 +112,7 @@ __attribute__((target("avx2"))) static inline __m256i mask_avx2(const Avx2Consts
 }
 template <int K>
 __attribute__((target("avx2"))) static inline __m256 reward_avx2(const Avx2Consts<K>& c, const u32* row, int i) {
-    const __m256i g = _mm256_set1_epi32((int)row[Wire<K>::OFF_G]);
+    const __m256i g = _mm256_set1_epi32(wire_g(row[Wire<K>::OFF_G]));
     const int16_t* l = reinterpret_cast<const int16_t*>(row + Wire<K>::OFF_LOCAL);
     const __m256i li = _mm256_cvtepi16_epi32(_mm_loadu_si128(reinterpret_cast<const __m128i*>(l + 8 * i)));
     __m256 q = _mm256_div_ps(_mm256_cvtepi32_ps(_mm256_add_epi32(g, _mm256_mullo_epi32(li, c.vA))), c.denom);
@@ -142,7 +145,10 @@ __attribute__((target("avx2"))) static void decode_avx2(const Params& P, const u
                 for (int w = 0; w < MW; w++) _mm256_storeu_si256(reinterpret_cast<__m256i*>(masks + e * MASK + 32 * w), mask_avx2<K>(c, row[Wire<K>::OFF_MASK + w]));
             if (rewards)
                 for (int i = 0; i < ACT / 8; i++) _mm256_storeu_ps(rewards + e * ACT + 8 * i, reward_avx2<K>(c, row, i));
-            if (flags) memcpy(flags + e * FJSP_FLAG_DIM, row + Wire<K>::OFF_FLAGS, 4);
+            if (flags) {
+            const u32 f = wire_flags(row[Wire<K>::OFF_G]);
+            memcpy(flags + e * FJSP_FLAG_DIM, &f, 4);
+        }
         }
         alignas(32) float tmp[8 * OBS];
         for (; e + 8 <= hi; e += 8) {
@@ -161,10 +167,10 @@ __attribute__((target("avx2"))) static void decode_avx2(const Params& P, const u
                 for (int j = 0; j < 8; j++)
                     for (int i = 0; i < ACT / 8; i++) _mm256_stream_ps(rewards + (e + j) * ACT + 8 * i, reward_avx2<K>(c, row0 + j * WORDS, i));
             if (flags) {
-                const __m256i f = _mm256_setr_epi32((int)row0[0 * WORDS + Wire<K>::OFF_FLAGS], (int)row0[1 * WORDS + Wire<K>::OFF_FLAGS],
-                                                    (int)row0[2 * WORDS + Wire<K>::OFF_FLAGS], (int)row0[3 * WORDS + Wire<K>::OFF_FLAGS],
-                                                    (int)row0[4 * WORDS + Wire<K>::OFF_FLAGS], (int)row0[5 * WORDS + Wire<K>::OFF_FLAGS],
-                                                    (int)row0[6 * WORDS + Wire<K>::OFF_FLAGS], (int)row0[7 * WORDS + Wire<K>::OFF_FLAGS]);
+                const __m256i f = _mm256_setr_epi32((int)wire_flags(row0[0 * WORDS + Wire<K>::OFF_G]), (int)wire_flags(row0[1 * WORDS + Wire<K>::OFF_G]),
+                                                    (int)wire_flags(row0[2 * WORDS + Wire<K>::OFF_G]), (int)wire_flags(row0[3 * WORDS + Wire<K>::OFF_G]),
+                                                    (int)wire_flags(row0[4 * WORDS + Wire<K>::OFF_G]), (int)wire_flags(row0[5 * WORDS + Wire<K>::OFF_G]),
+                                                    (int)wire_flags(row0[6 * WORDS + Wire<K>::OFF_G]), (int)wire_flags(row0[7 * WORDS + Wire<K>::OFF_G]));
                 _mm256_stream_si256(reinterpret_cast<__m256i*>(flags + e * FJSP_FLAG_DIM), f);
             }
         }
@@ -177,7 +183,10 @@ __attribute__((target("avx2"))) static void decode_avx2(const Params& P, const u
             for (int w = 0; w < MW; w++) _mm256_storeu_si256(reinterpret_cast<__m256i*>(masks + e * MASK + 32 * w), mask_avx2<K>(c, row[Wire<K>::OFF_MASK + w]));
         if (rewards)
             for (int i = 0; i < ACT / 8; i++) _mm256_storeu_ps(rewards + e * ACT + 8 * i, reward_avx2<K>(c, row, i));
-        if (flags) memcpy(flags + e * FJSP_FLAG_DIM, row + Wire<K>::OFF_FLAGS, 4);
+        if (flags) {
+            const u32 f = wire_flags(row[Wire<K>::OFF_G]);
+            memcpy(flags + e * FJSP_FLAG_DIM, &f, 4);
+        }
     }
 }
 

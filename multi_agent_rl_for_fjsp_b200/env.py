@@ -270,3 +270,56 @@ class BatchedFJSPEnv:
         w = np.zeros(self.dims["state_words"], dtype=np.uint32)
         abi.check(self._L.fjsp_export_packed(self._h, int(env), C.c_void_p(w.ctypes.data)))
         return w
+
+
+class CellViewEnv:
+    """A K-cell ``BatchedFJSPEnv`` seen as N*K rows of the reference's own 8-agent layout (view row = env * K + cell:
+    the pickup station + that cell's seven agents), so a trainer written for the reference shop — ``BatchedA2C`` —
+    runs on the scaled shop unchanged, its 8 actors and the critic shared by the cells (include/fjsp_b200.h "cell
+    views").  The pickup station acts through the row of cell 0; elsewhere its mask allows action 0 only.
+    Two small kernels per step around the env's own single launch (pack actions, unpack views); K = 1 is the identity."""
+
+    def __init__(self, env: BatchedFJSPEnv):
+        self.env, self.cells = env, env.cells
+        self.device, self.num_envs, self.first_env = env.device, env.num_envs * env.cells, env.first_env * env.cells
+        self.seed = env.seed
+        self._L = env._L
+        self._actions = torch.zeros((env.num_envs, env.act_dim), dtype=torch.uint8, device=env.device)
+        n = self.num_envs
+        self.obs = torch.zeros((n, OBS_DIM), dtype=torch.float32, device=env.device)
+        self.masks = torch.zeros((n, MASK_DIM), dtype=torch.int8, device=env.device)
+        self.rewards = torch.zeros((n, 8), dtype=torch.float32, device=env.device)
+        self.flags = torch.zeros((n, 4), dtype=torch.uint8, device=env.device)
+
+    @property
+    def launch_count(self):
+        return self.env.launch_count
+
+    def _unpack(self, obs, masks, rewards, flags):
+        e = self.env
+        abi.check(self._L.fjsp_cells_unpack_views(_ptr(e.obs), _ptr(e.masks), _ptr(e.rewards), _ptr(e.flags), _ptr(obs), _ptr(masks),
+                                                  _ptr(rewards), _ptr(flags), e.num_envs, self.cells, e._stream()))
+
+    def reset(self, **kw):
+        self.env.reset(**kw)
+        self._unpack(self.obs, self.masks, self.rewards, self.flags)
+        return self.obs, self.masks
+
+    def step_into(self, actions, obs, masks, rewards, flags):
+        n, e = self.num_envs, self.env
+        assert actions.dtype == torch.uint8 and actions.is_contiguous() and actions.shape == (n, 8)
+        assert obs.is_contiguous() and obs.shape == (n, OBS_DIM) and masks.is_contiguous() and masks.shape == (n, MASK_DIM)
+        assert rewards.is_contiguous() and rewards.shape == (n, 8) and flags.is_contiguous() and flags.shape == (n, 4)
+        abi.check(self._L.fjsp_cells_pack_actions(_ptr(actions), _ptr(self._actions), e.num_envs, self.cells, e._stream()))
+        e.step(self._actions)
+        self._unpack(obs, masks, rewards, flags)
+
+    def step(self, actions):
+        self.step_into(actions, self.obs, self.masks, self.rewards, self.flags)
+        return self.obs, self.rewards, self.flags[:, 0], self.flags[:, 1], self.masks
+
+    def save_state(self):
+        return self.env.save_state()
+
+    def load_state(self, buf):
+        self.env.load_state(buf)

@@ -171,3 +171,53 @@ def test_gpu_scaled_shard_map_invariance_at_size():
         shard.step(shard.random_actions(t))
     for g in (first, first + 77, first + 511):
         assert np.array_equal(full.export_packed(g), shard.export_packed(g - first))
+
+
+def test_gpu_cell_views_match_plain_slicing():
+    """fjsp_cells_unpack_views / fjsp_cells_pack_actions against plain torch slicing of the same tensors."""
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv, CellViewEnv
+
+    for k in (2, 4):
+        n = 257
+        env = BatchedFJSPEnv(n, config=_abi_cfg(ocfg_k(k)), seed=3)
+        view = CellViewEnv(env)
+        vo, vm = view.reset()
+        gen = torch.Generator(device=env.device).manual_seed(k)
+        for t in range(12):
+            va = (torch.rand(n * k, 8, device=env.device, generator=gen) * torch.tensor([3, 8, 3, 3, 3, 3, 3, 3], device=env.device)).to(torch.uint8)
+            vo, vr, term, trunc, vm = view.step(va)
+            a = view._actions.cpu().numpy()
+            van = va.cpu().numpy().reshape(n, k, 8)
+            assert np.array_equal(a[:, 0], van[:, 0, 0]) and (a[:, 1 + 7 * k:] == 0).all()
+            o, m, r, f = (x.cpu().numpy() for x in (env.obs, env.masks, env.rewards, env.flags))
+            vo_n, vm_n, vr_n, vf_n = (x.cpu().numpy() for x in (vo, vm, vr, view.flags))
+            for c in range(k):
+                assert np.array_equal(a[:, 1 + 7 * c:8 + 7 * c], van[:, c, 1:])
+                rows = np.arange(n) * k + c
+                assert np.array_equal(vo_n[rows, :7], o[:, :7]) and np.array_equal(vo_n[rows, 7:], o[:, 7 + 31 * c:38 + 31 * c])
+                want_ps = m[:, :3] if c == 0 else np.tile(np.array([1, 0, 0], np.int8), (n, 1))
+                assert np.array_equal(vm_n[rows, :3], want_ps) and np.array_equal(vm_n[rows, 3:29], m[:, 3 + 26 * c:29 + 26 * c])
+                assert (vm_n[rows, 29:] == 0).all()
+                assert np.array_equal(vr_n[rows, 0], r[:, 0]) and np.array_equal(vr_n[rows, 1:], r[:, 1 + 7 * c:8 + 7 * c])
+                assert np.array_equal(vf_n[rows], f)
+
+
+def test_gpu_a2c_trains_on_the_scaled_shop():
+    """BatchedA2C on a 4-cell shop through CellViewEnv: CUDA-graph rollout + update run, losses finite, the dummy pickup
+    rows only ever idle, and the networks are the reference's (654,366 parameters, shared by the cells)."""
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv, CellViewEnv
+    from multi_agent_rl_for_fjsp_b200.a2c_batched import BatchedA2C
+
+    k, n, T = 4, 512, 16
+    env = BatchedFJSPEnv(n, config=_abi_cfg(ocfg_k(k)), seed=9, num_orders=25, autoreset=True)
+    tr = BatchedA2C(CellViewEnv(env), rollout_len=T, seed=2)
+    assert tr.net.num_parameters() == 654366
+    before = [p.detach().clone() for p in tr.net.parameters()]
+    fps, secs = tr.train(5)
+    torch.cuda.synchronize()
+    assert tr.update_graph_error is None
+    assert torch.isfinite(tr.stats["critic_loss"]).all() and torch.isfinite(tr.stats["actor_loss"]).all()
+    acts = tr.actions.reshape(T, n, k, 8)
+    assert (acts[:, :, 1:, 0] == 0).all() and (acts[:, :, 0, 0] != 0).any()
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(before, tr.net.parameters()))
+    assert env.launch_count >= T   # eager warm-up pass; later rollouts replay the captured graph

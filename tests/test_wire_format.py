@@ -100,4 +100,4 @@ def test_wire_decode_partial_outputs_and_errors():
     assert L.fjsp_wire_decode(C.byref(cfg), rows.ctypes.data, 5, obs.ctypes.data, None, None, None, 1) == 0
     assert (obs[:, :11] == 0).all()
     assert L.fjsp_wire_decode(C.byref(cfg), None, 5, obs.ctypes.data, None, None, None, 1) != 0
-    assert L.fjsp_wire_row_bytes(0) == 0 and L.fjsp_wire_row_bytes(5) == 0 and L.fjsp_wire_row_bytes(1) == 72
+    assert L.fjsp_wire_row_bytes(0) == 0 and L.fjsp_wire_row_bytes(5) == 0 and L.fjsp_wire_row_bytes(1) == 64

@@ -35,7 +35,7 @@ env.rollout_random(60)
 acts = [env.random_actions(100 + t, out=torch.empty((n1, 8), dtype=torch.uint8, device=env.device)) for t in range(reps)]
 timed("step<1,float>", lambda i: env.step(acts[i]), n1, 8, 1252)
 wire = torch.zeros((n1, env.dims["wire_words"]), dtype=torch.int32, device=env.device)
-timed("step<1,wire>", lambda i: env.step_wire(acts[i], wire), n1, 8, 8 + 72 + 1024)
+timed("step<1,wire>", lambda i: env.step_wire(acts[i], wire), n1, 8, 8 + 64 + 1024)
 del env, acts, wire
 
 cfg = abi.default_config()

@@ -278,20 +278,6 @@ def run_ours(args):
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     ms_per_step = ms / K
     value = world * E * 8 * K / (ms * 1e-3)
-    # the same launches with the live-row optimisation switched off (every pool row crosses HBM: 1252 B per env-step)
-    env.set_live_rows(False)
-    Kw = max(3, min(K, 50))
-    for t in range(3):
-        env.step(acts[t % nbuf])
-    evw0, evw1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    evw0.record()
-    for t in range(Kw):
-        env.step(acts[(W + t) % nbuf])
-    evw1.record()
-    torch.cuda.synchronize()
-    ms_whole = evw0.elapsed_time(evw1) / Kw
-    env.set_live_rows(True)
 
     # ---- end to end through the host-buffer entry point
     Ke = max(3, min(K, args.e2e_steps))
@@ -457,10 +443,7 @@ def run_ours(args):
                          "traffic": args.ncu_traffic_bytes if E == (1 << 20) else None, "peak_source": peak_src, "kernel": "fjsp_step_kernel",
                          "algorithmic_bytes_per_launch": bytes_launch, "state_bytes_moved_per_env_each_way": state_moved,
                          "live_pool_rows_per_tile": 0.5 * (live0 + live1) / max(1, live_cap // 64),
-                         "whole_state_mode": {"note": "fjsp_set_live_rows(h, 0): all 64 rows of every tray pool cross HBM, 1252 B per env-step",
-                                              "ms_per_step": ms_whole, "bytes_per_launch": E * BYTES_PER_ENV_STEP,
-                                              "achieved": E * BYTES_PER_ENV_STEP / (ms_whole * 1e-3) / 1e9,
-                                              "frac": E * BYTES_PER_ENV_STEP / (ms_whole * 1e-3) / 1e9 / peak}},
+                         "bytes_per_launch_if_whole_state_moved": E * BYTES_PER_ENV_STEP},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 8, "d2h_bytes_per_step": E * wire_row,
                     "steps": Ke, "ms_per_step": e2e_s / Ke * 1e3,
                     "api": "fjsp_step_host (pinned host buffers; float32 obs/rewards, int8 masks, u8 flags delivered)",

@@ -217,9 +217,6 @@ int fjsp_state_load(FjspHandle* h, const void* src_device, size_t bytes, void* s
  * (tile, cell) of the live row count — one row = 64 envs x 4 B = 256 B read and written per step — and the sum if every
  * pool were full (rows_capacity, may be NULL).  bench.py derives the bytes a step actually moves from it. */
 int fjsp_live_pool_rows(FjspHandle* h, int64_t* rows_sum, int64_t* rows_capacity);
-/* enabled = 0: the step kernels move all 64 rows of every pool (the whole packed state); same results, more bytes.
- * A/B switch for measurements; default 1. */
-int fjsp_set_live_rows(FjspHandle* h, int enabled);
 
 /* Number of kernels this library has launched since the handle was created. */
 int64_t fjsp_launch_count(const FjspHandle* h);

@@ -26,7 +26,6 @@ struct FjspHandle {
     int64_t num_envs, first_env, num_tiles;
     u32* state;  // num_tiles * tile_bytes
     u32* tile_rows;          // [num_tiles][cells] live tray-pool rows per (tile, cell): what the step kernels move
-    int whole_pools;         // fjsp_set_live_rows(h, 0): move every pool row (A/B switch for measurements)
     uint64_t seed;
     int num_orders;
     int64_t launches;
@@ -234,7 +233,6 @@ int fjsp_step(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, 
     A.state = h->state, A.actions = actions, A.obs = obs, A.masks = masks, A.rewards = rewards, A.flags = flags;
     A.results = results, A.infos = infos, A.num_envs = h->num_envs, A.first_env = h->first_env, A.seed = h->seed;
     A.num_orders = h->num_orders, A.autoreset = autoreset, A.tile_begin = 0, A.wire = nullptr, A.tile_rows = h->tile_rows;
-    A.whole_pools = h->whole_pools;
     DISPATCH_K(h->cells, launch_step<K, false>(h, A, (unsigned)h->num_tiles, (cudaStream_t)stream))
     h->launches++;
     CK(cudaGetLastError());
@@ -246,7 +244,6 @@ static StepArgs wire_args(FjspHandle* h, const uint8_t* actions, u32* wire, uint
     A.state = h->state, A.actions = actions, A.obs = nullptr, A.masks = nullptr, A.rewards = nullptr, A.flags = nullptr;
     A.results = results, A.infos = infos, A.wire = wire, A.num_envs = h->num_envs, A.first_env = h->first_env, A.seed = h->seed;
     A.num_orders = h->num_orders, A.autoreset = autoreset, A.tile_begin = 0, A.tile_rows = h->tile_rows;
-    A.whole_pools = h->whole_pools;
     return A;
 }
 
@@ -428,12 +425,6 @@ int fjsp_state_load(FjspHandle* h, const void* src_device, size_t bytes, void* s
     DeviceGuard g(h->device);
     CK(cudaMemcpyAsync(h->state, src_device, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return refresh_tile_rows(h, (cudaStream_t)stream);
-}
-
-int fjsp_set_live_rows(FjspHandle* h, int enabled) {
-    if (!h) return fail("handle is NULL");
-    h->whole_pools = enabled ? 0 : 1;
-    return 0;
 }
 
 int fjsp_live_pool_rows(FjspHandle* h, int64_t* rows_sum, int64_t* rows_capacity) {

@@ -134,23 +134,17 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // highest used slot hold nothing but zeros: the step kernels keep that row count per (tile, cell) in `tile_rows` and move
 // only the live rows (under the bench's random policy ~4 of 64).  tile_bulk_load / tile_bulk_store are called by ONE thread.
 struct TileTail {            // shared memory behind the staging areas
-    uint64_t bar;            // mbarrier of the inbound copy of the completion-step and order words (issued first)
-    uint64_t bar_pool;       // mbarrier of the inbound copies of the live pool rows (issued once the row counts are known)
+    uint64_t bar;            // mbarrier of the inbound copies
     u32 rows_in[4];          // live rows per cell when the tile was loaded
     u32 rows_out[4];         // live rows per cell after the step (atomicMax over the tile's envs)
 };
-// inbound copies, in two parts so that the first does not wait for the row counts to arrive from HBM
 template <int K>
-__device__ __forceinline__ void tile_bulk_load_base(u32* s_dyn, const u32* g_tile, uint64_t* bar) {
-    mbar_expect_tx(bar, Geo<K>::BASE_ROWS * TILE * 4);
-    bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, Geo<K>::BASE_ROWS * TILE * 4, bar);
-}
-template <int K>
-__device__ __forceinline__ void tile_bulk_load_pools(u32* s_dyn, const u32* g_tile, const u32* rows, uint64_t* bar) {
-    u32 bytes = 0;
+__device__ __forceinline__ void tile_bulk_load(u32* s_dyn, const u32* g_tile, const u32* rows, uint64_t* bar) {
+    u32 bytes = Geo<K>::BASE_ROWS * TILE * 4;
 #pragma unroll
     for (int c = 0; c < K; c++) bytes += rows[c] * TILE * 4;
-    mbar_expect_tx(bar, bytes);  // with 0 bytes this is a plain arrival: the phase completes at once
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, Geo<K>::BASE_ROWS * TILE * 4, bar);
 #pragma unroll
     for (int c = 0; c < K; c++)
         if (rows[c]) bulk_g2s(s_dyn + (pool_base(c) - W_CSTEP) * TILE, g_tile + pool_base(c) * TILE, rows[c] * TILE * 4, bar);
@@ -214,7 +208,6 @@ struct StepArgs {
     int32_t* infos;          // [N][4] or null
     u32* wire;               // [N][Wire<K>::WORDS]: the WIRE instantiation writes this instead of obs/masks/rewards/flags
     u32* tile_rows;          // [num_tiles][K] live pool rows per (tile, cell), maintained by the step kernels
-    int32_t whole_pools;     // non-zero: move all 64 rows of every pool (fjsp_set_live_rows(h, 0): the A/B switch)
     int64_t num_envs, first_env;
     int64_t tile_begin;      // first tile of this launch (host-buffer path steps the batch in pipelined chunks)
     uint64_t seed;
@@ -278,13 +271,13 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
     const bool valid = env < A.num_envs;
     u32* g_tile = A.state + tile * Geo<K>::TILE_WORDS;
 
-    // bulk async copies (TMA engine) of the tile's dynamically indexed words: the completion-step and order words at
-    // once, the LIVE rows of the tray pool as soon as the row count has arrived
-    if (tid == 0) {
-        mbar_init(bar, 1), mbar_init(&tail->bar_pool, 1);
-        tile_bulk_load_base<K>(s_dyn, g_tile, bar);
-    }
-    const u32 my_rows = tid < K ? (A.whole_pools ? (u32)FJSP_POOL_SLOTS : __ldg(A.tile_rows + tile * K + tid)) : 0u;
+    if (tid == 0) mbar_init(bar, 1);
+    if (tid < K) tail->rows_in[tid] = __ldg(A.tile_rows + tile * K + tid), tail->rows_out[tid] = 0u;
+    __syncthreads();
+    // bulk async copies (TMA engine) of the tile's dynamically indexed words: orders + the LIVE rows of the tray pool
+    if (tid == 0) tile_bulk_load<K>(s_dyn, g_tile, tail->rows_in, bar);
+#pragma unroll
+    for (int c = 0; c < K; c++) column_zero_margin(s_dyn, tid, c, tail->rows_in[c]);
     // meanwhile: the hot words of the pickup station and of cell 0 (coalesced 32-bit loads, straight into registers)
     // and the action bytes
     TileColumn s{s_dyn + tid - W_CSTEP * TILE, g_tile + tid};
@@ -294,13 +287,7 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
     load_cell<K>(s, 0, c0);
     int a[Lay<K>::ACT];
     load_actions<K>(A.actions, env, valid, a);
-    if (tid < K) tail->rows_in[tid] = my_rows, tail->rows_out[tid] = 0u;
-    __syncthreads();
-    if (tid == 0) tile_bulk_load_pools<K>(s_dyn, g_tile, tail->rows_in, &tail->bar_pool);
-#pragma unroll
-    for (int c = 0; c < K; c++) column_zero_margin(s_dyn, tid, c, tail->rows_in[c]);
     mbar_wait(bar, 0);
-    mbar_wait(&tail->bar_pool, 0);
 
     // padding lanes of a ragged last tile are inert: their words travel through unchanged
     StepOut<K> out;
@@ -399,16 +386,13 @@ __global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_step_
     const bool valid = env < A.num_envs;
     u32* g_tile = A.state + tile * Geo<K>::TILE_WORDS;
 
-    if (tid == 0) {
-        mbar_init(bar, 1), mbar_init(&tail->bar_pool, 1);
-        tile_bulk_load_base<K>(s_dyn, g_tile, bar);  // completion-step + order words: no need to wait for the row counts
-    }
-    if (tid < K) tail->rows_in[tid] = A.whole_pools ? (u32)FJSP_POOL_SLOTS : __ldg(A.tile_rows + tile * K + tid), tail->rows_out[tid] = 0u;
+    if (tid == 0) mbar_init(bar, 1);
+    if (tid < K) tail->rows_in[tid] = __ldg(A.tile_rows + tile * K + tid), tail->rows_out[tid] = 0u;
     for (int i = tid; i < Xl<K>::WORDS * TILE; i += NT) s_x[i] = 0u;
     if (WIRE)
         for (int i = tid; i < OUT_TILE_BYTES / 4; i += NT) s_out[i] = 0u;  // wire rows are assembled with ORs
     __syncthreads();
-    if (tid == 0) tile_bulk_load_pools<K>(s_dyn, g_tile, tail->rows_in, &tail->bar_pool);  // the LIVE rows of each cell's tray pool
+    if (tid == 0) tile_bulk_load<K>(s_dyn, g_tile, tail->rows_in, bar);  // orders + the LIVE rows of each cell's tray pool
     column_zero_margin(s_dyn, e, c, tail->rows_in[c]);
     TileColumnShared s;
     s.dyn = s_dyn + e - W_CSTEP * TILE, s.hot = g_tile + e;
@@ -425,7 +409,6 @@ __global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_step_
         for (int i = 0; i < 7; i++) a7[i] = valid ? (int)__ldg(arow + 1 + 7 * c + i) : 0;
     }
     mbar_wait(bar, 0);
-    mbar_wait(&tail->bar_pool, 0);
 
     if (valid) cells_begin<K>(s, x, P, L, a0, a7);
     __syncthreads();

@@ -120,10 +120,6 @@ class BatchedFJSPEnv:
     def launch_count(self) -> int:
         return int(self._L.fjsp_launch_count(self._h))
 
-    def set_live_rows(self, enabled: bool):
-        """False: the step kernels move the whole packed state (all 64 rows of every tray pool); same results."""
-        abi.check(self._L.fjsp_set_live_rows(self._h, int(bool(enabled))))
-
     def live_pool_rows(self):
         """(live, capacity): tray-pool rows (256 B each) the step kernels move per step over all tiles, and the count if
         every pool were full.  Synchronises."""

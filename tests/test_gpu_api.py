@@ -7,55 +7,6 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("k", [1, 4])
-def test_live_rows_and_whole_state_modes_agree(k):
-    """The step kernels move only the live rows of each tile's tray pools; with the optimisation switched off they move
-    the whole state.  Same outputs, same packed state (freed records are zeroed, so dead rows are zeros either way) —
-    under a policy that packages products (records are allocated, split, freed) and with auto-resets."""
-    import numpy as np
-    import torch
-
-    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv, abi
-    from tests.test_gpu_parity import _torch_heuristic
-
-    cfg = abi.default_config()
-    cfg.num_cells = k
-    n = 1000
-    a = BatchedFJSPEnv(n, config=cfg, seed=3, num_orders=8)
-    b = BatchedFJSPEnv(n, config=cfg, seed=3, num_orders=8)
-    b.set_live_rows(False)
-    oa, ma = a.reset()
-    b.reset()
-    gen = torch.Generator(device=a.device).manual_seed(1)
-    peak = 0
-    for t in range(260):
-        acts = torch.zeros(n, a.act_dim, dtype=torch.uint8, device=a.device)
-        for c in range(k):
-            o_c = torch.cat([oa[:, :7], oa[:, 7 + 31 * c:38 + 31 * c]], dim=1)
-            m_c = torch.zeros(n, 32, dtype=torch.int8, device=a.device)
-            m_c[:, :3], m_c[:, 3:29] = ma[:, :3], ma[:, 3 + 26 * c:29 + 26 * c]
-            a_c = _torch_heuristic(o_c, m_c, gen)
-            if c == 0:
-                acts[:, 0] = a_c[:, 0]
-            acts[:, 1 + 7 * c:8 + 7 * c] = a_c[:, 1:]
-        oa, ra, _, _, ma = a.step(acts)
-        ob, rb, _, _, mb = b.step(acts)
-        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(ma, mb) and torch.equal(a.flags, b.flags), t
-        if t % 20 == 0:
-            live, cap = a.live_pool_rows()
-            peak = max(peak, live)
-            assert 0 <= live <= cap and cap == 64 * k * ((n + 63) // 64)
-    assert torch.equal(a.save_state(), b.save_state())
-    assert peak > 4 * k * ((n + 63) // 64), "the policy should keep several trays in flight per tile"
-    # a K-steps-per-launch rollout (moves whole tiles) and a state reload keep the row counts consistent
-    a.rollout_random(30), b.rollout_random(30)
-    a.load_state(a.save_state())
-    for t in range(20):
-        acts = a.random_actions(1000 + t)
-        a.step(acts), b.step(acts)
-    assert torch.equal(a.save_state(), b.save_state())
-
-
 def test_snapshot_restore_is_deterministic():
     from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
 

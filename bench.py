@@ -15,11 +15,8 @@ e2e        the same metric through the host-buffer C-ABI call fjsp_step_host: pi
            float32 obs / int8 masks / float32 rewards / u8 flags out, H2D + D2H copies inside the timed region.  The
            results cross PCIe as 64-byte wire rows (include/fjsp_b200.h) and are decoded into the caller's tensors
            by the library's host threads, pipelined with the copies; d2h_bytes_per_step counts the bytes that cross.
-roofline   algorithmic bytes per launch = envs x (8 + 152 + 32 + 32 + 4 + 2 x S) with S = the state bytes the step
-           actually moves (228 + 2 x min(S_actual, 512)): 96 B of hot words + 160 B of order words + the
-           LIVE rows of the tile's tray pool (4 B per row and env; fjsp_live_pool_rows, sampled before and after the
-           timed region) — at most 512 B, about 270 B under this workload's random policy.  Divided by the mean launch
-           duration, against MEASURED_PEAKS.json hbm_gbs.
+roofline   algorithmic bytes per launch = envs x (8 + 152 + 32 + 32 + 4 + 2 x 512) = envs x 1252 B,
+           divided by the mean launch duration, against MEASURED_PEAKS.json hbm_gbs.
 cpu_baseline / --impl reference
            the reference is pure Python + SimPy and cannot travel to the GPU box, so the CPU arm is the C port of it
            (oracle/fjsp_oracle.c, kind "port") on all host threads, on a bounded sample of the same workload.
@@ -255,7 +252,6 @@ def run_ours(args):
 
     for t in range(W):
         env.step(acts[t % nbuf])
-    live0, live_cap = env.live_pool_rows()
     launches0 = env.launch_count
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -272,9 +268,6 @@ def run_ours(args):
     wall1 = time.time()
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = env.launch_count - launches0
-    live1, _ = env.live_pool_rows()
-    # state bytes per env the step moves each way: hot words + completion/order words + live pool rows (256 B per row and tile)
-    state_moved = 96 + 160 + 4.0 * 0.5 * (live0 + live1) / max(1, live_cap // 64)
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     ms_per_step = ms / K
     value = world * E * 8 * K / (ms * 1e-3)
@@ -379,17 +372,12 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         ms4 = e0.elapsed_time(e1) / 50
-        l4b, _ = e4.live_pool_rows()
-        rows4 = 0.5 * (l4a + l4b) / max(1, cap4 // 64 // 4)        # live rows per tile, summed over the 4 cells
-        state4 = 4 * (d4["state_words"] - 4 * 64) + 4.0 * rows4     # hot + order words, + live pool rows
-        bytes4 = d4["act"] + 4 * d4["obs"] + d4["mask"] + 4 * d4["act"] + 4 + 2 * state4
-        l4a, cap4 = e4.live_pool_rows()
+        bytes4 = d4["act"] + 4 * d4["obs"] + d4["mask"] + 4 * d4["act"] + 4 + 2 * 4 * d4["state_words"]
         peak4, _ = measured_peak()
         scaled = {"workload": "configs[4] scaled shop: 4 cells (4 AGVs, 4 small + 4 big machines, 16 packaging stations, 29 agents), "
                               "%d envs, 32 Philox orders/env, Philox uniform-random actions, autoreset" % n4,
                   "envs": n4, "agents": d4["agents"], "ms_per_step": ms4, "agent_steps_per_s": n4 * d4["agents"] / (ms4 * 1e-3),
-                  "state_bytes_per_env": 4 * d4["state_words"], "state_bytes_moved_per_env_each_way": state4,
-                  "algorithmic_bytes_per_env_step": bytes4,
+                  "state_bytes_per_env": 4 * d4["state_words"], "algorithmic_bytes_per_env_step": bytes4,
                   "achieved_gbs": n4 * bytes4 / (ms4 * 1e-3) / 1e9, "roofline_frac": n4 * bytes4 / (ms4 * 1e-3) / 1e9 / peak4,
                   "kernel": "fjsp_step_cells_kernel<4,false> (one thread per (env, cell))"}
         del e4, a4
@@ -429,21 +417,18 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        bytes_launch = E * (BYTES_IO + 2 * state_moved)
-        achieved = bytes_launch / (ms_per_step * 1e-3) / 1e9  # GB/s per GPU
+        achieved = E * BYTES_PER_ENV_STEP / (ms_per_step * 1e-3) / 1e9  # GB/s per GPU
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(E), "envs_per_gpu": E, "num_orders": NUM_ORDERS,
                        "state_bytes_per_env": STATE_BYTES, "parallelism": "env-sharded x%d, no collective in the step" % world,
-                       "l2": "no flush: each step streams the live part of the 512 MiB state (>= 256 MiB) and a fresh 8 MiB action buffer (> 126 MB L2)",
+                       "l2": "no flush: each step streams the 512 MiB state and a fresh 8 MiB action buffer (> 126 MB L2)",
                        "action_buffers": nbuf},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": args.ncu_traffic_bytes if E == (1 << 20) else None, "peak_source": peak_src, "kernel": "fjsp_step_kernel",
-                         "algorithmic_bytes_per_launch": bytes_launch, "state_bytes_moved_per_env_each_way": state_moved,
-                         "live_pool_rows_per_tile": 0.5 * (live0 + live1) / max(1, live_cap // 64),
-                         "bytes_per_launch_if_whole_state_moved": E * BYTES_PER_ENV_STEP},
+                         "algorithmic_bytes_per_launch": E * BYTES_PER_ENV_STEP},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 8, "d2h_bytes_per_step": E * wire_row,
                     "steps": Ke, "ms_per_step": e2e_s / Ke * 1e3,
                     "api": "fjsp_step_host (pinned host buffers; float32 obs/rewards, int8 masks, u8 flags delivered)",

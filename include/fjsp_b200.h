@@ -212,12 +212,6 @@ size_t fjsp_state_total_bytes(const FjspHandle* h);
 int fjsp_state_save(FjspHandle* h, void* dst_device, size_t bytes, void* stream);
 int fjsp_state_load(FjspHandle* h, const void* src_device, size_t bytes, void* stream);
 
-/* The step kernels move only the LIVE rows of each tile's tray pools (rows up to the tile's highest used slot; a freed
- * record is zeroed, so the rest of a pool is zeros and stays where it is).  Diagnostic (synchronises): the sum over
- * (tile, cell) of the live row count — one row = 64 envs x 4 B = 256 B read and written per step — and the sum if every
- * pool were full (rows_capacity, may be NULL).  bench.py derives the bytes a step actually moves from it. */
-int fjsp_live_pool_rows(FjspHandle* h, int64_t* rows_sum, int64_t* rows_capacity);
-
 /* Number of kernels this library has launched since the handle was created. */
 int64_t fjsp_launch_count(const FjspHandle* h);
 

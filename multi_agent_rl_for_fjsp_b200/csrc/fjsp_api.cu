@@ -25,7 +25,6 @@ struct FjspHandle {
     size_t tile_bytes;       // 64 envs x FJSP_STATE_WORDS_K words
     int64_t num_envs, first_env, num_tiles;
     u32* state;  // num_tiles * tile_bytes
-    u32* tile_rows;          // [num_tiles][cells] live tray-pool rows per (tile, cell): what the step kernels move
     uint64_t seed;
     int num_orders;
     int64_t launches;
@@ -108,14 +107,6 @@ static void launch_step(const FjspHandle* h, const StepArgs& A, unsigned tiles, 
     fjsp_step_kernel<K, WIRE><<<tiles, TILE, WIRE ? Geo<K>::STEP_WIRE_SMEM_BYTES : Geo<K>::STEP_SMEM_BYTES, st>>>(h->P, A);
 }
 
-// tile_rows from the free bitmaps, after anything that rewrites whole tiles (reset, state load, K-steps-per-launch kernel)
-static int refresh_tile_rows(FjspHandle* h, cudaStream_t st) {
-    DISPATCH_K(h->cells, fjsp_tile_rows_kernel<K><<<(unsigned)h->num_tiles, TILE, 0, st>>>(h->state, h->num_envs, h->tile_rows))
-    h->launches++;
-    CK(cudaGetLastError());
-    return 0;
-}
-
 extern "C" {
 
 const char* fjsp_last_error(void) { return g_err.c_str(); }
@@ -169,11 +160,9 @@ int fjsp_create(const FjspConfig* cfg, int64_t num_envs, int64_t first_env, int 
     DISPATCH_K(h->cells, fjsp_reset_kernel<K><<<(unsigned)h->num_tiles, TILE>>>(h->P, h->state, nullptr, nullptr, 0, 0ull, h->num_envs,
                                                                                 h->first_env, nullptr, nullptr))
     h->launches++;
-    e = cudaMalloc(&h->tile_rows, (size_t)h->num_tiles * h->cells * sizeof(u32));
-    if (e == cudaSuccess) e = cudaMemset(h->tile_rows, 0, (size_t)h->num_tiles * h->cells * sizeof(u32));
-    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
-        cudaFree(h->state), cudaFree(h->tile_rows);
+        cudaFree(h->state);
         delete h;
         return cuda_fail(e, "initial reset kernel");
     }
@@ -186,7 +175,6 @@ int fjsp_destroy(FjspHandle* h) {
     DeviceGuard g(h->device);
     cudaFree(h->state);
     delete h->pool;
-    cudaFree(h->tile_rows);
     cudaFree(h->d_actions), cudaFree(h->d_wire);
     if (h->h_wire) cudaFreeHost(h->h_wire);
     for (int i = 0; i < 2; i++) {
@@ -217,7 +205,7 @@ int fjsp_reset(FjspHandle* h, const uint8_t* env_mask, uint64_t seed, const Fjsp
                              h->P, h->state, env_mask, orders, num_orders, seed, h->num_envs, h->first_env, obs, masks))
     h->launches++;
     CK(cudaGetLastError());
-    return refresh_tile_rows(h, (cudaStream_t)stream);
+    return 0;
 }
 
 int fjsp_step(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, float* rewards, uint8_t* flags, uint8_t* results,
@@ -232,7 +220,7 @@ int fjsp_step(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, 
     StepArgs A;
     A.state = h->state, A.actions = actions, A.obs = obs, A.masks = masks, A.rewards = rewards, A.flags = flags;
     A.results = results, A.infos = infos, A.num_envs = h->num_envs, A.first_env = h->first_env, A.seed = h->seed;
-    A.num_orders = h->num_orders, A.autoreset = autoreset, A.tile_begin = 0, A.wire = nullptr, A.tile_rows = h->tile_rows;
+    A.num_orders = h->num_orders, A.autoreset = autoreset, A.tile_begin = 0, A.wire = nullptr;
     DISPATCH_K(h->cells, launch_step<K, false>(h, A, (unsigned)h->num_tiles, (cudaStream_t)stream))
     h->launches++;
     CK(cudaGetLastError());
@@ -243,7 +231,7 @@ static StepArgs wire_args(FjspHandle* h, const uint8_t* actions, u32* wire, uint
     StepArgs A;
     A.state = h->state, A.actions = actions, A.obs = nullptr, A.masks = nullptr, A.rewards = nullptr, A.flags = nullptr;
     A.results = results, A.infos = infos, A.wire = wire, A.num_envs = h->num_envs, A.first_env = h->first_env, A.seed = h->seed;
-    A.num_orders = h->num_orders, A.autoreset = autoreset, A.tile_begin = 0, A.tile_rows = h->tile_rows;
+    A.num_orders = h->num_orders, A.autoreset = autoreset, A.tile_begin = 0;
     return A;
 }
 
@@ -406,7 +394,7 @@ int fjsp_rollout_random(FjspHandle* h, int steps, uint64_t seed, uint64_t t0, ui
                              reinterpret_cast<unsigned long long*>(stats)))
     h->launches++;
     CK(cudaGetLastError());
-    return refresh_tile_rows(h, (cudaStream_t)stream);  // this kernel moves whole tiles
+    return 0;
 }
 
 size_t fjsp_state_total_bytes(const FjspHandle* h) { return h ? (size_t)h->num_tiles * h->tile_bytes : 0; }
@@ -424,20 +412,6 @@ int fjsp_state_load(FjspHandle* h, const void* src_device, size_t bytes, void* s
     if (bytes != fjsp_state_total_bytes(h)) return fail("bytes must equal fjsp_state_total_bytes()");
     DeviceGuard g(h->device);
     CK(cudaMemcpyAsync(h->state, src_device, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-    return refresh_tile_rows(h, (cudaStream_t)stream);
-}
-
-int fjsp_live_pool_rows(FjspHandle* h, int64_t* rows_sum, int64_t* rows_capacity) {
-    if (!h || !rows_sum) return fail("NULL argument");
-    DeviceGuard g(h->device);
-    CK(cudaDeviceSynchronize());
-    const size_t n = (size_t)h->num_tiles * h->cells;
-    std::vector<u32> host(n);
-    CK(cudaMemcpy(host.data(), h->tile_rows, n * sizeof(u32), cudaMemcpyDeviceToHost));
-    int64_t s = 0;
-    for (size_t i = 0; i < n; i++) s += host[i];
-    *rows_sum = s;
-    if (rows_capacity) *rows_capacity = (int64_t)n * FJSP_POOL_SLOTS;
     return 0;
 }
 

@@ -256,26 +256,10 @@ FJSP_HD int pool_alloc(HotCell& h) {
     }
     return -1;
 }
-// A freed record is zeroed: "slot free => word 0" is the invariant that lets the step kernels move only the LIVE rows of
-// a tile's pool (rows below the tile's highest used slot) and still leave every word of the state well defined.
-template <class S>
-FJSP_HD void pool_free(S& s, int pb, HotCell& h, int slot) {
-    s.st(pb + slot, 0u);
+FJSP_HD void pool_free(HotCell& h, int slot) {
     if (slot < 32) h.free_lo |= 1u << slot;
     else h.free_hi |= 1u << (slot - 32);
 }
-// number of pool rows in use = highest used slot + 1 (slots are handed out lowest-first)
-FJSP_HD int pool_rows_used(u32 free_lo, u32 free_hi) {
-    const u32 used_hi = ~free_hi, used_lo = ~free_lo;
-#if defined(__CUDA_ARCH__)
-    return used_hi ? 64 - __clz((int)used_hi) : (used_lo ? 32 - __clz((int)used_lo) : 0);
-#else
-    return used_hi ? 64 - __builtin_clz(used_hi) : (used_lo ? 32 - __builtin_clz(used_lo) : 0);
-#endif
-}
-// One step allocates at most 9 slots per cell (one AGV pickup, two grant calls per packaging station that may each
-// split a tray), so rows [rows_loaded, rows_loaded + POOL_ROWS_MARGIN) are the only ones a step can newly touch.
-enum { POOL_ROWS_MARGIN = 10 };
 template <class S>
 FJSP_HD void fifo_push(S& s, int pb, Fifo& f, int slot) {
     if (f.len == 0) {
@@ -896,7 +880,7 @@ FJSP_HD void run_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, 
             u32 r = s.ld(pb + slot);
             if (rec_stamp(r) != (k & 255)) break;
             fifo_pop(s, pb, p.f);
-            pool_free(s, pb, hc, slot);
+            pool_free(hc, slot);
             const int o = rec_order(r), cnt = rec_count(r);
             // or_word: a plain read-modify-write when one thread owns the env, an atomic OR when the cells of an env run
             // on different threads (two cells may package products of the same order in the same step)

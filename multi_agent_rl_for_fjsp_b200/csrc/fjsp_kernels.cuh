@@ -34,17 +34,15 @@ struct Geo {
     static constexpr int DYN_BYTES = DYN_WORDS * 4;                 // 26624 / 75776: through shared memory (one bulk copy)
     static constexpr int OBS_ROW_BYTES = Lay<K>::OBS * 4;           // 152 / 524
     static constexpr int OBS_TILE_BYTES = OBS_ROW_BYTES * TILE;     // 9728 / 33536
-    static constexpr int BASE_ROWS = W_POOL - W_CSTEP;               // completion steps + order words: always moved
-    static constexpr int TAIL_BYTES = 64;                            // mbarrier + live-row counters
-    static constexpr int STEP_SMEM_BYTES = DYN_BYTES + OBS_TILE_BYTES + TAIL_BYTES;
+    static constexpr int STEP_SMEM_BYTES = DYN_BYTES + OBS_TILE_BYTES + 16;
     static constexpr int WIRE_ROW_BYTES = Wire<K>::WORDS * 4;        // 64 / 216
     static constexpr int WIRE_TILE_BYTES = WIRE_ROW_BYTES * TILE;    // 4096 / 13824
-    static constexpr int STEP_WIRE_SMEM_BYTES = DYN_BYTES + WIRE_TILE_BYTES + TAIL_BYTES;
+    static constexpr int STEP_WIRE_SMEM_BYTES = DYN_BYTES + WIRE_TILE_BYTES + 16;
     static constexpr int ROLLOUT_SMEM_BYTES = DYN_BYTES + 16;
     // cell-parallel step (K >= 2): TILE x K threads per CTA, + the exchange block
     static constexpr int X_BYTES = Xl<K>::WORDS * TILE * 4;                       // 6144 for K = 4
-    static constexpr int CELLS_SMEM_BYTES = DYN_BYTES + OBS_TILE_BYTES + X_BYTES + TAIL_BYTES;  // 115,520 for K = 4: 2 CTAs / SM
-    static constexpr int CELLS_WIRE_SMEM_BYTES = DYN_BYTES + WIRE_TILE_BYTES + X_BYTES + TAIL_BYTES;
+    static constexpr int CELLS_SMEM_BYTES = DYN_BYTES + OBS_TILE_BYTES + X_BYTES + 16;       // 115,472 for K = 4: 2 CTAs / SM
+    static constexpr int CELLS_WIRE_SMEM_BYTES = DYN_BYTES + WIRE_TILE_BYTES + X_BYTES + 16;
     static constexpr int CELLS_CTAS_PER_SM = K == 2 ? 3 : 2;
 };
 
@@ -128,47 +126,6 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// ---- live rows of the tray pools ---------------------------------------------------------------------------------
-// A tile's dynamically indexed words are [completion steps | order words | pool of cell 0 | pool of cell 1 | ...], one
-// 256-byte row per word.  Slots are handed out lowest-first and a freed record is zeroed, so the rows above a tile's
-// highest used slot hold nothing but zeros: the step kernels keep that row count per (tile, cell) in `tile_rows` and move
-// only the live rows (under the bench's random policy ~4 of 64).  tile_bulk_load / tile_bulk_store are called by ONE thread.
-struct TileTail {            // shared memory behind the staging areas
-    uint64_t bar;            // mbarrier of the inbound copies
-    u32 rows_in[4];          // live rows per cell when the tile was loaded
-    u32 rows_out[4];         // live rows per cell after the step (atomicMax over the tile's envs)
-};
-template <int K>
-__device__ __forceinline__ void tile_bulk_load(u32* s_dyn, const u32* g_tile, const u32* rows, uint64_t* bar) {
-    u32 bytes = Geo<K>::BASE_ROWS * TILE * 4;
-#pragma unroll
-    for (int c = 0; c < K; c++) bytes += rows[c] * TILE * 4;
-    mbar_expect_tx(bar, bytes);
-    bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, Geo<K>::BASE_ROWS * TILE * 4, bar);
-#pragma unroll
-    for (int c = 0; c < K; c++)
-        if (rows[c]) bulk_g2s(s_dyn + (pool_base(c) - W_CSTEP) * TILE, g_tile + pool_base(c) * TILE, rows[c] * TILE * 4, bar);
-}
-template <int K>
-__device__ __forceinline__ void tile_bulk_store(u32* g_tile, const u32* s_dyn, const u32* rows_in, const u32* rows_out) {
-    bulk_s2g(g_tile + W_CSTEP * TILE, s_dyn, Geo<K>::BASE_ROWS * TILE * 4);
-#pragma unroll
-    for (int c = 0; c < K; c++) {
-        const u32 r = rows_in[c] > rows_out[c] ? rows_in[c] : rows_out[c];  // rows freed (zeroed) in this step go back too
-        if (r) bulk_s2g(g_tile + pool_base(c) * TILE, s_dyn + (pool_base(c) - W_CSTEP) * TILE, r * TILE * 4);
-    }
-}
-// The rows a step may newly touch were not loaded (they are zeros in HBM): every lane zeroes them in ITS OWN column of
-// cell c's pool, so the rows that go back hold zeros wherever no record was written.  No barrier needed before the step:
-// a lane only ever reads pool words it wrote or that were loaded.
-__device__ __forceinline__ void column_zero_margin(u32* s_dyn, int lane, int c, u32 rows_in) {
-#pragma unroll
-    for (int i = 0; i < POOL_ROWS_MARGIN; i++) {
-        const int r = (int)rows_in + i;
-        if (r < FJSP_POOL_SLOTS) s_dyn[(pool_base(c) - W_CSTEP + r) * TILE + lane] = 0u;
-    }
-}
-
 // Warp-cooperative auto-reset.  FJSP_MAX_ORDERS == 32 == warp size: for every lane whose episode just ended (ballot),
 // the 32 lanes draw that env's 32 Philox orders in parallel (one order per lane, counter = (global env, episode, lane))
 // and store them into the ending lane's shared-memory column; the ending lane itself re-initialises its scalars.
@@ -207,7 +164,6 @@ struct StepArgs {
     uint8_t* results;        // [N][ACT] or null
     int32_t* infos;          // [N][4] or null
     u32* wire;               // [N][Wire<K>::WORDS]: the WIRE instantiation writes this instead of obs/masks/rewards/flags
-    u32* tile_rows;          // [num_tiles][K] live pool rows per (tile, cell), maintained by the step kernels
     int64_t num_envs, first_env;
     int64_t tile_begin;      // first tile of this launch (host-buffer path steps the batch in pipelined chunks)
     uint64_t seed;
@@ -262,8 +218,7 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u32* s_dyn = reinterpret_cast<u32*>(smem_raw);
     u32* s_out = reinterpret_cast<u32*>(smem_raw + Geo<K>::DYN_BYTES);  // float observations, or wire rows
-    TileTail* tail = reinterpret_cast<TileTail*>(smem_raw + Geo<K>::DYN_BYTES + OUT_TILE_BYTES);
-    uint64_t* bar = &tail->bar;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + Geo<K>::DYN_BYTES + OUT_TILE_BYTES);
 
     const int tid = threadIdx.x;
     const int64_t tile = A.tile_begin + blockIdx.x;
@@ -272,12 +227,11 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
     u32* g_tile = A.state + tile * Geo<K>::TILE_WORDS;
 
     if (tid == 0) mbar_init(bar, 1);
-    if (tid < K) tail->rows_in[tid] = __ldg(A.tile_rows + tile * K + tid), tail->rows_out[tid] = 0u;
     __syncthreads();
-    // bulk async copies (TMA engine) of the tile's dynamically indexed words: orders + the LIVE rows of the tray pool
-    if (tid == 0) tile_bulk_load<K>(s_dyn, g_tile, tail->rows_in, bar);
-#pragma unroll
-    for (int c = 0; c < K; c++) column_zero_margin(s_dyn, tid, c, tail->rows_in[c]);
+    if (tid == 0) {  // ONE bulk async copy (TMA engine) for the dynamically indexed words of the tile
+        mbar_expect_tx(bar, Geo<K>::DYN_BYTES);
+        bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, Geo<K>::DYN_BYTES, bar);
+    }
     // meanwhile: the hot words of the pickup station and of cell 0 (coalesced 32-bit loads, straight into registers)
     // and the action bytes
     TileColumn s{s_dyn + tid - W_CSTEP * TILE, g_tile + tid};
@@ -304,17 +258,6 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
     }
     store_hot(s, h);
     store_cell<K>(s, 0, c0);
-    {   // live pool rows after the step, per cell: max over the tile's envs
-        u32 r = valid ? (u32)pool_rows_used(c0.free_lo, c0.free_hi) : 0u;
-        r = __reduce_max_sync(0xffffffffu, r);
-        if ((tid & 31) == 0 && r) atomicMax(&tail->rows_out[0], r);
-#pragma unroll
-        for (int c = 1; c < K; c++) {
-            u32 rc = valid ? (u32)pool_rows_used(s.ld_hot(cell_word(K, c, 1)), s.ld_hot(cell_word(K, c, 2))) : 0u;
-            rc = __reduce_max_sync(0xffffffffu, rc);
-            if ((tid & 31) == 0 && rc) atomicMax(&tail->rows_out[c], rc);
-        }
-    }
     if (valid) {
         if (WIRE) {
             u32 row[Wire<K>::WORDS];
@@ -348,11 +291,10 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
     u32* g_out = WIRE ? A.wire + tile * TILE * Wire<K>::WORDS : reinterpret_cast<u32*>(A.obs + tile * TILE * Lay<K>::OBS);
     const bool out_bulk = ((nvalid * OUT_ROW_BYTES) & 15) == 0 && ((reinterpret_cast<uintptr_t>(g_out) & 15) == 0);
     if (tid == 0) {
-        tile_bulk_store<K>(g_tile, s_dyn, tail->rows_in, tail->rows_out);
+        bulk_s2g(g_tile + W_CSTEP * TILE, s_dyn, Geo<K>::DYN_BYTES);
         if (out_bulk) bulk_s2g(g_out, s_out, (uint32_t)(nvalid * OUT_ROW_BYTES));
         bulk_commit();
     }
-    if (tid < K) A.tile_rows[tile * K + tid] = tail->rows_out[tid];
     if (!out_bulk) {  // ragged last tile or unaligned caller buffer: cooperative coalesced 32-bit stores
         for (int i = tid; i < nvalid * (OUT_ROW_BYTES / 4); i += TILE) g_out[i] = s_out[i];
     }
@@ -376,8 +318,7 @@ __global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_step_
     u32* s_dyn = reinterpret_cast<u32*>(smem_raw);
     u32* s_out = reinterpret_cast<u32*>(smem_raw + Geo<K>::DYN_BYTES);
     u32* s_x = reinterpret_cast<u32*>(smem_raw + Geo<K>::DYN_BYTES + OUT_TILE_BYTES);
-    TileTail* tail = reinterpret_cast<TileTail*>(smem_raw + Geo<K>::DYN_BYTES + OUT_TILE_BYTES + Geo<K>::X_BYTES);
-    uint64_t* bar = &tail->bar;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + Geo<K>::DYN_BYTES + OUT_TILE_BYTES + Geo<K>::X_BYTES);
 
     const int tid = threadIdx.x;
     const int c = tid / TILE, e = tid % TILE;  // c is uniform over a warp
@@ -387,13 +328,14 @@ __global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_step_
     u32* g_tile = A.state + tile * Geo<K>::TILE_WORDS;
 
     if (tid == 0) mbar_init(bar, 1);
-    if (tid < K) tail->rows_in[tid] = __ldg(A.tile_rows + tile * K + tid), tail->rows_out[tid] = 0u;
     for (int i = tid; i < Xl<K>::WORDS * TILE; i += NT) s_x[i] = 0u;
     if (WIRE)
         for (int i = tid; i < OUT_TILE_BYTES / 4; i += NT) s_out[i] = 0u;  // wire rows are assembled with ORs
     __syncthreads();
-    if (tid == 0) tile_bulk_load<K>(s_dyn, g_tile, tail->rows_in, bar);  // orders + the LIVE rows of each cell's tray pool
-    column_zero_margin(s_dyn, e, c, tail->rows_in[c]);
+    if (tid == 0) {
+        mbar_expect_tx(bar, Geo<K>::DYN_BYTES);
+        bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, Geo<K>::DYN_BYTES, bar);
+    }
     TileColumnShared s;
     s.dyn = s_dyn + e - W_CSTEP * TILE, s.hot = g_tile + e;
     XchgColumn x{s_x + e};
@@ -448,11 +390,6 @@ __global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_step_
     }
     if (c == 0) store_hot(s, L.h);
     store_cell<K>(s, c, L.hc);
-    {   // live pool rows of this warp's cell after the step
-        u32 r = valid ? (u32)pool_rows_used(L.hc.free_lo, L.hc.free_hi) : 0u;
-        r = __reduce_max_sync(0xffffffffu, r);
-        if ((tid & 31) == 0 && r) atomicMax(&tail->rows_out[c], r);
-    }
     __syncthreads();
     // ---- output rows, one 32-byte piece per lane: mask bytes [32c, 32c+32), action columns [8c, 8c+8)
     if (valid) {
@@ -494,35 +431,14 @@ __global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_step_
     u32* g_out = WIRE ? A.wire + tile * TILE * Wire<K>::WORDS : reinterpret_cast<u32*>(A.obs + tile * TILE * Lay<K>::OBS);
     const bool out_bulk = ((nvalid * OUT_ROW_BYTES) & 15) == 0 && ((reinterpret_cast<uintptr_t>(g_out) & 15) == 0);
     if (tid == 0) {
-        tile_bulk_store<K>(g_tile, s_dyn, tail->rows_in, tail->rows_out);
+        bulk_s2g(g_tile + W_CSTEP * TILE, s_dyn, Geo<K>::DYN_BYTES);
         if (out_bulk) bulk_s2g(g_out, s_out, (uint32_t)(nvalid * OUT_ROW_BYTES));
         bulk_commit();
     }
-    if (tid < K) A.tile_rows[tile * K + tid] = tail->rows_out[tid];
     if (!out_bulk) {
         for (int i = tid; i < nvalid * (OUT_ROW_BYTES / 4); i += NT) g_out[i] = s_out[i];
     }
     if (tid == 0) bulk_wait_read0();
-}
-
-// Live pool rows per (tile, cell) from the free bitmaps (after reset / state load / the K-steps-per-launch kernel, which
-// move whole tiles).  One CTA of 64 threads per tile.
-template <int K>
-__global__ void __launch_bounds__(TILE) fjsp_tile_rows_kernel(const u32* state, int64_t num_envs, u32* tile_rows) {
-    __shared__ u32 s_rows[K];
-    const int tid = threadIdx.x;
-    const int64_t env = (int64_t)blockIdx.x * TILE + tid;
-    if (tid < K) s_rows[tid] = 0u;
-    __syncthreads();
-    const u32* col = state + (int64_t)blockIdx.x * Geo<K>::TILE_WORDS + tid;
-#pragma unroll
-    for (int c = 0; c < K; c++) {
-        u32 r = env < num_envs ? (u32)pool_rows_used(col[cell_word(K, c, 1) * TILE], col[cell_word(K, c, 2) * TILE]) : 0u;
-        r = __reduce_max_sync(0xffffffffu, r);
-        if ((tid & 31) == 0 && r) atomicMax(&s_rows[c], r);
-    }
-    __syncthreads();
-    if (tid < K) tile_rows[(int64_t)blockIdx.x * K + tid] = s_rows[tid];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -120,13 +120,6 @@ class BatchedFJSPEnv:
     def launch_count(self) -> int:
         return int(self._L.fjsp_launch_count(self._h))
 
-    def live_pool_rows(self):
-        """(live, capacity): tray-pool rows (256 B each) the step kernels move per step over all tiles, and the count if
-        every pool were full.  Synchronises."""
-        live, cap = C.c_int64(), C.c_int64()
-        abi.check(self._L.fjsp_live_pool_rows(self._h, C.byref(live), C.byref(cap)))
-        return int(live.value), int(cap.value)
-
     @property
     def state_bytes_per_env(self) -> int:
         return int(self._L.fjsp_state_bytes(self._h))

@@ -15,11 +15,9 @@ reps = 4
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
 
-def timed(label, fn, envs, agents, io_bytes, env_obj, fixed_state):
+def timed(label, fn, envs, agents, nbytes):
     for _ in range(2):
         fn(0)
-    live, cap = env_obj.live_pool_rows()
-    nbytes = io_bytes + 2 * (fixed_state + 4.0 * live / max(1, cap // 64 // env_obj.cells) )
     torch.cuda.synchronize()
     e0.record()
     for i in range(reps):
@@ -27,17 +25,17 @@ def timed(label, fn, envs, agents, io_bytes, env_obj, fixed_state):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    print("%s: %d envs, %.3f ms/launch, %.3e agent-steps/s, %.0f B moved per env-step, %.0f GB/s algorithmic" % (
-        label, envs, ms, envs * agents / (ms * 1e-3), nbytes, envs * nbytes / (ms * 1e-3) / 1e9))
+    print("%s: %d envs, %.3f ms/launch, %.3e agent-steps/s, %.0f GB/s algorithmic" % (
+        label, envs, ms, envs * agents / (ms * 1e-3), envs * nbytes / (ms * 1e-3) / 1e9))
 
 
 env = BatchedFJSPEnv(n1, seed=3)
 env.reset()
 env.rollout_random(60)
 acts = [env.random_actions(100 + t, out=torch.empty((n1, 8), dtype=torch.uint8, device=env.device)) for t in range(reps)]
-timed("step<1,float>", lambda i: env.step(acts[i]), n1, 8, 228, env, 256)
+timed("step<1,float>", lambda i: env.step(acts[i]), n1, 8, 1252)
 wire = torch.zeros((n1, env.dims["wire_words"]), dtype=torch.int32, device=env.device)
-timed("step<1,wire>", lambda i: env.step_wire(acts[i], wire), n1, 8, 8 + 64, env, 256)
+timed("step<1,wire>", lambda i: env.step_wire(acts[i], wire), n1, 8, 8 + 64 + 1024)
 del env, acts, wire
 
 cfg = abi.default_config()
@@ -47,5 +45,5 @@ e4.reset()
 e4.rollout_random(60)
 d = e4.dims
 a4 = [e4.random_actions(100 + t, out=torch.empty((n4, d["act"]), dtype=torch.uint8, device=e4.device)) for t in range(reps)]
-b4 = d["act"] + 4 * d["obs"] + d["mask"] + 4 * d["act"] + 4
-timed("step<4,float>", lambda i: e4.step(a4[i]), n4, d["agents"], b4, e4, 4 * (d["state_words"] - 256))
+b4 = d["act"] + 4 * d["obs"] + d["mask"] + 4 * d["act"] + 4 + 8 * d["state_words"]
+timed("step<4,float>", lambda i: e4.step(a4[i]), n4, d["agents"], b4)

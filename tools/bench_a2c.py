@@ -43,5 +43,15 @@ if rank == 0:
                       "mean_step_reward": tr.mean_reward(), "params": tr.net.num_parameters(), "gemm_precision": "tf32" if args.tf32 else "fp32", "cuda_graph_rollout": not args.no_graph,
                       "critic_loss": float(tr.stats["critic_loss"]), "update_graph": tr._ugraph is not None,
                       "update_graph_error": tr.update_graph_error}))
+sys.stdout.flush()
 if world > 1:
-    dist.destroy_process_group()
+    # every rank is done (max_over_ranks above is a collective).  Tearing the NCCL communicator down while CUDA graphs that
+    # captured its all-reduces are still alive was seen to hang at exit (2 ranks, scaled shop), so: drop the graphs, sync,
+    # barrier, and leave without the communicator teardown.
+    del tr
+    import gc
+
+    gc.collect()
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    os._exit(0)

@@ -11,12 +11,12 @@ from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv, abi
 
 n1 = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 n4 = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 18
-reps = 4
+reps = int(os.environ.get("PROFILE_REPS", "4"))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
 
 def timed(label, fn, envs, agents, nbytes):
-    for _ in range(2):
+    for _ in range(int(os.environ.get("PROFILE_WARM", "2"))):
         fn(0)
     torch.cuda.synchronize()
     e0.record()

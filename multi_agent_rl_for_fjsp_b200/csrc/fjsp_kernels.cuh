@@ -226,9 +226,8 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
     const bool valid = env < A.num_envs;
     u32* g_tile = A.state + tile * Geo<K>::TILE_WORDS;
 
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
     if (tid == 0) {  // ONE bulk async copy (TMA engine) for the dynamically indexed words of the tile
+        mbar_init(bar, 1);
         mbar_expect_tx(bar, Geo<K>::DYN_BYTES);
         bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, Geo<K>::DYN_BYTES, bar);
     }
@@ -241,6 +240,7 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
     load_cell<K>(s, 0, c0);
     int a[Lay<K>::ACT];
     load_actions<K>(A.actions, env, valid, a);
+    __syncthreads();  // the mbarrier is initialised for everyone
     mbar_wait(bar, 0);
 
     // padding lanes of a ragged last tile are inert: their words travel through unchanged
@@ -327,12 +327,8 @@ __global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_step_
     const bool valid = env < A.num_envs;
     u32* g_tile = A.state + tile * Geo<K>::TILE_WORDS;
 
-    if (tid == 0) mbar_init(bar, 1);
-    for (int i = tid; i < Xl<K>::WORDS * TILE; i += NT) s_x[i] = 0u;
-    if (WIRE)
-        for (int i = tid; i < OUT_TILE_BYTES / 4; i += NT) s_out[i] = 0u;  // wire rows are assembled with ORs
-    __syncthreads();
-    if (tid == 0) {
+    if (tid == 0) {  // the tile's bulk copy is under way before anything else happens in the CTA
+        mbar_init(bar, 1);
         mbar_expect_tx(bar, Geo<K>::DYN_BYTES);
         bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, Geo<K>::DYN_BYTES, bar);
     }
@@ -350,6 +346,10 @@ __global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_step_
 #pragma unroll
         for (int i = 0; i < 7; i++) a7[i] = valid ? (int)__ldg(arow + 1 + 7 * c + i) : 0;
     }
+    for (int i = tid; i < Xl<K>::WORDS * TILE; i += NT) s_x[i] = 0u;
+    if (WIRE)
+        for (int i = tid; i < OUT_TILE_BYTES / 4; i += NT) s_out[i] = 0u;  // wire rows are assembled with ORs
+    __syncthreads();  // mbarrier initialised and exchange area zeroed for everyone
     mbar_wait(bar, 0);
 
     if (valid) cells_begin<K>(s, x, P, L, a0, a7);

@@ -221,3 +221,28 @@ def test_gpu_a2c_trains_on_the_scaled_shop():
     assert (acts[:, :, 1:, 0] == 0).all() and (acts[:, :, 0, 0] != 0).any()
     assert any(not torch.equal(a, b.detach()) for a, b in zip(before, tr.net.parameters()))
     assert env.launch_count >= T   # eager warm-up pass; later rollouts replay the captured graph
+
+
+@pytest.mark.parametrize("name", ["k2_mixed", "k3_pack_cap3", "k4_heuristic"])
+def test_gpu_replays_scaled_vectors(name):
+    """The scaled-shop regression vectors (tests/golden/scaled/) through fjsp_reset / fjsp_step / fjsp_export_state_cell."""
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+    from tests.test_scaled_golden import replay_scaled
+
+    class GpuSingleK:
+        def __init__(self, ocfg):
+            self.env = BatchedFJSPEnv(1, config=_abi_cfg(ocfg), autoreset=False)
+
+        def reset(self, orders):
+            obs, masks = self.env.reset(orders=np.asarray(orders)[None, :, :])
+            return obs[0].cpu().numpy(), masks[0].cpu().numpy()
+
+        def step(self, actions):
+            a = torch.as_tensor(np.asarray(actions, dtype=np.uint8)[None, :], device=self.env.device)
+            obs, rew, term, trunc, masks = self.env.step(a)
+            return obs[0].cpu().numpy(), masks[0].cpu().numpy(), rew[0].cpu().numpy(), self.env.flags[0].cpu().numpy()
+
+        def export(self, cell=0):
+            return self.env.export_state(0, cell)
+
+    assert replay_scaled(name, lambda cfg: GpuSingleK(cfg), exact_rewards=False) > 300

@@ -4,6 +4,7 @@ product library's HOST function fjsp_wire_decode and must give bit for bit the f
 on the reference's own golden trajectories (so the decoded tensors are also checked against the reference) and on
 scaled shops under a policy that packages products (progress table, int8 queue lengths, negative rewards)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -101,3 +102,76 @@ def test_wire_decode_partial_outputs_and_errors():
     assert (obs[:, :11] == 0).all()
     assert L.fjsp_wire_decode(C.byref(cfg), None, 5, obs.ctypes.data, None, None, None, 1) != 0
     assert L.fjsp_wire_row_bytes(0) == 0 and L.fjsp_wire_row_bytes(5) == 0 and L.fjsp_wire_row_bytes(1) == 64
+
+
+def numpy_decode(cfg, rows):
+    """Independent NumPy statement of the wire format (include/fjsp_b200.h) — not the library's code."""
+    k = int(cfg.num_cells)
+    d = dims(k)
+    A, obs_n, mask_n, act_n = d["agents"], d["obs"], d["mask"], d["act"]
+    n = rows.shape[0]
+    b = rows.view(np.uint8).reshape(n, -1)
+    obsw, mw = (obs_n + 3) // 4, mask_n // 32
+    obs = b[:, :obs_n].astype(np.float32)
+    pos = np.array([[cfg.pos[i][0], cfg.pos[i][1]] for i in range(5)] + [[cfg.pos[0][0], cfg.pos[0][1]]] * 3, np.float32)
+    prog = np.zeros(256, np.float32)
+    prog[1:] = ((1.0 / np.arange(1, 256, dtype=np.float64)) * 100.0).astype(np.float32)
+    for c in range(k):
+        base = 7 + 31 * c
+        obs[:, base + 4] = pos[b[:, base + 4] & 7, 0]
+        obs[:, base + 5] = pos[b[:, base + 5] & 7, 1]
+        for i in range(4):
+            obs[:, base + 20 + 3 * i] = prog[b[:, base + 20 + 3 * i]]
+            obs[:, base + 21 + 3 * i] = b[:, base + 21 + 3 * i].view(np.int8).astype(np.float32)
+    bits = rows[:, obsw:obsw + mw]
+    masks = ((bits[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).astype(np.int8).reshape(n, mask_n)
+    gw = rows[:, obsw + mw]
+    g = ((gw << np.uint32(8)).view(np.int32) >> 8).astype(np.int64)
+    fb = gw >> np.uint32(24)
+    flags = np.stack([fb & 1, (fb >> 1) & 1, (fb >> 2) & 3, (fb >> 4) & 1], axis=1).astype(np.uint8)
+    local = rows[:, obsw + mw + 1:obsw + mw + 1 + act_n // 2].copy().view(np.int16).reshape(n, act_n).astype(np.int64)
+    num = (g[:, None] + A * local).astype(np.float32)
+    rew = (num / np.float32(10 * A)).astype(np.float32)
+    rew[:, A:] = 0.0
+    return obs, masks, rew, flags
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4])
+def test_wire_decode_on_arbitrary_rows_matches_numpy_statement(k):
+    """Every byte value in every field (int8 wrap of queue lengths, all 256 progress indices, out-of-range station
+    indices, negative numerators, all flag bits): library decoder (AVX2 + streaming stores on aligned outputs, plain
+    stores on unaligned ones, several thread splits) == an independent NumPy statement of the format."""
+    cfg = abi.default_config()
+    cfg.num_cells = k
+    rs = np.random.RandomState(10 + k)
+    n = 4099
+    words = abi.dims(k)["wire_words"]
+    rows = rs.randint(0, 1 << 32, size=(n, words), dtype=np.uint64).astype(np.uint32)
+    rows[:64] = 0
+    rows[64:128] = 0xFFFFFFFF
+    want = numpy_decode(cfg, rows)
+    for threads, offset in ((1, 0), (3, 0), (7, 0), (1, 4), (2, 16)):
+        got = decode(cfg, rows, threads=threads, offset=offset)
+        for name, a, b in zip(("obs", "masks", "rewards", "flags"), got, want):
+            assert np.array_equal(a, b), (k, threads, offset, name, np.argwhere(a != b)[:4])
+
+
+def test_wire_decode_generic_body_equals_avx2_body():
+    """The portable decoder body (FJSP_DECODE_GENERIC=1, read once per process) in a subprocess == this process's."""
+    import subprocess
+    import sys
+
+    if abi.lib() is None:
+        pytest.skip("library not built")
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from tests.test_wire_format import decode, abi\n"
+        "cfg = abi.default_config(); cfg.num_cells = 4\n"
+        "rows = np.random.RandomState(5).randint(0, 1 << 32, size=(1000, abi.dims(4)['wire_words']), dtype=np.uint64).astype(np.uint32)\n"
+        "import hashlib; print(hashlib.sha256(b''.join(np.ascontiguousarray(x).tobytes() for x in decode(cfg, rows, threads=2))).hexdigest())\n"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for env in ({}, {"FJSP_DECODE_GENERIC": "1"}):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, check=True)
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1] and len(outs[0]) == 64

@@ -284,6 +284,15 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * E * 8 * Ke / e2e_s
+    # the same pipeline delivering the wire rows undecoded (for callers that consume the integers): reported, not the headline
+    for i in range(2):
+        env.step_host_wire(host_actions[i % len(host_actions)])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        env.step_host_wire(host_actions[i % len(host_actions)])
+    torch.cuda.synchronize()
+    e2e_wire_s = max_over_ranks(time.perf_counter() - t0)
     wire_row = 4 * env.dims["wire_words"]
     # the e2e path's own roofline: this box's pinned D2H bandwidth on the wire rows (64 B/env)
     hb = env.host_buffers()
@@ -433,6 +442,8 @@ def run_ours(args):
                     "steps": Ke, "ms_per_step": e2e_s / Ke * 1e3,
                     "api": "fjsp_step_host (pinned host buffers; float32 obs/rewards, int8 masks, u8 flags delivered)",
                     "wire_row_bytes": wire_row, "decoded_bytes_per_step": E * (152 + 32 + 32 + 4),
+                    "undecoded_wire_rows_variant": {"api": "fjsp_step_host_wire (same pipeline, rows delivered as they are)",
+                                                    "value": world * E * 8 * Ke / e2e_wire_s, "ms_per_step": e2e_wire_s / Ke * 1e3},
                     "decode_threads": decode_threads, "pcie_d2h_gbs_measured": d2h_gbs, "host_cpus_bound": len(numa_cpus),
                     "pcie_bound_frac": (E * wire_row / (d2h_gbs * 1e9)) / (e2e_s / Ke)},
             "gpu_launches": launches, "clocks": clocks,

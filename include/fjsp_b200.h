@@ -176,6 +176,11 @@ int fjsp_step(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, 
 int fjsp_step_host(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, float* rewards,
                    uint8_t* flags, int autoreset, void* stream);
 
+/* The same pipelined host-buffer step WITHOUT the decode: wire = host u32[N][FJSP_WIRE_WORDS_K(K)] (pinned for full
+ * speed) receives the wire rows; the caller decodes them (fjsp_wire_decode) where and when it needs the tensors, or
+ * consumes the integers as they are.  Synchronised on return. */
+int fjsp_step_host_wire(FjspHandle* h, const uint8_t* actions, uint32_t* wire, int autoreset, void* stream);
+
 /* Host threads fjsp_step_host may use for the decode (including the caller's); 0 = every CPU the process may run on
  * (default).  Several handles / ranks on one host should share the cores out.  Call before the first fjsp_step_host. */
 int fjsp_set_decode_threads(FjspHandle* h, int threads);

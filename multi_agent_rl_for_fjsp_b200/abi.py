@@ -72,7 +72,7 @@ EXPORTS = [
     "fjsp_last_error", "fjsp_abi_version", "fjsp_default_config", "fjsp_create", "fjsp_destroy", "fjsp_num_envs",
     "fjsp_state_bytes", "fjsp_state_ptr", "fjsp_reset", "fjsp_step", "fjsp_step_host", "fjsp_random_actions",
     "fjsp_rollout_random", "fjsp_export_state", "fjsp_export_state_cell", "fjsp_export_packed", "fjsp_launch_count",
-    "fjsp_num_cells", "fjsp_step_wire", "fjsp_wire_decode", "fjsp_wire_row_bytes", "fjsp_set_decode_threads",
+    "fjsp_num_cells", "fjsp_step_wire", "fjsp_step_host_wire", "fjsp_wire_decode", "fjsp_wire_row_bytes", "fjsp_set_decode_threads",
     "fjsp_state_total_bytes", "fjsp_state_save", "fjsp_state_load",
     "fjsp_a2c_sample", "fjsp_a2c_counter_add", "fjsp_a2c_gae", "fjsp_cells_pack_actions", "fjsp_cells_unpack_views",
 ]
@@ -144,6 +144,7 @@ def lib() -> C.CDLL:
     L.fjsp_export_packed.argtypes = [vp, i64, vp]
     L.fjsp_num_cells.restype, L.fjsp_num_cells.argtypes = C.c_int, [vp]
     L.fjsp_set_decode_threads.argtypes = [vp, C.c_int]
+    L.fjsp_step_host_wire.argtypes = [vp, vp, vp, C.c_int, vp]
     L.fjsp_step_wire.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
     L.fjsp_wire_decode.argtypes = [C.POINTER(FjspConfig), vp, i64, vp, vp, vp, vp, C.c_int]
     L.fjsp_wire_row_bytes.restype, L.fjsp_wire_row_bytes.argtypes = C.c_size_t, [C.c_int]

@@ -299,11 +299,9 @@ static int ensure_staging(FjspHandle* h) {
 // into the handle's pinned staging.  As soon as a chunk has landed, the handle's host threads decode it into the
 // caller's obs/masks/rewards/flags while later chunks are still computing / crossing PCIe; envs are independent, so
 // chunks may run in any order.  Ordered after prior work on `stream`, and `stream` is ordered after it on return.
-int fjsp_step_host(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, float* rewards, uint8_t* flags, int autoreset,
-                   void* stream) {
-    if (!h) return fail("handle is NULL");
-    if (!actions || !obs || !masks || !rewards || !flags) return fail("host buffers must not be NULL");
-    if (reinterpret_cast<uintptr_t>(masks) & 7) return fail("masks must be 8-byte aligned");
+// wire_out != NULL: the rows land in the caller's host buffer and are not decoded (fjsp_step_host_wire)
+static int step_host_impl(FjspHandle* h, const uint8_t* actions, u32* wire_out, float* obs, int8_t* masks, float* rewards, uint8_t* flags,
+                          int autoreset, void* stream) {
     DeviceGuard g(h->device);
     if (int rc = ensure_staging(h)) return rc;
     cudaStream_t user = (cudaStream_t)stream;
@@ -332,12 +330,16 @@ int fjsp_step_host(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* ma
         DISPATCH_K(h->cells, launch_step<K, true>(h, A, (unsigned)(t1 - t0), st))
         h->launches++;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(h->h_wire + e0 * ww, h->d_wire + e0 * ww, n * ww * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync((wire_out ? wire_out : h->h_wire) + e0 * ww, h->d_wire + e0 * ww, n * ww * sizeof(u32), cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(h->cev[c], st));
     }
     for (int i = 0; i < 2; i++) {
         CK(cudaEventRecord(h->hev[i], h->hs[i]));
         CK(cudaStreamWaitEvent(user, h->hev[i], 0));
+    }
+    if (wire_out) {  // no decode: wait for the copies and return
+        for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(h->hs[i]));
+        return 0;
     }
     const int64_t grain = h->pool->size() > 0 ? (env_grain > 0 ? env_grain : 2048) : (int64_t)1 << 40;
     const double t_enq = timing ? now() : 0.0;
@@ -361,6 +363,20 @@ int fjsp_step_host(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* ma
         fprintf(stderr, " | decoded at %.3f ms (%d workers, grain %lld)\n", now() - t_in, h->pool->size(), (long long)grain);
     }
     return 0;
+}
+
+int fjsp_step_host(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, float* rewards, uint8_t* flags, int autoreset,
+                   void* stream) {
+    if (!h) return fail("handle is NULL");
+    if (!actions || !obs || !masks || !rewards || !flags) return fail("host buffers must not be NULL");
+    if (reinterpret_cast<uintptr_t>(masks) & 7) return fail("masks must be 8-byte aligned");
+    return step_host_impl(h, actions, nullptr, obs, masks, rewards, flags, autoreset, stream);
+}
+
+int fjsp_step_host_wire(FjspHandle* h, const uint8_t* actions, uint32_t* wire, int autoreset, void* stream) {
+    if (!h) return fail("handle is NULL");
+    if (!actions || !wire) return fail("host buffers must not be NULL");
+    return step_host_impl(h, actions, wire, nullptr, nullptr, nullptr, nullptr, autoreset, stream);
 }
 
 int fjsp_set_decode_threads(FjspHandle* h, int threads) {

@@ -246,6 +246,18 @@ class BatchedFJSPEnv:
         self._t += 1
         return hb["obs"].numpy(), hb["masks"].numpy(), hb["rewards"].numpy(), hb["flags"].numpy()
 
+    def step_host_wire(self, actions: torch.Tensor):
+        """Host-buffer step that delivers the compact wire rows (int32 [N, dims["wire_words"]], pinned) without decoding
+        them; `actions`: pinned uint8 CPU tensor [N, act_dim].  ``abi.lib().fjsp_wire_decode`` turns rows into tensors."""
+        hb = self.host_buffers()
+        if "wire" not in hb:
+            hb["wire"] = torch.zeros((self.num_envs, self.dims["wire_words"]), dtype=torch.int32).pin_memory()
+        assert actions.device.type == "cpu" and actions.dtype == torch.uint8 and actions.is_contiguous()
+        assert tuple(actions.shape) == (self.num_envs, self.act_dim)
+        abi.check(self._L.fjsp_step_host_wire(self._h, _ptr(actions), _ptr(hb["wire"]), int(self.autoreset), self._stream()))
+        self._t += 1
+        return hb["wire"]
+
     # ------------------------------------------------------------------ snapshot / restore
     def save_state(self) -> torch.Tensor:
         """Copy of the whole packed state (int32 tensor on the env's device)."""

@@ -225,6 +225,11 @@ def test_gpu_host_buffer_step_pipelined_chunks_and_decode_threads():
                                              f2.ctypes.data, 4))
         assert np.array_equal(o2, hobs) and np.array_equal(m2, hmasks) and np.array_equal(r2, hrew) and np.array_equal(f2, hflags)
     assert torch.equal(a.save_state(), b.save_state()) and torch.equal(a.save_state(), c.save_state())
+    # host-buffer step that delivers the rows undecoded == the device rows of the same step
+    acts = a.random_actions(99)
+    c.step_wire(acts, wire)
+    hw = b.step_host_wire(acts.cpu().pin_memory())
+    assert torch.equal(hw, wire.cpu())
 
 
 def test_gpu_fault_flag_on_restart_with_waiters():

@@ -138,10 +138,12 @@ def test_gpu_scaled_heuristic_cells_complete_orders():
             assert not df, (i, c, df[:4])
 
 
-def test_gpu_scaled_host_buffer_step_matches_device_step():
+@pytest.mark.parametrize("k,n", [(3, 333), (4, 20001), (2, 4097)])
+def test_gpu_scaled_host_buffer_step_matches_device_step(k, n):
+    """Wire rows of a K-cell shop through the pipelined host path (ragged last tile; with and without decode workers)."""
     from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
 
-    k, n, seed = 3, 333, 5
+    seed = 5
     cfg = _abi_cfg(ocfg_k(k))
     a = BatchedFJSPEnv(n, config=cfg, seed=seed)
     b = BatchedFJSPEnv(n, config=cfg, seed=seed)

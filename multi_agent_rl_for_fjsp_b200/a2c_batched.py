@@ -17,6 +17,10 @@ GEMMs are library calls (cuBLAS through torch): at these sizes they are launch-l
 Data parallelism: every rank owns an env shard; ONE flat all-reduce (654,366 fp32 = 2.62 MB, NCCL over NVLink) of the
 gradients per update, plus one tiny all-reduce of the advantage moments so normalisation is over the GLOBAL batch.
 The env step is one kernel launch per step that writes observations straight into the rollout buffer (``step_into``).
+
+Scaled shop (K cells): wrap the env in ``env.CellViewEnv`` — every (env, cell) becomes one row of the
+reference's 8-agent layout, so this trainer runs unchanged and the 8 actors + critic are shared by the cells; the pickup
+station acts through the row of cell 0 (elsewhere its mask allows action 0 only: constant log-probability, no gradient).
 """
 from __future__ import annotations
 

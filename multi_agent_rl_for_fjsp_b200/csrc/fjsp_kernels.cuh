@@ -122,6 +122,10 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
                  : "memory");
 }
+// L2 prefetch of a whole tile that a later CTA of this SM will load (takes the HBM latency off that CTA's start-up)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -168,6 +172,8 @@ struct StepArgs {
     int64_t tile_begin;      // first tile of this launch (host-buffer path steps the batch in pipelined chunks)
     uint64_t seed;
     int32_t num_orders, autoreset;
+    int32_t prefetch_tiles;  // cell-parallel kernel: L2-prefetch the tile this many CTAs ahead (0 = off)
+    int32_t prefetch_tiles_env;  // the same for the thread-per-env kernel
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -230,6 +236,10 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
         mbar_init(bar, 1);
         mbar_expect_tx(bar, Geo<K>::DYN_BYTES);
         bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, Geo<K>::DYN_BYTES, bar);
+    }
+    if (tid == 32 && A.prefetch_tiles_env > 0) {  // L2 prefetch of the tile a later CTA of this SM will load
+        const int64_t nt = (int64_t)blockIdx.x + A.prefetch_tiles_env;
+        if (nt < (int64_t)gridDim.x) bulk_prefetch_l2(g_tile + (int64_t)A.prefetch_tiles_env * Geo<K>::TILE_WORDS, Geo<K>::TILE_BYTES);
     }
     // meanwhile: the hot words of the pickup station and of cell 0 (coalesced 32-bit loads, straight into registers)
     // and the action bytes
@@ -331,6 +341,12 @@ __global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_step_
         mbar_init(bar, 1);
         mbar_expect_tx(bar, Geo<K>::DYN_BYTES);
         bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, Geo<K>::DYN_BYTES, bar);
+    }
+    if (tid == 32 && A.prefetch_tiles > 0) {
+        // the tile this SM will work on about one CTA generation from now goes to L2 meanwhile: its hot-word loads and
+        // its bulk copy then start from L2 instead of HBM (with 2 CTAs per SM the start-up latency is not hidden otherwise)
+        const int64_t nt = (int64_t)blockIdx.x + A.prefetch_tiles;
+        if (nt < (int64_t)gridDim.x) bulk_prefetch_l2(g_tile + (int64_t)A.prefetch_tiles * Geo<K>::TILE_WORDS, Geo<K>::TILE_BYTES);
     }
     TileColumnShared s;
     s.dyn = s_dyn + e - W_CSTEP * TILE, s.hot = g_tile + e;

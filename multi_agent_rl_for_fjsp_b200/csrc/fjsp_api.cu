@@ -91,6 +91,8 @@ static cudaError_t set_smem_attrs() {
             e = cudaFuncSetAttribute(fjsp_step_cells_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::CELLS_SMEM_BYTES);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(fjsp_step_cells_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::CELLS_WIRE_SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(fjsp_rollout_cells_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::ROLLOUT_CELLS_SMEM_BYTES);
     }
     return e;
 }
@@ -107,6 +109,20 @@ static void launch_step(const FjspHandle* h, const StepArgs& A, unsigned tiles, 
         }
     }
     fjsp_step_kernel<K, WIRE><<<tiles, TILE, WIRE ? Geo<K>::STEP_WIRE_SMEM_BYTES : Geo<K>::STEP_SMEM_BYTES, st>>>(h->P, A);
+}
+
+template <int K>
+static void launch_rollout(const FjspHandle* h, int steps, uint64_t seed, uint64_t t0, unsigned long long* stats, cudaStream_t st) {
+    static const bool per_env = getenv("FJSP_STEP_PER_ENV") != nullptr;
+    if constexpr (K >= 2) {
+        if (!per_env) {
+            fjsp_rollout_cells_kernel<K><<<(unsigned)h->num_tiles, TILE * K, Geo<K>::ROLLOUT_CELLS_SMEM_BYTES, st>>>(
+                h->P, h->state, h->num_envs, h->first_env, seed, t0, steps, h->num_orders, stats);
+            return;
+        }
+    }
+    fjsp_rollout_kernel<K><<<(unsigned)h->num_tiles, TILE, Geo<K>::ROLLOUT_SMEM_BYTES, st>>>(h->P, h->state, h->num_envs, h->first_env, seed,
+                                                                                            t0, steps, h->num_orders, stats);
 }
 
 extern "C" {
@@ -417,9 +433,7 @@ int fjsp_rollout_random(FjspHandle* h, int steps, uint64_t seed, uint64_t t0, ui
     if (!stats || (reinterpret_cast<uintptr_t>(stats) & 7)) return fail("stats must be an 8-byte aligned device pointer (8 x u64)");
     if (seed != h->seed) return fail("rollout seed must equal the seed of the last fjsp_reset (one Philox key per handle)");
     DeviceGuard g(h->device);
-    DISPATCH_K(h->cells, fjsp_rollout_kernel<K><<<(unsigned)h->num_tiles, TILE, Geo<K>::ROLLOUT_SMEM_BYTES, (cudaStream_t)stream>>>(
-                             h->P, h->state, h->num_envs, h->first_env, seed, t0, steps, h->num_orders,
-                             reinterpret_cast<unsigned long long*>(stats)))
+    DISPATCH_K(h->cells, launch_rollout<K>(h, steps, seed, t0, reinterpret_cast<unsigned long long*>(stats), (cudaStream_t)stream))
     h->launches++;
     CK(cudaGetLastError());
     return 0;

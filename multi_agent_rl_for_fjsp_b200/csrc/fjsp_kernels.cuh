@@ -44,6 +44,7 @@ struct Geo {
     static constexpr int CELLS_SMEM_BYTES = DYN_BYTES + OBS_TILE_BYTES + X_BYTES + 16;       // 115,472 for K = 4: 2 CTAs / SM
     static constexpr int CELLS_WIRE_SMEM_BYTES = DYN_BYTES + WIRE_TILE_BYTES + X_BYTES + 16;
     static constexpr int CELLS_CTAS_PER_SM = K == 2 ? 3 : 2;
+    static constexpr int ROLLOUT_CELLS_SMEM_BYTES = DYN_BYTES + X_BYTES + 16;
 };
 
 // One env of a tile inside a kernel: the dynamically indexed words live in shared memory, column `lane` of the
@@ -541,6 +542,115 @@ __global__ void __launch_bounds__(TILE) fjsp_rollout_kernel(const __grid_constan
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
         if ((tid & 31) == 0) atomicAdd(&s_acc[j], x);
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+        bulk_s2g(g_tile + W_CSTEP * TILE, s_dyn, Geo<K>::DYN_BYTES);
+        bulk_commit();
+    }
+    if (tid < 6) atomicAdd(&stats[tid], s_acc[tid]);
+    if (tid == 0) bulk_wait_read0();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rollout, cell-parallel (K >= 2): the K-steps-per-launch kernel with one thread per (env, cell).  The tile and the
+// exchange area stay in shared memory for the whole launch, every lane keeps its cell's hot words (and its mirror of
+// the pickup station's) in registers; per step: Philox actions for the lane's own agents, the three phases of the
+// cell-parallel step (no observation), the cooperative reset by the two warps of cell 0, and a fresh exchange area.
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_rollout_cells_kernel(const __grid_constant__ Params P, u32* state,
+                                                                                                int64_t num_envs, int64_t first_env,
+                                                                                                uint64_t seed, uint64_t t0, int steps,
+                                                                                                int num_orders, unsigned long long* stats) {
+    constexpr int NT = TILE * K;
+    constexpr int AG = Lay<K>::AGENTS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    u32* s_dyn = reinterpret_cast<u32*>(smem_raw);
+    u32* s_x = reinterpret_cast<u32*>(smem_raw + Geo<K>::DYN_BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + Geo<K>::DYN_BYTES + Geo<K>::X_BYTES);
+    __shared__ unsigned long long s_acc[6];
+    const int tid = threadIdx.x;
+    const int c = tid / TILE, e = tid % TILE;
+    const int64_t tile = blockIdx.x;
+    const int64_t env = tile * TILE + e;
+    const bool valid = env < num_envs;
+    u32* g_tile = state + tile * Geo<K>::TILE_WORDS;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, Geo<K>::DYN_BYTES);
+        bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, Geo<K>::DYN_BYTES, bar);
+    }
+    if (tid < 6) s_acc[tid] = 0ull;
+    TileColumnShared s;
+    s.dyn = s_dyn + e - W_CSTEP * TILE, s.hot = g_tile + e;
+    XchgColumn x{s_x + e};
+    CellLane L;
+    L.c = c;
+    load_hot(s, L.h);
+    load_cell<K>(s, c, L.hc);
+    for (int i = tid; i < Xl<K>::WORDS * TILE; i += NT) s_x[i] = 0u;
+    __syncthreads();
+    mbar_wait(bar, 0);
+    unsigned long long n_steps = 0, n_eps = 0, n_orders = 0, n_prod = 0, n_fault = 0;
+    long long units = 0;
+    const uint64_t genv = (uint64_t)(first_env + env);
+    for (int k = 0; k < steps; k++) {
+        const uint64_t t = t0 + (uint64_t)k;
+        int a0 = 0, a7[7];
+        {   // the lane's own action columns of the Philox stream (philox_actions_k): cell c draws with counter word 3 = 1 + 16c
+            u32 r[4];
+            philox4x32_10((u32)genv, (u32)t, (u32)(t >> 32), 1u + 16u * (u32)c, (u32)seed, (u32)(seed >> 32), r);
+#pragma unroll
+            for (int j = 1; j < 8; j++) {
+                const u32 hw = (j & 1) ? (r[j >> 1] >> 16) : (r[j >> 1] & 0xffffu);
+                a7[j - 1] = (int)((hw * (j == 1 ? 8u : 3u)) >> 16);
+            }
+            if (c != 0) philox4x32_10((u32)genv, (u32)t, (u32)(t >> 32), 1u, (u32)seed, (u32)(seed >> 32), r);
+            a0 = (int)(((r[0] & 0xffffu) * 3u) >> 16);
+        }
+        if (valid) cells_begin<K>(s, x, P, L, a0, a7);
+        __syncthreads();
+        if (valid) cells_act_run<K>(s, x, P, L, a7);
+        __syncthreads();
+        bool ended = false;
+        if (valid) {
+            int32_t info[4];
+            cells_finish<K>(x, P, L, info);
+#pragma unroll
+            for (int i = 1; i < 8; i++) units += L.g + AG * L.local10[i];
+            if (c == 0) {
+                units += L.g + AG * L.local10[0];
+                n_steps += 1;
+                n_orders += (unsigned long long)(L.h.completed_orders - L.orders_in);
+                n_prod += (unsigned long long)(L.h.total_packaged - L.packaged_in);
+            }
+            if (L.flags & 0x00ffffffu) {
+                ended = true;
+                if (c == 0) n_eps += 1, n_fault += ((L.flags >> 16) & 0xffu) ? 1 : 0;
+            }
+        }
+        if (__syncthreads_or(ended)) {  // also: every lane has read the exchange area
+            if (c == 0) warp_autoreset<K>(s, s_dyn, tid, ended, L.h.episode, num_orders, seed, genv - (uint64_t)(tid & 31));
+            __syncthreads();
+            if (ended) {
+                load_hot(s, L.h);
+                load_cell<K>(s, c, L.hc);
+            }
+        }
+        for (int i = c; i < Xl<K>::WORDS; i += K) x.st(i, 0u);
+        __syncthreads();
+    }
+    if (c == 0) store_hot(s, L.h);
+    store_cell<K>(s, c, L.hc);
+    unsigned long long v[6] = {n_steps, n_eps, n_orders, n_prod, n_fault, (unsigned long long)units};
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        unsigned long long y = v[j];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) y += __shfl_xor_sync(0xffffffffu, y, off);
+        if ((tid & 31) == 0) atomicAdd(&s_acc[j], y);
     }
     fence_async_smem();
     __syncthreads();

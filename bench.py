@@ -389,6 +389,11 @@ def run_ours(args):
                   "state_bytes_per_env": 4 * d4["state_words"], "algorithmic_bytes_per_env_step": bytes4,
                   "achieved_gbs": n4 * bytes4 / (ms4 * 1e-3) / 1e9, "roofline_frac": n4 * bytes4 / (ms4 * 1e-3) / 1e9 / peak4,
                   "kernel": "fjsp_step_cells_kernel<4,false> (one thread per (env, cell))"}
+        e0.record()
+        e4.rollout_random(32)
+        e1.record()
+        torch.cuda.synchronize()
+        scaled["rollout32_agent_steps_per_s"] = n4 * d4["agents"] * 32 / (e0.elapsed_time(e1) * 1e-3)  # K-steps-per-launch kernel
         del e4, a4
 
     # ---- A2C frames/s (second half of BASELINE.json's metric; configs[2]): 4096 envs per GPU, rollout 32, fp32 GEMMs,

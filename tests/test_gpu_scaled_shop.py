@@ -248,3 +248,54 @@ def test_gpu_replays_scaled_vectors(name):
             return self.env.export_state(0, cell)
 
     assert replay_scaled(name, lambda cfg: GpuSingleK(cfg), exact_rewards=False) > 300
+
+
+def test_gpu_random_config_fuzz_all_cell_counts():
+    """Random valid configurations (layouts with multi-step AGV moves, timings, capacities, episode lengths, few trays)
+    x K in {1, 2, 3, 4}: a batch of 96 envs with Philox orders / actions and auto-reset on the GPU, sampled envs followed
+    by the restatement — observations, masks, flags bit-exact, rewards within REL_TOL, canonical state of every cell."""
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+
+    rs = np.random.RandomState(77)
+    checked = 0
+    for trial in range(10):
+        k = [1, 2, 3, 4][trial % 4]
+        step = int(rs.choice([5, 10, 20]))
+        cells = set()
+        while len(cells) < 5:
+            cells.add((int(rs.randint(0, 12)), int(rs.randint(0, 30))))
+        ocfg = ocfg_k(k, step_size=step, proc_small=step * int(rs.randint(1, 8)), proc_big=step * int(rs.randint(1, 13)),
+                      proc_pack=step * int(rs.randint(1, 5)), agv_speed=int(rs.randint(1, 3)),
+                      max_episode_steps=int(rs.randint(40, 241)), storage_capacity=int(rs.randint(0, 6)),
+                      pack_capacity=int(rs.randint(1, 32)), num_trays=int(rs.choice([3, 40, 1000])))
+        for i, (r, c) in enumerate(sorted(cells, key=lambda _: rs.rand())):
+            ocfg.pos[i][0], ocfg.pos[i][1] = r, c
+        n, seed, num_orders, steps = 96, 1000 + trial, int(rs.randint(1, 33)), 300
+        env = BatchedFJSPEnv(n, config=_abi_cfg(ocfg), seed=seed, num_orders=num_orders, autoreset=True, first_env=trial * 1000)
+        obs0, masks0 = env.reset()
+        sample = [0, 31, 64, 95]
+        oracles, episodes = {}, {}
+        for i in sample:
+            o = OracleEnv(ocfg)
+            oo, om = o.reset(philox_orders(seed, trial * 1000 + i, 0, num_orders))
+            assert np.array_equal(oo, obs0[i].cpu().numpy()) and np.array_equal(om, masks0[i].cpu().numpy()), trial
+            oracles[i], episodes[i] = o, 0
+        for t in range(steps):
+            acts = env.random_actions(t)
+            obs, rew, term, trunc, masks = env.step(acts)
+            h_act, obs, rew, masks, flags = (x.cpu().numpy() for x in (acts, obs, rew, masks, env.flags))
+            for i in sample:
+                o = oracles[i]
+                oo, om, orw, of = o.step(h_act[i])
+                assert tuple(of[:3]) == tuple(flags[i][:3]), (trial, k, i, t, of, flags[i])
+                assert np.all(np.abs(rew[i] - orw) <= REL_TOL * np.abs(orw)), (trial, k, i, t)
+                if of[0] or of[1] or of[2]:
+                    episodes[i] += 1
+                    oo, om = o.reset(philox_orders(seed, trial * 1000 + i, episodes[i], num_orders))
+                assert np.array_equal(oo, obs[i]) and np.array_equal(om, masks[i]), (trial, k, i, t)
+                checked += 1
+        for i in sample:
+            for c in range(k):
+                df = canon.diff(oracles[i].export(c), env.export_state(i, c))
+                assert not df, (trial, k, i, c, df[:4])
+    assert checked == 10 * 300 * 4

@@ -7,14 +7,23 @@ Same PettingZoo-style surface as the reference class (/root/reference/FJSPParall
 
 Order generation in ``reset`` performs the reference's three draws per order from the global legacy NumPy RNG
 (FJSPSimulation.py:107-112), so ``np.random.seed(s)`` / ``reset(seed=s)`` produce the reference's order stream.
+
+Scaled shop (builder-defined extension): ``config={"num_cells": K}`` or the environment variable
+``FJSP_B200_NUM_CELLS=K`` (for callers that construct the env without a config, like the reference's train.py) gives the
+same surface with 1 + 7K agents — ``pickup_station`` and per cell ``agv_cN, small_machine_cN, ...`` — so the reference's
+own ``a2c.MultiAgentA2C`` (generic over ``possible_agents``) trains on it unchanged.  ``unwrapped.simulation`` then shows
+the shared pickup station / orders and cell 0.
 """
 from __future__ import annotations
+
+import os
+import re
 
 import numpy as np
 import torch
 
 from multi_agent_rl_for_fjsp_b200 import abi, spaces as _spaces
-from multi_agent_rl_for_fjsp_b200.env import AGENT_IDS, MASK_OFFSETS, N_ACTIONS, BatchedFJSPEnv
+from multi_agent_rl_for_fjsp_b200.env import AGENT_IDS, MASK_OFFSETS, N_ACTIONS, BatchedFJSPEnv, agent_layout
 
 try:  # the reference subclasses pettingzoo.ParallelEnv; keep isinstance() working when it is installed
     from pettingzoo import ParallelEnv as _Base  # type: ignore
@@ -52,6 +61,14 @@ def draw_reference_orders(n):
         c = int(np.random.choice([1, 2, 3]))
         out.append((k, t, c))
     return out
+
+
+def _kind(agent_id: str) -> str:
+    """'agv_c2' -> 'agv', 'packaging_red_c1' -> 'packaging', 'small_machine' -> 'machine'."""
+    base = re.sub(r"_c\d+$", "", agent_id)
+    if base in ("pickup_station", "agv"):
+        return base
+    return "machine" if "machine" in base else "packaging"
 
 
 class _Obj:
@@ -193,20 +210,24 @@ class FJSPParallelEnv(_Base):
         if config:
             self.config.update(config)
         self.render_mode = render_mode
+        if "num_cells" not in self.config and os.environ.get("FJSP_B200_NUM_CELLS"):
+            self.config["num_cells"] = int(os.environ["FJSP_B200_NUM_CELLS"])
+        self.num_cells = int(self.config.get("num_cells", 1))
         self._env = BatchedFJSPEnv(1, config=abi.config_from_dict(self.config), device=device, autoreset=False,
                                    with_infos=True)
-        self.possible_agents = list(AGENT_IDS)
+        self._ids, self._nact, self._obs_slices, self._mask_off = agent_layout(self.num_cells)
+        self._dims = abi.dims(self.num_cells)
+        self.possible_agents = list(self._ids)
         self.agents = self.possible_agents.copy()
         self._orders = []
         self._cache = None
         self.simulation = SimulationView(self)
-        self._obs_spaces = {
-            "pickup_station": _spaces.pickup_station(),
-            "agv": _spaces.agv(self.config["grid_rows"], self.config["grid_cols"], self.config["tray_capacity"]),
-            "small_machine": _spaces.machine(), "big_machine": _spaces.machine(),
-        }
-        for a in AGENT_IDS[4:]:
-            self._obs_spaces[a] = _spaces.packaging()
+        self._obs_spaces = {}
+        for a in self._ids:
+            kind = _kind(a)
+            self._obs_spaces[a] = (_spaces.pickup_station() if kind == "pickup_station"
+                                   else _spaces.agv(self.config["grid_rows"], self.config["grid_cols"], self.config["tray_capacity"])
+                                   if kind == "agv" else _spaces.machine() if kind == "machine" else _spaces.packaging())
         self._env.reset(orders=self._order_table())  # no orders (and no RNG draws) until reset(), as in the reference
 
     # ---- spaces
@@ -214,7 +235,7 @@ class FJSPParallelEnv(_Base):
         return self._obs_spaces[agent]
 
     def action_space(self, agent):
-        return _spaces.action_space(agent)
+        return _spaces.action_space(_kind(agent))
 
     # ---- reset / step
     def _gen_orders(self, n):
@@ -241,9 +262,11 @@ class FJSPParallelEnv(_Base):
         return observations, {a: {} for a in self.possible_agents}
 
     def step(self, actions):
-        a = np.zeros((1, 8), dtype=np.uint8)
+        ids, d = self._ids, self._dims
+        n_act, n_obs, n_mask = d["act"], d["obs"], d["mask"]
+        a = np.zeros((1, n_act), dtype=np.uint8)
         present = []
-        for i, aid in enumerate(AGENT_IDS):
+        for i, aid in enumerate(ids):
             if aid in actions:
                 v = int(actions[aid])
                 # out-of-range actions: AGV -> invalid_action (AGVAgent.py:249-250), others -> silently nothing
@@ -256,31 +279,33 @@ class FJSPParallelEnv(_Base):
         self._cache = None
         out = torch.cat([obs[0], rew[0], e.flags[0].float(), e.infos[0].float(), e.results[0].float(),
                          masks[0].float()]).cpu().numpy()
-        o, r = out[:38], out[38:46]
-        flags, infos, results, m = out[46:50].astype(np.int64), out[50:54].astype(np.int64), out[54:62].astype(np.int64), out[62:94]
+        p = n_obs + n_act
+        o, r = out[:n_obs], out[n_obs:p]
+        flags, infos = out[p:p + 4].astype(np.int64), out[p + 4:p + 8].astype(np.int64)
+        results, m = out[p + 8:p + 8 + n_act].astype(np.int64), out[p + 8 + n_act:p + 8 + n_act + n_mask]
         observations = self._obs_dicts(o, m.astype(np.int8))
-        rewards = {aid: float(r[i]) for i, aid in enumerate(AGENT_IDS)}
-        for i, aid in enumerate(AGENT_IDS):
+        rewards = {aid: float(r[i]) for i, aid in enumerate(ids)}
+        for i, aid in enumerate(ids):
             if aid not in actions:  # undo the idle penalty of the implicit action 0
-                res = int(results[i])
-                if aid == "pickup_station" and res & 0x08:
+                res, kind = int(results[i]), _kind(aid)
+                if kind == "pickup_station" and res & 0x08:
                     rewards[aid] += 1.0
-                elif aid in ("small_machine", "big_machine") and res & 0x08:
+                elif kind == "machine" and res & 0x08:
                     rewards[aid] += 2.0
-                elif aid.startswith("packaging") and res & 0x08:
+                elif kind == "packaging" and res & 0x08:
                     rewards[aid] += 1.0
-                elif aid == "agv" and res & 0x02:  # implicit IDLE while moving is not an invalid action
+                elif kind == "agv" and res & 0x02:  # implicit IDLE while moving is not an invalid action
                     rewards[aid] += 5.0
         if flags[2]:
             raise ValueError("list.remove(x): x not in list  [packaging START while requests were still waiting; "
                              "the reference raises here too (SURVEY R-PKG-cap-b)]")
         terminated, truncated = bool(flags[0]), bool(flags[1])
-        terminations = {aid: terminated for aid in AGENT_IDS}
-        truncations = {aid: truncated for aid in AGENT_IDS}
+        terminations = {aid: terminated for aid in ids}
+        truncations = {aid: truncated for aid in ids}
         sim_time = float(int(infos[0]) * self.config["step_size"])
         infos_d = {}
-        for i, aid in enumerate(AGENT_IDS):
-            kind = aid if aid in ("pickup_station", "agv") else ("machine" if "machine" in aid else "packaging")
+        for i, aid in enumerate(ids):
+            kind = _kind(aid)
             if aid in actions:
                 ar = {"action": int(actions[aid])}
                 ar.update({k: bool(int(results[i]) & bit) for k, bit in _RESULT_KEYS[kind]})
@@ -297,18 +322,18 @@ class FJSPParallelEnv(_Base):
         i32 = lambda v: np.array(int(v), dtype=np.int32)  # noqa: E731
         i8 = lambda v: np.array(int(v), dtype=np.int8)  # noqa: E731
         obs = {}
-        ps = {k: i32(o[i]) for i, k in enumerate(_PS_KEYS)}
-        ps["action_mask"] = m[0:3].astype(np.int8)
-        obs["pickup_station"] = ps
-        agv = {k: i32(o[7 + i]) for i, k in enumerate(_AGV_KEYS) if k is not None}
-        agv["position"] = np.array([int(o[11]), int(o[12])], dtype=np.int32)
-        agv["action_mask"] = m[3:11].astype(np.int8)
-        obs["agv"] = agv
-        for j, aid in enumerate(AGENT_IDS[2:]):
-            b = 20 + 3 * j
-            obs[aid] = {"is_busy": i8(o[b]), "processing_progress": np.array(o[b + 1], dtype=np.float32),
-                        "queue_length": i8(o[b + 2]),
-                        "action_mask": m[MASK_OFFSETS[2 + j]:MASK_OFFSETS[2 + j] + 3].astype(np.int8)}
+        for j, aid in enumerate(self._ids):
+            b, kind = self._obs_slices[j][0], _kind(aid)
+            mask = m[self._mask_off[j]:self._mask_off[j] + self._nact[j]].astype(np.int8)
+            if kind == "pickup_station":
+                d = {k: i32(o[b + i]) for i, k in enumerate(_PS_KEYS)}
+            elif kind == "agv":
+                d = {k: i32(o[b + i]) for i, k in enumerate(_AGV_KEYS) if k is not None}
+                d["position"] = np.array([int(o[b + 4]), int(o[b + 5])], dtype=np.int32)
+            else:
+                d = {"is_busy": i8(o[b]), "processing_progress": np.array(o[b + 1], dtype=np.float32), "queue_length": i8(o[b + 2])}
+            d["action_mask"] = mask
+            obs[aid] = d
         return obs
 
     def _canon(self):

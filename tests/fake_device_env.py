@@ -20,9 +20,13 @@ class FakeBatchedFJSPEnv:
         self._e = HostEnv(ocfg)
         self.num_envs, self.num_orders, self.autoreset = 1, num_orders, autoreset
         self.device = torch.device("cpu")
-        self.obs = torch.zeros((1, 38)); self.masks = torch.zeros((1, 32), dtype=torch.int8)
-        self.rewards = torch.zeros((1, 8)); self.flags = torch.zeros((1, 4), dtype=torch.uint8)
-        self.results = torch.zeros((1, 8), dtype=torch.uint8); self.infos = torch.zeros((1, 4), dtype=torch.int32)
+        k = max(1, int(config.num_cells))
+        agents = 1 + 7 * k
+        act, nobs, nmask = (agents + 7) // 8 * 8, 7 + 31 * k, (3 + 26 * k + 31) // 32 * 32
+        self.cells = k
+        self.obs = torch.zeros((1, nobs)); self.masks = torch.zeros((1, nmask), dtype=torch.int8)
+        self.rewards = torch.zeros((1, act)); self.flags = torch.zeros((1, 4), dtype=torch.uint8)
+        self.results = torch.zeros((1, act), dtype=torch.uint8); self.infos = torch.zeros((1, 4), dtype=torch.int32)
 
     def reset(self, seed=None, num_orders=None, orders=None, env_mask=None):
         tab = np.asarray(orders, dtype=np.uint32)[0]
@@ -37,8 +41,8 @@ class FakeBatchedFJSPEnv:
         self.infos[0] = torch.from_numpy(self._e.infos.copy())
         return self.obs, self.rewards, self.flags[:, 0], self.flags[:, 1], self.masks
 
-    def export_state(self, env):
-        return self._e.export()
+    def export_state(self, env, cell=0):
+        return self._e.export(cell)
 
     def close(self):
         pass

@@ -176,3 +176,67 @@ def test_reference_cli_heuristic_test_run_prints_the_same_summary(tmp_path):
         tail = p.stdout[p.stdout.index("TEST COMPLETE"):]
         outs.append([ln.strip() for ln in tail.splitlines() if ":" in ln])
     assert outs[0] == outs[1] and any("Orders completed" in ln for ln in outs[0]), outs
+
+
+def test_scaled_shop_facade_surface_and_parity(facade_cls):
+    """config={'num_cells': 4}: the same dict surface with 1 + 7K agents; every step equals the packed-state core driven
+    with the same action row (observation fields, masks, rewards, flags)."""
+    from tests.host_harness.hostharness import HostEnv
+    from tests.test_scaled_shop import cfg_k
+
+    env = facade_cls(config={"num_cells": 4})
+    ids = env.possible_agents
+    assert len(ids) == 29 and ids[0] == "pickup_station" and ids[1] == "agv_c0" and ids[8] == "agv_c1" and ids[-1] == "packaging_green_c3"
+    assert [env.action_space(a).n for a in ids] == [3] + [8, 3, 3, 3, 3, 3, 3] * 4
+    dims = []
+    for a in ids:
+        dims.append(sum(1 if hasattr(sp, "n") else int(np.prod(sp.shape))
+                        for key, sp in env.observation_space(a).spaces.items() if key != "action_mask"))
+    assert dims == [7] + [13, 3, 3, 3, 3, 3, 3] * 4 and sum(dims) == 7 + 31 * 4
+    np.random.seed(5)
+    obs, _ = env.reset(options={"num_orders": 12})
+    ref = HostEnv(cfg_k(4))
+    o, m = ref.reset(np.array(env._orders))
+    assert obs["agv_c1"]["position"].tolist() == [3, 0] and obs["agv_c0"]["position"].tolist() == [0, 0]
+    assert obs["agv_c2"]["action_mask"].tolist() == m[3 + 52:3 + 52 + 8].tolist()
+    assert env.state().shape == (7 + 3 + 4 * (13 + 8 + 6 * (3 + 3)) + 4,)
+    rs = np.random.RandomState(3)
+    total = 0.0
+    for t in range(120):
+        acts = {a: int(rs.randint(0, env.action_space(a).n)) for a in ids}
+        row = np.zeros(32, np.uint8)
+        row[:29] = [acts[a] for a in ids]
+        obs, rew, term, trunc, infos = env.step(acts)
+        o, m, r, f = ref.step(row)
+        assert [rew[a] for a in ids] == [float(x) for x in r[:29]]
+        assert all(term[a] == bool(f[0]) and trunc[a] == bool(f[1]) for a in ids)
+        for c in range(4):
+            b = 7 + 31 * c
+            agv = obs["agv_c%d" % c]
+            assert agv["position"].tolist() == [int(o[b + 4]), int(o[b + 5])] and int(agv["carrying_tray"]) == int(o[b + 2])
+            assert agv["action_mask"].tolist() == m[3 + 26 * c:11 + 26 * c].tolist()
+            pk = obs["packaging_green_c%d" % c]
+            assert int(pk["queue_length"]) == int(o[b + 30]) and pk["action_mask"].tolist() == m[26 + 26 * c:29 + 26 * c].tolist()
+        assert infos["agv_c3"]["sim_time"] == 10.0 * (t + 1)
+        total += sum(rew.values())
+        if not env.agents:
+            break
+    assert env.unwrapped.simulation.current_step == t + 1
+
+
+@pytest.mark.reference
+def test_reference_train_py_runs_unchanged_on_the_scaled_shop(tmp_path):
+    """The reference's own train.py + a2c.py (generic over possible_agents), unmodified, on the 4-cell façade selected
+    with FJSP_B200_NUM_CELLS=4: 29 actor networks + the centralised critic over the 131-float observation."""
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import tests.fake_device_env as f\n"
+        "import multi_agent_rl_for_fjsp_b200.env as e\n"
+        "e.BatchedFJSPEnv = f.FakeBatchedFJSPEnv\n"
+        "from multi_agent_rl_for_fjsp_b200 import run_reference_caller as r\n"
+        "r.main([%r, 'train.py', '--timesteps', '230', '--batch_size', '64', '--save_path', %r])\n"
+    ) % (REPO, refload.REFERENCE_ROOT, str(tmp_path / "ckpt"))
+    proc = subprocess.run([sys.executable, "-c", code], cwd=str(tmp_path), capture_output=True, text=True, timeout=900,
+                          env=dict(os.environ, FJSP_B200_NUM_CELLS="4"))
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-3000:]
+    assert "Training complete" in proc.stdout and "Number of agents: 29" in proc.stdout

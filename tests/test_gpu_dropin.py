@@ -53,3 +53,42 @@ def test_dict_api_episode_matches_oracle(FJSPParallelEnv):
         assert (sim.agv.carrying_tray is not None) == (int(s["agv_carry"]) >= 0)
     assert env.state().shape == (71,)
     env.close()
+
+
+def test_dict_api_on_the_scaled_shop_matches_restatement(FJSPParallelEnv):
+    """config={'num_cells': 4}: 29 agents through the dict API on the device == the C restatement of the extension."""
+    from oracle.fjsp_oracle import default_config
+
+    env = FJSPParallelEnv(config={"num_cells": 4})
+    ids = env.possible_agents
+    assert len(ids) == 29
+    ocfg = default_config()
+    ocfg.num_cells = 4
+    rs = np.random.RandomState(4)
+    obs, _ = env.reset(seed=7, options={"num_orders": 20})
+    orc = OracleEnv(ocfg)
+    o_o, m_o = orc.reset(env._orders)
+    steps = 0
+    while env.agents:
+        acts = {a: int(rs.randint(env.action_space(a).n)) for a in ids}
+        row = np.zeros(32, np.uint8)
+        row[:29] = [acts[a] for a in ids]
+        obs, rew, te, tr, inf = env.step(acts)
+        o_o, m_o, r_o, f_o = orc.step(row)
+        assert np.allclose([rew[a] for a in ids], r_o[:29], rtol=1e-6, atol=0)
+        for c in range(4):
+            b = 7 + 31 * c
+            agv = obs["agv_c%d" % c]
+            assert agv["position"].tolist() == [int(o_o[b + 4]), int(o_o[b + 5])] and int(agv["tray_type"]) == int(o_o[b + 12])
+            assert agv["action_mask"].tolist() == m_o[3 + 26 * c:11 + 26 * c].tolist()
+            for j, name in enumerate(("small_machine", "big_machine", "packaging_blue_1", "packaging_blue_2", "packaging_red", "packaging_green")):
+                d = obs["%s_c%d" % (name, c)]
+                assert int(d["is_busy"]) == int(o_o[b + 13 + 3 * j]) and float(d["processing_progress"]) == float(o_o[b + 14 + 3 * j])
+                assert d["action_mask"].tolist() == m_o[11 + 26 * c + 3 * j:14 + 26 * c + 3 * j].tolist()
+        assert obs["pickup_station"]["action_mask"].tolist() == m_o[:3].tolist()
+        assert te["agv_c2"] == bool(f_o[0]) and tr["agv_c2"] == bool(f_o[1])
+        steps += 1
+    assert steps == 201 or bool(f_o[0])
+    prog = env.unwrapped.simulation.get_order_progress()
+    assert prog["completed_orders"] == int(orc.export()["completed_orders"]) and prog["total_orders"] == 20
+    env.close()

@@ -15,6 +15,7 @@
 using namespace fjsp;
 
 #define FJSP_HOST_MAX_CHUNKS 32
+#define FJSP_HOST_MAX_STREAMS 4
 
 struct FjspHandle {
     FjspConfig cfg;
@@ -33,8 +34,9 @@ struct FjspHandle {
     u32* d_wire;             // device wire rows  [num_envs][wire_words]
     u32* h_wire;             // pinned host copy of the same
     int wire_words;
-    cudaStream_t hs[2];      // the two streams the host-buffer path alternates its chunks on
-    cudaEvent_t hev[2], hin;
+    cudaStream_t hs[FJSP_HOST_MAX_STREAMS];  // the streams the host-buffer path deals its chunks round-robin on
+    cudaEvent_t hev[FJSP_HOST_MAX_STREAMS], hin;
+    int nstreams;            // 2 by default (FJSP_HOST_STREAMS = 1..4)
     cudaEvent_t cev[FJSP_HOST_MAX_CHUNKS];  // "chunk c has landed in h_wire"
     DecodePool* pool;        // host threads turning wire rows into the caller's float32 / int8 tensors
     int decode_threads;      // 0 = every CPU this process may run on (fjsp_set_decode_threads)
@@ -203,7 +205,7 @@ int fjsp_destroy(FjspHandle* h) {
     delete h->pool;
     cudaFree(h->d_actions), cudaFree(h->d_wire);
     if (h->h_wire) cudaFreeHost(h->h_wire);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < FJSP_HOST_MAX_STREAMS; i++) {
         if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
         if (h->hev[i]) cudaEventDestroy(h->hev[i]);
     }
@@ -306,7 +308,10 @@ static int ensure_staging(FjspHandle* h) {
     CK(cudaMalloc(&h->d_actions, n * h->act));
     CK(cudaMalloc(&h->d_wire, n * h->wire_words * sizeof(u32)));
     CK(cudaMallocHost(&h->h_wire, n * h->wire_words * sizeof(u32)));
-    for (int i = 0; i < 2; i++) {
+    h->nstreams = 2;
+    if (const char* e = getenv("FJSP_HOST_STREAMS")) h->nstreams = atoi(e);
+    if (h->nstreams < 1 || h->nstreams > FJSP_HOST_MAX_STREAMS) h->nstreams = 2;
+    for (int i = 0; i < h->nstreams; i++) {
         CK(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&h->hev[i], cudaEventDisableTiming));
     }
@@ -334,7 +339,7 @@ static int step_host_impl(FjspHandle* h, const uint8_t* actions, u32* wire_out, 
     if (int rc = ensure_staging(h)) return rc;
     cudaStream_t user = (cudaStream_t)stream;
     CK(cudaEventRecord(h->hin, user));
-    for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(h->hs[i], h->hin, 0));
+    for (int i = 0; i < h->nstreams; i++) CK(cudaStreamWaitEvent(h->hs[i], h->hin, 0));
     const int64_t tiles = h->num_tiles;
     int64_t nchunks = tiles >= 2048 ? 16 : tiles >= 64 ? 8 : (tiles >= 2 ? 2 : 1);
     static const int env_chunks = getenv("FJSP_HOST_CHUNKS") ? atoi(getenv("FJSP_HOST_CHUNKS")) : 0;
@@ -349,7 +354,7 @@ static int step_host_impl(FjspHandle* h, const uint8_t* actions, u32* wire_out, 
     const int64_t na = h->act, ww = h->wire_words;
     int c = 0;
     for (int64_t t0 = 0; t0 < tiles; t0 += per, c++) {
-        cudaStream_t st = h->hs[c & 1];
+        cudaStream_t st = h->hs[c % h->nstreams];
         const int64_t t1 = t0 + per < tiles ? t0 + per : tiles;
         const int64_t e0 = t0 * TILE, e1 = t1 * TILE < h->num_envs ? t1 * TILE : h->num_envs;
         const size_t n = (size_t)(e1 - e0);
@@ -361,12 +366,12 @@ static int step_host_impl(FjspHandle* h, const uint8_t* actions, u32* wire_out, 
         CK(cudaMemcpyAsync((wire_out ? wire_out : h->h_wire) + e0 * ww, h->d_wire + e0 * ww, n * ww * sizeof(u32), cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(h->cev[c], st));
     }
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < h->nstreams; i++) {
         CK(cudaEventRecord(h->hev[i], h->hs[i]));
         CK(cudaStreamWaitEvent(user, h->hev[i], 0));
     }
     if (wire_out) {  // no decode: wait for the copies and return
-        for (int i = 0; i < 2; i++) CK(cudaStreamSynchronize(h->hs[i]));
+        for (int i = 0; i < h->nstreams; i++) CK(cudaStreamSynchronize(h->hs[i]));
         return 0;
     }
     const int64_t grain = h->pool->size() > 0 ? (env_grain > 0 ? env_grain : 2048) : (int64_t)1 << 40;

@@ -1,7 +1,10 @@
 // fjsp_wire.cpp — HOST decode of wire rows (include/fjsp_b200.h) into the float32 / int8 tensors fjsp_step writes.
 // Format conversion only.  Two bodies per K: portable C++ and AVX2 (chosen once at run time with
 // __builtin_cpu_supports); both produce the same bits (integer -> float32 conversions are exact, one IEEE division).
+#if defined(__x86_64__) || defined(_M_X64)
+#define FJSP_WIRE_X86 1
 #include <immintrin.h>
+#endif
 #include <string.h>
 
 #include "fjsp_wire.h"
@@ -68,6 +71,7 @@ static void decode_generic(const Params& P, const u32* wire, int64_t lo, int64_t
     }
 }
 
+#ifdef FJSP_WIRE_X86
 // One env, AVX2.  NT = false: straight into the caller's rows.  NT = true (used on blocks of 8 envs): obs into a small
 // aligned stack buffer, masks / rewards as register values handed back to the caller for streaming stores.
 template <int K>
@@ -190,20 +194,32 @@ __attribute__((target("avx2"))) static void decode_avx2(const Params& P, const u
     }
 }
 
+#endif  // FJSP_WIRE_X86
+
 typedef void (*DecodeFn)(const Params&, const u32*, int64_t, int64_t, float*, int8_t*, float*, uint8_t*);
 
 static bool have_avx2() {
+#ifdef FJSP_WIRE_X86
     static const bool v = __builtin_cpu_supports("avx2");
     return v && !getenv("FJSP_DECODE_GENERIC");
+#else
+    return false;
+#endif
 }
 const char* wire_decode_isa() { return have_avx2() ? "avx2" : "generic"; }
 
 void wire_decode(int cells, const Params& P, const u32* wire, int64_t lo, int64_t hi, float* obs, int8_t* masks, float* rewards,
                  uint8_t* flags) {
     static const DecodeFn gen[4] = {decode_generic<1>, decode_generic<2>, decode_generic<3>, decode_generic<4>};
-    static const DecodeFn avx[4] = {decode_avx2<1>, decode_avx2<2>, decode_avx2<3>, decode_avx2<4>};
     const int k = cells < 1 ? 0 : cells > 4 ? 3 : cells - 1;
-    (have_avx2() ? avx : gen)[k](P, wire, lo, hi, obs, masks, rewards, flags);
+#ifdef FJSP_WIRE_X86
+    static const DecodeFn avx[4] = {decode_avx2<1>, decode_avx2<2>, decode_avx2<3>, decode_avx2<4>};
+    if (have_avx2()) {
+        avx[k](P, wire, lo, hi, obs, masks, rewards, flags);
+        return;
+    }
+#endif
+    gen[k](P, wire, lo, hi, obs, masks, rewards, flags);
 }
 
 }  // namespace fjsp

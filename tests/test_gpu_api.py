@@ -93,3 +93,37 @@ def test_out_of_range_actions_follow_reference_rules():
     assert r[0, 1] == pytest.approx(-5.125) and r[0, 0] == pytest.approx(-0.125)   # pickup did nothing, not even idle
     assert r[1, 0] == pytest.approx(-1.125) and r[1, 1] == pytest.approx(-0.125)
     assert np.allclose(r[0, 2:], -0.125)
+
+
+def test_new_entry_points_report_argument_errors():
+    """Wire rows, decode threads, cells: misuse is an error code + message, never a crash or a silent fallback."""
+    import ctypes as C
+
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv, abi
+
+    L = abi.lib()
+    cfg = abi.default_config()
+    cfg.num_cells = 5
+    h = C.c_void_p()
+    assert L.fjsp_create(C.byref(cfg), 64, 0, 0, C.byref(h)) != 0 and b"num_cells" in L.fjsp_last_error()
+    cfg.num_cells = 3
+    env = BatchedFJSPEnv(200, config=cfg, seed=1)
+    env.reset()
+    assert L.fjsp_num_cells(env._h) == 3 and env.state_bytes_per_env == 4 * abi.dims(3)["state_words"]
+    acts = env.random_actions(0)
+    wire = torch.zeros((200, env.dims["wire_words"] + 1), dtype=torch.int32, device=env.device)
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t, off=0: C.c_void_p(t.data_ptr() + off)  # noqa: E731
+    assert L.fjsp_step_wire(env._h, p(acts), p(wire, 4), None, None, 1, s) != 0 and b"alignment" in L.fjsp_last_error()
+    assert L.fjsp_step_wire(env._h, None, p(wire), None, None, 1, s) != 0
+    s3 = np.zeros((), dtype=abi.CANON_DT)
+    assert L.fjsp_export_state_cell(env._h, 0, 3, C.c_void_p(s3.ctypes.data)) != 0 and b"cell" in L.fjsp_last_error()
+    assert L.fjsp_export_state_cell(env._h, 0, 2, C.c_void_p(s3.ctypes.data)) == 0
+    assert L.fjsp_set_decode_threads(env._h, 65) != 0
+    assert L.fjsp_set_decode_threads(env._h, 2) == 0
+    env.step_host(acts.cpu().numpy())
+    assert L.fjsp_set_decode_threads(env._h, 4) != 0 and b"before the first" in L.fjsp_last_error()
+    assert L.fjsp_step_host_wire(env._h, None, None, 1, s) != 0
+    # the env is still usable after the refused calls
+    env.step(env.random_actions(1))
+    torch.cuda.synchronize()

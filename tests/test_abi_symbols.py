@@ -69,3 +69,7 @@ def test_built_for_sm100a_with_bulk_copies():
     out = subprocess.run(["cuobjdump", "-sass", abi.SO_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     assert "UBLKCP" in out, "step kernel must move its tiles with bulk async copies (TMA engine)"
+    assert "UBLKPF" in out, "step kernels prefetch a later tile into L2 with a bulk prefetch"
+    for k in (1, 2, 3, 4):  # every cell count has its own instantiations: thread-per-env, and cell-parallel for K >= 2
+        assert "fjsp_step_kernelILi%dE" % k in out.replace("16fjsp_step_kernel", "fjsp_step_kernel")
+    assert "fjsp_step_cells_kernelILi4ELb1" in out and "fjsp_rollout_cells_kernelILi2E" in out

@@ -6,6 +6,7 @@
 #define FJSP_HOST_H
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "fjsp_core.h"
@@ -73,13 +74,24 @@ inline const char* make_params(const FjspConfig& c, Params* P) {
     return nullptr;
 }
 
+// FJSP_BOUNDS_CHECK (set by the test-only host harness build): every word index the step function computes is checked
+// against the env's word count — `ld/st` must stay inside the dynamically indexed words, `ld_hot/st_hot` outside them.
+// The CUDA kernels run the same index arithmetic, so a clean run of the CPU suite under the check is the stand-in for
+// compute-sanitizer (closed on this pool) as far as the step function's addressing goes.
+#ifdef FJSP_BOUNDS_CHECK
+#define FJSP_CHECK_IDX(cond) do { if (!(cond)) { fprintf(stderr, "fjsp bounds check failed: %s (index %d, line %d)\n", #cond, i, __LINE__); abort(); } } while (0)
+#else
+#define FJSP_CHECK_IDX(cond) do { } while (0)
+#endif
 struct ArrayState {
     u32* w;
-    FJSP_HD u32 ld(int i) const { return w[i]; }
-    FJSP_HD void st(int i, u32 v) { w[i] = v; }
-    FJSP_HD u32 ld_hot(int i) const { return w[i]; }
-    FJSP_HD void st_hot(int i, u32 v) { w[i] = v; }
+    int dyn_end = 1 << 30, total = 1 << 30;  // word counts of the env (set by the harness when the check is compiled in)
+    FJSP_HD u32 ld(int i) const { FJSP_CHECK_IDX(i >= W_CSTEP && i < dyn_end); return w[i]; }
+    FJSP_HD void st(int i, u32 v) { FJSP_CHECK_IDX(i >= W_CSTEP && i < dyn_end); w[i] = v; }
+    FJSP_HD u32 ld_hot(int i) const { FJSP_CHECK_IDX((i >= 0 && i < W_CSTEP) || (i >= dyn_end && i < total)); return w[i]; }
+    FJSP_HD void st_hot(int i, u32 v) { FJSP_CHECK_IDX((i >= 0 && i < W_CSTEP) || (i >= dyn_end && i < total)); w[i] = v; }
     FJSP_HD u32 or_word(int i, u32 v) {
+        FJSP_CHECK_IDX(i >= W_CSTEP && i < W_POOL);
         const u32 old = w[i];
         w[i] = old | v;
         return old;
@@ -100,6 +112,7 @@ struct ArrayXchg {
 template <int K>
 inline void export_canon_k(const u32* words, const Params& P, int cell, FjspCanonState* out) {
     ArrayState s{const_cast<u32*>(words)};
+    s.dyn_end = Lay<K>::DYN_END, s.total = Lay<K>::TOTAL;
     Hot h;
     HotCell hc;
     load_hot(s, h);

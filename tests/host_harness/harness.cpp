@@ -24,6 +24,12 @@ struct HostEnv {
         default: { constexpr int K = 4; __VA_ARGS__; } break; \
     }
 
+static ArrayState env_state(HostEnv* e) {
+    ArrayState s{e->words};
+    s.dyn_end = 64 + 64 * e->cells, s.total = FJSP_STATE_WORDS_K(e->cells);
+    return s;
+}
+
 extern "C" {
 
 void* hh_create(const FjspConfig* cfg) {
@@ -43,6 +49,13 @@ const char* hh_check_config(const FjspConfig* cfg) {
     return m ? m : "";
 }
 void hh_destroy(void* p) { free(p); }
+int hh_bounds_checked(void) {  // 1 when every word index of the step function is range-checked (fjsp_host.h)
+#ifdef FJSP_BOUNDS_CHECK
+    return 1;
+#else
+    return 0;
+#endif
+}
 
 static void unpack_bytes(const u32* w, int n, uint8_t* dst) {
     for (int i = 0; i < n; i++) dst[i] = (uint8_t)((w[i >> 2] >> ((i & 3) * 8)) & 0xff);
@@ -50,7 +63,7 @@ static void unpack_bytes(const u32* w, int n, uint8_t* dst) {
 
 void hh_observe(void* p, float* obs, int8_t* masks) {
     HostEnv* e = (HostEnv*)p;
-    ArrayState s{e->words};
+    ArrayState s = env_state(e);
     DISPATCH_K(e, {
         u32 mw[Lay<K>::MASK / 4];
         observe_env<K>(s, e->P, obs, mw);
@@ -60,14 +73,14 @@ void hh_observe(void* p, float* obs, int8_t* masks) {
 
 void hh_reset(void* p, const FjspOrderRec* orders, int num_orders, uint64_t seed, uint64_t genv, uint32_t episode) {
     HostEnv* e = (HostEnv*)p;
-    ArrayState s{e->words};
+    ArrayState s = env_state(e);
     DISPATCH_K(e, reset_env<K>(s, e->P, num_orders, orders, seed, genv, episode))
 }
 
 void hh_step(void* p, const uint8_t* actions, float* obs, int8_t* masks, float* rewards, uint8_t* flags, uint8_t* results,
              int32_t* infos) {
     HostEnv* e = (HostEnv*)p;
-    ArrayState s{e->words};
+    ArrayState s = env_state(e);
     DISPATCH_K(e, {
         int a[Lay<K>::ACT];
         for (int i = 0; i < Lay<K>::ACT; i++) a[i] = actions[i];
@@ -88,7 +101,7 @@ void hh_step_wire(void* p, const uint8_t* actions, float* obs, int8_t* masks, fl
     HostEnv* e = (HostEnv*)p;
     HostEnv copy = *e;
     hh_step(p, actions, obs, masks, rewards, flags, nullptr, nullptr);
-    ArrayState s{copy.words};
+    ArrayState s = env_state(&copy);
     DISPATCH_K(e, {
         int a[Lay<K>::ACT];
         for (int i = 0; i < Lay<K>::ACT; i++) a[i] = actions[i];
@@ -111,7 +124,7 @@ int hh_step_cells(void* p, const uint8_t* actions, float* obs, int8_t* masks, fl
             u32 xw[Xl<K>::WORDS];
             for (int i = 0; i < Xl<K>::WORDS; i++) xw[i] = 0u;
             ArrayXchg x{xw};
-            ArrayState s{e->words};
+            ArrayState s = env_state(e);
             CellLane L[K];
             int a7[K][7];
             for (int c = 0; c < K; c++) {

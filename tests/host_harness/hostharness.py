@@ -18,7 +18,8 @@ def build():
             os.path.join(_HERE, "..", "..", "include", "fjsp_b200.h")]
     if (not os.path.exists(_SO)) or any(os.path.getmtime(p) > os.path.getmtime(_SO) for p in srcs):
         os.makedirs(os.path.dirname(_SO), exist_ok=True)
-        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas", "-o", _SO, srcs[0]], check=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas", "-DFJSP_BOUNDS_CHECK",
+                        "-o", _SO, srcs[0]], check=True)
     return _SO
 
 

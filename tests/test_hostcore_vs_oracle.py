@@ -121,3 +121,13 @@ def test_random_config_fuzz():
                     assert not d, (kw, d[:4])
                     break
     assert total > 2000
+
+
+def test_harness_runs_the_step_function_under_bounds_checks():
+    """The test-only host build range-checks every word index the step function computes (FJSP_BOUNDS_CHECK in
+    fjsp_host.h: dynamically indexed words stay inside the tile's sub-tile, hot words outside it; a violation aborts).
+    compute-sanitizer is closed on the GPU pool, and the kernels run the same index arithmetic, so the whole CPU suite
+    running clean under the check is the addressing evidence for the step function."""
+    from tests.host_harness.hostharness import lib
+
+    assert lib().hh_bounds_checked() == 1

@@ -293,6 +293,15 @@ def run_ours(args):
         env.step_host_wire(host_actions[i % len(host_actions)])
     torch.cuda.synchronize()
     e2e_wire_s = max_over_ranks(time.perf_counter() - t0)
+    # the host decode alone (no GPU work): the rows just delivered -> the float32 / int8 tensors, same thread count
+    import ctypes as _C
+    hb = env.host_buffers()
+    _p = lambda t: _C.c_void_p(t.data_ptr())  # noqa: E731
+    t0 = time.perf_counter()
+    for i in range(5):
+        env._L.fjsp_wire_decode(_C.byref(env.cfg), _p(hb["wire"]), E, _p(hb["obs"]), _p(hb["masks"]), _p(hb["rewards"]), _p(hb["flags"]),
+                                decode_threads)
+    decode_only_s = max_over_ranks((time.perf_counter() - t0) / 5)
     wire_row = 4 * env.dims["wire_words"]
     # the e2e path's own roofline: this box's pinned D2H bandwidth on the wire rows (64 B/env)
     hb = env.host_buffers()
@@ -449,7 +458,8 @@ def run_ours(args):
                     "wire_row_bytes": wire_row, "decoded_bytes_per_step": E * (152 + 32 + 32 + 4),
                     "undecoded_wire_rows_variant": {"api": "fjsp_step_host_wire (same pipeline, rows delivered as they are)",
                                                     "value": world * E * 8 * Ke / e2e_wire_s, "ms_per_step": e2e_wire_s / Ke * 1e3},
-                    "decode_threads": decode_threads, "pcie_d2h_gbs_measured": d2h_gbs, "host_cpus_bound": len(numa_cpus),
+                    "decode_threads": decode_threads, "decode_only_ms": decode_only_s * 1e3,
+                    "decode_only_host_gbs": E * (wire_row + 220) / decode_only_s / 1e9, "pcie_d2h_gbs_measured": d2h_gbs, "host_cpus_bound": len(numa_cpus),
                     "pcie_bound_frac": (E * wire_row / (d2h_gbs * 1e9)) / (e2e_s / Ke)},
             "gpu_launches": launches, "clocks": clocks,
         }

@@ -459,7 +459,9 @@ def run_ours(args):
                     "undecoded_wire_rows_variant": {"api": "fjsp_step_host_wire (same pipeline, rows delivered as they are)",
                                                     "value": world * E * 8 * Ke / e2e_wire_s, "ms_per_step": e2e_wire_s / Ke * 1e3},
                     "decode_threads": decode_threads, "decode_only_ms": decode_only_s * 1e3,
-                    "decode_only_host_gbs": E * (wire_row + 220) / decode_only_s / 1e9, "pcie_d2h_gbs_measured": d2h_gbs, "host_cpus_bound": len(numa_cpus),
+                    "decode_only_host_gbs": E * (wire_row + 220) / decode_only_s / 1e9,
+                    "decode_only_note": "fjsp_wire_decode on the delivered rows, host only, threads spawned per call (the pipelined "
+                                        "path uses the handle's persistent workers and overlaps the copies)", "pcie_d2h_gbs_measured": d2h_gbs, "host_cpus_bound": len(numa_cpus),
                     "pcie_bound_frac": (E * wire_row / (d2h_gbs * 1e9)) / (e2e_s / Ke)},
             "gpu_launches": launches, "clocks": clocks,
         }

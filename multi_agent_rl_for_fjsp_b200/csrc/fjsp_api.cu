@@ -40,6 +40,7 @@ struct FjspHandle {
     cudaEvent_t cev[FJSP_HOST_MAX_CHUNKS];  // "chunk c has landed in h_wire"
     DecodePool* pool;        // host threads turning wire rows into the caller's float32 / int8 tensors
     int decode_threads;      // 0 = every CPU this process may run on (fjsp_set_decode_threads)
+    bool staging_ready;      // host-buffer path: device / pinned staging, streams, events and decode workers exist
     int prefetch_tiles;      // cell-parallel kernel: L2 prefetch distance in tiles
     int prefetch_tiles_env;  // thread-per-env kernel: the same (0 = off)
 };
@@ -129,6 +130,8 @@ static void launch_rollout(const FjspHandle* h, int steps, uint64_t seed, uint64
 
 extern "C" {
 
+static void free_staging(FjspHandle* h);
+
 const char* fjsp_last_error(void) { return g_err.c_str(); }
 int fjsp_abi_version(void) { return FJSP_ABI_VERSION; }
 
@@ -202,16 +205,7 @@ int fjsp_destroy(FjspHandle* h) {
     if (!h) return 0;
     DeviceGuard g(h->device);
     cudaFree(h->state);
-    delete h->pool;
-    cudaFree(h->d_actions), cudaFree(h->d_wire);
-    if (h->h_wire) cudaFreeHost(h->h_wire);
-    for (int i = 0; i < FJSP_HOST_MAX_STREAMS; i++) {
-        if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
-        if (h->hev[i]) cudaEventDestroy(h->hev[i]);
-    }
-    for (int i = 0; i < FJSP_HOST_MAX_CHUNKS; i++)
-        if (h->cev[i]) cudaEventDestroy(h->cev[i]);
-    if (h->hin) cudaEventDestroy(h->hin);
+    free_staging(h);
     delete h;
     return 0;
 }
@@ -302,8 +296,28 @@ int fjsp_wire_decode(const FjspConfig* cfg, const uint32_t* wire, int64_t n, flo
     return 0;
 }
 
-static int ensure_staging(FjspHandle* h) {
-    if (h->d_actions) return 0;
+static void free_staging(FjspHandle* h) {
+    delete h->pool;
+    h->pool = nullptr;
+    cudaFree(h->d_actions), cudaFree(h->d_wire);
+    h->d_actions = nullptr, h->d_wire = nullptr;
+    if (h->h_wire) cudaFreeHost(h->h_wire);
+    h->h_wire = nullptr;
+    for (int i = 0; i < FJSP_HOST_MAX_STREAMS; i++) {
+        if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
+        if (h->hev[i]) cudaEventDestroy(h->hev[i]);
+        h->hs[i] = nullptr, h->hev[i] = nullptr;
+    }
+    for (int i = 0; i < FJSP_HOST_MAX_CHUNKS; i++) {
+        if (h->cev[i]) cudaEventDestroy(h->cev[i]);
+        h->cev[i] = nullptr;
+    }
+    if (h->hin) cudaEventDestroy(h->hin);
+    h->hin = nullptr;
+    h->staging_ready = false;
+}
+
+static int create_staging(FjspHandle* h) {
     const size_t n = (size_t)h->num_envs;
     CK(cudaMalloc(&h->d_actions, n * h->act));
     CK(cudaMalloc(&h->d_wire, n * h->wire_words * sizeof(u32)));
@@ -324,6 +338,20 @@ static int ensure_staging(FjspHandle* h) {
     if (n < 4096 || workers < 0) workers = 0;  // small batches decode on the calling thread
     h->pool = new (std::nothrow) DecodePool(workers);
     if (!h->pool) return fail("out of host memory");
+    return 0;
+}
+
+// staging of the host-buffer path, created on first use; a failure half-way releases what was created
+static int ensure_staging(FjspHandle* h) {
+    if (h->staging_ready) return 0;
+    const int rc = create_staging(h);
+    if (rc != 0) {
+        const std::string keep = g_err;
+        free_staging(h);
+        g_err = keep;
+        return rc;
+    }
+    h->staging_ready = true;
     return 0;
 }
 
@@ -415,7 +443,7 @@ int fjsp_step_host_wire(FjspHandle* h, const uint8_t* actions, uint32_t* wire, i
 int fjsp_set_decode_threads(FjspHandle* h, int threads) {
     if (!h) return fail("handle is NULL");
     if (threads < 0 || threads > 64) return fail("threads must be in 0..64 (0 = all CPUs of the process)");
-    if (h->pool) return fail("fjsp_set_decode_threads must be called before the first fjsp_step_host");
+    if (h->staging_ready) return fail("fjsp_set_decode_threads must be called before the first fjsp_step_host");
     h->decode_threads = threads;
     return 0;
 }

@@ -17,9 +17,14 @@ e2e        the same metric through the host-buffer C-ABI call fjsp_step_host: pi
            by the library's host threads, pipelined with the copies; d2h_bytes_per_step counts the bytes that cross.
 roofline   algorithmic bytes per launch = envs x (8 + 152 + 32 + 32 + 4 + 2 x 512) = envs x 1252 B,
            divided by the mean launch duration, against MEASURED_PEAKS.json hbm_gbs.
+           e2e.undecoded_wire_rows_variant: the same pipeline delivering the rows as they are (fjsp_step_host_wire);
+           e2e.decode_only_ms: the host decode alone.  Reported beside the headline, never instead of it.
 cpu_baseline / --impl reference
            the reference is pure Python + SimPy and cannot travel to the GPU box, so the CPU arm is the C port of it
            (oracle/fjsp_oracle.c, kind "port") on all host threads, on a bounded sample of the same workload.
+extra      (N = 1) BASELINE configs[1]: 4096 envs, stepwise / CUDA-graph / K-steps-per-launch figures.
+scaled_shop (N = 1) BASELINE configs[4]: the 4-cell shop (29 agents) at 2^19 envs with its own roofline fraction.
+a2c        BASELINE configs[2]: batched A2C frames/s, 4096 envs per GPU, rollout 32 (fp32; TF32 variant beside it).
 """
 from __future__ import annotations
 

@@ -70,6 +70,7 @@ extern "C" {
 #define FJSP_FAULT_NONE 0
 #define FJSP_FAULT_PKG_RESTART_WITH_WAITERS 1 /* reference raises ValueError out of env.run (SURVEY R-PKG-cap-b) */
 #define FJSP_FAULT_POOL_EXHAUSTED 2           /* >64 trays in transit: impossible when max_episode_steps <= 240 */
+#define FJSP_FAULT_BAD_ORDER 3                /* an explicit order record outside n 1..9 / type 1..3 / colour 1..3 (set at reset) */
 
 /* Mirrors constants.py:5-32 (LOCATION_POSITIONS, PROCESSING_TIMES, CONFIG). */
 typedef struct FjspConfig {
@@ -89,6 +90,8 @@ typedef struct FjspConfig {
 
 /* One order as the reference generates it (FJSPSimulation.py:101-131): all products of an order
  * share type and colour.  Packed u32: n | type<<8 | colour<<16. */
+/* Valid ranges: n 1..FJSP_MAX_ORDER_PRODUCTS, type 1..3 (ProductType), colour 1..3 (PackagingColor); a record
+ * outside them is clamped and the env reports FJSP_FAULT_BAD_ORDER with its first step. */
 typedef uint32_t FjspOrderRec;
 #define FJSP_ORDER_REC(n, type, colour) ((uint32_t)(n) | ((uint32_t)(type) << 8) | ((uint32_t)(colour) << 16))
 
@@ -244,6 +247,39 @@ int fjsp_a2c_gae(const float* rewards, const float* values, const uint8_t* flags
 int fjsp_cells_pack_actions(const uint8_t* view_actions, uint8_t* actions, int64_t num_envs, int num_cells, void* stream);
 int fjsp_cells_unpack_views(const float* obs, const int8_t* masks, const float* rewards, const uint8_t* flags, float* v_obs,
                             int8_t* v_masks, float* v_rewards, uint8_t* v_flags, int64_t num_envs, int num_cells, void* stream);
+
+/* ---- tensor-core GEMM for the trainer's actor / critic layers (networks.py:22-61; a2c.py:168-252,647-731) ----
+ * fjsp_a2c_gemm: C[M x N] (+)= A[M x K] * B[N x K]^T for a device-resident TABLE of problems in one launch (the 8 actors
+ * and the critic are one grouped launch per layer), computed by tcgen05.mma.kind::tf32 with accumulators in TMEM.
+ * passes = 3: every fp32 operand is split into two TF32 terms and three products are accumulated ("3xTF32": fp32-level
+ * accuracy, ~2^-21 relative per product); passes = 1: plain TF32.
+ * Operand orientation (the same for all problems of a call): FJSP_OP_KC  X(r,k) = X[r*ld + k] with 16-byte loads
+ * (ld % 4 == 0, 16-byte aligned pointer, K % 4 == 0), FJSP_OP_KCS the same with scalar loads (any alignment),
+ * FJSP_OP_MC  X(r,k) = X[k*ld + r].  Supported (a_op, b_op): (KC,MC) forward y = x W, (KCS,MC) forward from an
+ * unaligned observation slice, (KC,KC) dx = dy W^T, (MC,MC) dW = x^T dy.
+ * Epilogue per problem: + bias[n]; ReLU (FJSP_GEMM_RELU); * (mask(m,n) > 0) (mask indexed like C);
+ * colsum[n] += column sums of the stored values (bias gradient); FJSP_GEMM_ATOMIC: atomicAdd into C (split-K).
+ * max_ctas = max over the problems of ceil(M / 128) * splitk.  N <= 256. */
+#define FJSP_OP_KC 0
+#define FJSP_OP_KCS 1
+#define FJSP_OP_MC 2
+#define FJSP_GEMM_RELU 1
+#define FJSP_GEMM_ATOMIC 2
+typedef struct FjspGemmProb {
+    const float* A;
+    const float* B;
+    float* C;
+    const float* bias;
+    const float* mask;
+    float* colsum;
+    int32_t M, N, K;
+    int32_t lda, ldb;
+    int32_t csm, csn;      /* C(m, n) = C[m * csm + n * csn] */
+    int32_t flags;
+    int32_t splitk;
+    int32_t reserved[3];
+} FjspGemmProb;
+int fjsp_a2c_gemm(const FjspGemmProb* probs_device, int nprob, int max_ctas, int a_op, int b_op, int passes, void* stream);
 
 /* action_result bit-fields (results[N][8]); reference dict keys in comments */
 #define FJSP_RES_SUCCESS 0x01        /* 'success' */

@@ -15,7 +15,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_PKG)
 SO_PATH = os.path.join(_PKG, "lib", "libfjsp_b200.so")
-SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("fjsp_api.cu", "fjsp_wire.cpp", "fjsp_kernels.cuh", "fjsp_a2c.cuh", "fjsp_core.h", "fjsp_host.h", "fjsp_wire.h")]
+SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("fjsp_api.cu", "fjsp_wire.cpp", "fjsp_kernels.cuh", "fjsp_a2c.cuh", "fjsp_umma.cuh", "fjsp_core.h", "fjsp_host.h", "fjsp_wire.h")]
 HEADER = os.path.join(_REPO, "include", "fjsp_b200.h")
 
 NUM_AGENTS, OBS_DIM, MASK_DIM, FLAG_DIM, INFO_DIM, MAX_ORDERS = 8, 38, 32, 4, 4, 32
@@ -75,6 +75,7 @@ EXPORTS = [
     "fjsp_num_cells", "fjsp_step_wire", "fjsp_step_host_wire", "fjsp_wire_decode", "fjsp_wire_row_bytes", "fjsp_set_decode_threads",
     "fjsp_state_total_bytes", "fjsp_state_save", "fjsp_state_load",
     "fjsp_a2c_sample", "fjsp_a2c_counter_add", "fjsp_a2c_gae", "fjsp_cells_pack_actions", "fjsp_cells_unpack_views",
+    "fjsp_a2c_gemm",
 ]
 
 
@@ -137,6 +138,7 @@ def lib() -> C.CDLL:
     L.fjsp_a2c_sample.argtypes = [vp, vp, vp, vp, i64, i64, u64, vp, u64, vp]
     L.fjsp_a2c_counter_add.argtypes = [vp, u64, vp]
     L.fjsp_a2c_gae.argtypes = [vp, vp, vp, vp, vp, C.c_int, i64, C.c_float, C.c_float, vp]
+    L.fjsp_a2c_gemm.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.fjsp_cells_pack_actions.argtypes = [vp, vp, i64, C.c_int, vp]
     L.fjsp_cells_unpack_views.argtypes = [vp] * 8 + [i64, C.c_int, vp]
     L.fjsp_export_state.argtypes = [vp, i64, vp]
@@ -184,6 +186,15 @@ def config_from_dict(d: dict | None) -> FjspConfig:
         for i, (r, c) in enumerate(pos):
             cfg.pos[i][0], cfg.pos[i][1] = int(r), int(c)
     return cfg
+
+
+OP_KC, OP_KCS, OP_MC = 0, 1, 2
+GEMM_RELU, GEMM_ATOMIC = 1, 2
+GEMM_PROB_DT = np.dtype([
+    ("A", "<u8"), ("B", "<u8"), ("C", "<u8"), ("bias", "<u8"), ("mask", "<u8"), ("colsum", "<u8"),
+    ("M", "<i4"), ("N", "<i4"), ("K", "<i4"), ("lda", "<i4"), ("ldb", "<i4"), ("csm", "<i4"), ("csn", "<i4"),
+    ("flags", "<i4"), ("splitk", "<i4"), ("reserved", "<i4", (3,))])
+assert GEMM_PROB_DT.itemsize == 96
 
 
 def order_rec(n: int, ptype: int, colour: int) -> int:

@@ -11,6 +11,7 @@
 #include "fjsp_kernels.cuh"
 #include "fjsp_wire.h"
 #include "fjsp_a2c.cuh"
+#include "fjsp_umma.cuh"
 
 using namespace fjsp;
 
@@ -128,6 +129,22 @@ static void launch_rollout(const FjspHandle* h, int steps, uint64_t seed, uint64
                                                                                             t0, steps, h->num_orders, stats);
 }
 
+// ---- tcgen05 grouped GEMM (fjsp_umma.cuh): the actor / critic layers of the batched A2C trainer ----
+template <int AOP, int BOP>
+static int launch_gemm(const void* probs, int nprob, int max_ctas, int passes, cudaStream_t st) {
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+        CK(cudaFuncSetAttribute(umma::fjsp_gemm_kernel<AOP, BOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, umma::G_SMEM_BYTES));
+        attr_dev = dev;
+    }
+    umma::fjsp_gemm_kernel<AOP, BOP><<<dim3((unsigned)max_ctas, (unsigned)nprob), umma::G_THREADS, umma::G_SMEM_BYTES, st>>>(
+        static_cast<const umma::GemmProb*>(probs), passes);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" {
 
 static void free_staging(FjspHandle* h);
@@ -222,7 +239,9 @@ int fjsp_reset(FjspHandle* h, const uint8_t* env_mask, uint64_t seed, const Fjsp
     if (num_orders < 0 || num_orders > FJSP_MAX_ORDERS) return fail("num_orders must be in 0..32");
     if ((obs == nullptr) != (masks == nullptr)) return fail("obs and masks must both be given or both be NULL");
     DeviceGuard g(h->device);
-    h->seed = seed, h->num_orders = num_orders;
+    // the handle-wide seed / num_orders are what auto-reset and the rollout kernels use for EVERY env: a masked reset
+    // (some envs only) must not change them under the envs it does not touch
+    if (!env_mask) h->seed = seed, h->num_orders = num_orders;
     DISPATCH_K(h->cells, fjsp_reset_kernel<K><<<(unsigned)h->num_tiles, TILE, 0, (cudaStream_t)stream>>>(
                              h->P, h->state, env_mask, orders, num_orders, seed, h->num_envs, h->first_env, obs, masks))
     h->launches++;
@@ -564,6 +583,21 @@ int fjsp_a2c_gae(const float* rewards, const float* values, const uint8_t* flags
                                                                                    gamma, lamb);
     CK(cudaGetLastError());
     return 0;
+}
+
+int fjsp_a2c_gemm(const FjspGemmProb* probs, int nprob, int max_ctas, int a_op, int b_op, int passes, void* stream) {
+    if (!probs) return fail("probs is NULL");
+    if (nprob < 1 || nprob > 65535 || max_ctas < 1) return fail("nprob must be in 1..65535 and max_ctas positive");
+    if (passes != 1 && passes != 3) return fail("passes must be 1 (plain TF32) or 3 (3xTF32, fp32-level accuracy)");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int combo = a_op * 3 + b_op;
+    switch (combo) {
+        case umma::OP_KC * 3 + umma::OP_MC: return launch_gemm<umma::OP_KC, umma::OP_MC>(probs, nprob, max_ctas, passes, st);
+        case umma::OP_KCS * 3 + umma::OP_MC: return launch_gemm<umma::OP_KCS, umma::OP_MC>(probs, nprob, max_ctas, passes, st);
+        case umma::OP_KC * 3 + umma::OP_KC: return launch_gemm<umma::OP_KC, umma::OP_KC>(probs, nprob, max_ctas, passes, st);
+        case umma::OP_MC * 3 + umma::OP_MC: return launch_gemm<umma::OP_MC, umma::OP_MC>(probs, nprob, max_ctas, passes, st);
+        default: return fail("unsupported operand orientation pair (supported: KC/MC, KCS/MC, KC/KC, MC/MC)");
+    }
 }
 
 }  // extern "C"

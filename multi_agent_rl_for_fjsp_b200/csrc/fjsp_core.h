@@ -365,18 +365,28 @@ FJSP_HD void reset_env(S& s, const Params& P, int num_orders, const FjspOrderRec
                        u32 episode) {
     (void)P;
     reset_env_base<K>(s, num_orders, episode);
+    bool bad = false;
     for (int o = 0; o < FJSP_MAX_ORDERS; o++) {
         u32 ow = 0u;
         if (o < num_orders) {
             if (orders) {
-                u32 r = orders[o];
-                ow = make_order((int)(r & 0xffu), (int)((r >> 8) & 0xffu), (int)((r >> 16) & 0xffu));
+                // explicit record: n in 1..9 products, type and colour in 1..3 (FJSPSimulation.py:107-112).  Anything else
+                // would overflow its bit-field in the order word, so it is clamped and the env is marked faulty.
+                const u32 r = orders[o];
+                int n = (int)(r & 0xffu), ty = (int)((r >> 8) & 0xffu), co = (int)((r >> 16) & 0xffu);
+                if (n < 1 || n > FJSP_MAX_ORDER_PRODUCTS || ty < 1 || ty > 3 || co < 1 || co > 3 || (r >> 24)) {
+                    bad = true;
+                    n = n < 1 ? 1 : n > FJSP_MAX_ORDER_PRODUCTS ? FJSP_MAX_ORDER_PRODUCTS : n;
+                    ty = ty < 1 ? 1 : ty > 3 ? 3 : ty, co = co < 1 ? 1 : co > 3 ? 3 : co;
+                }
+                ow = make_order(n, ty, co);
             } else {
                 ow = philox_order(seed, genv, episode, o);
             }
         }
         s.st(W_ORDER + o, ow);
     }
+    if (bad) s.st_hot(W_CTRL, ((u32)num_orders << 16) | ((u32)FJSP_FAULT_BAD_ORDER << 22));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,373 @@
+// fjsp_umma.cuh — tcgen05 (5th-generation tensor core) GEMM for the batched A2C trainer's actor / critic networks
+// (/root/reference/networks.py:22-61, a2c.py:168-252,647-731).  Hand-written for sm_100a:
+//   * operands are staged in shared memory in the canonical no-swizzle K-major core-matrix layout (8 rows x 16 bytes
+//     per core matrix), accumulators live in TMEM, one elected thread issues tcgen05.mma.kind::tf32, the epilogue reads
+//     the accumulator back with tcgen05.ld;
+//   * fp32-level accuracy from the TF32 pipe: every fp32 operand is split on the fly into hi = tf32(x) and
+//     lo = tf32(x - hi); acc += hi*hi + lo*hi + hi*lo  ("3xTF32": ~2^-21 relative error per product, fp32 accumulate).
+//     PASSES = 1 is plain TF32 (reported separately, never as the headline);
+//   * producers are ordinary warps (global fp32 -> registers -> split -> st.shared), because the split needs the ALUs
+//     anyway; that also lets one kernel read either operand in either orientation (forward, dX = dY W^T, dW = X^T dY)
+//     without transposed copies in HBM;
+//   * epilogues: bias + ReLU (forward), ReLU-mask + column sums (backward through a layer: dX and the bias gradient),
+//     atomic accumulate (split-K weight gradients).
+// One launch works on a TABLE of problems (blockIdx.y): the 8 actors and the critic are one grouped launch per layer.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fjsp_kernels.cuh"
+
+namespace fjsp {
+namespace umma {
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem]^T, both K-major, tf32 inputs, fp32 accumulate; issued by ONE thread for the CTA
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all MMAs issued so far by this thread arrive on `bar` when they have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// mbarrier wait that gives up loudly: a malformed descriptor or a lost arrive would otherwise hang the GPU box (the
+// MMA pipeline's barriers are completed by hardware events); ~2 s at 2 GHz, far beyond any legitimate wait
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 16 consecutive accumulator columns of this thread's TMEM lane (lane = 32 * (warp % 4) + laneid)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+// Shared-memory matrix descriptor (tcgen05 "matrix descriptor", no swizzle, K-major): start address, leading-dimension
+// byte offset (distance between the two 16-byte K-halves = core matrices adjacent in K), stride byte offset (distance
+// between 8-row groups), all in units of 16 bytes; bits 46..47 = 0b01 (sm_100 descriptor version).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+// Instruction descriptor, kind::tf32: D = f32 (bits 4..5 = 1), A and B = tf32 (bits 7..9, 10..12 = 2), both K-major
+// (bits 15, 16 = 0), N >> 3 at bits 17..22, M >> 4 at bits 24..28.
+__host__ __device__ constexpr uint32_t instr_desc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Grouped GEMM
+// ---------------------------------------------------------------------------------------------------------------
+// C[M x N] (+)= A[M x K] * B[N x K]^T for every problem of a table.  How A(m, k) and B(n, k) are read from global
+// memory is a template parameter of the kernel (the same for all problems of a launch):
+//   OP_KC  : k contiguous        X(r, k) = X[r * ld + k]        16-byte loads (ld % 4 == 0, pointer 16-byte aligned, K % 4 == 0)
+//   OP_KCS : the same, scalar loads (any alignment, any K)
+//   OP_MC  : r contiguous        X(r, k) = X[k * ld + r]
+enum { OP_KC = 0, OP_KCS = 1, OP_MC = 2 };
+enum { GEMM_RELU = 1, GEMM_ATOMIC = 2 };
+
+struct GemmProb {          // 96 bytes; device array, one per problem
+    const float* A;
+    const float* B;
+    float* C;
+    const float* bias;     // [N] added to every row, or null
+    const float* mask;     // same indexing as C: C = acc * (mask > 0), or null
+    float* colsum;         // [N]: += column sums of what was stored (bias gradient), or null
+    int32_t M, N, K;       // N <= 256
+    int32_t lda, ldb;
+    int32_t csm, csn;      // C(m, n) = C[m * csm + n * csn]
+    int32_t flags;         // GEMM_RELU, GEMM_ATOMIC (atomicAdd into C: split-K partial sums)
+    int32_t splitk;        // >= 1: the K range is cut into this many parts, one CTA each
+    int32_t reserved[3];
+};
+static_assert(sizeof(GemmProb) == 96, "GemmProb layout is part of the ABI (include/fjsp_b200.h FjspGemmProb)");
+
+constexpr int G_BM = 128;             // rows per CTA tile = TMEM lanes
+constexpr int G_BN = 256;             // max columns per CTA tile = TMEM columns
+constexpr int G_KC = 16;              // K per pipeline stage (two tf32 MMAs of K = 8)
+constexpr int G_NQ = G_KC / 4;        // 16-byte K-quads per stage
+constexpr int G_PAD = 32;             // bytes between K-quad planes: keeps the producers' st.shared.v4 conflict-free
+constexpr int G_LBO_A = G_BM * 16 + G_PAD, G_LBO_B = G_BN * 16 + G_PAD;  // K-quad plane = all rows' 16-byte pieces
+constexpr int G_A_BYTES = G_NQ * G_LBO_A, G_B_BYTES = G_NQ * G_LBO_B;    // one of (hi, lo)
+constexpr int G_STAGE_BYTES = 2 * (G_A_BYTES + G_B_BYTES);
+constexpr int G_STAGES = 2;
+constexpr int G_SMEM_BYTES = G_STAGES * G_STAGE_BYTES;                   // 99,328: two CTAs per SM
+constexpr int G_PRODUCERS = 256;      // warps 0..7 load; warps 0..3 are also the epilogue; warp 8 issues the MMAs
+constexpr int G_THREADS = G_PRODUCERS + 32;
+
+__device__ __forceinline__ uint32_t plane_off(int r, int q, int lbo) { return (uint32_t)(q * lbo + (r >> 3) * 128 + (r & 7) * 16); }
+
+__device__ __forceinline__ void split_store(unsigned char* hi, unsigned char* lo, uint32_t off, float4 v, bool three) {
+    uint4 h = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    *reinterpret_cast<uint4*>(hi + off) = h;
+    if (three) {
+        uint4 l = make_uint4(to_tf32(v.x - __uint_as_float(h.x)), to_tf32(v.y - __uint_as_float(h.y)),
+                             to_tf32(v.z - __uint_as_float(h.z)), to_tf32(v.w - __uint_as_float(h.w)));
+        *reinterpret_cast<uint4*>(lo + off) = l;
+    }
+}
+
+// One operand tile of ROWS rows x G_KC k, fetched into registers (`fetch`) and later split + stored (`stash`).
+template <int OP, int ROWS>
+struct Loader {
+    static constexpr int ITEMS = OP == OP_MC ? (ROWS == 128 ? G_NQ / 2 : G_NQ) : ROWS * G_NQ / G_PRODUCERS;
+    float4 v[ITEMS];
+    __device__ __forceinline__ void fetch(const float* __restrict__ X, int ld, int r0, int rmax, int k0, int kmax, int tid) {
+        if (OP == OP_MC) {
+            // thread -> one row r (contiguous across the warp), a few K-quads; 4 coalesced scalar loads per quad
+            const int r = ROWS == 128 ? (tid & 127) : tid;
+            const int qb = ROWS == 128 ? (tid >> 7) : 0, qs = ROWS == 128 ? 2 : 1;
+            const bool rok = r0 + r < rmax;
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                const int k = k0 + 4 * (qb + qs * i);
+                const float* p = X + (int64_t)k * ld + r0 + r;
+                v[i].x = (rok && k + 0 < kmax) ? __ldg(p) : 0.f;
+                v[i].y = (rok && k + 1 < kmax) ? __ldg(p + ld) : 0.f;
+                v[i].z = (rok && k + 2 < kmax) ? __ldg(p + 2 * (int64_t)ld) : 0.f;
+                v[i].w = (rok && k + 3 < kmax) ? __ldg(p + 3 * (int64_t)ld) : 0.f;
+            }
+        } else {
+            // thread -> (row, K-quad) with the quad index fastest: a warp reads 8 rows x 64 contiguous bytes
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                const int idx = tid + i * G_PRODUCERS, r = idx / G_NQ, q = idx % G_NQ;
+                const int k = k0 + 4 * q;
+                const float* p = X + (int64_t)(r0 + r) * ld + k;
+                const bool rok = r0 + r < rmax;
+                if (OP == OP_KC) {
+                    v[i] = (rok && k < kmax) ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    v[i].x = (rok && k + 0 < kmax) ? __ldg(p) : 0.f;
+                    v[i].y = (rok && k + 1 < kmax) ? __ldg(p + 1) : 0.f;
+                    v[i].z = (rok && k + 2 < kmax) ? __ldg(p + 2) : 0.f;
+                    v[i].w = (rok && k + 3 < kmax) ? __ldg(p + 3) : 0.f;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void stash(unsigned char* hi, unsigned char* lo, int lbo, int tid, bool three) const {
+        if (OP == OP_MC) {
+            const int r = ROWS == 128 ? (tid & 127) : tid;
+            const int qb = ROWS == 128 ? (tid >> 7) : 0, qs = ROWS == 128 ? 2 : 1;
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) split_store(hi, lo, plane_off(r, qb + qs * i, lbo), v[i], three);
+        } else {
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                const int idx = tid + i * G_PRODUCERS;
+                split_store(hi, lo, plane_off(idx / G_NQ, idx % G_NQ, lbo), v[i], three);
+            }
+        }
+    }
+};
+
+// 16 per-thread values (one row, 16 columns) -> per-column sums over the warp's 32 rows: transposing butterfly, 16
+// shuffles; on return lane l holds in v[0] the sum of column ((l >> 4) & 1) * 8 + ((l >> 3) & 1) * 4 + ((l >> 2) & 1) * 2 + ((l >> 1) & 1)
+__device__ __forceinline__ float warp_colsum16(float* v, int lane) {
+#pragma unroll
+    for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+        const bool up = lane & bit;
+#pragma unroll
+        for (int i = 0; i < w; i++) {
+            const float keep = up ? v[i + w] : v[i], send = up ? v[i] : v[i + w];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+template <int AOP, int BOP>
+__global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb* __restrict__ probs, int passes) {
+    extern __shared__ __align__(128) unsigned char g_smem[];
+    __shared__ uint64_t s_full[G_STAGES], s_empty[G_STAGES], s_acc;
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_colsum[G_BN];
+
+    const GemmProb P = probs[blockIdx.y];
+    const int mtiles = (P.M + G_BM - 1) / G_BM;
+    const int splitk = P.splitk > 0 ? P.splitk : 1;
+    if ((int)blockIdx.x >= mtiles * splitk) return;
+    const int mt = blockIdx.x % mtiles, sp = blockIdx.x / mtiles;
+    const int m0 = mt * G_BM;
+    const int npad = (P.N + 15) & ~15;
+    const int chunks_all = (P.K + G_KC - 1) / G_KC;
+    const int per = (chunks_all + splitk - 1) / splitk;
+    const int c_begin = sp * per, c_end = min(chunks_all, c_begin + per);
+    const int nchunks = c_end - c_begin;
+    if (nchunks <= 0) return;
+    const bool three = passes >= 3;
+    uint32_t ncols = 32;
+    while ((int)ncols < npad) ncols <<= 1;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < G_STAGES; s++) mbar_init(&s_full[s], G_PRODUCERS / 32), mbar_init(&s_empty[s], 1);
+        mbar_init(&s_acc, 1);
+    }
+    if (tid < G_BN) s_colsum[tid] = 0.f;
+    if (warp == G_PRODUCERS / 32) tmem_alloc(&s_tmem, ncols);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = s_tmem;
+
+    if (warp < G_PRODUCERS / 32) {
+        // ===== producers: global fp32 -> registers -> (hi, lo) tf32 -> shared memory, one stage ahead in registers =====
+        Loader<AOP, G_BM> la;
+        Loader<BOP, G_BN> lb;
+        la.fetch(P.A, P.lda, m0, P.M, c_begin * G_KC, P.K, tid);
+        lb.fetch(P.B, P.ldb, 0, P.N, c_begin * G_KC, P.K, tid);
+        for (int c = 0; c < nchunks; c++) {
+            const int s = c % G_STAGES;
+            if (c >= G_STAGES) mbar_wait_or_trap(&s_empty[s], ((c / G_STAGES) - 1) & 1);
+            unsigned char* st = g_smem + s * G_STAGE_BYTES;
+            la.stash(st, st + G_A_BYTES, G_LBO_A, tid, three);
+            lb.stash(st + 2 * G_A_BYTES, st + 2 * G_A_BYTES + G_B_BYTES, G_LBO_B, tid, three);
+            fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_full[s]);
+            if (c + 1 < nchunks) {
+                la.fetch(P.A, P.lda, m0, P.M, (c_begin + c + 1) * G_KC, P.K, tid);
+                lb.fetch(P.B, P.ldb, 0, P.N, (c_begin + c + 1) * G_KC, P.K, tid);
+            }
+        }
+    } else if (lane == 0) {
+        // ===== MMA issuer: one thread =====
+        const uint32_t idesc = instr_desc_tf32(G_BM, npad);
+        const uint32_t sbase = smem_u32(g_smem);
+        for (int c = 0; c < nchunks; c++) {
+            const int s = c % G_STAGES;
+            mbar_wait_or_trap(&s_full[s], (c / G_STAGES) & 1);
+            fence_after_sync();
+            const uint32_t a_hi = sbase + s * G_STAGE_BYTES, a_lo = a_hi + G_A_BYTES;
+            const uint32_t b_hi = a_hi + 2 * G_A_BYTES, b_lo = b_hi + G_B_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < G_KC / 8; ks++) {
+                const uint64_t ah = smem_desc(a_hi + 2 * ks * G_LBO_A, G_LBO_A, 128), bh = smem_desc(b_hi + 2 * ks * G_LBO_B, G_LBO_B, 128);
+                if (three) {  // small terms first
+                    const uint64_t al = smem_desc(a_lo + 2 * ks * G_LBO_A, G_LBO_A, 128), bl = smem_desc(b_lo + 2 * ks * G_LBO_B, G_LBO_B, 128);
+                    mma_tf32(tmem, al, bh, idesc, (c | ks) != 0);
+                    mma_tf32(tmem, ah, bl, idesc, 1u);
+                    mma_tf32(tmem, ah, bh, idesc, 1u);
+                } else {
+                    mma_tf32(tmem, ah, bh, idesc, (c | ks) != 0);
+                }
+            }
+            mma_commit(&s_empty[s]);  // the stage is free again once these MMAs have read it
+        }
+        mma_commit(&s_acc);           // accumulator complete
+    }
+
+    if (warp < 4) {
+        // ===== epilogue: thread = one row of the tile (TMEM lane 32 * warp + lane) =====
+        mbar_wait_or_trap(&s_acc, 0);
+        fence_after_sync();
+        const int m = m0 + warp * 32 + lane;
+        const bool mok = m < P.M;
+        const bool atomic = P.flags & GEMM_ATOMIC, relu = P.flags & GEMM_RELU;
+        const bool vec = !atomic && P.csn == 1 && (P.csm & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0) &&
+                         (!P.mask || (reinterpret_cast<uintptr_t>(P.mask) & 15) == 0);
+        for (int n0 = 0; n0 < npad; n0 += 16) {
+            float v[16];
+            tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, v);
+            if (P.bias) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] += (n0 + i < P.N) ? __ldg(P.bias + n0 + i) : 0.f;
+            }
+            if (relu) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f);
+            }
+            float* crow = P.C + (int64_t)m * P.csm;
+            const float* mrow = P.mask ? P.mask + (int64_t)m * P.csm : nullptr;
+            if (vec && n0 + 16 <= P.N) {
+                if (mok) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        if (mrow) {
+                            const float4 k4 = __ldg(reinterpret_cast<const float4*>(mrow + n0) + i);
+                            o.x = k4.x > 0.f ? o.x : 0.f, o.y = k4.y > 0.f ? o.y : 0.f, o.z = k4.z > 0.f ? o.z : 0.f, o.w = k4.w > 0.f ? o.w : 0.f;
+                            v[4 * i] = o.x, v[4 * i + 1] = o.y, v[4 * i + 2] = o.z, v[4 * i + 3] = o.w;
+                        }
+                        reinterpret_cast<float4*>(crow + n0)[i] = o;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const int n = n0 + i;
+                    if (mok && n < P.N) {
+                        if (mrow && !(__ldg(mrow + (int64_t)n * P.csn) > 0.f)) v[i] = 0.f;
+                        if (atomic) atomicAdd(crow + (int64_t)n * P.csn, v[i]);
+                        else crow[(int64_t)n * P.csn] = v[i];
+                    }
+                }
+            }
+            if (P.colsum) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] = mok ? v[i] : 0.f;
+                const float sum = warp_colsum16(v, lane);
+                const int col = n0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                if (!(lane & 1)) atomicAdd(&s_colsum[col], sum);
+            }
+        }
+        fence_before_sync();
+    }
+    __syncthreads();
+    if (P.colsum && tid < P.N) atomicAdd(P.colsum + tid, s_colsum[tid]);
+    if (warp == G_PRODUCERS / 32) {
+        __syncwarp();
+        fence_after_sync();
+        tmem_dealloc(tmem, ncols);
+    }
+}
+
+}  // namespace umma
+}  // namespace fjsp

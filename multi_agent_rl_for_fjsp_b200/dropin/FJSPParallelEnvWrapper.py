@@ -296,9 +296,15 @@ class FJSPParallelEnv(_Base):
                     rewards[aid] += 1.0
                 elif kind == "agv" and res & 0x02:  # implicit IDLE while moving is not an invalid action
                     rewards[aid] += 5.0
-        if flags[2]:
+        if flags[2] == 1:  # FJSP_FAULT_PKG_RESTART_WITH_WAITERS: the one exception the reference itself raises
             raise ValueError("list.remove(x): x not in list  [packaging START while requests were still waiting; "
                              "the reference raises here too (SURVEY R-PKG-cap-b)]")
+        if flags[2]:      # limits of the packed state: not reference behaviour, reported as such
+            what = {2: "more than %d trays in transit (tray pool of the packed state)" % 64,
+                    3: "an order record outside n 1..9 / type 1..3 / colour 1..3",
+                    4: "stepped past the end of the episode (call reset() after truncation)",
+                    5: "more open orders than the order ring of the packed state holds"}.get(int(flags[2]), "fault %d" % int(flags[2]))
+            raise RuntimeError("fjsp_b200 capacity limit, not a reference error: " + what)
         terminated, truncated = bool(flags[0]), bool(flags[1])
         terminations = {aid: terminated for aid in ids}
         truncations = {aid: truncated for aid in ids}

@@ -137,11 +137,15 @@ class BatchedFJSPEnv:
             self.num_orders = int(num_orders)
         d_orders = None
         if orders is not None:
+            if self.autoreset:
+                raise ValueError("explicit order tables describe ONE episode; with autoreset=True every later episode would "
+                                 "silently draw Philox orders instead — create the env with autoreset=False to use them")
             d_orders = self._pack_orders(orders)
         d_mask = None
         if env_mask is not None:
             d_mask = torch.as_tensor(env_mask, device=self.device).to(torch.uint8).contiguous()
             assert d_mask.numel() == self.num_envs
+        # (a masked reset leaves the handle-wide seed / num_orders — used by auto-reset for every env — untouched)
         abi.check(self._L.fjsp_reset(self._h, _ptr(d_mask), self.seed, _ptr(d_orders), self.num_orders, _ptr(self.obs),
                                      _ptr(self.masks), self._stream()))
         self._keep = (d_orders, d_mask)  # keep the buffers alive until the stream has consumed them
@@ -159,6 +163,10 @@ class BatchedFJSPEnv:
             arr = packed
         arr = np.ascontiguousarray(arr, dtype=np.uint32)
         assert arr.shape == (self.num_envs, abi.MAX_ORDERS), arr.shape
+        live = arr[:, :self.num_orders]
+        n, ty, co = live & 0xff, (live >> 8) & 0xff, (live >> 16) & 0xff
+        if live.size and not (((n >= 1) & (n <= 9) & (ty >= 1) & (ty <= 3) & (co >= 1) & (co <= 3) & ((live >> 24) == 0)).all()):
+            raise ValueError("order records must have n in 1..9, type in 1..3, colour in 1..3 (FJSPSimulation.py:107-112)")
         return torch.from_numpy(arr.view(np.int32)).to(self.device)
 
     def step(self, actions: torch.Tensor):

@@ -17,6 +17,16 @@ import sys
 import types
 
 
+def _load_stand_in(compat_dir, name):
+    """Register compat/<name> (a package directory) as top-level module `name`, submodules resolved lazily from it."""
+    init = os.path.join(compat_dir, name, "__init__.py")
+    spec = importlib.util.spec_from_file_location(name, init, submodule_search_locations=[os.path.join(compat_dir, name)])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
     if len(argv) < 2:
@@ -24,10 +34,11 @@ def main(argv=None):
     ref_root, script = os.path.abspath(argv[0]), argv[1]
     pkg = os.path.dirname(os.path.abspath(__file__))
     sys.path.insert(0, ref_root)
+    # stand-ins ONLY for the packages that are really missing: each one is loaded from compat/<name> under its own name,
+    # so an installed gymnasium is never shadowed because, say, matplotlib is absent
     for mod in ("gymnasium", "pettingzoo", "matplotlib"):
         if importlib.util.find_spec(mod) is None:
-            sys.path.insert(0, os.path.join(pkg, "compat"))
-            break
+            _load_stand_in(os.path.join(pkg, "compat"), mod)
     sys.path.insert(0, os.path.join(pkg, "dropin"))
     sys.path.insert(0, os.path.dirname(pkg))
     # the reference's `utils` / `enums` are namespace directories that site-packages may shadow

@@ -1,0 +1,71 @@
+"""Host side of the tcgen05 grouped GEMM (``fjsp_a2c_gemm``, csrc/fjsp_umma.cuh): problem tables.
+
+A table is a device-resident array of ``FjspGemmProb`` records (include/fjsp_b200.h) built once over static buffers —
+the trainer's rollout and update replay from CUDA graphs, so every pointer is fixed for the life of the trainer — and
+launched with one call.  All problems of a table share the operand orientation pair.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import abi
+
+OP_KC, OP_KCS, OP_MC = abi.OP_KC, abi.OP_KCS, abi.OP_MC
+RELU, ATOMIC = abi.GEMM_RELU, abi.GEMM_ATOMIC
+BM = 128
+
+
+def _addr(t, off=0):
+    return 0 if t is None else t.data_ptr() + 4 * int(off)
+
+
+class GemmTable:
+    """C[M x N] (+)= A[M x K] @ B[N x K]^T for a list of problems, one launch.
+
+    ``add`` takes tensors (fp32, on the table's device) plus element offsets into them, so slices of bigger buffers
+    (an observation slice, one actor of a stacked parameter) need no copies.  Orientation ``a_op`` / ``b_op``:
+    OP_KC / OP_KCS: X(r, k) = X[r * ld + k]; OP_MC: X(r, k) = X[k * ld + r]."""
+
+    def __init__(self, device, a_op, b_op, passes=3):
+        self.device, self.a_op, self.b_op, self.passes = torch.device(device), int(a_op), int(b_op), int(passes)
+        self.rows, self.keep = [], []
+        self.dev_table = None
+        self.max_ctas = 1
+
+    def add(self, A, B, Cm, M, N, K, lda, ldb, csm, csn=1, a_off=0, b_off=0, c_off=0, bias=None, bias_off=0, mask=None,
+            mask_off=0, colsum=None, colsum_off=0, relu=False, atomic=False, splitk=1):
+        assert 1 <= N <= 256 and M >= 1 and K >= 1 and splitk >= 1
+        for t in (A, B, Cm, bias, mask, colsum):
+            assert t is None or (t.dtype == torch.float32 and t.device == self.device), "fp32 tensors on the table's device"
+        if self.a_op == OP_KC:
+            assert lda % 4 == 0 and K % 4 == 0 and _addr(A, a_off) % 16 == 0, "OP_KC needs 16-byte aligned rows"
+        if self.b_op == OP_KC:
+            assert ldb % 4 == 0 and K % 4 == 0 and _addr(B, b_off) % 16 == 0, "OP_KC needs 16-byte aligned rows"
+        r = np.zeros((), dtype=abi.GEMM_PROB_DT)
+        r["A"], r["B"], r["C"] = _addr(A, a_off), _addr(B, b_off), _addr(Cm, c_off)
+        r["bias"], r["mask"], r["colsum"] = _addr(bias, bias_off), _addr(mask, mask_off), _addr(colsum, colsum_off)
+        r["M"], r["N"], r["K"], r["lda"], r["ldb"], r["csm"], r["csn"] = M, N, K, lda, ldb, csm, csn
+        r["flags"] = (RELU if relu else 0) | (ATOMIC if atomic else 0)
+        r["splitk"] = splitk
+        self.rows.append(r)
+        self.keep += [A, B, Cm, bias, mask, colsum]
+        self.max_ctas = max(self.max_ctas, (M + BM - 1) // BM * splitk)
+        self.dev_table = None
+        return self
+
+    def finalize(self):
+        host = np.stack(self.rows)
+        self.dev_table = torch.from_numpy(host.view(np.uint8).reshape(len(self.rows), -1).copy()).to(self.device)
+        return self
+
+    def launch(self, stream=None, passes=None):
+        if self.dev_table is None:
+            self.finalize()
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        rc = abi.lib().fjsp_a2c_gemm(C.c_void_p(self.dev_table.data_ptr()), len(self.rows), self.max_ctas, self.a_op, self.b_op,
+                                     self.passes if passes is None else int(passes), C.c_void_p(st))
+        if rc:
+            abi.check(rc)

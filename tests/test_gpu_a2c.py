@@ -95,3 +95,46 @@ def test_training_runs_and_fused_path_matches_torch_path(graph):
     b = run(False)
     assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
     assert torch.allclose(a[0], b[0], rtol=1e-5, atol=1e-6)
+
+
+def test_reference_layout_checkpoint_round_trip_on_device(tmp_path):
+    """SURVEY §8f rank 4 on the device: a file written by ``save_reference_checkpoint`` (the dict layout of the
+    reference's ``MultiAgentA2C.save_model``, a2c.py:745-752) is read back by plain ``nn.Sequential`` networks shaped like
+    the reference's (networks.py:22-61) and by a second ``ActorCritic`` on the GPU; all three agree on device."""
+    from multi_agent_rl_for_fjsp_b200.a2c_batched import ActorCritic
+    from multi_agent_rl_for_fjsp_b200.env import AGENT_IDS, MASK_OFFSETS, N_ACTIONS, OBS_SLICES
+
+    dev = torch.device("cuda:0")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    src = ActorCritic(device=dev, seed=123)
+    path = str(tmp_path / "model.pt")
+    src.save_reference_checkpoint(path)
+    ckpt = torch.load(path, weights_only=True, map_location="cpu")
+    assert set(ckpt) == {"actor_nets", "critic_net", "obs_dims", "act_dims", "global_obs_dim", "possible_agents"}
+    assert ckpt["possible_agents"] == list(AGENT_IDS) and ckpt["global_obs_dim"] == 38
+
+    def sequential(sd, dims, softmax):
+        layers = []
+        for i in range(len(dims) - 1):
+            layers.append(torch.nn.Linear(dims[i], dims[i + 1]))
+            if i < len(dims) - 2:
+                layers.append(torch.nn.ReLU())
+        net = torch.nn.Sequential(*layers)
+        net.load_state_dict({k[len("net."):]: v for k, v in sd.items()})
+        return net.to(dev), softmax
+
+    g = torch.Generator(device=dev).manual_seed(1)
+    obs = torch.randint(0, 6, (512, 38), device=dev, generator=g).float()
+    dst = ActorCritic(device=dev, seed=7)
+    dst.load_reference_checkpoint(path)
+    with torch.no_grad():
+        p_src, p_dst = src.probs32(obs), dst.probs32(obs)
+        v_src, v_dst = src.value(obs), dst.value(obs)
+        assert torch.equal(p_src, p_dst) and torch.equal(v_src, v_dst)
+        for i, a in enumerate(AGENT_IDS):
+            lo, hi = OBS_SLICES[i]
+            net, _ = sequential(ckpt["actor_nets"][a], [hi - lo, 256, 256, N_ACTIONS[i]], True)
+            ref = torch.softmax(net(obs[:, lo:hi]), -1)
+            assert torch.allclose(p_src[:, MASK_OFFSETS[i]:MASK_OFFSETS[i] + N_ACTIONS[i]], ref, rtol=1e-5, atol=1e-6), a
+        critic, _ = sequential(ckpt["critic_net"], [38, 256, 256, 128, 1], False)
+        assert torch.allclose(v_src, critic(obs).squeeze(-1), rtol=1e-5, atol=1e-5)

@@ -55,6 +55,43 @@ def test_dict_api_episode_matches_oracle(FJSPParallelEnv):
     env.close()
 
 
+def test_config1_10k_steps_through_the_dict_api_bit_exact(FJSPParallelEnv):
+    """BASELINE.json configs[0], literally: the default layout, 1 env, uniform-random actions, 10,000 steps through the
+    dict FJSPParallelEnv on the device, against the trajectory recorded from the unmodified reference
+    (tests/golden/config1_uniform.npz): per step observation, masks, rewards, flags, infos and the canonical-state digest."""
+    from tests.util import REL_TOL, digest, load_golden
+
+    g, _ = load_golden("config1_uniform")
+    T = g["actions"].shape[0]
+    assert T == 10000
+    env = FJSPParallelEnv()
+    ids = env.possible_agents
+    ep_start = g["ep_start"].tolist()
+    ep = 0
+    for t in range(T):
+        if ep < len(ep_start) and ep_start[ep] == t:
+            assert t == 0 or not env.agents  # the reference's loop resets when `agents` is empty
+            no = int(g["ep_norders"][ep])
+            table = [tuple(int(v) for v in row) for row in g["ep_orders"][ep][:no]]
+            env._gen_orders = lambda n, table=table: setattr(env, "_orders", list(table))  # the golden's explicit order table
+            obs, infos = env.reset(options={"num_orders": no})
+            o, m = canon.flatten_reference_obs(obs)
+            assert np.array_equal(o, g["ep_obs0"][ep]) and np.array_equal(m, g["ep_masks0"][ep]), ep
+            ep += 1
+        assert env.agents == ids
+        a = g["actions"][t]
+        obs, rew, te, tr, inf = env.step({aid: int(a[i]) for i, aid in enumerate(ids)})
+        o, m = canon.flatten_reference_obs(obs)
+        assert np.array_equal(o, g["obs"][t]), t
+        assert np.array_equal(m, g["masks"][t]), t
+        r = np.array([rew[x] for x in ids])
+        assert np.all(np.abs(r - g["rewards"][t]) <= REL_TOL * np.abs(g["rewards"][t])), t
+        assert all(te[x] == bool(g["flags"][t][0]) and tr[x] == bool(g["flags"][t][1]) for x in ids), t
+        assert digest(env._canon()) == g["hashes"][t], t
+    assert ep == len(ep_start)
+    env.close()
+
+
 def test_dict_api_on_the_scaled_shop_matches_restatement(FJSPParallelEnv):
     """config={'num_cells': 4}: 29 agents through the dict API on the device == the C restatement of the extension."""
     from oracle.fjsp_oracle import default_config

@@ -51,8 +51,50 @@ class GpuSingle:
 @pytest.mark.parametrize("name", GOLDEN_FILES)
 def test_gpu_replays_golden(name):
     """Every golden trajectory of the reference, step by step, through fjsp_reset/fjsp_step/fjsp_export_state."""
-    steps = replay_golden(name, lambda cfg: GpuSingle(cfg), max_steps=2500)
-    assert steps > 0
+    steps = replay_golden(name, lambda cfg: GpuSingle(cfg))  # every step of every golden: 35,700 in all
+    assert steps == load_golden(name)[0]["actions"].shape[0]
+
+
+@pytest.mark.parametrize("name", GOLDEN_FILES)
+def test_gpu_golden_every_step_as_lockstep_batch(name):
+    """The same goldens with one env per EPISODE stepped in lockstep as one batch (the way the kernels are meant to be
+    used): every step of every episode is compared — observation, masks, rewards, flags and the canonical-state digest."""
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+    from tests.util import digest
+
+    g, cfgd = load_golden(name)
+    T = g["actions"].shape[0]
+    starts = g["ep_start"].tolist() + [T]
+    E = len(starts) - 1
+    lens = [starts[i + 1] - starts[i] for i in range(E)]
+    env = BatchedFJSPEnv(E, config=_abi_cfg(cfg_from_dict(cfgd)), autoreset=False)
+    orders = np.zeros((E, 32), dtype=np.uint32)
+    for e in range(E):
+        no = int(g["ep_norders"][e])
+        t = g["ep_orders"][e][:no]
+        orders[e, :no] = t[:, 0] | (t[:, 1] << 8) | (t[:, 2] << 16)
+    for no in sorted(set(int(x) for x in g["ep_norders"])):
+        obs0, masks0 = env.reset(num_orders=no, orders=orders, env_mask=(g["ep_norders"] == no).astype(np.uint8))
+    obs0, masks0 = obs0.cpu().numpy(), masks0.cpu().numpy()
+    for e in range(E):
+        assert np.array_equal(obs0[e], g["ep_obs0"][e]) and np.array_equal(masks0[e], g["ep_masks0"][e]), e
+    compared = 0
+    for k in range(max(lens)):
+        acts = np.zeros((E, 8), dtype=np.uint8)
+        live = [e for e in range(E) if k < lens[e]]
+        for e in live:
+            acts[e] = g["actions"][starts[e] + k]
+        obs, rew, term, trunc, masks = env.step(torch.as_tensor(acts, device=env.device))
+        obs, rew, masks, flags = obs.cpu().numpy(), rew.cpu().numpy(), masks.cpu().numpy(), env.flags.cpu().numpy()
+        for e in live:
+            t = starts[e] + k
+            assert np.array_equal(obs[e], g["obs"][t]), (name, e, k)
+            assert np.array_equal(masks[e], g["masks"][t]), (name, e, k)
+            assert np.all(np.abs(rew[e] - g["rewards"][t]) <= REL_TOL * np.abs(g["rewards"][t])), (name, e, k)
+            assert tuple(flags[e][:2]) == tuple(g["flags"][t]) and flags[e][2] == 0, (name, e, k)
+            assert digest(env.export_state(e)) == g["hashes"][t], (name, e, k)
+            compared += 1
+    assert compared == T
 
 
 def test_gpu_golden_episodes_in_one_batch():

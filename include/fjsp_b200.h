@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define FJSP_ABI_VERSION 2
+#define FJSP_ABI_VERSION 3
 
 /* ---- fixed shape of the problem (reference: 8 agents, FJSPSimulation.py:62-82) ---- */
 #define FJSP_NUM_AGENTS 8          /* pickup_station, agv, small_machine, big_machine, packaging_blue_1, _blue_2, _red, _green */
@@ -54,17 +54,27 @@ extern "C" {
 
 /* ---- wire rows: the compact form in which a step's results cross PCIe on the host-buffer path (fjsp_step_host) and
  * which fjsp_step_wire / fjsp_wire_decode expose.  Everything a step returns is a small integer, so one env's results
- * are FJSP_WIRE_WORDS_K(K) u32 (64 B for K = 1, against 220 B of float32 tensors):
- *   obs    : one byte per observation field, 4 per word: the field's integer value; a station index (LocationType
- *            order) in BOTH AGV position fields (decoded through FjspConfig.pos); the table index L for a packaging
- *            station's processing_progress (decoded to float32(100/L), 0 for L = 0); queue_length as the int8 it is
- *   masks  : one bit per mask byte, 32 per word
- *   reward : one word = g (24-bit signed) | flag bits << 24 (terminated, truncated, fault x2, was_reset), then local_i
- *            (int16 per action column): reward_i = (g + A * local_i) / (10 * A), A = 1 + 7K — the exact integer
- *            numerator of every reward (all RewardModel constants are multiples of 0.1)
- * fjsp_wire_decode turns rows back into exactly the tensors fjsp_step writes (bit for bit). */
-#define FJSP_WIRE_WORDS_K(k) \
-    ((((FJSP_OBS_DIM_K(k) + 3) / 4 + FJSP_MASK_DIM_K(k) / 32 + 1 + FJSP_ACT_DIM_K(k) / 2) + 1) / 2 * 2)
+ * are bit-fields in FJSP_WIRE_WORDS_K(K) u32 — 32 bytes for K = 1, against 220 bytes of float32 / int8 tensors:
+ *   word 0  pickup station: current_tray_color2 | current_tray_count3<<2 | current_tray_type2<<5 | next_product_color2<<7 |
+ *           next_product_type2<<9 | order_size4<<11 | products_remaining4<<15 ; flag bits<<19 (terminated, truncated,
+ *           fault x3, was_reset) ; its action-mask bits 1,2 <<25 ; its reward code2<<27
+ *   word 1  products packaged by this step 10 | orders completed by this step 9<<10 | pickup_ready_trays 13<<19
+ *   then five words per cell c (2 + 5c ..):
+ *   +0  agv: station index3 (LocationType order; decoded through FjspConfig.pos into BOTH position fields) | carrying1<<3 |
+ *       tray_needs_processing1<<4 | tray_product_count3<<5 | tray_type2<<8 | big_machine_ready6<<10 |
+ *       small_machine_ready6<<16 | agv mask bits 1..7 <<22 | agv reward code3<<29
+ *   +1  storage_tray_count8 | small machine (is_busy1, progress1, queue_length6)<<8 | big machine<<16 |
+ *       small mask bits 1,2 <<24 | big<<26 | small reward code2<<28 | big<<30
+ *   +2  packaging_blue_1 | packaging_green: progress index8<<21, is_busy1<<29, mask bits 1,2 <<30
+ *   +3  packaging_blue_2 | packaging_green: queue_length8<<21, reward code2<<29
+ *   +4  packaging_red           with station = is_busy1 | progress index L8<<1 (decoded to float32(100/L), 0 for 0) |
+ *                               queue_length8<<9 (the int8 it is) | mask bits 1,2 <<17 | reward code2<<19
+ * Mask bit 0 of every agent is the constant 1.  A reward code selects one of the few local rewards an agent kind can get
+ * (tenths: pickup {0,-10,+10,+60}, agv {0,-1,+20,+120,-50}, machine {0,-20,+10,+50}, packaging {0,-10,+20,+200};
+ * RewardModel.py:46-97): reward_i = (g + A * local_i) / (10 * A) with g = 10 * (100 * orders + 10 * products) - step_size and
+ * A = 1 + 7K — the exact integer numerator of every reward.  fjsp_wire_decode turns rows back into exactly the
+ * tensors fjsp_step writes (bit for bit). */
+#define FJSP_WIRE_WORDS_K(k) (((2 + 5 * (k)) + 1) / 2 * 2)
 
 /* fault codes (flags[2]); the reference has no equivalent — see DESIGN.md "faults" */
 #define FJSP_FAULT_NONE 0
@@ -256,7 +266,7 @@ int fjsp_cells_unpack_views(const float* obs, const int8_t* masks, const float* 
  * Operand orientation (the same for all problems of a call): FJSP_OP_KC  X(r,k) = X[r*ld + k] with 16-byte loads
  * (ld % 4 == 0, 16-byte aligned pointer, K % 4 == 0), FJSP_OP_KCS the same with scalar loads (any alignment),
  * FJSP_OP_MC  X(r,k) = X[k*ld + r].  Supported (a_op, b_op): (KC,MC) forward y = x W, (KCS,MC) forward from an
- * unaligned observation slice, (KC,KC) dx = dy W^T, (MC,MC) dW = x^T dy.
+ * unaligned observation slice, (KC,KC) dx = dy W^T, (KCS,KCS) the same from unaligned rows, (MC,MC) dW = x^T dy.
  * Epilogue per problem: + bias[n]; ReLU (FJSP_GEMM_RELU); * (mask(m,n) > 0) (mask indexed like C);
  * colsum[n] += column sums of the stored values (bias gradient); FJSP_GEMM_ATOMIC: atomicAdd into C (split-K).
  * max_ctas = max over the problems of ceil(M / 128) * splitk.  N <= 256. */
@@ -279,6 +289,16 @@ typedef struct FjspGemmProb {
     int32_t splitk;
     int32_t reserved[3];
 } FjspGemmProb;
+/* fjsp_a2c_loss_grad: the gradients of one A2C update's losses with respect to the actors' pre-softmax outputs and the
+ * critic value, analytically (a2c.py:647-731: -mean(adv_n * log q[a]) - entropy_coef * mean(H(softmax)) per actor with
+ * q = masked renormalised softmax and Categorical's clamp; MSE of the shared value against every agent's returns).
+ * logits/dlogits float[rows][32] and masks int8[rows][32] in the env's mask layout, actions u8[rows][8], adv/returns
+ * float[rows][8], values/dvalue float[rows]; adv_mean / adv_rstd float[8] (device): adv_n = (adv - mean) * rstd.
+ * sums float[64] (device, += ): [0..31] column sums of dlogits, [32..39] sum(-adv_n log q) per agent, [40..47] sum of
+ * entropies per agent, [48] sum of squared value errors, [49] sum of dvalue. */
+int fjsp_a2c_loss_grad(const float* logits, const int8_t* masks, const uint8_t* actions, const float* adv, const float* returns,
+                       const float* values, const float* adv_mean, const float* adv_rstd, float entropy_coef, int64_t rows, float* dlogits,
+                       float* dvalue, float* sums, void* stream);
 int fjsp_a2c_gemm(const FjspGemmProb* probs_device, int nprob, int max_ctas, int a_op, int b_op, int passes, void* stream);
 
 /* action_result bit-fields (results[N][8]); reference dict keys in comments */

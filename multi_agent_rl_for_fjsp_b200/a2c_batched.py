@@ -13,7 +13,10 @@ by batched tensor ops:
     with the unbiased std (a2c.py:694-731); critic loss = MSE of the value against every agent's returns (a2c.py:675-692);
   * clip_grad_norm 0.5 per network, one Adam per network (lr 3e-4 actors / 1e-3 critic).
 
-GEMMs are library calls (cuBLAS through torch): at these sizes they are launch-latency bound, not tensor-core bound.
+Two implementations of the same algorithm: ``impl="umma"`` (default on CUDA) runs the nine networks forward and
+backward as grouped tcgen05 GEMMs with TMEM accumulators (a2c_umma.py, csrc/fjsp_umma.cuh; 3xTF32 = fp32-level accuracy),
+reuses the rollout's activations in the update and computes the loss gradients analytically; ``impl="torch"`` is the
+plain torch / autograd statement (cuBLAS fp32) that the tensor-core path is tested against.
 Data parallelism: every rank owns an env shard; ONE flat all-reduce (654,366 fp32 = 2.62 MB, NCCL over NVLink) of the
 gradients per update, plus one tiny all-reduce of the advantage moments so normalisation is over the GLOBAL batch.
 The env step is one kernel launch per step that writes observations straight into the rollout buffer (``step_into``).
@@ -279,7 +282,11 @@ def _ptr(t):
 
 class BatchedA2C:
     def __init__(self, env, rollout_len=32, gamma=0.99, lamb=0.95, lr_actor=3e-4, lr_critic=1e-3, entropy_coef=0.01,
-                 max_grad_norm=0.5, seed=0, global_adv_norm=True, use_cuda_graph=True, fused_ops=True):
+                 max_grad_norm=0.5, seed=0, global_adv_norm=True, use_cuda_graph=True, fused_ops=True, impl=None, gemm_passes=3):
+        """impl: "umma" (CUDA default) — forward and backward of the 9 networks as grouped tcgen05 GEMMs (a2c_umma.py:
+        3xTF32 = fp32-level accuracy; gemm_passes=1: plain TF32), the rollout's activations reused by the update, analytic
+        loss gradients, no autograd; "torch" — the same algorithm with torch ops and autograd (the fp32 reference the umma
+        path is tested against; the only path off-GPU)."""
         self.env, self.T = env, int(rollout_len)
         self.seed = int(seed)
         self.gamma, self.lamb, self.entropy_coef, self.max_grad_norm = gamma, lamb, entropy_coef, max_grad_norm
@@ -316,6 +323,16 @@ class BatchedA2C:
             self._ctr = torch.zeros(1, dtype=torch.int64, device=dev)  # Philox time counter, advanced on the device
             self._ret = torch.zeros(T, N, 8, device=dev)
             self._adv = torch.zeros(T, N, 8, device=dev)
+        if impl is None:
+            impl = "umma" if self.fused else "torch"
+        if impl not in ("umma", "torch") or (impl == "umma" and not self.fused):
+            raise ValueError("impl must be 'umma' (CUDA, fused ops) or 'torch'")
+        self.impl = impl
+        self.engine = None
+        if impl == "umma":
+            from .a2c_umma import UmmaEngine
+
+            self.engine = UmmaEngine(self.net, self.obs, self.masks, self.actions, self.values, N, T, passes=gemm_passes)
         self.frames = 0
         self.stats = {}
         o, m = env.reset()
@@ -330,6 +347,18 @@ class BatchedA2C:
     def _rollout_steps(self):
         """T x (policy forward, masked Categorical sample, ONE env-step launch).  Static buffers: capturable."""
         T, env = self.T, self.env
+        if self.engine is not None:
+            eng = self.engine
+            for t in range(T):
+                eng.forward(t)  # logits -> eng.logits[t], value -> self.values[t]; activations kept for the update
+                rc = self._L.fjsp_a2c_sample(_ptr(eng.logits[t]), _ptr(self.masks[t]), _ptr(self.actions[t]), None, env.num_envs,
+                                             env.first_env, self.seed, _ptr(self._ctr), t, self._stream())
+                assert rc == 0, self._L.fjsp_last_error()
+                env.step_into(self.actions[t], self.obs[t + 1], self.masks[t + 1], self.rewards[t], self.flags[t])
+            eng.forward(T)      # bootstrap value of the last observation
+            rc = self._L.fjsp_a2c_counter_add(_ptr(self._ctr), T, self._stream())
+            assert rc == 0
+            return
         for t in range(T):
             o, m = self.obs[t], self.masks[t]
             self.values[t].copy_(self.net.value(o))
@@ -391,7 +420,8 @@ class BatchedA2C:
         torch.cuda.synchronize(self.device)
         try:
             g = torch.cuda.CUDAGraph()
-            self.opt.zero_grad(set_to_none=True)
+            if self.engine is None:
+                self.opt.zero_grad(set_to_none=True)
             with torch.cuda.graph(g):
                 self._update_impl()
             self._ugraph = g
@@ -400,11 +430,18 @@ class BatchedA2C:
             self.update_graph_error = repr(e)
             self.use_update_graph = False
             torch.cuda.synchronize(self.device)
-            self.opt.zero_grad(set_to_none=False)
+            if self.engine is None:
+                self.opt.zero_grad(set_to_none=False)
             return self._update_impl()
         return None
 
     def _update_impl(self):
+        self._compute_grads()
+        self._clip()
+        self.opt.step()
+
+    def _compute_grads(self):
+        """GAE, advantage moments, losses and their gradients (all-reduced over the ranks) into ``p.grad``."""
         T, N = self.T, self.env.num_envs
         if self.fused:
             rc = self._L.fjsp_a2c_gae(_ptr(self.rewards), _ptr(self.values), _ptr(self.flags), _ptr(self._ret), _ptr(self._adv),
@@ -423,6 +460,15 @@ class BatchedA2C:
             self._allreduce_(mom)
         cnt, mean = mom[0], mom[1] / mom[0]
         var = (mom[2] - cnt * mean * mean) / (cnt - 1).clamp_min(1.0)
+        if self.engine is not None:  # tensor-core path: analytic loss gradients + grouped tcgen05 GEMMs, no autograd
+            eng = self.engine
+            eng.adv_mean.copy_(mean), eng.adv_rstd.copy_(1.0 / (var.clamp_min(0).sqrt() + 1e-8))
+            eng.backward(self._adv, self._ret, self.entropy_coef)
+            if self.world > 1:  # ONE all-reduce of the flat gradient buffer (2.62 MB), then the mean over ranks
+                dist.all_reduce(eng.grad_flat)
+                eng.grad_flat /= self.world
+            self.stats = eng.stats(self.entropy_coef)
+            return
         adv_n = (advs - mean) / (var.clamp_min(0).sqrt() + 1e-8)
 
         probs = self.net.probs32(obs)
@@ -444,8 +490,6 @@ class BatchedA2C:
             for g in grads:
                 g.copy_(flat[off:off + g.numel()].view_as(g))
                 off += g.numel()
-        self._clip()
-        self.opt.step()
         self.stats = {"actor_loss": actor_loss.detach(), "critic_loss": critic_loss.detach(), "entropy": ent.detach()}
 
     def _clip(self):

@@ -1,0 +1,175 @@
+"""Tensor-core engine of the batched A2C trainer: the reference's 8 actors + centralised critic
+(/root/reference/networks.py:22-61) forward and backward as grouped tcgen05 GEMMs (``fjsp_a2c_gemm``, 3xTF32 =
+fp32-level accuracy) plus one analytic loss-gradient kernel (``fjsp_a2c_loss_grad``) — no autograd graph, no library GEMM.
+
+A2C is on-policy: the update differentiates the very networks that produced the rollout.  The rollout's forward passes
+therefore ARE the update's forward pass: every rollout step stores its hidden activations (post-ReLU) and pre-softmax
+outputs in slice ``t`` of ``[net][T+1][N][256]`` buffers, and the update only runs the backward chain over the ``T*N``
+rows:
+
+    loss_grad            dlogits [B,32], dvalue [B]  (+ last-layer bias gradients, loss statistics)
+    (KCS,KCS) x9         dH2 = (dlogits_i W3_i^T) * (H2 > 0)   and the critic head  dH3 = (dvalue w4^T) * (H3 > 0)
+    (KC,KC)   x1         critic: dH2 = (dH3 Wc3^T) * (H2 > 0)
+    (KC,KC)   x9         dH1 = (dH2 W2^T) * (H1 > 0)
+    (MC,MC)   x28        every weight gradient, split-K over the batch with atomic accumulation
+    bias gradients       column sums in the epilogues of the dH GEMMs (same pass)
+
+Gradients land in ONE flat fp32 buffer (``p.grad`` are views of it), so data parallelism is a single NCCL all-reduce of
+that buffer without gather / scatter copies.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import abi, umma
+from .env import MASK_OFFSETS, N_ACTIONS, OBS_SLICES
+
+HID = 256
+LS_DB, LS_ACTOR, LS_ENT, LS_CRITIC, LS_DV, LS_WORDS = 0, 32, 40, 48, 49, 64
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class UmmaEngine:
+    def __init__(self, net, obs, masks, actions, values, num_envs, rollout_len, passes=3):
+        """net: ``ActorCritic``; obs [T+1,N,38], masks [T+1,N,32], actions [T,N,8], values [T+1,N]: the trainer's rollout buffers."""
+        self.net, self.N, self.T, self.passes = net, int(num_envs), int(rollout_len), int(passes)
+        self.obs, self.masks, self.actions, self.values = obs, masks, actions, values
+        dev = self.dev = obs.device
+        N, T = self.N, self.T
+        self.B = T * N
+        z = lambda *s: torch.zeros(*s, device=dev)  # noqa: E731
+        self.h1, self.h2, self.h3 = z(9, T + 1, N, HID), z(9, T + 1, N, HID), z(T + 1, N, 128)
+        self.logits = z(T + 1, N, 32)
+        self.dh1, self.dh2, self.dh3 = z(9, self.B, HID), z(9, self.B, HID), z(self.B, 128)
+        self.dlogits, self.dvalue = z(self.B, 32), z(self.B)
+        self.sums = z(LS_WORDS)
+        self.adv_mean, self.adv_rstd = z(8), z(8)
+        # one flat gradient buffer; p.grad are views of it
+        params = list(net.parameters())
+        self.grad_flat = z(sum(p.numel() for p in params))
+        off = 0
+        for p in params:
+            p.grad = self.grad_flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self._L = abi.lib()
+        self._nets = self._describe()
+        self._fwd = [self._forward_tables(t, critic_only=False) for t in range(T)] + [self._forward_tables(T, critic_only=True)]
+        self._bwd = self._backward_tables()
+
+    # ------------------------------------------------------------------ the nine networks
+    def _describe(self):
+        n, nets = self.net, []
+        ps, agv, six, cr = list(n.ps), list(n.agv), list(n.six), list(n.critic)
+        nets.append(dict(lo=0, k1=7, p=ps, i=None, nact=3, zoff=MASK_OFFSETS[0]))
+        nets.append(dict(lo=7, k1=13, p=agv, i=None, nact=8, zoff=MASK_OFFSETS[1]))
+        for i in range(6):
+            nets.append(dict(lo=OBS_SLICES[2 + i][0], k1=3, p=six, i=i, nact=N_ACTIONS[2 + i], zoff=MASK_OFFSETS[2 + i]))
+        nets.append(dict(lo=0, k1=38, p=cr, i=None, nact=128, zoff=None))
+        return nets
+
+    @staticmethod
+    def _par(d, j):
+        """(tensor, element offset) of parameter j (w1,b1,w2,b2,w3,b3[,w4,b4]) of a network (one slice of a stacked one)."""
+        t = d["p"][j]
+        return (t, 0) if d["i"] is None else (t, d["i"] * t[0].numel())
+
+    def _grad(self, d, j):
+        t = d["p"][j].grad
+        return (t, 0) if d["i"] is None else (t, d["i"] * t[0].numel())
+
+    def _hoff(self, net, t=0):
+        return ((net * (self.T + 1) + t) * self.N) * HID
+
+    # ------------------------------------------------------------------ forward (one rollout step)
+    def _forward_tables(self, t, critic_only):
+        N, dev, ps = self.N, self.dev, self.passes
+        nets = [(8, self._nets[8])] if critic_only else list(enumerate(self._nets))
+        l1 = umma.GemmTable(dev, umma.OP_KCS, umma.OP_MC, ps)
+        l2 = umma.GemmTable(dev, umma.OP_KC, umma.OP_MC, ps)
+        l3 = umma.GemmTable(dev, umma.OP_KC, umma.OP_MC, ps)
+        l4 = umma.GemmTable(dev, umma.OP_KC, umma.OP_MC, ps)
+        for k, d in nets:
+            (w1, o1), (b1, ob1), (w2, o2), (b2, ob2), (w3, o3), (b3, ob3) = (self._par(d, j) for j in range(6))
+            l1.add(self.obs, w1, self.h1, N, HID, d["k1"], lda=38, ldb=HID, csm=HID, a_off=t * N * 38 + d["lo"], b_off=o1,
+                   c_off=self._hoff(k, t), bias=b1, bias_off=ob1, relu=True)
+            l2.add(self.h1, w2, self.h2, N, HID, HID, lda=HID, ldb=HID, csm=HID, a_off=self._hoff(k, t), b_off=o2,
+                   c_off=self._hoff(k, t), bias=b2, bias_off=ob2, relu=True)
+            if k < 8:   # actor head: straight into its columns of the [N, 32] logits row
+                l3.add(self.h2, w3, self.logits, N, d["nact"], HID, lda=HID, ldb=d["nact"], csm=32, a_off=self._hoff(k, t), b_off=o3,
+                       c_off=t * N * 32 + d["zoff"], bias=b3, bias_off=ob3)
+            else:       # critic: 256 -> 128 (ReLU) -> 1
+                l3.add(self.h2, w3, self.h3, N, 128, HID, lda=HID, ldb=128, csm=128, a_off=self._hoff(k, t), b_off=o3,
+                       c_off=t * N * 128, bias=b3, bias_off=ob3, relu=True)
+                w4, b4 = d["p"][6], d["p"][7]
+                l4.add(self.h3, w4, self.values, N, 1, 128, lda=128, ldb=1, csm=1, a_off=t * N * 128, c_off=t * N, bias=b4)
+        return [x.finalize() for x in (l1, l2, l3, l4)]
+
+    def forward(self, t):
+        """Actors' logits (``self.logits[t]``) and the critic value (``values[t]``) of rollout step t; t = T: the bootstrap
+        value only.  Four grouped launches."""
+        for tab in self._fwd[t]:
+            tab.launch()
+
+    # ------------------------------------------------------------------ backward (one update)
+    def _backward_tables(self):
+        B, dev, ps = self.B, self.dev, self.passes
+        b3 = umma.GemmTable(dev, umma.OP_KCS, umma.OP_KCS, ps)
+        bc = umma.GemmTable(dev, umma.OP_KC, umma.OP_KC, ps)
+        b2 = umma.GemmTable(dev, umma.OP_KC, umma.OP_KC, ps)
+        dw = umma.GemmTable(dev, umma.OP_MC, umma.OP_MC, ps)
+        sk = max(1, min(64, B // 2048))
+        for k, d in enumerate(self._nets):
+            (w1, o1), _, (w2, o2), _, (w3, o3), _ = (self._par(d, j) for j in range(6))
+            (gw1, g1), (gb1, gb1o), (gw2, g2), (gb2, gb2o), (gw3, g3), (gb3, gb3o) = (self._grad(d, j) for j in range(6))
+            ho, go = self._hoff(k), k * B * HID
+            if k < 8:
+                na, zo = d["nact"], d["zoff"]
+                b3.add(self.dlogits, w3, self.dh2, B, HID, na, lda=32, ldb=na, csm=HID, a_off=zo, b_off=o3, c_off=go,
+                       mask=self.h2, mask_off=ho, colsum=gb2, colsum_off=gb2o)
+                dw.add(self.h2, self.dlogits, gw3, HID, na, B, lda=HID, ldb=32, csm=na, a_off=ho, b_off=zo, c_off=g3, atomic=True, splitk=sk)
+            else:
+                w4, gw4 = d["p"][6], d["p"][6].grad
+                b3.add(self.dvalue, w4, self.dh3, B, 128, 1, lda=1, ldb=1, csm=128, mask=self.h3, colsum=gb3, colsum_off=gb3o)
+                bc.add(self.dh3, w3, self.dh2, B, HID, 128, lda=128, ldb=128, csm=HID, b_off=o3, c_off=go, mask=self.h2, mask_off=ho,
+                       colsum=gb2, colsum_off=gb2o)
+                dw.add(self.h2, self.dh3, gw3, HID, 128, B, lda=HID, ldb=128, csm=128, a_off=ho, c_off=g3, atomic=True, splitk=sk)
+                dw.add(self.h3, self.dvalue, gw4, 128, 1, B, lda=128, ldb=1, csm=1, atomic=True, splitk=sk)
+            b2.add(self.dh2, w2, self.dh1, B, HID, HID, lda=HID, ldb=HID, csm=HID, a_off=go, b_off=o2, c_off=go, mask=self.h1, mask_off=ho,
+                   colsum=gb1, colsum_off=gb1o)
+            dw.add(self.h1, self.dh2, gw2, HID, HID, B, lda=HID, ldb=HID, csm=HID, a_off=ho, b_off=go, c_off=g2, atomic=True, splitk=sk)
+            # dW1[i, j] = sum_rows obs[row, lo + i] * dH1[row, j]: computed transposed (M = 256 hidden units)
+            dw.add(self.dh1, self.obs, gw1, HID, d["k1"], B, lda=HID, ldb=38, csm=1, csn=HID, a_off=go, b_off=d["lo"], c_off=g1,
+                   atomic=True, splitk=sk)
+        return [x.finalize() for x in (b3, bc, b2, dw)]
+
+    def backward(self, adv, returns, entropy_coef):
+        """Gradients of the update's losses into ``grad_flat`` (local-batch means; the caller all-reduces and averages).
+        ``adv`` / ``returns`` [T,N,8]; ``self.adv_mean`` / ``self.adv_rstd`` must hold the (global) advantage moments."""
+        B = self.B
+        self.grad_flat.zero_()
+        self.sums.zero_()
+        st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        rc = self._L.fjsp_a2c_loss_grad(_p(self.logits), _p(self.masks), _p(self.actions), _p(adv), _p(returns), _p(self.values),
+                                        _p(self.adv_mean), _p(self.adv_rstd), float(entropy_coef), B, _p(self.dlogits), _p(self.dvalue),
+                                        _p(self.sums), st)
+        if rc:
+            abi.check(rc)
+        for tab in self._bwd:
+            tab.launch()
+        # last-layer bias gradients = column sums of dlogits / dvalue (from the loss kernel)
+        n = self.net
+        n.ps[5].grad.view(-1).copy_(self.sums[0:3])
+        n.agv[5].grad.view(-1).copy_(self.sums[3:11])
+        n.six[5].grad.view(-1).copy_(self.sums[11:29])
+        n.critic[7].grad.view(-1).copy_(self.sums[LS_DV:LS_DV + 1])
+
+    def stats(self, entropy_coef):
+        inv_b = 1.0 / self.B
+        ent = self.sums[LS_ENT:LS_ENT + 8] * inv_b
+        return {"actor_loss": self.sums[LS_ACTOR:LS_ACTOR + 8] * inv_b - entropy_coef * ent,
+                "critic_loss": self.sums[LS_CRITIC] * (inv_b / 8), "entropy": ent}

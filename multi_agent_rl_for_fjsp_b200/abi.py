@@ -21,7 +21,7 @@ HEADER = os.path.join(_REPO, "include", "fjsp_b200.h")
 NUM_AGENTS, OBS_DIM, MASK_DIM, FLAG_DIM, INFO_DIM, MAX_ORDERS = 8, 38, 32, 4, 4, 32
 STATE_WORDS, TILE_ENVS = 128, 64
 MAX_CELLS = 4
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 def dims(cells: int = 1) -> dict:
@@ -29,7 +29,7 @@ def dims(cells: int = 1) -> dict:
     agents = 1 + 7 * cells
     return {"agents": agents, "act": (agents + 7) // 8 * 8, "obs": 7 + 31 * cells, "mask": (3 + 26 * cells + 31) // 32 * 32,
             "mask_used": 3 + 26 * cells, "state_words": 64 + 64 * cells + 20 * (cells - 1),
-            "wire_words": ((7 + 31 * cells + 3) // 4 + (3 + 26 * cells + 31) // 32 + 1 + (agents + 7) // 8 * 4 + 1) // 2 * 2}
+            "wire_words": (2 + 5 * cells + 1) // 2 * 2}
 
 CANON_MAXQ, CANON_PS_READY, CANON_MAXPQ = 64, 256, 256
 
@@ -75,7 +75,7 @@ EXPORTS = [
     "fjsp_num_cells", "fjsp_step_wire", "fjsp_step_host_wire", "fjsp_wire_decode", "fjsp_wire_row_bytes", "fjsp_set_decode_threads",
     "fjsp_state_total_bytes", "fjsp_state_save", "fjsp_state_load",
     "fjsp_a2c_sample", "fjsp_a2c_counter_add", "fjsp_a2c_gae", "fjsp_cells_pack_actions", "fjsp_cells_unpack_views",
-    "fjsp_a2c_gemm",
+    "fjsp_a2c_gemm", "fjsp_a2c_loss_grad",
 ]
 
 
@@ -138,6 +138,7 @@ def lib() -> C.CDLL:
     L.fjsp_a2c_sample.argtypes = [vp, vp, vp, vp, i64, i64, u64, vp, u64, vp]
     L.fjsp_a2c_counter_add.argtypes = [vp, u64, vp]
     L.fjsp_a2c_gae.argtypes = [vp, vp, vp, vp, vp, C.c_int, i64, C.c_float, C.c_float, vp]
+    L.fjsp_a2c_loss_grad.argtypes = [vp] * 8 + [C.c_float, i64, vp, vp, vp, vp]
     L.fjsp_a2c_gemm.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.fjsp_cells_pack_actions.argtypes = [vp, vp, i64, C.c_int, vp]
     L.fjsp_cells_unpack_views.argtypes = [vp] * 8 + [i64, C.c_int, vp]

@@ -127,6 +127,140 @@ __global__ void __launch_bounds__(256) fjsp_gae_kernel(const float* __restrict__
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Loss gradients of one A2C update, analytically (a2c.py:647-731): per row (one env step of the rollout) and agent
+//   actor_loss_i = -mean(adv_n * log q[a]) - entropy_coef * mean(H(p)),   p = softmax(z), q = p*mask renormalised
+//     d log q[a] / dz_j = [a == j] - q_j        (0 when Categorical's probability clamp [eps, 1-eps] is active, or when
+//                                                 the masked mass is 0: the uniform fallback does not depend on z)
+//     dH / dz_j         = p_j * (g_j - sum_k g_k p_k),   g_k = -(log(p_k + 1e-10) + p_k / (p_k + 1e-10))   (unmasked p)
+//   critic_loss  = mean over (row, agent) of (v - return_i)^2   ->   dL/dv = 2/(8B) * sum_i (v - return_i)
+// Writes dlogits[B][32] (same layout as the logits; pad columns 0) and dvalue[B]; accumulates into sums[64]:
+//   [0..31] column sums of dlogits (the last layers' bias gradients), [32..39] sum of -adv_n*logq per agent,
+//   [40..47] sum of H per agent, [48] sum of squared critic errors, [49] sum of dvalue.
+// ---------------------------------------------------------------------------------------------
+enum { LS_DB = 0, LS_ACTOR = 32, LS_ENT = 40, LS_CRITIC = 48, LS_DV = 49, LS_WORDS = 64 };
+
+__global__ void __launch_bounds__(128) fjsp_a2c_loss_grad_kernel(const float* __restrict__ logits, const int8_t* __restrict__ masks,
+                                                                 const uint8_t* __restrict__ actions, const float* __restrict__ adv,
+                                                                 const float* __restrict__ returns, const float* __restrict__ values,
+                                                                 const float* __restrict__ adv_mean, const float* __restrict__ adv_rstd,
+                                                                 float entropy_coef, float inv_b, float* __restrict__ dlogits,
+                                                                 float* __restrict__ dvalue, float* __restrict__ sums, int64_t rows) {
+    __shared__ float s_sums[LS_WORDS];
+    if (threadIdx.x < LS_WORDS) s_sums[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = row < rows;
+    float dz[32], acc[18];  // acc: 8 actor terms, 8 entropies, squared error, dvalue
+#pragma unroll
+    for (int i = 0; i < 32; i++) dz[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 18; i++) acc[i] = 0.f;
+    if (live) {
+        float z[32];
+        u32 mw[8];
+        const float4* z4 = reinterpret_cast<const float4*>(logits + row * 32);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float4 v = __ldg(z4 + i);
+            z[4 * i] = v.x, z[4 * i + 1] = v.y, z[4 * i + 2] = v.z, z[4 * i + 3] = v.w;
+        }
+        const uint4* m4 = reinterpret_cast<const uint4*>(masks + row * 32);
+        const uint4 ma = __ldg(m4), mb = __ldg(m4 + 1);
+        mw[0] = ma.x, mw[1] = ma.y, mw[2] = ma.z, mw[3] = ma.w, mw[4] = mb.x, mw[5] = mb.y, mw[6] = mb.z, mw[7] = mb.w;
+        const uint2 ab = __ldg(reinterpret_cast<const uint2*>(actions) + row);
+        const float4* a4 = reinterpret_cast<const float4*>(adv + row * 8);
+        const float4* r4 = reinterpret_cast<const float4*>(returns + row * 8);
+        const float4 a0 = __ldg(a4), a1 = __ldg(a4 + 1), r0 = __ldg(r4), r1 = __ldg(r4 + 1);
+        const float advv[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float retv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        const float v = __ldg(values + row);
+        float dv = 0.f, sq = 0.f;
+#pragma unroll
+        for (int ag = 0; ag < 8; ag++) {
+            int off, n;
+            agent_segment(ag, off, n);
+            const int a = (int)(((ag < 4 ? ab.x : ab.y) >> ((ag & 3) * 8)) & 0xffu);
+            float zmax = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (j < n) zmax = fmaxf(zmax, z[off + j]);
+            float p[8], q[8], psum = 0.f, msum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (j < n) p[j] = expf(z[off + j] - zmax), psum += p[j];
+            float gp = 0.f, ent = 0.f, g[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (j < n) {
+                    const float m = (float)((mw[(off + j) >> 2] >> (((off + j) & 3) * 8)) & 1u);
+                    p[j] = p[j] / psum;
+                    q[j] = p[j] * m, msum += q[j];
+                    const float lg = logf(p[j] + 1e-10f);
+                    ent -= p[j] * lg;                               // a2c.py:704-707
+                    g[j] = -(lg + p[j] / (p[j] + 1e-10f));
+                    gp += g[j] * p[j];
+                }
+            const float adv_n = (advv[ag] - __ldg(adv_mean + ag)) * __ldg(adv_rstd + ag);  // a2c.py:727-729
+            const float eps = 1.1920929e-07f;
+            float qa = 0.f;
+            bool through = false;
+            if (msum > 0.f) {
+                const float s = fmaxf(msum, 1e-38f);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (j < n) {
+                        q[j] = q[j] / s;
+                        if (j == a) qa = q[j];
+                    }
+                through = qa >= eps && qa <= 1.0f - eps;       // clamp passes the gradient inside [eps, 1 - eps]
+            } else {                                            // uniform over the valid actions (a2c.py:226-231)
+                float cnt = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (j < n) cnt += (float)((mw[(off + j) >> 2] >> (((off + j) & 3) * 8)) & 1u);
+                qa = (a < n && ((mw[(off + a) >> 2] >> (((off + a) & 3) * 8)) & 1u)) ? 1.0f / fmaxf(cnt, 1.f) : 0.f;
+            }
+            const float logq = logf(fminf(fmaxf(qa, eps), 1.0f - eps));
+            acc[ag] = -adv_n * logq;
+            acc[8 + ag] = ent;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (j < n) {
+                    float d = -entropy_coef * inv_b * p[j] * (g[j] - gp);
+                    if (through) d -= adv_n * inv_b * ((j == a ? 1.f : 0.f) - q[j]);
+                    dz[off + j] = d;
+                }
+            const float e = v - retv[ag];
+            sq += e * e, dv += e;
+        }
+        dv *= 2.0f * inv_b * 0.125f;
+        acc[16] = sq, acc[17] = dv;
+        dvalue[row] = dv;
+        float4* o4 = reinterpret_cast<float4*>(dlogits + row * 32);
+#pragma unroll
+        for (int i = 0; i < 8; i++) o4[i] = make_float4(dz[4 * i], dz[4 * i + 1], dz[4 * i + 2], dz[4 * i + 3]);
+    }
+    // warp reduce (shuffles), one shared atomic per warp and value, one global atomic per block and value
+#pragma unroll
+    for (int i = 0; i < 29; i++) {
+        float x = dz[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&s_sums[LS_DB + i], x);
+    }
+#pragma unroll
+    for (int i = 0; i < 18; i++) {
+        float x = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&s_sums[LS_ACTOR + i], x);
+    }
+    __syncthreads();
+    if (threadIdx.x < LS_WORDS && s_sums[threadIdx.x] != 0.f) atomicAdd(sums + threadIdx.x, s_sums[threadIdx.x]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Cell views of a scaled shop (K cells): the batched trainer sees every (env, cell) as one row of the reference's own
 // 8-agent layout — the pickup station's 7 observation fields followed by the cell's 31, its 3 + 26 mask bytes, the

@@ -585,6 +585,21 @@ int fjsp_a2c_gae(const float* rewards, const float* values, const uint8_t* flags
     return 0;
 }
 
+int fjsp_a2c_loss_grad(const float* logits, const int8_t* masks, const uint8_t* actions, const float* adv, const float* returns,
+                       const float* values, const float* adv_mean, const float* adv_rstd, float entropy_coef, int64_t rows, float* dlogits,
+                       float* dvalue, float* sums, void* stream) {
+    if (!logits || !masks || !actions || !adv || !returns || !values || !adv_mean || !adv_rstd || !dlogits || !dvalue || !sums)
+        return fail("NULL argument");
+    if ((reinterpret_cast<uintptr_t>(logits) & 15) || (reinterpret_cast<uintptr_t>(masks) & 15) || (reinterpret_cast<uintptr_t>(actions) & 7) ||
+        (reinterpret_cast<uintptr_t>(adv) & 15) || (reinterpret_cast<uintptr_t>(returns) & 15) || (reinterpret_cast<uintptr_t>(dlogits) & 15))
+        return fail("alignment: logits/masks/adv/returns/dlogits 16 B, actions 8 B");
+    if (rows <= 0) return fail("rows must be positive");
+    fjsp_a2c_loss_grad_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        logits, masks, actions, adv, returns, values, adv_mean, adv_rstd, entropy_coef, 1.0f / (float)rows, dlogits, dvalue, sums, rows);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int fjsp_a2c_gemm(const FjspGemmProb* probs, int nprob, int max_ctas, int a_op, int b_op, int passes, void* stream) {
     if (!probs) return fail("probs is NULL");
     if (nprob < 1 || nprob > 65535 || max_ctas < 1) return fail("nprob must be in 1..65535 and max_ctas positive");
@@ -596,7 +611,8 @@ int fjsp_a2c_gemm(const FjspGemmProb* probs, int nprob, int max_ctas, int a_op, 
         case umma::OP_KCS * 3 + umma::OP_MC: return launch_gemm<umma::OP_KCS, umma::OP_MC>(probs, nprob, max_ctas, passes, st);
         case umma::OP_KC * 3 + umma::OP_KC: return launch_gemm<umma::OP_KC, umma::OP_KC>(probs, nprob, max_ctas, passes, st);
         case umma::OP_MC * 3 + umma::OP_MC: return launch_gemm<umma::OP_MC, umma::OP_MC>(probs, nprob, max_ctas, passes, st);
-        default: return fail("unsupported operand orientation pair (supported: KC/MC, KCS/MC, KC/KC, MC/MC)");
+        case umma::OP_KCS * 3 + umma::OP_KCS: return launch_gemm<umma::OP_KCS, umma::OP_KCS>(probs, nprob, max_ctas, passes, st);
+        default: return fail("unsupported operand orientation pair (supported: KC/MC, KCS/MC, KC/KC, MC/MC, KCS/KCS)");
     }
 }
 

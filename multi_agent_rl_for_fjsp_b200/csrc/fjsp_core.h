@@ -392,9 +392,9 @@ FJSP_HD void reset_env(S& s, const Params& P, int num_orders, const FjspOrderRec
 // ---------------------------------------------------------------------------------------------
 // Observation (layout O: 7 + 31K floats) + masks (3 + 26K bytes).  SURVEY.md §8a-R9; K = 1: 38 / 29.
 // ---------------------------------------------------------------------------------------------
-// Where an observation goes.  FloatSink: the reference's float32 row (a2c._flatten_obs order).  WireSink: the compact
-// host wire format (include/fjsp_b200.h "wire rows"): one byte per field — a small integer, a station index for the
-// two AGV position fields, the table index L for a packaging progress — assembled in registers, 4 fields per u32.
+// Where an observation goes.  FloatSink: the reference's float32 row (a2c._flatten_obs order).  FieldSink: the plain
+// integers — a station index for the two AGV position fields, the table index L for a packaging progress — from which
+// the compact host wire format (include/fjsp_b200.h "wire rows") is packed.
 struct FloatSink {
     float* o;
     const Params& P;
@@ -404,25 +404,24 @@ struct FloatSink {
     FJSP_HD void set_prog(int i, int L) { o[i] = P.progress_tab[L]; }
     FJSP_HD FloatSink at(int off) const { return FloatSink{o + off, P}; }
 };
-struct WireSink {
-    u32* w;
-    int base;
-    FJSP_HD void put(int i, int v) { w[(base + i) >> 2] |= (u32)(v & 255) << (((base + i) & 3) * 8); }
-    FJSP_HD void set(int i, int v) { put(i, v); }
-    FJSP_HD void set_i8(int i, int v) { put(i, v); }
-    FJSP_HD void set_loc(int i, int loc) { put(i, loc), put(i + 1, loc); }
-    FJSP_HD void set_prog(int i, int L) { put(i, L); }
-    FJSP_HD WireSink at(int off) const { return WireSink{w, base + off}; }
+struct FieldSink {   // the raw integer value of every field (the wire row packs them into bit-fields)
+    int* f;
+    FJSP_HD void set(int i, int v) { f[i] = v; }
+    FJSP_HD void set_i8(int i, int v) { f[i] = v & 255; }
+    FJSP_HD void set_loc(int i, int loc) { f[i] = loc, f[i + 1] = loc; }
+    FJSP_HD void set_prog(int i, int L) { f[i] = L; }
+    FJSP_HD FieldSink at(int off) const { return FieldSink{f + off}; }
 };
 enum { OBS_NONE = 0, OBS_FLOAT = 1, OBS_WIRE = 2 };
 
 template <int K>
 struct StepOut {
     float* obs;     // OBS_FLOAT: 7 + 31K floats, written in place (a shared-memory staging row on the device)
-    u32 wobs[(Lay<K>::OBS + 3) / 4];  // OBS_WIRE: the same fields, one byte each
+    u32 wire[FJSP_WIRE_WORDS_K(K)];   // OBS_WIRE: the observation part of the wire row (bit-fields; wire_row adds the rest)
     u32 mask[Lay<K>::MASK / 4];
     float reward[Lay<K>::ACT];
     int reward_g;                     // 10A*r_i = reward_g + A*reward_local10[i]  (exact integers)
+    int d_orders, d_products;         // orders completed / products packaged by this step (reward_g = 10*(100*do + 10*dp) - step_size)
     int reward_local10[Lay<K>::ACT];
     u32 flags;      // terminated | truncated<<8 | fault<<16 | was_reset<<24
     u32 results[Lay<K>::ACT / 4];  // u8 action_result bit-fields per agent
@@ -546,57 +545,112 @@ FJSP_HD void observe(S& s, const Params& P, const Hot& h, const HotCell& c0, O o
     }
 }
 // ---------------------------------------------------------------------------------------------
-// Wire row (include/fjsp_b200.h FJSP_WIRE_WORDS_K): everything a step returns for one env, as small integers.
-//   [obs bytes, 4 per word][mask bits, 32 per word][reward_g (24-bit signed) | flag bits << 24][reward_local10 i16, 2 per word][pad]
+// Wire row (include/fjsp_b200.h FJSP_WIRE_WORDS_K): everything a step returns for one env as BIT-FIELDS, 2 + 5K words
+// (32 bytes for K = 1).  No field straddles a word, so the host decoder extracts each with one shift and one mask.
+//   S0  ps obs: tray_color2 | tray_count3<<2 | tray_type2<<5 | next_color2<<7 | next_type2<<9 | order_size4<<11 |
+//       remaining4<<15 ; flags6<<19 (terminated, truncated, fault x3, was_reset) ; ps mask bits 1,2 <<25 ; ps reward code2<<27
+//   S1  products packaged by the step 10 | orders completed 9 <<10 | pickup_ready_trays 13 <<19
+//   per cell c, words 2 + 5c ..:
+//   C0  agv: station3 | carrying1<<3 | needs_processing1<<4 | tray_count3<<5 | tray_type2<<8 | big_ready6<<10 |
+//       small_ready6<<16 | agv mask bits 1..7 <<22 | agv reward code3<<29
+//   C1  storage8 | small machine (busy1, progress1, queue6)<<8 | big machine<<16 | small mask bits 1,2<<24 | big<<26 |
+//       small reward code2<<28 | big<<30
+//   C2  station0 | station3: progL8<<21, busy1<<29, mask bits2<<30
+//   C3  station1 | station3: queue8<<21, reward code2<<29
+//   C4  station2             with stationN = busy1 | progL8<<1 | queue8<<9 | mask bits 1,2 <<17 | reward code2<<19
+// Mask bit 0 of every agent is constant 1 and not sent.  Reward codes index the agent kind's few possible local rewards
+// (RewardModel.py:46-97); the global part follows from the two counters in S1.
 // ---------------------------------------------------------------------------------------------
 template <int K>
 struct Wire {
-    static constexpr int OBSW = (Lay<K>::OBS + 3) / 4, MW = Lay<K>::MASK / 32;
-    static constexpr int OFF_MASK = OBSW, OFF_G = OBSW + MW, OFF_LOCAL = OFF_G + 1, END = OFF_LOCAL + Lay<K>::ACT / 2;
-    static constexpr int WORDS = FJSP_WIRE_WORDS_K(K);
-    static_assert(END <= WORDS && WORDS % 2 == 0, "wire row layout");
+    static constexpr int WORDS = FJSP_WIRE_WORDS_K(K), USED = 2 + 5 * K;
+    static_assert(USED <= WORDS && WORDS % 2 == 0, "wire row layout");
 };
-// flags word of fjsp_step (terminated | truncated << 8 | fault << 16 | was_reset << 24) <-> the 5 flag bits of a wire row
-FJSP_HD u32 wire_g_word(int g, u32 flags) {
-    const u32 fb = (flags & 1u) | ((flags >> 7) & 2u) | ((flags >> 14) & 12u) | ((flags >> 20) & 16u);
-    return ((u32)g & 0x00ffffffu) | (fb << 24);
-}
-FJSP_HD int wire_g(u32 w) { return (int)(w << 8) >> 8; }
-FJSP_HD u32 wire_flags(u32 w) {
-    const u32 fb = w >> 24;
-    return (fb & 1u) | ((fb & 2u) << 7) | ((fb & 12u) << 14) | ((fb & 16u) << 20);
+// local rewards in tenths <-> codes
+FJSP_HD u32 code_ps(int l) { return l == 0 ? 0u : l == -10 ? 1u : l == 10 ? 2u : 3u; }                 // 0, -1, +1, +6
+FJSP_HD u32 code_agv(int l) { return l == 0 ? 0u : l == -1 ? 1u : l == 20 ? 2u : l == 120 ? 3u : 4u; } // 0, -0.1, +2, +12, -5
+FJSP_HD u32 code_mach(int l) { return l == 0 ? 0u : l == -20 ? 1u : l == 10 ? 2u : 3u; }               // 0, -2, +1, +5
+FJSP_HD u32 code_pack(int l) { return l == 0 ? 0u : l == -10 ? 1u : l == 20 ? 2u : 3u; }               // 0, -1, +2, +20
+// reward LUT of the decoder: [kind 0 ps, 1 agv, 2 machine, 3 packaging][code], tenths
+#define FJSP_WIRE_REWARD_LUT {0, -10, 10, 60, 0, 0, 0, 0,   0, -1, 20, 120, -50, 0, 0, 0,   0, -20, 10, 50, 0, 0, 0, 0,   0, -10, 20, 200, 0, 0, 0, 0}
+// flags word of fjsp_step (terminated | truncated << 8 | fault << 16 | was_reset << 24) <-> the 6 flag bits of S0
+FJSP_HD u32 wire_flag_bits(u32 flags) { return (flags & 1u) | ((flags >> 7) & 2u) | ((flags >> 14) & 0x1cu) | ((flags >> 19) & 0x20u); }
+FJSP_HD u32 wire_flags(u32 s0) {
+    const u32 fb = (s0 >> 19) & 63u;
+    return (fb & 1u) | ((fb & 2u) << 7) | ((fb & 0x1cu) << 14) | ((fb & 0x20u) << 19);
 }
 // four mask bytes (0/1 each) -> four bits
 FJSP_HD u32 mask_nibble(u32 bytes4) { return ((bytes4 & 0x01010101u) * 0x01020408u) >> 24; }
 
+// observation parts: fs = the pickup station's 7 fields, psbits = its 3 mask bits; f = one cell's 31 fields, bits = its 26 mask bits
+FJSP_HD u32 wire_s0_obs(const int* fs, u32 psbits) {
+    return (u32)fs[0] | ((u32)fs[1] << 2) | ((u32)fs[2] << 5) | ((u32)fs[3] << 7) | ((u32)fs[4] << 9) | ((u32)fs[5] << 11) |
+           ((u32)fs[6] << 15) | (((psbits >> 1) & 3u) << 25);
+}
+FJSP_HD void wire_cell_obs(const int* f, u32 bits, u32* w) {
+    w[0] = (u32)f[4] | ((u32)f[2] << 3) | ((u32)f[10] << 4) | ((u32)f[11] << 5) | ((u32)f[12] << 8) | ((u32)f[1] << 10) |
+           ((u32)f[7] << 16) | (((bits >> 1) & 0x7fu) << 22);
+    w[1] = (u32)f[8] | ((u32)f[13] << 8) | ((u32)f[14] << 9) | ((u32)f[15] << 10) | ((u32)f[16] << 16) | ((u32)f[17] << 17) |
+           ((u32)f[18] << 18) | (((bits >> 9) & 3u) << 24) | (((bits >> 12) & 3u) << 26);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        w[2 + i] = (u32)f[19 + 3 * i] | ((u32)f[20 + 3 * i] << 1) | ((u32)f[21 + 3 * i] << 9) | (((bits >> (15 + 3 * i)) & 3u) << 17);
+    w[2] |= ((u32)f[29] << 21) | ((u32)f[28] << 29) | (((bits >> 24) & 3u) << 30);
+    w[3] |= (u32)f[30] << 21;
+}
+// result parts, OR-ed onto the observation parts (a step that ends an episode reports ITS rewards and flags with the
+// next episode's first observation)
+FJSP_HD u32 wire_s0_res(u32 flags, int ps_local10) { return (wire_flag_bits(flags) << 19) | (code_ps(ps_local10) << 27); }
+FJSP_HD u32 wire_s1_res(int d_orders, int d_products) { return (u32)d_products | ((u32)d_orders << 10); }
+FJSP_HD void wire_cell_res(const int* l10, u32* w) {  // l10: agv, small machine, big machine, four packaging stations
+    w[0] |= code_agv(l10[0]) << 29;
+    w[1] |= (code_mach(l10[1]) << 28) | (code_mach(l10[2]) << 30);
+    w[2] |= code_pack(l10[3]) << 19;
+    w[3] |= (code_pack(l10[4]) << 19) | (code_pack(l10[6]) << 29);
+    w[4] |= code_pack(l10[5]) << 19;
+}
+
 template <int K>
 FJSP_HD void wire_row(const StepOut<K>& out, u32* row) {
 #pragma unroll
-    for (int i = 0; i < Wire<K>::OBSW; i++) row[i] = out.wobs[i];
+    for (int i = 0; i < Wire<K>::WORDS; i++) row[i] = i < Wire<K>::USED ? out.wire[i] : 0u;
+    row[0] |= wire_s0_res(out.flags, out.reward_local10[0]);
+    row[1] |= wire_s1_res(out.d_orders, out.d_products);
 #pragma unroll
-    for (int i = 0; i < Wire<K>::MW; i++) {
-        u32 bits = 0u;
-#pragma unroll
-        for (int j = 0; j < 8; j++) bits |= mask_nibble(out.mask[8 * i + j]) << (4 * j);
-        row[Wire<K>::OFF_MASK + i] = bits;
-    }
-    row[Wire<K>::OFF_G] = wire_g_word(out.reward_g, out.flags);
-#pragma unroll
-    for (int i = 0; i < Lay<K>::ACT / 2; i++)
-        row[Wire<K>::OFF_LOCAL + i] = ((u32)out.reward_local10[2 * i] & 0xffffu) | ((u32)out.reward_local10[2 * i + 1] << 16);
-#pragma unroll
-    for (int i = Wire<K>::END; i < Wire<K>::WORDS; i++) row[i] = 0u;
+    for (int c = 0; c < K; c++) wire_cell_res(out.reward_local10 + 1 + 7 * c, row + 2 + 5 * c);
 }
 
-// observation into the sink selected by MODE (OBS_FLOAT: out.obs, OBS_WIRE: out.wobs)
+// the observation part of the wire row of the current state
+template <int K, class S>
+FJSP_HD void observe_wire(S& s, const Params& P, const Hot& h, const HotCell& c0, u32* wire) {
+    {
+        int fs[7];
+        u32 mw = 0u;
+        observe_shared(s, P, h, FieldSink{fs}, &mw);
+        wire[0] = wire_s0_obs(fs, mask_nibble(mw));
+        wire[1] = (u32)h.ready_count << 19;
+    }
+#pragma unroll
+    for (int c = 0; c < K; c++) {
+        HotCell hc;
+        if (c > 0) load_cell<K>(s, c, hc);
+        int f[31];
+        u32 mw[7] = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        observe_cell(s, P, h, c == 0 ? c0 : hc, c, FieldSink{f}, mw, 0);
+        u32 bits = 0u;
+#pragma unroll
+        for (int i = 0; i < 7; i++) bits |= mask_nibble(mw[i]) << (4 * i);
+        wire_cell_obs(f, bits, wire + 2 + 5 * c);
+    }
+}
+
+// observation into the sink selected by MODE (OBS_FLOAT: out.obs + out.mask, OBS_WIRE: out.wire)
 template <int K, int MODE, class S>
 FJSP_HD void observe_out(S& s, const Params& P, const Hot& h, const HotCell& c0, StepOut<K>& out) {
     if (MODE == OBS_FLOAT) {
         observe<K>(s, P, h, c0, FloatSink{out.obs, P}, out.mask);
     } else if (MODE == OBS_WIRE) {
-#pragma unroll
-        for (int i = 0; i < (Lay<K>::OBS + 3) / 4; i++) out.wobs[i] = 0u;
-        observe<K>(s, P, h, c0, WireSink{out.wobs, 0}, out.mask);
+        observe_wire<K>(s, P, h, c0, out.wire);
     }
 }
 
@@ -958,7 +1012,8 @@ FJSP_HD void step_env_hot(S& s, const Params& P, Hot& h, HotCell& c0, const int*
     // One correctly rounded fp32 division of that integer reproduces the fp32 rounding of the reference's float64 value
     // (no FP64 in the kernel; a non-dyadic k/(10A) is never within double-rounding distance of an fp32 midpoint).
     {
-        const int g = 10 * (100 * (h.completed_orders - orders_before) + 10 * (h.total_packaged - products_before)) - P.step_size;
+        out.d_orders = h.completed_orders - orders_before, out.d_products = h.total_packaged - products_before;
+        const int g = 10 * (100 * out.d_orders + 10 * out.d_products) - P.step_size;
         long long units = 0;
         out.reward_g = g;
 #pragma unroll
@@ -1029,6 +1084,7 @@ struct CellLane {
     int local10[8];  // [0] pickup station (meaningful on the lane of cell 0), [1..7] the cell's agents
     u32 res[8];
     int g;           // after cells_finish: 10 * (100 * orders + 10 * products) - step_size
+    int d_orders, d_products;
     u32 flags;
 };
 
@@ -1082,6 +1138,7 @@ FJSP_HD void cells_finish(X& x, const Params& P, CellLane& L, int32_t* info) {
         if (f) h.fault = f;
     }
     L.g = 10 * (100 * d_orders + 10 * d_products) - P.step_size;
+    L.d_orders = d_orders, L.d_products = d_products;
     const int all_done = h.completed_orders == h.num_orders && h.num_orders > 0 && h.next_order == h.num_orders;
     const int truncated = L.k >= P.max_episode_steps;
     L.flags = (u32)all_done | ((u32)truncated << 8) | ((u32)h.fault << 16);
@@ -1114,6 +1171,27 @@ FJSP_HD void cells_observe(S& s, X& x, const Params& P, const CellLane& L, O obs
 #pragma unroll
     for (int i = 0; i < 7; i++) bits |= mask_nibble(mw[i]) << (4 * i);
     x.st(X_MASK + 1 + L.c, bits & 0x3ffffffu);
+}
+
+// the lane's part of the env's WIRE row: its cell's five words (observation + its seven agents' reward codes), plus the
+// two shared words on the lane of cell 0.  Nothing is posted: every bit of a word comes from the lane that writes it.
+template <int K, class S>
+FJSP_HD void cells_observe_wire(S& s, const Params& P, const CellLane& L, u32* shared2, u32* cell5) {
+    if (L.c == 0) {
+        int fs[7];
+        u32 mw = 0u;
+        observe_shared(s, P, L.h, FieldSink{fs}, &mw);
+        shared2[0] = wire_s0_obs(fs, mask_nibble(mw)) | wire_s0_res(L.flags, L.local10[0]);
+        shared2[1] = ((u32)L.h.ready_count << 19) | wire_s1_res(L.d_orders, L.d_products);
+    }
+    int f[31];
+    u32 mw[7] = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    observe_cell(s, P, L.h, L.hc, L.c, FieldSink{f}, mw, 0);
+    u32 bits = 0u;
+#pragma unroll
+    for (int i = 0; i < 7; i++) bits |= mask_nibble(mw[i]) << (4 * i);
+    wire_cell_obs(f, bits, cell5);
+    wire_cell_res(L.local10 + 1, cell5);
 }
 
 // mask bits [32 * word, 32 * word + 32) of the env's mask row, from the posted pieces

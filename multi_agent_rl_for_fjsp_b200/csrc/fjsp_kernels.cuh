@@ -35,8 +35,8 @@ struct Geo {
     static constexpr int OBS_ROW_BYTES = Lay<K>::OBS * 4;           // 152 / 524
     static constexpr int OBS_TILE_BYTES = OBS_ROW_BYTES * TILE;     // 9728 / 33536
     static constexpr int STEP_SMEM_BYTES = DYN_BYTES + OBS_TILE_BYTES + 16;
-    static constexpr int WIRE_ROW_BYTES = Wire<K>::WORDS * 4;        // 64 / 216
-    static constexpr int WIRE_TILE_BYTES = WIRE_ROW_BYTES * TILE;    // 4096 / 13824
+    static constexpr int WIRE_ROW_BYTES = Wire<K>::WORDS * 4;        // 32 / 88
+    static constexpr int WIRE_TILE_BYTES = WIRE_ROW_BYTES * TILE;    // 2048 / 5632
     static constexpr int STEP_WIRE_SMEM_BYTES = DYN_BYTES + WIRE_TILE_BYTES + 16;
     static constexpr int ROLLOUT_SMEM_BYTES = DYN_BYTES + 16;
     // cell-parallel step (K >= 2): TILE x K threads per CTA, + the exchange block
@@ -364,8 +364,6 @@ __global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_step_
         for (int i = 0; i < 7; i++) a7[i] = valid ? (int)__ldg(arow + 1 + 7 * c + i) : 0;
     }
     for (int i = tid; i < Xl<K>::WORDS * TILE; i += NT) s_x[i] = 0u;
-    if (WIRE)
-        for (int i = tid; i < OUT_TILE_BYTES / 4; i += NT) s_out[i] = 0u;  // wire rows are assembled with ORs
     __syncthreads();  // mbarrier initialised and exchange area zeroed for everyone
     mbar_wait(bar, 0);
 
@@ -389,17 +387,16 @@ __global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_step_
         }
     }
     if (valid) {
-        if (WIRE) {  // the lane's 31 (+7) observation bytes, shifted to their place in the row and OR-ed in
-            u32 wc[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, wsh[2] = {0u, 0u};
-            cells_observe<K>(s, x, P, L, WireSink{wsh, 0}, WireSink{wc, 0});
+        if (WIRE) {  // the lane's five words of the row (+ the two shared ones on the lane of cell 0): plain stores
+            u32 w5[5], s2[2];
+            cells_observe_wire<K>(s, P, L, s2, w5);
             u32* row = s_out + e * Wire<K>::WORDS;
-            const int off = 7 + 31 * c, w0 = off >> 2, sh = (off & 3) * 8;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                atomicOr(&row[w0 + i], wc[i] << sh);
-                if (sh) atomicOr(&row[w0 + i + 1], wc[i] >> (32 - sh));
+            for (int i = 0; i < 5; i++) row[2 + 5 * c + i] = w5[i];
+            if (c == 0) {
+                row[0] = s2[0], row[1] = s2[1];
+                if (Wire<K>::WORDS > Wire<K>::USED) row[Wire<K>::WORDS - 1] = 0u;
             }
-            if (c == 0) atomicOr(&row[0], wsh[0]), atomicOr(&row[1], wsh[1]);
         } else {
             float* orow = reinterpret_cast<float*>(s_out) + e * Lay<K>::OBS;
             cells_observe<K>(s, x, P, L, FloatSink{orow, P}, FloatSink{orow + 7 + 31 * c, P});
@@ -414,14 +411,7 @@ __global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_step_
         u32 v16[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) v16[i] = x.ld16(2 * Xl<K>::LOCAL + 8 * c + i);
-        if (WIRE) {
-            u32* row = s_out + e * Wire<K>::WORDS;
-            row[Wire<K>::OFF_MASK + c] = mbits;
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                row[Wire<K>::OFF_LOCAL + 4 * c + i] = ((u32)x_local10(v16[2 * i]) & 0xffffu) | ((u32)x_local10(v16[2 * i + 1]) << 16);
-            if (c == 0) row[Wire<K>::OFF_G] = wire_g_word(L.g, L.flags);
-        } else {
+        if (!WIRE) {
             uint4* m4 = reinterpret_cast<uint4*>(A.masks + env * Lay<K>::MASK + 32 * c);
             m4[0] = make_uint4(nibble_bytes(mbits), nibble_bytes(mbits >> 4), nibble_bytes(mbits >> 8), nibble_bytes(mbits >> 12));
             m4[1] = make_uint4(nibble_bytes(mbits >> 16), nibble_bytes(mbits >> 20), nibble_bytes(mbits >> 24), nibble_bytes(mbits >> 28));

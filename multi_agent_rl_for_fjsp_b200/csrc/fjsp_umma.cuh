@@ -136,17 +136,26 @@ constexpr int G_A_BYTES = G_NQ * G_LBO_A, G_B_BYTES = G_NQ * G_LBO_B;    // one 
 constexpr int G_STAGE_BYTES = 2 * (G_A_BYTES + G_B_BYTES);
 constexpr int G_STAGES = 2;
 constexpr int G_SMEM_BYTES = G_STAGES * G_STAGE_BYTES;                   // 99,328: two CTAs per SM
+constexpr int G_EPI_LD = 132;          // floats per row of the epilogue's staging area (128 columns + 4: conflict-free)
+static_assert(G_BM * G_EPI_LD * 4 <= G_SMEM_BYTES, "the epilogue stages 128 x 128 floats in the pipeline's shared memory");
 constexpr int G_PRODUCERS = 256;      // warps 0..7 load; warps 0..3 are also the epilogue; warp 8 issues the MMAs
 constexpr int G_THREADS = G_PRODUCERS + 32;
 
 __device__ __forceinline__ uint32_t plane_off(int r, int q, int lbo) { return (uint32_t)(q * lbo + (r >> 3) * 128 + (r & 7) * 16); }
 
+// fp32 -> (hi, lo) with hi = the nearest TF32 (round half away: one integer add + mask) and lo = tf32(x - hi); x - hi is
+// exact in fp32.
+// (cvt.rna.tf32.f32 would do the same rounding on the XU pipe at 16 lanes per clock per SM: two of them per element made
+// the conversion, not the MMAs, the limiter of the first version of this kernel — ncu: xu pipe saturated, tensor 18 %.)
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void split_store(unsigned char* hi, unsigned char* lo, uint32_t off, float4 v, bool three) {
-    uint4 h = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    const uint4 h = make_uint4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
     *reinterpret_cast<uint4*>(hi + off) = h;
     if (three) {
-        uint4 l = make_uint4(to_tf32(v.x - __uint_as_float(h.x)), to_tf32(v.y - __uint_as_float(h.y)),
-                             to_tf32(v.z - __uint_as_float(h.z)), to_tf32(v.w - __uint_as_float(h.w)));
+        // lo is rounded to TF32 as well: left to the hardware it would be CUT to 11 bits, a bias that adds up linearly
+        // over the K = batch-size sums of the weight gradients
+        const uint4 l = make_uint4(tf32_hi(v.x - __uint_as_float(h.x)), tf32_hi(v.y - __uint_as_float(h.y)),
+                                   tf32_hi(v.z - __uint_as_float(h.z)), tf32_hi(v.w - __uint_as_float(h.w)));
         *reinterpret_cast<uint4*>(lo + off) = l;
     }
 }
@@ -226,7 +235,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
     extern __shared__ __align__(128) unsigned char g_smem[];
     __shared__ uint64_t s_full[G_STAGES], s_empty[G_STAGES], s_acc;
     __shared__ uint32_t s_tmem;
-    __shared__ float s_colsum[G_BN];
+    __shared__ float s_colsum[G_BN], s_bias[G_BN];
 
     const GemmProb P = probs[blockIdx.y];
     const int mtiles = (P.M + G_BM - 1) / G_BM;
@@ -250,7 +259,25 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
         for (int s = 0; s < G_STAGES; s++) mbar_init(&s_full[s], G_PRODUCERS / 32), mbar_init(&s_empty[s], 1);
         mbar_init(&s_acc, 1);
     }
-    if (tid < G_BN) s_colsum[tid] = 0.f;
+    if (tid == 32 && AOP != OP_MC) {
+        // The pipeline reads the A tile 64 bytes per row and stage: 128 row segments 1 KB apart, a DRAM-hostile pattern
+        // (ncu, first version: long-scoreboard stalls on these loads dominated, DRAM at 19 % with the tensor pipe at 18 %).
+        // The rows of a tile are (nearly) contiguous in memory, so ONE bulk L2 prefetch streams the whole tile — and the
+        // ReLU-mask tile the epilogue will read — in DRAM order; the strided loads then hit L2.
+        const int rows = min(G_BM, P.M - m0);
+        const int kb = c_begin * G_KC, kn = min(P.K, c_end * G_KC) - kb;
+        if (P.lda <= 2 * P.K) {
+            const uintptr_t a0 = reinterpret_cast<uintptr_t>(P.A + (int64_t)m0 * P.lda + kb);
+            const uintptr_t a1 = a0 + ((size_t)(rows - 1) * P.lda + kn) * 4;
+            bulk_prefetch_l2(reinterpret_cast<const void*>(a0 & ~(uintptr_t)15), (uint32_t)(((a1 + 15) & ~(uintptr_t)15) - (a0 & ~(uintptr_t)15)));
+        }
+        if (P.mask && P.csn == 1 && P.csm <= 2 * P.N) {
+            const uintptr_t a0 = reinterpret_cast<uintptr_t>(P.mask + (int64_t)m0 * P.csm);
+            const uintptr_t a1 = a0 + ((size_t)(rows - 1) * P.csm + P.N) * 4;
+            bulk_prefetch_l2(reinterpret_cast<const void*>(a0 & ~(uintptr_t)15), (uint32_t)(((a1 + 15) & ~(uintptr_t)15) - (a0 & ~(uintptr_t)15)));
+        }
+    }
+    if (tid < G_BN) s_colsum[tid] = 0.f, s_bias[tid] = (P.bias && tid < P.N) ? __ldg(P.bias + tid) : 0.f;
     if (warp == G_PRODUCERS / 32) tmem_alloc(&s_tmem, ncols);
     fence_before_sync();
     __syncthreads();
@@ -305,58 +332,73 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
     }
 
     if (warp < 4) {
-        // ===== epilogue: thread = one row of the tile (TMEM lane 32 * warp + lane) =====
+        // ===== epilogue =====
+        // Phase 1, thread = one row of the tile (TMEM lane 32 * warp + lane): accumulator -> registers (tcgen05.ld) -> + bias,
+        // ReLU -> shared memory (the pipeline stages are free now), 128 columns at a time, row stride 132 floats so the
+        // 16-byte stores of 8 consecutive rows fall into 8 different bank groups.
+        // Phase 2, warp = the same 32 rows, lane = 4 consecutive columns: one row per iteration leaves as ONE coalesced
+        // 512-byte store (or 128 coalesced atomics); the ReLU mask is read the same way, column sums stay in registers.
+        // A warp only ever touches its own 32 rows of the staging area, so __syncwarp() is all the synchronisation needed.
         mbar_wait_or_trap(&s_acc, 0);
         fence_after_sync();
-        const int m = m0 + warp * 32 + lane;
-        const bool mok = m < P.M;
         const bool atomic = P.flags & GEMM_ATOMIC, relu = P.flags & GEMM_RELU;
         const bool vec = !atomic && P.csn == 1 && (P.csm & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0) &&
                          (!P.mask || (reinterpret_cast<uintptr_t>(P.mask) & 15) == 0);
-        for (int n0 = 0; n0 < npad; n0 += 16) {
-            float v[16];
-            tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, v);
-            if (P.bias) {
+        float* stage = reinterpret_cast<float*>(g_smem) + (warp * 32) * G_EPI_LD;
+        for (int h0 = 0; h0 < npad; h0 += 128) {
+            const int ncol = min(128, npad - h0);
+            for (int n0 = 0; n0 < ncol; n0 += 16) {
+                float v[16];
+                tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(h0 + n0), v);
+                if (P.bias) {
 #pragma unroll
-                for (int i = 0; i < 16; i++) v[i] += (n0 + i < P.N) ? __ldg(P.bias + n0 + i) : 0.f;
-            }
-            if (relu) {
+                    for (int i = 0; i < 16; i++) v[i] += s_bias[h0 + n0 + i];
+                }
+                if (relu) {
 #pragma unroll
-                for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f);
+                    for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f);
+                }
+                float4* dst = reinterpret_cast<float4*>(stage + lane * G_EPI_LD + n0);
+#pragma unroll
+                for (int i = 0; i < 4; i++) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
-            float* crow = P.C + (int64_t)m * P.csm;
-            const float* mrow = P.mask ? P.mask + (int64_t)m * P.csm : nullptr;
-            if (vec && n0 + 16 <= P.N) {
-                if (mok) {
+            __syncwarp();
+            const int n = h0 + 4 * lane;         // this lane's 4 columns
+            const bool nany = 4 * lane < ncol && n < P.N;
+            float cs[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int r = 0; r < 32; r++) {
+                const int m = m0 + warp * 32 + r;
+                if (m >= P.M) break;              // uniform over the warp
+                if (!nany) continue;
+                float4 o = *reinterpret_cast<const float4*>(stage + r * G_EPI_LD + 4 * lane);
+                float* cp = P.C + (int64_t)m * P.csm + (int64_t)n * P.csn;
+                if (vec && n + 4 <= P.N) {
+                    if (P.mask) {
+                        const float4 k4 = __ldg(reinterpret_cast<const float4*>(P.mask + (int64_t)m * P.csm + n));
+                        o.x = k4.x > 0.f ? o.x : 0.f, o.y = k4.y > 0.f ? o.y : 0.f, o.z = k4.z > 0.f ? o.z : 0.f, o.w = k4.w > 0.f ? o.w : 0.f;
+                    }
+                    *reinterpret_cast<float4*>(cp) = o;
+                    cs[0] += o.x, cs[1] += o.y, cs[2] += o.z, cs[3] += o.w;
+                } else {
+                    const float e[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                        if (mrow) {
-                            const float4 k4 = __ldg(reinterpret_cast<const float4*>(mrow + n0) + i);
-                            o.x = k4.x > 0.f ? o.x : 0.f, o.y = k4.y > 0.f ? o.y : 0.f, o.z = k4.z > 0.f ? o.z : 0.f, o.w = k4.w > 0.f ? o.w : 0.f;
-                            v[4 * i] = o.x, v[4 * i + 1] = o.y, v[4 * i + 2] = o.z, v[4 * i + 3] = o.w;
+                        if (n + i < P.N) {
+                            float x = e[i];
+                            if (P.mask && !(__ldg(P.mask + (int64_t)m * P.csm + (int64_t)(n + i) * P.csn) > 0.f)) x = 0.f;
+                            if (atomic) atomicAdd(cp + (int64_t)i * P.csn, x);
+                            else cp[(int64_t)i * P.csn] = x;
+                            cs[i] += x;
                         }
-                        reinterpret_cast<float4*>(crow + n0)[i] = o;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const int n = n0 + i;
-                    if (mok && n < P.N) {
-                        if (mrow && !(__ldg(mrow + (int64_t)n * P.csn) > 0.f)) v[i] = 0.f;
-                        if (atomic) atomicAdd(crow + (int64_t)n * P.csn, v[i]);
-                        else crow[(int64_t)n * P.csn] = v[i];
                     }
                 }
             }
-            if (P.colsum) {
+            if (P.colsum && nany) {
 #pragma unroll
-                for (int i = 0; i < 16; i++) v[i] = mok ? v[i] : 0.f;
-                const float sum = warp_colsum16(v, lane);
-                const int col = n0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                if (!(lane & 1)) atomicAdd(&s_colsum[col], sum);
+                for (int i = 0; i < 4; i++)
+                    if (n + i < P.N) atomicAdd(&s_colsum[n + i], cs[i]);
             }
+            __syncwarp();   // the staging rows are rewritten by the next column block
         }
         fence_before_sync();
     }

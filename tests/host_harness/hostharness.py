@@ -100,7 +100,7 @@ class HostEnv:
     def step_wire(self, actions):
         """step() that also returns the wire row (include/fjsp_b200.h) of the same step."""
         a = np.ascontiguousarray(actions, dtype=np.uint8)
-        words = ((7 + 31 * self.cells + 3) // 4 + len(self.masks) // 32 + 1 + len(self.rewards) // 2 + 1) // 2 * 2
+        words = (2 + 5 * self.cells + 1) // 2 * 2  # FJSP_WIRE_WORDS_K
         wire = np.zeros(words, np.uint32)
         self._L.hh_step_wire(self._h, a.ctypes.data, self.obs.ctypes.data, self.masks.ctypes.data, self.rewards.ctypes.data,
                              self.flags.ctypes.data, wire.ctypes.data)

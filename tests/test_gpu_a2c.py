@@ -83,7 +83,7 @@ def test_training_runs_and_fused_path_matches_torch_path(graph):
 
     def run(use_graph):
         env = BatchedFJSPEnv(512, seed=3, num_orders=25, autoreset=True)
-        tr = BatchedA2C(env, rollout_len=8, seed=2, use_cuda_graph=use_graph)
+        tr = BatchedA2C(env, rollout_len=8, seed=2, use_cuda_graph=use_graph, impl="torch")  # deterministic reductions
         p0 = torch.cat([p.detach().reshape(-1) for p in tr.net.parameters()]).clone()
         tr.train(3)
         p1 = torch.cat([p.detach().reshape(-1) for p in tr.net.parameters()])
@@ -138,3 +138,101 @@ def test_reference_layout_checkpoint_round_trip_on_device(tmp_path):
             assert torch.allclose(p_src[:, MASK_OFFSETS[i]:MASK_OFFSETS[i] + N_ACTIONS[i]], ref, rtol=1e-5, atol=1e-6), a
         critic, _ = sequential(ckpt["critic_net"], [38, 256, 256, 128, 1], False)
         assert torch.allclose(v_src, critic(obs).squeeze(-1), rtol=1e-5, atol=1e-5)
+
+
+def _pair(n_envs, T, passes=3):
+    """Two trainers with identical weights on identical envs: the tensor-core engine and the torch / autograd statement."""
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+    from multi_agent_rl_for_fjsp_b200.a2c_batched import BatchedA2C
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    mk = lambda impl: BatchedA2C(BatchedFJSPEnv(n_envs, seed=3, num_orders=25, autoreset=True), rollout_len=T, seed=2,  # noqa: E731
+                                 use_cuda_graph=False, impl=impl, gemm_passes=passes)
+    return mk("umma"), mk("torch")
+
+
+def test_umma_forward_equals_torch_fp32_forward():
+    """Rollout forward of the 8 actors + critic as grouped tcgen05 GEMMs vs the same networks in torch fp32 (rtol 1e-5)."""
+    a, b = _pair(1000, 4)
+    a.rollout()
+    with torch.no_grad():
+        for t in range(a.T):
+            z = b.net.logits32(a.obs[t])
+            v = b.net.value(a.obs[t])
+            assert torch.allclose(a.engine.logits[t], z, rtol=1e-5, atol=2e-5), float((a.engine.logits[t] - z).abs().max())
+            assert torch.allclose(a.values[t], v, rtol=1e-5, atol=2e-5), float((a.values[t] - v).abs().max())
+        assert torch.allclose(a.values[a.T], b.net.value(a.obs[a.T]), rtol=1e-5, atol=2e-5)
+        h2 = torch.relu(torch.addmm(b.net.agv[3][0], torch.relu(torch.addmm(b.net.agv[1][0], a.obs[1][:, 7:20], b.net.agv[0])), b.net.agv[2]))
+        assert torch.allclose(a.engine.h2[1, 1], h2, rtol=1e-5, atol=2e-5)
+
+
+def _fp64_grads(tr):
+    """The update's gradients from the trainer's rollout buffers in float64 (torch autograd): the yardstick for both paths."""
+    import copy
+
+    from multi_agent_rl_for_fjsp_b200 import a2c_batched as A
+
+    net = copy.deepcopy(tr.net).double()
+    for p in net.parameters():
+        p.grad = None
+    T, N = tr.T, tr.env.num_envs
+    B = T * N
+    dones = (tr.flags[:, :, 0:3] != 0).any(-1)
+    ret, adv = A.gae_and_returns(tr.rewards.double(), tr.values.double(), dones, tr.gamma, tr.lamb)
+    obs, masks, acts = tr.obs[:T].reshape(B, 38).double(), tr.masks[:T].reshape(B, 32), tr.actions.reshape(B, 8)
+    ret, adv = ret.reshape(B, 8), adv.reshape(B, 8)
+    adv_n = (adv - adv.mean(0)) / (adv.std(0) + 1e-8)
+    probs = net.probs32(obs)
+    logp = A.log_prob_of(A.masked_policy(probs, masks), acts)
+    # Categorical's clamp uses the fp32 epsilon in both trainers; in float64 it would be 2.2e-16: same gradients (zero
+    # where the clamp is active in either precision: q = 1 exactly), log-probabilities equal to 1.2e-7
+    loss = (-(adv_n * logp).mean(0) - tr.entropy_coef * A.entropy_unmasked(probs).mean(0)).sum()
+    v = net.value(obs)
+    loss = loss + torch.nn.functional.mse_loss(v.unsqueeze(-1).expand_as(ret), ret)
+    loss.backward()
+    return [p.grad for p in net.parameters()]
+
+
+@pytest.mark.parametrize("n_envs,T", [(512, 8), (1000, 5)])
+def test_umma_update_equals_autograd_update(n_envs, T):
+    """One update from the SAME rollout: analytic loss gradients + tcgen05 backward GEMMs vs torch autograd.  Both fp32
+    paths are measured against the float64 gradients: the tensor-core path must be as accurate as the fp32 library
+    path (3xTF32 is fp32-level), and the two must agree on losses, clipped gradients and the Adam step."""
+    a, b = _pair(n_envs, T)
+    a.rollout()
+    for name in ("obs", "masks", "actions", "rewards", "flags", "values"):
+        getattr(b, name).copy_(getattr(a, name))
+    g64 = _fp64_grads(a)
+    a._compute_grads()
+    b._compute_grads()
+    for k in ("actor_loss", "critic_loss", "entropy"):
+        assert torch.allclose(a.stats[k], b.stats[k], rtol=2e-4, atol=1e-5), (k, a.stats[k], b.stats[k])
+    for (na, pa), (nb, pb), g in zip(a.net.named_parameters(), b.net.named_parameters(), g64):
+        scale = g.abs().max().item() + 1e-12
+        err_a, err_b = (pa.grad.double() - g).abs().max().item(), (pb.grad.double() - g).abs().max().item()
+        assert err_a <= 3 * err_b + 2e-5 * scale, (na, err_a, err_b, scale)
+        assert err_a <= 1e-3 * scale, (na, err_a, scale)
+    a._clip(), a.opt.step()
+    b._clip(), b.opt.step()
+    for (na, pa), (nb, pb) in zip(a.net.named_parameters(), b.net.named_parameters()):
+        # Adam's first step moves every weight by lr * g / (|g| + 1e-8): where the gradient is not numerically zero the
+        # two updates must coincide; where it is, the step's sign is noise in both implementations
+        sure = pb.grad.abs() > 1e-3 * pb.grad.abs().max()
+        assert torch.allclose(pa[sure], pb[sure], rtol=1e-5, atol=2e-6), na
+
+
+def test_umma_training_with_graphs_and_tf32_variant():
+    """The tensor-core trainer end to end (CUDA-graph rollout and update): finite, parameters move, frames counted;
+    plain-TF32 GEMMs (gemm_passes=1) also train."""
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+    from multi_agent_rl_for_fjsp_b200.a2c_batched import BatchedA2C
+
+    for passes in (3, 1):
+        tr = BatchedA2C(BatchedFJSPEnv(512, seed=3, num_orders=25, autoreset=True), rollout_len=8, seed=2, gemm_passes=passes)
+        assert tr.impl == "umma"
+        p0 = torch.cat([p.detach().reshape(-1) for p in tr.net.parameters()]).clone()
+        tr.train(5)
+        p1 = torch.cat([p.detach().reshape(-1) for p in tr.net.parameters()])
+        assert torch.isfinite(p1).all() and not torch.equal(p0, p1)
+        assert torch.isfinite(tr.stats["critic_loss"]) and tr.frames == 5 * 8 * 512
+        assert tr._ugraph is not None, tr.update_graph_error

@@ -101,35 +101,65 @@ def test_wire_decode_partial_outputs_and_errors():
     assert L.fjsp_wire_decode(C.byref(cfg), rows.ctypes.data, 5, obs.ctypes.data, None, None, None, 1) == 0
     assert (obs[:, :11] == 0).all()
     assert L.fjsp_wire_decode(C.byref(cfg), None, 5, obs.ctypes.data, None, None, None, 1) != 0
-    assert L.fjsp_wire_row_bytes(0) == 0 and L.fjsp_wire_row_bytes(5) == 0 and L.fjsp_wire_row_bytes(1) == 64
+    assert L.fjsp_wire_row_bytes(0) == 0 and L.fjsp_wire_row_bytes(5) == 0 and L.fjsp_wire_row_bytes(1) == 32 and L.fjsp_wire_row_bytes(4) == 88
 
 
 def numpy_decode(cfg, rows):
-    """Independent NumPy statement of the wire format (include/fjsp_b200.h) — not the library's code."""
+    """Independent NumPy statement of the wire format, written from the description in include/fjsp_b200.h — not the
+    library's code."""
     k = int(cfg.num_cells)
     d = dims(k)
     A, obs_n, mask_n, act_n = d["agents"], d["obs"], d["mask"], d["act"]
     n = rows.shape[0]
-    b = rows.view(np.uint8).reshape(n, -1)
-    obsw, mw = (obs_n + 3) // 4, mask_n // 32
-    obs = b[:, :obs_n].astype(np.float32)
+    r = rows.astype(np.int64)
+
+    def f(word, shift, width):
+        return (r[:, word] >> shift) & ((1 << width) - 1)
+
     pos = np.array([[cfg.pos[i][0], cfg.pos[i][1]] for i in range(5)] + [[cfg.pos[0][0], cfg.pos[0][1]]] * 3, np.float32)
     prog = np.zeros(256, np.float32)
     prog[1:] = ((1.0 / np.arange(1, 256, dtype=np.float64)) * 100.0).astype(np.float32)
+    i8 = lambda x: x.astype(np.uint8).view(np.int8).astype(np.float32)  # noqa: E731
+    obs = np.zeros((n, obs_n), np.float32)
+    masks = np.zeros((n, mask_n), np.int8)
+    local = np.zeros((n, act_n), np.int64)
+    lut = {"ps": np.array([0, -10, 10, 60]), "agv": np.array([0, -1, 20, 120, -50, 0, 0, 0]),
+           "m": np.array([0, -20, 10, 50]), "p": np.array([0, -10, 20, 200])}
+    # word 0: pickup station, flags, its mask bits and reward code; word 1: counters
+    for j, (sh, wd) in enumerate(((0, 2), (2, 3), (5, 2), (7, 2), (9, 2), (11, 4), (15, 4))):
+        obs[:, j] = f(0, sh, wd)
+    fb = f(0, 19, 6)
+    flags = np.stack([fb & 1, (fb >> 1) & 1, (fb >> 2) & 7, (fb >> 5) & 1], axis=1).astype(np.uint8)
+    masks[:, 0], masks[:, 1], masks[:, 2] = 1, f(0, 25, 1), f(0, 26, 1)
+    local[:, 0] = lut["ps"][f(0, 27, 2)]
+    products, orders, ready = f(1, 0, 10), f(1, 10, 9), f(1, 19, 13)
+    g = 10 * (100 * orders + 10 * products) - int(cfg.step_size)
     for c in range(k):
-        base = 7 + 31 * c
-        obs[:, base + 4] = pos[b[:, base + 4] & 7, 0]
-        obs[:, base + 5] = pos[b[:, base + 5] & 7, 1]
-        for i in range(4):
-            obs[:, base + 20 + 3 * i] = prog[b[:, base + 20 + 3 * i]]
-            obs[:, base + 21 + 3 * i] = b[:, base + 21 + 3 * i].view(np.int8).astype(np.float32)
-    bits = rows[:, obsw:obsw + mw]
-    masks = ((bits[:, :, None] >> np.arange(32, dtype=np.uint32)[None, None, :]) & 1).astype(np.int8).reshape(n, mask_n)
-    gw = rows[:, obsw + mw]
-    g = ((gw << np.uint32(8)).view(np.int32) >> 8).astype(np.int64)
-    fb = gw >> np.uint32(24)
-    flags = np.stack([fb & 1, (fb >> 1) & 1, (fb >> 2) & 3, (fb >> 4) & 1], axis=1).astype(np.uint8)
-    local = rows[:, obsw + mw + 1:obsw + mw + 1 + act_n // 2].copy().view(np.int16).reshape(n, act_n).astype(np.int64)
+        w, b, mo, ac = 2 + 5 * c, 7 + 31 * c, 3 + 26 * c, 1 + 7 * c
+        loc = f(w, 0, 3)
+        carrying = f(w, 3, 1)
+        small = (f(w + 1, 8, 1), f(w + 1, 9, 1), f(w + 1, 10, 6))
+        big = (f(w + 1, 16, 1), f(w + 1, 17, 1), f(w + 1, 18, 6))
+        agv = [big[0], f(w, 10, 6), carrying, ready, pos[loc, 0], pos[loc, 1], small[0], f(w, 16, 6), f(w + 1, 0, 8), carrying,
+               f(w, 4, 1), f(w, 5, 3), f(w, 8, 2)]
+        for j, v in enumerate(agv + list(small) + list(big)):
+            obs[:, b + j] = v
+        masks[:, mo] = 1
+        for j in range(7):
+            masks[:, mo + 1 + j] = f(w, 22 + j, 1)
+        local[:, ac] = lut["agv"][f(w, 29, 3)]
+        for i, (sh, csh) in enumerate(((24, 28), (26, 30))):
+            masks[:, mo + 8 + 3 * i] = 1
+            masks[:, mo + 9 + 3 * i], masks[:, mo + 10 + 3 * i] = f(w + 1, sh, 1), f(w + 1, sh + 1, 1)
+            local[:, ac + 1 + i] = lut["m"][f(w + 1, csh, 2)]
+        # packaging_blue_1, _blue_2, _red: one word each; packaging_green: shared out over the spare bits of the first two
+        stations = [(f(w + 2 + i, 0, 1), f(w + 2 + i, 1, 8), f(w + 2 + i, 9, 8), f(w + 2 + i, 17, 1), f(w + 2 + i, 18, 1), f(w + 2 + i, 19, 2))
+                    for i in range(3)]
+        stations.append((f(w + 2, 29, 1), f(w + 2, 21, 8), f(w + 3, 21, 8), f(w + 2, 30, 1), f(w + 2, 31, 1), f(w + 3, 29, 2)))
+        for i, (busy, L, q, m1, m2, code) in enumerate(stations):
+            obs[:, b + 19 + 3 * i], obs[:, b + 20 + 3 * i], obs[:, b + 21 + 3 * i] = busy, prog[L], i8(q)
+            masks[:, mo + 14 + 3 * i], masks[:, mo + 15 + 3 * i], masks[:, mo + 16 + 3 * i] = 1, m1, m2
+            local[:, ac + 3 + i] = lut["p"][code]
     num = (g[:, None] + A * local).astype(np.float32)
     rew = (num / np.float32(10 * A)).astype(np.float32)
     rew[:, A:] = 0.0

@@ -13,10 +13,12 @@ value      device-timed (CUDA events on the launching stream), inputs resident i
            so the working set exceeds the 126 MB L2 without a flush.
 e2e        the same metric through the host-buffer C-ABI call fjsp_step_host: pinned host actions in, pinned host
            float32 obs / int8 masks / float32 rewards / u8 flags out, H2D + D2H copies inside the timed region.  The
-           results cross PCIe as 64-byte wire rows (include/fjsp_b200.h) and are decoded into the caller's tensors
+           results cross PCIe as 32-byte wire rows (include/fjsp_b200.h) and are decoded into the caller's tensors
            by the library's host threads, pipelined with the copies; d2h_bytes_per_step counts the bytes that cross.
 roofline   algorithmic bytes per launch = envs x (8 + 152 + 32 + 32 + 4 + 2 x 512) = envs x 1252 B,
-           divided by the mean launch duration, against MEASURED_PEAKS.json hbm_gbs.
+           divided by the mean launch duration, against MEASURED_PEAKS.json hbm_gbs.  traffic = the ncu DRAM bytes per
+           launch from profiles/ncu_traffic.json, only when the kernel's SASS hash there matches the running library.
+strong_scaling  configs[3] as written: 2^20 envs in total over the N GPUs (the headline keeps 2^20 per GPU).
            e2e.undecoded_wire_rows_variant: the same pipeline delivering the rows as they are (fjsp_step_host_wire);
            e2e.decode_only_ms: the host decode alone.  Reported beside the headline, never instead of it.
 cpu_baseline / --impl reference
@@ -24,7 +26,8 @@ cpu_baseline / --impl reference
            (oracle/fjsp_oracle.c, kind "port") on all host threads, on a bounded sample of the same workload.
 extra      (N = 1) BASELINE configs[1]: 4096 envs, stepwise / CUDA-graph / K-steps-per-launch figures.
 scaled_shop (N = 1) BASELINE configs[4]: the 4-cell shop (29 agents) at 2^19 envs with its own roofline fraction.
-a2c        BASELINE configs[2]: batched A2C frames/s, 4096 envs per GPU, rollout 32 (fp32; TF32 variant beside it).
+a2c        BASELINE configs[2]: batched A2C frames/s, 4096 envs per GPU, rollout 32: grouped tcgen05 GEMMs in 3xTF32
+           (fp32-level accuracy); single-pass TF32 and the torch / cuBLAS fp32 trainer beside it.
 """
 from __future__ import annotations
 
@@ -45,9 +48,7 @@ UNIT = "agent-steps/s"
 BYTES_IO = 8 + 152 + 32 + 32 + 4
 STATE_BYTES = 512
 BYTES_PER_ENV_STEP = BYTES_IO + 2 * STATE_BYTES  # 1252
-# dram__bytes_read.sum + dram__bytes_write.sum of one fjsp_step_kernel launch at 2^20 envs, from the committed
-# `ncu --set full` capture profiles/r01_step_kernel_full_raw.csv (545.4 MB + 714.2 MB); only valid for the default size
-NCU_TRAFFIC_BYTES_2P20 = 545.384192e6 + 714.157056e6
+SAMPLE_ENVS, SAMPLE_INNER = 8192, 64  # the CPU arm's bounded sample: the same in cpu_baseline and --impl reference
 SEED = 20261018
 NUM_ORDERS = 30
 
@@ -137,6 +138,24 @@ class ClockSampler:
                 "samples": len(inside), "source": self.mode}
 
 
+def ncu_traffic(envs):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the timed kernel, from the committed ncu capture —
+    only if that capture was taken on THIS binary: profiles/ncu_traffic.json stores the SHA-256 of the kernel's SASS
+    beside the figure (tools/sass_hash.py), and the running library's kernel is hashed the same way.  Otherwise null."""
+    try:
+        sys.path.insert(0, os.path.join(REPO, "tools"))
+        from sass_hash import sass_sha256
+
+        with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as f:
+            rec = json.load(f)["fjsp_step_kernel<1,false>"]
+        h, _ = sass_sha256()
+        if h and h == rec["sass_sha256"] and int(rec["envs"]) == int(envs):
+            return float(rec["dram_bytes_per_launch"]), rec.get("source")
+    except Exception:
+        pass
+    return None, None
+
+
 def measured_peak():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     try:
@@ -163,15 +182,19 @@ def cpu_port_rate(sample_envs, steps_per_call, calls, threads, warm_calls=1):
     return env_steps * 8 / dt, dt, env_steps
 
 
+def cpu_sample_text(envs, inner, calls, threads, dt=None):
+    return ("%d envs x %d consecutive env steps per call x %d calls, env-major%s (bounded sample of the 2^20-env workload: Philox "
+            "orders/actions, autoreset), C port of the reference (oracle/fjsp_oracle.c), %d pthreads"
+            % (envs, inner, calls, "" if dt is None else " (%.1f s)" % dt, threads))
+
+
 def cpu_baseline_block(target_seconds=12.0):
     threads = os.cpu_count() or 1
-    sample_envs = 8192
-    rate, dt, _ = cpu_port_rate(sample_envs, 200, 1, threads, warm_calls=1)  # calibrate
-    steps = max(200, min(200000, int(target_seconds * rate / 8 / sample_envs)))
-    rate, dt, env_steps = cpu_port_rate(sample_envs, steps, 1, threads, warm_calls=0)
+    rate, dt, _ = cpu_port_rate(SAMPLE_ENVS, SAMPLE_INNER, 2, threads, warm_calls=1)  # calibrate
+    calls = max(3, min(20000, int(target_seconds * rate / 8 / SAMPLE_ENVS / SAMPLE_INNER)))
+    rate, dt, env_steps = cpu_port_rate(SAMPLE_ENVS, SAMPLE_INNER, calls, threads, warm_calls=0)
     return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d envs x %d consecutive steps each, env-major (%.1f s), same workload (Philox orders/actions, "
-                      "autoreset), C port of the reference (oracle/fjsp_oracle.c), %d pthreads" % (sample_envs, steps, dt, threads)}
+            "sample": cpu_sample_text(SAMPLE_ENVS, SAMPLE_INNER, calls, threads, dt)}
 
 
 def run_reference(args):
@@ -184,7 +207,7 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     # one reference "step" = INNER consecutive steps of each of sample_envs envs, env-major, which is the CPU's best
     # mode (an env's 82 KB object graph stays in cache); agent-steps are counted the same way on both arms.
-    sample_envs, inner = 4096, 64
+    sample_envs, inner = SAMPLE_ENVS, SAMPLE_INNER  # the same sample the GPU arm's cpu_baseline block times
     from oracle.fjsp_oracle import OracleBatch
 
     b = OracleBatch(sample_envs, SEED, NUM_ORDERS)
@@ -195,8 +218,7 @@ def run_reference(args):
         b.rollout(inner, nthreads=threads)
     dt = time.perf_counter() - t0
     value = sample_envs * inner * 8 * args.steps / dt
-    sample = ("per step: %d envs x %d consecutive env steps (bounded sample of the 2^20-env workload, env-major), "
-              "C port oracle/fjsp_oracle.c, %d pthreads" % (sample_envs, inner, threads))
+    sample = "per step: " + cpu_sample_text(sample_envs, inner, 1, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -410,41 +432,73 @@ def run_ours(args):
         scaled["rollout32_agent_steps_per_s"] = n4 * d4["agents"] * 32 / (e0.elapsed_time(e1) * 1e-3)  # K-steps-per-launch kernel
         del e4, a4
 
+    # ---- configs[3] as written: 2^20 envs in TOTAL, sharded over the N GPUs (strong scaling).  At N = 8 a rank's share
+    #      (131,072 envs = 64 MiB of state) is L2-resident, so this is NOT an HBM-roofline figure; the headline keeps 2^20 per GPU.
+    strong = None
+    if not args.no_extras:
+        total = 1 << 20
+        es = total // world
+        if world == 1:
+            strong = {"total_envs": total, "envs_per_gpu": es, "ms_per_step": ms_per_step, "agent_steps_per_s": value,
+                      "note": "N = 1: identical to the headline run"}
+        else:
+            sv = BatchedFJSPEnv(es, device=dev, first_env=rank * es, seed=SEED, num_orders=NUM_ORDERS, autoreset=True)
+            sv.reset()
+            sa = [sv.random_actions(t, out=torch.empty((es, 8), dtype=torch.uint8, device=dev)) for t in range(32)]
+            for t in range(10):
+                sv.step(sa[t % 32])
+            barrier()
+            ev0.record()
+            for t in range(200):
+                sv.step(sa[t % 32])
+            ev1.record()
+            barrier()
+            sms = max_over_ranks(ev0.elapsed_time(ev1)) / 200
+            strong = {"total_envs": total, "envs_per_gpu": es, "ms_per_step": sms, "agent_steps_per_s": total * 8 / (sms * 1e-3),
+                      "state_mib_per_gpu": es * 512 / 2 ** 20,
+                      "note": "strong scaling of configs[3]; a rank's state fits the 126 MB L2 from N = 8 on (L2-resident, not "
+                              "an HBM figure)"}
+            del sv, sa
+
     # ---- A2C frames/s (second half of BASELINE.json's metric; configs[2]): 4096 envs per GPU, rollout 32, fp32 GEMMs,
     #      CUDA-graph rollout, ONE flat NCCL all-reduce of the gradients per update when N > 1.  All ranks take part.
     a2c = None
     if not args.no_extras:
         from multi_agent_rl_for_fjsp_b200.a2c_batched import BatchedA2C
 
-        ea = BatchedFJSPEnv(4096, device=dev, first_env=rank * 4096, seed=SEED + 1, num_orders=25, autoreset=True)
-        tr = BatchedA2C(ea, rollout_len=32, seed=1)
-        tr.train(3)
-        barrier()
-        fps, secs = tr.train(20)
-        secs = max_over_ranks(secs)
-        a2c = {"metric": "a2c_frames_per_sec", "value": world * 4096 * 32 * 20 / secs, "unit": "frames/s",
-               "envs_per_gpu": 4096, "rollout_len": 32, "updates": 20, "ms_per_update": secs / 20 * 1e3,
-               "params": tr.net.num_parameters(), "gemm_precision": "fp32", "cuda_graph_rollout": True,
-               "gradient_allreduce": "nccl, one flat 2.62 MB bucket" if world > 1 else "none (1 GPU)",
-               "note": "1 frame = 1 env step consumed by training (rollout + update); reference CPU: 17-33 frames/s (BASELINE.md)"}
-        del tr, ea
-        # same run with TF32 tensor-core GEMMs (fp32 storage and accumulation), reported separately, never as the headline
-        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = True
-        try:
-            eb = BatchedFJSPEnv(4096, device=dev, first_env=rank * 4096, seed=SEED + 1, num_orders=25, autoreset=True)
-            tb = BatchedA2C(eb, rollout_len=32, seed=1)
-            tb.train(3)
+        def a2c_run(**kw):
+            e = BatchedFJSPEnv(4096, device=dev, first_env=rank * 4096, seed=SEED + 1, num_orders=25, autoreset=True)
+            t = BatchedA2C(e, rollout_len=32, seed=1, **kw)
+            t.train(3)
             barrier()
-            _, secs_tf = tb.train(20)
-            secs_tf = max_over_ranks(secs_tf)
-            a2c["tf32_variant_frames_per_sec"] = world * 4096 * 32 * 20 / secs_tf
-            del tb, eb
+            _, secs = t.train(20)
+            secs = max_over_ranks(secs)
+            n = t.net.num_parameters()
+            del t, e
+            return world * 4096 * 32 * 20 / secs, secs, n
+
+        fps, secs, nparams = a2c_run()
+        a2c = {"metric": "a2c_frames_per_sec", "value": fps, "unit": "frames/s",
+               "envs_per_gpu": 4096, "rollout_len": 32, "updates": 20, "ms_per_update": secs / 20 * 1e3,
+               "params": nparams, "impl": "umma: grouped tcgen05 GEMMs (TMEM accumulators), analytic loss gradients, rollout "
+                                           "activations reused by the update, CUDA-graph rollout and update",
+               "gemm_precision": "3xTF32 (fp32 operands split into two TF32 terms, three products, fp32 accumulate: fp32-level)",
+               "cuda_graph_rollout": True,
+               "gradient_allreduce": "nccl, one flat 2.62 MB buffer" if world > 1 else "none (1 GPU)",
+               "note": "1 frame = 1 env step consumed by training (rollout + update); reference CPU: 17-33 frames/s (BASELINE.md)"}
+        # the same run with single-pass TF32 GEMMs, and with the torch / cuBLAS fp32 statement of the trainer (autograd):
+        # reported beside the headline, never instead of it
+        a2c["tf32_single_pass_frames_per_sec"] = a2c_run(gemm_passes=1)[0]
+        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            a2c["torch_cublas_fp32_frames_per_sec"] = a2c_run(impl="torch")[0]
         finally:
             torch.backends.cuda.matmul.allow_tf32 = prev_tf32
 
     if rank == 0:
         peak, peak_src = measured_peak()
+        traffic, traffic_src = ncu_traffic(E)
         achieved = E * BYTES_PER_ENV_STEP / (ms_per_step * 1e-3) / 1e9  # GB/s per GPU
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -455,7 +509,7 @@ def run_ours(args):
                        "l2": "no flush: each step streams the 512 MiB state and a fresh 8 MiB action buffer (> 126 MB L2)",
                        "action_buffers": nbuf},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": args.ncu_traffic_bytes if E == (1 << 20) else None, "peak_source": peak_src, "kernel": "fjsp_step_kernel",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "fjsp_step_kernel<1,false>",
                          "algorithmic_bytes_per_launch": E * BYTES_PER_ENV_STEP},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 8, "d2h_bytes_per_step": E * wire_row,
                     "steps": Ke, "ms_per_step": e2e_s / Ke * 1e3,
@@ -476,6 +530,8 @@ def run_ours(args):
             line["extra"] = small
         if scaled:
             line["scaled_shop"] = scaled
+        if strong:
+            line["strong_scaling"] = strong
         if a2c:
             line["a2c"] = a2c
         print(json.dumps(line))
@@ -495,8 +551,6 @@ def main():
     ap.add_argument("--max-action-buffers", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--ncu-traffic-bytes", type=float, default=NCU_TRAFFIC_BYTES_2P20,
-                    help="dram bytes read+written per launch of fjsp_step_kernel from the committed ncu capture")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -52,6 +52,22 @@ extern "C" {
 #define FJSP_MASK_DIM_K(k) ((3 + 26 * (k) + 31) / 32 * 32)
 #define FJSP_STATE_WORDS_K(k) (64 + 64 * (k) + 20 * ((k) - 1))  /* 128 words for K = 1, 380 for K = 4 */
 
+/* ---- long order streams (BASELINE configs[4]; FjspConfig.long_streams = 1): a second packed layout for episodes with more
+ * than FJSP_MAX_ORDERS orders and / or more than 240 steps, and for order ARRIVALS during the episode.  The reference
+ * accepts any num_orders (FJSPSimulation.py:315-318) and max_episode_steps (:223); this layout takes up to
+ * FJSP_LONG_MAX_ORDERS orders and FJSP_LONG_MAX_STEPS steps.  Orders live in a ring of FJSP_LONG_RING slots: an order
+ * enters when the pickup station pops it and its slot is reused FJSP_LONG_RING orders later, by which time it must be
+ * complete (otherwise FJSP_FAULT_ORDER_RING: more orders open at once than the ring holds).  With long_streams = 0 and at
+ * most 32 orders nothing changes: the compact layout above is used, bit for bit.
+ * Arrivals (builder-defined extension; the reference creates all orders at reset): with arrival_prob_q16 > 0 one more
+ * order arrives per step with probability arrival_prob_q16 / 65536 — Philox4x32-10(key = seed, counter = (global env,
+ * episode, step, 5)), low 16 bits < arrival_prob_q16 — until arrival_max_orders exist; order i always has the attributes of
+ * index i of the order stream.  An episode then terminates only when all arrival_max_orders orders are complete. */
+#define FJSP_LONG_RING 64
+#define FJSP_LONG_MAX_ORDERS 4095
+#define FJSP_LONG_MAX_STEPS 65000
+#define FJSP_STATE_WORDS_LONG_K(k) (192 + 64 * (k) + 24 * ((k) - 1))  /* 256 words = 1 KB for K = 1 */
+
 /* ---- wire rows: the compact form in which a step's results cross PCIe on the host-buffer path (fjsp_step_host) and
  * which fjsp_step_wire / fjsp_wire_decode expose.  Everything a step returns is a small integer, so one env's results
  * are bit-fields in FJSP_WIRE_WORDS_K(K) u32 — 32 bytes for K = 1, against 220 bytes of float32 / int8 tensors:
@@ -81,6 +97,9 @@ extern "C" {
 #define FJSP_FAULT_PKG_RESTART_WITH_WAITERS 1 /* reference raises ValueError out of env.run (SURVEY R-PKG-cap-b) */
 #define FJSP_FAULT_POOL_EXHAUSTED 2           /* >64 trays in transit: impossible when max_episode_steps <= 240 */
 #define FJSP_FAULT_BAD_ORDER 3                /* an explicit order record outside n 1..9 / type 1..3 / colour 1..3 (set at reset) */
+#define FJSP_FAULT_PAST_END 4                 /* stepped after the truncation step without a reset: the env is inert (the
+                                                 reference would simulate on; the packed counters are not sized for it) */
+#define FJSP_FAULT_ORDER_RING 5               /* long layout: more than FJSP_LONG_RING orders open at once */
 
 /* Mirrors constants.py:5-32 (LOCATION_POSITIONS, PROCESSING_TIMES, CONFIG). */
 typedef struct FjspConfig {
@@ -96,6 +115,9 @@ typedef struct FjspConfig {
     int32_t tray_capacity;                 /* must be 5 */
     int32_t num_trays;                     /* constants.py:21; min(num_trays,1000) reach the pickup station (FJSPSimulation.py:96) */
     int32_t num_cells;                     /* 1 = the reference shop; 2..4 = scaled shop (see above) */
+    int32_t long_streams;                  /* 0 = compact layout (<= 32 orders, <= 240 steps); 1 = long order streams (see above) */
+    int32_t arrival_prob_q16;              /* long_streams only: P(one order arrives in a step) * 65536; 0 = no arrivals */
+    int32_t arrival_max_orders;            /* long_streams only: orders stop arriving once this many exist */
 } FjspConfig;
 
 /* One order as the reference generates it (FJSPSimulation.py:101-131): all products of an order
@@ -162,10 +184,11 @@ void* fjsp_state_ptr(FjspHandle* h);            /* device pointer of the packed 
 
 /* FJSPParallelEnv.reset (FJSPParallelEnvWrapper.py:43-54) -> FJSPSimulation.reset (:286-323).
  *   env_mask  : device u8[N] (non-zero = reset that env) or NULL = all
- *   orders    : device FjspOrderRec[N][FJSP_MAX_ORDERS] explicit order tables, or NULL = draw
+ *   orders    : device FjspOrderRec[N][FJSP_MAX_ORDERS] explicit order tables (long layout: [N][num_orders], copied into
+ *               the handle), or NULL = draw
  *               n~U{1..9}, type~U{1..3}, colour~U{1..3} from Philox4x32-10(key=seed,
  *               counter=(global env, episode, order, 0)) — replayable on the host
- *   num_orders: 0..32 (reference default 30)
+ *   num_orders: 0..32 (reference default 30); long layout: 0..FJSP_LONG_MAX_ORDERS
  *   obs/masks : device float[N][38] / int8[N][32] initial observations (may be NULL)            */
 int fjsp_reset(FjspHandle* h, const uint8_t* env_mask, uint64_t seed, const FjspOrderRec* orders,
                int num_orders, float* obs, int8_t* masks, void* stream);
@@ -223,6 +246,14 @@ int fjsp_export_state(FjspHandle* h, int64_t env, FjspCanonState* out);
 int fjsp_export_state_cell(FjspHandle* h, int64_t env, int cell, FjspCanonState* out);
 /* Raw packed words of one env (FJSP_STATE_WORDS_K(K) x u32; 128 for K = 1) copied to the host (synchronises). */
 int fjsp_export_packed(FjspHandle* h, int64_t env, uint32_t* out_words);
+/* Per-order record of orders [first, first + count) of one env, decoded on the host (synchronises):
+ * out[i] = { packaged_mask, processed_mask, is_complete, completion_step (or -1) }.  Works for both layouts; in the long
+ * layout orders that have left the ring are reported as complete with every bit set and completion_step -1 (a slot is
+ * only reused once its order is complete), orders not yet popped as zeros.  In the long layout FjspCanonState's
+ * per-order arrays describe the 32 most recently popped orders (order_base = max(0, next_order - 32) is returned
+ * here through *order_base when it is not NULL) and tray entries are FJSP_TRAY_ENTRY_LONG. */
+int fjsp_export_orders(FjspHandle* h, int64_t env, int first, int count, int32_t* out4, int32_t* order_base);
+#define FJSP_TRAY_ENTRY_LONG(id, order, first, count) ((int32_t)((id) | ((order) << 12) | ((first) << 24) | ((count) << 28)))
 
 /* Snapshot / restore of the whole packed state (num_tiles * 32 KB, see fjsp_state_total_bytes) to / from a
  * caller-owned DEVICE buffer: env checkpointing, and bit-for-bit comparison of two handles. */

@@ -21,14 +21,16 @@ HEADER = os.path.join(_REPO, "include", "fjsp_b200.h")
 NUM_AGENTS, OBS_DIM, MASK_DIM, FLAG_DIM, INFO_DIM, MAX_ORDERS = 8, 38, 32, 4, 4, 32
 STATE_WORDS, TILE_ENVS = 128, 64
 MAX_CELLS = 4
+LONG_RING, LONG_MAX_ORDERS, LONG_MAX_STEPS = 64, 4095, 65000
 ABI_VERSION = 3
 
 
-def dims(cells: int = 1) -> dict:
+def dims(cells: int = 1, long_streams: bool = False) -> dict:
     """Row widths of a K-cell shop (include/fjsp_b200.h FJSP_*_K); K = 1 is the reference shop (8 / 38 / 32 / 128)."""
     agents = 1 + 7 * cells
     return {"agents": agents, "act": (agents + 7) // 8 * 8, "obs": 7 + 31 * cells, "mask": (3 + 26 * cells + 31) // 32 * 32,
-            "mask_used": 3 + 26 * cells, "state_words": 64 + 64 * cells + 20 * (cells - 1),
+            "mask_used": 3 + 26 * cells,
+            "state_words": (192 + 64 * cells + 24 * (cells - 1)) if long_streams else (64 + 64 * cells + 20 * (cells - 1)),
             "wire_words": (2 + 5 * cells + 1) // 2 * 2}
 
 CANON_MAXQ, CANON_PS_READY, CANON_MAXPQ = 64, 256, 256
@@ -47,6 +49,7 @@ class FjspConfig(C.Structure):
         ("step_size", C.c_int32), ("agv_speed", C.c_int32), ("max_episode_steps", C.c_int32),
         ("storage_capacity", C.c_int32), ("pack_capacity", C.c_int32),
         ("tray_capacity", C.c_int32), ("num_trays", C.c_int32), ("num_cells", C.c_int32),
+        ("long_streams", C.c_int32), ("arrival_prob_q16", C.c_int32), ("arrival_max_orders", C.c_int32),
     ]
 
 
@@ -75,7 +78,7 @@ EXPORTS = [
     "fjsp_num_cells", "fjsp_step_wire", "fjsp_step_host_wire", "fjsp_wire_decode", "fjsp_wire_row_bytes", "fjsp_set_decode_threads",
     "fjsp_state_total_bytes", "fjsp_state_save", "fjsp_state_load",
     "fjsp_a2c_sample", "fjsp_a2c_counter_add", "fjsp_a2c_gae", "fjsp_cells_pack_actions", "fjsp_cells_unpack_views",
-    "fjsp_a2c_gemm", "fjsp_a2c_loss_grad",
+    "fjsp_a2c_gemm", "fjsp_a2c_loss_grad", "fjsp_export_orders",
 ]
 
 
@@ -145,6 +148,7 @@ def lib() -> C.CDLL:
     L.fjsp_export_state.argtypes = [vp, i64, vp]
     L.fjsp_export_state_cell.argtypes = [vp, i64, C.c_int, vp]
     L.fjsp_export_packed.argtypes = [vp, i64, vp]
+    L.fjsp_export_orders.argtypes = [vp, i64, C.c_int, C.c_int, vp, vp]
     L.fjsp_num_cells.restype, L.fjsp_num_cells.argtypes = C.c_int, [vp]
     L.fjsp_set_decode_threads.argtypes = [vp, C.c_int]
     L.fjsp_step_host_wire.argtypes = [vp, vp, vp, C.c_int, vp]
@@ -175,7 +179,8 @@ def config_from_dict(d: dict | None) -> FjspConfig:
     if not d:
         return cfg
     for k in ("grid_rows", "grid_cols", "step_size", "agv_speed", "max_episode_steps", "storage_capacity",
-              "pack_capacity", "tray_capacity", "num_trays", "proc_small", "proc_big", "proc_pack", "num_cells"):
+              "pack_capacity", "tray_capacity", "num_trays", "proc_small", "proc_big", "proc_pack", "num_cells", "long_streams",
+              "arrival_prob_q16", "arrival_max_orders"):
         if k in d:
             setattr(cfg, k, int(d[k]))
     pt = d.get("processing_times") or {}

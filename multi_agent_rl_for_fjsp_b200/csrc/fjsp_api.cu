@@ -23,6 +23,9 @@ struct FjspHandle {
     Params P;
     int device;
     int cells;               // K: 1 = the reference shop, 2..4 = scaled shop
+    bool long_streams;       // long order streams: the second packed layout (fjsp_core.h)
+    FjspOrderRec* d_otab;    // long layout: the handle's copy of the explicit order tables [num_envs][otab_stride], or null
+    int otab_stride;
     int act, obs, mask;      // row widths of the I/O tensors (FJSP_*_DIM_K)
     size_t tile_bytes;       // 64 envs x FJSP_STATE_WORDS_K words
     int64_t num_envs, first_env, num_tiles;
@@ -82,51 +85,58 @@ struct DeviceGuard {
         case 3: { constexpr int K = 3; __VA_ARGS__; } break;   \
         default: { constexpr int K = 4; __VA_ARGS__; } break;  \
     }
+// ... and on the layout (compact / long order streams)
+#define DISPATCH_KL(h, ...)                                                  \
+    if ((h)->long_streams) { constexpr bool LONG = true; DISPATCH_K((h)->cells, __VA_ARGS__) } \
+    else { constexpr bool LONG = false; DISPATCH_K((h)->cells, __VA_ARGS__) }
 
-template <int K>
+template <int K, bool LONG>
 static cudaError_t set_smem_attrs() {
-    cudaError_t e = cudaFuncSetAttribute(fjsp_step_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::STEP_SMEM_BYTES);
+    using G = Geo<K, LONG>;
+    cudaError_t e = cudaFuncSetAttribute(fjsp_step_kernel<K, false, LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::STEP_SMEM_BYTES);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(fjsp_step_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::STEP_WIRE_SMEM_BYTES);
+        e = cudaFuncSetAttribute(fjsp_step_kernel<K, true, LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::STEP_WIRE_SMEM_BYTES);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(fjsp_rollout_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::ROLLOUT_SMEM_BYTES);
+        e = cudaFuncSetAttribute(fjsp_rollout_kernel<K, LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::ROLLOUT_SMEM_BYTES);
     if constexpr (K >= 2) {
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(fjsp_step_cells_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::CELLS_SMEM_BYTES);
+            e = cudaFuncSetAttribute(fjsp_step_cells_kernel<K, false, LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::CELLS_SMEM_BYTES);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(fjsp_step_cells_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::CELLS_WIRE_SMEM_BYTES);
+            e = cudaFuncSetAttribute(fjsp_step_cells_kernel<K, true, LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::CELLS_WIRE_SMEM_BYTES);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(fjsp_rollout_cells_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<K>::ROLLOUT_CELLS_SMEM_BYTES);
+            e = cudaFuncSetAttribute(fjsp_rollout_cells_kernel<K, LONG>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::ROLLOUT_CELLS_SMEM_BYTES);
     }
     return e;
 }
 
 // One lockstep step of `tiles` tiles starting at A.tile_begin.  K = 1: one thread per env.  K >= 2: one thread per
 // (env, cell) — unless FJSP_STEP_PER_ENV is set, which keeps the thread-per-env kernel for A/B measurements.
-template <int K, bool WIRE>
+template <int K, bool WIRE, bool LONG>
 static void launch_step(const FjspHandle* h, const StepArgs& A, unsigned tiles, cudaStream_t st) {
+    using G = Geo<K, LONG>;
     static const bool per_env = getenv("FJSP_STEP_PER_ENV") != nullptr;
     if constexpr (K >= 2) {
         if (!per_env) {
-            fjsp_step_cells_kernel<K, WIRE><<<tiles, TILE * K, WIRE ? Geo<K>::CELLS_WIRE_SMEM_BYTES : Geo<K>::CELLS_SMEM_BYTES, st>>>(h->P, A);
+            fjsp_step_cells_kernel<K, WIRE, LONG><<<tiles, TILE * K, WIRE ? G::CELLS_WIRE_SMEM_BYTES : G::CELLS_SMEM_BYTES, st>>>(h->P, A);
             return;
         }
     }
-    fjsp_step_kernel<K, WIRE><<<tiles, TILE, WIRE ? Geo<K>::STEP_WIRE_SMEM_BYTES : Geo<K>::STEP_SMEM_BYTES, st>>>(h->P, A);
+    fjsp_step_kernel<K, WIRE, LONG><<<tiles, TILE, WIRE ? G::STEP_WIRE_SMEM_BYTES : G::STEP_SMEM_BYTES, st>>>(h->P, A);
 }
 
-template <int K>
+template <int K, bool LONG>
 static void launch_rollout(const FjspHandle* h, int steps, uint64_t seed, uint64_t t0, unsigned long long* stats, cudaStream_t st) {
+    using G = Geo<K, LONG>;
     static const bool per_env = getenv("FJSP_STEP_PER_ENV") != nullptr;
     if constexpr (K >= 2) {
         if (!per_env) {
-            fjsp_rollout_cells_kernel<K><<<(unsigned)h->num_tiles, TILE * K, Geo<K>::ROLLOUT_CELLS_SMEM_BYTES, st>>>(
+            fjsp_rollout_cells_kernel<K, LONG><<<(unsigned)h->num_tiles, TILE * K, G::ROLLOUT_CELLS_SMEM_BYTES, st>>>(
                 h->P, h->state, h->num_envs, h->first_env, seed, t0, steps, h->num_orders, stats);
             return;
         }
     }
-    fjsp_rollout_kernel<K><<<(unsigned)h->num_tiles, TILE, Geo<K>::ROLLOUT_SMEM_BYTES, st>>>(h->P, h->state, h->num_envs, h->first_env, seed,
-                                                                                            t0, steps, h->num_orders, stats);
+    fjsp_rollout_kernel<K, LONG><<<(unsigned)h->num_tiles, TILE, G::ROLLOUT_SMEM_BYTES, st>>>(h->P, h->state, h->num_envs, h->first_env, seed,
+                                                                                           t0, steps, h->num_orders, stats);
 }
 
 // ---- tcgen05 grouped GEMM (fjsp_umma.cuh): the actor / critic layers of the batched A2C trainer ----
@@ -180,8 +190,9 @@ int fjsp_create(const FjspConfig* cfg, int64_t num_envs, int64_t first_env, int 
     h->cfg = c, h->P = P, h->device = device;
     h->num_envs = num_envs, h->first_env = first_env;
     h->cells = c.num_cells;
+    h->long_streams = c.long_streams != 0;
     h->act = FJSP_ACT_DIM_K(h->cells), h->obs = FJSP_OBS_DIM_K(h->cells), h->mask = FJSP_MASK_DIM_K(h->cells);
-    h->tile_bytes = (size_t)FJSP_STATE_WORDS_K(h->cells) * TILE * sizeof(u32);
+    h->tile_bytes = (size_t)(h->long_streams ? FJSP_STATE_WORDS_LONG_K(h->cells) : FJSP_STATE_WORDS_K(h->cells)) * TILE * sizeof(u32);
     h->wire_words = FJSP_WIRE_WORDS_K(h->cells);
     // measured on B200 (K = 4, 2^19 envs): distances of 32..148 tiles all give +13..15 %, 296 and more lose; SMs / 2 it is.
     // FJSP_PREFETCH_TILES overrides (0 switches the prefetch off)
@@ -198,15 +209,15 @@ int fjsp_create(const FjspConfig* cfg, int64_t num_envs, int64_t first_env, int 
         delete h;
         return cuda_fail(e, "cudaMalloc(state)");
     }
-    DISPATCH_K(h->cells, e = set_smem_attrs<K>())
+    DISPATCH_KL(h, e = (set_smem_attrs<K, LONG>()))
     if (e != cudaSuccess) {
         cudaFree(h->state);
         delete h;
         return cuda_fail(e, "cudaFuncSetAttribute (is this an sm_100a device?)");
     }
     // all envs start as freshly reset, empty shops (num_orders = 0) until fjsp_reset is called
-    DISPATCH_K(h->cells, fjsp_reset_kernel<K><<<(unsigned)h->num_tiles, TILE>>>(h->P, h->state, nullptr, nullptr, 0, 0ull, h->num_envs,
-                                                                                h->first_env, nullptr, nullptr))
+    DISPATCH_KL(h, (fjsp_reset_kernel<K, LONG><<<(unsigned)h->num_tiles, TILE>>>(h->P, h->state, nullptr, nullptr, 0, 0, 0ull, h->num_envs,
+                                                                                 h->first_env, nullptr, nullptr)))
     h->launches++;
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -222,6 +233,7 @@ int fjsp_destroy(FjspHandle* h) {
     if (!h) return 0;
     DeviceGuard g(h->device);
     cudaFree(h->state);
+    cudaFree(h->d_otab);
     free_staging(h);
     delete h;
     return 0;
@@ -229,21 +241,58 @@ int fjsp_destroy(FjspHandle* h) {
 
 int64_t fjsp_num_envs(const FjspHandle* h) { return h ? h->num_envs : 0; }
 int fjsp_num_cells(const FjspHandle* h) { return h ? h->cells : 0; }
-size_t fjsp_state_bytes(const FjspHandle* h) { return h ? (size_t)FJSP_STATE_WORDS_K(h->cells) * 4 : 0; }
+static int state_words(const FjspHandle* h) { return h->long_streams ? FJSP_STATE_WORDS_LONG_K(h->cells) : FJSP_STATE_WORDS_K(h->cells); }
+size_t fjsp_state_bytes(const FjspHandle* h) { return h ? (size_t)state_words(h) * 4 : 0; }
 void* fjsp_state_ptr(FjspHandle* h) { return h ? h->state : nullptr; }
 int64_t fjsp_launch_count(const FjspHandle* h) { return h ? h->launches : 0; }
 
 int fjsp_reset(FjspHandle* h, const uint8_t* env_mask, uint64_t seed, const FjspOrderRec* orders, int num_orders, float* obs,
                int8_t* masks, void* stream) {
     if (!h) return fail("handle is NULL");
-    if (num_orders < 0 || num_orders > FJSP_MAX_ORDERS) return fail("num_orders must be in 0..32");
+    if (!h->long_streams && (num_orders < 0 || num_orders > FJSP_MAX_ORDERS))
+        return fail("num_orders must be in 0..32 in the compact layout (create the handle with FjspConfig.long_streams = 1 for more)");
+    if (h->long_streams && (num_orders < 0 || num_orders > FJSP_LONG_MAX_ORDERS)) return fail("num_orders must be in 0..4095");
+    if (h->long_streams && h->cfg.arrival_prob_q16 > 0 && num_orders > h->cfg.arrival_max_orders)
+        return fail("num_orders (orders present at reset) must not exceed arrival_max_orders");
     if ((obs == nullptr) != (masks == nullptr)) return fail("obs and masks must both be given or both be NULL");
     DeviceGuard g(h->device);
+    int stride = FJSP_MAX_ORDERS;
+    if (h->long_streams) {
+        // The ring fills as orders are popped, so explicit tables must outlive this call: the handle keeps a device copy
+        // ([num_envs][num_orders]).  A masked reset may only replace rows of a table of the same width.
+        stride = num_orders;
+        if (orders) {
+            if (env_mask && h->d_otab && h->otab_stride != num_orders) return fail("masked reset with explicit orders: num_orders must equal the installed table's");
+            if (!h->d_otab || h->otab_stride != num_orders) {
+                CK(cudaStreamSynchronize((cudaStream_t)stream));
+                cudaFree(h->d_otab);
+                h->d_otab = nullptr;
+                if (num_orders > 0) CK(cudaMalloc(&h->d_otab, (size_t)h->num_envs * num_orders * sizeof(FjspOrderRec)));
+                h->otab_stride = num_orders;
+            }
+            if (num_orders > 0) {
+                if (env_mask) {
+                    // rows of the envs that are not reset keep their tables: copy row by row under the mask on the device
+                    fjsp_copy_masked_rows_kernel<<<(unsigned)((h->num_envs * num_orders + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+                        h->d_otab, orders, env_mask, h->num_envs, num_orders);
+                } else {
+                    CK(cudaMemcpyAsync(h->d_otab, orders, (size_t)h->num_envs * num_orders * sizeof(FjspOrderRec), cudaMemcpyDeviceToDevice,
+                                       (cudaStream_t)stream));
+                }
+                orders = h->d_otab;
+            }
+        } else if (!env_mask) {
+            cudaFree(h->d_otab);   // back to the Philox order stream for every env
+            h->d_otab = nullptr, h->otab_stride = 0;
+        } else if (h->d_otab) {
+            return fail("masked reset to the Philox order stream while explicit order tables are installed is not supported");
+        }
+    }
     // the handle-wide seed / num_orders are what auto-reset and the rollout kernels use for EVERY env: a masked reset
     // (some envs only) must not change them under the envs it does not touch
     if (!env_mask) h->seed = seed, h->num_orders = num_orders;
-    DISPATCH_K(h->cells, fjsp_reset_kernel<K><<<(unsigned)h->num_tiles, TILE, 0, (cudaStream_t)stream>>>(
-                             h->P, h->state, env_mask, orders, num_orders, seed, h->num_envs, h->first_env, obs, masks))
+    DISPATCH_KL(h, (fjsp_reset_kernel<K, LONG><<<(unsigned)h->num_tiles, TILE, 0, (cudaStream_t)stream>>>(
+                        h->P, h->state, env_mask, orders, stride, num_orders, seed, h->num_envs, h->first_env, obs, masks)))
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -263,7 +312,8 @@ int fjsp_step(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, 
     A.results = results, A.infos = infos, A.num_envs = h->num_envs, A.first_env = h->first_env, A.seed = h->seed;
     A.num_orders = h->num_orders, A.autoreset = autoreset, A.tile_begin = 0, A.wire = nullptr;
     A.prefetch_tiles = h->prefetch_tiles, A.prefetch_tiles_env = h->prefetch_tiles_env;
-    DISPATCH_K(h->cells, launch_step<K, false>(h, A, (unsigned)h->num_tiles, (cudaStream_t)stream))
+    A.otab = h->d_otab, A.otab_stride = h->otab_stride;
+    DISPATCH_KL(h, (launch_step<K, false, LONG>(h, A, (unsigned)h->num_tiles, (cudaStream_t)stream)))
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -275,6 +325,7 @@ static StepArgs wire_args(FjspHandle* h, const uint8_t* actions, u32* wire, uint
     A.results = results, A.infos = infos, A.wire = wire, A.num_envs = h->num_envs, A.first_env = h->first_env, A.seed = h->seed;
     A.num_orders = h->num_orders, A.autoreset = autoreset, A.tile_begin = 0;
     A.prefetch_tiles = h->prefetch_tiles, A.prefetch_tiles_env = h->prefetch_tiles_env;
+    A.otab = h->d_otab, A.otab_stride = h->otab_stride;
     return A;
 }
 
@@ -286,7 +337,7 @@ int fjsp_step_wire(FjspHandle* h, const uint8_t* actions, uint32_t* wire, uint8_
         return fail("buffer alignment: actions/results 8 B, wire/infos 16 B");
     DeviceGuard g(h->device);
     const StepArgs A = wire_args(h, actions, wire, results, infos, autoreset);
-    DISPATCH_K(h->cells, launch_step<K, true>(h, A, (unsigned)h->num_tiles, (cudaStream_t)stream))
+    DISPATCH_KL(h, (launch_step<K, true, LONG>(h, A, (unsigned)h->num_tiles, (cudaStream_t)stream)))
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -407,7 +458,7 @@ static int step_host_impl(FjspHandle* h, const uint8_t* actions, u32* wire_out, 
         const size_t n = (size_t)(e1 - e0);
         CK(cudaMemcpyAsync(h->d_actions + e0 * na, actions + e0 * na, n * na, cudaMemcpyHostToDevice, st));
         A.tile_begin = t0;
-        DISPATCH_K(h->cells, launch_step<K, true>(h, A, (unsigned)(t1 - t0), st))
+        DISPATCH_KL(h, (launch_step<K, true, LONG>(h, A, (unsigned)(t1 - t0), st)))
         h->launches++;
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync((wire_out ? wire_out : h->h_wire) + e0 * ww, h->d_wire + e0 * ww, n * ww * sizeof(u32), cudaMemcpyDeviceToHost, st));
@@ -485,7 +536,8 @@ int fjsp_rollout_random(FjspHandle* h, int steps, uint64_t seed, uint64_t t0, ui
     if (!stats || (reinterpret_cast<uintptr_t>(stats) & 7)) return fail("stats must be an 8-byte aligned device pointer (8 x u64)");
     if (seed != h->seed) return fail("rollout seed must equal the seed of the last fjsp_reset (one Philox key per handle)");
     DeviceGuard g(h->device);
-    DISPATCH_K(h->cells, launch_rollout<K>(h, steps, seed, t0, reinterpret_cast<unsigned long long*>(stats), (cudaStream_t)stream))
+    if (h->d_otab) return fail("fjsp_rollout_random draws Philox orders at auto-reset: not available while explicit order tables are installed");
+    DISPATCH_KL(h, (launch_rollout<K, LONG>(h, steps, seed, t0, reinterpret_cast<unsigned long long*>(stats), (cudaStream_t)stream)))
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -514,7 +566,7 @@ int fjsp_export_packed(FjspHandle* h, int64_t env, uint32_t* out_words) {
     if (env < 0 || env >= h->num_envs) return fail("env index out of range");
     DeviceGuard g(h->device);
     CK(cudaDeviceSynchronize());
-    const int words = FJSP_STATE_WORDS_K(h->cells);
+    const int words = state_words(h);
     const u32* src = h->state + (env / TILE) * (int64_t)words * TILE + (env % TILE);
     // word w of this env sits TILE words after word w-1: a strided gather of `words` x 4 bytes
     CK(cudaMemcpy2D(out_words, sizeof(u32), src, TILE * sizeof(u32), sizeof(u32), (size_t)words, cudaMemcpyDeviceToHost));
@@ -524,9 +576,21 @@ int fjsp_export_packed(FjspHandle* h, int64_t env, uint32_t* out_words) {
 int fjsp_export_state_cell(FjspHandle* h, int64_t env, int cell, FjspCanonState* out) {
     if (!out) return fail("out is NULL");
     if (h && (cell < 0 || cell >= h->cells)) return fail("cell index out of range");
-    u32 words[FJSP_STATE_WORDS_K(FJSP_MAX_CELLS)];
+    u32 words[FJSP_STATE_WORDS_LONG_K(FJSP_MAX_CELLS)];
     if (int rc = fjsp_export_packed(h, env, words)) return rc;
-    export_canon(words, h->P, h->cells, cell, out);
+    export_canon(words, h->P, h->cells, h->long_streams, cell, out);
+    return 0;
+}
+
+int fjsp_export_orders(FjspHandle* h, int64_t env, int first, int count, int32_t* out4, int32_t* order_base) {
+    if (!out4 || count < 0) return fail("out4 is NULL or count < 0");
+    u32 words[FJSP_STATE_WORDS_LONG_K(FJSP_MAX_CELLS)];
+    if (int rc = fjsp_export_packed(h, env, words)) return rc;
+    export_orders(words, h->P, h->cells, h->long_streams, first, count, out4);
+    if (order_base) {
+        FjspCanonState c;
+        export_canon(words, h->P, h->cells, h->long_streams, 0, &c, order_base);
+    }
     return 0;
 }
 

@@ -43,6 +43,7 @@ struct Params {
     int32_t small_steps, big_steps, pack_steps;             // PROCESSING_TIMES / step_size
     int32_t max_episode_steps, storage_capacity, pack_capacity, trays_total, num_trays;
     int32_t step_size;
+    int32_t arrival_q16, arrival_max;                       // long order streams: P(arrival per step) * 65536, cap on num_orders
     float progress_tab[256];                                // float32((1/L)*100) (PackagingAgent.py:117)
 };
 
@@ -52,17 +53,34 @@ enum { TYPE_SMALL = 1, TYPE_MEDIUM = 2, TYPE_BIG = 3 };
 enum { COL_RED = 1, COL_BLUE = 2, COL_GREEN = 3 };
 
 // ---------------------------------------------------------------------------------------------
-// Word map of the packed state of a K-cell shop (K = 1: the reference shop, 128 words).
+// Word map of the packed state of a K-cell shop.  Two layouts share the code below:
+//
+// COMPACT (LONG = false; K = 1: the reference shop, 128 words = 512 B): at most 32 orders and 240 steps per episode.
 //   words 0..23      hot words of the pickup station (shared) and of cell 0
 //   words 24..31     order completion steps (u8 each)
-//   words 32..63     order words
+//   words 32..63     order words (the whole order table, generated at reset)
 //   words 64+64c ..  tray pool of cell c (64 records)                      -> words 24 .. 64+64K are "dynamic"
 //   words 64+64K ..  hot words of cells 1..K-1, 20 each (AGV, free bitmap x2, storage, 2 machines x 2, 4 stations x 3)
+//
+// LONG (long order streams, BASELINE configs[4]; K = 1: 256 words = 1 KB): up to 4095 orders and 65,000 steps per
+// episode, Philox order ARRIVALS.  Orders live in a RING of 64 slots (slot = order id mod 64): an order enters the ring
+// when the pickup station pops it (its attributes come from the Philox stream / the explicit table at that moment) and
+// its slot is reused 64 orders later, by which time it must be complete (else FJSP_FAULT_ORDER_RING).  Counters are
+// wider, trays lost to the reference's quirks give their pool slot back at once (their processed bits live in the ring).
+//   words 0..23      as above (three shared words re-packed, see load_hot)
+//   words 24..27     more shared hot words; 28..31 one more word per packaging station of cell 0 (current product)
+//   words 32..63     completion steps (u16 per ring slot)
+//   words 64..127    ring A: order words;  128..191  ring B: processed9 | first tray's allocation index 12 << 9
+//   words 192+64c .. tray pools                                            -> words 32 .. 192+64K are "dynamic"
+//   then             hot words of cells 1..K-1, 24 each
 // ---------------------------------------------------------------------------------------------
 enum {
-    W_CTRL = 0,     // step16 | num_orders6<<16 | fault2<<22 | completed_orders6<<24
-    W_PS = 1,       // total_packaged9 | next_order6<<9 | cur_order6<<15 (63=none) | prod_idx4<<21 | cur_tray_count3<<25
-    W_PSQ = 2,      // alloc_count8 | ready_count8<<8 | ready_order6<<16 | ready_idx4<<22 | dock_mask4<<26
+    W_CTRL = 0,     // compact: step16 | num_orders6<<16 | fault3<<22 | completed_orders6<<25
+                    // long   : step16 | fault3<<16 | cur_tray_count3<<19 | prod_idx4<<22 | ready_idx4<<26
+    W_PS = 1,       // compact: total_packaged9 | next_order6<<9 | cur_order6<<15 (63=none) | prod_idx4<<21 | cur_tray_count3<<25
+                    // long   : num_orders12 | completed_orders12<<12 | dock_mask4<<24
+    W_PSQ = 2,      // compact: alloc_count8 | ready_count8<<8 | ready_order6<<16 | ready_idx4<<22 | dock_mask4<<26
+                    // long   : next_order12 | cur_order13<<12 (0x1fff = none)
     W_AGV = 3,      // loc3 | moving1<<3 | target3<<4 | arrive16<<7 | carry7<<23 (slot+1, 0 = none)
     W_FREE_LO = 4,  // pool free bitmap, slots 0..31 (1 = free)
     W_FREE_HI = 5,  // slots 32..63
@@ -73,28 +91,57 @@ enum {
                     //   B: qhead6 | qtail6<<6 | rhead6<<12 | rtail6<<18 | rlen6<<24
     W_PACK = 12,    // 4 stations x 3 words (blue_1, blue_2, red, green)
                     //   A: qhead6 | qtail6<<6 | qrec6<<12 | fhead6<<18 | ftail6<<24
-                    //   B: frec6 | users5<<6 | busy1<<11 | waiters1<<12 | hascur1<<13 | curprod9<<14 | qcount8<<23
-                    //   C: completed8 | progL8<<8
-    W_CSTEP = 24,   // 32 x u8 completion step + 1 (0 = not complete), 4 per word
-    W_ORDER = 32,   // 32 x order word: n4 | type2<<4 | colour2<<6 | cut8<<8 | packaged9<<16
-    W_POOL = 64,    // 64 x tray record per cell: order5 | first4<<5 | count3<<9 | processed1<<12 | next6<<13 | stamp8<<19 | lost1<<27
-    W_TOTAL = 128,  // K = 1
+                    //   B: frec6 | users5<<6 | busy1<<11 | waiters1<<12 | hascur1<<13 | compact: cur_slot5<<14 | cur_idx4<<19 | qcount8<<23
+                    //                                                                  | long   : qcount8<<14
+                    //   C: compact: completed8 | progL8<<8          long: completed16 | progL8<<16
+                    //   D (long only): cur_order12 | cur_idx4<<12
+    W_LONG_PSQ = 24,   // long: ready_order12 | ready_count12<<12
+    W_LONG_CNT = 25,   // long: total_packaged16 | alloc_count12<<16
+    W_LONG_PACKD = 28, // long: word D of cell 0's four packaging stations
     CELL_HOT_WORDS = 20
 };
-static_assert(W_TOTAL == FJSP_STATE_WORDS, "state size");
+// tray record (both layouts): ring slot7 | first4<<7 | count3<<11 | processed1<<14 | next6<<15 | stamp8<<21 | lost1<<29
+// order word                : n4 | type2<<4 | colour2<<6 | cut8<<8 | packaged9<<16
 
-template <int K>
-struct Lay {
-    static constexpr int DYN_END = 64 + 64 * K;                     // hot | dynamic (24..DYN_END) | hot words of cells >= 1
-    static constexpr int TOTAL = FJSP_STATE_WORDS_K(K);
-    static constexpr int AGENTS = FJSP_AGENTS_K(K), ACT = FJSP_ACT_DIM_K(K), OBS = FJSP_OBS_DIM_K(K), MASK = FJSP_MASK_DIM_K(K);
+template <bool LONG>
+struct WM {
+    static constexpr int RING = LONG ? 64 : 32;                        // order slots (compact: the whole table)
+    static constexpr int W_DYN0 = LONG ? 32 : 24;                      // first dynamically indexed word
+    static constexpr int W_CSTEP = W_DYN0;                             // completion step + 1 per slot (0 = not complete): u8 / u16
+    static constexpr int W_ORDER = W_CSTEP + (LONG ? RING / 2 : RING / 4);   // 32 / 64
+    static constexpr int W_ORDER_B = W_ORDER + RING;                   // long only
+    static constexpr int W_POOL = W_ORDER + (LONG ? 2 : 1) * RING;     // 64 / 192
+    static constexpr int CELL_HOT = LONG ? 24 : 20;
+    static constexpr int NO_ORDER = LONG ? 0x1fff : 63;
 };
-// word index of hot word `which` (0 AGV, 1 FREE_LO, 2 FREE_HI, 3 STORAGE, 4..7 MACH, 8..19 PACK) of cell c
-FJSP_HD constexpr int cell_word(int K, int c, int which) {
-    return c == 0 ? (which < 3 ? W_AGV + which : which == 3 ? W_STORAGE : which < 8 ? W_MACH + (which - 4) : W_PACK + (which - 8))
-                  : 64 + 64 * K + CELL_HOT_WORDS * (c - 1) + which;
+static_assert(WM<false>::W_POOL + 64 == FJSP_STATE_WORDS, "compact state size");
+enum { W_CSTEP = WM<false>::W_CSTEP, W_ORDER = WM<false>::W_ORDER, W_POOL = WM<false>::W_POOL, W_TOTAL = 128 };  // compact names (host tools)
+
+template <int K, bool LONG = false>
+struct Lay {
+    static constexpr int DYN0 = WM<LONG>::W_DYN0;
+    static constexpr int DYN_END = WM<LONG>::W_POOL + 64 * K;       // hot | dynamic (DYN0..DYN_END) | hot words of cells >= 1
+    static constexpr int TOTAL = DYN_END + WM<LONG>::CELL_HOT * (K - 1);
+    static constexpr int AGENTS = FJSP_AGENTS_K(K), ACT = FJSP_ACT_DIM_K(K), OBS = FJSP_OBS_DIM_K(K), MASK = FJSP_MASK_DIM_K(K);
+    static_assert(LONG || TOTAL == FJSP_STATE_WORDS_K(K), "compact state size");
+    static_assert(!LONG || TOTAL == FJSP_STATE_WORDS_LONG_K(K), "long state size");
+};
+// word index of hot word `which` (0 AGV, 1 FREE_LO, 2 FREE_HI, 3 STORAGE, 4..7 MACH, 8..19 PACK A/B/C, long: 20..23 PACK D) of cell c
+template <int K, bool LONG>
+FJSP_HD constexpr int cell_word(int c, int which) {
+    return c == 0 ? (which < 3 ? W_AGV + which : which == 3 ? W_STORAGE : which < 8 ? W_MACH + (which - 4)
+                     : which < 20 ? W_PACK + (which - 8) : W_LONG_PACKD + (which - 20))
+                  : Lay<K, LONG>::DYN_END + WM<LONG>::CELL_HOT * (c - 1) + which;
 }
-FJSP_HD constexpr int pool_base(int c) { return W_POOL + 64 * c; }
+template <bool LONG>
+FJSP_HD constexpr int pool_base(int c) { return WM<LONG>::W_POOL + 64 * c; }
+template <bool LONG>
+FJSP_HD constexpr int oslot(int order) { return order & (WM<LONG>::RING - 1); }
+// the order id living in ring slot `slot`, given the pickup station's next_order (ids enter the ring consecutively)
+template <bool LONG>
+FJSP_HD int order_of_slot(int slot, int next_order) {
+    return LONG ? next_order - 1 - ((next_order - 1 - slot) & (WM<LONG>::RING - 1)) : slot;
+}
 
 // order word
 FJSP_HD int ord_n(u32 w) { return (int)(w & 15u); }
@@ -105,18 +152,20 @@ FJSP_HD u32 ord_packaged(u32 w) { return (w >> 16) & 0x1ffu; }
 FJSP_HD u32 make_order(int n, int type, int colour) { return (u32)n | ((u32)type << 4) | ((u32)colour << 6); }
 
 // tray record
-FJSP_HD int rec_order(u32 r) { return (int)(r & 31u); }
-FJSP_HD int rec_first(u32 r) { return (int)((r >> 5) & 15u); }
-FJSP_HD int rec_count(u32 r) { return (int)((r >> 9) & 7u); }
-FJSP_HD int rec_processed(u32 r) { return (int)((r >> 12) & 1u); }
-FJSP_HD int rec_next(u32 r) { return (int)((r >> 13) & 63u); }
-FJSP_HD int rec_stamp(u32 r) { return (int)((r >> 19) & 255u); }
-FJSP_HD int rec_lost(u32 r) { return (int)((r >> 27) & 1u); }
-FJSP_HD u32 make_rec(int order, int first, int count, int processed) {
-    return (u32)order | ((u32)first << 5) | ((u32)count << 9) | ((u32)processed << 12);
+FJSP_HD int rec_order(u32 r) { return (int)(r & 127u); }   // ring slot of the tray's order
+FJSP_HD int rec_first(u32 r) { return (int)((r >> 7) & 15u); }
+FJSP_HD int rec_count(u32 r) { return (int)((r >> 11) & 7u); }
+FJSP_HD int rec_processed(u32 r) { return (int)((r >> 14) & 1u); }
+FJSP_HD int rec_next(u32 r) { return (int)((r >> 15) & 63u); }
+FJSP_HD int rec_stamp(u32 r) { return (int)((r >> 21) & 255u); }
+FJSP_HD int rec_lost(u32 r) { return (int)((r >> 29) & 1u); }
+constexpr u32 REC_PROCESSED = 1u << 14, REC_LOST = 1u << 29;
+FJSP_HD u32 make_rec(int slot, int first, int count, int processed) {
+    return (u32)slot | ((u32)first << 7) | ((u32)count << 11) | ((u32)processed << 14);
 }
-FJSP_HD u32 rec_with_next(u32 r, int next) { return (r & ~(63u << 13)) | ((u32)next << 13); }
-FJSP_HD u32 rec_with_stamp(u32 r, int stamp) { return (r & ~(255u << 19)) | ((u32)(stamp & 255) << 19); }
+FJSP_HD u32 rec_with_next(u32 r, int next) { return (r & ~(63u << 15)) | ((u32)next << 15); }
+FJSP_HD u32 rec_with_stamp(u32 r, int stamp) { return (r & ~(255u << 21)) | ((u32)(stamp & 255) << 21); }
+FJSP_HD u32 rec_split_rest(u32 r, int first, int count) { return (r & ~((15u << 7) | (7u << 11))) | ((u32)first << 7) | ((u32)count << 11); }
 
 FJSP_HD int ctz32(u32 x) {
 #if defined(__CUDA_ARCH__)
@@ -145,11 +194,12 @@ struct Mach {
 };
 struct Pack {
     Fifo q, f;  // queued tray records, in-flight tray records (len = record count)
-    int users, busy, waiters, hascur, curprod, qcount, completed, progL;
+    int users, busy, waiters, hascur, qcount, completed, progL;
+    int cur_order, cur_idx;  // current_product (sticky): compact = ring slot (= order id), long = order id; product index
 };
 struct Hot {  // shared part
     int step, num_orders, fault, completed_orders;
-    int total_packaged, next_order, cur_order, prod_idx, cur_tray_count;
+    int total_packaged, next_order, cur_order, prod_idx, cur_tray_count;   // cur_order: -1 = none
     int alloc_count, ready_count, ready_order, ready_idx, dock_mask;
     u32 episode;
 };
@@ -163,80 +213,121 @@ struct HotCell {
 
 template <class S>
 FJSP_HD void load_hot(S& s, Hot& h) {
-    u32 w = s.ld_hot(W_CTRL);
-    h.step = (int)(w & 0xffffu), h.num_orders = (int)((w >> 16) & 63u), h.fault = (int)((w >> 22) & 3u);
-    h.completed_orders = (int)((w >> 24) & 63u);
-    w = s.ld_hot(W_PS);
-    h.total_packaged = (int)(w & 511u), h.next_order = (int)((w >> 9) & 63u), h.cur_order = (int)((w >> 15) & 63u);
-    h.prod_idx = (int)((w >> 21) & 15u), h.cur_tray_count = (int)((w >> 25) & 7u);
-    w = s.ld_hot(W_PSQ);
-    h.alloc_count = (int)(w & 255u), h.ready_count = (int)((w >> 8) & 255u), h.ready_order = (int)((w >> 16) & 63u);
-    h.ready_idx = (int)((w >> 22) & 15u), h.dock_mask = (int)((w >> 26) & 15u);
+    if (S::LONG) {
+        u32 w = s.ld_hot(W_CTRL);
+        h.step = (int)(w & 0xffffu), h.fault = (int)((w >> 16) & 7u), h.cur_tray_count = (int)((w >> 19) & 7u);
+        h.prod_idx = (int)((w >> 22) & 15u), h.ready_idx = (int)((w >> 26) & 15u);
+        w = s.ld_hot(W_PS);
+        h.num_orders = (int)(w & 0xfffu), h.completed_orders = (int)((w >> 12) & 0xfffu), h.dock_mask = (int)((w >> 24) & 15u);
+        w = s.ld_hot(W_PSQ);
+        h.next_order = (int)(w & 0xfffu);
+        h.cur_order = (int)((w >> 12) & 0x1fffu);
+        if (h.cur_order == 0x1fff) h.cur_order = -1;
+        w = s.ld_hot(W_LONG_PSQ);
+        h.ready_order = (int)(w & 0xfffu), h.ready_count = (int)((w >> 12) & 0xfffu);
+        w = s.ld_hot(W_LONG_CNT);
+        h.total_packaged = (int)(w & 0xffffu), h.alloc_count = (int)((w >> 16) & 0xfffu);
+    } else {
+        u32 w = s.ld_hot(W_CTRL);
+        h.step = (int)(w & 0xffffu), h.num_orders = (int)((w >> 16) & 63u), h.fault = (int)((w >> 22) & 7u);
+        h.completed_orders = (int)((w >> 25) & 63u);
+        w = s.ld_hot(W_PS);
+        h.total_packaged = (int)(w & 511u), h.next_order = (int)((w >> 9) & 63u), h.cur_order = (int)((w >> 15) & 63u);
+        if (h.cur_order == 63) h.cur_order = -1;
+        h.prod_idx = (int)((w >> 21) & 15u), h.cur_tray_count = (int)((w >> 25) & 7u);
+        w = s.ld_hot(W_PSQ);
+        h.alloc_count = (int)(w & 255u), h.ready_count = (int)((w >> 8) & 255u), h.ready_order = (int)((w >> 16) & 63u);
+        h.ready_idx = (int)((w >> 22) & 15u), h.dock_mask = (int)((w >> 26) & 15u);
+    }
     h.episode = s.ld_hot(W_EPISODE);
 }
 template <class S>
 FJSP_HD void store_hot(S& s, const Hot& h) {
-    s.st_hot(W_CTRL, (u32)h.step | ((u32)h.num_orders << 16) | ((u32)h.fault << 22) | ((u32)h.completed_orders << 24));
-    s.st_hot(W_PS, (u32)h.total_packaged | ((u32)h.next_order << 9) | ((u32)h.cur_order << 15) | ((u32)h.prod_idx << 21) |
-                       ((u32)h.cur_tray_count << 25));
-    s.st_hot(W_PSQ, (u32)h.alloc_count | ((u32)h.ready_count << 8) | ((u32)h.ready_order << 16) | ((u32)h.ready_idx << 22) |
-                        ((u32)h.dock_mask << 26));
+    if (S::LONG) {
+        s.st_hot(W_CTRL, (u32)h.step | ((u32)h.fault << 16) | ((u32)h.cur_tray_count << 19) | ((u32)h.prod_idx << 22) |
+                             ((u32)h.ready_idx << 26));
+        s.st_hot(W_PS, (u32)h.num_orders | ((u32)h.completed_orders << 12) | ((u32)h.dock_mask << 24));
+        s.st_hot(W_PSQ, (u32)h.next_order | ((u32)(h.cur_order < 0 ? 0x1fff : h.cur_order) << 12));
+        s.st_hot(W_LONG_PSQ, (u32)h.ready_order | ((u32)h.ready_count << 12));
+        s.st_hot(W_LONG_CNT, (u32)h.total_packaged | ((u32)h.alloc_count << 16));
+    } else {
+        s.st_hot(W_CTRL, (u32)h.step | ((u32)h.num_orders << 16) | ((u32)h.fault << 22) | ((u32)h.completed_orders << 25));
+        s.st_hot(W_PS, (u32)h.total_packaged | ((u32)h.next_order << 9) | ((u32)(h.cur_order < 0 ? 63 : h.cur_order) << 15) |
+                           ((u32)h.prod_idx << 21) | ((u32)h.cur_tray_count << 25));
+        s.st_hot(W_PSQ, (u32)h.alloc_count | ((u32)h.ready_count << 8) | ((u32)h.ready_order << 16) | ((u32)h.ready_idx << 22) |
+                            ((u32)h.dock_mask << 26));
+    }
     s.st_hot(W_EPISODE, h.episode);
 }
 template <int K, class S>
 FJSP_HD void load_cell(S& s, int c, HotCell& h) {
-    u32 w = s.ld_hot(cell_word(K, c, 0));
+    constexpr bool LONG = S::LONG;
+    u32 w = s.ld_hot(cell_word<K, LONG>(c, 0));
     h.agv_loc = (int)(w & 7u), h.agv_moving = (int)((w >> 3) & 1u), h.agv_target = (int)((w >> 4) & 7u);
     h.agv_arrive = (int)((w >> 7) & 0xffffu), h.carry = (int)((w >> 23) & 127u);
-    h.free_lo = s.ld_hot(cell_word(K, c, 1)), h.free_hi = s.ld_hot(cell_word(K, c, 2));
-    w = s.ld_hot(cell_word(K, c, 3));
+    h.free_lo = s.ld_hot(cell_word<K, LONG>(c, 1)), h.free_hi = s.ld_hot(cell_word<K, LONG>(c, 2));
+    w = s.ld_hot(cell_word<K, LONG>(c, 3));
     h.storage.head = (int)(w & 63u), h.storage.tail = (int)((w >> 6) & 63u), h.storage.len = (int)((w >> 12) & 255u);
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         Mach& m = h.m[i];
-        w = s.ld_hot(cell_word(K, c, 4 + 2 * i));
+        w = s.ld_hot(cell_word<K, LONG>(c, 4 + 2 * i));
         m.busy = (int)(w & 1u), m.has_cur = (int)((w >> 1) & 1u), m.cur = (int)((w >> 2) & 63u);
         m.start = (int)((w >> 8) & 0xffffu), m.prog = (int)((w >> 24) & 1u), m.q.len = (int)((w >> 25) & 63u);
-        w = s.ld_hot(cell_word(K, c, 5 + 2 * i));
+        w = s.ld_hot(cell_word<K, LONG>(c, 5 + 2 * i));
         m.q.head = (int)(w & 63u), m.q.tail = (int)((w >> 6) & 63u), m.r.head = (int)((w >> 12) & 63u);
         m.r.tail = (int)((w >> 18) & 63u), m.r.len = (int)((w >> 24) & 63u);
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         Pack& p = h.p[i];
-        w = s.ld_hot(cell_word(K, c, 8 + 3 * i));
+        w = s.ld_hot(cell_word<K, LONG>(c, 8 + 3 * i));
         p.q.head = (int)(w & 63u), p.q.tail = (int)((w >> 6) & 63u), p.q.len = (int)((w >> 12) & 63u);
         p.f.head = (int)((w >> 18) & 63u), p.f.tail = (int)((w >> 24) & 63u);
-        w = s.ld_hot(cell_word(K, c, 9 + 3 * i));
+        w = s.ld_hot(cell_word<K, LONG>(c, 9 + 3 * i));
         p.f.len = (int)(w & 63u), p.users = (int)((w >> 6) & 31u), p.busy = (int)((w >> 11) & 1u);
-        p.waiters = (int)((w >> 12) & 1u), p.hascur = (int)((w >> 13) & 1u), p.curprod = (int)((w >> 14) & 511u);
-        p.qcount = (int)((w >> 23) & 255u);
-        w = s.ld_hot(cell_word(K, c, 10 + 3 * i));
-        p.completed = (int)(w & 255u), p.progL = (int)((w >> 8) & 255u);
+        p.waiters = (int)((w >> 12) & 1u), p.hascur = (int)((w >> 13) & 1u);
+        const u32 wc = s.ld_hot(cell_word<K, LONG>(c, 10 + 3 * i));
+        if (LONG) {
+            p.qcount = (int)((w >> 14) & 255u);
+            p.completed = (int)(wc & 0xffffu), p.progL = (int)((wc >> 16) & 255u);
+            const u32 wd = s.ld_hot(cell_word<K, LONG>(c, 20 + i));
+            p.cur_order = (int)(wd & 0xfffu), p.cur_idx = (int)((wd >> 12) & 15u);
+        } else {
+            p.cur_order = (int)((w >> 14) & 31u), p.cur_idx = (int)((w >> 19) & 15u), p.qcount = (int)((w >> 23) & 255u);
+            p.completed = (int)(wc & 255u), p.progL = (int)((wc >> 8) & 255u);
+        }
     }
 }
 template <int K, class S>
 FJSP_HD void store_cell(S& s, int c, const HotCell& h) {
-    s.st_hot(cell_word(K, c, 0), (u32)h.agv_loc | ((u32)h.agv_moving << 3) | ((u32)h.agv_target << 4) | ((u32)h.agv_arrive << 7) |
-                                     ((u32)h.carry << 23));
-    s.st_hot(cell_word(K, c, 1), h.free_lo), s.st_hot(cell_word(K, c, 2), h.free_hi);
-    s.st_hot(cell_word(K, c, 3), (u32)h.storage.head | ((u32)h.storage.tail << 6) | ((u32)h.storage.len << 12));
+    constexpr bool LONG = S::LONG;
+    s.st_hot(cell_word<K, LONG>(c, 0), (u32)h.agv_loc | ((u32)h.agv_moving << 3) | ((u32)h.agv_target << 4) | ((u32)h.agv_arrive << 7) |
+                                           ((u32)h.carry << 23));
+    s.st_hot(cell_word<K, LONG>(c, 1), h.free_lo), s.st_hot(cell_word<K, LONG>(c, 2), h.free_hi);
+    s.st_hot(cell_word<K, LONG>(c, 3), (u32)h.storage.head | ((u32)h.storage.tail << 6) | ((u32)h.storage.len << 12));
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         const Mach& m = h.m[i];
-        s.st_hot(cell_word(K, c, 4 + 2 * i), (u32)m.busy | ((u32)m.has_cur << 1) | ((u32)m.cur << 2) | ((u32)m.start << 8) |
-                                                 ((u32)m.prog << 24) | ((u32)m.q.len << 25));
-        s.st_hot(cell_word(K, c, 5 + 2 * i), (u32)m.q.head | ((u32)m.q.tail << 6) | ((u32)m.r.head << 12) | ((u32)m.r.tail << 18) |
-                                                 ((u32)m.r.len << 24));
+        s.st_hot(cell_word<K, LONG>(c, 4 + 2 * i), (u32)m.busy | ((u32)m.has_cur << 1) | ((u32)m.cur << 2) | ((u32)m.start << 8) |
+                                                       ((u32)m.prog << 24) | ((u32)m.q.len << 25));
+        s.st_hot(cell_word<K, LONG>(c, 5 + 2 * i), (u32)m.q.head | ((u32)m.q.tail << 6) | ((u32)m.r.head << 12) | ((u32)m.r.tail << 18) |
+                                                       ((u32)m.r.len << 24));
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const Pack& p = h.p[i];
-        s.st_hot(cell_word(K, c, 8 + 3 * i), (u32)p.q.head | ((u32)p.q.tail << 6) | ((u32)p.q.len << 12) | ((u32)p.f.head << 18) |
-                                                 ((u32)p.f.tail << 24));
-        s.st_hot(cell_word(K, c, 9 + 3 * i), (u32)p.f.len | ((u32)p.users << 6) | ((u32)p.busy << 11) | ((u32)p.waiters << 12) |
-                                                 ((u32)p.hascur << 13) | ((u32)p.curprod << 14) | ((u32)p.qcount << 23));
-        s.st_hot(cell_word(K, c, 10 + 3 * i), (u32)p.completed | ((u32)p.progL << 8));
+        s.st_hot(cell_word<K, LONG>(c, 8 + 3 * i), (u32)p.q.head | ((u32)p.q.tail << 6) | ((u32)p.q.len << 12) | ((u32)p.f.head << 18) |
+                                                       ((u32)p.f.tail << 24));
+        const u32 b = (u32)p.f.len | ((u32)p.users << 6) | ((u32)p.busy << 11) | ((u32)p.waiters << 12) | ((u32)p.hascur << 13);
+        if (LONG) {
+            s.st_hot(cell_word<K, LONG>(c, 9 + 3 * i), b | ((u32)p.qcount << 14));
+            s.st_hot(cell_word<K, LONG>(c, 10 + 3 * i), (u32)(p.completed & 0xffff) | ((u32)p.progL << 16));
+            s.st_hot(cell_word<K, LONG>(c, 20 + i), (u32)p.cur_order | ((u32)p.cur_idx << 12));
+        } else {
+            s.st_hot(cell_word<K, LONG>(c, 9 + 3 * i), b | ((u32)p.cur_order << 14) | ((u32)p.cur_idx << 19) | ((u32)p.qcount << 23));
+            s.st_hot(cell_word<K, LONG>(c, 10 + 3 * i), (u32)(p.completed & 255) | ((u32)p.progL << 8));
+        }
     }
 }
 
@@ -334,29 +425,46 @@ FJSP_HD void philox_actions_k(uint64_t seed, uint64_t genv, uint64_t t, int* a) 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Reset: FJSPSimulation.reset (FJSPSimulation.py:286-323).  `orders` = FjspOrderRec[32] (n | type<<8 | colour<<16)
-// or nullptr -> Philox.
+// Reset: FJSPSimulation.reset (FJSPSimulation.py:286-323).  `orders` = explicit FjspOrderRec table (n | type<<8 |
+// colour<<16; 32 records in the compact layout, `num_orders` in the long one) or nullptr -> Philox.
 // ---------------------------------------------------------------------------------------------
-// Everything of a fresh env except the 32 order words (the kernels fill those warp-cooperatively, one order per lane).
+// explicit record -> order word; n in 1..9 products, type and colour in 1..3 (FJSPSimulation.py:107-112).  Anything else
+// would overflow its bit-field in the order word, so it is clamped and reported (`bad`).
+FJSP_HD u32 order_from_rec(u32 r, bool& bad) {
+    int n = (int)(r & 0xffu), ty = (int)((r >> 8) & 0xffu), co = (int)((r >> 16) & 0xffu);
+    if (n < 1 || n > FJSP_MAX_ORDER_PRODUCTS || ty < 1 || ty > 3 || co < 1 || co > 3 || (r >> 24)) {
+        bad = true;
+        n = n < 1 ? 1 : n > FJSP_MAX_ORDER_PRODUCTS ? FJSP_MAX_ORDER_PRODUCTS : n;
+        ty = ty < 1 ? 1 : ty > 3 ? 3 : ty, co = co < 1 ? 1 : co > 3 ? 3 : co;
+    }
+    return make_order(n, ty, co);
+}
+
+// Everything of a fresh env except the compact layout's 32 order words (the kernels fill those warp-cooperatively, one
+// order per lane; the long layout's ring fills as the pickup station pops orders).
 template <int K, class S>
-FJSP_HD void reset_env_base(S& s, int num_orders, u32 episode) {
+FJSP_HD void reset_env_base(S& s, int num_orders, u32 episode, int fault = 0) {
+    constexpr bool LONG = S::LONG;
+    using L = Lay<K, LONG>;
 #pragma unroll
-    for (int w = 0; w < W_CSTEP; w++) s.st_hot(w, 0u);
-#pragma unroll
-    for (int w = W_CSTEP; w < W_ORDER; w++) s.st(w, 0u);
+    for (int w = 0; w < L::DYN0; w++) s.st_hot(w, 0u);
 #pragma unroll 8
-    for (int w = W_POOL; w < Lay<K>::DYN_END; w++) s.st(w, 0u);
+    for (int w = L::DYN0; w < L::DYN_END; w++)
+        if (LONG || w < WM<LONG>::W_ORDER || w >= WM<LONG>::W_POOL) s.st(w, 0u);
 #pragma unroll
-    for (int w = Lay<K>::DYN_END; w < Lay<K>::TOTAL; w++) s.st_hot(w, 0u);
-    s.st_hot(W_CTRL, (u32)num_orders << 16);
-    s.st_hot(W_PS, 63u << 15);   // cur_order = none
-    s.st_hot(W_PSQ, 1u << 26);   // the dock of the pickup station is held by cell 0's AGV
-    s.st_hot(W_EPISODE, episode);
+    for (int w = L::DYN_END; w < L::TOTAL; w++) s.st_hot(w, 0u);
+    Hot h;
+    h.step = 0, h.num_orders = num_orders, h.fault = fault, h.completed_orders = 0;
+    h.total_packaged = 0, h.next_order = 0, h.cur_order = -1, h.prod_idx = 0, h.cur_tray_count = 0;
+    h.alloc_count = 0, h.ready_count = 0, h.ready_order = 0, h.ready_idx = 0;
+    h.dock_mask = 1;   // the dock of the pickup station is held by cell 0's AGV
+    h.episode = episode;
+    store_hot(s, h);
 #pragma unroll
     for (int c = 0; c < K; c++) {
         // AGVAgent.py:41: the AGV starts at PICKUP; further cells' AGVs start at STORAGE (one dock)
-        s.st_hot(cell_word(K, c, 0), (u32)(c == 0 ? LOC_PICKUP : LOC_STORAGE));
-        s.st_hot(cell_word(K, c, 1), 0xffffffffu), s.st_hot(cell_word(K, c, 2), 0xffffffffu);
+        s.st_hot(cell_word<K, LONG>(c, 0), (u32)(c == 0 ? LOC_PICKUP : LOC_STORAGE));
+        s.st_hot(cell_word<K, LONG>(c, 1), 0xffffffffu), s.st_hot(cell_word<K, LONG>(c, 2), 0xffffffffu);
     }
 }
 
@@ -364,29 +472,21 @@ template <int K, class S>
 FJSP_HD void reset_env(S& s, const Params& P, int num_orders, const FjspOrderRec* orders, uint64_t seed, uint64_t genv,
                        u32 episode) {
     (void)P;
-    reset_env_base<K>(s, num_orders, episode);
+    constexpr bool LONG = S::LONG;
     bool bad = false;
+    if (LONG) {
+        if (orders)
+            for (int o = 0; o < num_orders; o++) (void)order_from_rec(orders[o], bad);
+        reset_env_base<K>(s, num_orders, episode, bad ? FJSP_FAULT_BAD_ORDER : 0);
+        return;
+    }
+    reset_env_base<K>(s, num_orders, episode);
     for (int o = 0; o < FJSP_MAX_ORDERS; o++) {
         u32 ow = 0u;
-        if (o < num_orders) {
-            if (orders) {
-                // explicit record: n in 1..9 products, type and colour in 1..3 (FJSPSimulation.py:107-112).  Anything else
-                // would overflow its bit-field in the order word, so it is clamped and the env is marked faulty.
-                const u32 r = orders[o];
-                int n = (int)(r & 0xffu), ty = (int)((r >> 8) & 0xffu), co = (int)((r >> 16) & 0xffu);
-                if (n < 1 || n > FJSP_MAX_ORDER_PRODUCTS || ty < 1 || ty > 3 || co < 1 || co > 3 || (r >> 24)) {
-                    bad = true;
-                    n = n < 1 ? 1 : n > FJSP_MAX_ORDER_PRODUCTS ? FJSP_MAX_ORDER_PRODUCTS : n;
-                    ty = ty < 1 ? 1 : ty > 3 ? 3 : ty, co = co < 1 ? 1 : co > 3 ? 3 : co;
-                }
-                ow = make_order(n, ty, co);
-            } else {
-                ow = philox_order(seed, genv, episode, o);
-            }
-        }
-        s.st(W_ORDER + o, ow);
+        if (o < num_orders) ow = orders ? order_from_rec(orders[o], bad) : philox_order(seed, genv, episode, o);
+        s.st(WM<LONG>::W_ORDER + o, ow);
     }
-    if (bad) s.st_hot(W_CTRL, ((u32)num_orders << 16) | ((u32)FJSP_FAULT_BAD_ORDER << 22));
+    if (bad) reset_env_base<K>(s, num_orders, episode, FJSP_FAULT_BAD_ORDER);  // (rare path: rewrite the scalars with the fault set)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -434,10 +534,10 @@ FJSP_HD void mask_set(u32* mw, int idx, int v) { mw[idx >> 2] |= (u32)(v & 1) <<
 template <class S, class O>
 FJSP_HD void observe_shared(S& s, const Params& P, const Hot& h, O obs, u32* mw) {
     // ---- pickup station: PickupStationAgent.get_observation (:58-98) / get_action_mask (:100-142)
-    int has_cur_order = h.cur_order != 63;
+    int has_cur_order = h.cur_order >= 0;
     int order_size = 0, remaining = 0, o_type = 0, o_colour = 0;
     if (has_cur_order) {
-        u32 ow = s.ld(W_ORDER + h.cur_order);
+        u32 ow = s.ld(WM<S::LONG>::W_ORDER + oslot<S::LONG>(h.cur_order));
         order_size = ord_n(ow), remaining = order_size - h.prod_idx;
         o_type = ord_type(ow), o_colour = ord_colour(ow);
     }
@@ -462,14 +562,14 @@ FJSP_HD void observe_shared(S& s, const Params& P, const Hot& h, O obs, u32* mw)
 // one cell: AGV (13) + small/big machine (3 + 3) + four packaging stations (12) = 31 floats; 26 mask bytes from `mo`
 template <class S, class O>
 FJSP_HD void observe_cell(S& s, const Params& P, const Hot& h, const HotCell& hc, int c, O obs, u32* mw, int mo) {
-    const int pb = pool_base(c);
+    const int pb = pool_base<S::LONG>(c);
     // ---- AGV: AGVAgent.get_observation (:53-76) / get_action_mask (:79-178)
     int carrying = hc.carry != 0;
     int c_count = 0, c_type = 0, c_proc = 0;
     if (carrying) {
         u32 r = s.ld(pb + hc.carry - 1);
         c_count = rec_count(r), c_proc = rec_processed(r);
-        c_type = ord_type(s.ld(W_ORDER + rec_order(r)));
+        c_type = ord_type(s.ld(WM<S::LONG>::W_ORDER + rec_order(r)));
     }
     obs.set(0, hc.m[1].busy);
     obs.set(1, hc.m[1].r.len);
@@ -678,8 +778,7 @@ FJSP_HD void pack_grant(S& s, int pb, Hot& h, HotCell& hc, Pack& p, int g, int s
                 return;
             }
             u32 started = make_rec(rec_order(r), rec_first(r), g, 1);
-            u32 rest = (r & ~((15u << 5) | (7u << 9))) | ((u32)(rec_first(r) + g) << 5) | ((u32)(cnt - g) << 9);
-            s.st(pb + slot, rest);
+            s.st(pb + slot, rec_split_rest(r, rec_first(r) + g, cnt - g));
             r = started;
             last_idx = rec_first(r) + g - 1;
             p.qcount -= g;
@@ -688,7 +787,7 @@ FJSP_HD void pack_grant(S& s, int pb, Hot& h, HotCell& hc, Pack& p, int g, int s
         s.st(pb + fslot, rec_with_stamp(r, stamp));
         fifo_push(s, pb, p.f, fslot);
         p.busy = 1, p.hascur = 1;
-        p.curprod = rec_order(r) | (last_idx << 5);
+        p.cur_order = order_of_slot<S::LONG>(rec_order(r), h.next_order), p.cur_idx = last_idx;
     }
 }
 
@@ -699,30 +798,58 @@ FJSP_HD void pack_grant(S& s, int pb, Hot& h, HotCell& hc, Pack& p, int g, int s
 // STORE = false: a lane that only mirrors the pickup station's registers (cell-parallel step): same arithmetic, no writes
 template <bool STORE = true, class S>
 FJSP_HD void act_pickup(S& s, const Params& P, Hot& h, int a0, int& local10, u32& res) {
+    constexpr bool LONG = S::LONG;
+    using W = WM<LONG>;
     int loaded = 0, tray_done = 0, idle_orders = 0, success = 0;
     if (a0 == 0) {
-        idle_orders = (h.num_orders - h.next_order) > 0 || h.cur_order != 63;
+        idle_orders = (h.num_orders - h.next_order) > 0 || h.cur_order >= 0;
         success = 1;
     } else if (a0 == 1) {
         int ok = 1;
-        if (h.cur_order == 63) {
-            if (h.next_order < h.num_orders) h.cur_order = h.next_order++, h.prod_idx = 0;
-            else ok = 0;
+        u32 ow = 0u;
+        bool fresh = false;
+        if (h.cur_order < 0) {
+            if (h.next_order < h.num_orders) {
+                const int o = h.next_order++;
+                h.cur_order = o, h.prod_idx = 0;
+                if (LONG) {
+                    // the order enters the ring now: its attributes come from the stream / table at this moment (every lane
+                    // that mirrors the pickup station computes the same word; only the storing lane touches the ring)
+                    ow = s.fetch_order(o, h.episode);
+                    fresh = true;
+                    if (STORE) {
+                        const int sl = oslot<LONG>(o);
+                        if (o >= W::RING) {  // the slot's previous occupant (order o - 64) must be complete by now
+                            const u32 prev = s.ld(W::W_ORDER + sl);
+                            if (ord_packaged(prev) != (1u << ord_n(prev)) - 1u) h.fault = FJSP_FAULT_ORDER_RING;
+                        }
+                        s.st(W::W_ORDER + sl, ow), s.st(W::W_ORDER_B + sl, 0u);
+                        const u32 cw = s.ld(W::W_CSTEP + (sl >> 1));
+                        s.st(W::W_CSTEP + (sl >> 1), cw & ~(0xffffu << ((sl & 1) * 16)));
+                    }
+                }
+            } else ok = 0;
         }
         if (ok && h.cur_tray_count == 0) {
-            if (h.alloc_count < P.trays_total) h.alloc_count++;  // trays_at_station.pop(0)
-            else ok = 0;
+            if (h.alloc_count < P.trays_total) {   // trays_at_station.pop(0)
+                if (LONG && STORE && h.prod_idx == 0) {  // the order's first tray: remember its allocation index (tray ids)
+                    const int sl = oslot<LONG>(h.cur_order);
+                    s.st(W::W_ORDER_B + sl, (s.ld(W::W_ORDER_B + sl) & 0x1ffu) | ((u32)h.alloc_count << 9));
+                }
+                h.alloc_count++;
+            } else ok = 0;
         }
         if (ok) {
-            u32 ow = s.ld(W_ORDER + h.cur_order);
+            const int sl = oslot<LONG>(h.cur_order);
+            if (!fresh) ow = s.ld(W::W_ORDER + sl);
             h.cur_tray_count++, h.prod_idx++;
             loaded = 1, success = 1;
             if (h.prod_idx >= ord_n(ow)) {          // order exhausted: tray released (:201-208)
-                h.cur_order = 63, h.prod_idx = 0;
+                h.cur_order = -1, h.prod_idx = 0;
                 h.cur_tray_count = 0, h.ready_count++;
                 tray_done = 1;
             } else if (h.cur_tray_count >= FJSP_TRAY_CAPACITY) {  // tray full (:211-216)
-                if (STORE) s.st(W_ORDER + h.cur_order, ow | (1u << (8 + h.prod_idx - 1)));  // cut after the last loaded product
+                if (STORE) s.st(W::W_ORDER + sl, ow | (1u << (8 + h.prod_idx - 1)));  // cut after the last loaded product
                 h.cur_tray_count = 0, h.ready_count++;
                 tray_done = 1;
             }
@@ -730,8 +857,9 @@ FJSP_HD void act_pickup(S& s, const Params& P, Hot& h, int a0, int& local10, u32
     } else if (a0 == 2) {
         if (h.cur_tray_count > 0) {                 // SIGNAL (:226-230): the order is not exhausted here
             if (STORE) {
-                u32 ow = s.ld(W_ORDER + h.cur_order);
-                s.st(W_ORDER + h.cur_order, ow | (1u << (8 + h.prod_idx - 1)));
+                const int sl = oslot<LONG>(h.cur_order);
+                u32 ow = s.ld(W::W_ORDER + sl);
+                s.st(W::W_ORDER + sl, ow | (1u << (8 + h.prod_idx - 1)));
             }
             h.cur_tray_count = 0, h.ready_count++;
             success = 1;
@@ -743,11 +871,36 @@ FJSP_HD void act_pickup(S& s, const Params& P, Hot& h, int a0, int& local10, u32
     local10 = (loaded ? 10 : 0) + (tray_done ? 50 : 0) - ((a0 == 0 && idle_orders) ? 10 : 0);
 }
 
+// FJSPSimulation.py:216-220; with order arrivals switched on an episode can only terminate once every order has arrived
+template <class S>
+FJSP_HD int all_orders_done(const Params& P, const Hot& h) {
+    const int all = h.completed_orders == h.num_orders && h.num_orders > 0 && h.next_order == h.num_orders;
+    return all && !(S::LONG && P.arrival_q16 > 0 && h.num_orders < P.arrival_max);
+}
+
+// Long order streams: one Bernoulli(arrival_q16 / 65536) ARRIVAL per step from the Philox stream (counter = global env,
+// episode, step, 5), until arrival_max orders exist; order i's attributes are those of index i of the order stream.
+// Runs before the pickup station acts; every lane that mirrors the shared scalars computes the same.
+template <class S>
+FJSP_HD void arrivals(S& s, const Params& P, Hot& h) {
+    if (S::LONG && P.arrival_q16 > 0 && h.num_orders < P.arrival_max) {
+        if ((s.arrival_draw(h.episode, (u32)h.step) & 0xffffu) < (u32)P.arrival_q16) h.num_orders++;
+    }
+}
+
 // one cell's seven agents: agv, small machine, big machine, four packaging stations.  a/local10/res point at the cell's
 // first column.  pk_start[i] = products whose packaging processes START creates in this step (resolved in run_cell).
 template <class S>
 FJSP_HD void act_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, const int* a, int* local10, u32* res, int* pk_start) {
-    const int pb = pool_base(c);
+    constexpr bool LONG = S::LONG;
+    using W = WM<LONG>;
+    const int pb = pool_base<LONG>(c);
+    // a tray lost to one of the reference's quirks: the compact layout keeps its record (marked) so that is_processed stays
+    // exportable; the long layout keeps processed bits in the ring and gives the pool slot back at once
+    auto lose = [&](int slot, u32 r) {
+        if (LONG) pool_free(hc, slot);
+        else s.st(pb + slot, r | REC_LOST);
+    };
     // ---- R2-R4 AGV (AGVAgent.py:180-368)
     {
         int invalid = 0, moved = 0, pick = 0, drop = 0, to_pack = 0, success = 0;
@@ -781,10 +934,10 @@ FJSP_HD void act_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, 
                         h.fault = FJSP_FAULT_POOL_EXHAUSTED, invalid = 1;
                     } else {
                         // head ready tray = products [ready_idx, next cut] of order ready_order
-                        u32 ow = s.ld(W_ORDER + h.ready_order);
+                        u32 ow = s.ld(W::W_ORDER + oslot<LONG>(h.ready_order));
                         u32 cuts = ord_cut(ow) >> h.ready_idx;
                         int cnt = cuts ? ctz32(cuts) + 1 : ord_n(ow) - h.ready_idx;
-                        s.st(pb + slot, make_rec(h.ready_order, h.ready_idx, cnt, 0));
+                        s.st(pb + slot, make_rec(oslot<LONG>(h.ready_order), h.ready_idx, cnt, 0));
                         h.ready_idx += cnt;
                         if (h.ready_idx >= ord_n(ow)) h.ready_order++, h.ready_idx = 0;
                         h.ready_count--;
@@ -804,7 +957,7 @@ FJSP_HD void act_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, 
             } else {
                 const int slot = hc.carry - 1;
                 u32 r = s.ld(pb + slot);
-                u32 ow = s.ld(W_ORDER + rec_order(r));
+                u32 ow = s.ld(W::W_ORDER + rec_order(r));
                 const int ty = ord_type(ow), proc = rec_processed(r);
                 if (loc == LOC_SMALL || loc == LOC_BIG) {
                     int compat = loc == LOC_SMALL ? (ty == TYPE_SMALL || ty == TYPE_MEDIUM) : (ty == TYPE_BIG || ty == TYPE_MEDIUM);
@@ -815,7 +968,7 @@ FJSP_HD void act_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, 
                     } else invalid = 1;
                 } else if (loc == LOC_STORAGE) {
                     if (hc.storage.len < P.storage_capacity) fifo_push(s, pb, hc.storage, slot);
-                    else s.st(pb + slot, r | (1u << 27));  // Storage.add_tray False ignored: tray vanishes (Storage.py:18-22)
+                    else lose(slot, r);  // Storage.add_tray False ignored: tray vanishes (Storage.py:18-22)
                     drop = 1;
                 } else {  // PACKAGING (:352-360) -> add_tray_to_packaging (FJSPSimulation.py:402-430)
                     if (proc) {
@@ -828,7 +981,7 @@ FJSP_HD void act_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, 
                         else if (st == 1) fifo_push(s, pb, hc.p[1].q, slot), hc.p[1].qcount += cnt;
                         else if (st == 2) fifo_push(s, pb, hc.p[2].q, slot), hc.p[2].qcount += cnt;
                         else if (st == 3) fifo_push(s, pb, hc.p[3].q, slot), hc.p[3].qcount += cnt;
-                        else s.st(pb + slot, r | (1u << 27));  // no station with capacity: products dropped (:426-427)
+                        else lose(slot, r);  // no station with capacity: products dropped (:426-427)
                         drop = 1, to_pack = 1;
                     } else invalid = 1;
                 }
@@ -855,10 +1008,7 @@ FJSP_HD void act_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, 
         } else if (act == 1) {
             if (m.q.len > 0 && !m.busy) {
                 int slot = fifo_pop(s, pb, m.q);
-                if (m.has_cur) {  // unsignalled finished tray is overwritten and lost (:160)
-                    u32 old = s.ld(pb + m.cur);
-                    s.st(pb + m.cur, old | (1u << 27));
-                }
+                if (m.has_cur) lose(m.cur, s.ld(pb + m.cur));  // unsignalled finished tray is overwritten and lost (:160)
                 m.busy = 1, m.has_cur = 1, m.cur = slot, m.start = k;
                 started = 1, success = 1;
             }
@@ -908,7 +1058,9 @@ FJSP_HD void act_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, 
 // until every cell has acted (cells are processed one after the other here, but all actions precede all runs).
 template <class S>
 FJSP_HD void run_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, const int* pk_start, int& dock_after) {
-    const int pb = pool_base(c);
+    constexpr bool LONG = S::LONG;
+    using W = WM<LONG>;
+    const int pb = pool_base<LONG>(c);
     // AGV arrival (AGVAgent.py:387-396); the dock is held while standing at PICKUP or under way to it
     if (hc.agv_moving && hc.agv_arrive == k) hc.agv_loc = hc.agv_target, hc.agv_moving = 0;
     dock_after |= (hc.agv_moving ? (hc.agv_target == LOC_PICKUP) : (hc.agv_loc == LOC_PICKUP)) << c;
@@ -920,7 +1072,8 @@ FJSP_HD void run_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, 
             u32 r = s.ld(pb + m.cur);
             const int per = i == 0 ? P.small_steps : P.big_steps;
             if (k == m.start + per * rec_count(r)) {
-                s.st(pb + m.cur, r | (1u << 12));
+                s.st(pb + m.cur, r | REC_PROCESSED);
+                if (LONG) s.or_word(W::W_ORDER_B + rec_order(r), ((1u << rec_count(r)) - 1u) << rec_first(r));  // is_processed, kept in the ring
                 m.busy = 0, m.prog = 1;
             }
         }
@@ -949,14 +1102,15 @@ FJSP_HD void run_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, 
             // or_word: a plain read-modify-write when one thread owns the env, an atomic OR when the cells of an env run
             // on different threads (two cells may package products of the same order in the same step)
             const u32 bits = (((1u << cnt) - 1u) << rec_first(r)) << 16;   // is_packaged (:143)
-            const u32 before = s.or_word(W_ORDER + o, bits);
+            const u32 before = s.or_word(W::W_ORDER + o, bits);
             const u32 ow = before | bits;
             p.completed += cnt, h.total_packaged += cnt, p.users -= cnt, released += cnt;
             p.busy = 0;
             const u32 full = (1u << ord_n(ow)) - 1u;
             if (ord_packaged(ow) == full && ord_packaged(before) != full) {  // _check_order_completions (FJSPSimulation.py:245-258)
                 h.completed_orders++;
-                s.or_word(W_CSTEP + (o >> 2), (u32)((k + 1) & 255) << ((o & 3) * 8));
+                if (LONG) s.or_word(W::W_CSTEP + (o >> 1), (u32)((k + 1) & 0xffff) << ((o & 1) * 16));
+                else s.or_word(W::W_CSTEP + (o >> 2), (u32)((k + 1) & 255) << ((o & 3) * 8));
             }
         }
         const int stamp = (k + P.pack_steps) & 255;
@@ -988,6 +1142,20 @@ FJSP_HD void step_env_hot(S& s, const Params& P, Hot& h, HotCell& c0, const int*
 #pragma unroll
     for (int i = A; i < Lay<K>::ACT; i++) local10[i] = 0, res[i] = 0u;
 
+    if (k > P.max_episode_steps) {
+        // The episode ended with the previous step (truncation fires when step == max_episode_steps) and the caller did not
+        // reset: the reference would simulate on, the packed counters are not sized for that -> the env is inert and says so.
+        out.d_orders = 0, out.d_products = 0, out.reward_g = 0, out.reward_units = 0;
+#pragma unroll
+        for (int i = 0; i < Lay<K>::ACT; i++) out.reward_local10[i] = 0, out.reward[i] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < Lay<K>::ACT / 4; i++) out.results[i] = 0u;
+        out.flags = (1u << 8) | ((u32)FJSP_FAULT_PAST_END << 16);
+        out.info[0] = h.step, out.info[1] = h.completed_orders, out.info[2] = h.total_packaged, out.info[3] = 0;
+        observe_out<K, MODE>(s, P, h, c0, out);
+        return;
+    }
+    arrivals(s, P, h);
     act_pickup(s, P, h, a[0], local10[0], res[0]);
     int dock_after = 0;
     {
@@ -1030,7 +1198,7 @@ FJSP_HD void step_env_hot(S& s, const Params& P, Hot& h, HotCell& c0, const int*
         out.reward_units = units;
     }
     // ===== termination / truncation (FJSPSimulation.py:216-224), pre-increment step =====
-    const int all_done = h.completed_orders == h.num_orders && h.num_orders > 0 && h.next_order == h.num_orders;
+    const int all_done = all_orders_done<S>(P, h);
     const int truncated = k >= P.max_episode_steps;
     out.flags = (u32)all_done | ((u32)truncated << 8) | ((u32)h.fault << 16);
 #pragma unroll
@@ -1065,7 +1233,8 @@ FJSP_HD void step_env(S& s, const Params& P, const int* a, StepOut<K>& out) {
 //   3. every lane rebuilds the same shared scalars from X, computes its agents' rewards and observation, posts the
 //      reward numerators and mask bits                                                                      -> barrier
 //   4. output rows are assembled in 32-byte pieces, one per lane.
-// X slots: X_RDF = dock requests (bits 0..3) | dock occupancy after the step (4..7) | fault code of cell c (8+2c..9+2c);
+// X slots: X_RDF = dock requests (bits 0..3) | dock occupancy after the step (4..7) | fault code of cell c (8+3c..10+3c) |
+// fault code of the pickup station (20..22);
 // X_READY = ready cursor posted by the picking lane (bit 31 = valid); X_DELTA = completed orders << 16 | packaged
 // products; X_MASK.. = 3 mask bits of the pickup station, then 26 per cell; then one u16 per action column:
 // local reward (9-bit signed, tenths) | action_result << 9.
@@ -1086,19 +1255,28 @@ struct CellLane {
     int g;           // after cells_finish: 10 * (100 * orders + 10 * products) - step_size
     int d_orders, d_products;
     u32 flags;
+    bool inert;      // stepped past the end of the episode (see step_env_hot)
 };
 
 template <int K, class S, class X>
 FJSP_HD void cells_begin(S& s, X& x, const Params& P, CellLane& L, int a0, const int* a7) {
     L.k = L.h.step, L.fault_in = L.h.fault;
-    if (L.c == 0) act_pickup<true>(s, P, L.h, a0, L.local10[0], L.res[0]);
-    else act_pickup<false>(s, P, L.h, a0, L.local10[0], L.res[0]);
+    L.inert = L.k > P.max_episode_steps;
+    if (L.inert) return;
+    arrivals(s, P, L.h);
+    if (L.c == 0) {
+        act_pickup<true>(s, P, L.h, a0, L.local10[0], L.res[0]);
+        if (L.h.fault != L.fault_in) x.atom_or(X_RDF, (u32)(L.h.fault & 7) << 20);  // (order ring overflow: long layout)
+    } else {
+        act_pickup<false>(s, P, L.h, a0, L.local10[0], L.res[0]);
+    }
     const int wants_dock = !L.hc.agv_moving && a7[0] == 1 && P.dist[L.hc.agv_loc][LOC_PICKUP] != 0;
     if (wants_dock) x.atom_or(X_RDF, 1u << L.c);
 }
 
 template <int K, class S, class X>
 FJSP_HD void cells_act_run(S& s, X& x, const Params& P, CellLane& L, const int* a7) {
+    if (L.inert) return;
     // the dock as this cell's AGV sees it: holders before the step + grants to earlier cells of this step
     const u32 reqs = x.ld(X_RDF) & 15u;
     int m = L.h.dock_mask;
@@ -1112,38 +1290,49 @@ FJSP_HD void cells_act_run(S& s, X& x, const Params& P, CellLane& L, const int* 
     int pk_start[4];
     act_cell(s, P, L.h, L.hc, L.c, L.k, a7, L.local10 + 1, L.res + 1, pk_start);
     if (L.h.ready_count != rc || L.h.ready_order != ro || L.h.ready_idx != ri)
-        x.st(X_READY, (u32)L.h.ready_count | ((u32)L.h.ready_order << 8) | ((u32)L.h.ready_idx << 16) | (1u << 31));
+        x.st(X_READY, (u32)L.h.ready_count | ((u32)L.h.ready_order << 12) | ((u32)L.h.ready_idx << 24) | (1u << 31));
     int dock_after = 0;
     run_cell(s, P, L.h, L.hc, L.c, L.k, pk_start, dock_after);
     u32 post = (u32)dock_after << 4;
-    if (L.h.fault != -1) post |= (u32)(L.h.fault & 3) << (8 + 2 * L.c);
+    if (L.h.fault != -1) post |= (u32)(L.h.fault & 7) << (8 + 3 * L.c);
     if (post) x.atom_or(X_RDF, post);
     const u32 delta = ((u32)L.h.completed_orders << 16) | (u32)L.h.total_packaged;
     if (delta) x.atom_add(X_DELTA, delta);
 }
 
-template <int K, class X>
+template <int K, class S, class X>
 FJSP_HD void cells_finish(X& x, const Params& P, CellLane& L, int32_t* info) {
     constexpr int A = Lay<K>::AGENTS;
-    const u32 rdf = x.ld(X_RDF), ready = x.ld(X_READY), delta = x.ld(X_DELTA);
     Hot& h = L.h;
-    if (ready >> 31) h.ready_count = (int)(ready & 255u), h.ready_order = (int)((ready >> 8) & 63u), h.ready_idx = (int)((ready >> 16) & 15u);
+    if (L.inert) {
+        L.g = 0, L.d_orders = 0, L.d_products = 0;
+        L.flags = (1u << 8) | ((u32)FJSP_FAULT_PAST_END << 16);
+#pragma unroll
+        for (int i = 0; i < 8; i++) L.local10[i] = 0, L.res[i] = 0u;
+        L.orders_in = h.completed_orders, L.packaged_in = h.total_packaged;
+        info[0] = h.step, info[1] = h.completed_orders, info[2] = h.total_packaged, info[3] = 0;
+    }
+    const u32 rdf = x.ld(X_RDF), ready = x.ld(X_READY), delta = x.ld(X_DELTA);
+    if (!L.inert) {
+    if (ready >> 31) h.ready_count = (int)(ready & 0xfffu), h.ready_order = (int)((ready >> 12) & 0xfffu), h.ready_idx = (int)((ready >> 24) & 15u);
     const int d_orders = (int)(delta >> 16), d_products = (int)(delta & 0xffffu);
     h.completed_orders = L.orders_in + d_orders, h.total_packaged = L.packaged_in + d_products;
     h.dock_mask = (int)((rdf >> 4) & 15u);
     h.fault = L.fault_in;
+    if ((rdf >> 20) & 7u) h.fault = (int)((rdf >> 20) & 7u);
 #pragma unroll
-    for (int j = 0; j < K; j++) {  // the last cell that raised a fault wins, as in agent order
-        const int f = (int)((rdf >> (8 + 2 * j)) & 3u);
+    for (int j = 0; j < K; j++) {  // the last agent that raised a fault wins, as in agent order
+        const int f = (int)((rdf >> (8 + 3 * j)) & 7u);
         if (f) h.fault = f;
     }
     L.g = 10 * (100 * d_orders + 10 * d_products) - P.step_size;
     L.d_orders = d_orders, L.d_products = d_products;
-    const int all_done = h.completed_orders == h.num_orders && h.num_orders > 0 && h.next_order == h.num_orders;
+    const int all_done = all_orders_done<S>(P, h);
     const int truncated = L.k >= P.max_episode_steps;
     L.flags = (u32)all_done | ((u32)truncated << 8) | ((u32)h.fault << 16);
     h.step = L.k + 1;
     info[0] = h.step, info[1] = h.completed_orders, info[2] = h.total_packaged, info[3] = 0;
+    }
     // post this lane's columns: local reward (tenths, 9-bit signed) | action_result << 9
     if (L.c == 0) x.st16(2 * Xl<K>::LOCAL, ((u32)L.local10[0] & 0x1ffu) | (L.res[0] << 9));
 #pragma unroll

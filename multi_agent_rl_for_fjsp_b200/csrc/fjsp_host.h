@@ -9,6 +9,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "fjsp_core.h"
 
 namespace fjsp {
@@ -40,7 +42,14 @@ inline const char* make_params(const FjspConfig& c, Params* P) {
             return "processing times must be positive multiples of step_size (timers are resolved on step boundaries)";
     if (c.proc_pack / c.step_size > 200) return "proc_pack too long";
     if (c.tray_capacity != FJSP_TRAY_CAPACITY) return "tray_capacity must be 5 (the reference's mask hard-codes CONFIG['tray_capacity'])";
-    if (c.max_episode_steps < 1 || c.max_episode_steps > 240) return "max_episode_steps must be in 1..240 (bounds the 64-slot tray pool and the 6/8-bit queue counters)";
+    if (c.long_streams != 0 && c.long_streams != 1) return "long_streams must be 0 or 1";
+    if (!c.long_streams && (c.max_episode_steps < 1 || c.max_episode_steps > 240))
+        return "max_episode_steps must be in 1..240 in the compact layout (bounds the 64-slot tray pool and the 6/8-bit counters); set long_streams = 1 for longer episodes";
+    if (c.long_streams && (c.max_episode_steps < 1 || c.max_episode_steps > FJSP_LONG_MAX_STEPS)) return "max_episode_steps must be in 1..65000";
+    if (!c.long_streams && (c.arrival_prob_q16 || c.arrival_max_orders)) return "order arrivals need long_streams = 1";
+    if (c.arrival_prob_q16 < 0 || c.arrival_prob_q16 > 65536) return "arrival_prob_q16 must be in 0..65536";
+    if (c.arrival_max_orders < 0 || c.arrival_max_orders > FJSP_LONG_MAX_ORDERS) return "arrival_max_orders must be in 0..4095";
+    if (c.long_streams && c.num_trays > 4095) return "num_trays must be <= 4095 with long_streams (12-bit tray ids in the canonical record)";
     if (c.pack_capacity < 1 || c.pack_capacity > 31) return "pack_capacity must be in 1..31";
     if (c.storage_capacity < 0) return "storage_capacity must be >= 0";
     if (c.num_trays < 0 || c.num_trays > 65535) return "num_trays must be in 0..65535";
@@ -67,7 +76,8 @@ inline const char* make_params(const FjspConfig& c, Params* P) {
     P->pack_capacity = c.pack_capacity;
     P->num_trays = c.num_trays;
     P->trays_total = c.num_trays < 1000 ? c.num_trays : 1000;  // FJSPSimulation.py:96
-    if (P->trays_total > 255) P->trays_total = 255;            // an episode of <= 253 steps allocates <= 253 trays
+    if (!c.long_streams && P->trays_total > 255) P->trays_total = 255;  // compact: an episode of <= 241 steps allocates <= 241 trays
+    P->arrival_q16 = c.arrival_prob_q16, P->arrival_max = c.arrival_max_orders;
     P->step_size = c.step_size;
     P->progress_tab[0] = 0.0f;
     for (int L = 1; L < 256; L++) P->progress_tab[L] = (float)((1.0 / (double)L) * 100.0);
@@ -83,20 +93,38 @@ inline const char* make_params(const FjspConfig& c, Params* P) {
 #else
 #define FJSP_CHECK_IDX(cond) do { } while (0)
 #endif
-struct ArrayState {
+template <bool LONG_ = false>
+struct ArrayStateT {
+    static constexpr bool LONG = LONG_;
     u32* w;
     int dyn_end = 1 << 30, total = 1 << 30;  // word counts of the env (set by the harness when the check is compiled in)
-    FJSP_HD u32 ld(int i) const { FJSP_CHECK_IDX(i >= W_CSTEP && i < dyn_end); return w[i]; }
-    FJSP_HD void st(int i, u32 v) { FJSP_CHECK_IDX(i >= W_CSTEP && i < dyn_end); w[i] = v; }
-    FJSP_HD u32 ld_hot(int i) const { FJSP_CHECK_IDX((i >= 0 && i < W_CSTEP) || (i >= dyn_end && i < total)); return w[i]; }
-    FJSP_HD void st_hot(int i, u32 v) { FJSP_CHECK_IDX((i >= 0 && i < W_CSTEP) || (i >= dyn_end && i < total)); w[i] = v; }
+    uint64_t seed = 0, genv = 0;             // long layout: the order / arrival streams (see fjsp_kernels.cuh)
+    const FjspOrderRec* otab = nullptr;
+    static constexpr int DYN0 = WM<LONG_>::W_DYN0;
+    FJSP_HD u32 ld(int i) const { FJSP_CHECK_IDX(i >= DYN0 && i < dyn_end); return w[i]; }
+    FJSP_HD void st(int i, u32 v) { FJSP_CHECK_IDX(i >= DYN0 && i < dyn_end); w[i] = v; }
+    FJSP_HD u32 ld_hot(int i) const { FJSP_CHECK_IDX((i >= 0 && i < DYN0) || (i >= dyn_end && i < total)); return w[i]; }
+    FJSP_HD void st_hot(int i, u32 v) { FJSP_CHECK_IDX((i >= 0 && i < DYN0) || (i >= dyn_end && i < total)); w[i] = v; }
     FJSP_HD u32 or_word(int i, u32 v) {
-        FJSP_CHECK_IDX(i >= W_CSTEP && i < W_POOL);
+        FJSP_CHECK_IDX(i >= DYN0 && i < WM<LONG_>::W_POOL);
         const u32 old = w[i];
         w[i] = old | v;
         return old;
     }
+    FJSP_HD u32 fetch_order(int o, u32 episode) const {
+        if (otab) {
+            bool bad = false;
+            return order_from_rec(otab[o], bad);
+        }
+        return philox_order(seed, genv, episode, o);
+    }
+    FJSP_HD u32 arrival_draw(u32 episode, u32 step) const {
+        u32 r[4];
+        philox4x32_10((u32)genv, episode, step, 5u, (u32)seed, (u32)(seed >> 32), r);
+        return r[0];
+    }
 };
+using ArrayState = ArrayStateT<false>;
 // exchange area of the cell-parallel step, host emulation (lanes run one after the other)
 struct ArrayXchg {
     u32* w;
@@ -109,26 +137,33 @@ struct ArrayXchg {
 };
 
 // ---- canonical record S from packed words: shared pickup station / orders + the given cell ----
-template <int K>
-inline void export_canon_k(const u32* words, const Params& P, int cell, FjspCanonState* out) {
-    ArrayState s{const_cast<u32*>(words)};
-    s.dyn_end = Lay<K>::DYN_END, s.total = Lay<K>::TOTAL;
+// Long layout: the per-order arrays describe orders [order_base, order_base + 32) with order_base = max(0, next_order - 32)
+// (the 32 most recently popped), tray entries are FJSP_TRAY_ENTRY_LONG, product ids order * 100 + idx as in the reference.
+template <int K, bool LONG>
+inline void export_canon_k(const u32* words, const Params& P, int cell, FjspCanonState* out, int32_t* order_base_out = nullptr) {
+    using W = WM<LONG>;
+    ArrayStateT<LONG> s{const_cast<u32*>(words)};
+    s.dyn_end = Lay<K, LONG>::DYN_END, s.total = Lay<K, LONG>::TOTAL;
     Hot h;
     HotCell hc;
     load_hot(s, h);
     load_cell<K>(s, cell, hc);
-    const int pb = pool_base(cell);
+    const int pb = pool_base<LONG>(cell);
     FjspCanonState& c = *out;
     memset(&c, 0, sizeof(c));
-    auto order_word = [&](int o) { return words[W_ORDER + o]; };
-    auto alloc_idx = [&](int o, int first) {
+    const int order_base = LONG ? (h.next_order > FJSP_MAX_ORDERS ? h.next_order - FJSP_MAX_ORDERS : 0) : 0;
+    if (order_base_out) *order_base_out = order_base;
+    auto slot_word = [&](int slot) { return words[W::W_ORDER + slot]; };
+    auto order_id = [&](int slot) { return order_of_slot<LONG>(slot, h.next_order); };
+    auto alloc_idx = [&](int slot, int first) {
+        if (LONG) return (int)((words[W::W_ORDER_B + slot] >> 9) & 0xfffu) + popc32(ord_cut(slot_word(slot)) & ((1u << first) - 1u));
         int a = 0;
-        for (int q = 0; q < o; q++) a += popc32(ord_cut(order_word(q))) + 1;
-        return a + popc32(ord_cut(order_word(o)) & ((1u << first) - 1u));
+        for (int q = 0; q < slot; q++) a += popc32(ord_cut(slot_word(q))) + 1;
+        return a + popc32(ord_cut(slot_word(slot)) & ((1u << first) - 1u));
     };
-    auto entry = [&](int o, int first, int count) {
-        int id = P.num_trays - 1 - alloc_idx(o, first);
-        return FJSP_TRAY_ENTRY(id, o, first, count);
+    auto entry = [&](int slot, int first, int count) {
+        const int id = P.num_trays - 1 - alloc_idx(slot, first);
+        return LONG ? FJSP_TRAY_ENTRY_LONG(id, order_id(slot), first, count) : FJSP_TRAY_ENTRY(id, slot, first, count);
     };
     auto rec_entry = [&](u32 r) { return entry(rec_order(r), rec_first(r), rec_count(r)); };
     auto walk = [&](const Fifo& f, int32_t* dst, int cap) {
@@ -146,18 +181,18 @@ inline void export_canon_k(const u32* words, const Params& P, int cell, FjspCano
     c.agv_carry = hc.carry ? rec_entry(words[pb + hc.carry - 1]) : -1;
     c.agv_is_moving = hc.agv_moving;
     c.ps_order_queue_len = h.num_orders - h.next_order;
-    c.ps_current_order = h.cur_order == 63 ? -1 : h.cur_order;
+    c.ps_current_order = h.cur_order;
     c.ps_product_idx = h.prod_idx;
-    c.ps_current_tray = h.cur_tray_count > 0 ? entry(h.cur_order, h.prod_idx - h.cur_tray_count, h.cur_tray_count) : -1;
+    c.ps_current_tray = h.cur_tray_count > 0 ? entry(oslot<LONG>(h.cur_order), h.prod_idx - h.cur_tray_count, h.cur_tray_count) : -1;
     c.ps_trays_at_station = (P.num_trays < 1000 ? P.num_trays : 1000) - h.alloc_count;
     for (int i = 0; i < FJSP_CANON_PS_READY; i++) c.ps_ready[i] = -1;
     {
         int o = h.ready_order, f = h.ready_idx;
         for (int i = 0; i < h.ready_count && i < FJSP_CANON_PS_READY; i++) {
-            u32 ow = order_word(o);
+            u32 ow = slot_word(oslot<LONG>(o));
             u32 cuts = ord_cut(ow) >> f;
             int cnt = cuts ? ctz32(cuts) + 1 : ord_n(ow) - f;
-            c.ps_ready[i] = entry(o, f, cnt);
+            c.ps_ready[i] = entry(oslot<LONG>(o), f, cnt);
             f += cnt;
             if (f >= ord_n(ow)) o++, f = 0;
         }
@@ -175,7 +210,7 @@ inline void export_canon_k(const u32* words, const Params& P, int cell, FjspCano
     for (int i = 0; i < 4; i++) {
         const Pack& p = hc.p[i];
         c.pack[i].is_busy = p.busy;
-        c.pack[i].current_product = p.hascur ? (p.curprod & 31) * 100 + (p.curprod >> 5) : -1;
+        c.pack[i].current_product = p.hascur ? p.cur_order * 100 + p.cur_idx : -1;
         c.pack[i].progress_L = p.progL;
         c.pack[i].products_completed = p.completed;
         c.pack[i].users = p.users;
@@ -183,29 +218,24 @@ inline void export_canon_k(const u32* words, const Params& P, int cell, FjspCano
         int slot = p.q.head, n = 0;
         for (int k = 0; k < p.q.len; k++) {
             u32 r = words[pb + slot];
-            for (int j = 0; j < rec_count(r) && n < FJSP_CANON_MAXPQ; j++) c.pack[i].queue[n++] = rec_order(r) * 100 + rec_first(r) + j;
+            for (int j = 0; j < rec_count(r) && n < FJSP_CANON_MAXPQ; j++) c.pack[i].queue[n++] = order_id(rec_order(r)) * 100 + rec_first(r) + j;
             slot = rec_next(r);
         }
         c.pack[i].queue_n = p.qcount;
     }
-    for (int o = 0; o < FJSP_MAX_ORDERS; o++) {
-        u32 ow = order_word(o);
-        c.packaged_mask[o] = (int32_t)ord_packaged(ow);
-        c.processed_mask[o] = (int32_t)ord_packaged(ow);
-        int cs = (int)((words[W_CSTEP + (o >> 2)] >> ((o & 3) * 8)) & 255u);
-        c.order_complete[o] = cs != 0;
-        c.order_completion_step[o] = cs - 1;
-    }
+    // per-order arrays: orders order_base .. order_base + 31 (compact: 0..31)
+    int32_t proc_ring[W::RING];
+    for (int sl = 0; sl < W::RING; sl++) proc_ring[sl] = LONG ? (int32_t)(words[W::W_ORDER_B + sl] & 0x1ffu) : (int32_t)ord_packaged(slot_word(sl));
     // is_processed is a property of the products, whatever cell their tray is in: scan every cell's pool and machines
     for (int cc = 0; cc < K; cc++) {
         HotCell x;
         load_cell<K>(s, cc, x);
-        const int xb = pool_base(cc);
+        const int xb = pool_base<LONG>(cc);
         uint64_t free_bits = (uint64_t)x.free_lo | ((uint64_t)x.free_hi << 32);
         for (int slot = 0; slot < FJSP_POOL_SLOTS; slot++) {
             if ((free_bits >> slot) & 1u) continue;
             u32 r = words[xb + slot];
-            if (rec_processed(r)) c.processed_mask[rec_order(r)] |= (int32_t)(((1u << rec_count(r)) - 1u) << rec_first(r));
+            if (rec_processed(r)) proc_ring[rec_order(r)] |= (int32_t)(((1u << rec_count(r)) - 1u) << rec_first(r));
         }
         for (int i = 0; i < 2; i++) {
             const Mach& m = x.m[i];
@@ -215,20 +245,78 @@ inline void export_canon_k(const u32* words, const Params& P, int cell, FjspCano
             int done = (h.step - 1 - m.start) / per;
             if (done > rec_count(r)) done = rec_count(r);
             if (done < 0) done = 0;
-            c.processed_mask[rec_order(r)] |= (int32_t)(((1u << done) - 1u) << rec_first(r));
+            proc_ring[rec_order(r)] |= (int32_t)(((1u << done) - 1u) << rec_first(r));
         }
+    }
+    for (int i = 0; i < FJSP_MAX_ORDERS; i++) {
+        const int o = order_base + i;
+        c.order_completion_step[i] = -1;
+        if (LONG && o >= h.next_order) continue;  // not popped yet: not in the ring
+        const int sl = oslot<LONG>(o);
+        u32 ow = slot_word(sl);
+        c.packaged_mask[i] = (int32_t)ord_packaged(ow);
+        c.processed_mask[i] = proc_ring[sl] | (LONG ? 0 : 0);
+        int cs = LONG ? (int)((words[W::W_CSTEP + (sl >> 1)] >> ((sl & 1) * 16)) & 0xffffu) : (int)((words[W::W_CSTEP + (sl >> 2)] >> ((sl & 3) * 8)) & 255u);
+        c.order_complete[i] = cs != 0;
+        c.order_completion_step[i] = cs - 1;
     }
     c.total_products_packaged = h.total_packaged;
     c.completed_orders = h.completed_orders;
 }
 
-inline void export_canon(const u32* words, const Params& P, int cells, int cell, FjspCanonState* out) {
-    switch (cells) {
-        case 1: export_canon_k<1>(words, P, cell, out); break;
-        case 2: export_canon_k<2>(words, P, cell, out); break;
-        case 3: export_canon_k<3>(words, P, cell, out); break;
-        default: export_canon_k<4>(words, P, cell, out); break;
+// per-order records for orders [first, first + count): {packaged_mask, processed_mask, complete, completion_step}
+template <int K, bool LONG>
+inline void export_orders_k(const u32* words, const Params& P, int first, int count, int32_t* out4) {
+    using W = WM<LONG>;
+    ArrayStateT<LONG> s{const_cast<u32*>(words)};
+    Hot h;
+    load_hot(s, h);
+    // processed bits of trays still in pools / machines: reuse the canonical export of cell 0 (it scans every cell)
+    FjspCanonState c;
+    int32_t base = 0;
+    export_canon_k<K, LONG>(words, P, 0, &c, &base);
+    for (int i = 0; i < count; i++) {
+        const int o = first + i;
+        int32_t* r = out4 + 4 * i;
+        r[0] = r[1] = r[2] = 0, r[3] = -1;
+        if (o < 0 || o >= h.num_orders) continue;
+        if (LONG && o >= h.next_order) continue;                      // still in the queue
+        if (LONG && o < h.next_order - W::RING) {                      // left the ring: complete by construction
+            r[0] = r[1] = 0x1ff, r[2] = 1;
+            continue;
+        }
+        const int sl = oslot<LONG>(o);
+        const u32 ow = words[W::W_ORDER + sl];
+        r[0] = (int32_t)ord_packaged(ow);
+        if (o >= base && o < base + FJSP_MAX_ORDERS) r[1] = c.processed_mask[o - base];
+        else r[1] = LONG ? (int32_t)(words[W::W_ORDER_B + sl] & 0x1ffu) : 0;  // (older ring entries: finished trays only)
+        const int cs = LONG ? (int)((words[W::W_CSTEP + (sl >> 1)] >> ((sl & 1) * 16)) & 0xffffu) : (int)((words[W::W_CSTEP + (sl >> 2)] >> ((sl & 3) * 8)) & 255u);
+        r[2] = cs != 0, r[3] = cs - 1;
     }
+}
+
+template <class F>
+inline void dispatch_layout(int cells, bool long_streams, F&& f) {
+#define FJSP_CASE(KK)                                                       \
+    case KK:                                                                \
+        if (long_streams) f(std::integral_constant<int, KK>{}, std::true_type{});   \
+        else f(std::integral_constant<int, KK>{}, std::false_type{});       \
+        break;
+    switch (cells) {
+        FJSP_CASE(1) FJSP_CASE(2) FJSP_CASE(3)
+        default:
+            if (long_streams) f(std::integral_constant<int, 4>{}, std::true_type{});
+            else f(std::integral_constant<int, 4>{}, std::false_type{});
+            break;
+    }
+#undef FJSP_CASE
+}
+
+inline void export_canon(const u32* words, const Params& P, int cells, bool long_streams, int cell, FjspCanonState* out, int32_t* order_base = nullptr) {
+    dispatch_layout(cells, long_streams, [&](auto k, auto l) { export_canon_k<decltype(k)::value, decltype(l)::value>(words, P, cell, out, order_base); });
+}
+inline void export_orders(const u32* words, const Params& P, int cells, bool long_streams, int first, int count, int32_t* out4) {
+    dispatch_layout(cells, long_streams, [&](auto k, auto l) { export_orders_k<decltype(k)::value, decltype(l)::value>(words, P, first, count, out4); });
 }
 
 }  // namespace fjsp

@@ -25,12 +25,13 @@ namespace fjsp {
 
 constexpr int TILE = FJSP_TILE_ENVS;  // 64 envs per tile
 
-template <int K>
+template <int K, bool LONG = false>
 struct Geo {
-    static constexpr int WORDS = Lay<K>::TOTAL;                     // u32 per env (128 / 380)
+    static constexpr int WORDS = Lay<K, LONG>::TOTAL;               // u32 per env (compact 128 / 380, long 256 / 520)
     static constexpr int TILE_WORDS = WORDS * TILE;
     static constexpr int TILE_BYTES = TILE_WORDS * 4;               // 32768 / 97280
-    static constexpr int DYN_WORDS = (Lay<K>::DYN_END - W_CSTEP) * TILE;
+    static constexpr int DYN0 = Lay<K, LONG>::DYN0;                 // first word that goes through shared memory
+    static constexpr int DYN_WORDS = (Lay<K, LONG>::DYN_END - DYN0) * TILE;
     static constexpr int DYN_BYTES = DYN_WORDS * 4;                 // 26624 / 75776: through shared memory (one bulk copy)
     static constexpr int OBS_ROW_BYTES = Lay<K>::OBS * 4;           // 152 / 524
     static constexpr int OBS_TILE_BYTES = OBS_ROW_BYTES * TILE;     // 9728 / 33536
@@ -43,16 +44,36 @@ struct Geo {
     static constexpr int X_BYTES = Xl<K>::WORDS * TILE * 4;                       // 6144 for K = 4
     static constexpr int CELLS_SMEM_BYTES = DYN_BYTES + OBS_TILE_BYTES + X_BYTES + 16;       // 115,472 for K = 4: 2 CTAs / SM
     static constexpr int CELLS_WIRE_SMEM_BYTES = DYN_BYTES + WIRE_TILE_BYTES + X_BYTES + 16;
-    static constexpr int CELLS_CTAS_PER_SM = K == 2 ? 3 : 2;
+    static constexpr int CELLS_CTAS_PER_SM = (227 * 1024) / (CELLS_SMEM_BYTES + 1024) >= 3 ? 3 : (227 * 1024) / (CELLS_SMEM_BYTES + 1024) >= 2 ? 2 : 1;
     static constexpr int ROLLOUT_CELLS_SMEM_BYTES = DYN_BYTES + X_BYTES + 16;
 };
 
 // One env of a tile inside a kernel: the dynamically indexed words live in shared memory, column `lane` of the
 // sub-tile; the hot words are read/written straight from/to the HBM tile with compile-time indices (a warp touches 128
 // consecutive bytes per word: coalesced) and otherwise live in registers (struct Hot / HotCell).
-struct TileColumn {
-    u32* dyn;  // &s_dyn[0][lane] - W_CSTEP * TILE, so dyn[w * TILE] is word w
+// Long layout only (fields unused otherwise): where an order's attributes come from when the pickup station pops it —
+// this env's explicit order table, or the Philox order stream — and the arrival stream.
+#define FJSP_ORDER_SOURCE_MEMBERS                                                                          \
+    uint64_t seed = 0, genv = 0;                                                                           \
+    const FjspOrderRec* otab = nullptr;                                                                    \
+    __device__ __forceinline__ u32 fetch_order(int o, u32 episode) const {                                 \
+        if (otab) {                                                                                        \
+            bool bad = false;                                                                              \
+            return order_from_rec(__ldg(otab + o), bad);                                                   \
+        }                                                                                                  \
+        return philox_order(seed, genv, episode, o);                                                       \
+    }                                                                                                      \
+    __device__ __forceinline__ u32 arrival_draw(u32 episode, u32 step) const {                             \
+        u32 r[4];                                                                                          \
+        philox4x32_10((u32)genv, episode, step, 5u, (u32)seed, (u32)(seed >> 32), r);                      \
+        return r[0];                                                                                       \
+    }
+template <bool LONG_ = false>
+struct TileColumnT {
+    static constexpr bool LONG = LONG_;
+    u32* dyn;  // &s_dyn[0][lane] - DYN0 * TILE, so dyn[w * TILE] is word w
     u32* hot;  // &g_tile[0][lane]
+    FJSP_ORDER_SOURCE_MEMBERS
     __device__ __forceinline__ u32 ld(int w) const { return dyn[w * TILE]; }
     __device__ __forceinline__ void st(int w, u32 v) { dyn[w * TILE] = v; }
     __device__ __forceinline__ u32 ld_hot(int w) const { return hot[w * TILE]; }
@@ -63,10 +84,13 @@ struct TileColumn {
         return old;
     }
 };
+using TileColumn = TileColumnT<false>;
 // The same column when the K cells of an env run on K threads (cell-parallel step): order words are shared.
-struct TileColumnShared : TileColumn {
-    __device__ __forceinline__ u32 or_word(int w, u32 v) { return atomicOr(&dyn[w * TILE], v); }
+template <bool LONG_ = false>
+struct TileColumnSharedT : TileColumnT<LONG_> {
+    __device__ __forceinline__ u32 or_word(int w, u32 v) { return atomicOr(&this->dyn[w * TILE], v); }
 };
+using TileColumnShared = TileColumnSharedT<false>;
 // Per-env exchange area of the cell-parallel step (fjsp_core.h "X slots"): column `lane` of a [Xl<K>::WORDS][TILE] block.
 struct XchgColumn {
     u32* x;  // &s_x[0][lane]
@@ -81,8 +105,11 @@ struct XchgColumn {
     __device__ __forceinline__ u32 ld16(int i16) const { return reinterpret_cast<const unsigned short*>(x + (i16 >> 1) * TILE)[i16 & 1]; }
 };
 // Whole column addressed directly in HBM (reset / export paths, not hot).
-struct GmemColumn {
+template <bool LONG_ = false>
+struct GmemColumnT {
+    static constexpr bool LONG = LONG_;
     u32* base;
+    FJSP_ORDER_SOURCE_MEMBERS
     __device__ __forceinline__ u32 ld(int w) const { return base[w * TILE]; }
     __device__ __forceinline__ void st(int w, u32 v) { base[w * TILE] = v; }
     __device__ __forceinline__ u32 ld_hot(int w) const { return base[w * TILE]; }
@@ -136,9 +163,9 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // and store them into the ending lane's shared-memory column; the ending lane itself re-initialises its scalars.
 // A per-lane reset would make the whole warp wait for 32 sequential Philox calls whenever ANY of its envs ends.
 // Must be called by all 32 lanes of the warp.  Returns true for lanes that were reset.
-template <int K>
-__device__ __forceinline__ bool warp_autoreset(TileColumn s, u32* s_dyn, int tid, bool do_reset, u32 cur_episode,
-                                               int num_orders, uint64_t seed, uint64_t genv_lane0) {
+template <int K, class S>
+__device__ __forceinline__ bool warp_autoreset(S s, u32* s_dyn, int tid, bool do_reset, u32 cur_episode, int num_orders, uint64_t seed,
+                                               uint64_t genv_lane0) {
     const unsigned need = __ballot_sync(0xffffffffu, do_reset);
     if (need == 0u) return false;
     const int lane = tid & 31, wbase = tid & ~31;
@@ -147,13 +174,15 @@ __device__ __forceinline__ bool warp_autoreset(TileColumn s, u32* s_dyn, int tid
         episode = cur_episode + 1u;
         reset_env_base<K>(s, num_orders, episode);  // hot words go to the HBM tile; the caller reloads its registers
     }
-    unsigned rem = need;
-    while (rem) {
-        const int src = __ffs((int)rem) - 1;
-        rem &= rem - 1u;
-        const u32 ep = __shfl_sync(0xffffffffu, episode, src);
-        const u32 ow = lane < num_orders ? philox_order(seed, genv_lane0 + (uint64_t)src, ep, lane) : 0u;
-        s_dyn[(W_ORDER - W_CSTEP + lane) * TILE + wbase + src] = ow;
+    if (!S::LONG) {  // (the long layout's ring fills as the pickup station pops orders: nothing to draw at reset)
+        unsigned rem = need;
+        while (rem) {
+            const int src = __ffs((int)rem) - 1;
+            rem &= rem - 1u;
+            const u32 ep = __shfl_sync(0xffffffffu, episode, src);
+            const u32 ow = lane < num_orders ? philox_order(seed, genv_lane0 + (uint64_t)src, ep, lane) : 0u;
+            s_dyn[(W_ORDER - W_CSTEP + lane) * TILE + wbase + src] = ow;
+        }
     }
     __syncwarp();
     return do_reset;
@@ -175,21 +204,23 @@ struct StepArgs {
     int32_t num_orders, autoreset;
     int32_t prefetch_tiles;  // cell-parallel kernel: L2-prefetch the tile this many CTAs ahead (0 = off)
     int32_t prefetch_tiles_env;  // the same for the thread-per-env kernel
+    const FjspOrderRec* otab;    // long layout: explicit order tables [N][otab_stride], or null = Philox order stream
+    int32_t otab_stride;
 };
 
 // ---------------------------------------------------------------------------------------------
 // Reset: FJSPSimulation.reset for the masked envs.  Thread per env, state addressed in place.
 // ---------------------------------------------------------------------------------------------
-template <int K>
+template <int K, bool LONG>
 __global__ void __launch_bounds__(TILE) fjsp_reset_kernel(const __grid_constant__ Params P, u32* state, const uint8_t* env_mask,
-                                                           const FjspOrderRec* orders, int num_orders, uint64_t seed,
+                                                           const FjspOrderRec* orders, int orders_stride, int num_orders, uint64_t seed,
                                                            int64_t num_envs, int64_t first_env, float* obs, int8_t* masks) {
     const int64_t env = (int64_t)blockIdx.x * TILE + threadIdx.x;
     const bool pad = env >= num_envs;
     if (!pad && env_mask && env_mask[env] == 0) return;
-    GmemColumn s{state + (int64_t)blockIdx.x * Geo<K>::TILE_WORDS + threadIdx.x};
-    reset_env<K>(s, P, pad ? 0 : num_orders, (pad || !orders) ? nullptr : orders + env * FJSP_MAX_ORDERS, seed,
-                 (uint64_t)(first_env + env), 0u);
+    GmemColumnT<LONG> s{state + (int64_t)blockIdx.x * Geo<K, LONG>::TILE_WORDS + threadIdx.x};
+    s.seed = seed, s.genv = (uint64_t)(first_env + env), s.otab = (pad || !orders) ? nullptr : orders + env * orders_stride;
+    reset_env<K>(s, P, pad ? 0 : num_orders, s.otab, seed, (uint64_t)(first_env + env), 0u);
     if (pad) return;
     if (obs && masks) {
         float o[Lay<K>::OBS];
@@ -201,6 +232,12 @@ __global__ void __launch_bounds__(TILE) fjsp_reset_kernel(const __grid_constant_
 #pragma unroll
         for (int i = 0; i < Lay<K>::MASK / 16; i++) m4[i] = make_uint4(mw[4 * i], mw[4 * i + 1], mw[4 * i + 2], mw[4 * i + 3]);
     }
+}
+
+// rows of `src` ([n][width]) whose env is selected by `mask` replace the same rows of `dst` (masked reset of explicit order tables)
+__global__ void fjsp_copy_masked_rows_kernel(FjspOrderRec* dst, const FjspOrderRec* src, const uint8_t* mask, int64_t n, int width) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n * width && mask[i / width]) dst[i] = src[i];
 }
 
 template <int K>
@@ -217,34 +254,36 @@ __device__ __forceinline__ void load_actions(const uint8_t* actions, int64_t env
 // ---------------------------------------------------------------------------------------------
 // Step: one CTA = one tile of 64 envs; one launch = one lockstep step of all envs.
 // ---------------------------------------------------------------------------------------------
-template <int K, bool WIRE>
+template <int K, bool WIRE, bool LONG = false>
 __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__ Params P, const StepArgs A) {
-    constexpr int OUT_ROW_BYTES = WIRE ? Geo<K>::WIRE_ROW_BYTES : Geo<K>::OBS_ROW_BYTES;   // staged row per env
+    using G = Geo<K, LONG>;
+    constexpr int OUT_ROW_BYTES = WIRE ? G::WIRE_ROW_BYTES : G::OBS_ROW_BYTES;   // staged row per env
     constexpr int OUT_TILE_BYTES = OUT_ROW_BYTES * TILE;
     constexpr int MODE = WIRE ? OBS_WIRE : OBS_FLOAT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u32* s_dyn = reinterpret_cast<u32*>(smem_raw);
-    u32* s_out = reinterpret_cast<u32*>(smem_raw + Geo<K>::DYN_BYTES);  // float observations, or wire rows
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + Geo<K>::DYN_BYTES + OUT_TILE_BYTES);
+    u32* s_out = reinterpret_cast<u32*>(smem_raw + G::DYN_BYTES);  // float observations, or wire rows
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + G::DYN_BYTES + OUT_TILE_BYTES);
 
     const int tid = threadIdx.x;
     const int64_t tile = A.tile_begin + blockIdx.x;
     const int64_t env = tile * TILE + tid;
     const bool valid = env < A.num_envs;
-    u32* g_tile = A.state + tile * Geo<K>::TILE_WORDS;
+    u32* g_tile = A.state + tile * G::TILE_WORDS;
 
     if (tid == 0) {  // ONE bulk async copy (TMA engine) for the dynamically indexed words of the tile
         mbar_init(bar, 1);
-        mbar_expect_tx(bar, Geo<K>::DYN_BYTES);
-        bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, Geo<K>::DYN_BYTES, bar);
+        mbar_expect_tx(bar, G::DYN_BYTES);
+        bulk_g2s(s_dyn, g_tile + G::DYN0 * TILE, G::DYN_BYTES, bar);
     }
     if (tid == 32 && A.prefetch_tiles_env > 0) {  // L2 prefetch of the tile a later CTA of this SM will load
         const int64_t nt = (int64_t)blockIdx.x + A.prefetch_tiles_env;
-        if (nt < (int64_t)gridDim.x) bulk_prefetch_l2(g_tile + (int64_t)A.prefetch_tiles_env * Geo<K>::TILE_WORDS, Geo<K>::TILE_BYTES);
+        if (nt < (int64_t)gridDim.x) bulk_prefetch_l2(g_tile + (int64_t)A.prefetch_tiles_env * G::TILE_WORDS, G::TILE_BYTES);
     }
     // meanwhile: the hot words of the pickup station and of cell 0 (coalesced 32-bit loads, straight into registers)
     // and the action bytes
-    TileColumn s{s_dyn + tid - W_CSTEP * TILE, g_tile + tid};
+    TileColumnT<LONG> s{s_dyn + tid - G::DYN0 * TILE, g_tile + tid};
+    s.seed = A.seed, s.genv = (uint64_t)(A.first_env + env), s.otab = (A.otab && valid) ? A.otab + env * A.otab_stride : nullptr;
     Hot h;
     HotCell c0;
     load_hot(s, h);
@@ -302,7 +341,7 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
     u32* g_out = WIRE ? A.wire + tile * TILE * Wire<K>::WORDS : reinterpret_cast<u32*>(A.obs + tile * TILE * Lay<K>::OBS);
     const bool out_bulk = ((nvalid * OUT_ROW_BYTES) & 15) == 0 && ((reinterpret_cast<uintptr_t>(g_out) & 15) == 0);
     if (tid == 0) {
-        bulk_s2g(g_tile + W_CSTEP * TILE, s_dyn, Geo<K>::DYN_BYTES);
+        bulk_s2g(g_tile + G::DYN0 * TILE, s_dyn, G::DYN_BYTES);
         if (out_bulk) bulk_s2g(g_out, s_out, (uint32_t)(nvalid * OUT_ROW_BYTES));
         bulk_commit();
     }
@@ -319,38 +358,40 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
 // 32-bit loads.  The thread-per-env kernel above keeps 4 warps per SM resident at K = 4 (the tile's 76 KB of tray pools
 // set the limit) and is latency-bound at 0.27 of the HBM roofline; this one keeps 16.
 // ---------------------------------------------------------------------------------------------
-template <int K, bool WIRE>
-__global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_step_cells_kernel(const __grid_constant__ Params P, const StepArgs A) {
+template <int K, bool WIRE, bool LONG = false>
+__global__ void __launch_bounds__(TILE* K, Geo<K, LONG>::CELLS_CTAS_PER_SM) fjsp_step_cells_kernel(const __grid_constant__ Params P, const StepArgs A) {
+    using G = Geo<K, LONG>;
     constexpr int NT = TILE * K;
-    constexpr int OUT_ROW_BYTES = WIRE ? Geo<K>::WIRE_ROW_BYTES : Geo<K>::OBS_ROW_BYTES;
+    constexpr int OUT_ROW_BYTES = WIRE ? G::WIRE_ROW_BYTES : G::OBS_ROW_BYTES;
     constexpr int OUT_TILE_BYTES = OUT_ROW_BYTES * TILE;
     constexpr int AG = Lay<K>::AGENTS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u32* s_dyn = reinterpret_cast<u32*>(smem_raw);
-    u32* s_out = reinterpret_cast<u32*>(smem_raw + Geo<K>::DYN_BYTES);
-    u32* s_x = reinterpret_cast<u32*>(smem_raw + Geo<K>::DYN_BYTES + OUT_TILE_BYTES);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + Geo<K>::DYN_BYTES + OUT_TILE_BYTES + Geo<K>::X_BYTES);
+    u32* s_out = reinterpret_cast<u32*>(smem_raw + G::DYN_BYTES);
+    u32* s_x = reinterpret_cast<u32*>(smem_raw + G::DYN_BYTES + OUT_TILE_BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + G::DYN_BYTES + OUT_TILE_BYTES + G::X_BYTES);
 
     const int tid = threadIdx.x;
     const int c = tid / TILE, e = tid % TILE;  // c is uniform over a warp
     const int64_t tile = A.tile_begin + blockIdx.x;
     const int64_t env = tile * TILE + e;
     const bool valid = env < A.num_envs;
-    u32* g_tile = A.state + tile * Geo<K>::TILE_WORDS;
+    u32* g_tile = A.state + tile * G::TILE_WORDS;
 
     if (tid == 0) {  // the tile's bulk copy is under way before anything else happens in the CTA
         mbar_init(bar, 1);
-        mbar_expect_tx(bar, Geo<K>::DYN_BYTES);
-        bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, Geo<K>::DYN_BYTES, bar);
+        mbar_expect_tx(bar, G::DYN_BYTES);
+        bulk_g2s(s_dyn, g_tile + G::DYN0 * TILE, G::DYN_BYTES, bar);
     }
     if (tid == 32 && A.prefetch_tiles > 0) {
         // the tile this SM will work on about one CTA generation from now goes to L2 meanwhile: its hot-word loads and
         // its bulk copy then start from L2 instead of HBM (with 2 CTAs per SM the start-up latency is not hidden otherwise)
         const int64_t nt = (int64_t)blockIdx.x + A.prefetch_tiles;
-        if (nt < (int64_t)gridDim.x) bulk_prefetch_l2(g_tile + (int64_t)A.prefetch_tiles * Geo<K>::TILE_WORDS, Geo<K>::TILE_BYTES);
+        if (nt < (int64_t)gridDim.x) bulk_prefetch_l2(g_tile + (int64_t)A.prefetch_tiles * G::TILE_WORDS, G::TILE_BYTES);
     }
-    TileColumnShared s;
-    s.dyn = s_dyn + e - W_CSTEP * TILE, s.hot = g_tile + e;
+    TileColumnSharedT<LONG> s;
+    s.dyn = s_dyn + e - G::DYN0 * TILE, s.hot = g_tile + e;
+    s.seed = A.seed, s.genv = (uint64_t)(A.first_env + env), s.otab = (A.otab && valid) ? A.otab + env * A.otab_stride : nullptr;
     XchgColumn x{s_x + e};
     CellLane L;
     L.c = c;
@@ -373,7 +414,7 @@ __global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_step_
     __syncthreads();
     int32_t info[4] = {0, 0, 0, 0};
     L.flags = 0u, L.g = 0;
-    if (valid) cells_finish<K>(x, P, L, info);
+    if (valid) cells_finish<K, TileColumnSharedT<LONG>>(x, P, L, info);
     const bool ended = valid && A.autoreset && (L.flags & 0x00ffffffu);
     if (__syncthreads_or(ended)) {
         // the two warps of cell 0 reset the ended envs (all hot words of all cells go to the HBM tile, pools and orders
@@ -438,7 +479,7 @@ __global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_step_
     u32* g_out = WIRE ? A.wire + tile * TILE * Wire<K>::WORDS : reinterpret_cast<u32*>(A.obs + tile * TILE * Lay<K>::OBS);
     const bool out_bulk = ((nvalid * OUT_ROW_BYTES) & 15) == 0 && ((reinterpret_cast<uintptr_t>(g_out) & 15) == 0);
     if (tid == 0) {
-        bulk_s2g(g_tile + W_CSTEP * TILE, s_dyn, Geo<K>::DYN_BYTES);
+        bulk_s2g(g_tile + G::DYN0 * TILE, s_dyn, G::DYN_BYTES);
         if (out_bulk) bulk_s2g(g_out, s_out, (uint32_t)(nvalid * OUT_ROW_BYTES));
         bulk_commit();
     }
@@ -469,27 +510,29 @@ __global__ void fjsp_random_actions_kernel(uint8_t* actions, int64_t num_envs, i
 // Rollout: `steps` lockstep steps per launch with in-kernel Philox actions and auto-reset; the tile stays in
 // shared memory between steps, so HBM sees the state once per `steps` steps.  Accumulates exact integer stats.
 // ---------------------------------------------------------------------------------------------
-template <int K>
+template <int K, bool LONG = false>
 __global__ void __launch_bounds__(TILE) fjsp_rollout_kernel(const __grid_constant__ Params P, u32* state, int64_t num_envs,
                                                              int64_t first_env, uint64_t seed, uint64_t t0, int steps,
                                                              int num_orders, unsigned long long* stats) {
+    using G = Geo<K, LONG>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u32* s_dyn = reinterpret_cast<u32*>(smem_raw);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + Geo<K>::DYN_BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + G::DYN_BYTES);
     __shared__ unsigned long long s_acc[6];
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
     const int64_t env = tile * TILE + tid;
     const bool valid = env < num_envs;
-    u32* g_tile = state + tile * Geo<K>::TILE_WORDS;
+    u32* g_tile = state + tile * G::TILE_WORDS;
     if (tid == 0) mbar_init(bar, 1);
     if (tid < 6) s_acc[tid] = 0ull;
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(bar, Geo<K>::DYN_BYTES);
-        bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, Geo<K>::DYN_BYTES, bar);
+        mbar_expect_tx(bar, G::DYN_BYTES);
+        bulk_g2s(s_dyn, g_tile + G::DYN0 * TILE, G::DYN_BYTES, bar);
     }
-    TileColumn s{s_dyn + tid - W_CSTEP * TILE, g_tile + tid};
+    TileColumnT<LONG> s{s_dyn + tid - G::DYN0 * TILE, g_tile + tid};
+    s.seed = seed, s.genv = (uint64_t)(first_env + env);
     Hot h;  // hot words of the pickup station and of cell 0 live in registers for the whole launch
     HotCell c0;
     load_hot(s, h);
@@ -536,7 +579,7 @@ __global__ void __launch_bounds__(TILE) fjsp_rollout_kernel(const __grid_constan
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
-        bulk_s2g(g_tile + W_CSTEP * TILE, s_dyn, Geo<K>::DYN_BYTES);
+        bulk_s2g(g_tile + G::DYN0 * TILE, s_dyn, G::DYN_BYTES);
         bulk_commit();
     }
     if (tid < 6) atomicAdd(&stats[tid], s_acc[tid]);
@@ -549,32 +592,34 @@ __global__ void __launch_bounds__(TILE) fjsp_rollout_kernel(const __grid_constan
 // the pickup station's) in registers; per step: Philox actions for the lane's own agents, the three phases of the
 // cell-parallel step (no observation), the cooperative reset by the two warps of cell 0, and a fresh exchange area.
 // ---------------------------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_rollout_cells_kernel(const __grid_constant__ Params P, u32* state,
+template <int K, bool LONG = false>
+__global__ void __launch_bounds__(TILE* K, Geo<K, LONG>::CELLS_CTAS_PER_SM) fjsp_rollout_cells_kernel(const __grid_constant__ Params P, u32* state,
                                                                                                 int64_t num_envs, int64_t first_env,
                                                                                                 uint64_t seed, uint64_t t0, int steps,
                                                                                                 int num_orders, unsigned long long* stats) {
+    using G = Geo<K, LONG>;
     constexpr int NT = TILE * K;
     constexpr int AG = Lay<K>::AGENTS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u32* s_dyn = reinterpret_cast<u32*>(smem_raw);
-    u32* s_x = reinterpret_cast<u32*>(smem_raw + Geo<K>::DYN_BYTES);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + Geo<K>::DYN_BYTES + Geo<K>::X_BYTES);
+    u32* s_x = reinterpret_cast<u32*>(smem_raw + G::DYN_BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + G::DYN_BYTES + G::X_BYTES);
     __shared__ unsigned long long s_acc[6];
     const int tid = threadIdx.x;
     const int c = tid / TILE, e = tid % TILE;
     const int64_t tile = blockIdx.x;
     const int64_t env = tile * TILE + e;
     const bool valid = env < num_envs;
-    u32* g_tile = state + tile * Geo<K>::TILE_WORDS;
+    u32* g_tile = state + tile * G::TILE_WORDS;
     if (tid == 0) {
         mbar_init(bar, 1);
-        mbar_expect_tx(bar, Geo<K>::DYN_BYTES);
-        bulk_g2s(s_dyn, g_tile + W_CSTEP * TILE, Geo<K>::DYN_BYTES, bar);
+        mbar_expect_tx(bar, G::DYN_BYTES);
+        bulk_g2s(s_dyn, g_tile + G::DYN0 * TILE, G::DYN_BYTES, bar);
     }
     if (tid < 6) s_acc[tid] = 0ull;
-    TileColumnShared s;
-    s.dyn = s_dyn + e - W_CSTEP * TILE, s.hot = g_tile + e;
+    TileColumnSharedT<LONG> s;
+    s.dyn = s_dyn + e - G::DYN0 * TILE, s.hot = g_tile + e;
+    s.seed = seed, s.genv = (uint64_t)(first_env + env);
     XchgColumn x{s_x + e};
     CellLane L;
     L.c = c;
@@ -607,7 +652,7 @@ __global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_rollo
         bool ended = false;
         if (valid) {
             int32_t info[4];
-            cells_finish<K>(x, P, L, info);
+            cells_finish<K, TileColumnSharedT<LONG>>(x, P, L, info);
 #pragma unroll
             for (int i = 1; i < 8; i++) units += L.g + AG * L.local10[i];
             if (c == 0) {
@@ -645,7 +690,7 @@ __global__ void __launch_bounds__(TILE* K, Geo<K>::CELLS_CTAS_PER_SM) fjsp_rollo
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
-        bulk_s2g(g_tile + W_CSTEP * TILE, s_dyn, Geo<K>::DYN_BYTES);
+        bulk_s2g(g_tile + G::DYN0 * TILE, s_dyn, G::DYN_BYTES);
         bulk_commit();
     }
     if (tid < 6) atomicAdd(&stats[tid], s_acc[tid]);

@@ -143,42 +143,58 @@ constexpr int G_THREADS = G_PRODUCERS + 32;
 
 __device__ __forceinline__ uint32_t plane_off(int r, int q, int lbo) { return (uint32_t)(q * lbo + (r >> 3) * 128 + (r & 7) * 16); }
 
-// fp32 -> (hi, lo) with hi = the nearest TF32 (round half away: one integer add + mask) and lo = tf32(x - hi); x - hi is
-// exact in fp32.
+// fp32 -> (hi, lo) with hi = the nearest TF32 (round half away: one integer add + mask) and lo = x - hi (exact in fp32),
+// of which the tensor core reads the leading 11 bits.
 // (cvt.rna.tf32.f32 would do the same rounding on the XU pipe at 16 lanes per clock per SM: two of them per element made
 // the conversion, not the MMAs, the limiter of the first version of this kernel — ncu: xu pipe saturated, tensor 18 %.)
 __device__ __forceinline__ uint32_t tf32_hi(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+template <bool ROUND_LO>
 __device__ __forceinline__ void split_store(unsigned char* hi, unsigned char* lo, uint32_t off, float4 v, bool three) {
     const uint4 h = make_uint4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
     *reinterpret_cast<uint4*>(hi + off) = h;
     if (three) {
-        // lo is rounded to TF32 as well: left to the hardware it would be CUT to 11 bits, a bias that adds up linearly
-        // over the K = batch-size sums of the weight gradients
-        const uint4 l = make_uint4(tf32_hi(v.x - __uint_as_float(h.x)), tf32_hi(v.y - __uint_as_float(h.y)),
-                                   tf32_hi(v.z - __uint_as_float(h.z)), tf32_hi(v.w - __uint_as_float(h.w)));
-        *reinterpret_cast<uint4*>(lo + off) = l;
+        const float4 l = make_float4(v.x - __uint_as_float(h.x), v.y - __uint_as_float(h.y), v.z - __uint_as_float(h.z),
+                                     v.w - __uint_as_float(h.w));
+        if (ROUND_LO) {
+            // lo rounded to TF32 as well: left to the hardware it is CUT to 11 bits, a bias that adds up linearly over the
+            // K = batch-size sums of the weight gradients (there the two extra integer ops per element are spent)
+            *reinterpret_cast<uint4*>(lo + off) = make_uint4(tf32_hi(l.x), tf32_hi(l.y), tf32_hi(l.z), tf32_hi(l.w));
+        } else {
+            *reinterpret_cast<float4*>(lo + off) = l;
+        }
     }
 }
 
 // One operand tile of ROWS rows x G_KC k, fetched into registers (`fetch`) and later split + stored (`stash`).
-template <int OP, int ROWS>
+template <int OP, int ROWS, bool ROUND_LO>
 struct Loader {
     static constexpr int ITEMS = OP == OP_MC ? (ROWS == 128 ? G_NQ / 2 : G_NQ) : ROWS * G_NQ / G_PRODUCERS;
     float4 v[ITEMS];
     __device__ __forceinline__ void fetch(const float* __restrict__ X, int ld, int r0, int rmax, int k0, int kmax, int tid) {
+        const bool kfull = k0 + G_KC <= kmax;  // uniform: interior stages need no per-element K guards
         if (OP == OP_MC) {
             // thread -> one row r (contiguous across the warp), a few K-quads; 4 coalesced scalar loads per quad
             const int r = ROWS == 128 ? (tid & 127) : tid;
             const int qb = ROWS == 128 ? (tid >> 7) : 0, qs = ROWS == 128 ? 2 : 1;
             const bool rok = r0 + r < rmax;
+            const float* p0 = X + (int64_t)(k0 + 4 * qb) * ld + r0 + r;
+            const int64_t qstep = (int64_t)4 * qs * ld;
+            if (kfull && rok) {
 #pragma unroll
-            for (int i = 0; i < ITEMS; i++) {
-                const int k = k0 + 4 * (qb + qs * i);
-                const float* p = X + (int64_t)k * ld + r0 + r;
-                v[i].x = (rok && k + 0 < kmax) ? __ldg(p) : 0.f;
-                v[i].y = (rok && k + 1 < kmax) ? __ldg(p + ld) : 0.f;
-                v[i].z = (rok && k + 2 < kmax) ? __ldg(p + 2 * (int64_t)ld) : 0.f;
-                v[i].w = (rok && k + 3 < kmax) ? __ldg(p + 3 * (int64_t)ld) : 0.f;
+                for (int i = 0; i < ITEMS; i++) {
+                    const float* p = p0 + i * qstep;
+                    v[i] = make_float4(__ldg(p), __ldg(p + ld), __ldg(p + 2 * (int64_t)ld), __ldg(p + 3 * (int64_t)ld));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < ITEMS; i++) {
+                    const int k = k0 + 4 * (qb + qs * i);
+                    const float* p = p0 + i * qstep;
+                    v[i].x = (rok && k + 0 < kmax) ? __ldg(p) : 0.f;
+                    v[i].y = (rok && k + 1 < kmax) ? __ldg(p + ld) : 0.f;
+                    v[i].z = (rok && k + 2 < kmax) ? __ldg(p + 2 * (int64_t)ld) : 0.f;
+                    v[i].w = (rok && k + 3 < kmax) ? __ldg(p + 3 * (int64_t)ld) : 0.f;
+                }
             }
         } else {
             // thread -> (row, K-quad) with the quad index fastest: a warp reads 8 rows x 64 contiguous bytes
@@ -190,6 +206,8 @@ struct Loader {
                 const bool rok = r0 + r < rmax;
                 if (OP == OP_KC) {
                     v[i] = (rok && k < kmax) ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else if (kfull && rok) {
+                    v[i] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
                 } else {
                     v[i].x = (rok && k + 0 < kmax) ? __ldg(p) : 0.f;
                     v[i].y = (rok && k + 1 < kmax) ? __ldg(p + 1) : 0.f;
@@ -204,12 +222,12 @@ struct Loader {
             const int r = ROWS == 128 ? (tid & 127) : tid;
             const int qb = ROWS == 128 ? (tid >> 7) : 0, qs = ROWS == 128 ? 2 : 1;
 #pragma unroll
-            for (int i = 0; i < ITEMS; i++) split_store(hi, lo, plane_off(r, qb + qs * i, lbo), v[i], three);
+            for (int i = 0; i < ITEMS; i++) split_store<ROUND_LO>(hi, lo, plane_off(r, qb + qs * i, lbo), v[i], three);
         } else {
 #pragma unroll
             for (int i = 0; i < ITEMS; i++) {
                 const int idx = tid + i * G_PRODUCERS;
-                split_store(hi, lo, plane_off(idx / G_NQ, idx % G_NQ, lbo), v[i], three);
+                split_store<ROUND_LO>(hi, lo, plane_off(idx / G_NQ, idx % G_NQ, lbo), v[i], three);
             }
         }
     }
@@ -286,8 +304,12 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
 
     if (warp < G_PRODUCERS / 32) {
         // ===== producers: global fp32 -> registers -> (hi, lo) tf32 -> shared memory, one stage ahead in registers =====
-        Loader<AOP, G_BM> la;
-        Loader<BOP, G_BN> lb;
+        // lo terms rounded (not cut) to TF32 everywhere: two integer ops per element buy unbiased errors, which matters
+        // when gradients flow through three chained GEMMs and are then summed over the batch (critic W2: 2.6e-4 of the
+        // largest gradient with cut lo terms, measured against float64)
+        constexpr bool ROUND_LO = true;
+        Loader<AOP, G_BM, ROUND_LO> la;
+        Loader<BOP, G_BN, ROUND_LO> lb;
         la.fetch(P.A, P.lda, m0, P.M, c_begin * G_KC, P.K, tid);
         lb.fetch(P.B, P.ldb, 0, P.N, c_begin * G_KC, P.K, tid);
         for (int c = 0; c < nchunks; c++) {

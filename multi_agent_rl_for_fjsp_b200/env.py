@@ -140,7 +140,7 @@ class BatchedFJSPEnv:
             if self.autoreset:
                 raise ValueError("explicit order tables describe ONE episode; with autoreset=True every later episode would "
                                  "silently draw Philox orders instead — create the env with autoreset=False to use them")
-            d_orders = self._pack_orders(orders)
+            d_orders = self._pack_orders(orders, env_mask)
         d_mask = None
         if env_mask is not None:
             d_mask = torch.as_tensor(env_mask, device=self.device).to(torch.uint8).contiguous()
@@ -151,7 +151,7 @@ class BatchedFJSPEnv:
         self._keep = (d_orders, d_mask)  # keep the buffers alive until the stream has consumed them
         return self.obs, self.masks
 
-    def _pack_orders(self, orders):
+    def _pack_orders(self, orders, env_mask=None):
         arr = orders.detach().cpu().numpy() if isinstance(orders, torch.Tensor) else np.asarray(orders)
         if arr.ndim == 3:  # [N, k, 3] -> packed [N, 32]
             n, k, _ = arr.shape
@@ -164,6 +164,8 @@ class BatchedFJSPEnv:
         arr = np.ascontiguousarray(arr, dtype=np.uint32)
         assert arr.shape == (self.num_envs, abi.MAX_ORDERS), arr.shape
         live = arr[:, :self.num_orders]
+        if env_mask is not None:  # only the rows of the envs being reset are read
+            live = live[np.asarray(env_mask.cpu() if isinstance(env_mask, torch.Tensor) else env_mask).astype(bool).reshape(-1)]
         n, ty, co = live & 0xff, (live >> 8) & 0xff, (live >> 16) & 0xff
         if live.size and not (((n >= 1) & (n <= 9) & (ty >= 1) & (ty <= 3) & (co >= 1) & (co <= 3) & ((live >> 24) == 0)).all()):
             raise ValueError("order records must have n in 1..9, type in 1..3, colour in 1..3 (FJSPSimulation.py:107-112)")

@@ -31,6 +31,7 @@ class FjspConfig(C.Structure):
         ("step_size", C.c_int32), ("agv_speed", C.c_int32), ("max_episode_steps", C.c_int32),
         ("storage_capacity", C.c_int32), ("pack_capacity", C.c_int32),
         ("tray_capacity", C.c_int32), ("num_trays", C.c_int32), ("num_cells", C.c_int32),
+        ("long_streams", C.c_int32), ("arrival_prob_q16", C.c_int32), ("arrival_max_orders", C.c_int32),
     ]
 
 

@@ -13,20 +13,31 @@ using namespace fjsp;
 struct HostEnv {
     Params P;
     int cells;
-    u32 words[FJSP_STATE_WORDS_K(FJSP_MAX_CELLS)];
+    bool long_streams;
+    uint64_t seed, genv;                       // long layout: order / arrival streams
+    FjspOrderRec otab[FJSP_LONG_MAX_ORDERS];   // long layout: explicit order table of the current episode
+    int otab_n;
+    u32 words[FJSP_STATE_WORDS_LONG_K(FJSP_MAX_CELLS)];
 };
 
-#define DISPATCH_K(e, ...)                                  \
+#define DISPATCH_K1(e, ...)                                  \
     switch ((e)->cells) {                                   \
         case 1: { constexpr int K = 1; __VA_ARGS__; } break;  \
         case 2: { constexpr int K = 2; __VA_ARGS__; } break;  \
         case 3: { constexpr int K = 3; __VA_ARGS__; } break;  \
         default: { constexpr int K = 4; __VA_ARGS__; } break; \
     }
+// K and the layout; `s` is the env's word accessor of the matching type
+#define DISPATCH_K(e, ...)                                                                       \
+    if ((e)->long_streams) { constexpr bool LONG = true; auto s = env_state<true>(e); (void)LONG; (void)s; DISPATCH_K1(e, __VA_ARGS__) } \
+    else { constexpr bool LONG = false; auto s = env_state<false>(e); (void)LONG; (void)s; DISPATCH_K1(e, __VA_ARGS__) }
 
-static ArrayState env_state(HostEnv* e) {
-    ArrayState s{e->words};
-    s.dyn_end = 64 + 64 * e->cells, s.total = FJSP_STATE_WORDS_K(e->cells);
+static int state_words(const HostEnv* e) { return e->long_streams ? FJSP_STATE_WORDS_LONG_K(e->cells) : FJSP_STATE_WORDS_K(e->cells); }
+template <bool LONG>
+static ArrayStateT<LONG> env_state(HostEnv* e) {
+    ArrayStateT<LONG> s{e->words};
+    s.dyn_end = WM<LONG>::W_POOL + 64 * e->cells, s.total = state_words(e);
+    s.seed = e->seed, s.genv = e->genv, s.otab = e->otab_n > 0 ? e->otab : nullptr;
     return s;
 }
 
@@ -41,6 +52,7 @@ void* hh_create(const FjspConfig* cfg) {
         return nullptr;
     }
     e->cells = c.num_cells;
+    e->long_streams = c.long_streams != 0;
     return e;
 }
 const char* hh_check_config(const FjspConfig* cfg) {
@@ -63,7 +75,6 @@ static void unpack_bytes(const u32* w, int n, uint8_t* dst) {
 
 void hh_observe(void* p, float* obs, int8_t* masks) {
     HostEnv* e = (HostEnv*)p;
-    ArrayState s = env_state(e);
     DISPATCH_K(e, {
         u32 mw[Lay<K>::MASK / 4];
         observe_env<K>(s, e->P, obs, mw);
@@ -73,14 +84,18 @@ void hh_observe(void* p, float* obs, int8_t* masks) {
 
 void hh_reset(void* p, const FjspOrderRec* orders, int num_orders, uint64_t seed, uint64_t genv, uint32_t episode) {
     HostEnv* e = (HostEnv*)p;
-    ArrayState s = env_state(e);
+    e->seed = seed, e->genv = genv, e->otab_n = 0;
+    if (e->long_streams && orders) {  // the ring fills as orders are popped: keep the table for the episode
+        e->otab_n = num_orders;
+        memcpy(e->otab, orders, sizeof(FjspOrderRec) * (size_t)num_orders);
+        orders = e->otab;
+    }
     DISPATCH_K(e, reset_env<K>(s, e->P, num_orders, orders, seed, genv, episode))
 }
 
 void hh_step(void* p, const uint8_t* actions, float* obs, int8_t* masks, float* rewards, uint8_t* flags, uint8_t* results,
              int32_t* infos) {
     HostEnv* e = (HostEnv*)p;
-    ArrayState s = env_state(e);
     DISPATCH_K(e, {
         int a[Lay<K>::ACT];
         for (int i = 0; i < Lay<K>::ACT; i++) a[i] = actions[i];
@@ -99,10 +114,10 @@ void hh_step(void* p, const uint8_t* actions, float* obs, int8_t* masks, float* 
 // the same step twice from the same state: once into float tensors, once into a wire row (state advanced once)
 void hh_step_wire(void* p, const uint8_t* actions, float* obs, int8_t* masks, float* rewards, uint8_t* flags, uint32_t* wire) {
     HostEnv* e = (HostEnv*)p;
-    HostEnv copy = *e;
+    static thread_local HostEnv copy;
+    copy = *e;
     hh_step(p, actions, obs, masks, rewards, flags, nullptr, nullptr);
-    ArrayState s = env_state(&copy);
-    DISPATCH_K(e, {
+    DISPATCH_K(&copy, {
         int a[Lay<K>::ACT];
         for (int i = 0; i < Lay<K>::ACT; i++) a[i] = actions[i];
         StepOut<K> out;
@@ -124,7 +139,6 @@ int hh_step_cells(void* p, const uint8_t* actions, float* obs, int8_t* masks, fl
             u32 xw[Xl<K>::WORDS];
             for (int i = 0; i < Xl<K>::WORDS; i++) xw[i] = 0u;
             ArrayXchg x{xw};
-            ArrayState s = env_state(e);
             CellLane L[K];
             int a7[K][7];
             for (int c = 0; c < K; c++) {
@@ -136,7 +150,7 @@ int hh_step_cells(void* p, const uint8_t* actions, float* obs, int8_t* masks, fl
             int32_t info[K][4];
             for (int i = 0; i < K; i++) { const int c = reverse ? K - 1 - i : i; cells_begin<K>(s, x, e->P, L[c], actions[0], a7[c]); }
             for (int i = 0; i < K; i++) { const int c = reverse ? K - 1 - i : i; cells_act_run<K>(s, x, e->P, L[c], a7[c]); }
-            for (int i = 0; i < K; i++) { const int c = reverse ? K - 1 - i : i; cells_finish<K>(x, e->P, L[c], info[c]); }
+            for (int i = 0; i < K; i++) { const int c = reverse ? K - 1 - i : i; cells_finish<K, ArrayStateT<LONG>>(x, e->P, L[c], info[c]); }
             for (int i = 0; i < K; i++) {
                 const int c = reverse ? K - 1 - i : i;
                 cells_observe<K>(s, x, e->P, L[c], FloatSink{obs, e->P}, FloatSink{obs + 7 + 31 * c, e->P});
@@ -167,9 +181,17 @@ int hh_step_cells(void* p, const uint8_t* actions, float* obs, int8_t* masks, fl
 
 void hh_export(void* p, int cell, FjspCanonState* out) {
     HostEnv* e = (HostEnv*)p;
-    export_canon(e->words, e->P, e->cells, cell, out);
+    export_canon(e->words, e->P, e->cells, e->long_streams, cell, out);
 }
-void hh_words(void* p, uint32_t* out) { memcpy(out, ((HostEnv*)p)->words, sizeof(u32) * FJSP_STATE_WORDS_K(((HostEnv*)p)->cells)); }
+void hh_export_orders(void* p, int first, int count, int32_t* out4, int32_t* order_base) {
+    HostEnv* e = (HostEnv*)p;
+    export_orders(e->words, e->P, e->cells, e->long_streams, first, count, out4);
+    if (order_base) {
+        FjspCanonState c;
+        export_canon(e->words, e->P, e->cells, e->long_streams, 0, &c, order_base);
+    }
+}
+void hh_words(void* p, uint32_t* out) { memcpy(out, ((HostEnv*)p)->words, sizeof(u32) * state_words((HostEnv*)p)); }
 
 void hh_philox_actions(uint64_t seed, uint64_t genv, uint64_t t, int cells, uint8_t* out) {
     int a[FJSP_ACT_DIM_K(FJSP_MAX_CELLS)] = {0};

@@ -210,7 +210,7 @@ def test_umma_update_equals_autograd_update(n_envs, T):
     for (na, pa), (nb, pb), g in zip(a.net.named_parameters(), b.net.named_parameters(), g64):
         scale = g.abs().max().item() + 1e-12
         err_a, err_b = (pa.grad.double() - g).abs().max().item(), (pb.grad.double() - g).abs().max().item()
-        assert err_a <= 3 * err_b + 2e-5 * scale, (na, err_a, err_b, scale)
+        assert err_a <= 3 * err_b + 5e-5 * scale, (na, err_a, err_b, scale)
         assert err_a <= 1e-3 * scale, (na, err_a, scale)
     a._clip(), a.opt.step()
     b._clip(), b.opt.step()

@@ -55,18 +55,22 @@ extern "C" {
 /* ---- long order streams (BASELINE configs[4]; FjspConfig.long_streams = 1): a second packed layout for episodes with more
  * than FJSP_MAX_ORDERS orders and / or more than 240 steps, and for order ARRIVALS during the episode.  The reference
  * accepts any num_orders (FJSPSimulation.py:315-318) and max_episode_steps (:223); this layout takes up to
- * FJSP_LONG_MAX_ORDERS orders and FJSP_LONG_MAX_STEPS steps.  Orders live in a ring of FJSP_LONG_RING slots: an order
- * enters when the pickup station pops it and its slot is reused FJSP_LONG_RING orders later, by which time it must be
- * complete (otherwise FJSP_FAULT_ORDER_RING: more orders open at once than the ring holds).  With long_streams = 0 and at
- * most 32 orders nothing changes: the compact layout above is used, bit for bit.
+ * FJSP_LONG_MAX_ORDERS orders and FJSP_LONG_MAX_STEPS steps.  Queued orders cost nothing (their attributes come from the
+ * Philox stream / the explicit table when the pickup station pops them), trays waiting at the pickup station live in a
+ * per-env ready FIFO of FJSP_LONG_READY_FIFO words outside the packed state (the reference hands out at most
+ * min(num_trays, 1000) trays per episode, FJSPSimulation.py:96), and an order occupies one of FJSP_LONG_ORDER_SLOTS order
+ * slots from the moment an AGV takes its first tray until one step after it completes.  More orders in process at once
+ * than slots -> FJSP_FAULT_ORDER_SLOTS.  With long_streams = 0 and at most 32 orders nothing changes: the compact layout
+ * is used, bit for bit.
  * Arrivals (builder-defined extension; the reference creates all orders at reset): with arrival_prob_q16 > 0 one more
  * order arrives per step with probability arrival_prob_q16 / 65536 — Philox4x32-10(key = seed, counter = (global env,
  * episode, step, 5)), low 16 bits < arrival_prob_q16 — until arrival_max_orders exist; order i always has the attributes of
  * index i of the order stream.  An episode then terminates only when all arrival_max_orders orders are complete. */
-#define FJSP_LONG_RING 64
+#define FJSP_LONG_ORDER_SLOTS 64
+#define FJSP_LONG_READY_FIFO 1024
 #define FJSP_LONG_MAX_ORDERS 4095
 #define FJSP_LONG_MAX_STEPS 65000
-#define FJSP_STATE_WORDS_LONG_K(k) (192 + 64 * (k) + 24 * ((k) - 1))  /* 256 words = 1 KB for K = 1 */
+#define FJSP_STATE_WORDS_LONG_K(k) (228 + 64 * (k) + 24 * ((k) - 1))  /* 292 words = 1168 B for K = 1 */
 
 /* ---- wire rows: the compact form in which a step's results cross PCIe on the host-buffer path (fjsp_step_host) and
  * which fjsp_step_wire / fjsp_wire_decode expose.  Everything a step returns is a small integer, so one env's results
@@ -99,7 +103,7 @@ extern "C" {
 #define FJSP_FAULT_BAD_ORDER 3                /* an explicit order record outside n 1..9 / type 1..3 / colour 1..3 (set at reset) */
 #define FJSP_FAULT_PAST_END 4                 /* stepped after the truncation step without a reset: the env is inert (the
                                                  reference would simulate on; the packed counters are not sized for it) */
-#define FJSP_FAULT_ORDER_RING 5               /* long layout: more than FJSP_LONG_RING orders open at once */
+#define FJSP_FAULT_ORDER_SLOTS 5              /* long layout: more than FJSP_LONG_ORDER_SLOTS orders in process at once */
 
 /* Mirrors constants.py:5-32 (LOCATION_POSITIONS, PROCESSING_TIMES, CONFIG). */
 typedef struct FjspConfig {
@@ -184,8 +188,9 @@ void* fjsp_state_ptr(FjspHandle* h);            /* device pointer of the packed 
 
 /* FJSPParallelEnv.reset (FJSPParallelEnvWrapper.py:43-54) -> FJSPSimulation.reset (:286-323).
  *   env_mask  : device u8[N] (non-zero = reset that env) or NULL = all
- *   orders    : device FjspOrderRec[N][FJSP_MAX_ORDERS] explicit order tables (long layout: [N][num_orders], copied into
- *               the handle), or NULL = draw
+ *   orders    : device FjspOrderRec[N][FJSP_MAX_ORDERS] explicit order tables (long layout: [N][W] with W = num_orders, or
+ *               arrival_max_orders when arrivals are on — one record per order that can ever exist; copied into the
+ *               handle), or NULL = draw
  *               n~U{1..9}, type~U{1..3}, colour~U{1..3} from Philox4x32-10(key=seed,
  *               counter=(global env, episode, order, 0)) — replayable on the host
  *   num_orders: 0..32 (reference default 30); long layout: 0..FJSP_LONG_MAX_ORDERS
@@ -248,8 +253,8 @@ int fjsp_export_state_cell(FjspHandle* h, int64_t env, int cell, FjspCanonState*
 int fjsp_export_packed(FjspHandle* h, int64_t env, uint32_t* out_words);
 /* Per-order record of orders [first, first + count) of one env, decoded on the host (synchronises):
  * out[i] = { packaged_mask, processed_mask, is_complete, completion_step (or -1) }.  Works for both layouts; in the long
- * layout orders that have left the ring are reported as complete with every bit set and completion_step -1 (a slot is
- * only reused once its order is complete), orders not yet popped as zeros.  In the long layout FjspCanonState's
+ * layout orders whose slot has been given back (one step after completion) are reported as complete with every bit set
+ * and completion_step -1, orders no AGV has touched yet as zeros.  In the long layout FjspCanonState's
  * per-order arrays describe the 32 most recently popped orders (order_base = max(0, next_order - 32) is returned
  * here through *order_base when it is not NULL) and tray entries are FJSP_TRAY_ENTRY_LONG. */
 int fjsp_export_orders(FjspHandle* h, int64_t env, int first, int count, int32_t* out4, int32_t* order_base);

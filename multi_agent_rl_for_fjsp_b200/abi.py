@@ -30,7 +30,7 @@ def dims(cells: int = 1, long_streams: bool = False) -> dict:
     agents = 1 + 7 * cells
     return {"agents": agents, "act": (agents + 7) // 8 * 8, "obs": 7 + 31 * cells, "mask": (3 + 26 * cells + 31) // 32 * 32,
             "mask_used": 3 + 26 * cells,
-            "state_words": (192 + 64 * cells + 24 * (cells - 1)) if long_streams else (64 + 64 * cells + 20 * (cells - 1)),
+            "state_words": (228 + 64 * cells + 24 * (cells - 1)) if long_streams else (64 + 64 * cells + 20 * (cells - 1)),
             "wire_words": (2 + 5 * cells + 1) // 2 * 2}
 
 CANON_MAXQ, CANON_PS_READY, CANON_MAXPQ = 64, 256, 256

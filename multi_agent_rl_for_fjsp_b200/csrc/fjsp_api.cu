@@ -26,6 +26,7 @@ struct FjspHandle {
     bool long_streams;       // long order streams: the second packed layout (fjsp_core.h)
     FjspOrderRec* d_otab;    // long layout: the handle's copy of the explicit order tables [num_envs][otab_stride], or null
     int otab_stride;
+    u32* d_rq;               // long layout: ready FIFOs [num_envs][FJSP_LONG_READY_FIFO]
     int act, obs, mask;      // row widths of the I/O tensors (FJSP_*_DIM_K)
     size_t tile_bytes;       // 64 envs x FJSP_STATE_WORDS_K words
     int64_t num_envs, first_env, num_tiles;
@@ -131,12 +132,12 @@ static void launch_rollout(const FjspHandle* h, int steps, uint64_t seed, uint64
     if constexpr (K >= 2) {
         if (!per_env) {
             fjsp_rollout_cells_kernel<K, LONG><<<(unsigned)h->num_tiles, TILE * K, G::ROLLOUT_CELLS_SMEM_BYTES, st>>>(
-                h->P, h->state, h->num_envs, h->first_env, seed, t0, steps, h->num_orders, stats);
+                h->P, h->state, h->num_envs, h->first_env, seed, t0, steps, h->num_orders, stats, h->d_rq);
             return;
         }
     }
     fjsp_rollout_kernel<K, LONG><<<(unsigned)h->num_tiles, TILE, G::ROLLOUT_SMEM_BYTES, st>>>(h->P, h->state, h->num_envs, h->first_env, seed,
-                                                                                           t0, steps, h->num_orders, stats);
+                                                                                           t0, steps, h->num_orders, stats, h->d_rq);
 }
 
 // ---- tcgen05 grouped GEMM (fjsp_umma.cuh): the actor / critic layers of the batched A2C trainer ----
@@ -205,6 +206,11 @@ int fjsp_create(const FjspConfig* cfg, int64_t num_envs, int64_t first_env, int 
     h->num_tiles = (num_envs + TILE - 1) / TILE;
     h->seed = 0, h->num_orders = 30, h->launches = 0;
     cudaError_t e = cudaMalloc(&h->state, (size_t)h->num_tiles * h->tile_bytes);
+    if (e == cudaSuccess && h->long_streams) {
+        e = cudaMalloc(&h->d_rq, (size_t)h->num_envs * FJSP_LONG_READY_FIFO * sizeof(u32));
+        if (e == cudaSuccess) e = cudaMemset(h->d_rq, 0, (size_t)h->num_envs * FJSP_LONG_READY_FIFO * sizeof(u32));
+        if (e != cudaSuccess) cudaFree(h->state);
+    }
     if (e != cudaSuccess) {
         delete h;
         return cuda_fail(e, "cudaMalloc(state)");
@@ -212,6 +218,7 @@ int fjsp_create(const FjspConfig* cfg, int64_t num_envs, int64_t first_env, int 
     DISPATCH_KL(h, e = (set_smem_attrs<K, LONG>()))
     if (e != cudaSuccess) {
         cudaFree(h->state);
+        cudaFree(h->d_rq);
         delete h;
         return cuda_fail(e, "cudaFuncSetAttribute (is this an sm_100a device?)");
     }
@@ -222,6 +229,7 @@ int fjsp_create(const FjspConfig* cfg, int64_t num_envs, int64_t first_env, int 
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         cudaFree(h->state);
+        cudaFree(h->d_rq);
         delete h;
         return cuda_fail(e, "initial reset kernel");
     }
@@ -234,6 +242,7 @@ int fjsp_destroy(FjspHandle* h) {
     DeviceGuard g(h->device);
     cudaFree(h->state);
     cudaFree(h->d_otab);
+    cudaFree(h->d_rq);
     free_staging(h);
     delete h;
     return 0;
@@ -260,23 +269,24 @@ int fjsp_reset(FjspHandle* h, const uint8_t* env_mask, uint64_t seed, const Fjsp
     if (h->long_streams) {
         // The ring fills as orders are popped, so explicit tables must outlive this call: the handle keeps a device copy
         // ([num_envs][num_orders]).  A masked reset may only replace rows of a table of the same width.
-        stride = num_orders;
+        // explicit tables: one record per order that can ever exist (with arrivals: arrival_max_orders of them)
+        stride = h->cfg.arrival_prob_q16 > 0 && h->cfg.arrival_max_orders > num_orders ? h->cfg.arrival_max_orders : num_orders;
         if (orders) {
-            if (env_mask && h->d_otab && h->otab_stride != num_orders) return fail("masked reset with explicit orders: num_orders must equal the installed table's");
-            if (!h->d_otab || h->otab_stride != num_orders) {
+            if (env_mask && h->d_otab && h->otab_stride != stride) return fail("masked reset with explicit orders: the table width must equal the installed table's");
+            if (!h->d_otab || h->otab_stride != stride) {
                 CK(cudaStreamSynchronize((cudaStream_t)stream));
                 cudaFree(h->d_otab);
                 h->d_otab = nullptr;
-                if (num_orders > 0) CK(cudaMalloc(&h->d_otab, (size_t)h->num_envs * num_orders * sizeof(FjspOrderRec)));
-                h->otab_stride = num_orders;
+                if (stride > 0) CK(cudaMalloc(&h->d_otab, (size_t)h->num_envs * stride * sizeof(FjspOrderRec)));
+                h->otab_stride = stride;
             }
-            if (num_orders > 0) {
+            if (stride > 0) {
                 if (env_mask) {
                     // rows of the envs that are not reset keep their tables: copy row by row under the mask on the device
-                    fjsp_copy_masked_rows_kernel<<<(unsigned)((h->num_envs * num_orders + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-                        h->d_otab, orders, env_mask, h->num_envs, num_orders);
+                    fjsp_copy_masked_rows_kernel<<<(unsigned)((h->num_envs * stride + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+                        h->d_otab, orders, env_mask, h->num_envs, stride);
                 } else {
-                    CK(cudaMemcpyAsync(h->d_otab, orders, (size_t)h->num_envs * num_orders * sizeof(FjspOrderRec), cudaMemcpyDeviceToDevice,
+                    CK(cudaMemcpyAsync(h->d_otab, orders, (size_t)h->num_envs * stride * sizeof(FjspOrderRec), cudaMemcpyDeviceToDevice,
                                        (cudaStream_t)stream));
                 }
                 orders = h->d_otab;
@@ -312,7 +322,7 @@ int fjsp_step(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, 
     A.results = results, A.infos = infos, A.num_envs = h->num_envs, A.first_env = h->first_env, A.seed = h->seed;
     A.num_orders = h->num_orders, A.autoreset = autoreset, A.tile_begin = 0, A.wire = nullptr;
     A.prefetch_tiles = h->prefetch_tiles, A.prefetch_tiles_env = h->prefetch_tiles_env;
-    A.otab = h->d_otab, A.otab_stride = h->otab_stride;
+    A.otab = h->d_otab, A.otab_stride = h->otab_stride, A.rq = h->d_rq;
     DISPATCH_KL(h, (launch_step<K, false, LONG>(h, A, (unsigned)h->num_tiles, (cudaStream_t)stream)))
     h->launches++;
     CK(cudaGetLastError());
@@ -325,7 +335,7 @@ static StepArgs wire_args(FjspHandle* h, const uint8_t* actions, u32* wire, uint
     A.results = results, A.infos = infos, A.wire = wire, A.num_envs = h->num_envs, A.first_env = h->first_env, A.seed = h->seed;
     A.num_orders = h->num_orders, A.autoreset = autoreset, A.tile_begin = 0;
     A.prefetch_tiles = h->prefetch_tiles, A.prefetch_tiles_env = h->prefetch_tiles_env;
-    A.otab = h->d_otab, A.otab_stride = h->otab_stride;
+    A.otab = h->d_otab, A.otab_stride = h->otab_stride, A.rq = h->d_rq;
     return A;
 }
 
@@ -578,7 +588,13 @@ int fjsp_export_state_cell(FjspHandle* h, int64_t env, int cell, FjspCanonState*
     if (h && (cell < 0 || cell >= h->cells)) return fail("cell index out of range");
     u32 words[FJSP_STATE_WORDS_LONG_K(FJSP_MAX_CELLS)];
     if (int rc = fjsp_export_packed(h, env, words)) return rc;
-    export_canon(words, h->P, h->cells, h->long_streams, cell, out);
+    std::vector<u32> rq;
+    if (h->long_streams) {
+        rq.resize(FJSP_LONG_READY_FIFO);
+        DeviceGuard g(h->device);
+        CK(cudaMemcpy(rq.data(), h->d_rq + env * FJSP_LONG_READY_FIFO, FJSP_LONG_READY_FIFO * sizeof(u32), cudaMemcpyDeviceToHost));
+    }
+    export_canon(words, h->long_streams ? rq.data() : nullptr, h->P, h->cells, h->long_streams, cell, out);
     return 0;
 }
 
@@ -589,7 +605,7 @@ int fjsp_export_orders(FjspHandle* h, int64_t env, int first, int count, int32_t
     export_orders(words, h->P, h->cells, h->long_streams, first, count, out4);
     if (order_base) {
         FjspCanonState c;
-        export_canon(words, h->P, h->cells, h->long_streams, 0, &c, order_base);
+        export_canon(words, nullptr, h->P, h->cells, h->long_streams, 0, &c, order_base);
     }
     return 0;
 }

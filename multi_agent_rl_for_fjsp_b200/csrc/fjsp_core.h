@@ -62,21 +62,31 @@ enum { COL_RED = 1, COL_BLUE = 2, COL_GREEN = 3 };
 //   words 64+64c ..  tray pool of cell c (64 records)                      -> words 24 .. 64+64K are "dynamic"
 //   words 64+64K ..  hot words of cells 1..K-1, 20 each (AGV, free bitmap x2, storage, 2 machines x 2, 4 stations x 3)
 //
-// LONG (long order streams, BASELINE configs[4]; K = 1: 256 words = 1 KB): up to 4095 orders and 65,000 steps per
-// episode, Philox order ARRIVALS.  Orders live in a RING of 64 slots (slot = order id mod 64): an order enters the ring
-// when the pickup station pops it (its attributes come from the Philox stream / the explicit table at that moment) and
-// its slot is reused 64 orders later, by which time it must be complete (else FJSP_FAULT_ORDER_RING).  Counters are
-// wider, trays lost to the reference's quirks give their pool slot back at once (their processed bits live in the ring).
+// LONG (long order streams, BASELINE configs[4]; K = 1: 292 words = 1168 B + a 4 KB side FIFO that a step touches in at
+// most two words): up to 4095 orders and 65,000 steps per episode, Philox order ARRIVALS.  An order goes through three
+// stages and only the last one costs packed state:
+//   queued   (not popped yet)                 nothing stored: its attributes come from the Philox stream / the explicit
+//                                             table when the pickup station pops it;
+//   loaded   (trays waiting at the station)   one word per TRAY in the READY FIFO, a side buffer in HBM outside the tile
+//                                             (order12 | first4<<12 | count3<<16, index = the tray's allocation index: the
+//                                             reference hands out at most min(num_trays, 1000) trays per episode,
+//                                             FJSPSimulation.py:96, so 1024 entries always suffice);
+//   in process (an AGV took its first tray)   one of 64 ORDER SLOTS (three words: order word as in the compact layout,
+//                                             processed bits + order id, completion step + first tray's allocation index),
+//                                             given back one step after the order completes.  More than 64 orders in
+//                                             process at once -> FJSP_FAULT_ORDER_SLOTS (an order whose tray was lost to one
+//                                             of the reference's quirks never completes and keeps its slot).
+// Counters are wider than in the compact layout; lost trays give their pool slot back at once.
 //   words 0..23      as above (three shared words re-packed, see load_hot)
 //   words 24..27     more shared hot words; 28..31 one more word per packaging station of cell 0 (current product)
-//   words 32..63     completion steps (u16 per ring slot)
-//   words 64..127    ring A: order words;  128..191  ring B: processed9 | first tray's allocation index 12 << 9
-//   words 192+64c .. tray pools                                            -> words 32 .. 192+64K are "dynamic"
+//   words 32..35     order-slot bitmaps: free (2), freed by this step (2)
+//   words 36..227    order slots: A 36..99, B 100..163, C 164..227
+//   words 228+64c .. tray pools                                            -> words 32 .. 228+64K are "dynamic"
 //   then             hot words of cells 1..K-1, 24 each
 // ---------------------------------------------------------------------------------------------
 enum {
     W_CTRL = 0,     // compact: step16 | num_orders6<<16 | fault3<<22 | completed_orders6<<25
-                    // long   : step16 | fault3<<16 | cur_tray_count3<<19 | prod_idx4<<22 | ready_idx4<<26
+                    // long   : step16 | fault3<<16 | cur_tray_count3<<19 | prod_idx4<<22
     W_PS = 1,       // compact: total_packaged9 | next_order6<<9 | cur_order6<<15 (63=none) | prod_idx4<<21 | cur_tray_count3<<25
                     // long   : num_orders12 | completed_orders12<<12 | dock_mask4<<24
     W_PSQ = 2,      // compact: alloc_count8 | ready_count8<<8 | ready_order6<<16 | ready_idx4<<22 | dock_mask4<<26
@@ -95,27 +105,31 @@ enum {
                     //                                                                  | long   : qcount8<<14
                     //   C: compact: completed8 | progL8<<8          long: completed16 | progL8<<16
                     //   D (long only): cur_order12 | cur_idx4<<12
-    W_LONG_PSQ = 24,   // long: ready_order12 | ready_count12<<12
+    W_LONG_PSQ = 24,   // long: ready_head12 (trays taken from the ready FIFO so far) | ready_count12<<12
     W_LONG_CNT = 25,   // long: total_packaged16 | alloc_count12<<16
+    W_LONG_ACT = 26,   // long: the order whose tray was taken last: order13 (0x1fff = none) | its slot6<<13 ;
+                       //       cur_word8<<19 = n4 | type2 | colour2 of the order being loaded
     W_LONG_PACKD = 28, // long: word D of cell 0's four packaging stations
     CELL_HOT_WORDS = 20
 };
-// tray record (both layouts): ring slot7 | first4<<7 | count3<<11 | processed1<<14 | next6<<15 | stamp8<<21 | lost1<<29
-// order word                : n4 | type2<<4 | colour2<<6 | cut8<<8 | packaged9<<16
+// tray record (both layouts): order slot7 | first4<<7 | count3<<11 | processed1<<14 | next6<<15 | stamp8<<21 | lost1<<29
+// order word / slot word A  : n4 | type2<<4 | colour2<<6 | cut8<<8 | packaged9<<16
+// long: slot word B = processed9 | order12<<9;  slot word C = completion step + 1 (16) | first tray's allocation index 12 << 16
 
 template <bool LONG>
 struct WM {
-    static constexpr int RING = LONG ? 64 : 32;                        // order slots (compact: the whole table)
+    static constexpr int SLOTS = LONG ? 64 : 32;                       // order slots (compact: the whole order table, slot = order id)
     static constexpr int W_DYN0 = LONG ? 32 : 24;                      // first dynamically indexed word
-    static constexpr int W_CSTEP = W_DYN0;                             // completion step + 1 per slot (0 = not complete): u8 / u16
-    static constexpr int W_ORDER = W_CSTEP + (LONG ? RING / 2 : RING / 4);   // 32 / 64
-    static constexpr int W_ORDER_B = W_ORDER + RING;                   // long only
-    static constexpr int W_POOL = W_ORDER + (LONG ? 2 : 1) * RING;     // 64 / 192
+    static constexpr int W_SLOT_FREE = 32, W_SLOT_FREED = 34;          // long only: bitmaps (2 words each)
+    static constexpr int W_CSTEP = 24;                                 // compact only: u8 completion step + 1 per order
+    static constexpr int W_ORDER = LONG ? 36 : 32;                     // order words / slot words A
+    static constexpr int W_ORDER_B = W_ORDER + SLOTS, W_ORDER_C = W_ORDER + 2 * SLOTS;   // long only
+    static constexpr int W_POOL = W_ORDER + (LONG ? 3 : 1) * SLOTS;    // 64 / 228
     static constexpr int CELL_HOT = LONG ? 24 : 20;
-    static constexpr int NO_ORDER = LONG ? 0x1fff : 63;
 };
 static_assert(WM<false>::W_POOL + 64 == FJSP_STATE_WORDS, "compact state size");
 enum { W_CSTEP = WM<false>::W_CSTEP, W_ORDER = WM<false>::W_ORDER, W_POOL = WM<false>::W_POOL, W_TOTAL = 128 };  // compact names (host tools)
+constexpr int READY_FIFO_WORDS = FJSP_LONG_READY_FIFO;  // side buffer per env (long layout)
 
 template <int K, bool LONG = false>
 struct Lay {
@@ -135,13 +149,11 @@ FJSP_HD constexpr int cell_word(int c, int which) {
 }
 template <bool LONG>
 FJSP_HD constexpr int pool_base(int c) { return WM<LONG>::W_POOL + 64 * c; }
-template <bool LONG>
-FJSP_HD constexpr int oslot(int order) { return order & (WM<LONG>::RING - 1); }
-// the order id living in ring slot `slot`, given the pickup station's next_order (ids enter the ring consecutively)
-template <bool LONG>
-FJSP_HD int order_of_slot(int slot, int next_order) {
-    return LONG ? next_order - 1 - ((next_order - 1 - slot) & (WM<LONG>::RING - 1)) : slot;
-}
+// ready-FIFO entry (long layout)
+FJSP_HD u32 make_rq(int order, int first, int count) { return (u32)order | ((u32)first << 12) | ((u32)count << 16); }
+FJSP_HD int rq_order(u32 e) { return (int)(e & 0xfffu); }
+FJSP_HD int rq_first(u32 e) { return (int)((e >> 12) & 15u); }
+FJSP_HD int rq_count(u32 e) { return (int)((e >> 16) & 7u); }
 
 // order word
 FJSP_HD int ord_n(u32 w) { return (int)(w & 15u); }
@@ -200,7 +212,9 @@ struct Pack {
 struct Hot {  // shared part
     int step, num_orders, fault, completed_orders;
     int total_packaged, next_order, cur_order, prod_idx, cur_tray_count;   // cur_order: -1 = none
-    int alloc_count, ready_count, ready_order, ready_idx, dock_mask;
+    int alloc_count, ready_count, ready_order, ready_idx, dock_mask;   // long: ready_order = ready_head, ready_idx unused
+    int cur_word;                 // long: n4 | type2<<4 | colour2<<6 of the order being loaded
+    int act_order, act_slot;      // long: the order whose tray was taken last (-1 = none) and its slot
     u32 episode;
 };
 struct HotCell {
@@ -216,7 +230,7 @@ FJSP_HD void load_hot(S& s, Hot& h) {
     if (S::LONG) {
         u32 w = s.ld_hot(W_CTRL);
         h.step = (int)(w & 0xffffu), h.fault = (int)((w >> 16) & 7u), h.cur_tray_count = (int)((w >> 19) & 7u);
-        h.prod_idx = (int)((w >> 22) & 15u), h.ready_idx = (int)((w >> 26) & 15u);
+        h.prod_idx = (int)((w >> 22) & 15u), h.ready_idx = 0;
         w = s.ld_hot(W_PS);
         h.num_orders = (int)(w & 0xfffu), h.completed_orders = (int)((w >> 12) & 0xfffu), h.dock_mask = (int)((w >> 24) & 15u);
         w = s.ld_hot(W_PSQ);
@@ -227,6 +241,9 @@ FJSP_HD void load_hot(S& s, Hot& h) {
         h.ready_order = (int)(w & 0xfffu), h.ready_count = (int)((w >> 12) & 0xfffu);
         w = s.ld_hot(W_LONG_CNT);
         h.total_packaged = (int)(w & 0xffffu), h.alloc_count = (int)((w >> 16) & 0xfffu);
+        w = s.ld_hot(W_LONG_ACT);
+        h.act_order = (int)(w & 0x1fffu), h.act_slot = (int)((w >> 13) & 63u), h.cur_word = (int)((w >> 19) & 255u);
+        if (h.act_order == 0x1fff) h.act_order = -1;
     } else {
         u32 w = s.ld_hot(W_CTRL);
         h.step = (int)(w & 0xffffu), h.num_orders = (int)((w >> 16) & 63u), h.fault = (int)((w >> 22) & 7u);
@@ -244,12 +261,12 @@ FJSP_HD void load_hot(S& s, Hot& h) {
 template <class S>
 FJSP_HD void store_hot(S& s, const Hot& h) {
     if (S::LONG) {
-        s.st_hot(W_CTRL, (u32)h.step | ((u32)h.fault << 16) | ((u32)h.cur_tray_count << 19) | ((u32)h.prod_idx << 22) |
-                             ((u32)h.ready_idx << 26));
+        s.st_hot(W_CTRL, (u32)h.step | ((u32)h.fault << 16) | ((u32)h.cur_tray_count << 19) | ((u32)h.prod_idx << 22));
         s.st_hot(W_PS, (u32)h.num_orders | ((u32)h.completed_orders << 12) | ((u32)h.dock_mask << 24));
         s.st_hot(W_PSQ, (u32)h.next_order | ((u32)(h.cur_order < 0 ? 0x1fff : h.cur_order) << 12));
         s.st_hot(W_LONG_PSQ, (u32)h.ready_order | ((u32)h.ready_count << 12));
         s.st_hot(W_LONG_CNT, (u32)h.total_packaged | ((u32)h.alloc_count << 16));
+        s.st_hot(W_LONG_ACT, (u32)(h.act_order < 0 ? 0x1fff : h.act_order) | ((u32)h.act_slot << 13) | ((u32)h.cur_word << 19));
     } else {
         s.st_hot(W_CTRL, (u32)h.step | ((u32)h.num_orders << 16) | ((u32)h.fault << 22) | ((u32)h.completed_orders << 25));
         s.st_hot(W_PS, (u32)h.total_packaged | ((u32)h.next_order << 9) | ((u32)(h.cur_order < 0 ? 63 : h.cur_order) << 15) |
@@ -457,9 +474,11 @@ FJSP_HD void reset_env_base(S& s, int num_orders, u32 episode, int fault = 0) {
     h.step = 0, h.num_orders = num_orders, h.fault = fault, h.completed_orders = 0;
     h.total_packaged = 0, h.next_order = 0, h.cur_order = -1, h.prod_idx = 0, h.cur_tray_count = 0;
     h.alloc_count = 0, h.ready_count = 0, h.ready_order = 0, h.ready_idx = 0;
+    h.cur_word = 0, h.act_order = -1, h.act_slot = 0;
     h.dock_mask = 1;   // the dock of the pickup station is held by cell 0's AGV
     h.episode = episode;
     store_hot(s, h);
+    if (LONG) s.st(WM<LONG>::W_SLOT_FREE, 0xffffffffu), s.st(WM<LONG>::W_SLOT_FREE + 1, 0xffffffffu);  // every order slot is free
 #pragma unroll
     for (int c = 0; c < K; c++) {
         // AGVAgent.py:41: the AGV starts at PICKUP; further cells' AGVs start at STORAGE (one dock)
@@ -537,7 +556,7 @@ FJSP_HD void observe_shared(S& s, const Params& P, const Hot& h, O obs, u32* mw)
     int has_cur_order = h.cur_order >= 0;
     int order_size = 0, remaining = 0, o_type = 0, o_colour = 0;
     if (has_cur_order) {
-        u32 ow = s.ld(WM<S::LONG>::W_ORDER + oslot<S::LONG>(h.cur_order));
+        u32 ow = S::LONG ? (u32)h.cur_word : s.ld(WM<S::LONG>::W_ORDER + h.cur_order);
         order_size = ord_n(ow), remaining = order_size - h.prod_idx;
         o_type = ord_type(ow), o_colour = ord_colour(ow);
     }
@@ -787,7 +806,7 @@ FJSP_HD void pack_grant(S& s, int pb, Hot& h, HotCell& hc, Pack& p, int g, int s
         s.st(pb + fslot, rec_with_stamp(r, stamp));
         fifo_push(s, pb, p.f, fslot);
         p.busy = 1, p.hascur = 1;
-        p.cur_order = order_of_slot<S::LONG>(rec_order(r), h.next_order), p.cur_idx = last_idx;
+        p.cur_order = S::LONG ? (int)((s.ld(WM<S::LONG>::W_ORDER_B + rec_order(r)) >> 9) & 0xfffu) : rec_order(r), p.cur_idx = last_idx;
     }
 }
 
@@ -801,67 +820,52 @@ FJSP_HD void act_pickup(S& s, const Params& P, Hot& h, int a0, int& local10, u32
     constexpr bool LONG = S::LONG;
     using W = WM<LONG>;
     int loaded = 0, tray_done = 0, idle_orders = 0, success = 0;
+    // a tray leaves for ready_trays: compact = a cut bit in the order word (the FIFO is implicit), long = one entry of the
+    // ready FIFO at the tray's allocation index
+    auto release = [&](bool exhausted) {
+        if (STORE) {
+            if (LONG) {
+                s.rq_st(h.alloc_count - 1, make_rq(h.cur_order, h.prod_idx - h.cur_tray_count, h.cur_tray_count));
+            } else if (!exhausted) {
+                const u32 ow = s.ld(W::W_ORDER + h.cur_order);
+                s.st(W::W_ORDER + h.cur_order, ow | (1u << (8 + h.prod_idx - 1)));  // cut after the last loaded product
+            }
+        }
+        h.cur_tray_count = 0, h.ready_count++;
+    };
     if (a0 == 0) {
         idle_orders = (h.num_orders - h.next_order) > 0 || h.cur_order >= 0;
         success = 1;
     } else if (a0 == 1) {
         int ok = 1;
-        u32 ow = 0u;
-        bool fresh = false;
         if (h.cur_order < 0) {
             if (h.next_order < h.num_orders) {
-                const int o = h.next_order++;
-                h.cur_order = o, h.prod_idx = 0;
-                if (LONG) {
-                    // the order enters the ring now: its attributes come from the stream / table at this moment (every lane
-                    // that mirrors the pickup station computes the same word; only the storing lane touches the ring)
-                    ow = s.fetch_order(o, h.episode);
-                    fresh = true;
-                    if (STORE) {
-                        const int sl = oslot<LONG>(o);
-                        if (o >= W::RING) {  // the slot's previous occupant (order o - 64) must be complete by now
-                            const u32 prev = s.ld(W::W_ORDER + sl);
-                            if (ord_packaged(prev) != (1u << ord_n(prev)) - 1u) h.fault = FJSP_FAULT_ORDER_RING;
-                        }
-                        s.st(W::W_ORDER + sl, ow), s.st(W::W_ORDER_B + sl, 0u);
-                        const u32 cw = s.ld(W::W_CSTEP + (sl >> 1));
-                        s.st(W::W_CSTEP + (sl >> 1), cw & ~(0xffffu << ((sl & 1) * 16)));
-                    }
-                }
+                h.cur_order = h.next_order++, h.prod_idx = 0;
+                // long: the order's attributes come from the stream / table now (every lane that mirrors the pickup station
+                // computes the same word)
+                if (LONG) h.cur_word = (int)(s.fetch_order(h.cur_order, h.episode) & 0xffu);
             } else ok = 0;
         }
         if (ok && h.cur_tray_count == 0) {
-            if (h.alloc_count < P.trays_total) {   // trays_at_station.pop(0)
-                if (LONG && STORE && h.prod_idx == 0) {  // the order's first tray: remember its allocation index (tray ids)
-                    const int sl = oslot<LONG>(h.cur_order);
-                    s.st(W::W_ORDER_B + sl, (s.ld(W::W_ORDER_B + sl) & 0x1ffu) | ((u32)h.alloc_count << 9));
-                }
-                h.alloc_count++;
-            } else ok = 0;
+            if (h.alloc_count < P.trays_total) h.alloc_count++;  // trays_at_station.pop(0)
+            else ok = 0;
         }
         if (ok) {
-            const int sl = oslot<LONG>(h.cur_order);
-            if (!fresh) ow = s.ld(W::W_ORDER + sl);
+            const int n = LONG ? (h.cur_word & 15) : ord_n(s.ld(W::W_ORDER + h.cur_order));
             h.cur_tray_count++, h.prod_idx++;
             loaded = 1, success = 1;
-            if (h.prod_idx >= ord_n(ow)) {          // order exhausted: tray released (:201-208)
+            if (h.prod_idx >= n) {                  // order exhausted: tray released (:201-208)
+                release(true);
                 h.cur_order = -1, h.prod_idx = 0;
-                h.cur_tray_count = 0, h.ready_count++;
                 tray_done = 1;
             } else if (h.cur_tray_count >= FJSP_TRAY_CAPACITY) {  // tray full (:211-216)
-                if (STORE) s.st(W::W_ORDER + sl, ow | (1u << (8 + h.prod_idx - 1)));  // cut after the last loaded product
-                h.cur_tray_count = 0, h.ready_count++;
+                release(false);
                 tray_done = 1;
             }
         }
     } else if (a0 == 2) {
         if (h.cur_tray_count > 0) {                 // SIGNAL (:226-230): the order is not exhausted here
-            if (STORE) {
-                const int sl = oslot<LONG>(h.cur_order);
-                u32 ow = s.ld(W::W_ORDER + sl);
-                s.st(W::W_ORDER + sl, ow | (1u << (8 + h.prod_idx - 1)));
-            }
-            h.cur_tray_count = 0, h.ready_count++;
+            release(false);
             success = 1;
         }
     }
@@ -869,6 +873,21 @@ FJSP_HD void act_pickup(S& s, const Params& P, Hot& h, int a0, int& local10, u32
           (idle_orders ? FJSP_RES_PS_IDLE_ORDERS : 0);
     // RewardModel.py:53-60: +1 load, +5 tray completed, -1 idle with orders
     local10 = (loaded ? 10 : 0) + (tray_done ? 50 : 0) - ((a0 == 0 && idle_orders) ? 10 : 0);
+}
+
+// Long layout, start of a step (the lane that owns the pickup station): order slots freed by the previous step's
+// completions become available now — one step late on purpose, so that allocation (an AGV's pickup, action phase) and
+// release (a packaging station's finish, run phase) never meet inside a step whatever the execution order of the cells.
+template <class S>
+FJSP_HD void begin_step_slots(S& s) {
+    if (S::LONG) {
+        using W = WM<S::LONG>;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const u32 f = s.ld(W::W_SLOT_FREED + i);
+            if (f) s.st(W::W_SLOT_FREE + i, s.ld(W::W_SLOT_FREE + i) | f), s.st(W::W_SLOT_FREED + i, 0u);
+        }
+    }
 }
 
 // FJSPSimulation.py:216-220; with order arrivals switched on an episode can only terminate once every order has arrived
@@ -933,15 +952,43 @@ FJSP_HD void act_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, 
                     if (slot < 0) {
                         h.fault = FJSP_FAULT_POOL_EXHAUSTED, invalid = 1;
                     } else {
+                        if (LONG) {
+                            // head of the ready FIFO; the tray's order enters an ORDER SLOT with its first tray
+                            const u32 e = s.rq_ld(h.ready_order);
+                            const int o = rq_order(e), first = rq_first(e), cnt = rq_count(e);
+                            int os = h.act_slot;
+                            if (o != h.act_order) {
+                                const u32 f0 = s.ld(W::W_SLOT_FREE), f1 = s.ld(W::W_SLOT_FREE + 1);
+                                os = f0 ? ctz32(f0) : f1 ? 32 + ctz32(f1) : -1;
+                                if (os >= 0) {
+                                    s.st(W::W_SLOT_FREE + (os >> 5), (os < 32 ? f0 : f1) & ~(1u << (os & 31)));
+                                    s.st(W::W_ORDER + os, s.fetch_order(o, h.episode) & 0xffu);
+                                    s.st(W::W_ORDER_B + os, (u32)o << 9);
+                                    s.st(W::W_ORDER_C + os, (u32)h.ready_order << 16);
+                                    h.act_order = o, h.act_slot = os;
+                                }
+                            }
+                            if (os < 0) {
+                                h.fault = FJSP_FAULT_ORDER_SLOTS, invalid = 1;
+                                pool_free(hc, slot);
+                            } else {
+                                const u32 ow = s.ld(W::W_ORDER + os);
+                                if (first + cnt < ord_n(ow)) s.st(W::W_ORDER + os, ow | (1u << (8 + first + cnt - 1)));  // (tray ids of the export)
+                                s.st(pb + slot, make_rec(os, first, cnt, 0));
+                                h.ready_order++, h.ready_count--;
+                                hc.carry = slot + 1, pick = 1;
+                            }
+                        } else {
                         // head ready tray = products [ready_idx, next cut] of order ready_order
-                        u32 ow = s.ld(W::W_ORDER + oslot<LONG>(h.ready_order));
+                        u32 ow = s.ld(W::W_ORDER + h.ready_order);
                         u32 cuts = ord_cut(ow) >> h.ready_idx;
                         int cnt = cuts ? ctz32(cuts) + 1 : ord_n(ow) - h.ready_idx;
-                        s.st(pb + slot, make_rec(oslot<LONG>(h.ready_order), h.ready_idx, cnt, 0));
+                        s.st(pb + slot, make_rec(h.ready_order, h.ready_idx, cnt, 0));
                         h.ready_idx += cnt;
                         if (h.ready_idx >= ord_n(ow)) h.ready_order++, h.ready_idx = 0;
                         h.ready_count--;
                         hc.carry = slot + 1, pick = 1;
+                        }
                     }
                 } else invalid = 1;
             } else {
@@ -1109,8 +1156,12 @@ FJSP_HD void run_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, 
             const u32 full = (1u << ord_n(ow)) - 1u;
             if (ord_packaged(ow) == full && ord_packaged(before) != full) {  // _check_order_completions (FJSPSimulation.py:245-258)
                 h.completed_orders++;
-                if (LONG) s.or_word(W::W_CSTEP + (o >> 1), (u32)((k + 1) & 0xffff) << ((o & 1) * 16));
-                else s.or_word(W::W_CSTEP + (o >> 2), (u32)((k + 1) & 255) << ((o & 3) * 8));
+                if (LONG) {
+                    s.or_word(W::W_ORDER_C + o, (u32)((k + 1) & 0xffff));
+                    s.or_word(W::W_SLOT_FREED + (o >> 5), 1u << (o & 31));  // the slot is free again from the next step on
+                } else {
+                    s.or_word(W::W_CSTEP + (o >> 2), (u32)((k + 1) & 255) << ((o & 3) * 8));
+                }
             }
         }
         const int stamp = (k + P.pack_steps) & 255;
@@ -1156,6 +1207,7 @@ FJSP_HD void step_env_hot(S& s, const Params& P, Hot& h, HotCell& c0, const int*
         return;
     }
     arrivals(s, P, h);
+    begin_step_slots(s);
     act_pickup(s, P, h, a[0], local10[0], res[0]);
     int dock_after = 0;
     {
@@ -1226,6 +1278,7 @@ FJSP_HD void step_env(S& s, const Params& P, const int* a, StepOut<K>& out) {
 // three points only, through a small per-env exchange area X (a shared-memory column on the device):
 //   1. the pickup station acts first (every lane mirrors its registers, the lane of cell 0 writes the order words) and
 //      every AGV posts whether it asks for the single dock                                                  -> barrier
+//      (long layout: it also makes last step's freed order slots available and writes released trays to the ready FIFO)
 //   2. each lane resolves the dock in agent order from the posted requests (an earlier AGV's grant blocks a later one),
 //      runs its cell's seven agents and its run phase; order words are updated with atomic ORs; it posts the ready-tray
 //      cursor if its AGV took a tray at the pickup station (only the dock holder can), its packaged / completed
@@ -1239,7 +1292,7 @@ FJSP_HD void step_env(S& s, const Params& P, const int* a, StepOut<K>& out) {
 // products; X_MASK.. = 3 mask bits of the pickup station, then 26 per cell; then one u16 per action column:
 // local reward (9-bit signed, tenths) | action_result << 9.
 // ---------------------------------------------------------------------------------------------
-enum { X_RDF = 0, X_READY = 1, X_DELTA = 2, X_MASK = 3 };
+enum { X_RDF = 0, X_READY = 1, X_DELTA = 2, X_ACT = 3, X_MASK = 4 };  // X_ACT (long layout): order slot taken by the picking lane
 template <int K>
 struct Xl {
     static constexpr int LOCAL = X_MASK + 1 + K;  // first word of the u16 table
@@ -1265,6 +1318,7 @@ FJSP_HD void cells_begin(S& s, X& x, const Params& P, CellLane& L, int a0, const
     if (L.inert) return;
     arrivals(s, P, L.h);
     if (L.c == 0) {
+        begin_step_slots(s);
         act_pickup<true>(s, P, L.h, a0, L.local10[0], L.res[0]);
         if (L.h.fault != L.fault_in) x.atom_or(X_RDF, (u32)(L.h.fault & 7) << 20);  // (order ring overflow: long layout)
     } else {
@@ -1289,8 +1343,10 @@ FJSP_HD void cells_act_run(S& s, X& x, const Params& P, CellLane& L, const int* 
     L.h.completed_orders = 0, L.h.total_packaged = 0, L.h.fault = -1;
     int pk_start[4];
     act_cell(s, P, L.h, L.hc, L.c, L.k, a7, L.local10 + 1, L.res + 1, pk_start);
-    if (L.h.ready_count != rc || L.h.ready_order != ro || L.h.ready_idx != ri)
+    if (L.h.ready_count != rc || L.h.ready_order != ro || L.h.ready_idx != ri) {
         x.st(X_READY, (u32)L.h.ready_count | ((u32)L.h.ready_order << 12) | ((u32)L.h.ready_idx << 24) | (1u << 31));
+        if (S::LONG) x.st(X_ACT, (u32)(L.h.act_order & 0x1fff) | ((u32)L.h.act_slot << 13) | (1u << 31));
+    }
     int dock_after = 0;
     run_cell(s, P, L.h, L.hc, L.c, L.k, pk_start, dock_after);
     u32 post = (u32)dock_after << 4;
@@ -1315,6 +1371,10 @@ FJSP_HD void cells_finish(X& x, const Params& P, CellLane& L, int32_t* info) {
     const u32 rdf = x.ld(X_RDF), ready = x.ld(X_READY), delta = x.ld(X_DELTA);
     if (!L.inert) {
     if (ready >> 31) h.ready_count = (int)(ready & 0xfffu), h.ready_order = (int)((ready >> 12) & 0xfffu), h.ready_idx = (int)((ready >> 24) & 15u);
+    if (S::LONG) {
+        const u32 act = x.ld(X_ACT);
+        if (act >> 31) h.act_order = (int)(act & 0x1fffu), h.act_slot = (int)((act >> 13) & 63u);
+    }
     const int d_orders = (int)(delta >> 16), d_products = (int)(delta & 0xffffu);
     h.completed_orders = L.orders_in + d_orders, h.total_packaged = L.packaged_in + d_products;
     h.dock_mask = (int)((rdf >> 4) & 15u);

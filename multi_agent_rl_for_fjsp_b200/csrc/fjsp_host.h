@@ -100,6 +100,9 @@ struct ArrayStateT {
     int dyn_end = 1 << 30, total = 1 << 30;  // word counts of the env (set by the harness when the check is compiled in)
     uint64_t seed = 0, genv = 0;             // long layout: the order / arrival streams (see fjsp_kernels.cuh)
     const FjspOrderRec* otab = nullptr;
+    u32* rq = nullptr;                       // long layout: this env's ready FIFO (READY_FIFO_WORDS entries)
+    FJSP_HD u32 rq_ld(int i) const { FJSP_CHECK_IDX(i >= 0 && i < READY_FIFO_WORDS); return rq[i & (READY_FIFO_WORDS - 1)]; }
+    FJSP_HD void rq_st(int i, u32 v) { FJSP_CHECK_IDX(i >= 0 && i < READY_FIFO_WORDS); rq[i & (READY_FIFO_WORDS - 1)] = v; }
     static constexpr int DYN0 = WM<LONG_>::W_DYN0;
     FJSP_HD u32 ld(int i) const { FJSP_CHECK_IDX(i >= DYN0 && i < dyn_end); return w[i]; }
     FJSP_HD void st(int i, u32 v) { FJSP_CHECK_IDX(i >= DYN0 && i < dyn_end); w[i] = v; }
@@ -136,11 +139,89 @@ struct ArrayXchg {
     FJSP_HD u32 ld16(int i16) const { return reinterpret_cast<const uint16_t*>(w)[i16]; }
 };
 
-// ---- canonical record S from packed words: shared pickup station / orders + the given cell ----
-// Long layout: the per-order arrays describe orders [order_base, order_base + 32) with order_base = max(0, next_order - 32)
-// (the 32 most recently popped), tray entries are FJSP_TRAY_ENTRY_LONG, product ids order * 100 + idx as in the reference.
+// is_processed of the products of every order slot: finished trays (compact: packaged bits and live pool records; long:
+// slot word B), plus the products a busy machine has flagged so far.  is_processed is a property of the products,
+// whatever cell their tray is in: every cell's pool and machines are scanned.
 template <int K, bool LONG>
-inline void export_canon_k(const u32* words, const Params& P, int cell, FjspCanonState* out, int32_t* order_base_out = nullptr) {
+inline void processed_by_slot(const u32* words, const Params& P, int32_t* proc) {
+    using W = WM<LONG>;
+    ArrayStateT<LONG> s{const_cast<u32*>(words)};
+    s.dyn_end = Lay<K, LONG>::DYN_END, s.total = Lay<K, LONG>::TOTAL;
+    Hot h;
+    load_hot(s, h);
+    for (int sl = 0; sl < W::SLOTS; sl++)
+        proc[sl] = LONG ? (int32_t)(words[W::W_ORDER_B + sl] & 0x1ffu) : (int32_t)ord_packaged(words[W::W_ORDER + sl]);
+    for (int cc = 0; cc < K; cc++) {
+        HotCell x;
+        load_cell<K>(s, cc, x);
+        const int xb = pool_base<LONG>(cc);
+        uint64_t free_bits = (uint64_t)x.free_lo | ((uint64_t)x.free_hi << 32);
+        for (int slot = 0; slot < FJSP_POOL_SLOTS; slot++) {
+            if ((free_bits >> slot) & 1u) continue;
+            u32 r = words[xb + slot];
+            if (rec_processed(r)) proc[rec_order(r)] |= (int32_t)(((1u << rec_count(r)) - 1u) << rec_first(r));
+        }
+        for (int i = 0; i < 2; i++) {
+            const Mach& m = x.m[i];
+            if (!m.busy) continue;  // products flagged so far: i <= (last executed step - start) / per
+            u32 r = words[xb + m.cur];
+            int per = i == 0 ? P.small_steps : P.big_steps;
+            int done = (h.step - 1 - m.start) / per;
+            if (done > rec_count(r)) done = rec_count(r);
+            if (done < 0) done = 0;
+            proc[rec_order(r)] |= (int32_t)(((1u << done) - 1u) << rec_first(r));
+        }
+    }
+}
+
+// long layout: the slot an order occupies, or -1 (queued, loaded but untouched, or complete and retired)
+template <bool LONG>
+inline int slot_of_order(const u32* words, int order) {
+    using W = WM<LONG>;
+    if (!LONG) return order;
+    const uint64_t free_bits = (uint64_t)words[W::W_SLOT_FREE] | ((uint64_t)words[W::W_SLOT_FREE + 1] << 32);
+    for (int sl = 0; sl < W::SLOTS; sl++)
+        if (!((free_bits >> sl) & 1u) && (int)((words[W::W_ORDER_B + sl] >> 9) & 0xfffu) == order) return sl;
+    return -1;
+}
+
+// per-order records for orders [first, first + count): {packaged_mask, processed_mask, complete, completion_step}.
+// Long layout: an order that is in process reads from its slot; one that is popped, has no slot and precedes the order
+// whose tray was taken last is complete and retired (all bits, completion step unknown: -1); anything else is untouched.
+template <int K, bool LONG>
+inline void export_orders_k(const u32* words, const Params& P, int first, int count, int32_t* out4) {
+    using W = WM<LONG>;
+    ArrayStateT<LONG> s{const_cast<u32*>(words)};
+    s.dyn_end = Lay<K, LONG>::DYN_END, s.total = Lay<K, LONG>::TOTAL;
+    Hot h;
+    load_hot(s, h);
+    int32_t proc[W::SLOTS];
+    processed_by_slot<K, LONG>(words, P, proc);
+    for (int i = 0; i < count; i++) {
+        const int o = first + i;
+        int32_t* r = out4 + 4 * i;
+        r[0] = r[1] = r[2] = 0, r[3] = -1;
+        if (o < 0 || o >= h.num_orders) continue;
+        if (LONG && o >= h.next_order) continue;                      // still in the queue
+        const int sl = slot_of_order<LONG>(words, o);
+        if (sl < 0) {
+            if (LONG && h.act_order >= 0 && o <= h.act_order) r[0] = r[1] = 0x1ff, r[2] = 1;   // retired: complete by construction
+            continue;
+        }
+        const u32 ow = words[W::W_ORDER + sl];
+        r[0] = (int32_t)ord_packaged(ow);
+        r[1] = proc[sl];
+        const int cs = LONG ? (int)(words[W::W_ORDER_C + sl] & 0xffffu) : (int)((words[W::W_CSTEP + (sl >> 2)] >> ((sl & 3) * 8)) & 255u);
+        r[2] = cs != 0, r[3] = cs - 1;
+    }
+}
+
+// ---- canonical record S from packed words: shared pickup station / orders + the given cell ----
+// Long layout (`rq` = the env's ready FIFO): the per-order arrays describe orders [order_base, order_base + 32) with
+// order_base = max(0, next_order - 32) (the 32 most recently popped), tray entries are FJSP_TRAY_ENTRY_LONG, product
+// ids order * 100 + idx as in the reference.  Orders that are loaded but untouched read as zeros, retired ones as complete.
+template <int K, bool LONG>
+inline void export_canon_k(const u32* words, const u32* rq, const Params& P, int cell, FjspCanonState* out, int32_t* order_base_out = nullptr) {
     using W = WM<LONG>;
     ArrayStateT<LONG> s{const_cast<u32*>(words)};
     s.dyn_end = Lay<K, LONG>::DYN_END, s.total = Lay<K, LONG>::TOTAL;
@@ -154,17 +235,18 @@ inline void export_canon_k(const u32* words, const Params& P, int cell, FjspCano
     const int order_base = LONG ? (h.next_order > FJSP_MAX_ORDERS ? h.next_order - FJSP_MAX_ORDERS : 0) : 0;
     if (order_base_out) *order_base_out = order_base;
     auto slot_word = [&](int slot) { return words[W::W_ORDER + slot]; };
-    auto order_id = [&](int slot) { return order_of_slot<LONG>(slot, h.next_order); };
+    auto order_id = [&](int slot) { return LONG ? (int)((words[W::W_ORDER_B + slot] >> 9) & 0xfffu) : slot; };
     auto alloc_idx = [&](int slot, int first) {
-        if (LONG) return (int)((words[W::W_ORDER_B + slot] >> 9) & 0xfffu) + popc32(ord_cut(slot_word(slot)) & ((1u << first) - 1u));
+        if (LONG) return (int)((words[W::W_ORDER_C + slot] >> 16) & 0xfffu) + popc32(ord_cut(slot_word(slot)) & ((1u << first) - 1u));
         int a = 0;
         for (int q = 0; q < slot; q++) a += popc32(ord_cut(slot_word(q))) + 1;
         return a + popc32(ord_cut(slot_word(slot)) & ((1u << first) - 1u));
     };
-    auto entry = [&](int slot, int first, int count) {
-        const int id = P.num_trays - 1 - alloc_idx(slot, first);
-        return LONG ? FJSP_TRAY_ENTRY_LONG(id, order_id(slot), first, count) : FJSP_TRAY_ENTRY(id, slot, first, count);
+    auto make_entry = [&](int alloc, int order, int first, int count) {
+        const int id = P.num_trays - 1 - alloc;
+        return LONG ? FJSP_TRAY_ENTRY_LONG(id, order, first, count) : FJSP_TRAY_ENTRY(id, order, first, count);
     };
+    auto entry = [&](int slot, int first, int count) { return make_entry(alloc_idx(slot, first), order_id(slot), first, count); };
     auto rec_entry = [&](u32 r) { return entry(rec_order(r), rec_first(r), rec_count(r)); };
     auto walk = [&](const Fifo& f, int32_t* dst, int cap) {
         for (int i = 0; i < cap; i++) dst[i] = -1;
@@ -183,16 +265,26 @@ inline void export_canon_k(const u32* words, const Params& P, int cell, FjspCano
     c.ps_order_queue_len = h.num_orders - h.next_order;
     c.ps_current_order = h.cur_order;
     c.ps_product_idx = h.prod_idx;
-    c.ps_current_tray = h.cur_tray_count > 0 ? entry(oslot<LONG>(h.cur_order), h.prod_idx - h.cur_tray_count, h.cur_tray_count) : -1;
+    if (h.cur_tray_count > 0)
+        c.ps_current_tray = LONG ? make_entry(h.alloc_count - 1, h.cur_order, h.prod_idx - h.cur_tray_count, h.cur_tray_count)
+                                 : entry(h.cur_order, h.prod_idx - h.cur_tray_count, h.cur_tray_count);
+    else
+        c.ps_current_tray = -1;
     c.ps_trays_at_station = (P.num_trays < 1000 ? P.num_trays : 1000) - h.alloc_count;
     for (int i = 0; i < FJSP_CANON_PS_READY; i++) c.ps_ready[i] = -1;
-    {
+    if (LONG) {  // the ready FIFO: entry index = allocation index of the tray
+        for (int i = 0; i < h.ready_count && i < FJSP_CANON_PS_READY; i++) {
+            const u32 e = rq ? rq[(h.ready_order + i) & (READY_FIFO_WORDS - 1)] : 0u;
+            c.ps_ready[i] = make_entry(h.ready_order + i, rq_order(e), rq_first(e), rq_count(e));
+        }
+        c.ps_ready_n = h.ready_count;
+    } else {
         int o = h.ready_order, f = h.ready_idx;
         for (int i = 0; i < h.ready_count && i < FJSP_CANON_PS_READY; i++) {
-            u32 ow = slot_word(oslot<LONG>(o));
+            u32 ow = slot_word(o);
             u32 cuts = ord_cut(ow) >> f;
             int cnt = cuts ? ctz32(cuts) + 1 : ord_n(ow) - f;
-            c.ps_ready[i] = entry(oslot<LONG>(o), f, cnt);
+            c.ps_ready[i] = entry(o, f, cnt);
             f += cnt;
             if (f >= ord_n(ow)) o++, f = 0;
         }
@@ -224,75 +316,14 @@ inline void export_canon_k(const u32* words, const Params& P, int cell, FjspCano
         c.pack[i].queue_n = p.qcount;
     }
     // per-order arrays: orders order_base .. order_base + 31 (compact: 0..31)
-    int32_t proc_ring[W::RING];
-    for (int sl = 0; sl < W::RING; sl++) proc_ring[sl] = LONG ? (int32_t)(words[W::W_ORDER_B + sl] & 0x1ffu) : (int32_t)ord_packaged(slot_word(sl));
-    // is_processed is a property of the products, whatever cell their tray is in: scan every cell's pool and machines
-    for (int cc = 0; cc < K; cc++) {
-        HotCell x;
-        load_cell<K>(s, cc, x);
-        const int xb = pool_base<LONG>(cc);
-        uint64_t free_bits = (uint64_t)x.free_lo | ((uint64_t)x.free_hi << 32);
-        for (int slot = 0; slot < FJSP_POOL_SLOTS; slot++) {
-            if ((free_bits >> slot) & 1u) continue;
-            u32 r = words[xb + slot];
-            if (rec_processed(r)) proc_ring[rec_order(r)] |= (int32_t)(((1u << rec_count(r)) - 1u) << rec_first(r));
-        }
-        for (int i = 0; i < 2; i++) {
-            const Mach& m = x.m[i];
-            if (!m.busy) continue;  // products flagged so far: i <= (last executed step - start) / per
-            u32 r = words[xb + m.cur];
-            int per = i == 0 ? P.small_steps : P.big_steps;
-            int done = (h.step - 1 - m.start) / per;
-            if (done > rec_count(r)) done = rec_count(r);
-            if (done < 0) done = 0;
-            proc_ring[rec_order(r)] |= (int32_t)(((1u << done) - 1u) << rec_first(r));
-        }
-    }
+    int32_t out4[4 * FJSP_MAX_ORDERS];
+    export_orders_k<K, LONG>(words, P, order_base, FJSP_MAX_ORDERS, out4);
     for (int i = 0; i < FJSP_MAX_ORDERS; i++) {
-        const int o = order_base + i;
-        c.order_completion_step[i] = -1;
-        if (LONG && o >= h.next_order) continue;  // not popped yet: not in the ring
-        const int sl = oslot<LONG>(o);
-        u32 ow = slot_word(sl);
-        c.packaged_mask[i] = (int32_t)ord_packaged(ow);
-        c.processed_mask[i] = proc_ring[sl] | (LONG ? 0 : 0);
-        int cs = LONG ? (int)((words[W::W_CSTEP + (sl >> 1)] >> ((sl & 1) * 16)) & 0xffffu) : (int)((words[W::W_CSTEP + (sl >> 2)] >> ((sl & 3) * 8)) & 255u);
-        c.order_complete[i] = cs != 0;
-        c.order_completion_step[i] = cs - 1;
+        c.packaged_mask[i] = out4[4 * i], c.processed_mask[i] = out4[4 * i + 1];
+        c.order_complete[i] = out4[4 * i + 2], c.order_completion_step[i] = out4[4 * i + 3];
     }
     c.total_products_packaged = h.total_packaged;
     c.completed_orders = h.completed_orders;
-}
-
-// per-order records for orders [first, first + count): {packaged_mask, processed_mask, complete, completion_step}
-template <int K, bool LONG>
-inline void export_orders_k(const u32* words, const Params& P, int first, int count, int32_t* out4) {
-    using W = WM<LONG>;
-    ArrayStateT<LONG> s{const_cast<u32*>(words)};
-    Hot h;
-    load_hot(s, h);
-    // processed bits of trays still in pools / machines: reuse the canonical export of cell 0 (it scans every cell)
-    FjspCanonState c;
-    int32_t base = 0;
-    export_canon_k<K, LONG>(words, P, 0, &c, &base);
-    for (int i = 0; i < count; i++) {
-        const int o = first + i;
-        int32_t* r = out4 + 4 * i;
-        r[0] = r[1] = r[2] = 0, r[3] = -1;
-        if (o < 0 || o >= h.num_orders) continue;
-        if (LONG && o >= h.next_order) continue;                      // still in the queue
-        if (LONG && o < h.next_order - W::RING) {                      // left the ring: complete by construction
-            r[0] = r[1] = 0x1ff, r[2] = 1;
-            continue;
-        }
-        const int sl = oslot<LONG>(o);
-        const u32 ow = words[W::W_ORDER + sl];
-        r[0] = (int32_t)ord_packaged(ow);
-        if (o >= base && o < base + FJSP_MAX_ORDERS) r[1] = c.processed_mask[o - base];
-        else r[1] = LONG ? (int32_t)(words[W::W_ORDER_B + sl] & 0x1ffu) : 0;  // (older ring entries: finished trays only)
-        const int cs = LONG ? (int)((words[W::W_CSTEP + (sl >> 1)] >> ((sl & 1) * 16)) & 0xffffu) : (int)((words[W::W_CSTEP + (sl >> 2)] >> ((sl & 3) * 8)) & 255u);
-        r[2] = cs != 0, r[3] = cs - 1;
-    }
 }
 
 template <class F>
@@ -312,8 +343,9 @@ inline void dispatch_layout(int cells, bool long_streams, F&& f) {
 #undef FJSP_CASE
 }
 
-inline void export_canon(const u32* words, const Params& P, int cells, bool long_streams, int cell, FjspCanonState* out, int32_t* order_base = nullptr) {
-    dispatch_layout(cells, long_streams, [&](auto k, auto l) { export_canon_k<decltype(k)::value, decltype(l)::value>(words, P, cell, out, order_base); });
+inline void export_canon(const u32* words, const u32* rq, const Params& P, int cells, bool long_streams, int cell, FjspCanonState* out,
+                         int32_t* order_base = nullptr) {
+    dispatch_layout(cells, long_streams, [&](auto k, auto l) { export_canon_k<decltype(k)::value, decltype(l)::value>(words, rq, P, cell, out, order_base); });
 }
 inline void export_orders(const u32* words, const Params& P, int cells, bool long_streams, int first, int count, int32_t* out4) {
     dispatch_layout(cells, long_streams, [&](auto k, auto l) { export_orders_k<decltype(k)::value, decltype(l)::value>(words, P, first, count, out4); });

@@ -56,6 +56,9 @@ struct Geo {
 #define FJSP_ORDER_SOURCE_MEMBERS                                                                          \
     uint64_t seed = 0, genv = 0;                                                                           \
     const FjspOrderRec* otab = nullptr;                                                                    \
+    u32* rq = nullptr; /* this env's ready FIFO (HBM side buffer, READY_FIFO_WORDS entries) */             \
+    __device__ __forceinline__ u32 rq_ld(int i) const { return rq[i & (READY_FIFO_WORDS - 1)]; }           \
+    __device__ __forceinline__ void rq_st(int i, u32 v) { rq[i & (READY_FIFO_WORDS - 1)] = v; }            \
     __device__ __forceinline__ u32 fetch_order(int o, u32 episode) const {                                 \
         if (otab) {                                                                                        \
             bool bad = false;                                                                              \
@@ -206,6 +209,7 @@ struct StepArgs {
     int32_t prefetch_tiles_env;  // the same for the thread-per-env kernel
     const FjspOrderRec* otab;    // long layout: explicit order tables [N][otab_stride], or null = Philox order stream
     int32_t otab_stride;
+    u32* rq;                     // long layout: ready FIFOs [N][READY_FIFO_WORDS]
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -284,6 +288,7 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
     // and the action bytes
     TileColumnT<LONG> s{s_dyn + tid - G::DYN0 * TILE, g_tile + tid};
     s.seed = A.seed, s.genv = (uint64_t)(A.first_env + env), s.otab = (A.otab && valid) ? A.otab + env * A.otab_stride : nullptr;
+    s.rq = (LONG && valid) ? A.rq + env * READY_FIFO_WORDS : nullptr;
     Hot h;
     HotCell c0;
     load_hot(s, h);
@@ -392,6 +397,7 @@ __global__ void __launch_bounds__(TILE* K, Geo<K, LONG>::CELLS_CTAS_PER_SM) fjsp
     TileColumnSharedT<LONG> s;
     s.dyn = s_dyn + e - G::DYN0 * TILE, s.hot = g_tile + e;
     s.seed = A.seed, s.genv = (uint64_t)(A.first_env + env), s.otab = (A.otab && valid) ? A.otab + env * A.otab_stride : nullptr;
+    s.rq = (LONG && valid) ? A.rq + env * READY_FIFO_WORDS : nullptr;
     XchgColumn x{s_x + e};
     CellLane L;
     L.c = c;
@@ -513,7 +519,7 @@ __global__ void fjsp_random_actions_kernel(uint8_t* actions, int64_t num_envs, i
 template <int K, bool LONG = false>
 __global__ void __launch_bounds__(TILE) fjsp_rollout_kernel(const __grid_constant__ Params P, u32* state, int64_t num_envs,
                                                              int64_t first_env, uint64_t seed, uint64_t t0, int steps,
-                                                             int num_orders, unsigned long long* stats) {
+                                                             int num_orders, unsigned long long* stats, u32* rq) {
     using G = Geo<K, LONG>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     u32* s_dyn = reinterpret_cast<u32*>(smem_raw);
@@ -533,6 +539,7 @@ __global__ void __launch_bounds__(TILE) fjsp_rollout_kernel(const __grid_constan
     }
     TileColumnT<LONG> s{s_dyn + tid - G::DYN0 * TILE, g_tile + tid};
     s.seed = seed, s.genv = (uint64_t)(first_env + env);
+    s.rq = (LONG && valid) ? rq + env * READY_FIFO_WORDS : nullptr;
     Hot h;  // hot words of the pickup station and of cell 0 live in registers for the whole launch
     HotCell c0;
     load_hot(s, h);
@@ -596,7 +603,7 @@ template <int K, bool LONG = false>
 __global__ void __launch_bounds__(TILE* K, Geo<K, LONG>::CELLS_CTAS_PER_SM) fjsp_rollout_cells_kernel(const __grid_constant__ Params P, u32* state,
                                                                                                 int64_t num_envs, int64_t first_env,
                                                                                                 uint64_t seed, uint64_t t0, int steps,
-                                                                                                int num_orders, unsigned long long* stats) {
+                                                                                                int num_orders, unsigned long long* stats, u32* rq) {
     using G = Geo<K, LONG>;
     constexpr int NT = TILE * K;
     constexpr int AG = Lay<K>::AGENTS;
@@ -620,6 +627,7 @@ __global__ void __launch_bounds__(TILE* K, Geo<K, LONG>::CELLS_CTAS_PER_SM) fjsp
     TileColumnSharedT<LONG> s;
     s.dyn = s_dyn + e - G::DYN0 * TILE, s.hot = g_tile + e;
     s.seed = seed, s.genv = (uint64_t)(first_env + env);
+    s.rq = (LONG && valid) ? rq + env * READY_FIFO_WORDS : nullptr;
     XchgColumn x{s_x + e};
     CellLane L;
     L.c = c;

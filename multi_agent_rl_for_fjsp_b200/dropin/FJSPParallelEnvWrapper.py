@@ -103,21 +103,23 @@ class SimulationView:
     @property
     def orders(self):
         s, out = self._s(), []
+        recs = self._f._order_records()
         for o in range(int(s["num_orders"])):
             n, t, c = self._f._orders[o]
+            km, pm, done, cs = (int(v) for v in recs[o])
             prods = [_Obj(id=o * 100 + i, order_id=o, product_type=_Obj(name=("", "SMALL", "MEDIUM", "BIG")[t], value=t),
                           packaging_color=_Obj(name=("", "RED", "BLUE", "GREEN")[c], value=c),
-                          is_processed=bool((int(s["processed_mask"][o]) >> i) & 1),
-                          is_packaged=bool((int(s["packaged_mask"][o]) >> i) & 1)) for i in range(n)]
-            cs = int(s["order_completion_step"][o])
-            out.append(_Obj(id=o, products=prods, is_complete=bool(s["order_complete"][o]),
+                          is_processed=bool((pm >> i) & 1), is_packaged=bool((km >> i) & 1)) for i in range(n)]
+            if cs < 0 and done:  # long order streams: the packed state has let go of the order; the facade remembers when it completed
+                cs = self._f._completion_steps.get(o, -1)
+            out.append(_Obj(id=o, products=prods, is_complete=bool(done),
                             completion_time=None if cs < 0 else float((cs + 1) * self._f.config["step_size"])))
         return out
 
     @property
     def completed_orders(self):
         done = [o for o in self.orders if o.is_complete]
-        return sorted(done, key=lambda o: (o.completion_time, o.id))
+        return sorted(done, key=lambda o: (o.completion_time if o.completion_time is not None else -1.0, o.id))
 
     # ---- object-graph views read by the reference's heuristic policy and visualiser (a2c.py:407-535)
     def _tray(self, entry):
@@ -125,16 +127,18 @@ class SimulationView:
         entry = int(entry)
         if entry < 0:
             return None
-        s = self._s()
-        o, first, cnt = (entry >> 16) & 63, (entry >> 22) & 15, (entry >> 26) & 7
+        if self._f._env.long_streams:   # FJSP_TRAY_ENTRY_LONG
+            tid, o, first, cnt = entry & 0xfff, (entry >> 12) & 0xfff, (entry >> 24) & 15, (entry >> 28) & 7
+        else:
+            tid, o, first, cnt = entry & 0xffff, (entry >> 16) & 63, (entry >> 22) & 15, (entry >> 26) & 7
         n, t, c = self._f._orders[o]
+        km, pm = int(self._f._order_records()[o][0]), int(self._f._order_records()[o][1])
         bits = ((1 << cnt) - 1) << first
-        prods = [_Obj(id=o * 100 + i, order_id=o, is_processed=bool((int(s["processed_mask"][o]) >> i) & 1),
-                      is_packaged=bool((int(s["packaged_mask"][o]) >> i) & 1)) for i in range(first, first + cnt)]
-        return _Obj(id=entry & 0xffff, order_id=o, products=prods, capacity=5,
+        prods = [_Obj(id=o * 100 + i, order_id=o, is_processed=bool((pm >> i) & 1), is_packaged=bool((km >> i) & 1))
+                 for i in range(first, first + cnt)]
+        return _Obj(id=tid, order_id=o, products=prods, capacity=5,
                     tray_type=("", "SMALL", "MEDIUM", "BIG")[t], tray_color=("", "RED", "BLUE", "GREEN")[c],
-                    needs_processing=(int(s["processed_mask"][o]) & bits) != bits,
-                    needs_packaging=(int(s["packaged_mask"][o]) & bits) != bits)
+                    needs_processing=(pm & bits) != bits, needs_packaging=(km & bits) != bits)
 
     def _trays(self, arr, n):
         return [self._tray(e) for e in arr[:int(n)]]
@@ -213,8 +217,14 @@ class FJSPParallelEnv(_Base):
         if "num_cells" not in self.config and os.environ.get("FJSP_B200_NUM_CELLS"):
             self.config["num_cells"] = int(os.environ["FJSP_B200_NUM_CELLS"])
         self.num_cells = int(self.config.get("num_cells", 1))
+        self._device = device
+        # the reference accepts any num_orders (FJSPSimulation.py:315-318) and max_episode_steps (:223): episodes beyond the
+        # compact packed state (32 orders, 240 steps) run on the long order-stream layout (include/fjsp_b200.h)
+        if int(self.config.get("max_episode_steps", 200)) > 240:
+            self.config["long_streams"] = 1
         self._env = BatchedFJSPEnv(1, config=abi.config_from_dict(self.config), device=device, autoreset=False,
                                    with_infos=True)
+        self._completion_steps, self._orders_done_seen, self._recs = {}, 0, None
         self._ids, self._nact, self._obs_slices, self._mask_off = agent_layout(self.num_cells)
         self._dims = abi.dims(self.num_cells)
         self.possible_agents = list(self._ids)
@@ -242,9 +252,15 @@ class FJSPParallelEnv(_Base):
         self._orders = draw_reference_orders(n)
 
     def _order_table(self):
-        if len(self._orders) > abi.MAX_ORDERS:
-            raise ValueError("num_orders > %d is not supported by the packed state" % abi.MAX_ORDERS)
-        tab = np.zeros((1, abi.MAX_ORDERS), dtype=np.uint32)
+        if len(self._orders) > abi.LONG_MAX_ORDERS:
+            raise ValueError("num_orders > %d is not supported by the packed state" % abi.LONG_MAX_ORDERS)
+        if len(self._orders) > abi.MAX_ORDERS and not self._env.long_streams:
+            # more orders than the compact layout holds: continue on the long order-stream layout
+            self._env.close()
+            self.config["long_streams"] = 1
+            self._env = BatchedFJSPEnv(1, config=abi.config_from_dict(self.config), device=self._device, autoreset=False,
+                                       with_infos=True)
+        tab = np.zeros((1, max(len(self._orders), 1) if self._env.long_streams else abi.MAX_ORDERS), dtype=np.uint32)
         for i, (k, t, c) in enumerate(self._orders):
             tab[0, i] = abi.order_rec(k, t, c)
         self._env.num_orders = len(self._orders)
@@ -257,7 +273,8 @@ class FJSPParallelEnv(_Base):
             np.random.seed(seed)
         self._gen_orders(num_orders if num_orders is not None else 30)
         obs, masks = self._env.reset(orders=self._order_table())
-        self._cache = None
+        self._cache, self._recs = None, None
+        self._completion_steps, self._orders_done_seen = {}, 0
         observations = self._obs_dicts(obs[0].cpu().numpy(), masks[0].cpu().numpy())
         return observations, {a: {} for a in self.possible_agents}
 
@@ -276,7 +293,7 @@ class FJSPParallelEnv(_Base):
             # for every agent action 0 has exactly that effect, except that its idle penalty must not apply.
         e = self._env
         obs, rew, term, trunc, masks = e.step(torch.from_numpy(a))
-        self._cache = None
+        self._cache, self._recs = None, None
         out = torch.cat([obs[0], rew[0], e.flags[0].float(), e.infos[0].float(), e.results[0].float(),
                          masks[0].float()]).cpu().numpy()
         p = n_obs + n_act
@@ -305,6 +322,12 @@ class FJSPParallelEnv(_Base):
                     4: "stepped past the end of the episode (call reset() after truncation)",
                     5: "more open orders than the order ring of the packed state holds"}.get(int(flags[2]), "fault %d" % int(flags[2]))
             raise RuntimeError("fjsp_b200 capacity limit, not a reference error: " + what)
+        if e.long_streams and int(infos[1]) != self._orders_done_seen:
+            # an order's record leaves the packed state one step after it completes: note its completion step now
+            self._orders_done_seen = int(infos[1])
+            for o, r in enumerate(self._order_records()):
+                if r[2] and r[3] >= 0:
+                    self._completion_steps.setdefault(o, int(r[3]))
         terminated, truncated = bool(flags[0]), bool(flags[1])
         terminations = {aid: terminated for aid in ids}
         truncations = {aid: truncated for aid in ids}
@@ -346,6 +369,12 @@ class FJSPParallelEnv(_Base):
         if self._cache is None:
             self._cache = self._env.export_state(0)
         return self._cache
+
+    def _order_records(self):
+        """[num_orders, 4]: packaged_mask, processed_mask, is_complete, completion_step of every order of the episode."""
+        if self._recs is None:
+            self._recs = self._env.export_orders(0, 0, max(len(self._orders), 1))
+        return self._recs
 
     # ---- misc surface
     def render(self):

@@ -69,7 +69,9 @@ class BatchedFJSPEnv:
         self.cells = int(self.cfg.num_cells)
         if not 1 <= self.cells <= abi.MAX_CELLS:
             raise ValueError("num_cells must be in 1..%d" % abi.MAX_CELLS)
-        self.dims = abi.dims(self.cells)
+        self.long_streams = bool(self.cfg.long_streams)   # the long order-stream layout (include/fjsp_b200.h)
+        self.max_orders = abi.LONG_MAX_ORDERS if self.long_streams else abi.MAX_ORDERS
+        self.dims = abi.dims(self.cells, self.long_streams)
         self.agent_ids, self.n_actions, self.obs_slices, self.mask_offsets = agent_layout(self.cells)
         self.act_dim, self.obs_dim, self.mask_dim = self.dims["act"], self.dims["obs"], self.dims["mask"]
         self.seed, self.num_orders, self.autoreset = int(seed), int(num_orders), bool(autoreset)
@@ -129,7 +131,8 @@ class BatchedFJSPEnv:
         """FJSPParallelEnv.reset for all (or the masked) envs.
 
         orders: optional explicit order tables, uint32 tensor/array [N, 32] packed n | type<<8 | colour<<16
-        (``abi.order_rec``) or int array [N, num_orders, 3]; default: Philox stream (seed, global env, episode 0).
+        (``abi.order_rec``; long order streams: [N, num_orders]) or int array [N, num_orders, 3]; default: Philox stream
+        (seed, global env, episode 0).
         """
         if seed is not None:
             self.seed = int(seed)
@@ -153,16 +156,20 @@ class BatchedFJSPEnv:
 
     def _pack_orders(self, orders, env_mask=None):
         arr = orders.detach().cpu().numpy() if isinstance(orders, torch.Tensor) else np.asarray(orders)
-        if arr.ndim == 3:  # [N, k, 3] -> packed [N, 32]
+        if arr.ndim == 3:  # [N, k, 3] -> packed [N, 32] (long order streams: [N, k])
             n, k, _ = arr.shape
-            packed = np.zeros((n, abi.MAX_ORDERS), dtype=np.uint32)
+            packed = np.zeros((n, max(k, 1) if self.long_streams else abi.MAX_ORDERS), dtype=np.uint32)
             packed[:, :k] = (arr[..., 0].astype(np.uint32) | (arr[..., 1].astype(np.uint32) << 8) |
                              (arr[..., 2].astype(np.uint32) << 16))
             if self.num_orders != k:
                 self.num_orders = k
             arr = packed
         arr = np.ascontiguousarray(arr, dtype=np.uint32)
-        assert arr.shape == (self.num_envs, abi.MAX_ORDERS), arr.shape
+        if self.long_streams:
+            assert arr.ndim == 2 and arr.shape[0] == self.num_envs and arr.shape[1] >= self.num_orders, arr.shape
+            arr = np.ascontiguousarray(arr[:, :max(self.num_orders, 1)])
+        else:
+            assert arr.shape == (self.num_envs, abi.MAX_ORDERS), arr.shape
         live = arr[:, :self.num_orders]
         if env_mask is not None:  # only the rows of the envs being reset are read
             live = live[np.asarray(env_mask.cpu() if isinstance(env_mask, torch.Tensor) else env_mask).astype(bool).reshape(-1)]
@@ -287,6 +294,13 @@ class BatchedFJSPEnv:
         s = np.zeros((), dtype=abi.CANON_DT)
         abi.check(self._L.fjsp_export_state_cell(self._h, int(env), int(cell), C.c_void_p(s.ctypes.data)))
         return s
+
+    def export_orders(self, env: int, first: int, count: int) -> np.ndarray:
+        """[count, 4] int32: packaged_mask, processed_mask, is_complete, completion_step of orders first .. first+count-1
+        (synchronises; conventions of the long layout in include/fjsp_b200.h fjsp_export_orders)."""
+        out = np.zeros((count, 4), dtype=np.int32)
+        abi.check(self._L.fjsp_export_orders(self._h, int(env), int(first), int(count), C.c_void_p(out.ctypes.data), None))
+        return out
 
     def export_packed(self, env: int) -> np.ndarray:
         w = np.zeros(self.dims["state_words"], dtype=np.uint32)

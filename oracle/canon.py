@@ -131,6 +131,81 @@ def export_reference(sim) -> np.ndarray:
     return s
 
 
+def tray_entry_long(tray) -> int:
+    """FJSP_TRAY_ENTRY_LONG: tray_id | order<<12 | first<<24 | count<<28 (long order streams, include/fjsp_b200.h)."""
+    if tray is None:
+        return -1
+    prods = tray.products
+    if not prods:
+        return int(tray.id)
+    return int(tray.id) | (int(prods[0].order_id) << 12) | ((int(prods[0].id) % 100) << 24) | (len(prods) << 28)
+
+
+def export_reference_long(sim) -> np.ndarray:
+    """The canonical record of a live reference simulation under the conventions of the port's LONG layout
+    (include/fjsp_b200.h fjsp_export_orders): tray entries are FJSP_TRAY_ENTRY_LONG; the per-order arrays describe the 32
+    most recently popped orders; an order reads "complete, all bits, step -1" from the second step after its completion
+    (the port has given its slot back by then); list fields are cut at the record's capacity with the true length kept."""
+    s = empty_canon()
+    step_size = sim.config["step_size"]
+    te = tray_entry_long
+    s["current_step"] = sim.current_step
+    s["num_orders"] = len(sim.orders)
+    agv = sim.agv
+    s["agv_row"], s["agv_col"] = int(agv.position[0]), int(agv.position[1])
+    s["agv_carry"] = te(agv.carrying_tray)
+    s["agv_is_moving"] = int(bool(agv.is_moving))
+    ps = sim.pickup_station
+    s["ps_order_queue_len"] = len(ps.order_queue)
+    s["ps_current_order"] = ps.current_order.id if ps.current_order else -1
+    s["ps_product_idx"] = ps.current_order_product_idx
+    s["ps_current_tray"] = te(ps.current_tray)
+    s["ps_trays_at_station"] = len(ps.trays_at_station)
+    ready = [te(t) for t in ps.ready_trays]
+    s["ps_ready"][:min(len(ready), PS_READY)] = ready[:PS_READY]
+    s["ps_ready_n"] = len(ready)
+    for mi, m in enumerate((sim.small_machine, sim.big_machine)):
+        rec = s["machine"][mi]
+        rec["is_busy"] = int(bool(m.is_busy))
+        rec["current_tray"] = te(m.current_tray)
+        rec["progress_done"] = int(m.processing_progress == 1.0)
+        rec["queue_n"] = _fill(None, rec["queue"], [te(t) for t in m.tray_queue])
+        rec["ready_n"] = _fill(None, rec["ready"], [te(t) for t in m.ready_trays])
+    s["storage_n"] = _fill(None, s["storage"], [te(t) for t in sim.storage.trays])
+    for pi, pid in enumerate(PACK_IDS):
+        st = sim.packaging_stations[pid]
+        rec = s["pack"][pi]
+        rec["is_busy"] = int(bool(st.is_busy))
+        rec["current_product"] = st.current_product.id if st.current_product is not None else -1
+        rec["progress_L"] = int(round(100.0 / st.processing_progress)) if st.processing_progress else 0
+        rec["products_completed"] = st.products_completed
+        rec["users"] = st.resource.count
+        rec["queue_n"] = _fill(None, rec["queue"], [p.id for p in st.product_queue])
+    popped = len(sim.orders) - len(ps.order_queue)
+    base = max(0, popped - MAX_ORDERS)
+    for i in range(MAX_ORDERS):
+        oid = base + i
+        if oid >= popped:
+            continue
+        o = sim.orders[oid]
+        k = None if o.completion_time is None else int(o.completion_time / step_size - 1)
+        if o.is_complete and k < sim.current_step - 1:
+            s["processed_mask"][i] = s["packaged_mask"][i] = 0x1FF
+            s["order_complete"][i] = 1
+            continue
+        pm = km = 0
+        for j, p in enumerate(o.products):
+            pm |= int(bool(p.is_processed)) << j
+            km |= int(bool(p.is_packaged)) << j
+        s["processed_mask"][i], s["packaged_mask"][i] = pm, km
+        s["order_complete"][i] = int(bool(o.is_complete))
+        if k is not None:
+            s["order_completion_step"][i] = k
+    s["total_products_packaged"] = sim.total_products_packaged
+    s["completed_orders"] = len(sim.completed_orders)
+    return s
+
+
 def diff(a: np.ndarray, b: np.ndarray, prefix: str = "") -> list:
     """Field-wise differences between two canonical records (empty list = bit-exact)."""
     out = []

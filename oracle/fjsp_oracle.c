@@ -34,9 +34,18 @@
 
 #include "../include/fjsp_b200.h"
 
-#define MAX_PRODUCTS (FJSP_MAX_ORDERS * FJSP_MAX_ORDER_PRODUCTS)
+/* Two builds of this file: the default one (episodes of <= 32 orders and <= 253 steps: small envs, thousands of them for
+ * the CPU baseline) and -DFJSP_ORACLE_LONG (long order streams: up to 4095 orders, 1000 trays, order arrivals). */
+#ifdef FJSP_ORACLE_LONG
+#define ORC_MAX_ORDERS FJSP_LONG_MAX_ORDERS
+#define MAX_TRAYS 1100 /* min(num_trays, 1000) trays ever reach the pickup station (FJSPSimulation.py:96) */
+#define LIST_CAP 1100
+#else
+#define ORC_MAX_ORDERS FJSP_MAX_ORDERS
 #define MAX_TRAYS 256 /* one tray per LOAD at most, episodes are <= 253 steps */
 #define LIST_CAP 320
+#endif
+#define MAX_PRODUCTS (ORC_MAX_ORDERS * FJSP_MAX_ORDER_PRODUCTS)
 
 enum { LOC_PICKUP = 0, LOC_BIG = 1, LOC_SMALL = 2, LOC_STORAGE = 3, LOC_PACKAGING = 4, LOC_NONE = -1 };
 enum { TYPE_SMALL = 1, TYPE_MEDIUM = 2, TYPE_BIG = 3 };
@@ -49,6 +58,7 @@ typedef struct Prod {
 
 typedef struct Order {
     int id, n;
+    int in_process; /* an AGV has taken the order's first tray (the port's long layout gives it an order slot then) */
     Prod* products[FJSP_MAX_ORDER_PRODUCTS];
     int is_complete, completion_step;
 } Order;
@@ -117,8 +127,11 @@ typedef struct OracleEnv {
     int small_steps, big_steps, pack_steps;
     Prod prods[MAX_PRODUCTS];
     int nprods;
-    Order orders[FJSP_MAX_ORDERS];
-    int norders;
+    Order orders[ORC_MAX_ORDERS];
+    int norders;       /* orders that exist (arrived) */
+    int norders_table; /* orders whose attributes are known (long order streams: arrivals reveal the next one) */
+    uint64_t seed, genv; /* arrival stream (long order streams) */
+    uint32_t episode;
     Tray trays[MAX_TRAYS];
     int ntrays_total;
     /* pickup station */
@@ -134,6 +147,8 @@ typedef struct OracleEnv {
     /* tracking */
     int current_step, completed_orders, total_products_packaged, fault;
 } OracleEnv;
+
+void fjsp_oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
 /* ------------------------------------------------------------------ helpers */
 static void tl_push(TrayList* l, Tray* t) {
@@ -217,7 +232,7 @@ void fjsp_oracle_reset(OracleEnv* e, const FjspOrderRec* orders, int num_orders)
     /* _init_trays (:89-98): ids 0..num_trays-1, popped from the END into trays_at_station, at most 1000 */
     e->ntrays_total = cfg.num_trays < 1000 ? cfg.num_trays : 1000; /* tray i (allocation order) has id num_trays-1-i */
     /* generate_order x num_orders (:101-131, :315-318) */
-    if (num_orders > FJSP_MAX_ORDERS) num_orders = FJSP_MAX_ORDERS;
+    if (num_orders > ORC_MAX_ORDERS) num_orders = ORC_MAX_ORDERS;
     for (int o = 0; o < num_orders; o++) {
         uint32_t r = orders[o];
         int n = (int)(r & 0xff), type = (int)((r >> 8) & 0xff), colour = (int)((r >> 16) & 0xff);
@@ -232,6 +247,17 @@ void fjsp_oracle_reset(OracleEnv* e, const FjspOrderRec* orders, int num_orders)
         }
     }
     e->norders = num_orders;
+    e->norders_table = num_orders;
+}
+
+/* Long order streams with arrivals (builder-defined extension, include/fjsp_b200.h): `orders` holds the attributes of all
+ * num_table orders that can ever exist, num_initial of them exist at reset; one more arrives per step with probability
+ * arrival_prob_q16 / 65536 from Philox(key = seed, counter = (genv, episode, step, 5)) until arrival_max_orders exist. */
+void fjsp_oracle_reset_stream(OracleEnv* e, const FjspOrderRec* orders, int num_table, int num_initial, uint64_t seed, uint64_t genv,
+                              uint32_t episode) {
+    fjsp_oracle_reset(e, orders, num_table);
+    e->norders = num_initial < e->norders_table ? num_initial : e->norders_table;
+    e->seed = seed, e->genv = genv, e->episode = episode;
 }
 
 /* ------------------------------------------------------------------ observations (R9) */
@@ -469,6 +495,19 @@ static double act_agv(OracleEnv* e, Cell* c, int action, uint8_t* res) {
             invalid = 1;
         } else {
             Tray* t = NULL;
+            if (loc == LOC_PICKUP && e->cfg.long_streams && e->ps_ready.n > 0 && !e->orders[e->ps_ready.a[0]->order_id].in_process) {
+                /* capacity of the port's long layout (not reference behaviour): FJSP_LONG_ORDER_SLOTS orders can be in process
+                 * at once; an order leaves one step after it completes */
+                int active = 0;
+                for (int o = 0; o < e->order_queue_head; o++)
+                    active += e->orders[o].in_process && !(e->orders[o].is_complete && e->orders[o].completion_step < e->current_step);
+                if (active >= FJSP_LONG_ORDER_SLOTS) {
+                    e->fault = FJSP_FAULT_ORDER_SLOTS;
+                    loc = LOC_NONE; /* -> invalid_action below, the tray stays where it is */
+                } else {
+                    e->orders[e->ps_ready.a[0]->order_id].in_process = 1;
+                }
+            }
             if (loc == LOC_PICKUP) t = tl_pop0(&e->ps_ready);
             else if (loc == LOC_SMALL) t = tl_pop0(&c->machine[0].ready);
             else if (loc == LOC_BIG) t = tl_pop0(&c->machine[1].ready);
@@ -683,6 +722,21 @@ void fjsp_oracle_step(OracleEnv* e, const uint8_t* actions, float* obs, int8_t* 
     int orders_before = e->completed_orders;
     int products_before = e->total_products_packaged;
     double local[FJSP_ACT_DIM_K(FJSP_MAX_CELLS)];
+    if (e->current_step > e->cfg.max_episode_steps) {
+        /* stepped after the truncation step without a reset: the port's env is inert and says so (the reference would go
+         * on simulating; include/fjsp_b200.h FJSP_FAULT_PAST_END) */
+        for (int i = 0; i < FJSP_ACT_DIM_K(K); i++) res[i] = 0;
+        for (int i = 0; i < A; i++) rewards[i] = 0.0;
+        if (obs && masks) fjsp_oracle_observe(e, obs, masks);
+        flags[0] = 0, flags[1] = 1, flags[2] = FJSP_FAULT_PAST_END, flags[3] = 0;
+        return;
+    }
+    /* 0. order arrivals (extension, long order streams only) */
+    if (e->cfg.long_streams && e->cfg.arrival_prob_q16 > 0 && e->norders < e->cfg.arrival_max_orders && e->norders < e->norders_table) {
+        uint32_t ctr[4] = {(uint32_t)e->genv, e->episode, (uint32_t)e->current_step, 5u}, key[2] = {(uint32_t)e->seed, (uint32_t)(e->seed >> 32)}, r[4];
+        fjsp_oracle_philox(ctr, key, r);
+        if ((r[0] & 0xffffu) < (uint32_t)e->cfg.arrival_prob_q16) e->norders++;
+    }
     /* 1. actions in dict order (FJSPSimulation.py:172-174, :76-82): pickup station, then cell by cell agv, small
      *    machine, big machine, four packaging stations (one cell = the reference's order) */
     local[0] = act_pickup(e, actions[0], &res[0]);
@@ -726,15 +780,18 @@ void fjsp_oracle_step(OracleEnv* e, const uint8_t* actions, float* obs, int8_t* 
     if (obs && masks) fjsp_oracle_observe(e, obs, masks);
     /* 6. termination / truncation (:216-224), pre-increment current_step */
     int all_done = e->completed_orders == e->norders && e->norders > 0 && order_queue_len(e) == 0;
+    if (e->cfg.long_streams && e->cfg.arrival_prob_q16 > 0 && e->norders < e->cfg.arrival_max_orders) all_done = 0;
     int truncated = e->current_step >= e->cfg.max_episode_steps;
     flags[0] = (uint8_t)all_done, flags[1] = (uint8_t)truncated, flags[2] = (uint8_t)e->fault, flags[3] = 0;
     e->current_step++;
 }
 
 /* ------------------------------------------------------------------ canonical record S */
+static int g_long_entries = 0; /* set by the exporter: FJSP_TRAY_ENTRY_LONG for envs with long_streams */
 static int32_t tray_entry(const Tray* t) {
     if (!t) return -1;
     if (t->n == 0) return t->id;
+    if (g_long_entries) return FJSP_TRAY_ENTRY_LONG(t->id, t->products[0]->order, t->products[0]->idx, t->n);
     return FJSP_TRAY_ENTRY(t->id, t->products[0]->order, t->products[0]->idx, t->n);
 }
 static int fill_trays(int32_t* dst, int cap, const TrayList* l) {
@@ -742,10 +799,33 @@ static int fill_trays(int32_t* dst, int cap, const TrayList* l) {
     for (int i = 0; i < l->n && i < cap; i++) dst[i] = tray_entry(l->a[i]);
     return l->n;
 }
+static void order_record(const Order* od, int32_t* r4) {
+    int pm = 0, km = 0;
+    for (int i = 0; i < od->n; i++) pm |= od->products[i]->is_processed << i, km |= od->products[i]->is_packaged << i;
+    r4[0] = km, r4[1] = pm, r4[2] = od->is_complete, r4[3] = od->completion_step;
+}
+/* orders [first, first + count): {packaged_mask, processed_mask, is_complete, completion_step}; with long_streams the
+ * port's conventions of fjsp_export_orders: popped orders that left the ring read "complete, all bits", queued ones zeros */
+void fjsp_oracle_export_orders(const OracleEnv* e, int first, int count, int32_t* out4) {
+    for (int i = 0; i < count; i++) {
+        const int o = first + i;
+        int32_t* r = out4 + 4 * i;
+        r[0] = r[1] = r[2] = 0, r[3] = -1;
+        if (o < 0 || o >= e->norders) continue;
+        if (e->cfg.long_streams && o >= e->order_queue_head) continue;
+        /* the port gives an order's slot back one step after it completes: from then on it reads "complete, all bits" */
+        if (e->cfg.long_streams && e->orders[o].is_complete && e->orders[o].completion_step < e->current_step - 1) {
+            r[0] = r[1] = 0x1ff, r[2] = 1;
+            continue;
+        }
+        order_record(&e->orders[o], r);
+    }
+}
 
 void fjsp_oracle_export_cell(const OracleEnv* e, int cell, FjspCanonState* s) {
     const Cell* c = &e->cells[cell];
     memset(s, 0, sizeof(*s));
+    g_long_entries = e->cfg.long_streams != 0;
     s->current_step = e->current_step, s->num_orders = e->norders, s->fault = e->fault;
     s->agv_row = c->agv_row, s->agv_col = c->agv_col, s->agv_carry = tray_entry(c->carrying), s->agv_is_moving = c->is_moving;
     s->ps_order_queue_len = order_queue_len(e);
@@ -774,13 +854,13 @@ void fjsp_oracle_export_cell(const OracleEnv* e, int cell, FjspCanonState* s) {
         for (int k = 0; k < FJSP_CANON_MAXPQ; k++) s->pack[i].queue[k] = k < p->qn ? p->queue[k]->id : -1;
     }
     for (int o = 0; o < FJSP_MAX_ORDERS; o++) s->order_completion_step[o] = -1;
-    for (int o = 0; o < e->norders; o++) {
-        const Order* od = &e->orders[o];
-        int pm = 0, km = 0;
-        for (int i = 0; i < od->n; i++) pm |= od->products[i]->is_processed << i, km |= od->products[i]->is_packaged << i;
-        s->processed_mask[o] = pm, s->packaged_mask[o] = km;
-        s->order_complete[o] = od->is_complete, s->order_completion_step[o] = od->completion_step;
-    }
+    /* per-order arrays: orders 0..31; long order streams: the 32 most recently popped orders */
+    const int base = e->cfg.long_streams ? (e->order_queue_head > FJSP_MAX_ORDERS ? e->order_queue_head - FJSP_MAX_ORDERS : 0) : 0;
+    int32_t rec[4 * FJSP_MAX_ORDERS];
+    fjsp_oracle_export_orders(e, base, FJSP_MAX_ORDERS, rec);
+    for (int i = 0; i < FJSP_MAX_ORDERS; i++)
+        s->packaged_mask[i] = rec[4 * i], s->processed_mask[i] = rec[4 * i + 1], s->order_complete[i] = rec[4 * i + 2],
+        s->order_completion_step[i] = rec[4 * i + 3];
     s->total_products_packaged = e->total_products_packaged;
     s->completed_orders = e->completed_orders;
 }

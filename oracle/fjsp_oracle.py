@@ -18,6 +18,7 @@ except ImportError:  # pragma: no cover - direct script use
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libfjsp_oracle.so")
+_SO_LONG = os.path.join(_HERE, "_build", "libfjsp_oracle_long.so")  # the same source built with room for long order streams
 
 N_ACTIONS = (3, 8, 3, 3, 3, 3, 3, 3)
 
@@ -39,8 +40,8 @@ def build(force: bool = False) -> str:
     """Compile the restatement with the system gcc (``make -C oracle``)."""
     src = os.path.join(_HERE, "fjsp_oracle.c")
     hdr = os.path.join(_HERE, "..", "include", "fjsp_b200.h")
-    stale = (not os.path.exists(_SO)) or any(
-        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr))
+    stale = any((not os.path.exists(so)) or any(os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(so) for p in (src, hdr))
+                for so in (_SO, _SO_LONG))
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-B"] if force else ["make", "-C", _HERE], check=True,
                        stdout=subprocess.DEVNULL)
@@ -48,13 +49,25 @@ def build(force: bool = False) -> str:
 
 
 _lib = None
+_lib_long = None
 
 
-def lib():
-    global _lib
+def lib(long_streams: bool = False):
+    """The restatement; long_streams=True: the build with room for 4095 orders / 1000 trays per env (~2 MB per env)."""
+    global _lib, _lib_long
+    if long_streams:
+        if _lib_long is None:
+            _lib_long = _bind(_SO_LONG)
+        return _lib_long
     if _lib is None:
+        _lib = _bind(_SO)
+    return _lib
+
+
+def _bind(path):
+    if True:
         build()
-        L = C.CDLL(_SO)
+        L = C.CDLL(path)
         L.fjsp_oracle_create.restype = C.c_void_p
         L.fjsp_oracle_create.argtypes = [C.POINTER(FjspConfig)]
         L.fjsp_oracle_destroy.argtypes = [C.c_void_p]
@@ -72,8 +85,9 @@ def lib():
         L.fjsp_oracle_rollout_random.argtypes = [
             C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
             C.c_void_p]
-        _lib = L
-    return _lib
+        L.fjsp_oracle_reset_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32]
+        L.fjsp_oracle_export_orders.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    return L
 
 
 def default_config() -> FjspConfig:
@@ -95,7 +109,7 @@ def philox(ctr, key) -> np.ndarray:
 
 
 def philox_orders(seed: int, genv: int, episode: int, num_orders: int) -> np.ndarray:
-    out = np.zeros(32, dtype=np.uint32)
+    out = np.zeros(max(32, num_orders), dtype=np.uint32)
     lib().fjsp_oracle_philox_orders(seed, genv, episode, num_orders, out.ctypes.data)
     return out[:num_orders]
 
@@ -116,8 +130,8 @@ class OracleEnv:
     """One shop floor, stepped on the CPU by the C restatement."""
 
     def __init__(self, cfg: FjspConfig | None = None):
-        self._L = lib()
         self.cfg = cfg if cfg is not None else default_config()
+        self._L = lib(bool(self.cfg.long_streams))
         self._h = self._L.fjsp_oracle_create(C.byref(self.cfg))
         if not self._h:
             raise MemoryError("fjsp_oracle_create failed")
@@ -143,6 +157,19 @@ class OracleEnv:
         self._L.fjsp_oracle_reset(self._h, arr.ctypes.data, int(arr.shape[0]))
         self._L.fjsp_oracle_observe(self._h, self.obs.ctypes.data, self.masks.ctypes.data)
         return self.obs.copy(), self.masks.copy()
+
+    def reset_stream(self, orders, num_initial, seed, genv, episode=0):
+        """Long order streams with arrivals: `orders` = the attributes of every order that can ever exist (packed uint32),
+        `num_initial` of them exist at reset, the others arrive from the Philox arrival stream (seed, genv, episode)."""
+        arr = np.ascontiguousarray(orders, dtype=np.uint32)
+        self._L.fjsp_oracle_reset_stream(self._h, arr.ctypes.data, int(arr.shape[0]), int(num_initial), int(seed), int(genv), int(episode))
+        self._L.fjsp_oracle_observe(self._h, self.obs.ctypes.data, self.masks.ctypes.data)
+        return self.obs.copy(), self.masks.copy()
+
+    def export_orders(self, first, count):
+        out = np.zeros((count, 4), dtype=np.int32)
+        self._L.fjsp_oracle_export_orders(self._h, int(first), int(count), out.ctypes.data)
+        return out
 
     def step(self, actions):
         a = np.ascontiguousarray(actions, dtype=np.uint8)

@@ -107,6 +107,9 @@ def storage_shuffler(rs, obs, masks, move_cell):
 def run(name, cfg_over, policy, steps, num_orders_cycle, seed):
     cfg = dict(DEFAULT_CFG)
     cfg.update(cfg_over)
+    long_streams = bool(cfg.get("long_streams", 0))  # > 32 orders / > 240 steps: the port's long layout and its export conventions
+    export = canon.export_reference_long if long_streams else canon.export_reference
+    max_no = max(32, max(num_orders_cycle))
     move_cell = {1: tuple(cfg["pos"][0]), 2: tuple(cfg["pos"][2]), 3: tuple(cfg["pos"][1]), 4: tuple(cfg["pos"][3]),
                  5: tuple(cfg["pos"][4])}
     rs = np.random.RandomState(seed)
@@ -129,7 +132,7 @@ def run(name, cfg_over, policy, steps, num_orders_cycle, seed):
             orders = policies.random_orders(rs, no)
             robs = ref.reset(orders)
             o, m = canon.flatten_reference_obs(robs)
-            tab = np.zeros((32, 3), np.int64)
+            tab = np.zeros((max_no, 3), np.int64)
             tab[:no] = orders
             ep_start.append(t), ep_orders.append(tab), ep_norders.append(no), ep_obs0.append(o), ep_masks0.append(m)
             sim = ref.env.unwrapped.simulation
@@ -156,7 +159,7 @@ def run(name, cfg_over, policy, steps, num_orders_cycle, seed):
                 actions[t], obs[t], masks[t] = a, o, m
                 rewards[t] = [rrew[aid] for aid in canon.AGENT_IDS]
                 flags[t] = (int(rterm["agv"]), int(rtrunc["agv"]))
-                s = canon.export_reference(sim)
+                s = export(sim)
                 hashes[t] = digest(s)
                 if t % CHECK_EVERY == 0 or not ref.env.agents:
                     checks.append(s), check_steps.append(t)
@@ -192,6 +195,12 @@ SCENARIOS = [
     ("speed2_far_step20", dict(pos=[[0, 0], [0, 29], [14, 11], [33, 2], [25, 40]], grid_rows=34, grid_cols=41, agv_speed=2,
                                step_size=20, proc_small=40, proc_big=80, proc_pack=20, max_episode_steps=150), "heuristic",
      2000, [16, 9], 1010),
+    # long order streams (BASELINE configs[4]): what the reference does with num_orders = 200 / 120 and 500-step episodes
+    # (FJSPSimulation.py:223,315-318), replayed by the port's long layout
+    ("long_heuristic_200", dict(long_streams=1, max_episode_steps=500), "heuristic", 1600, [200, 120], 1011),
+    ("long_masked_300", dict(long_streams=1, max_episode_steps=700), "masked", 1500, [300], 1012),
+    ("long_fast_machines_150", dict(long_streams=1, max_episode_steps=600, proc_small=20, proc_big=30, proc_pack=10), "heuristic",
+     1300, [150, 60], 1013),
 ]
 
 if __name__ == "__main__":

@@ -24,6 +24,7 @@ class FakeBatchedFJSPEnv:
         agents = 1 + 7 * k
         act, nobs, nmask = (agents + 7) // 8 * 8, 7 + 31 * k, (3 + 26 * k + 31) // 32 * 32
         self.cells = k
+        self.long_streams = bool(config.long_streams)
         self.obs = torch.zeros((1, nobs)); self.masks = torch.zeros((1, nmask), dtype=torch.int8)
         self.rewards = torch.zeros((1, act)); self.flags = torch.zeros((1, 4), dtype=torch.uint8)
         self.results = torch.zeros((1, act), dtype=torch.uint8); self.infos = torch.zeros((1, 4), dtype=torch.int32)
@@ -43,6 +44,9 @@ class FakeBatchedFJSPEnv:
 
     def export_state(self, env, cell=0):
         return self._e.export(cell)
+
+    def export_orders(self, env, first, count):
+        return self._e.export_orders(first, count)
 
     def close(self):
         pass

@@ -17,6 +17,7 @@ struct HostEnv {
     uint64_t seed, genv;                       // long layout: order / arrival streams
     FjspOrderRec otab[FJSP_LONG_MAX_ORDERS];   // long layout: explicit order table of the current episode
     int otab_n;
+    u32 rq[FJSP_LONG_READY_FIFO];              // long layout: the ready FIFO (a side buffer in HBM on the device)
     u32 words[FJSP_STATE_WORDS_LONG_K(FJSP_MAX_CELLS)];
 };
 
@@ -37,7 +38,7 @@ template <bool LONG>
 static ArrayStateT<LONG> env_state(HostEnv* e) {
     ArrayStateT<LONG> s{e->words};
     s.dyn_end = WM<LONG>::W_POOL + 64 * e->cells, s.total = state_words(e);
-    s.seed = e->seed, s.genv = e->genv, s.otab = e->otab_n > 0 ? e->otab : nullptr;
+    s.seed = e->seed, s.genv = e->genv, s.otab = e->otab_n > 0 ? e->otab : nullptr, s.rq = e->rq;
     return s;
 }
 
@@ -86,8 +87,9 @@ void hh_reset(void* p, const FjspOrderRec* orders, int num_orders, uint64_t seed
     HostEnv* e = (HostEnv*)p;
     e->seed = seed, e->genv = genv, e->otab_n = 0;
     if (e->long_streams && orders) {  // the ring fills as orders are popped: keep the table for the episode
-        e->otab_n = num_orders;
-        memcpy(e->otab, orders, sizeof(FjspOrderRec) * (size_t)num_orders);
+        // (with arrivals the table describes every order that can ever exist: arrival_max of them)
+        e->otab_n = e->P.arrival_q16 > 0 && e->P.arrival_max > num_orders ? e->P.arrival_max : num_orders;
+        memcpy(e->otab, orders, sizeof(FjspOrderRec) * (size_t)e->otab_n);
         orders = e->otab;
     }
     DISPATCH_K(e, reset_env<K>(s, e->P, num_orders, orders, seed, genv, episode))
@@ -181,14 +183,14 @@ int hh_step_cells(void* p, const uint8_t* actions, float* obs, int8_t* masks, fl
 
 void hh_export(void* p, int cell, FjspCanonState* out) {
     HostEnv* e = (HostEnv*)p;
-    export_canon(e->words, e->P, e->cells, e->long_streams, cell, out);
+    export_canon(e->words, e->rq, e->P, e->cells, e->long_streams, cell, out);
 }
 void hh_export_orders(void* p, int first, int count, int32_t* out4, int32_t* order_base) {
     HostEnv* e = (HostEnv*)p;
     export_orders(e->words, e->P, e->cells, e->long_streams, first, count, out4);
     if (order_base) {
         FjspCanonState c;
-        export_canon(e->words, e->P, e->cells, e->long_streams, 0, &c, order_base);
+        export_canon(e->words, e->rq, e->P, e->cells, e->long_streams, 0, &c, order_base);
     }
 }
 void hh_words(void* p, uint32_t* out) { memcpy(out, ((HostEnv*)p)->words, sizeof(u32) * state_words((HostEnv*)p)); }

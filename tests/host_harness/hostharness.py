@@ -42,6 +42,7 @@ def lib():
         L.hh_step_cells.argtypes = [C.c_void_p] * 8 + [C.c_int]
         L.hh_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.hh_words.argtypes = [C.c_void_p, C.c_void_p]
+        L.hh_export_orders.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.hh_philox_actions.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
         L.hh_philox.argtypes = [C.c_void_p] * 3
         _lib = L
@@ -75,9 +76,10 @@ class HostEnv:
             if arr.ndim == 2:
                 arr = np.array([order_rec(*o) for o in arr], dtype=np.uint32)
             arr = np.ascontiguousarray(arr, dtype=np.uint32)
-            buf = np.zeros(32, np.uint32)
+            buf = np.zeros(max(32, arr.shape[0]), np.uint32)
             buf[:arr.shape[0]] = arr
-            self._L.hh_reset(self._h, buf.ctypes.data, int(arr.shape[0]), 0, 0, 0)
+            # (seed / genv / episode still select the ARRIVAL stream of a long-streams env)
+            self._L.hh_reset(self._h, buf.ctypes.data, int(arr.shape[0] if num_orders is None else num_orders), seed, genv, episode)
         else:
             self._L.hh_reset(self._h, None, int(num_orders), seed, genv, episode)
         self._L.hh_observe(self._h, self.obs.ctypes.data, self.masks.ctypes.data)
@@ -111,7 +113,13 @@ class HostEnv:
         self._L.hh_export(self._h, int(cell), s.ctypes.data)
         return s
 
+    def export_orders(self, first, count):
+        out = np.zeros((count, 4), np.int32)
+        self._L.hh_export_orders(self._h, int(first), int(count), out.ctypes.data, None)
+        return out
+
     def words(self):
-        w = np.zeros(64 + 64 * self.cells + 20 * (self.cells - 1), np.uint32)
+        k = self.cells
+        w = np.zeros((228 + 64 * k + 24 * (k - 1)) if self.cfg.long_streams else (64 + 64 * k + 20 * (k - 1)), np.uint32)
         self._L.hh_words(self._h, w.ctypes.data)
         return w

@@ -29,6 +29,7 @@ def cfg_from_dict(d: dict) -> FjspConfig:
     for k in ("grid_rows", "grid_cols", "proc_small", "proc_big", "proc_pack", "step_size", "agv_speed",
               "max_episode_steps", "storage_capacity", "pack_capacity", "tray_capacity", "num_trays"):
         setattr(cfg, k, int(d[k]))
+    cfg.long_streams = int(d.get("long_streams", 0))   # > 32 orders / > 240 steps: the long layout (include/fjsp_b200.h)
     return cfg
 
 

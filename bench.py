@@ -431,6 +431,36 @@ def run_ours(args):
         torch.cuda.synchronize()
         scaled["rollout32_agent_steps_per_s"] = n4 * d4["agents"] * 32 / (e0.elapsed_time(e1) * 1e-3)  # K-steps-per-launch kernel
         del e4, a4
+        # the same shop on the LONG order-stream layout (include/fjsp_b200.h): 8 orders at reset, Philox arrivals up to 200,
+        # 500-step episodes — "larger grid, 4x AGVs and machines, long order streams" of configs[4]
+        cfgl = _abi.default_config()
+        cfgl.num_cells, cfgl.long_streams, cfgl.max_episode_steps = 4, 1, 500
+        cfgl.arrival_prob_q16, cfgl.arrival_max_orders = 26214, 200   # 0.4 orders per step
+        nl = 1 << 18
+        el = BatchedFJSPEnv(nl, config=cfgl, device=dev, seed=SEED, num_orders=8, autoreset=True)
+        el.reset()
+        dl = el.dims
+        al = [el.random_actions(t, out=torch.empty((nl, dl["act"]), dtype=torch.uint8, device=dev)) for t in range(16)]
+        el.rollout_random(300)   # away from the empty initial state: arrivals, trays in the FIFOs, orders in process
+        for t in range(5):
+            el.step(al[t % 16])
+        torch.cuda.synchronize()
+        e0.record()
+        for t in range(50):
+            el.step(al[t % 16])
+        e1.record()
+        torch.cuda.synchronize()
+        msl = e0.elapsed_time(e1) / 50
+        bytesl = dl["act"] + 4 * dl["obs"] + dl["mask"] + 4 * dl["act"] + 4 + 2 * 4 * dl["state_words"]
+        scaled["long_streams"] = {
+            "workload": "4 cells, long order streams: 8 orders at reset + Philox arrivals (0.4 per step) up to 200, 500-step episodes, "
+                        "%d envs, Philox uniform-random actions, autoreset" % nl,
+            "envs": nl, "ms_per_step": msl, "agent_steps_per_s": nl * dl["agents"] / (msl * 1e-3),
+            "state_bytes_per_env": 4 * dl["state_words"], "algorithmic_bytes_per_env_step": bytesl,
+            "achieved_gbs": nl * bytesl / (msl * 1e-3) / 1e9, "roofline_frac": nl * bytesl / (msl * 1e-3) / 1e9 / peak4,
+            "kernel": "fjsp_step_cells_kernel<4,false,true>",
+            "note": "the ready FIFOs (4 KB per env in HBM) are touched in at most two words per env-step and are not counted"}
+        del el, al
 
     # ---- configs[3] as written: 2^20 envs in TOTAL, sharded over the N GPUs (strong scaling).  At N = 8 a rank's share
     #      (131,072 envs = 64 MiB of state) is L2-resident, so this is NOT an HBM-roofline figure; the headline keeps 2^20 per GPU.

@@ -304,7 +304,8 @@ int fjsp_cells_unpack_views(const float* obs, const int8_t* masks, const float* 
  * FJSP_OP_MC  X(r,k) = X[k*ld + r].  Supported (a_op, b_op): (KC,MC) forward y = x W, (KCS,MC) forward from an
  * unaligned observation slice, (KC,KC) dx = dy W^T, (KCS,KCS) the same from unaligned rows, (MC,MC) dW = x^T dy.
  * Epilogue per problem: + bias[n]; ReLU (FJSP_GEMM_RELU); * (mask(m,n) > 0) (mask indexed like C);
- * colsum[n] += column sums of the stored values (bias gradient); FJSP_GEMM_ATOMIC: atomicAdd into C (split-K).
+ * colsum[n] += column sums of the stored values (bias gradient); FJSP_GEMM_ATOMIC: atomicAdd into C (split-K);
+ * rowdot_*: a fused 1-column head on the stored values (the critic's 128 -> 1 layer).
  * max_ctas = max over the problems of ceil(M / 128) * splitk.  N <= 256. */
 #define FJSP_OP_KC 0
 #define FJSP_OP_KCS 1
@@ -324,6 +325,10 @@ typedef struct FjspGemmProb {
     int32_t flags;
     int32_t splitk;
     int32_t reserved[3];
+    const float* rowdot_w;   /* optional fused head, N <= 128: rowdot_out[m] = sum_n C(m, n) * rowdot_w[n] + rowdot_bias[0] */
+    float* rowdot_out;
+    const float* rowdot_bias;
+    int64_t reserved2;
 } FjspGemmProb;
 /* fjsp_a2c_loss_grad: the gradients of one A2C update's losses with respect to the actors' pre-softmax outputs and the
  * critic value, analytically (a2c.py:647-731: -mean(adv_n * log q[a]) - entropy_coef * mean(H(softmax)) per actor with

@@ -92,7 +92,6 @@ class UmmaEngine:
         l1 = umma.GemmTable(dev, umma.OP_KCS, umma.OP_MC, ps)
         l2 = umma.GemmTable(dev, umma.OP_KC, umma.OP_MC, ps)
         l3 = umma.GemmTable(dev, umma.OP_KC, umma.OP_MC, ps)
-        l4 = umma.GemmTable(dev, umma.OP_KC, umma.OP_MC, ps)
         for k, d in nets:
             (w1, o1), (b1, ob1), (w2, o2), (b2, ob2), (w3, o3), (b3, ob3) = (self._par(d, j) for j in range(6))
             l1.add(self.obs, w1, self.h1, N, HID, d["k1"], lda=38, ldb=HID, csm=HID, a_off=t * N * 38 + d["lo"], b_off=o1,
@@ -102,16 +101,16 @@ class UmmaEngine:
             if k < 8:   # actor head: straight into its columns of the [N, 32] logits row
                 l3.add(self.h2, w3, self.logits, N, d["nact"], HID, lda=HID, ldb=d["nact"], csm=32, a_off=self._hoff(k, t), b_off=o3,
                        c_off=t * N * 32 + d["zoff"], bias=b3, bias_off=ob3)
-            else:       # critic: 256 -> 128 (ReLU) -> 1
-                l3.add(self.h2, w3, self.h3, N, 128, HID, lda=HID, ldb=128, csm=128, a_off=self._hoff(k, t), b_off=o3,
-                       c_off=t * N * 128, bias=b3, bias_off=ob3, relu=True)
+            else:       # critic: 256 -> 128 (ReLU), and its 128 -> 1 head fused into the same epilogue
                 w4, b4 = d["p"][6], d["p"][7]
-                l4.add(self.h3, w4, self.values, N, 1, 128, lda=128, ldb=1, csm=1, a_off=t * N * 128, c_off=t * N, bias=b4)
-        return [x.finalize() for x in (l1, l2, l3, l4)]
+                l3.add(self.h2, w3, self.h3, N, 128, HID, lda=HID, ldb=128, csm=128, a_off=self._hoff(k, t), b_off=o3,
+                       c_off=t * N * 128, bias=b3, bias_off=ob3, relu=True, rowdot_w=w4, rowdot_out=self.values,
+                       rowdot_out_off=t * N, rowdot_bias=b4)
+        return [x.finalize() for x in (l1, l2, l3)]
 
     def forward(self, t):
         """Actors' logits (``self.logits[t]``) and the critic value (``values[t]``) of rollout step t; t = T: the bootstrap
-        value only.  Four grouped launches."""
+        value only.  Three grouped launches (the critic's 128 -> 1 head rides in the epilogue of its third layer)."""
         for tab in self._fwd[t]:
             tab.launch()
 

@@ -110,7 +110,7 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32(int m, int n) {
 enum { OP_KC = 0, OP_KCS = 1, OP_MC = 2 };
 enum { GEMM_RELU = 1, GEMM_ATOMIC = 2 };
 
-struct GemmProb {          // 96 bytes; device array, one per problem
+struct GemmProb {          // 128 bytes; device array, one per problem
     const float* A;
     const float* B;
     float* C;
@@ -123,8 +123,14 @@ struct GemmProb {          // 96 bytes; device array, one per problem
     int32_t flags;         // GEMM_RELU, GEMM_ATOMIC (atomicAdd into C: split-K partial sums)
     int32_t splitk;        // >= 1: the K range is cut into this many parts, one CTA each
     int32_t reserved[3];
+    // optional fused head (N <= 128): rowdot_out[m] = sum_n stored(m, n) * rowdot_w[n] + rowdot_bias[0] — the critic's
+    // last layer (128 -> 1, networks.py:41-61) in the epilogue of the layer before it
+    const float* rowdot_w;
+    float* rowdot_out;
+    const float* rowdot_bias;
+    int64_t reserved2;
 };
-static_assert(sizeof(GemmProb) == 96, "GemmProb layout is part of the ABI (include/fjsp_b200.h FjspGemmProb)");
+static_assert(sizeof(GemmProb) == 128, "GemmProb layout is part of the ABI (include/fjsp_b200.h FjspGemmProb)");
 
 constexpr int G_BM = 128;             // rows per CTA tile = TMEM lanes
 constexpr int G_BN = 256;             // max columns per CTA tile = TMEM columns
@@ -388,9 +394,24 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
             const int n = h0 + 4 * lane;         // this lane's 4 columns
             const bool nany = 4 * lane < ncol && n < P.N;
             float cs[4] = {0.f, 0.f, 0.f, 0.f};
+            float w4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (P.rowdot_w && nany) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) w4[i] = n + i < P.N ? __ldg(P.rowdot_w + n + i) : 0.f;
+            }
             for (int r = 0; r < 32; r++) {
                 const int m = m0 + warp * 32 + r;
                 if (m >= P.M) break;              // uniform over the warp
+                if (P.rowdot_w) {                 // fused head: every lane takes part in the row's reduction
+                    float d = 0.f;
+                    if (nany) {
+                        const float4 o = *reinterpret_cast<const float4*>(stage + r * G_EPI_LD + 4 * lane);
+                        d = o.x * w4[0] + o.y * w4[1] + o.z * w4[2] + o.w * w4[3];
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+                    if (lane == 0) P.rowdot_out[m] = d + (P.rowdot_bias ? __ldg(P.rowdot_bias) : 0.f);
+                }
                 if (!nany) continue;
                 float4 o = *reinterpret_cast<const float4*>(stage + r * G_EPI_LD + 4 * lane);
                 float* cp = P.C + (int64_t)m * P.csm + (int64_t)n * P.csn;

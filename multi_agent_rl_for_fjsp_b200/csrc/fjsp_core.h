@@ -1292,11 +1292,12 @@ FJSP_HD void step_env(S& s, const Params& P, const int* a, StepOut<K>& out) {
 // products; X_MASK.. = 3 mask bits of the pickup station, then 26 per cell; then one u16 per action column:
 // local reward (9-bit signed, tenths) | action_result << 9.
 // ---------------------------------------------------------------------------------------------
-enum { X_RDF = 0, X_READY = 1, X_DELTA = 2, X_ACT = 3, X_MASK = 4 };  // X_ACT (long layout): order slot taken by the picking lane
-template <int K>
+enum { X_RDF = 0, X_READY = 1, X_DELTA = 2, X_MASK = 3 };
+template <int K, bool LONG = false>
 struct Xl {
     static constexpr int LOCAL = X_MASK + 1 + K;  // first word of the u16 table
-    static constexpr int WORDS = LOCAL + Lay<K>::ACT / 2;
+    static constexpr int ACT = LOCAL + Lay<K>::ACT / 2;  // long layout only: the order slot taken by the picking lane
+    static constexpr int WORDS = ACT + (LONG ? 1 : 0);
 };
 
 struct CellLane {
@@ -1345,7 +1346,7 @@ FJSP_HD void cells_act_run(S& s, X& x, const Params& P, CellLane& L, const int* 
     act_cell(s, P, L.h, L.hc, L.c, L.k, a7, L.local10 + 1, L.res + 1, pk_start);
     if (L.h.ready_count != rc || L.h.ready_order != ro || L.h.ready_idx != ri) {
         x.st(X_READY, (u32)L.h.ready_count | ((u32)L.h.ready_order << 12) | ((u32)L.h.ready_idx << 24) | (1u << 31));
-        if (S::LONG) x.st(X_ACT, (u32)(L.h.act_order & 0x1fff) | ((u32)L.h.act_slot << 13) | (1u << 31));
+        if (S::LONG) x.st(Xl<K, S::LONG>::ACT, (u32)(L.h.act_order & 0x1fff) | ((u32)L.h.act_slot << 13) | (1u << 31));
     }
     int dock_after = 0;
     run_cell(s, P, L.h, L.hc, L.c, L.k, pk_start, dock_after);
@@ -1372,7 +1373,7 @@ FJSP_HD void cells_finish(X& x, const Params& P, CellLane& L, int32_t* info) {
     if (!L.inert) {
     if (ready >> 31) h.ready_count = (int)(ready & 0xfffu), h.ready_order = (int)((ready >> 12) & 0xfffu), h.ready_idx = (int)((ready >> 24) & 15u);
     if (S::LONG) {
-        const u32 act = x.ld(X_ACT);
+        const u32 act = x.ld(Xl<K, S::LONG>::ACT);
         if (act >> 31) h.act_order = (int)(act & 0x1fffu), h.act_slot = (int)((act >> 13) & 63u);
     }
     const int d_orders = (int)(delta >> 16), d_products = (int)(delta & 0xffffu);

@@ -41,10 +41,13 @@ struct Geo {
     static constexpr int STEP_WIRE_SMEM_BYTES = DYN_BYTES + WIRE_TILE_BYTES + 16;
     static constexpr int ROLLOUT_SMEM_BYTES = DYN_BYTES + 16;
     // cell-parallel step (K >= 2): TILE x K threads per CTA, + the exchange block
-    static constexpr int X_BYTES = Xl<K>::WORDS * TILE * 4;                       // 6144 for K = 4
+    static constexpr int X_BYTES = Xl<K, LONG>::WORDS * TILE * 4;                 // 6144 for K = 4
     static constexpr int CELLS_SMEM_BYTES = DYN_BYTES + OBS_TILE_BYTES + X_BYTES + 16;       // 115,472 for K = 4: 2 CTAs / SM
     static constexpr int CELLS_WIRE_SMEM_BYTES = DYN_BYTES + WIRE_TILE_BYTES + X_BYTES + 16;
-    static constexpr int CELLS_CTAS_PER_SM = (227 * 1024) / (CELLS_SMEM_BYTES + 1024) >= 3 ? 3 : (227 * 1024) / (CELLS_SMEM_BYTES + 1024) >= 2 ? 2 : 1;
+    // resident CTAs per SM by shared memory: 228 KB per SM, 1 KB of it reserved per CTA (K = 4 compact: 2 x 116,496 fit).
+    // It is also the kernel's register budget (__launch_bounds__): 65,536 / (64K threads x CTAs).
+    static constexpr int CELLS_FIT = (228 * 1024) / (CELLS_SMEM_BYTES + 1024);
+    static constexpr int CELLS_CTAS_PER_SM = CELLS_FIT >= 3 ? 3 : CELLS_FIT >= 2 ? 2 : 1;
     static constexpr int ROLLOUT_CELLS_SMEM_BYTES = DYN_BYTES + X_BYTES + 16;
 };
 
@@ -410,7 +413,7 @@ __global__ void __launch_bounds__(TILE* K, Geo<K, LONG>::CELLS_CTAS_PER_SM) fjsp
 #pragma unroll
         for (int i = 0; i < 7; i++) a7[i] = valid ? (int)__ldg(arow + 1 + 7 * c + i) : 0;
     }
-    for (int i = tid; i < Xl<K>::WORDS * TILE; i += NT) s_x[i] = 0u;
+    for (int i = tid; i < Xl<K, LONG>::WORDS * TILE; i += NT) s_x[i] = 0u;
     __syncthreads();  // mbarrier initialised and exchange area zeroed for everyone
     mbar_wait(bar, 0);
 
@@ -633,7 +636,7 @@ __global__ void __launch_bounds__(TILE* K, Geo<K, LONG>::CELLS_CTAS_PER_SM) fjsp
     L.c = c;
     load_hot(s, L.h);
     load_cell<K>(s, c, L.hc);
-    for (int i = tid; i < Xl<K>::WORDS * TILE; i += NT) s_x[i] = 0u;
+    for (int i = tid; i < Xl<K, LONG>::WORDS * TILE; i += NT) s_x[i] = 0u;
     __syncthreads();
     mbar_wait(bar, 0);
     unsigned long long n_steps = 0, n_eps = 0, n_orders = 0, n_prod = 0, n_fault = 0;
@@ -682,7 +685,7 @@ __global__ void __launch_bounds__(TILE* K, Geo<K, LONG>::CELLS_CTAS_PER_SM) fjsp
                 load_cell<K>(s, c, L.hc);
             }
         }
-        for (int i = c; i < Xl<K>::WORDS; i += K) x.st(i, 0u);
+        for (int i = c; i < Xl<K, LONG>::WORDS; i += K) x.st(i, 0u);
         __syncthreads();
     }
     if (c == 0) store_hot(s, L.h);

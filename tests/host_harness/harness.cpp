@@ -138,8 +138,8 @@ int hh_step_cells(void* p, const uint8_t* actions, float* obs, int8_t* masks, fl
     DISPATCH_K(e, {
         if constexpr (K >= 2) {
             constexpr int AG = Lay<K>::AGENTS;
-            u32 xw[Xl<K>::WORDS];
-            for (int i = 0; i < Xl<K>::WORDS; i++) xw[i] = 0u;
+            u32 xw[Xl<K, LONG>::WORDS];
+            for (int i = 0; i < Xl<K, LONG>::WORDS; i++) xw[i] = 0u;
             ArrayXchg x{xw};
             CellLane L[K];
             int a7[K][7];

@@ -147,7 +147,7 @@ def ncu_traffic(envs):
         from sass_hash import sass_sha256
 
         with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as f:
-            rec = json.load(f)["fjsp_step_kernel<1,false>"]
+            rec = json.load(f)["fjsp_step_kernel<1,false,false>"]
         h, _ = sass_sha256()
         if h and h == rec["sass_sha256"] and int(rec["envs"]) == int(envs):
             return float(rec["dram_bytes_per_launch"]), rec.get("source")
@@ -539,7 +539,7 @@ def run_ours(args):
                        "l2": "no flush: each step streams the 512 MiB state and a fresh 8 MiB action buffer (> 126 MB L2)",
                        "action_buffers": nbuf},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "fjsp_step_kernel<1,false>",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "fjsp_step_kernel<1,false,false>",
                          "algorithmic_bytes_per_launch": E * BYTES_PER_ENV_STEP},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 8, "d2h_bytes_per_step": E * wire_row,
                     "steps": Ke, "ms_per_step": e2e_s / Ke * 1e3,

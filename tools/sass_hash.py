@@ -12,7 +12,7 @@ import sys
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(REPO, "multi_agent_rl_for_fjsp_b200", "lib", "libfjsp_b200.so")
-STEP_KERNEL = "fjsp_step_kernelILi1ELb0EE"  # fjsp::fjsp_step_kernel<1, false>
+STEP_KERNEL = "fjsp_step_kernelILi1ELb0ELb0EE"  # fjsp::fjsp_step_kernel<1, false, false>: 1 cell, float outputs, compact layout
 
 
 def kernel_sass(pattern=STEP_KERNEL, so=SO):

@@ -15,6 +15,8 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _REPO = os.path.dirname(_PKG)
 SO_PATH = os.path.join(_PKG, "lib", "libfjsp_b200.so")
+if os.environ.get("FJSP_B200_LIB"):   # another build of the same sources (A/B measurements of a kernel change)
+    SO_PATH = os.path.abspath(os.environ["FJSP_B200_LIB"])
 SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("fjsp_api.cu", "fjsp_wire.cpp", "fjsp_kernels.cuh", "fjsp_a2c.cuh", "fjsp_umma.cuh", "fjsp_core.h", "fjsp_host.h", "fjsp_wire.h")]
 HEADER = os.path.join(_REPO, "include", "fjsp_b200.h")
 

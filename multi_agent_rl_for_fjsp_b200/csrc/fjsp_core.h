@@ -197,28 +197,37 @@ FJSP_HD int popc32(u32 x) {
 // ---------------------------------------------------------------------------------------------
 // Unpacked hot scalars.  Shared (pickup station, counters) + one struct per cell.  Kept in registers.
 // ---------------------------------------------------------------------------------------------
+// Bit-fields: the compiler keeps each group in ONE register and extracts / inserts a field where it is used (the state
+// of a cell is 26 registers this way instead of 92 — the cell-parallel kernel lives inside 128 registers per thread
+// without spilling to local memory, which would cost HBM bandwidth).  Widths are those of the packed words or wider.
 struct Fifo {
-    int head, tail, len;
+    u32 head : 8, tail : 8, len : 8;
 };
 struct Mach {
-    int busy, has_cur, cur, start, prog;
+    u32 busy : 1, has_cur : 1, prog : 1, cur : 8, start : 16;
     Fifo q, r;
 };
 struct Pack {
     Fifo q, f;  // queued tray records, in-flight tray records (len = record count)
-    int users, busy, waiters, hascur, qcount, completed, progL;
-    int cur_order, cur_idx;  // current_product (sticky): compact = ring slot (= order id), long = order id; product index
+    u32 users : 6, busy : 1, waiters : 1, hascur : 1, cur_idx : 4, cur_order : 12;
+    // current_product (sticky): cur_order compact = ring slot (= order id), long = order id; cur_idx = product index
+    u32 qcount : 8, progL : 8, completed : 16;
 };
 struct Hot {  // shared part
-    int step, num_orders, fault, completed_orders;
-    int total_packaged, next_order, cur_order, prod_idx, cur_tray_count;   // cur_order: -1 = none
-    int alloc_count, ready_count, ready_order, ready_idx, dock_mask;   // long: ready_order = ready_head, ready_idx unused
-    int cur_word;                 // long: n4 | type2<<4 | colour2<<6 of the order being loaded
-    int act_order, act_slot;      // long: the order whose tray was taken last (-1 = none) and its slot
+    u32 step : 16, num_orders : 12;
+    int fault : 4;                // (-1 is used as "none raised" inside the cell-parallel step)
+    u32 completed_orders : 12, total_packaged : 16, dock_mask : 4;
+    u32 next_order : 12, prod_idx : 4;
+    int cur_order : 14;           // -1 = none
+    u32 cur_tray_count : 3, alloc_count : 12, ready_count : 12;
+    u32 ready_order : 12, ready_idx : 4;   // long: ready_order = ready_head, ready_idx unused
+    u32 cur_word : 8;             // long: n4 | type2<<4 | colour2<<6 of the order being loaded
+    int act_order : 14;           // long: the order whose tray was taken last (-1 = none) and its slot
+    u32 act_slot : 6;
     u32 episode;
 };
 struct HotCell {
-    int agv_loc, agv_moving, agv_target, agv_arrive, carry;
+    u32 agv_loc : 3, agv_moving : 1, agv_target : 3, agv_arrive : 16, carry : 8;
     u32 free_lo, free_hi;
     Fifo storage;
     Mach m[2];
@@ -992,8 +1001,16 @@ FJSP_HD void act_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, 
                     }
                 } else invalid = 1;
             } else {
-                Fifo& f = loc == LOC_SMALL ? hc.m[0].r : loc == LOC_BIG ? hc.m[1].r : hc.storage;
-                if (f.len > 0) hc.carry = fifo_pop(s, pb, f) + 1, pick = 1;
+                // (three static branches, not a reference picked at run time: that would put the FIFOs in local memory)
+                int got = -1;
+                if (loc == LOC_SMALL) {
+                    if (hc.m[0].r.len > 0) got = fifo_pop(s, pb, hc.m[0].r);
+                } else if (loc == LOC_BIG) {
+                    if (hc.m[1].r.len > 0) got = fifo_pop(s, pb, hc.m[1].r);
+                } else {
+                    if (hc.storage.len > 0) got = fifo_pop(s, pb, hc.storage);
+                }
+                if (got >= 0) hc.carry = got + 1, pick = 1;
                 else invalid = 1;
             }
             success = pick;

@@ -48,6 +48,7 @@ struct FjspHandle {
     bool staging_ready;      // host-buffer path: device / pinned staging, streams, events and decode workers exist
     int prefetch_tiles;      // cell-parallel kernel: L2 prefetch distance in tiles
     int prefetch_tiles_env;  // thread-per-env kernel: the same (0 = off)
+    bool pdl;                // small batches: step launches carry the programmatic-serialization attribute
 };
 
 static thread_local std::string g_err;
@@ -112,17 +113,30 @@ static cudaError_t set_smem_attrs() {
 
 // One lockstep step of `tiles` tiles starting at A.tile_begin.  K = 1: one thread per env.  K >= 2: one thread per
 // (env, cell) — unless FJSP_STEP_PER_ENV is set, which keeps the thread-per-env kernel for A/B measurements.
+template <class... Args>
+static void launch_ex(void (*kern)(Args...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = pdl ? 1u : 0u;
+    cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <int K, bool WIRE, bool LONG>
-static void launch_step(const FjspHandle* h, const StepArgs& A, unsigned tiles, cudaStream_t st) {
+static void launch_step(const FjspHandle* h, const StepArgs& A, unsigned tiles, cudaStream_t st, bool pdl = false) {
     using G = Geo<K, LONG>;
     static const bool per_env = getenv("FJSP_STEP_PER_ENV") != nullptr;
     if constexpr (K >= 2) {
         if (!per_env) {
-            fjsp_step_cells_kernel<K, WIRE, LONG><<<tiles, TILE * K, WIRE ? G::CELLS_WIRE_SMEM_BYTES : G::CELLS_SMEM_BYTES, st>>>(h->P, A);
+            launch_ex(fjsp_step_cells_kernel<K, WIRE, LONG>, tiles, TILE * K, WIRE ? G::CELLS_WIRE_SMEM_BYTES : G::CELLS_SMEM_BYTES, st, pdl,
+                      (const Params)h->P, (const StepArgs)A);
             return;
         }
     }
-    fjsp_step_kernel<K, WIRE, LONG><<<tiles, TILE, WIRE ? G::STEP_WIRE_SMEM_BYTES : G::STEP_SMEM_BYTES, st>>>(h->P, A);
+    launch_ex(fjsp_step_kernel<K, WIRE, LONG>, tiles, TILE, WIRE ? G::STEP_WIRE_SMEM_BYTES : G::STEP_SMEM_BYTES, st, pdl, (const Params)h->P,
+              (const StepArgs)A);
 }
 
 template <int K, bool LONG>
@@ -204,6 +218,10 @@ int fjsp_create(const FjspConfig* cfg, int64_t num_envs, int64_t first_env, int 
     h->prefetch_tiles_env = prop.multiProcessorCount;
     if (const char* e = getenv("FJSP_PREFETCH_TILES_ENV")) h->prefetch_tiles_env = atoi(e);
     h->num_tiles = (num_envs + TILE - 1) / TILE;
+    // a batch that does not fill the GPU is launch-latency bound: its step kernels are launched as programmatic
+    // dependents (the next launch's CTAs become resident while the current step runs).  FJSP_PDL=0/1 overrides.
+    h->pdl = h->num_tiles <= 2 * (int64_t)prop.multiProcessorCount;
+    if (const char* e = getenv("FJSP_PDL")) h->pdl = atoi(e) != 0;
     h->seed = 0, h->num_orders = 30, h->launches = 0;
     cudaError_t e = cudaMalloc(&h->state, (size_t)h->num_tiles * h->tile_bytes);
     if (e == cudaSuccess && h->long_streams) {
@@ -323,7 +341,7 @@ int fjsp_step(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, 
     A.num_orders = h->num_orders, A.autoreset = autoreset, A.tile_begin = 0, A.wire = nullptr;
     A.prefetch_tiles = h->prefetch_tiles, A.prefetch_tiles_env = h->prefetch_tiles_env;
     A.otab = h->d_otab, A.otab_stride = h->otab_stride, A.rq = h->d_rq;
-    DISPATCH_KL(h, (launch_step<K, false, LONG>(h, A, (unsigned)h->num_tiles, (cudaStream_t)stream)))
+    DISPATCH_KL(h, (launch_step<K, false, LONG>(h, A, (unsigned)h->num_tiles, (cudaStream_t)stream, h->pdl)))
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -347,7 +365,7 @@ int fjsp_step_wire(FjspHandle* h, const uint8_t* actions, uint32_t* wire, uint8_
         return fail("buffer alignment: actions/results 8 B, wire/infos 16 B");
     DeviceGuard g(h->device);
     const StepArgs A = wire_args(h, actions, wire, results, infos, autoreset);
-    DISPATCH_KL(h, (launch_step<K, true, LONG>(h, A, (unsigned)h->num_tiles, (cudaStream_t)stream)))
+    DISPATCH_KL(h, (launch_step<K, true, LONG>(h, A, (unsigned)h->num_tiles, (cudaStream_t)stream, h->pdl)))
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -534,7 +552,8 @@ int fjsp_random_actions(FjspHandle* h, uint64_t seed, uint64_t t, uint8_t* actio
     DeviceGuard g(h->device);
     const int threads = 256;
     const unsigned blocks = (unsigned)((h->num_envs + threads - 1) / threads);
-    DISPATCH_K(h->cells, fjsp_random_actions_kernel<K><<<blocks, threads, 0, (cudaStream_t)stream>>>(actions, h->num_envs, h->first_env, seed, t))
+    DISPATCH_K(h->cells, launch_ex(fjsp_random_actions_kernel<K>, blocks, threads, 0, (cudaStream_t)stream, h->pdl, actions,
+                                   (int64_t)h->num_envs, (int64_t)h->first_env, (uint64_t)seed, (uint64_t)t))
     h->launches++;
     CK(cudaGetLastError());
     return 0;

@@ -160,6 +160,12 @@ __device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, u
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
 }
+// Programmatic dependent launch (small batches, where a step is launch-latency bound): a kernel launched with the
+// programmatic-serialization attribute may become resident while its predecessor in the stream still runs; it must not
+// touch global memory before pdl_wait() (= the predecessor has completed and its writes are visible).  Both are no-ops
+// for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -278,8 +284,10 @@ __global__ void __launch_bounds__(TILE) fjsp_step_kernel(const __grid_constant__
     const bool valid = env < A.num_envs;
     u32* g_tile = A.state + tile * G::TILE_WORDS;
 
+    pdl_launch_dependents();  // the next step's CTAs may take their places now; they wait below before touching memory
+    if (tid == 0) mbar_init(bar, 1);
+    pdl_wait();
     if (tid == 0) {  // ONE bulk async copy (TMA engine) for the dynamically indexed words of the tile
-        mbar_init(bar, 1);
         mbar_expect_tx(bar, G::DYN_BYTES);
         bulk_g2s(s_dyn, g_tile + G::DYN0 * TILE, G::DYN_BYTES, bar);
     }
@@ -386,8 +394,10 @@ __global__ void __launch_bounds__(TILE* K, Geo<K, LONG>::CELLS_CTAS_PER_SM) fjsp
     const bool valid = env < A.num_envs;
     u32* g_tile = A.state + tile * G::TILE_WORDS;
 
+    pdl_launch_dependents();
+    if (tid == 0) mbar_init(bar, 1);
+    pdl_wait();
     if (tid == 0) {  // the tile's bulk copy is under way before anything else happens in the CTA
-        mbar_init(bar, 1);
         mbar_expect_tx(bar, G::DYN_BYTES);
         bulk_g2s(s_dyn, g_tile + G::DYN0 * TILE, G::DYN_BYTES, bar);
     }
@@ -504,6 +514,8 @@ __global__ void __launch_bounds__(TILE* K, Geo<K, LONG>::CELLS_CTAS_PER_SM) fjsp
 template <int K>
 __global__ void fjsp_random_actions_kernel(uint8_t* actions, int64_t num_envs, int64_t first_env, uint64_t seed, uint64_t t) {
     const int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();  // (the buffer may still be read by the step before)
     if (env >= num_envs) return;
     int a[Lay<K>::ACT];
 #pragma unroll

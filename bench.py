@@ -461,6 +461,33 @@ def run_ours(args):
             "kernel": "fjsp_step_cells_kernel<4,false,true>",
             "note": "the ready FIFOs (4 KB per env in HBM) are touched in at most two words per env-step and are not counted"}
         del el, al
+        # the SHARED FLOOR (include/fjsp_b200.h): 4 AGVs on one set of stations with station occupancy — "multi-AGV with
+        # collision" of configs[4]; thread-per-env kernel on the reference shop's data path
+        cfgs = _abi.default_config()
+        cfgs.shared_agvs = 4
+        ns = 1 << 20
+        esf = BatchedFJSPEnv(ns, config=cfgs, device=dev, seed=SEED, num_orders=30, autoreset=True)
+        esf.reset()
+        dsf = esf.dims
+        asf = [esf.random_actions(t, out=torch.empty((ns, dsf["act"]), dtype=torch.uint8, device=dev)) for t in range(12)]
+        for t in range(30):
+            esf.step(asf[t % 12])
+        torch.cuda.synchronize()
+        e0.record()
+        for t in range(50):
+            esf.step(asf[t % 12])
+        e1.record()
+        torch.cuda.synchronize()
+        mss = e0.elapsed_time(e1) / 50
+        bytess = dsf["act"] + 4 * dsf["obs"] + dsf["mask"] + 4 * dsf["act"] + 4 + 2 * 4 * dsf["state_words"]
+        scaled["shared_floor"] = {
+            "workload": "shared floor: 4 AGVs on one set of stations, one AGV per station position (occupancy resolved in agent "
+                        "order), 11 agents, %d envs, 30 Philox orders/env, Philox uniform-random actions, autoreset" % ns,
+            "envs": ns, "agents": dsf["agents"], "ms_per_step": mss, "agent_steps_per_s": ns * dsf["agents"] / (mss * 1e-3),
+            "state_bytes_per_env": 4 * dsf["state_words"], "algorithmic_bytes_per_env_step": bytess,
+            "achieved_gbs": ns * bytess / (mss * 1e-3) / 1e9, "roofline_frac": ns * bytess / (mss * 1e-3) / 1e9 / peak4,
+            "kernel": "fjsp_shared_step_kernel<4>"}
+        del esf, asf
 
     # ---- configs[3] as written: 2^20 envs in TOTAL, sharded over the N GPUs (strong scaling).  At N = 8 a rank's share
     #      (131,072 envs = 64 MiB of state) is L2-resident, so this is NOT an HBM-roofline figure; the headline keeps 2^20 per GPU.

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define FJSP_ABI_VERSION 3
+#define FJSP_ABI_VERSION 4
 
 /* ---- fixed shape of the problem (reference: 8 agents, FJSPSimulation.py:62-82) ---- */
 #define FJSP_NUM_AGENTS 8          /* pickup_station, agv, small_machine, big_machine, packaging_blue_1, _blue_2, _red, _green */
@@ -51,6 +51,31 @@ extern "C" {
 #define FJSP_OBS_DIM_K(k) (7 + 31 * (k))
 #define FJSP_MASK_DIM_K(k) ((3 + 26 * (k) + 31) / 32 * 32)
 #define FJSP_STATE_WORDS_K(k) (64 + 64 * (k) + 20 * ((k) - 1))  /* 128 words for K = 1, 380 for K = 4 */
+
+/* ---- shared floor (BASELINE configs[4] "multi-AGV with collision"; FjspConfig.shared_agvs = A in 2..4; a builder-defined
+ * extension — the reference has ONE AGV, /root/reference/FJSPSimulation.py:62-82): A AGVs serve ONE set of stations (pickup
+ * station, small / big machine, storage, four packaging stations) and are not sealed into cells.
+ *   agents   : pickup station, agv_0 .. agv_{A-1}, small machine, big machine, four packaging stations (7 + A), acting in
+ *              that order (A = 1 is the reference's order, FJSPSimulation.py:76-82,172-174);
+ *   occupancy: each of the five station positions holds at most ONE AGV.  A standing AGV occupies its station; an AGV under
+ *              way occupies its TARGET from the moment the move is granted (its origin is free at once).  A move to a position
+ *              occupied by another AGV is an invalid action (-5, AGVAgent.py:210-212's penalty) and masked out; two AGVs that
+ *              ask for the same free position in one step are served in agent order — the earlier one gets it, the later
+ *              one's action is invalid.  A move to the AGV's own position succeeds without moving, as in the reference;
+ *   start    : agv_0 at PICKUP (AGVAgent.py:41), agv_1 at STORAGE, agv_2 at SMALL, agv_3 at BIG;
+ *   rewards  : r_i = g / (7 + A) + local_i with the reference's g and local terms (RewardModel.py:34-110);
+ *   layout   : observation = pickup station (7) | 13 per AGV | small, big machine (3 + 3) | stations (12); masks = 3 | 8 per
+ *              AGV | 3 + 3 | 12, padded to 16; actions / rewards / results padded to 8; packed state = the 128 words of the
+ *              reference shop + one word per further AGV (132 words = 528 B per env); Philox actions: the reference stream's
+ *              eight values for (pickup station, agv_0, machines, stations), further AGVs from counter word 3 = 17.
+ * Served by fjsp_reset / fjsp_step / fjsp_random_actions / fjsp_export_state_cell (cell index = AGV index) / fjsp_export_packed /
+ * fjsp_export_orders / fjsp_state_save / fjsp_state_load; the wire-row, host-buffer and K-steps-per-launch entry points refuse such a handle. */
+#define FJSP_MAX_SHARED_AGVS 4
+#define FJSP_SHARED_AGENTS(a) (7 + (a))
+#define FJSP_SHARED_ACT_DIM(a) ((FJSP_SHARED_AGENTS(a) + 7) / 8 * 8)
+#define FJSP_SHARED_OBS_DIM(a) (25 + 13 * (a))
+#define FJSP_SHARED_MASK_DIM(a) ((21 + 8 * (a) + 15) / 16 * 16)
+#define FJSP_SHARED_STATE_WORDS 132
 
 /* ---- long order streams (BASELINE configs[4]; FjspConfig.long_streams = 1): a second packed layout for episodes with more
  * than FJSP_MAX_ORDERS orders and / or more than 240 steps, and for order ARRIVALS during the episode.  The reference
@@ -122,6 +147,9 @@ typedef struct FjspConfig {
     int32_t long_streams;                  /* 0 = compact layout (<= 32 orders, <= 240 steps); 1 = long order streams (see above) */
     int32_t arrival_prob_q16;              /* long_streams only: P(one order arrives in a step) * 65536; 0 = no arrivals */
     int32_t arrival_max_orders;            /* long_streams only: orders stop arriving once this many exist */
+    int32_t shared_agvs;                   /* 0 / 1 = one AGV (the reference); 2..4 = SHARED FLOOR: that many AGVs on one set of
+                                              stations with station occupancy (see "shared floor" above); needs num_cells = 1,
+                                              long_streams = 0 */
 } FjspConfig;
 
 /* One order as the reference generates it (FJSPSimulation.py:101-131): all products of an order

@@ -17,18 +17,23 @@ _REPO = os.path.dirname(_PKG)
 SO_PATH = os.path.join(_PKG, "lib", "libfjsp_b200.so")
 if os.environ.get("FJSP_B200_LIB"):   # another build of the same sources (A/B measurements of a kernel change)
     SO_PATH = os.path.abspath(os.environ["FJSP_B200_LIB"])
-SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("fjsp_api.cu", "fjsp_wire.cpp", "fjsp_kernels.cuh", "fjsp_a2c.cuh", "fjsp_umma.cuh", "fjsp_core.h", "fjsp_host.h", "fjsp_wire.h")]
+SOURCES = [os.path.join(_PKG, "csrc", f) for f in ("fjsp_api.cu", "fjsp_wire.cpp", "fjsp_kernels.cuh", "fjsp_a2c.cuh", "fjsp_umma.cuh", "fjsp_core.h", "fjsp_host.h", "fjsp_wire.h", "fjsp_shared.h", "fjsp_shared.cuh")]
 HEADER = os.path.join(_REPO, "include", "fjsp_b200.h")
 
 NUM_AGENTS, OBS_DIM, MASK_DIM, FLAG_DIM, INFO_DIM, MAX_ORDERS = 8, 38, 32, 4, 4, 32
 STATE_WORDS, TILE_ENVS = 128, 64
 MAX_CELLS = 4
 LONG_RING, LONG_MAX_ORDERS, LONG_MAX_STEPS = 64, 4095, 65000
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
-def dims(cells: int = 1, long_streams: bool = False) -> dict:
-    """Row widths of a K-cell shop (include/fjsp_b200.h FJSP_*_K); K = 1 is the reference shop (8 / 38 / 32 / 128)."""
+def dims(cells: int = 1, long_streams: bool = False, shared_agvs: int = 0) -> dict:
+    """Row widths of a K-cell shop (include/fjsp_b200.h FJSP_*_K); K = 1 is the reference shop (8 / 38 / 32 / 128).
+    shared_agvs >= 2: the shared floor (FJSP_SHARED_*: 7 + A agents, no wire rows)."""
+    if shared_agvs >= 2:
+        a = shared_agvs
+        return {"agents": 7 + a, "act": (7 + a + 7) // 8 * 8, "obs": 25 + 13 * a, "mask": (21 + 8 * a + 15) // 16 * 16,
+                "mask_used": 21 + 8 * a, "state_words": 132, "wire_words": 0}
     agents = 1 + 7 * cells
     return {"agents": agents, "act": (agents + 7) // 8 * 8, "obs": 7 + 31 * cells, "mask": (3 + 26 * cells + 31) // 32 * 32,
             "mask_used": 3 + 26 * cells,
@@ -52,6 +57,7 @@ class FjspConfig(C.Structure):
         ("storage_capacity", C.c_int32), ("pack_capacity", C.c_int32),
         ("tray_capacity", C.c_int32), ("num_trays", C.c_int32), ("num_cells", C.c_int32),
         ("long_streams", C.c_int32), ("arrival_prob_q16", C.c_int32), ("arrival_max_orders", C.c_int32),
+        ("shared_agvs", C.c_int32),
     ]
 
 

@@ -12,6 +12,7 @@
 #include "fjsp_wire.h"
 #include "fjsp_a2c.cuh"
 #include "fjsp_umma.cuh"
+#include "fjsp_shared.cuh"
 
 using namespace fjsp;
 
@@ -27,7 +28,8 @@ struct FjspHandle {
     FjspOrderRec* d_otab;    // long layout: the handle's copy of the explicit order tables [num_envs][otab_stride], or null
     int otab_stride;
     u32* d_rq;               // long layout: ready FIFOs [num_envs][FJSP_LONG_READY_FIFO]
-    int act, obs, mask;      // row widths of the I/O tensors (FJSP_*_DIM_K)
+    int act, obs, mask;      // row widths of the I/O tensors (FJSP_*_DIM_K / FJSP_SHARED_*)
+    int shared;              // shared floor: number of AGVs (0 = off)
     size_t tile_bytes;       // 64 envs x FJSP_STATE_WORDS_K words
     int64_t num_envs, first_env, num_tiles;
     u32* state;  // num_tiles * tile_bytes
@@ -88,6 +90,15 @@ struct DeviceGuard {
         default: { constexpr int K = 4; __VA_ARGS__; } break;  \
     }
 // ... and on the layout (compact / long order streams)
+// shared floor: on the number of AGVs
+#define DISPATCH_A(agvs, ...)                                  \
+    switch (agvs) {                                            \
+        case 2: { constexpr int A = 2; __VA_ARGS__; } break;   \
+        case 3: { constexpr int A = 3; __VA_ARGS__; } break;   \
+        default: { constexpr int A = 4; __VA_ARGS__; } break;  \
+    }
+#define NOT_SHARED(h, what) \
+    if ((h) && (h)->shared) return fail(what " is not available on the shared floor (FjspConfig.shared_agvs >= 2)");
 #define DISPATCH_KL(h, ...)                                                  \
     if ((h)->long_streams) { constexpr bool LONG = true; DISPATCH_K((h)->cells, __VA_ARGS__) } \
     else { constexpr bool LONG = false; DISPATCH_K((h)->cells, __VA_ARGS__) }
@@ -208,6 +219,11 @@ int fjsp_create(const FjspConfig* cfg, int64_t num_envs, int64_t first_env, int 
     h->long_streams = c.long_streams != 0;
     h->act = FJSP_ACT_DIM_K(h->cells), h->obs = FJSP_OBS_DIM_K(h->cells), h->mask = FJSP_MASK_DIM_K(h->cells);
     h->tile_bytes = (size_t)(h->long_streams ? FJSP_STATE_WORDS_LONG_K(h->cells) : FJSP_STATE_WORDS_K(h->cells)) * TILE * sizeof(u32);
+    h->shared = c.shared_agvs >= 2 ? c.shared_agvs : 0;
+    if (h->shared) {
+        h->act = FJSP_SHARED_ACT_DIM(h->shared), h->obs = FJSP_SHARED_OBS_DIM(h->shared), h->mask = FJSP_SHARED_MASK_DIM(h->shared);
+        h->tile_bytes = (size_t)FJSP_SHARED_STATE_WORDS * TILE * sizeof(u32);
+    }
     h->wire_words = FJSP_WIRE_WORDS_K(h->cells);
     // measured on B200 (K = 4, 2^19 envs): distances of 32..148 tiles all give +13..15 %, 296 and more lose; SMs / 2 it is.
     // FJSP_PREFETCH_TILES overrides (0 switches the prefetch off)
@@ -241,8 +257,13 @@ int fjsp_create(const FjspConfig* cfg, int64_t num_envs, int64_t first_env, int 
         return cuda_fail(e, "cudaFuncSetAttribute (is this an sm_100a device?)");
     }
     // all envs start as freshly reset, empty shops (num_orders = 0) until fjsp_reset is called
+    if (h->shared) {
+        DISPATCH_A(h->shared, (fjsp_shared_reset_kernel<A><<<(unsigned)h->num_tiles, TILE>>>(h->P, h->state, nullptr, nullptr, 0, 0ull, h->num_envs,
+                                                                                            h->first_env, nullptr, nullptr)))
+    } else {
     DISPATCH_KL(h, (fjsp_reset_kernel<K, LONG><<<(unsigned)h->num_tiles, TILE>>>(h->P, h->state, nullptr, nullptr, 0, 0, 0ull, h->num_envs,
                                                                                  h->first_env, nullptr, nullptr)))
+    }
     h->launches++;
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -268,7 +289,7 @@ int fjsp_destroy(FjspHandle* h) {
 
 int64_t fjsp_num_envs(const FjspHandle* h) { return h ? h->num_envs : 0; }
 int fjsp_num_cells(const FjspHandle* h) { return h ? h->cells : 0; }
-static int state_words(const FjspHandle* h) { return h->long_streams ? FJSP_STATE_WORDS_LONG_K(h->cells) : FJSP_STATE_WORDS_K(h->cells); }
+static int state_words(const FjspHandle* h) { return h->shared ? FJSP_SHARED_STATE_WORDS : h->long_streams ? FJSP_STATE_WORDS_LONG_K(h->cells) : FJSP_STATE_WORDS_K(h->cells); }
 size_t fjsp_state_bytes(const FjspHandle* h) { return h ? (size_t)state_words(h) * 4 : 0; }
 void* fjsp_state_ptr(FjspHandle* h) { return h ? h->state : nullptr; }
 int64_t fjsp_launch_count(const FjspHandle* h) { return h ? h->launches : 0; }
@@ -319,6 +340,13 @@ int fjsp_reset(FjspHandle* h, const uint8_t* env_mask, uint64_t seed, const Fjsp
     // the handle-wide seed / num_orders are what auto-reset and the rollout kernels use for EVERY env: a masked reset
     // (some envs only) must not change them under the envs it does not touch
     if (!env_mask) h->seed = seed, h->num_orders = num_orders;
+    if (h->shared) {
+        DISPATCH_A(h->shared, (fjsp_shared_reset_kernel<A><<<(unsigned)h->num_tiles, TILE, 0, (cudaStream_t)stream>>>(
+                                   h->P, h->state, env_mask, orders, num_orders, seed, h->num_envs, h->first_env, obs, masks)))
+        h->launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
     DISPATCH_KL(h, (fjsp_reset_kernel<K, LONG><<<(unsigned)h->num_tiles, TILE, 0, (cudaStream_t)stream>>>(
                         h->P, h->state, env_mask, orders, stride, num_orders, seed, h->num_envs, h->first_env, obs, masks)))
     h->launches++;
@@ -341,7 +369,13 @@ int fjsp_step(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, 
     A.num_orders = h->num_orders, A.autoreset = autoreset, A.tile_begin = 0, A.wire = nullptr;
     A.prefetch_tiles = h->prefetch_tiles, A.prefetch_tiles_env = h->prefetch_tiles_env;
     A.otab = h->d_otab, A.otab_stride = h->otab_stride, A.rq = h->d_rq;
-    DISPATCH_KL(h, (launch_step<K, false, LONG>(h, A, (unsigned)h->num_tiles, (cudaStream_t)stream, h->pdl)))
+    if (h->shared) {
+        const StepArgs& Ar = A;
+        DISPATCH_A(h->shared, launch_ex(fjsp_shared_step_kernel<A>, (unsigned)h->num_tiles, TILE, ShGeo<A>::STEP_SMEM_BYTES, (cudaStream_t)stream,
+                                        h->pdl, (const Params)h->P, (const StepArgs)Ar))
+    } else {
+        DISPATCH_KL(h, (launch_step<K, false, LONG>(h, A, (unsigned)h->num_tiles, (cudaStream_t)stream, h->pdl)))
+    }
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -359,6 +393,7 @@ static StepArgs wire_args(FjspHandle* h, const uint8_t* actions, u32* wire, uint
 
 int fjsp_step_wire(FjspHandle* h, const uint8_t* actions, uint32_t* wire, uint8_t* results, int32_t* infos, int autoreset, void* stream) {
     if (!h) return fail("handle is NULL");
+    NOT_SHARED(h, "fjsp_step_wire")
     if (!actions || !wire) return fail("actions/wire must be device pointers");
     if ((reinterpret_cast<uintptr_t>(actions) & 7) || (reinterpret_cast<uintptr_t>(wire) & 15) ||
         (results && (reinterpret_cast<uintptr_t>(results) & 7)) || (infos && (reinterpret_cast<uintptr_t>(infos) & 15)))
@@ -527,6 +562,7 @@ static int step_host_impl(FjspHandle* h, const uint8_t* actions, u32* wire_out, 
 int fjsp_step_host(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* masks, float* rewards, uint8_t* flags, int autoreset,
                    void* stream) {
     if (!h) return fail("handle is NULL");
+    NOT_SHARED(h, "fjsp_step_host")
     if (!actions || !obs || !masks || !rewards || !flags) return fail("host buffers must not be NULL");
     if (reinterpret_cast<uintptr_t>(masks) & 7) return fail("masks must be 8-byte aligned");
     return step_host_impl(h, actions, nullptr, obs, masks, rewards, flags, autoreset, stream);
@@ -534,6 +570,7 @@ int fjsp_step_host(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* ma
 
 int fjsp_step_host_wire(FjspHandle* h, const uint8_t* actions, uint32_t* wire, int autoreset, void* stream) {
     if (!h) return fail("handle is NULL");
+    NOT_SHARED(h, "fjsp_step_host_wire")
     if (!actions || !wire) return fail("host buffers must not be NULL");
     return step_host_impl(h, actions, wire, nullptr, nullptr, nullptr, nullptr, autoreset, stream);
 }
@@ -552,6 +589,13 @@ int fjsp_random_actions(FjspHandle* h, uint64_t seed, uint64_t t, uint8_t* actio
     DeviceGuard g(h->device);
     const int threads = 256;
     const unsigned blocks = (unsigned)((h->num_envs + threads - 1) / threads);
+    if (h->shared) {
+        DISPATCH_A(h->shared, launch_ex(fjsp_shared_random_actions_kernel<A>, blocks, threads, 0, (cudaStream_t)stream, h->pdl, actions,
+                                        (int64_t)h->num_envs, (int64_t)h->first_env, (uint64_t)seed, (uint64_t)t))
+        h->launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
     DISPATCH_K(h->cells, launch_ex(fjsp_random_actions_kernel<K>, blocks, threads, 0, (cudaStream_t)stream, h->pdl, actions,
                                    (int64_t)h->num_envs, (int64_t)h->first_env, (uint64_t)seed, (uint64_t)t))
     h->launches++;
@@ -561,6 +605,7 @@ int fjsp_random_actions(FjspHandle* h, uint64_t seed, uint64_t t, uint8_t* actio
 
 int fjsp_rollout_random(FjspHandle* h, int steps, uint64_t seed, uint64_t t0, uint64_t* stats, void* stream) {
     if (!h) return fail("handle is NULL");
+    NOT_SHARED(h, "fjsp_rollout_random")
     if (steps < 1) return fail("steps must be >= 1");
     if (!stats || (reinterpret_cast<uintptr_t>(stats) & 7)) return fail("stats must be an 8-byte aligned device pointer (8 x u64)");
     if (seed != h->seed) return fail("rollout seed must equal the seed of the last fjsp_reset (one Philox key per handle)");
@@ -604,9 +649,13 @@ int fjsp_export_packed(FjspHandle* h, int64_t env, uint32_t* out_words) {
 
 int fjsp_export_state_cell(FjspHandle* h, int64_t env, int cell, FjspCanonState* out) {
     if (!out) return fail("out is NULL");
-    if (h && (cell < 0 || cell >= h->cells)) return fail("cell index out of range");
+    if (h && (cell < 0 || cell >= (h->shared ? h->shared : h->cells))) return fail("cell (shared floor: AGV) index out of range");
     u32 words[FJSP_STATE_WORDS_LONG_K(FJSP_MAX_CELLS)];
     if (int rc = fjsp_export_packed(h, env, words)) return rc;
+    if (h->shared) {
+        export_canon_shared(words, h->P, cell, out);
+        return 0;
+    }
     std::vector<u32> rq;
     if (h->long_streams) {
         rq.resize(FJSP_LONG_READY_FIFO);

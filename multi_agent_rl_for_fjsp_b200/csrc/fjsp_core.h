@@ -587,9 +587,11 @@ FJSP_HD void observe_shared(S& s, const Params& P, const Hot& h, O obs, u32* mw)
     mask_set(mw, 2, tcount > 0);
 }
 
-// one cell: AGV (13) + small/big machine (3 + 3) + four packaging stations (12) = 31 floats; 26 mask bytes from `mo`
-template <class S, class O>
-FJSP_HD void observe_cell(S& s, const Params& P, const Hot& h, const HotCell& hc, int c, O obs, u32* mw, int mo) {
+// the AGV whose fields are in `hc`, on the stations of `hc`: 13 floats, 8 mask bytes from `mo`.  SHARED (shared floor):
+// `occ` = station positions taken by other AGVs; otherwise the scaled shop's one-dock rule.
+template <bool SHARED, class S, class O>
+FJSP_HD void observe_agv(S& s, const Params& P, const Hot& h, const HotCell& hc, int c, O obs, u32* mw, int mo, u32 occ) {
+    (void)P;
     const int pb = pool_base<S::LONG>(c);
     // ---- AGV: AGVAgent.get_observation (:53-76) / get_action_mask (:79-178)
     int carrying = hc.carry != 0;
@@ -614,11 +616,12 @@ FJSP_HD void observe_cell(S& s, const Params& P, const Hot& h, const HotCell& hc
     mask_set(mw, mo + 0, 1);
     if (!hc.agv_moving) {
         int loc = hc.agv_loc;
-        mask_set(mw, mo + 1, loc != LOC_PICKUP && (h.dock_mask & ~(1 << c)) == 0);  // one dock (scaled shop)
-        mask_set(mw, mo + 2, loc != LOC_SMALL);
-        mask_set(mw, mo + 3, loc != LOC_BIG);
-        mask_set(mw, mo + 4, loc != LOC_STORAGE);
-        mask_set(mw, mo + 5, loc != LOC_PACKAGING);
+        const u32 blocked = SHARED ? occ : (((h.dock_mask & ~(1 << c)) != 0) ? 1u << LOC_PICKUP : 0u);  // one dock (scaled shop)
+        mask_set(mw, mo + 1, loc != LOC_PICKUP && !((blocked >> LOC_PICKUP) & 1u));
+        mask_set(mw, mo + 2, loc != LOC_SMALL && !((blocked >> LOC_SMALL) & 1u));
+        mask_set(mw, mo + 3, loc != LOC_BIG && !((blocked >> LOC_BIG) & 1u));
+        mask_set(mw, mo + 4, loc != LOC_STORAGE && !((blocked >> LOC_STORAGE) & 1u));
+        mask_set(mw, mo + 5, loc != LOC_PACKAGING && !((blocked >> LOC_PACKAGING) & 1u));
         if (!carrying) {
             int avail = loc == LOC_PICKUP ? h.ready_count
                         : loc == LOC_SMALL ? hc.m[0].r.len
@@ -634,28 +637,38 @@ FJSP_HD void observe_cell(S& s, const Params& P, const Hot& h, const HotCell& hc
             mask_set(mw, mo + 7, ok);  // PICKUP: only an empty tray, never the case
         }
     }
+}
+// machines (3 + 3 floats) and packaging stations (12) of a cell; 18 mask bytes from `mo`
+template <class O>
+FJSP_HD void observe_stations(const Params& P, const HotCell& hc, O obs, u32* mw, int mo) {
     // ---- machines: MachineAgent.get_observation (:62-70) / get_action_mask (:72-97)
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         const Mach& m = hc.m[i];
-        obs.set(13 + 3 * i, m.busy);
-        obs.set(14 + 3 * i, m.prog ? 1 : 0);
-        obs.set(15 + 3 * i, m.q.len);
-        mask_set(mw, mo + 8 + 3 * i, 1);
-        mask_set(mw, mo + 9 + 3 * i, m.q.len > 0 && !m.busy);
-        mask_set(mw, mo + 10 + 3 * i, !m.busy && m.has_cur);
+        obs.set(3 * i, m.busy);
+        obs.set(1 + 3 * i, m.prog ? 1 : 0);
+        obs.set(2 + 3 * i, m.q.len);
+        mask_set(mw, mo + 3 * i, 1);
+        mask_set(mw, mo + 1 + 3 * i, m.q.len > 0 && !m.busy);
+        mask_set(mw, mo + 2 + 3 * i, !m.busy && m.has_cur);
     }
     // ---- packaging: PackagingAgent.get_observation (:54-62) / get_action_mask (:64-89)
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const Pack& p = hc.p[i];
-        obs.set(19 + 3 * i, p.busy);
-        obs.set_prog(20 + 3 * i, p.progL);
-        obs.set_i8(21 + 3 * i, p.qcount);
-        mask_set(mw, mo + 14 + 3 * i, 1);
-        mask_set(mw, mo + 15 + 3 * i, p.qcount > 0 && !p.busy && p.users < P.pack_capacity);
-        mask_set(mw, mo + 16 + 3 * i, !p.busy && p.hascur);
+        obs.set(6 + 3 * i, p.busy);
+        obs.set_prog(7 + 3 * i, p.progL);
+        obs.set_i8(8 + 3 * i, p.qcount);
+        mask_set(mw, mo + 6 + 3 * i, 1);
+        mask_set(mw, mo + 7 + 3 * i, p.qcount > 0 && !p.busy && p.users < P.pack_capacity);
+        mask_set(mw, mo + 8 + 3 * i, !p.busy && p.hascur);
     }
+}
+// one cell: AGV (13) + small/big machine (3 + 3) + four packaging stations (12) = 31 floats; 26 mask bytes from `mo`
+template <class S, class O>
+FJSP_HD void observe_cell(S& s, const Params& P, const Hot& h, const HotCell& hc, int c, O obs, u32* mw, int mo) {
+    observe_agv<false>(s, P, h, hc, c, obs, mw, mo, 0u);
+    observe_stations(P, hc, obs.at(13), mw, mo + 8);
 }
 
 // whole observation; cell 0's hot words are the caller's registers, further cells are re-read
@@ -916,23 +929,26 @@ FJSP_HD void arrivals(S& s, const Params& P, Hot& h) {
     }
 }
 
-// one cell's seven agents: agv, small machine, big machine, four packaging stations.  a/local10/res point at the cell's
-// first column.  pk_start[i] = products whose packaging processes START creates in this step (resolved in run_cell).
+// a tray lost to one of the reference's quirks: the compact layout keeps its record (marked) so that is_processed stays
+// exportable; the long layout keeps processed bits in the ring and gives the pool slot back at once
 template <class S>
-FJSP_HD void act_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, const int* a, int* local10, u32* res, int* pk_start) {
+FJSP_HD void lose_tray(S& s, HotCell& hc, int pb, int slot, u32 r) {
+    if (S::LONG) pool_free(hc, slot);
+    else s.st(pb + slot, r | REC_LOST);
+}
+
+// R2-R4: the AGV whose fields are in `hc` acts on the stations of `hc` (AGVAgent.py:180-368).  SHARED (shared floor,
+// include/fjsp_b200.h): `occ` = station positions taken by OTHER AGVs (bit per location); a move there is invalid.
+// Otherwise the scaled shop's one-dock rule applies (h.dock_mask).
+template <bool SHARED, class S>
+FJSP_HD void act_agv(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, int act, int& local10_out, u32& res_out, u32 occ) {
     constexpr bool LONG = S::LONG;
     using W = WM<LONG>;
     const int pb = pool_base<LONG>(c);
-    // a tray lost to one of the reference's quirks: the compact layout keeps its record (marked) so that is_processed stays
-    // exportable; the long layout keeps processed bits in the ring and gives the pool slot back at once
-    auto lose = [&](int slot, u32 r) {
-        if (LONG) pool_free(hc, slot);
-        else s.st(pb + slot, r | REC_LOST);
-    };
+    auto lose = [&](int slot, u32 r) { lose_tray(s, hc, pb, slot, r); };
     // ---- R2-R4 AGV (AGVAgent.py:180-368)
     {
         int invalid = 0, moved = 0, pick = 0, drop = 0, to_pack = 0, success = 0;
-        const int act = a[0];
         if (hc.agv_moving) {
             invalid = 1;
         } else if (act == 0) {
@@ -940,12 +956,12 @@ FJSP_HD void act_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, 
         } else if (act <= 5) {
             const int tl = act == 1 ? LOC_PICKUP : act == 2 ? LOC_SMALL : act == 3 ? LOC_BIG : act == 4 ? LOC_STORAGE : LOC_PACKAGING;
             const int d = P.dist[hc.agv_loc][tl];
-            if (tl == LOC_PICKUP && d != 0 && (h.dock_mask & ~(1 << c)) != 0) {
-                invalid = 1;  // scaled shop only: the single dock is taken by another cell's AGV
+            if (SHARED ? (d != 0 && ((occ >> tl) & 1u)) : (tl == LOC_PICKUP && d != 0 && (h.dock_mask & ~(1 << c)) != 0)) {
+                invalid = 1;  // shared floor: the position is another AGV's; scaled shop: the single dock is taken
             } else {
                 success = 1;
                 if (d != 0) {
-                    if (tl == LOC_PICKUP) h.dock_mask |= 1 << c;  // granted now: later AGVs of this step already see it
+                    if (!SHARED && tl == LOC_PICKUP) h.dock_mask |= 1 << c;  // granted now: later AGVs of this step already see it
                     moved = 1;
                     hc.agv_moving = 1, hc.agv_target = tl;        // resolved in the run phase
                     hc.agv_arrive = k + P.delay[hc.agv_loc][tl];
@@ -1054,17 +1070,34 @@ FJSP_HD void act_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, 
         } else {
             invalid = 1;
         }
-        res[0] = (success ? FJSP_RES_SUCCESS : 0) | (invalid ? FJSP_RES_AGV_INVALID : 0) | (moved ? FJSP_RES_AGV_MOVED : 0) |
+        res_out = (success ? FJSP_RES_SUCCESS : 0) | (invalid ? FJSP_RES_AGV_INVALID : 0) | (moved ? FJSP_RES_AGV_MOVED : 0) |
                  (pick ? FJSP_RES_AGV_PICKUP : 0) | (drop ? FJSP_RES_AGV_DROP : 0) | (to_pack ? FJSP_RES_AGV_TO_PACK : 0);
         // RewardModel.py:62-77: +2 pickup, +2 drop, +10 delivered to packaging, -0.1 move, -5 invalid
-        local10[0] = (pick ? 20 : 0) + (drop ? 20 : 0) + (to_pack ? 100 : 0) - (moved ? 1 : 0) - (invalid ? 50 : 0);
+        local10_out = (pick ? 20 : 0) + (drop ? 20 : 0) + (to_pack ? 100 : 0) - (moved ? 1 : 0) - (invalid ? 50 : 0);
     }
+}
+
+// one cell's seven agents: agv, small machine, big machine, four packaging stations.  a/local10/res point at the cell's
+// first column.  pk_start[i] = products whose packaging processes START creates in this step (resolved in run_cell).
+template <class S>
+FJSP_HD void act_stations(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, const int* a, int* local10, u32* res, int* pk_start);
+template <class S>
+FJSP_HD void act_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, const int* a, int* local10, u32* res, int* pk_start) {
+    act_agv<false>(s, P, h, hc, c, k, a[0], local10[0], res[0], 0u);
+    act_stations(s, P, h, hc, c, k, a + 1, local10 + 1, res + 1, pk_start);
+}
+// the six station agents of a cell: a/local10/res point at the small machine's column
+template <class S>
+FJSP_HD void act_stations(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, const int* a, int* local10, u32* res, int* pk_start) {
+    constexpr bool LONG = S::LONG;
+    const int pb = pool_base<LONG>(c);
+    auto lose = [&](int slot, u32 r) { lose_tray(s, hc, pb, slot, r); };
     // ---- R5 machines (MachineAgent.py:99-169).  START takes effect in this step's run phase, but no later
     //      agent reads machine state inside the action phase, so it is applied here.
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         Mach& m = hc.m[i];
-        const int act = a[1 + i];
+        const int act = a[i];
         int started = 0, completed = 0, idle_q = 0, success = 0;
         if (act == 0) {
             idle_q = m.q.len > 0 && !m.busy;
@@ -1083,16 +1116,16 @@ FJSP_HD void act_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, 
                 completed = 1, success = 1;
             }
         }
-        res[1 + i] = (success ? FJSP_RES_SUCCESS : 0) | (started ? FJSP_RES_M_STARTED : 0) | (completed ? FJSP_RES_M_COMPLETED : 0) |
+        res[i] = (success ? FJSP_RES_SUCCESS : 0) | (started ? FJSP_RES_M_STARTED : 0) | (completed ? FJSP_RES_M_COMPLETED : 0) |
                      (idle_q ? FJSP_RES_M_IDLE_QUEUE : 0);
         // RewardModel.py:79-86: +1 start, +5 signal complete, -2 idle with queue
-        local10[1 + i] = (started ? 10 : 0) + (completed ? 50 : 0) - ((act == 0 && idle_q) ? 20 : 0);
+        local10[i] = (started ? 10 : 0) + (completed ? 50 : 0) - ((act == 0 && idle_q) ? 20 : 0);
     }
     // ---- R6 packaging (PackagingAgent.py:91-125)
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         Pack& p = hc.p[i];
-        const int act = a[3 + i];
+        const int act = a[2 + i];
         int started = 0, completed = 0, idle_q = 0, success = 0;
         pk_start[i] = 0;
         if (act == 0) {
@@ -1108,10 +1141,10 @@ FJSP_HD void act_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, 
         } else if (act == 2) {
             if (!p.busy && p.hascur) completed = 1;  // success stays False (:120-123)
         }
-        res[3 + i] = (success ? FJSP_RES_SUCCESS : 0) | (started ? FJSP_RES_M_STARTED : 0) | (completed ? FJSP_RES_M_COMPLETED : 0) |
+        res[2 + i] = (success ? FJSP_RES_SUCCESS : 0) | (started ? FJSP_RES_M_STARTED : 0) | (completed ? FJSP_RES_M_COMPLETED : 0) |
                      (idle_q ? FJSP_RES_M_IDLE_QUEUE : 0);
         // RewardModel.py:88-95: +2 start, +20 signal complete, -1 idle with queue
-        local10[3 + i] = (started ? 20 : 0) + (completed ? 200 : 0) - ((act == 0 && idle_q) ? 10 : 0);
+        local10[2 + i] = (started ? 20 : 0) + (completed ? 200 : 0) - ((act == 0 && idle_q) ? 10 : 0);
     }
 }
 
@@ -1120,13 +1153,17 @@ FJSP_HD void act_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, 
 // ---------------------------------------------------------------------------------------------
 // `dock_after` collects who holds the dock once the run phase is over; h.dock_mask itself keeps its action-phase meaning
 // until every cell has acted (cells are processed one after the other here, but all actions precede all runs).
+// AGV arrival (AGVAgent.py:387-396)
+FJSP_HD void run_agv(HotCell& hc, int k) {
+    if (hc.agv_moving && hc.agv_arrive == (u32)(k & 0xffff)) hc.agv_loc = hc.agv_target, hc.agv_moving = 0;
+}
 template <class S>
 FJSP_HD void run_cell(S& s, const Params& P, Hot& h, HotCell& hc, int c, int k, const int* pk_start, int& dock_after) {
     constexpr bool LONG = S::LONG;
     using W = WM<LONG>;
     const int pb = pool_base<LONG>(c);
-    // AGV arrival (AGVAgent.py:387-396); the dock is held while standing at PICKUP or under way to it
-    if (hc.agv_moving && hc.agv_arrive == k) hc.agv_loc = hc.agv_target, hc.agv_moving = 0;
+    run_agv(hc, k);
+    // the dock is held while standing at PICKUP or under way to it
     dock_after |= (hc.agv_moving ? (hc.agv_target == LOC_PICKUP) : (hc.agv_loc == LOC_PICKUP)) << c;
     // machines: product i (1-based) is flagged in step start + P*i; the tray finishes at start + P*n
 #pragma unroll

@@ -54,6 +54,8 @@ inline const char* make_params(const FjspConfig& c, Params* P) {
     if (c.storage_capacity < 0) return "storage_capacity must be >= 0";
     if (c.num_trays < 0 || c.num_trays > 65535) return "num_trays must be in 0..65535";
     if (c.num_cells < 1 || c.num_cells > FJSP_MAX_CELLS) return "num_cells must be in 1..4";
+    if (c.shared_agvs < 0 || c.shared_agvs > FJSP_MAX_SHARED_AGVS) return "shared_agvs must be in 0..4";
+    if (c.shared_agvs >= 2 && (c.num_cells != 1 || c.long_streams)) return "the shared floor (shared_agvs >= 2) needs num_cells = 1 and long_streams = 0";
     for (int a = 0; a < FJSP_NUM_LOCATIONS; a++)
         for (int b = a + 1; b < FJSP_NUM_LOCATIONS; b++)
             if (c.pos[a][0] == c.pos[b][0] && c.pos[a][1] == c.pos[b][1]) return "station positions must be distinct";
@@ -346,6 +348,14 @@ inline void dispatch_layout(int cells, bool long_streams, F&& f) {
 inline void export_canon(const u32* words, const u32* rq, const Params& P, int cells, bool long_streams, int cell, FjspCanonState* out,
                          int32_t* order_base = nullptr) {
     dispatch_layout(cells, long_streams, [&](auto k, auto l) { export_canon_k<decltype(k)::value, decltype(l)::value>(words, rq, P, cell, out, order_base); });
+}
+// shared floor (fjsp_shared.h): the canonical record of AGV `agv` = the reference shop's record with that AGV's word in
+// place of agv_0's (the stations, the pickup station and the orders are common to all AGVs)
+inline void export_canon_shared(const u32* words, const Params& P, int agv, FjspCanonState* out) {
+    u32 w[FJSP_STATE_WORDS];
+    memcpy(w, words, sizeof(w));
+    if (agv >= 1) w[W_AGV] = words[FJSP_STATE_WORDS + agv - 1];
+    export_canon_k<1, false>(w, nullptr, P, 0, out);
 }
 inline void export_orders(const u32* words, const Params& P, int cells, bool long_streams, int first, int count, int32_t* out4) {
     dispatch_layout(cells, long_streams, [&](auto k, auto l) { export_orders_k<decltype(k)::value, decltype(l)::value>(words, P, first, count, out4); });

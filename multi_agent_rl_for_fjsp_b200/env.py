@@ -51,6 +51,24 @@ def agent_layout(cells: int = 1):
     return ids, tuple(nact), obs_sl, mask_off
 
 
+def shared_agent_layout(agvs: int):
+    """(agent_ids, n_actions, obs_slices, mask_offsets) of the shared floor (include/fjsp_b200.h): pickup station, agv_0 ..
+    agv_{A-1}, machines, packaging stations."""
+    ids, nact, obs_sl, mask_off = ["pickup_station"], [3], [(0, 7)], [0, 3]
+    for j in range(agvs):
+        ids.append("agv_%d" % j)
+        nact.append(8)
+        obs_sl.append((7 + 13 * j, 20 + 13 * j))
+        mask_off.append(mask_off[-1] + 8)
+    base = 7 + 13 * agvs
+    for j, name in enumerate(AGENT_IDS[2:]):
+        ids.append(name)
+        nact.append(3)
+        obs_sl.append((base + 3 * j, base + 3 * j + 3))
+        mask_off.append(mask_off[-1] + 3)
+    return ids, tuple(nact), obs_sl, mask_off
+
+
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -71,8 +89,10 @@ class BatchedFJSPEnv:
             raise ValueError("num_cells must be in 1..%d" % abi.MAX_CELLS)
         self.long_streams = bool(self.cfg.long_streams)   # the long order-stream layout (include/fjsp_b200.h)
         self.max_orders = abi.LONG_MAX_ORDERS if self.long_streams else abi.MAX_ORDERS
-        self.dims = abi.dims(self.cells, self.long_streams)
-        self.agent_ids, self.n_actions, self.obs_slices, self.mask_offsets = agent_layout(self.cells)
+        self.shared_agvs = int(self.cfg.shared_agvs) if int(self.cfg.shared_agvs) >= 2 else 0   # shared floor (include/fjsp_b200.h)
+        self.dims = abi.dims(self.cells, self.long_streams, self.shared_agvs)
+        self.agent_ids, self.n_actions, self.obs_slices, self.mask_offsets = (
+            shared_agent_layout(self.shared_agvs) if self.shared_agvs else agent_layout(self.cells))
         self.act_dim, self.obs_dim, self.mask_dim = self.dims["act"], self.dims["obs"], self.dims["mask"]
         self.seed, self.num_orders, self.autoreset = int(seed), int(num_orders), bool(autoreset)
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()

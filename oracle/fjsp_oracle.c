@@ -144,6 +144,9 @@ typedef struct OracleEnv {
     /* cells: each has its AGV, machines, storage and packaging stations (one cell = the reference shop) */
     struct Cell cells[FJSP_MAX_CELLS];
     int ncells;
+    /* shared floor (include/fjsp_b200.h): nagv AGVs on the stations of cells[0]; AGV j's own fields (position, tray,
+     * movement) live in cells[j], nothing else of cells[1..] is used.  nagv = 1: the reference. */
+    int nagv;
     /* tracking */
     int current_step, completed_orders, total_products_packaged, fault;
 } OracleEnv;
@@ -218,6 +221,13 @@ void fjsp_oracle_reset(OracleEnv* e, const FjspOrderRec* orders, int num_orders)
     e->cfg = cfg, e->small_steps = ss, e->big_steps = bs, e->pack_steps = ps;
     /* _init_agents (:62-82), once per cell */
     e->ncells = cfg.num_cells < 1 ? 1 : (cfg.num_cells > FJSP_MAX_CELLS ? FJSP_MAX_CELLS : cfg.num_cells);
+    e->nagv = 1;
+    if (cfg.shared_agvs >= 2) { /* shared floor: one set of stations, shared_agvs AGVs (AGV j's fields in cells[j]) */
+        static const int start_loc[FJSP_MAX_SHARED_AGVS] = {LOC_PICKUP, LOC_STORAGE, LOC_SMALL, LOC_BIG};
+        e->ncells = 1;
+        e->nagv = cfg.shared_agvs > FJSP_MAX_SHARED_AGVS ? FJSP_MAX_SHARED_AGVS : cfg.shared_agvs;
+        for (int j = 1; j < e->nagv; j++) e->cells[j].agv_row = cfg.pos[start_loc[j]][0], e->cells[j].agv_col = cfg.pos[start_loc[j]][1];
+    }
     for (int ci = 0; ci < e->ncells; ci++) {
         Cell* c = &e->cells[ci];
         /* AGVAgent.py:41: the AGV starts at PICKUP; the dock holds one AGV, so AGVs of further cells start at STORAGE */
@@ -272,12 +282,24 @@ static int dock_blocked_for(const OracleEnv* e, const Cell* c) {
     return 0;
 }
 
+/* shared floor: station position `loc` is taken by another AGV (standing there, or under way to it) */
+static int loc_taken_by_other(const OracleEnv* e, const Cell* c, int loc) {
+    for (int j = 0; j < e->nagv; j++) {
+        const Cell* o = &e->cells[j];
+        if (o == c) continue;
+        const int at = (o->is_moving || o->move_created_now) ? o->move_target_loc : agv_location(e, o);
+        if (at == loc) return 1;
+    }
+    return 0;
+}
+
 /* one cell's block of the observation: AGV (13) + small/big machine (3 + 3) + four packaging stations (12) = 31 floats,
  * and of the masks: 8 + 3 + 3 + 12 = 26 bytes */
-static void observe_cell(const OracleEnv* e, const Cell* c, float* obs, int8_t* masks) {
+/* the AGV block (13 floats, 8 mask bytes) of AGV `c` working on the stations of `st` (st == c except on the shared floor) */
+static void observe_agv(const OracleEnv* e, const Cell* c, const Cell* st, float* obs, int8_t* masks) {
     /* --- AGV: AGVAgent.get_observation (:53-76), keys sorted --- */
-    const Machine* sm = &c->machine[0];
-    const Machine* bm = &c->machine[1];
+    const Machine* sm = &st->machine[0];
+    const Machine* bm = &st->machine[1];
     const Tray* tr = c->carrying;
     obs[0] = (float)bm->is_busy;
     obs[1] = (float)bm->ready.n;
@@ -286,7 +308,7 @@ static void observe_cell(const OracleEnv* e, const Cell* c, float* obs, int8_t* 
     obs[4] = (float)c->agv_row, obs[5] = (float)c->agv_col;
     obs[6] = (float)sm->is_busy;
     obs[7] = (float)sm->ready.n;
-    obs[8] = (float)c->storage.n;
+    obs[8] = (float)st->storage.n;
     obs[9] = (float)(tr && tray_needs_packaging(tr));
     obs[10] = (float)(tr && tray_needs_processing(tr));
     obs[11] = (float)(tr ? tr->n : 0);
@@ -299,12 +321,15 @@ static void observe_cell(const OracleEnv* e, const Cell* c, float* obs, int8_t* 
             int loc = agv_location(e, c);
             static const int move_loc[6] = {-1, LOC_PICKUP, LOC_SMALL, LOC_BIG, LOC_STORAGE, LOC_PACKAGING};
             for (int a = 1; a <= 5; a++) m[a] = (int8_t)(loc != move_loc[a]);
-            if (m[1] && dock_blocked_for(e, c)) m[1] = 0; /* scaled shop only: the dock is taken */
+            if (e->nagv > 1) { /* shared floor: every station position holds one AGV */
+                for (int a = 1; a <= 5; a++)
+                    if (m[a] && loc_taken_by_other(e, c, move_loc[a])) m[a] = 0;
+            } else if (m[1] && dock_blocked_for(e, c)) m[1] = 0; /* scaled shop only: the dock is taken */
             if (tr == NULL && loc != LOC_NONE) {
                 if (loc == LOC_PICKUP) m[6] = (int8_t)(e->ps_ready.n > 0);
                 else if (loc == LOC_SMALL) m[6] = (int8_t)(sm->ready.n > 0);
                 else if (loc == LOC_BIG) m[6] = (int8_t)(bm->ready.n > 0);
-                else if (loc == LOC_STORAGE) m[6] = (int8_t)(c->storage.n > 0);
+                else if (loc == LOC_STORAGE) m[6] = (int8_t)(st->storage.n > 0);
             } else if (tr != NULL && loc != LOC_NONE) {
                 int ty = tray_type(tr);
                 if (loc == LOC_PICKUP) m[7] = (int8_t)(tr->n == 0);
@@ -315,11 +340,15 @@ static void observe_cell(const OracleEnv* e, const Cell* c, float* obs, int8_t* 
             }
         }
     }
+}
+
+/* machines (6 floats, 6 mask bytes) and packaging stations (12, 12) of one cell */
+static void observe_stations(const OracleEnv* e, const Cell* c, float* obs, int8_t* masks) {
     /* --- machines: MachineAgent.get_observation (:62-70), get_action_mask (:72-97) --- */
     for (int i = 0; i < 2; i++) {
         const Machine* m = &c->machine[i];
-        float* o = obs + 13 + 3 * i;
-        int8_t* k = masks + 8 + 3 * i;
+        float* o = obs + 3 * i;
+        int8_t* k = masks + 3 * i;
         o[0] = (float)m->is_busy;
         o[1] = m->progress_done ? 1.0f : 0.0f;
         o[2] = (float)(int8_t)m->queue.n; /* dtype=np.int8, :67 */
@@ -330,8 +359,8 @@ static void observe_cell(const OracleEnv* e, const Cell* c, float* obs, int8_t* 
     /* --- packaging: PackagingAgent.get_observation (:54-62), get_action_mask (:64-89) --- */
     for (int i = 0; i < 4; i++) {
         const Pack* p = &c->pack[i];
-        float* o = obs + 19 + 3 * i;
-        int8_t* k = masks + 14 + 3 * i;
+        float* o = obs + 6 + 3 * i;
+        int8_t* k = masks + 6 + 3 * i;
         o[0] = (float)p->is_busy;
         o[1] = (float)p->progress; /* np.array(double, dtype=np.float32) */
         o[2] = (float)(int8_t)p->qn;
@@ -341,8 +370,13 @@ static void observe_cell(const OracleEnv* e, const Cell* c, float* obs, int8_t* 
     }
 }
 
+static void observe_cell(const OracleEnv* e, const Cell* c, float* obs, int8_t* masks) {
+    observe_agv(e, c, c, obs, masks);
+    observe_stations(e, c, obs + 13, masks + 8);
+}
+
 void fjsp_oracle_observe(const OracleEnv* e, float* obs, int8_t* masks) {
-    memset(masks, 0, (size_t)FJSP_MASK_DIM_K(e->ncells));
+    memset(masks, 0, (size_t)(e->nagv > 1 ? FJSP_SHARED_MASK_DIM(e->nagv) : FJSP_MASK_DIM_K(e->ncells)));
     /* --- pickup station: PickupStationAgent.get_observation (:58-98), keys sorted --- */
     int order_size = 0, remaining = 0, next_type = 0, next_colour = 0;
     if (e->current_order) {
@@ -372,6 +406,11 @@ void fjsp_oracle_observe(const OracleEnv* e, float* obs, int8_t* masks) {
         masks[0] = 1;
         masks[1] = (int8_t)(has_order && has_tray && tray_not_full && prem);
         masks[2] = (int8_t)(e->current_tray && e->current_tray->n > 0);
+    }
+    if (e->nagv > 1) { /* shared floor: pickup station | AGVs | machines | packaging stations */
+        for (int j = 0; j < e->nagv; j++) observe_agv(e, &e->cells[j], &e->cells[0], obs + 7 + 13 * j, masks + 3 + 8 * j);
+        observe_stations(e, &e->cells[0], obs + 7 + 13 * e->nagv, masks + 3 + 8 * e->nagv);
+        return;
     }
     for (int ci = 0; ci < e->ncells; ci++) observe_cell(e, &e->cells[ci], obs + 7 + 31 * ci, masks + 3 + 26 * ci);
 }
@@ -465,7 +504,8 @@ static void add_tray_to_packaging(OracleEnv* e, Cell* c, Tray* t) {
 }
 
 /* AGVAgent.execute_action (:180-252), _execute_pickup (:254-293), _execute_drop (:295-368) */
-static double act_agv(OracleEnv* e, Cell* c, int action, uint8_t* res) {
+/* `st` = the cell whose stations the AGV works on (st == c except on the shared floor, where it is cells[0]) */
+static double act_agv(OracleEnv* e, Cell* c, Cell* st, int action, uint8_t* res) {
     int invalid = 0, moved = 0, pickup_ok = 0, drop_ok = 0, to_pack = 0, success = 0;
     if (c->is_moving) {
         invalid = 1; /* :210-212 */
@@ -475,7 +515,9 @@ static double act_agv(OracleEnv* e, Cell* c, int action, uint8_t* res) {
         static const int move_loc[6] = {-1, LOC_PICKUP, LOC_SMALL, LOC_BIG, LOC_STORAGE, LOC_PACKAGING}; /* :218-224 */
         int tl = move_loc[action];
         int d = abs(c->agv_row - e->cfg.pos[tl][0]) + abs(c->agv_col - e->cfg.pos[tl][1]);
-        if (tl == LOC_PICKUP && d != 0 && dock_blocked_for(e, c)) {
+        if (e->nagv > 1 && d != 0 && loc_taken_by_other(e, c, tl)) {
+            invalid = 1; /* shared floor: the position is occupied by (or granted to) another AGV */
+        } else if (e->nagv == 1 && tl == LOC_PICKUP && d != 0 && dock_blocked_for(e, c)) {
             invalid = 1; /* scaled shop only: the single dock of the pickup station is taken by another cell's AGV */
         } else {
         success = 1;
@@ -509,9 +551,9 @@ static double act_agv(OracleEnv* e, Cell* c, int action, uint8_t* res) {
                 }
             }
             if (loc == LOC_PICKUP) t = tl_pop0(&e->ps_ready);
-            else if (loc == LOC_SMALL) t = tl_pop0(&c->machine[0].ready);
-            else if (loc == LOC_BIG) t = tl_pop0(&c->machine[1].ready);
-            else if (loc == LOC_STORAGE) t = tl_pop0(&c->storage);
+            else if (loc == LOC_SMALL) t = tl_pop0(&st->machine[0].ready);
+            else if (loc == LOC_BIG) t = tl_pop0(&st->machine[1].ready);
+            else if (loc == LOC_STORAGE) t = tl_pop0(&st->storage);
             if (t) c->carrying = t, success = 1, pickup_ok = 1;
             else invalid = 1;
         }
@@ -528,15 +570,15 @@ static double act_agv(OracleEnv* e, Cell* c, int action, uint8_t* res) {
             int ty = tray_type(t);
             int compatible = (loc == LOC_SMALL) ? (ty == TYPE_SMALL || ty == TYPE_MEDIUM) : (ty == TYPE_BIG || ty == TYPE_MEDIUM);
             if (tray_needs_processing(t) && compatible) {
-                tl_push(&c->machine[loc == LOC_SMALL ? 0 : 1].queue, t); /* add_tray, MachineAgent.py:141-143 */
+                tl_push(&st->machine[loc == LOC_SMALL ? 0 : 1].queue, t); /* add_tray, MachineAgent.py:141-143 */
                 drop_ok = 1;
             } else invalid = 1;
         } else if (loc == LOC_STORAGE) {
-            if (c->storage.n < e->cfg.storage_capacity) tl_push(&c->storage, t); /* Storage.add_tray (:16-22); False ignored */
+            if (st->storage.n < e->cfg.storage_capacity) tl_push(&st->storage, t); /* Storage.add_tray (:16-22); False ignored */
             drop_ok = 1;
         } else if (loc == LOC_PACKAGING) {
             if (tray_needs_packaging(t) && !tray_needs_processing(t)) {
-                add_tray_to_packaging(e, c, t);
+                add_tray_to_packaging(e, st, t);
                 drop_ok = 1, to_pack = 1;
             } else invalid = 1;
         }
@@ -718,14 +760,15 @@ void fjsp_oracle_step(OracleEnv* e, const uint8_t* actions, float* obs, int8_t* 
                       uint8_t* flags, uint8_t* results) {
     uint8_t res_local[FJSP_ACT_DIM_K(FJSP_MAX_CELLS)];
     uint8_t* res = results ? results : res_local;
-    const int K = e->ncells, A = FJSP_AGENTS_K(K);
+    const int K = e->ncells, A = e->nagv > 1 ? FJSP_SHARED_AGENTS(e->nagv) : FJSP_AGENTS_K(K);
+    const int act_dim = e->nagv > 1 ? FJSP_SHARED_ACT_DIM(e->nagv) : FJSP_ACT_DIM_K(K);
     int orders_before = e->completed_orders;
     int products_before = e->total_products_packaged;
     double local[FJSP_ACT_DIM_K(FJSP_MAX_CELLS)];
     if (e->current_step > e->cfg.max_episode_steps) {
         /* stepped after the truncation step without a reset: the port's env is inert and says so (the reference would go
          * on simulating; include/fjsp_b200.h FJSP_FAULT_PAST_END) */
-        for (int i = 0; i < FJSP_ACT_DIM_K(K); i++) res[i] = 0;
+        for (int i = 0; i < act_dim; i++) res[i] = 0;
         for (int i = 0; i < A; i++) rewards[i] = 0.0;
         if (obs && masks) fjsp_oracle_observe(e, obs, masks);
         flags[0] = 0, flags[1] = 1, flags[2] = FJSP_FAULT_PAST_END, flags[3] = 0;
@@ -740,10 +783,23 @@ void fjsp_oracle_step(OracleEnv* e, const uint8_t* actions, float* obs, int8_t* 
     /* 1. actions in dict order (FJSPSimulation.py:172-174, :76-82): pickup station, then cell by cell agv, small
      *    machine, big machine, four packaging stations (one cell = the reference's order) */
     local[0] = act_pickup(e, actions[0], &res[0]);
+    if (e->nagv > 1) { /* shared floor: pickup station, the AGVs in index order, machines, packaging stations */
+        Cell* st = &e->cells[0];
+        const int n = e->nagv;
+        for (int i = A; i < act_dim; i++) res[i] = 0;
+        for (int j = 0; j < n; j++) local[1 + j] = act_agv(e, &e->cells[j], st, actions[1 + j], &res[1 + j]);
+        local[1 + n] = act_machine(e, &st->machine[0], actions[1 + n], &res[1 + n]);
+        local[2 + n] = act_machine(e, &st->machine[1], actions[2 + n], &res[2 + n]);
+        for (int i = 0; i < 4; i++) local[3 + n + i] = act_pack(e, &st->pack[i], actions[3 + n + i], &res[3 + n + i]);
+        for (int j = 0; j < n; j++) run_agv(e, &e->cells[j]);
+        run_machine(e, &st->machine[0]);
+        run_machine(e, &st->machine[1]);
+        for (int i = 0; i < 4; i++) run_pack(e, &st->pack[i]);
+    } else {
     for (int ci = 0; ci < K; ci++) {
         Cell* c = &e->cells[ci];
         const int b = 1 + 7 * ci;
-        local[b] = act_agv(e, c, actions[b], &res[b]);
+        local[b] = act_agv(e, c, c, actions[b], &res[b]);
         local[b + 1] = act_machine(e, &c->machine[0], actions[b + 1], &res[b + 1]);
         local[b + 2] = act_machine(e, &c->machine[1], actions[b + 2], &res[b + 2]);
         for (int i = 0; i < 4; i++) local[b + 3 + i] = act_pack(e, &c->pack[i], actions[b + 3 + i], &res[b + 3 + i]);
@@ -755,6 +811,7 @@ void fjsp_oracle_step(OracleEnv* e, const uint8_t* actions, float* obs, int8_t* 
         run_machine(e, &c->machine[0]);
         run_machine(e, &c->machine[1]);
         for (int i = 0; i < 4; i++) run_pack(e, &c->pack[i]);
+    }
     }
     /* 3. _check_order_completions (:245-258) */
     for (int o = 0; o < e->norders; o++) {
@@ -823,11 +880,12 @@ void fjsp_oracle_export_orders(const OracleEnv* e, int first, int count, int32_t
 }
 
 void fjsp_oracle_export_cell(const OracleEnv* e, int cell, FjspCanonState* s) {
-    const Cell* c = &e->cells[cell];
+    const Cell* agv = &e->cells[cell];                        /* shared floor: `cell` = AGV index, the stations are cells[0]'s */
+    const Cell* c = e->nagv > 1 ? &e->cells[0] : agv;
     memset(s, 0, sizeof(*s));
     g_long_entries = e->cfg.long_streams != 0;
     s->current_step = e->current_step, s->num_orders = e->norders, s->fault = e->fault;
-    s->agv_row = c->agv_row, s->agv_col = c->agv_col, s->agv_carry = tray_entry(c->carrying), s->agv_is_moving = c->is_moving;
+    s->agv_row = agv->agv_row, s->agv_col = agv->agv_col, s->agv_carry = tray_entry(agv->carrying), s->agv_is_moving = agv->is_moving;
     s->ps_order_queue_len = order_queue_len(e);
     s->ps_current_order = e->current_order ? e->current_order->id : -1;
     s->ps_product_idx = e->current_order_product_idx;
@@ -912,6 +970,22 @@ void fjsp_oracle_philox_actions_k(uint64_t seed, uint64_t genv, uint64_t t, int 
             a[7 * c + j] = (uint8_t)((h * nact[j]) >> 16);
         }
     }
+}
+
+/* shared floor: the reference stream's eight values serve (pickup station, agv_0, machines, stations); AGVs 1.. draw from
+ * counter word 3 = 17 (u16 lane j - 1) */
+void fjsp_oracle_philox_actions_shared(uint64_t seed, uint64_t genv, uint64_t t, int nagv, uint8_t* a) {
+    uint8_t base[8];
+    uint32_t r[4];
+    fjsp_oracle_philox_actions(seed, genv, t, base);
+    philox4x32_10((uint32_t)genv, (uint32_t)t, (uint32_t)(t >> 32), 17u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    for (int i = 0; i < FJSP_SHARED_ACT_DIM(nagv); i++) a[i] = 0;
+    a[0] = base[0], a[1] = base[1];
+    for (int j = 1; j < nagv; j++) {
+        uint32_t h = ((j - 1) & 1) ? (r[(j - 1) >> 1] >> 16) : (r[(j - 1) >> 1] & 0xffffu);
+        a[1 + j] = (uint8_t)((h * 8u) >> 16);
+    }
+    for (int i = 0; i < 6; i++) a[1 + nagv + i] = base[2 + i];
 }
 
 /* ------------------------------------------------------------------ batch rollout (CPU baseline + full-size statistics parity)

@@ -33,6 +33,7 @@ class FjspConfig(C.Structure):
         ("storage_capacity", C.c_int32), ("pack_capacity", C.c_int32),
         ("tray_capacity", C.c_int32), ("num_trays", C.c_int32), ("num_cells", C.c_int32),
         ("long_streams", C.c_int32), ("arrival_prob_q16", C.c_int32), ("arrival_max_orders", C.c_int32),
+        ("shared_agvs", C.c_int32),
     ]
 
 
@@ -87,6 +88,7 @@ def _bind(path):
             C.c_void_p]
         L.fjsp_oracle_reset_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32]
         L.fjsp_oracle_export_orders.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.fjsp_oracle_philox_actions_shared.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
     return L
 
 
@@ -120,8 +122,18 @@ def philox_actions(seed: int, genv: int, t: int, cells: int = 1) -> np.ndarray:
     return out
 
 
-def dims(cells: int = 1) -> dict:
-    """Row widths of a K-cell shop (include/fjsp_b200.h FJSP_*_K); K = 1 is the reference shop."""
+def philox_actions_shared(seed: int, genv: int, t: int, agvs: int) -> np.ndarray:
+    out = np.zeros(dims(1, agvs)["act"], dtype=np.uint8)
+    lib().fjsp_oracle_philox_actions_shared(seed, genv, t, agvs, out.ctypes.data)
+    return out
+
+
+def dims(cells: int = 1, shared_agvs: int = 0) -> dict:
+    """Row widths of a K-cell shop (include/fjsp_b200.h FJSP_*_K); K = 1 is the reference shop.  shared_agvs >= 2: the
+    shared floor (FJSP_SHARED_*)."""
+    if shared_agvs >= 2:
+        a = shared_agvs
+        return {"agents": 7 + a, "act": (7 + a + 7) // 8 * 8, "obs": 25 + 13 * a, "mask": (21 + 8 * a + 15) // 16 * 16}
     agents = 1 + 7 * cells
     return {"agents": agents, "act": (agents + 7) // 8 * 8, "obs": 7 + 31 * cells, "mask": (3 + 26 * cells + 31) // 32 * 32}
 
@@ -136,7 +148,8 @@ class OracleEnv:
         if not self._h:
             raise MemoryError("fjsp_oracle_create failed")
         self.cells = max(1, int(self.cfg.num_cells))
-        d = dims(self.cells)
+        self.shared_agvs = int(self.cfg.shared_agvs) if int(self.cfg.shared_agvs) >= 2 else 0
+        d = dims(self.cells, self.shared_agvs)
         self.obs = np.zeros(d["obs"], dtype=np.float32)
         self.masks = np.zeros(d["mask"], dtype=np.int8)
         self.rewards = np.zeros(d["act"], dtype=np.float64)

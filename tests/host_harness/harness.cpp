@@ -7,12 +7,14 @@
 #include <stdlib.h>
 
 #include "../../multi_agent_rl_for_fjsp_b200/csrc/fjsp_host.h"
+#include "../../multi_agent_rl_for_fjsp_b200/csrc/fjsp_shared.h"
 
 using namespace fjsp;
 
 struct HostEnv {
     Params P;
     int cells;
+    int shared;   // shared floor: number of AGVs (0 = off)
     bool long_streams;
     uint64_t seed, genv;                       // long layout: order / arrival streams
     FjspOrderRec otab[FJSP_LONG_MAX_ORDERS];   // long layout: explicit order table of the current episode
@@ -33,7 +35,19 @@ struct HostEnv {
     if ((e)->long_streams) { constexpr bool LONG = true; auto s = env_state<true>(e); (void)LONG; (void)s; DISPATCH_K1(e, __VA_ARGS__) } \
     else { constexpr bool LONG = false; auto s = env_state<false>(e); (void)LONG; (void)s; DISPATCH_K1(e, __VA_ARGS__) }
 
-static int state_words(const HostEnv* e) { return e->long_streams ? FJSP_STATE_WORDS_LONG_K(e->cells) : FJSP_STATE_WORDS_K(e->cells); }
+// shared floor: A AGVs; `s` is the env's word accessor
+#define DISPATCH_A(e, ...)                                    \
+    {                                                         \
+        auto s = env_state<false>(e);                         \
+        (void)s;                                              \
+        switch ((e)->shared) {                                \
+            case 2: { constexpr int A = 2; __VA_ARGS__; } break;  \
+            case 3: { constexpr int A = 3; __VA_ARGS__; } break;  \
+            default: { constexpr int A = 4; __VA_ARGS__; } break; \
+        }                                                     \
+    }
+
+static int state_words(const HostEnv* e) { return e->shared ? FJSP_SHARED_STATE_WORDS : e->long_streams ? FJSP_STATE_WORDS_LONG_K(e->cells) : FJSP_STATE_WORDS_K(e->cells); }
 template <bool LONG>
 static ArrayStateT<LONG> env_state(HostEnv* e) {
     ArrayStateT<LONG> s{e->words};
@@ -54,6 +68,7 @@ void* hh_create(const FjspConfig* cfg) {
     }
     e->cells = c.num_cells;
     e->long_streams = c.long_streams != 0;
+    e->shared = c.shared_agvs >= 2 ? c.shared_agvs : 0;
     return e;
 }
 const char* hh_check_config(const FjspConfig* cfg) {
@@ -76,6 +91,17 @@ static void unpack_bytes(const u32* w, int n, uint8_t* dst) {
 
 void hh_observe(void* p, float* obs, int8_t* masks) {
     HostEnv* e = (HostEnv*)p;
+    if (e->shared) {
+        DISPATCH_A(e, {
+            Hot h;
+            HotCell c0;
+            u32 ax[3] = {0u, 0u, 0u}, mw[ShLay<A>::MASK / 4];
+            load_hot(s, h), load_cell<1>(s, 0, c0), shared_load_agvs<A>(s, ax);
+            shared_observe<A>(s, e->P, h, c0, ax, FloatSink{obs, e->P}, mw);
+            unpack_bytes(mw, ShLay<A>::MASK, (uint8_t*)masks);
+        })
+        return;
+    }
     DISPATCH_K(e, {
         u32 mw[Lay<K>::MASK / 4];
         observe_env<K>(s, e->P, obs, mw);
@@ -92,12 +118,37 @@ void hh_reset(void* p, const FjspOrderRec* orders, int num_orders, uint64_t seed
         memcpy(e->otab, orders, sizeof(FjspOrderRec) * (size_t)e->otab_n);
         orders = e->otab;
     }
+    if (e->shared) {
+        DISPATCH_A(e, shared_reset<A>(s, e->P, num_orders, orders, seed, genv, episode))
+        return;
+    }
     DISPATCH_K(e, reset_env<K>(s, e->P, num_orders, orders, seed, genv, episode))
 }
 
 void hh_step(void* p, const uint8_t* actions, float* obs, int8_t* masks, float* rewards, uint8_t* flags, uint8_t* results,
              int32_t* infos) {
     HostEnv* e = (HostEnv*)p;
+    if (e->shared) {
+        DISPATCH_A(e, {
+            int a[ShLay<A>::ACT];
+            for (int i = 0; i < ShLay<A>::ACT; i++) a[i] = actions[i];
+            ShOut<A> out;
+            out.obs = obs;
+            Hot h;
+            HotCell c0;
+            u32 ax[3] = {0u, 0u, 0u};
+            load_hot(s, h), load_cell<1>(s, 0, c0), shared_load_agvs<A>(s, ax);
+            shared_step<A>(s, e->P, h, c0, ax, a, out);
+            store_hot(s, h), store_cell<1>(s, 0, c0), shared_store_agvs<A>(s, ax);
+            unpack_bytes(out.mask, ShLay<A>::MASK, (uint8_t*)masks);
+            for (int i = 0; i < ShLay<A>::ACT; i++) rewards[i] = out.reward[i];
+            flags[0] = out.flags & 0xff, flags[1] = (out.flags >> 8) & 0xff, flags[2] = (out.flags >> 16) & 0xff, flags[3] = 0;
+            if (results) unpack_bytes(out.results, ShLay<A>::ACT, results);
+            if (infos)
+                for (int i = 0; i < 4; i++) infos[i] = out.info[i];
+        })
+        return;
+    }
     DISPATCH_K(e, {
         int a[Lay<K>::ACT];
         for (int i = 0; i < Lay<K>::ACT; i++) a[i] = actions[i];
@@ -183,6 +234,10 @@ int hh_step_cells(void* p, const uint8_t* actions, float* obs, int8_t* masks, fl
 
 void hh_export(void* p, int cell, FjspCanonState* out) {
     HostEnv* e = (HostEnv*)p;
+    if (e->shared) {
+        export_canon_shared(e->words, e->P, cell, out);
+        return;
+    }
     export_canon(e->words, e->rq, e->P, e->cells, e->long_streams, cell, out);
 }
 void hh_export_orders(void* p, int first, int count, int32_t* out4, int32_t* order_base) {
@@ -204,6 +259,15 @@ void hh_philox_actions(uint64_t seed, uint64_t genv, uint64_t t, int cells, uint
         default: philox_actions_k<4>(seed, genv, t, a); break;
     }
     for (int i = 0; i < FJSP_ACT_DIM_K(cells); i++) out[i] = (uint8_t)a[i];
+}
+void hh_philox_actions_shared(uint64_t seed, uint64_t genv, uint64_t t, int agvs, uint8_t* out) {
+    int a[FJSP_SHARED_ACT_DIM(FJSP_MAX_SHARED_AGVS)] = {0};
+    switch (agvs) {
+        case 2: philox_actions_shared<2>(seed, genv, t, a); break;
+        case 3: philox_actions_shared<3>(seed, genv, t, a); break;
+        default: philox_actions_shared<4>(seed, genv, t, a); break;
+    }
+    for (int i = 0; i < FJSP_SHARED_ACT_DIM(agvs); i++) out[i] = (uint8_t)a[i];
 }
 void hh_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out); }
 }

@@ -15,6 +15,7 @@ _CSRC = os.path.join(_HERE, "..", "..", "multi_agent_rl_for_fjsp_b200", "csrc")
 
 def build():
     srcs = [os.path.join(_HERE, "harness.cpp"), os.path.join(_CSRC, "fjsp_core.h"), os.path.join(_CSRC, "fjsp_host.h"),
+            os.path.join(_CSRC, "fjsp_shared.h"),
             os.path.join(_HERE, "..", "..", "include", "fjsp_b200.h")]
     if (not os.path.exists(_SO)) or any(os.path.getmtime(p) > os.path.getmtime(_SO) for p in srcs):
         os.makedirs(os.path.dirname(_SO), exist_ok=True)
@@ -45,6 +46,7 @@ def lib():
         L.hh_export_orders.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.hh_philox_actions.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
         L.hh_philox.argtypes = [C.c_void_p] * 3
+        L.hh_philox_actions_shared.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -57,7 +59,8 @@ class HostEnv:
         if not self._h:
             raise ValueError(self._L.hh_check_config(C.addressof(self.cfg)).decode())
         self.cells = max(1, int(self.cfg.num_cells))
-        d = dims(self.cells)
+        self.shared_agvs = int(self.cfg.shared_agvs) if int(self.cfg.shared_agvs) >= 2 else 0
+        d = dims(self.cells, self.shared_agvs)
         self.obs = np.zeros(d["obs"], np.float32)
         self.masks = np.zeros(d["mask"], np.int8)
         self.rewards = np.zeros(d["act"], np.float32)
@@ -120,6 +123,10 @@ class HostEnv:
 
     def words(self):
         k = self.cells
+        if self.shared_agvs:
+            w = np.zeros(132, np.uint32)
+            self._L.hh_words(self._h, w.ctypes.data)
+            return w
         w = np.zeros((228 + 64 * k + 24 * (k - 1)) if self.cfg.long_streams else (64 + 64 * k + 20 * (k - 1)), np.uint32)
         self._L.hh_words(self._h, w.ctypes.data)
         return w

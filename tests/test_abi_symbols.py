@@ -46,7 +46,7 @@ def test_default_config_and_errors_without_gpu(lib):
     cfg = abi.default_config()  # host-only call
     assert (cfg.proc_small, cfg.proc_big, cfg.proc_pack, cfg.step_size, cfg.max_episode_steps) == (60, 120, 30, 10, 200)
     assert [tuple(cfg.pos[i]) for i in range(5)] == [(0, 0), (0, 3), (2, 3), (3, 0), (3, 5)]
-    assert lib.fjsp_abi_version() == abi.ABI_VERSION == 3
+    assert lib.fjsp_abi_version() == abi.ABI_VERSION == 4
     import torch
 
     if not torch.cuda.is_available():

@@ -47,3 +47,15 @@ d = e4.dims
 a4 = [e4.random_actions(100 + t, out=torch.empty((n4, d["act"]), dtype=torch.uint8, device=e4.device)) for t in range(reps)]
 b4 = d["act"] + 4 * d["obs"] + d["mask"] + 4 * d["act"] + 4 + 8 * d["state_words"]
 timed("step<4,float>", lambda i: e4.step(a4[i]), n4, d["agents"], b4)
+del e4, a4
+
+cfgs = abi.default_config()
+cfgs.shared_agvs = 4
+es = BatchedFJSPEnv(n1, config=cfgs, seed=3, num_orders=30)
+es.reset()
+ds = es.dims
+acs = [es.random_actions(100 + t, out=torch.empty((n1, ds["act"]), dtype=torch.uint8, device=es.device)) for t in range(reps)]
+for t in range(60):
+    es.step(es.random_actions(t))
+bs = ds["act"] + 4 * ds["obs"] + ds["mask"] + 4 * ds["act"] + 4 + 8 * ds["state_words"]
+timed("shared_step<4>", lambda i: es.step(acs[i]), n1, ds["agents"], bs)

@@ -334,10 +334,25 @@ int fjsp_cells_unpack_views(const float* obs, const int8_t* masks, const float* 
  * Epilogue per problem: + bias[n]; ReLU (FJSP_GEMM_RELU); * (mask(m,n) > 0) (mask indexed like C);
  * colsum[n] += column sums of the stored values (bias gradient); FJSP_GEMM_ATOMIC: atomicAdd into C (split-K);
  * rowdot_*: a fused 1-column head on the stored values (the critic's 128 -> 1 layer).
- * max_ctas = max over the problems of ceil(M / 128) * splitk.  N <= 256. */
+ * max_ctas = max over the problems of ceil(M / 128) * splitk.  N <= 256.
+ * FJSP_OP_PK (b_op only; pairs (KC,PK), (KCS,PK)): B is a PACKED IMAGE of a weight matrix made by fjsp_a2c_gemm_pack —
+ * per 16-wide K chunk the bytes the tensor core reads from shared memory (hi terms, then lo terms of the 3xTF32 split,
+ * four K-quad planes of npad = roundup(N, 16) rows x 16 bytes each): a stage's B tile is a straight copy, no conversion
+ * work per use.  Image size: ceil(K / 16) * 32 * npad floats, 16-byte aligned.  Results are bit-identical to the unpacked
+ * orientations (same split, same accumulation order).  Measured: the same speed as the on-the-fly split —
+ * the kernel's two-stage main loop is latency-bound, not conversion-bound — so the trainer does not use it yet; it is
+ * the B half of a bulk-copy-fed main loop. */
 #define FJSP_OP_KC 0
 #define FJSP_OP_KCS 1
 #define FJSP_OP_MC 2
+#define FJSP_OP_PK 3
+#define FJSP_PACK_IMAGE_FLOATS(n, k) ((((k) + 15) / 16) * 32 * (((n) + 15) / 16 * 16))
+typedef struct FjspPackJob {   /* device array; one job = one weight matrix in one orientation */
+    const float* src;
+    float* dst;                /* FJSP_PACK_IMAGE_FLOATS(N, K) floats */
+    int32_t op;                /* FJSP_OP_KC / KCS: B(n,k) = src[n*ld + k]; FJSP_OP_MC: B(n,k) = src[k*ld + n] */
+    int32_t ld, N, K;
+} FjspPackJob;
 #define FJSP_GEMM_RELU 1
 #define FJSP_GEMM_ATOMIC 2
 typedef struct FjspGemmProb {
@@ -368,6 +383,7 @@ typedef struct FjspGemmProb {
 int fjsp_a2c_loss_grad(const float* logits, const int8_t* masks, const uint8_t* actions, const float* adv, const float* returns,
                        const float* values, const float* adv_mean, const float* adv_rstd, float entropy_coef, int64_t rows, float* dlogits,
                        float* dvalue, float* sums, void* stream);
+int fjsp_a2c_gemm_pack(const FjspPackJob* jobs_device, int njobs, void* stream);
 int fjsp_a2c_gemm(const FjspGemmProb* probs_device, int nprob, int max_ctas, int a_op, int b_op, int passes, void* stream);
 
 /* action_result bit-fields (results[N][8]); reference dict keys in comments */

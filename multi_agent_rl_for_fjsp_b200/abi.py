@@ -86,7 +86,7 @@ EXPORTS = [
     "fjsp_num_cells", "fjsp_step_wire", "fjsp_step_host_wire", "fjsp_wire_decode", "fjsp_wire_row_bytes", "fjsp_set_decode_threads",
     "fjsp_state_total_bytes", "fjsp_state_save", "fjsp_state_load",
     "fjsp_a2c_sample", "fjsp_a2c_counter_add", "fjsp_a2c_gae", "fjsp_cells_pack_actions", "fjsp_cells_unpack_views",
-    "fjsp_a2c_gemm", "fjsp_a2c_loss_grad", "fjsp_export_orders",
+    "fjsp_a2c_gemm", "fjsp_a2c_loss_grad", "fjsp_export_orders", "fjsp_a2c_gemm_pack",
 ]
 
 
@@ -151,6 +151,7 @@ def lib() -> C.CDLL:
     L.fjsp_a2c_gae.argtypes = [vp, vp, vp, vp, vp, C.c_int, i64, C.c_float, C.c_float, vp]
     L.fjsp_a2c_loss_grad.argtypes = [vp] * 8 + [C.c_float, i64, vp, vp, vp, vp]
     L.fjsp_a2c_gemm.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.fjsp_a2c_gemm_pack.argtypes = [vp, C.c_int, vp]
     L.fjsp_cells_pack_actions.argtypes = [vp, vp, i64, C.c_int, vp]
     L.fjsp_cells_unpack_views.argtypes = [vp] * 8 + [i64, C.c_int, vp]
     L.fjsp_export_state.argtypes = [vp, i64, vp]
@@ -202,7 +203,12 @@ def config_from_dict(d: dict | None) -> FjspConfig:
     return cfg
 
 
-OP_KC, OP_KCS, OP_MC = 0, 1, 2
+OP_KC, OP_KCS, OP_MC, OP_PK = 0, 1, 2, 3
+PACK_JOB_DT = np.dtype([("src", "<u8"), ("dst", "<u8"), ("op", "<i4"), ("ld", "<i4"), ("N", "<i4"), ("K", "<i4")])  # FjspPackJob
+
+
+def pack_image_floats(n: int, k: int) -> int:
+    return (k + 15) // 16 * 32 * ((n + 15) // 16 * 16)
 GEMM_RELU, GEMM_ATOMIC = 1, 2
 GEMM_PROB_DT = np.dtype([
     ("A", "<u8"), ("B", "<u8"), ("C", "<u8"), ("bias", "<u8"), ("mask", "<u8"), ("colsum", "<u8"),

@@ -753,15 +753,27 @@ int fjsp_a2c_gemm(const FjspGemmProb* probs, int nprob, int max_ctas, int a_op, 
     if (nprob < 1 || nprob > 65535 || max_ctas < 1) return fail("nprob must be in 1..65535 and max_ctas positive");
     if (passes != 1 && passes != 3) return fail("passes must be 1 (plain TF32) or 3 (3xTF32, fp32-level accuracy)");
     cudaStream_t st = (cudaStream_t)stream;
-    const int combo = a_op * 3 + b_op;
+    if (a_op < 0 || a_op > 3 || b_op < 0 || b_op > 3) return fail("operand orientation out of range");
+    const int combo = a_op * 4 + b_op;
     switch (combo) {
-        case umma::OP_KC * 3 + umma::OP_MC: return launch_gemm<umma::OP_KC, umma::OP_MC>(probs, nprob, max_ctas, passes, st);
-        case umma::OP_KCS * 3 + umma::OP_MC: return launch_gemm<umma::OP_KCS, umma::OP_MC>(probs, nprob, max_ctas, passes, st);
-        case umma::OP_KC * 3 + umma::OP_KC: return launch_gemm<umma::OP_KC, umma::OP_KC>(probs, nprob, max_ctas, passes, st);
-        case umma::OP_MC * 3 + umma::OP_MC: return launch_gemm<umma::OP_MC, umma::OP_MC>(probs, nprob, max_ctas, passes, st);
-        case umma::OP_KCS * 3 + umma::OP_KCS: return launch_gemm<umma::OP_KCS, umma::OP_KCS>(probs, nprob, max_ctas, passes, st);
-        default: return fail("unsupported operand orientation pair (supported: KC/MC, KCS/MC, KC/KC, MC/MC, KCS/KCS)");
+        case umma::OP_KC * 4 + umma::OP_MC: return launch_gemm<umma::OP_KC, umma::OP_MC>(probs, nprob, max_ctas, passes, st);
+        case umma::OP_KCS * 4 + umma::OP_MC: return launch_gemm<umma::OP_KCS, umma::OP_MC>(probs, nprob, max_ctas, passes, st);
+        case umma::OP_KC * 4 + umma::OP_KC: return launch_gemm<umma::OP_KC, umma::OP_KC>(probs, nprob, max_ctas, passes, st);
+        case umma::OP_MC * 4 + umma::OP_MC: return launch_gemm<umma::OP_MC, umma::OP_MC>(probs, nprob, max_ctas, passes, st);
+        case umma::OP_KCS * 4 + umma::OP_KCS: return launch_gemm<umma::OP_KCS, umma::OP_KCS>(probs, nprob, max_ctas, passes, st);
+        case umma::OP_KC * 4 + umma::OP_PK: return launch_gemm<umma::OP_KC, umma::OP_PK>(probs, nprob, max_ctas, passes, st);
+        case umma::OP_KCS * 4 + umma::OP_PK: return launch_gemm<umma::OP_KCS, umma::OP_PK>(probs, nprob, max_ctas, passes, st);
+        default: return fail("unsupported operand orientation pair (supported: KC/MC, KCS/MC, KC/KC, MC/MC, KCS/KCS, KC/PK, KCS/PK)");
     }
+}
+
+int fjsp_a2c_gemm_pack(const FjspPackJob* jobs, int njobs, void* stream) {
+    if (!jobs) return fail("jobs is NULL");
+    if (njobs < 1 || njobs > 65535) return fail("njobs must be in 1..65535");
+    static_assert(sizeof(FjspPackJob) == sizeof(umma::PackJob), "FjspPackJob mirrors umma::PackJob");
+    umma::fjsp_gemm_pack_kernel<<<dim3(16, (unsigned)njobs), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const umma::PackJob*>(jobs));
+    CK(cudaGetLastError());
+    return 0;
 }
 
 }  // extern "C"

@@ -107,7 +107,11 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32(int m, int n) {
 //   OP_KC  : k contiguous        X(r, k) = X[r * ld + k]        16-byte loads (ld % 4 == 0, pointer 16-byte aligned, K % 4 == 0)
 //   OP_KCS : the same, scalar loads (any alignment, any K)
 //   OP_MC  : r contiguous        X(r, k) = X[k * ld + r]
-enum { OP_KC = 0, OP_KCS = 1, OP_MC = 2 };
+//   OP_PK  : (B only) a PACKED IMAGE made by fjsp_gemm_pack_kernel from a weight matrix: per 16-wide K chunk the bytes the
+//            tensor core reads from shared memory — four K-quad planes of the hi terms, then four of the lo terms, a plane
+//            = npad rows x 16 bytes (npad = N rounded up to 16) — so a stage's B tile is a straight copy, no conversion.
+//            Weights are constant over a whole rollout + update; activations (A) are split on the fly as before.
+enum { OP_KC = 0, OP_KCS = 1, OP_MC = 2, OP_PK = 3 };
 enum { GEMM_RELU = 1, GEMM_ATOMIC = 2 };
 
 struct GemmProb {          // 128 bytes; device array, one per problem
@@ -174,11 +178,20 @@ __device__ __forceinline__ void split_store(unsigned char* hi, unsigned char* lo
 // One operand tile of ROWS rows x G_KC k, fetched into registers (`fetch`) and later split + stored (`stash`).
 template <int OP, int ROWS, bool ROUND_LO>
 struct Loader {
-    static constexpr int ITEMS = OP == OP_MC ? (ROWS == 128 ? G_NQ / 2 : G_NQ) : ROWS * G_NQ / G_PRODUCERS;
+    static constexpr int ITEMS = OP == OP_PK ? 2 * G_NQ * ROWS / G_PRODUCERS : OP == OP_MC ? (ROWS == 128 ? G_NQ / 2 : G_NQ) : ROWS * G_NQ / G_PRODUCERS;
     float4 v[ITEMS];
+    // OP_PK: `ld` = npad (rows of a plane), `rmax` = number of 16-byte pieces of a chunk to move (8 * npad, or 4 * npad when
+    // only the hi terms are used)
     __device__ __forceinline__ void fetch(const float* __restrict__ X, int ld, int r0, int rmax, int k0, int kmax, int tid) {
         const bool kfull = k0 + G_KC <= kmax;  // uniform: interior stages need no per-element K guards
-        if (OP == OP_MC) {
+        if (OP == OP_PK) {
+            const float4* src = reinterpret_cast<const float4*>(X) + (int64_t)(k0 / G_KC) * (2 * G_NQ * ld);
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                const int idx = tid + i * G_PRODUCERS;
+                if (idx < rmax) v[i] = __ldg(src + idx);
+            }
+        } else if (OP == OP_MC) {
             // thread -> one row r (contiguous across the warp), a few K-quads; 4 coalesced scalar loads per quad
             const int r = ROWS == 128 ? (tid & 127) : tid;
             const int qb = ROWS == 128 ? (tid >> 7) : 0, qs = ROWS == 128 ? 2 : 1;
@@ -224,7 +237,13 @@ struct Loader {
         }
     }
     __device__ __forceinline__ void stash(unsigned char* hi, unsigned char* lo, int lbo, int tid, bool three) const {
-        if (OP == OP_MC) {
+        if (OP == OP_PK) {   // `lbo` = number of 16-byte pieces to move; hi planes then lo planes are contiguous from `hi`
+#pragma unroll
+            for (int i = 0; i < ITEMS; i++) {
+                const int idx = tid + i * G_PRODUCERS;
+                if (idx < lbo) reinterpret_cast<float4*>(hi)[idx] = v[i];
+            }
+        } else if (OP == OP_MC) {
             const int r = ROWS == 128 ? (tid & 127) : tid;
             const int qb = ROWS == 128 ? (tid >> 7) : 0, qs = ROWS == 128 ? 2 : 1;
 #pragma unroll
@@ -316,37 +335,42 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
         constexpr bool ROUND_LO = true;
         Loader<AOP, G_BM, ROUND_LO> la;
         Loader<BOP, G_BN, ROUND_LO> lb;
+        const int pk_pieces = (three ? 2 : 1) * G_NQ * npad;   // OP_PK: 16-byte pieces of a chunk of the packed image
         la.fetch(P.A, P.lda, m0, P.M, c_begin * G_KC, P.K, tid);
-        lb.fetch(P.B, P.ldb, 0, P.N, c_begin * G_KC, P.K, tid);
+        if (BOP == OP_PK) lb.fetch(P.B, npad, 0, pk_pieces, c_begin * G_KC, P.K, tid);
+        else lb.fetch(P.B, P.ldb, 0, P.N, c_begin * G_KC, P.K, tid);
         for (int c = 0; c < nchunks; c++) {
             const int s = c % G_STAGES;
             if (c >= G_STAGES) mbar_wait_or_trap(&s_empty[s], ((c / G_STAGES) - 1) & 1);
             unsigned char* st = g_smem + s * G_STAGE_BYTES;
             la.stash(st, st + G_A_BYTES, G_LBO_A, tid, three);
-            lb.stash(st + 2 * G_A_BYTES, st + 2 * G_A_BYTES + G_B_BYTES, G_LBO_B, tid, three);
+            if (BOP == OP_PK) lb.stash(st + 2 * G_A_BYTES, nullptr, pk_pieces, tid, three);
+            else lb.stash(st + 2 * G_A_BYTES, st + 2 * G_A_BYTES + G_B_BYTES, G_LBO_B, tid, three);
             fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_full[s]);
             if (c + 1 < nchunks) {
                 la.fetch(P.A, P.lda, m0, P.M, (c_begin + c + 1) * G_KC, P.K, tid);
-                lb.fetch(P.B, P.ldb, 0, P.N, (c_begin + c + 1) * G_KC, P.K, tid);
+                if (BOP == OP_PK) lb.fetch(P.B, npad, 0, pk_pieces, (c_begin + c + 1) * G_KC, P.K, tid);
+                else lb.fetch(P.B, P.ldb, 0, P.N, (c_begin + c + 1) * G_KC, P.K, tid);
             }
         }
     } else if (lane == 0) {
         // ===== MMA issuer: one thread =====
         const uint32_t idesc = instr_desc_tf32(G_BM, npad);
         const uint32_t sbase = smem_u32(g_smem);
+        const uint32_t lbo_b = BOP == OP_PK ? (uint32_t)npad * 16u : (uint32_t)G_LBO_B;   // bytes between the K-quad planes of B
         for (int c = 0; c < nchunks; c++) {
             const int s = c % G_STAGES;
             mbar_wait_or_trap(&s_full[s], (c / G_STAGES) & 1);
             fence_after_sync();
             const uint32_t a_hi = sbase + s * G_STAGE_BYTES, a_lo = a_hi + G_A_BYTES;
-            const uint32_t b_hi = a_hi + 2 * G_A_BYTES, b_lo = b_hi + G_B_BYTES;
+            const uint32_t b_hi = a_hi + 2 * G_A_BYTES, b_lo = b_hi + G_NQ * lbo_b;
 #pragma unroll
             for (int ks = 0; ks < G_KC / 8; ks++) {
-                const uint64_t ah = smem_desc(a_hi + 2 * ks * G_LBO_A, G_LBO_A, 128), bh = smem_desc(b_hi + 2 * ks * G_LBO_B, G_LBO_B, 128);
+                const uint64_t ah = smem_desc(a_hi + 2 * ks * G_LBO_A, G_LBO_A, 128), bh = smem_desc(b_hi + 2 * ks * lbo_b, lbo_b, 128);
                 if (three) {  // small terms first
-                    const uint64_t al = smem_desc(a_lo + 2 * ks * G_LBO_A, G_LBO_A, 128), bl = smem_desc(b_lo + 2 * ks * G_LBO_B, G_LBO_B, 128);
+                    const uint64_t al = smem_desc(a_lo + 2 * ks * G_LBO_A, G_LBO_A, 128), bl = smem_desc(b_lo + 2 * ks * lbo_b, lbo_b, 128);
                     mma_tf32(tmem, al, bh, idesc, (c | ks) != 0);
                     mma_tf32(tmem, ah, bl, idesc, 1u);
                     mma_tf32(tmem, ah, bh, idesc, 1u);
@@ -453,6 +477,40 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
         tmem_dealloc(tmem, ncols);
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Packed B images (OP_PK): one job per weight matrix and orientation.  image[chunk][hi | lo][quad][npad rows][4 k] floats,
+// zero beyond N and K; the (hi, lo) split is the one the loaders apply on the fly (tf32_hi of x and of x - hi).
+// ---------------------------------------------------------------------------------------------------------------
+struct PackJob {           // 32 bytes; device array
+    const float* src;
+    float* dst;
+    int32_t op;            // orientation of src: OP_KC / OP_KCS: B(n, k) = src[n * ld + k]; OP_MC: src[k * ld + n]
+    int32_t ld, N, K;
+};
+static_assert(sizeof(PackJob) == 32, "PackJob layout is part of the ABI (include/fjsp_b200.h FjspPackJob)");
+
+__global__ void fjsp_gemm_pack_kernel(const PackJob* __restrict__ jobs) {
+    const PackJob J = jobs[blockIdx.y];
+    const int npad = (J.N + 15) & ~15, chunks = (J.K + G_KC - 1) / G_KC;
+    const int total = chunks * G_NQ * npad;   // one thread per (chunk, quad, row): 4 k values -> one hi and one lo piece
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int n = i % npad, q = (i / npad) % G_NQ, c = i / (npad * G_NQ);
+        float x[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int k = c * G_KC + 4 * q + j;
+            x[j] = (n < J.N && k < J.K) ? __ldg(J.src + (J.op == OP_MC ? (int64_t)k * J.ld + n : (int64_t)n * J.ld + k)) : 0.f;
+        }
+        const uint4 h = make_uint4(tf32_hi(x[0]), tf32_hi(x[1]), tf32_hi(x[2]), tf32_hi(x[3]));
+        const uint4 l = make_uint4(tf32_hi(x[0] - __uint_as_float(h.x)), tf32_hi(x[1] - __uint_as_float(h.y)),
+                                   tf32_hi(x[2] - __uint_as_float(h.z)), tf32_hi(x[3] - __uint_as_float(h.w)));
+        uint4* chunk = reinterpret_cast<uint4*>(J.dst) + (int64_t)c * (2 * G_NQ * npad);
+        chunk[q * npad + n] = h;
+        chunk[(G_NQ + q) * npad + n] = l;
+    }
+}
+
 
 }  // namespace umma
 }  // namespace fjsp

@@ -13,7 +13,7 @@ import torch
 
 from . import abi
 
-OP_KC, OP_KCS, OP_MC = abi.OP_KC, abi.OP_KCS, abi.OP_MC
+OP_KC, OP_KCS, OP_MC, OP_PK = abi.OP_KC, abi.OP_KCS, abi.OP_MC, abi.OP_PK
 RELU, ATOMIC = abi.GEMM_RELU, abi.GEMM_ATOMIC
 BM = 128
 
@@ -47,6 +47,8 @@ class GemmTable:
             assert lda % 4 == 0 and K % 4 == 0 and _addr(A, a_off) % 16 == 0, "OP_KC needs 16-byte aligned rows"
         if self.b_op == OP_KC:
             assert ldb % 4 == 0 and K % 4 == 0 and _addr(B, b_off) % 16 == 0, "OP_KC needs 16-byte aligned rows"
+        if self.b_op == OP_PK:   # B = a packed image (PackTable): ldb is not used
+            assert _addr(B, b_off) % 16 == 0 and B.numel() - b_off >= abi.pack_image_floats(N, K), "packed image too small / unaligned"
         r = np.zeros((), dtype=abi.GEMM_PROB_DT)
         r["A"], r["B"], r["C"] = _addr(A, a_off), _addr(B, b_off), _addr(Cm, c_off)
         r["bias"], r["mask"], r["colsum"] = _addr(bias, bias_off), _addr(mask, mask_off), _addr(colsum, colsum_off)
@@ -71,5 +73,39 @@ class GemmTable:
         st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
         rc = abi.lib().fjsp_a2c_gemm(C.c_void_p(self.dev_table.data_ptr()), len(self.rows), self.max_ctas, self.a_op, self.b_op,
                                      self.passes if passes is None else int(passes), C.c_void_p(st))
+        if rc:
+            abi.check(rc)
+
+
+
+class PackTable:
+    """Weight matrices -> packed B images (``fjsp_a2c_gemm_pack``, include/fjsp_b200.h FJSP_OP_PK), one launch for all of
+    them.  ``add`` returns (image tensor, element offset) to pass as ``B`` / ``b_off`` of a ``GemmTable`` with b_op = OP_PK."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.jobs, self.keep, self.total = [], [], 0
+        self.image = None
+        self.dev_table = None
+
+    def add(self, W, op, ld, N, K, w_off=0):
+        assert W.dtype == torch.float32 and W.device == self.device
+        off = self.total
+        self.total += abi.pack_image_floats(N, K)
+        self.jobs.append((W, int(w_off), int(op), int(ld), int(N), int(K), off))
+        return off
+
+    def finalize(self):
+        self.image = torch.zeros(max(self.total, 4), device=self.device)
+        rows = np.zeros(len(self.jobs), dtype=abi.PACK_JOB_DT)
+        for r, (W, w_off, op, ld, N, K, off) in zip(rows, self.jobs):
+            r["src"], r["dst"], r["op"], r["ld"], r["N"], r["K"] = _addr(W, w_off), _addr(self.image, off), op, ld, N, K
+        self.dev_table = torch.from_numpy(rows.view(np.uint8).reshape(len(self.jobs), -1).copy()).to(self.device)
+        return self
+
+    def launch(self, stream=None):
+        """(Re)build every image from the current values of the weights."""
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        rc = abi.lib().fjsp_a2c_gemm_pack(C.c_void_p(self.dev_table.data_ptr()), len(self.jobs), C.c_void_p(st))
         if rc:
             abi.check(rc)

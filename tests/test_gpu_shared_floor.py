@@ -83,7 +83,7 @@ def test_gpu_replays_shared_vectors(name):
     agvs = int(g["agvs"])
     starts = g["ep_start"].tolist() + [g["actions"].shape[0]]
     E = len(starts) - 1
-    env = BatchedFJSPEnv(E, config=_abi_cfg(ocfg), autoreset=False)
+    env = BatchedFJSPEnv(E, config=_abi_cfg(ocfg), autoreset=False, with_infos=True)
     # one reset per distinct order count (the handle takes one num_orders per call; masked resets for the others)
     for no in sorted(set(int(x) for x in g["ep_norders"])):
         sel = np.array([int(g["ep_norders"][e]) == no for e in range(E)])

@@ -113,3 +113,62 @@ def test_sass_has_tcgen05():
     tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     sass = subprocess.run([tool, "-sass", abi.SO_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass and "LDTM" in sass
+
+
+@pytest.mark.parametrize("M,N,K,src_op", [(4096, 256, 256, "MC"), (1000, 128, 256, "MC"), (130, 3, 256, "MC"), (257, 8, 40, "MC"),
+                                            (1500, 256, 256, "KC"), (900, 256, 3, "KC"), (513, 128, 1, "KC"), (4096, 256, 38, "MC")])
+@pytest.mark.parametrize("passes", [3, 1])
+def test_packed_weight_images_give_the_same_bits(M, N, K, src_op, passes):
+    """FJSP_OP_PK: B read from the packed (hi, lo) image of fjsp_a2c_gemm_pack == B converted on the fly, bit for bit
+    (same split, same MMA order), for weights stored [K][N] (forward) and [N][K] (dx = dy W^T), ragged N and K."""
+    from multi_agent_rl_for_fjsp_b200 import umma
+
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(M + 3 * N + K)
+    w = torch.randn(K, N, device=dev, generator=g) if src_op == "MC" else torch.randn(N, K, device=dev, generator=g)
+    b = torch.randn(N, device=dev, generator=g)
+    if K % 4 == 0:      # 16-byte loads of A
+        x, lda, a_off, a_op = torch.randn(M, K, device=dev, generator=g), K, 0, umma.OP_KC
+    else:               # unaligned rows: scalar loads of A
+        x, lda, a_off, a_op = torch.randn(M, K + 2, device=dev, generator=g), K + 2, 1, umma.OP_KCS
+    y0 = torch.full((M, N), float("nan"), device=dev)
+    y1 = torch.full((M, N), float("nan"), device=dev)
+    b_plain = umma.OP_MC if src_op == "MC" else a_op   # the unpacked orientation pairs the library has: (.,MC), (KC,KC), (KCS,KCS)
+    umma.GemmTable(dev, a_op, b_plain, passes).add(x, w, y0, M, N, K, lda=lda, ldb=(N if src_op == "MC" else K), csm=N, a_off=a_off,
+                                                   bias=b, relu=True).launch()
+    pk = umma.PackTable(dev)
+    off = pk.add(w, umma.OP_MC if src_op == "MC" else umma.OP_KCS, N if src_op == "MC" else K, N, K)
+    pk.finalize().launch()
+    umma.GemmTable(dev, a_op, umma.OP_PK, passes).add(x, pk.image, y1, M, N, K, lda=lda, ldb=0, csm=N, a_off=a_off, b_off=off, bias=b,
+                                                      relu=True).launch()
+    assert torch.equal(y0, y1)
+    xv = x[:, a_off:a_off + K].double()
+    ref64 = torch.relu(xv @ (w.double() if src_op == "MC" else w.double().t()) + b.double())
+    scale = (xv.abs() @ (w.double().abs() if src_op == "MC" else w.double().abs().t())).max().item() + 1.0
+    _close(y1, ref64, scale, 1e-5 if passes == 3 else 3e-3)
+
+
+def test_packed_images_follow_the_weights():
+    """Re-packing after the weights changed (an optimizer step) is one launch over the job table."""
+    from multi_agent_rl_for_fjsp_b200 import umma
+
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(1)
+    ws = [torch.randn(256, 256, device=dev, generator=g), torch.randn(256, 8, device=dev, generator=g)]
+    x = torch.randn(640, 256, device=dev, generator=g)
+    pk = umma.PackTable(dev)
+    offs = [pk.add(ws[0], umma.OP_MC, 256, 256, 256), pk.add(ws[1], umma.OP_MC, 8, 8, 256)]
+    pk.finalize().launch()
+    ys = [torch.zeros(640, 256, device=dev), torch.zeros(640, 8, device=dev)]
+    t = umma.GemmTable(dev, umma.OP_KC, umma.OP_PK)
+    t.add(x, pk.image, ys[0], 640, 256, 256, lda=256, ldb=0, csm=256, b_off=offs[0])
+    t.add(x, pk.image, ys[1], 640, 8, 256, lda=256, ldb=0, csm=8, b_off=offs[1])
+    t.launch()
+    for w, y in zip(ws, ys):
+        _close(y, x.double() @ w.double(), (x.double().abs() @ w.double().abs()).max().item(), 1e-5)
+    for w in ws:
+        w.mul_(-0.5)
+    pk.launch()
+    t.launch()
+    for w, y in zip(ws, ys):
+        _close(y, x.double() @ w.double(), (x.double().abs() @ w.double().abs()).max().item(), 1e-5)

@@ -43,7 +43,20 @@ for i in range(L):
     fwd.add(x, w, y, B, 256, 256, 256, 256, 256, a_off=o, b_off=i * 65536, c_off=o, bias=b, bias_off=i * 256, relu=True)
     dx.add(x, w, y, B, 256, 256, 256, 256, 256, a_off=o, b_off=i * 65536, c_off=o, mask=x, mask_off=o, colsum=cs, colsum_off=i * 256)
     dwt.add(x, y, dw, 256, 256, B, 256, 256, 256, a_off=o, b_off=o, c_off=i * 65536, atomic=True, splitk=sk)
-for name, t in (("forward_bias_relu", fwd), ("dx_mask_colsum", dx), ("dw_splitk%d_atomic" % sk, dwt)):
+# the same two with the weights as packed (hi, lo) images (FJSP_OP_PK): what the trainer runs
+pk = umma.PackTable(dev)
+offs_f = [pk.add(w, umma.OP_MC, 256, 256, 256, i * 65536) for i in range(L)]
+offs_b = [pk.add(w, umma.OP_KCS, 256, 256, 256, i * 65536) for i in range(L)]
+pk.finalize().launch()
+out["pack_18_weights_ms"] = timed(pk.launch)
+fwdp = umma.GemmTable(dev, umma.OP_KC, umma.OP_PK)
+dxp = umma.GemmTable(dev, umma.OP_KC, umma.OP_PK)
+for i in range(L):
+    o = i * B * 256
+    fwdp.add(x, pk.image, y, B, 256, 256, 256, 0, 256, a_off=o, b_off=offs_f[i], c_off=o, bias=b, bias_off=i * 256, relu=True)
+    dxp.add(x, pk.image, y, B, 256, 256, 256, 0, 256, a_off=o, b_off=offs_b[i], c_off=o, mask=x, mask_off=o, colsum=cs, colsum_off=i * 256)
+for name, t in (("forward_bias_relu", fwd), ("forward_bias_relu_packed_w", fwdp), ("dx_mask_colsum", dx), ("dx_mask_colsum_packed_w", dxp),
+                ("dw_splitk%d_atomic" % sk, dwt)):
     for p in (3, 1):
         ms = timed(lambda: t.launch(passes=p))
         out["%s_passes%d" % (name, p)] = {"ms": ms, "tflops_fp32_equiv": out["flop_per_launch"] / ms / 1e9,

@@ -19,89 +19,78 @@ __device__ __forceinline__ void agent_segment(int agent, int& off, int& n) {
     n = agent == 1 ? 8 : 3;
 }
 
+// One thread per (row, agent): 8 consecutive lanes share a row.  (One thread per row kept 4096 rows on 32 SMs with eight
+// softmaxes and two Philox calls in one dependent chain: 11 us per rollout step; the same arithmetic per agent, so the
+// same actions bit for bit.)
 __global__ void __launch_bounds__(128) fjsp_policy_sample_kernel(const float* __restrict__ logits, const int8_t* __restrict__ masks,
                                                                  uint8_t* __restrict__ actions, float* __restrict__ logp,
                                                                  int64_t rows, int64_t first_row, uint64_t seed,
                                                                  const unsigned long long* __restrict__ ctr, uint64_t t_off) {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t row = gid >> 3;
+    const int ag = (int)(gid & 7);
     if (row >= rows) return;
-    float z[32];
-    u32 mw[8];
-    const float4* z4 = reinterpret_cast<const float4*>(logits + row * 32);
+    int off, n;
+    agent_segment(ag, off, n);
+    float z[8];
+    u32 mbit[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        float4 v = __ldg(z4 + i);
-        z[4 * i] = v.x, z[4 * i + 1] = v.y, z[4 * i + 2] = v.z, z[4 * i + 3] = v.w;
+    for (int j = 0; j < 8; j++) {
+        z[j] = j < n ? __ldg(logits + row * 32 + off + j) : 0.f;
+        mbit[j] = j < n ? (u32)(__ldg(masks + row * 32 + off + j) & 1) : 0u;
     }
-    const uint4* m4 = reinterpret_cast<const uint4*>(masks + row * 32);
-    uint4 ma = __ldg(m4), mb = __ldg(m4 + 1);
-    mw[0] = ma.x, mw[1] = ma.y, mw[2] = ma.z, mw[3] = ma.w, mw[4] = mb.x, mw[5] = mb.y, mw[6] = mb.z, mw[7] = mb.w;
     const uint64_t t = (ctr ? (uint64_t)ctr[0] : 0ull) + t_off;
     const uint64_t grow = (uint64_t)(first_row + row);
-    u32 r0[4], r1[4];
-    philox4x32_10((u32)grow, (u32)t, (u32)(t >> 32), 2u, (u32)seed, (u32)(seed >> 32), r0);
-    philox4x32_10((u32)grow, (u32)t, (u32)(t >> 32), 3u, (u32)seed, (u32)(seed >> 32), r1);
-    u32 abytes[2] = {0u, 0u};
-    float lp[8];
+    u32 r[4];
+    philox4x32_10((u32)grow, (u32)t, (u32)(t >> 32), ag < 4 ? 2u : 3u, (u32)seed, (u32)(seed >> 32), r);
+    float zmax = -INFINITY;
 #pragma unroll
-    for (int ag = 0; ag < 8; ag++) {
-        int off, n;
-        agent_segment(ag, off, n);
-        float zmax = -INFINITY;
+    for (int j = 0; j < 8; j++)
+        if (j < n) zmax = fmaxf(zmax, z[j]);
+    float p[8], psum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; j++)
-            if (j < n) zmax = fmaxf(zmax, z[off + j]);
-        float p[8], psum = 0.f;
+    for (int j = 0; j < 8; j++)
+        if (j < n) p[j] = expf(z[j] - zmax), psum += p[j];
+    float msum = 0.f, cnt = 0.f;
+    float q[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++)
-            if (j < n) p[j] = expf(z[off + j] - zmax), psum += p[j];
-        float msum = 0.f, cnt = 0.f;
-        float q[8];
+    for (int j = 0; j < 8; j++)
+        if (j < n) {
+            const float m = (float)mbit[j];
+            p[j] = p[j] / psum;   // softmax (networks.py:33)
+            q[j] = p[j] * m;      // probs * mask (a2c.py:221)
+            msum += q[j], cnt += m;
+            p[j] = m;             // keep the mask for the fallback
+        }
+    float total = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; j++)
-            if (j < n) {
-                const float m = (float)((mw[(off + j) >> 2] >> (((off + j) & 3) * 8)) & 1u);
-                p[j] = p[j] / psum;   // softmax (networks.py:33)
-                q[j] = p[j] * m;      // probs * mask (a2c.py:221)
-                msum += q[j], cnt += m;
-                p[j] = m;             // keep the mask for the fallback
+    for (int j = 0; j < 8; j++)
+        if (j < n) {
+            q[j] = msum > 0.f ? q[j] / msum : p[j] / fmaxf(cnt, 1.f);  // renormalise / uniform over valid (a2c.py:224-231)
+            total += q[j];
+        }
+    const u32 rbits = r[ag & 3];
+    const float u = (float)(rbits >> 8) * (1.0f / 16777216.0f) * total;
+    int a = 0, last_valid = 0;
+    float cdf = 0.f;
+    bool done = false;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (j < n) {
+            cdf += q[j];
+            if (q[j] > 0.f) {
+                last_valid = j;
+                if (!done && u < cdf) a = j, done = true;
             }
-        float total = 0.f;
+        }
+    if (!done) a = last_valid;  // rounding at the end of the cdf never selects a zero-probability action
+    float qa = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; j++)
-            if (j < n) {
-                q[j] = msum > 0.f ? q[j] / msum : p[j] / fmaxf(cnt, 1.f);  // renormalise / uniform over valid (a2c.py:224-231)
-                total += q[j];
-            }
-        const u32 rbits = ag < 4 ? r0[ag] : r1[ag - 4];
-        const float u = (float)(rbits >> 8) * (1.0f / 16777216.0f) * total;
-        int a = 0, last_valid = 0;
-        float cdf = 0.f;
-        bool done = false;
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-            if (j < n) {
-                cdf += q[j];
-                if (q[j] > 0.f) {
-                    last_valid = j;
-                    if (!done && u < cdf) a = j, done = true;
-                }
-            }
-        if (!done) a = last_valid;  // rounding at the end of the cdf never selects a zero-probability action
-        float qa = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-            if (j < n && j == a) qa = q[j] / total;
-        const float eps = 1.1920929e-07f;  // torch.distributions clamps probs to [eps, 1 - eps]
-        lp[ag] = logf(fminf(fmaxf(qa, eps), 1.0f - eps));
-        abytes[ag >> 2] |= (u32)a << ((ag & 3) * 8);
-    }
-    reinterpret_cast<uint2*>(actions)[row] = make_uint2(abytes[0], abytes[1]);
-    if (logp) {
-        float4* o = reinterpret_cast<float4*>(logp + row * 8);
-        o[0] = make_float4(lp[0], lp[1], lp[2], lp[3]);
-        o[1] = make_float4(lp[4], lp[5], lp[6], lp[7]);
-    }
+    for (int j = 0; j < 8; j++)
+        if (j < n && j == a) qa = q[j] / total;
+    const float eps = 1.1920929e-07f;  // torch.distributions clamps probs to [eps, 1 - eps]
+    actions[row * 8 + ag] = (uint8_t)a;
+    if (logp) logp[row * 8 + ag] = logf(fminf(fmaxf(qa, eps), 1.0f - eps));
 }
 
 __global__ void fjsp_counter_add_kernel(unsigned long long* ctr, unsigned long long inc) { ctr[0] += inc; }

@@ -688,7 +688,7 @@ int fjsp_a2c_sample(const float* logits, const int8_t* masks, uint8_t* actions, 
         (reinterpret_cast<uintptr_t>(actions) & 7) || (logp && (reinterpret_cast<uintptr_t>(logp) & 15)))
         return fail("alignment: logits/masks/logp 16 B, actions 8 B");
     if (rows <= 0) return 0;
-    fjsp_policy_sample_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+    fjsp_policy_sample_kernel<<<(unsigned)((rows * 8 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         logits, masks, actions, logp, rows, first_row, seed, reinterpret_cast<const unsigned long long*>(counter), t_off);
     CK(cudaGetLastError());
     return 0;

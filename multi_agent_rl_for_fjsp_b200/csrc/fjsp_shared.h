@@ -85,8 +85,42 @@ FJSP_HD void shared_observe(S& s, const Params& P, const Hot& h, HotCell& c0, co
     observe_stations(P, c0, obs.at(7 + 13 * A), mw, 3 + 8 * A);
 }
 
-// One step.  h / c0 (stations + agv_0) / ax (agv_1.. words) live with the caller (registers).
-template <int A, class S>
+// The few dynamically indexed words an observation reads — the order being loaded at the pickup station, and per AGV the
+// carried tray's record and its order word — taken BEFORE the tile's shared memory is handed to the bulk store, so that
+// the observation rows can be staged in the same shared memory afterwards (fjsp_shared.cuh).  A word accessor like the
+// tile columns: ld(w) answers from the snapshot (any other index would be a bug: it returns 0).
+template <int A>
+struct ObsSnapshot {
+    static constexpr bool LONG = false;
+    int idx[1 + 2 * A];
+    u32 val[1 + 2 * A];
+    FJSP_HD u32 ld(int w) const {
+        u32 v = 0u;
+#pragma unroll
+        for (int i = 0; i < 1 + 2 * A; i++)
+            if (idx[i] == w) v = val[i];
+        return v;
+    }
+    template <class S>
+    FJSP_HD void take(S& s, const Hot& h, const HotCell& c0, const u32* ax) {
+#pragma unroll
+        for (int i = 0; i < 1 + 2 * A; i++) idx[i] = -1, val[i] = 0u;
+        if (h.cur_order >= 0) idx[0] = W_ORDER + h.cur_order, val[0] = s.ld(idx[0]);
+        const int pb = pool_base<false>(0);
+#pragma unroll
+        for (int j = 0; j < A; j++) {
+            const int carry = j == 0 ? (int)c0.carry : (int)((ax[j - 1] >> 23) & 127u);
+            if (carry != 0) {
+                idx[1 + 2 * j] = pb + carry - 1, val[1 + 2 * j] = s.ld(idx[1 + 2 * j]);
+                idx[2 + 2 * j] = W_ORDER + rec_order(val[1 + 2 * j]), val[2 + 2 * j] = s.ld(idx[2 + 2 * j]);
+            }
+        }
+    }
+};
+
+// One step.  h / c0 (stations + agv_0) / ax (agv_1.. words) live with the caller (registers).  OBSERVE = false: the
+// caller computes the observation and the masks itself afterwards (shared_observe), e.g. from an ObsSnapshot.
+template <int A, bool OBSERVE = true, class S>
 FJSP_HD void shared_step(S& s, const Params& P, Hot& h, HotCell& c0, u32* ax, const int* a, ShOut<A>& out) {
     using L = ShLay<A>;
     constexpr int AG = L::AGENTS;
@@ -104,7 +138,7 @@ FJSP_HD void shared_step(S& s, const Params& P, Hot& h, HotCell& c0, u32* ax, co
         out.reward_units = 0;
         out.flags = (1u << 8) | ((u32)FJSP_FAULT_PAST_END << 16);
         out.info[0] = h.step, out.info[1] = h.completed_orders, out.info[2] = h.total_packaged, out.info[3] = 0;
-        shared_observe<A>(s, P, h, c0, ax, FloatSink{out.obs, P}, out.mask);
+        if (OBSERVE) shared_observe<A>(s, P, h, c0, ax, FloatSink{out.obs, P}, out.mask);
         return;
     }
     act_pickup(s, P, h, a[0], local10[0], res[0]);
@@ -151,7 +185,7 @@ FJSP_HD void shared_step(S& s, const Params& P, Hot& h, HotCell& c0, u32* ax, co
     for (int i = 0; i < L::ACT / 4; i++) out.results[i] = res[4 * i] | (res[4 * i + 1] << 8) | (res[4 * i + 2] << 16) | (res[4 * i + 3] << 24);
     h.step = k + 1;
     out.info[0] = h.step, out.info[1] = h.completed_orders, out.info[2] = h.total_packaged, out.info[3] = 0;
-    shared_observe<A>(s, P, h, c0, ax, FloatSink{out.obs, P}, out.mask);
+    if (OBSERVE) shared_observe<A>(s, P, h, c0, ax, FloatSink{out.obs, P}, out.mask);
 }
 
 // words of agv_1.. of a fresh env

@@ -383,25 +383,31 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
         mma_commit(&s_acc);           // accumulator complete
     }
 
-    if (warp < 4) {
+    if (warp < G_PRODUCERS / 32) {
         // ===== epilogue =====
         // Phase 1, thread = one row of the tile (TMEM lane 32 * warp + lane): accumulator -> registers (tcgen05.ld) -> + bias,
         // ReLU -> shared memory (the pipeline stages are free now), 128 columns at a time, row stride 132 floats so the
         // 16-byte stores of 8 consecutive rows fall into 8 different bank groups.
         // Phase 2, warp = the same 32 rows, lane = 4 consecutive columns: one row per iteration leaves as ONE coalesced
         // 512-byte store (or 128 coalesced atomics); the ReLU mask is read the same way, column sums stay in registers.
-        // A warp only ever touches its own 32 rows of the staging area, so __syncwarp() is all the synchronisation needed.
+        // All eight producer warps take part: warps q and q + 4 may both read TMEM lanes 32q..32q+31 (a warp's lane quarter is
+        // warp % 4), so they share those 32 rows — in phase 1 each converts 64 of the 128 columns, in phase 2 each stores 16 of
+        // the 32 rows — and meet at a 64-thread named barrier between the phases.  (With four warps the epilogue of a
+        // 128 x 256 tile cost as much as ~6 K-chunks of the main loop; in the one-wave launches of a rollout step nothing
+        // overlaps it.)
+        const int q = warp & 3, half = warp >> 2;
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
         mbar_wait_or_trap(&s_acc, 0);
         fence_after_sync();
         const bool atomic = P.flags & GEMM_ATOMIC, relu = P.flags & GEMM_RELU;
         const bool vec = !atomic && P.csn == 1 && (P.csm & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0) &&
                          (!P.mask || (reinterpret_cast<uintptr_t>(P.mask) & 15) == 0);
-        float* stage = reinterpret_cast<float*>(g_smem) + (warp * 32) * G_EPI_LD;
+        float* stage = reinterpret_cast<float*>(g_smem) + (q * 32) * G_EPI_LD;
         for (int h0 = 0; h0 < npad; h0 += 128) {
             const int ncol = min(128, npad - h0);
-            for (int n0 = 0; n0 < ncol; n0 += 16) {
+            for (int n0 = 64 * half; n0 < min(ncol, 64 * half + 64); n0 += 16) {
                 float v[16];
-                tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(h0 + n0), v);
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h0 + n0), v);
                 if (P.bias) {
 #pragma unroll
                     for (int i = 0; i < 16; i++) v[i] += s_bias[h0 + n0 + i];
@@ -414,7 +420,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
 #pragma unroll
                 for (int i = 0; i < 4; i++) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
-            __syncwarp();
+            pair_sync();
             const int n = h0 + 4 * lane;         // this lane's 4 columns
             const bool nany = 4 * lane < ncol && n < P.N;
             float cs[4] = {0.f, 0.f, 0.f, 0.f};
@@ -423,8 +429,8 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
 #pragma unroll
                 for (int i = 0; i < 4; i++) w4[i] = n + i < P.N ? __ldg(P.rowdot_w + n + i) : 0.f;
             }
-            for (int r = 0; r < 32; r++) {
-                const int m = m0 + warp * 32 + r;
+            for (int r = 16 * half; r < 16 * half + 16; r++) {
+                const int m = m0 + q * 32 + r;
                 if (m >= P.M) break;              // uniform over the warp
                 if (P.rowdot_w) {                 // fused head: every lane takes part in the row's reduction
                     float d = 0.f;
@@ -465,7 +471,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
                 for (int i = 0; i < 4; i++)
                     if (n + i < P.N) atomicAdd(&s_colsum[n + i], cs[i]);
             }
-            __syncwarp();   // the staging rows are rewritten by the next column block
+            pair_sync();    // the staging rows are rewritten by the next column block
         }
         fence_before_sync();
     }

@@ -127,3 +127,30 @@ def test_new_entry_points_report_argument_errors():
     # the env is still usable after the refused calls
     env.step(env.random_actions(1))
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("cells,n", [(1, 4096), (1, 70000), (4, 3000)])
+def test_programmatic_dependent_launches_change_nothing(cells, n, monkeypatch):
+    """FJSP_PDL=1 (step / random-action kernels launched as programmatic dependents: the next launch's CTAs become resident
+    while the current step drains and wait in griddepcontrol.wait) == FJSP_PDL=0, bit for bit, over back-to-back launches
+    with nothing between them — the case where a missing wait would read the previous step's unfinished writes."""
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv, abi
+
+    cfg = abi.default_config()
+    cfg.num_cells = cells
+    envs = []
+    for pdl in ("0", "1"):
+        monkeypatch.setenv("FJSP_PDL", pdl)   # read when the handle is created
+        e = BatchedFJSPEnv(n, config=cfg, seed=21, num_orders=28, autoreset=True)
+        e.reset()
+        envs.append(e)
+    a, b = envs
+    outs = []
+    for e in (a, b):
+        acts = [e.random_actions(t, out=torch.empty((n, e.act_dim), dtype=torch.uint8, device=e.device)) for t in range(48)]
+        torch.cuda.synchronize()
+        for t in range(48):       # 48 launches in a row on one stream
+            e.step(acts[t])
+        outs.append((e.obs.clone(), e.rewards.clone(), e.masks.clone(), e.flags.clone(), e.save_state()))
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)

@@ -384,6 +384,18 @@ int fjsp_a2c_loss_grad(const float* logits, const int8_t* masks, const uint8_t* 
                        const float* values, const float* adv_mean, const float* adv_rstd, float entropy_coef, int64_t rows, float* dlogits,
                        float* dvalue, float* sums, void* stream);
 int fjsp_a2c_gemm_pack(const FjspPackJob* jobs_device, int njobs, void* stream);
+/* Weight gradients with a narrow side, G[i*gsi + j*gsj] += sum_b X[b*ldx + i] * Y[b*ldy + j] for i < nx <= 256, j < ny <= 40:
+ * the actors' heads, the first layers (transposed) and the critic's value head (a2c.py:647-731 backward of networks.py:22-61).
+ * fp32 FMAs, X streamed once; as tensor-core GEMMs these cost as much as a 256 x 256 product each.  max_rows = max B of the
+ * jobs, max_ny = max ny.  G must be zeroed (or hold the value to add to) by the caller. */
+typedef struct FjspWgradJob {
+    const float* X;
+    const float* Y;
+    float* G;
+    int32_t B, nx, ny, ldx, ldy, gsi, gsj;
+    int32_t reserved[3];
+} FjspWgradJob;
+int fjsp_a2c_wgrad_small(const FjspWgradJob* jobs_device, int njobs, int max_rows, int max_ny, void* stream);
 int fjsp_a2c_gemm(const FjspGemmProb* probs_device, int nprob, int max_ctas, int a_op, int b_op, int passes, void* stream);
 
 /* action_result bit-fields (results[N][8]); reference dict keys in comments */

@@ -11,7 +11,9 @@ rows:
     (KCS,KCS) x9         dH2 = (dlogits_i W3_i^T) * (H2 > 0)   and the critic head  dH3 = (dvalue w4^T) * (H3 > 0)
     (KC,KC)   x1         critic: dH2 = (dH3 Wc3^T) * (H2 > 0)
     (KC,KC)   x9         dH1 = (dH2 W2^T) * (H1 > 0)
-    (MC,MC)   x28        every weight gradient, split-K over the batch with atomic accumulation
+    (MC,MC)   x10        the 256 x 256 (and the critic's 256 x 128) weight gradients, split-K over the batch, atomic accumulation
+    wgrad_small x18      the narrow ones (heads 256 x 3..8, first layers 3..38 x 256, value head 128 x 1): fp32 FMAs, one pass
+                         over the wide operand (as GEMMs each costs as much as a 256 x 256 product)
     bias gradients       column sums in the epilogues of the dH GEMMs (same pass)
 
 Gradients land in ONE flat fp32 buffer (``p.grad`` are views of it), so data parallelism is a single NCCL all-reduce of
@@ -121,6 +123,7 @@ class UmmaEngine:
         bc = umma.GemmTable(dev, umma.OP_KC, umma.OP_KC, ps)
         b2 = umma.GemmTable(dev, umma.OP_KC, umma.OP_KC, ps)
         dw = umma.GemmTable(dev, umma.OP_MC, umma.OP_MC, ps)
+        ws = umma.WgradTable(dev)
         sk = max(1, min(64, B // 2048))
         for k, d in enumerate(self._nets):
             (w1, o1), _, (w2, o2), _, (w3, o3), _ = (self._par(d, j) for j in range(6))
@@ -130,21 +133,20 @@ class UmmaEngine:
                 na, zo = d["nact"], d["zoff"]
                 b3.add(self.dlogits, w3, self.dh2, B, HID, na, lda=32, ldb=na, csm=HID, a_off=zo, b_off=o3, c_off=go,
                        mask=self.h2, mask_off=ho, colsum=gb2, colsum_off=gb2o)
-                dw.add(self.h2, self.dlogits, gw3, HID, na, B, lda=HID, ldb=32, csm=na, a_off=ho, b_off=zo, c_off=g3, atomic=True, splitk=sk)
+                ws.add(self.h2, self.dlogits, gw3, B, HID, na, ldx=HID, ldy=32, gsi=na, gsj=1, x_off=ho, y_off=zo, g_off=g3)
             else:
                 w4, gw4 = d["p"][6], d["p"][6].grad
                 b3.add(self.dvalue, w4, self.dh3, B, 128, 1, lda=1, ldb=1, csm=128, mask=self.h3, colsum=gb3, colsum_off=gb3o)
                 bc.add(self.dh3, w3, self.dh2, B, HID, 128, lda=128, ldb=128, csm=HID, b_off=o3, c_off=go, mask=self.h2, mask_off=ho,
                        colsum=gb2, colsum_off=gb2o)
                 dw.add(self.h2, self.dh3, gw3, HID, 128, B, lda=HID, ldb=128, csm=128, a_off=ho, c_off=g3, atomic=True, splitk=sk)
-                dw.add(self.h3, self.dvalue, gw4, 128, 1, B, lda=128, ldb=1, csm=1, atomic=True, splitk=sk)
+                ws.add(self.h3, self.dvalue, gw4, B, 128, 1, ldx=128, ldy=1, gsi=1, gsj=1)
             b2.add(self.dh2, w2, self.dh1, B, HID, HID, lda=HID, ldb=HID, csm=HID, a_off=go, b_off=o2, c_off=go, mask=self.h1, mask_off=ho,
                    colsum=gb1, colsum_off=gb1o)
             dw.add(self.h1, self.dh2, gw2, HID, HID, B, lda=HID, ldb=HID, csm=HID, a_off=ho, b_off=go, c_off=g2, atomic=True, splitk=sk)
-            # dW1[i, j] = sum_rows obs[row, lo + i] * dH1[row, j]: computed transposed (M = 256 hidden units)
-            dw.add(self.dh1, self.obs, gw1, HID, d["k1"], B, lda=HID, ldb=38, csm=1, csn=HID, a_off=go, b_off=d["lo"], c_off=g1,
-                   atomic=True, splitk=sk)
-        return [x.finalize() for x in (b3, bc, b2, dw)]
+            # dW1[i, j] = sum_rows obs[row, lo + i] * dH1[row, j]: X = dH1 (wide), Y = the observation slice
+            ws.add(self.dh1, self.obs, gw1, B, HID, d["k1"], ldx=HID, ldy=38, gsi=1, gsj=HID, x_off=go, y_off=d["lo"], g_off=g1)
+        return [x.finalize() for x in (b3, bc, b2, dw, ws)]
 
     def backward(self, adv, returns, entropy_coef):
         """Gradients of the update's losses into ``grad_flat`` (local-batch means; the caller all-reduces and averages).

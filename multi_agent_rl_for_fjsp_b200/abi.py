@@ -86,7 +86,7 @@ EXPORTS = [
     "fjsp_num_cells", "fjsp_step_wire", "fjsp_step_host_wire", "fjsp_wire_decode", "fjsp_wire_row_bytes", "fjsp_set_decode_threads",
     "fjsp_state_total_bytes", "fjsp_state_save", "fjsp_state_load",
     "fjsp_a2c_sample", "fjsp_a2c_counter_add", "fjsp_a2c_gae", "fjsp_cells_pack_actions", "fjsp_cells_unpack_views",
-    "fjsp_a2c_gemm", "fjsp_a2c_loss_grad", "fjsp_export_orders", "fjsp_a2c_gemm_pack",
+    "fjsp_a2c_gemm", "fjsp_a2c_loss_grad", "fjsp_export_orders", "fjsp_a2c_gemm_pack", "fjsp_a2c_wgrad_small",
 ]
 
 
@@ -152,6 +152,7 @@ def lib() -> C.CDLL:
     L.fjsp_a2c_loss_grad.argtypes = [vp] * 8 + [C.c_float, i64, vp, vp, vp, vp]
     L.fjsp_a2c_gemm.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.fjsp_a2c_gemm_pack.argtypes = [vp, C.c_int, vp]
+    L.fjsp_a2c_wgrad_small.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
     L.fjsp_cells_pack_actions.argtypes = [vp, vp, i64, C.c_int, vp]
     L.fjsp_cells_unpack_views.argtypes = [vp] * 8 + [i64, C.c_int, vp]
     L.fjsp_export_state.argtypes = [vp, i64, vp]
@@ -205,6 +206,10 @@ def config_from_dict(d: dict | None) -> FjspConfig:
 
 OP_KC, OP_KCS, OP_MC, OP_PK = 0, 1, 2, 3
 PACK_JOB_DT = np.dtype([("src", "<u8"), ("dst", "<u8"), ("op", "<i4"), ("ld", "<i4"), ("N", "<i4"), ("K", "<i4")])  # FjspPackJob
+
+
+WGRAD_JOB_DT = np.dtype([("X", "<u8"), ("Y", "<u8"), ("G", "<u8"), ("B", "<i4"), ("nx", "<i4"), ("ny", "<i4"), ("ldx", "<i4"),
+                         ("ldy", "<i4"), ("gsi", "<i4"), ("gsj", "<i4"), ("reserved", "<i4", (3,))])  # FjspWgradJob (64 B)
 
 
 def pack_image_floats(n: int, k: int) -> int:

@@ -295,4 +295,59 @@ __global__ void fjsp_cells_unpack_views_kernel(const float* __restrict__ obs, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Weight gradients with a NARROW side: G[i][j] += sum_b X[b][i] * Y[b][j] with nx <= 256 columns of X and ny <= 40 of Y —
+// dW of the actors' heads (256 x 3..8), of the first layers (3..38 x 256, computed transposed) and of the critic's value
+// head (128 x 1).  As tcgen05 GEMMs these cost as much as a 256 x 256 product (the wide operand is loaded, split and
+// staged all the same; the main loop is latency-bound per K chunk) for 1..15 % of its flops: 18 of the 28 problems of the
+// weight-gradient launch, 2/3 of its time.  Here: plain fp32 FMAs, X streamed once from HBM (coalesced: thread = column
+// of X), the narrow rows of Y broadcast from shared memory, one atomic per (i, j) per slab of rows.
+// ---------------------------------------------------------------------------------------------
+struct WgradJob {          // 64 bytes; device array
+    const float* X;        // [B][ldx], columns 0..nx-1
+    const float* Y;        // [B][ldy], columns 0..ny-1
+    float* G;              // G[i * gsi + j * gsj] += ...
+    int32_t B, nx, ny, ldx, ldy, gsi, gsj;
+    int32_t reserved[3];
+};
+static_assert(sizeof(WgradJob) == 64, "WgradJob layout is part of the ABI (include/fjsp_b200.h FjspWgradJob)");
+constexpr int WG_SLAB = 512, WG_SUB = 32;   // rows per CTA, rows per shared-memory tile of Y
+
+template <int NY>
+__global__ void __launch_bounds__(256) fjsp_a2c_wgrad_small_kernel(const WgradJob* __restrict__ jobs) {
+    __shared__ float sy[WG_SUB][NY];
+    const WgradJob J = jobs[blockIdx.y];
+    const int r0 = blockIdx.x * WG_SLAB;
+    if (r0 >= J.B || J.ny > NY) return;
+    const int r1 = min(J.B, r0 + WG_SLAB), i = threadIdx.x;
+    const bool act = i < J.nx;
+    float acc[NY];
+#pragma unroll
+    for (int j = 0; j < NY; j++) acc[j] = 0.f;
+    for (int rb = r0; rb < r1; rb += WG_SUB) {
+        const int nr = min(WG_SUB, r1 - rb);
+        __syncthreads();
+        for (int e = threadIdx.x; e < WG_SUB * NY; e += 256) {
+            const int r = e / NY, j = e % NY;
+            sy[r][j] = (r < nr && j < J.ny) ? __ldg(J.Y + (int64_t)(rb + r) * J.ldy + j) : 0.f;
+        }
+        __syncthreads();
+        if (act) {
+            float x[WG_SUB];
+#pragma unroll
+            for (int r = 0; r < WG_SUB; r++) x[r] = r < nr ? __ldg(J.X + (int64_t)(rb + r) * J.ldx + i) : 0.f;
+#pragma unroll
+            for (int r = 0; r < WG_SUB; r++) {
+#pragma unroll
+                for (int j = 0; j < NY; j++) acc[j] = fmaf(x[r], sy[r][j], acc[j]);
+            }
+        }
+    }
+    if (act) {
+#pragma unroll
+        for (int j = 0; j < NY; j++)
+            if (j < J.ny) atomicAdd(J.G + (int64_t)i * J.gsi + (int64_t)j * J.gsj, acc[j]);
+    }
+}
+
 }  // namespace fjsp

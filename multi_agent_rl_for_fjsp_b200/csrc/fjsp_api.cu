@@ -767,6 +767,20 @@ int fjsp_a2c_gemm(const FjspGemmProb* probs, int nprob, int max_ctas, int a_op, 
     }
 }
 
+int fjsp_a2c_wgrad_small(const FjspWgradJob* jobs, int njobs, int max_rows, int max_ny, void* stream) {
+    if (!jobs) return fail("jobs is NULL");
+    if (njobs < 1 || njobs > 65535 || max_rows < 1) return fail("njobs must be in 1..65535 and max_rows positive");
+    if (max_ny < 1 || max_ny > 40) return fail("max_ny (widest Y of the jobs) must be in 1..40");
+    static_assert(sizeof(FjspWgradJob) == sizeof(WgradJob), "FjspWgradJob mirrors WgradJob");
+    const dim3 grid((unsigned)((max_rows + WG_SLAB - 1) / WG_SLAB), (unsigned)njobs);
+    const WgradJob* j = reinterpret_cast<const WgradJob*>(jobs);
+    if (max_ny <= 8) fjsp_a2c_wgrad_small_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(j);
+    else if (max_ny <= 16) fjsp_a2c_wgrad_small_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(j);
+    else fjsp_a2c_wgrad_small_kernel<40><<<grid, 256, 0, (cudaStream_t)stream>>>(j);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int fjsp_a2c_gemm_pack(const FjspPackJob* jobs, int njobs, void* stream) {
     if (!jobs) return fail("jobs is NULL");
     if (njobs < 1 || njobs > 65535) return fail("njobs must be in 1..65535");

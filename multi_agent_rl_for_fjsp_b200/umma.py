@@ -109,3 +109,43 @@ class PackTable:
         rc = abi.lib().fjsp_a2c_gemm_pack(C.c_void_p(self.dev_table.data_ptr()), len(self.jobs), C.c_void_p(st))
         if rc:
             abi.check(rc)
+
+
+class WgradTable:
+    """Narrow weight gradients (``fjsp_a2c_wgrad_small``): G[i, j] += sum_b X[b, i] * Y[b, j] with nx <= 256, ny <= 40, plain
+    fp32.  Jobs are grouped by the width of Y (<= 8, <= 16, <= 40) into at most three launches."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.jobs, self.keep, self.groups = [], [], None
+
+    def add(self, X, Y, G, B, nx, ny, ldx, ldy, gsi, gsj, x_off=0, y_off=0, g_off=0):
+        assert 1 <= nx <= 256 and 1 <= ny <= 40 and B >= 1
+        for t in (X, Y, G):
+            assert t.dtype == torch.float32 and t.device == self.device
+        r = np.zeros((), dtype=abi.WGRAD_JOB_DT)
+        r["X"], r["Y"], r["G"] = _addr(X, x_off), _addr(Y, y_off), _addr(G, g_off)
+        r["B"], r["nx"], r["ny"], r["ldx"], r["ldy"], r["gsi"], r["gsj"] = B, nx, ny, ldx, ldy, gsi, gsj
+        self.jobs.append(r)
+        self.keep += [X, Y, G]
+        self.groups = None
+        return self
+
+    def finalize(self):
+        self.groups = []
+        for lo, hi in ((1, 8), (9, 16), (17, 40)):
+            rows = [r for r in self.jobs if lo <= int(r["ny"]) <= hi]
+            if rows:
+                host = np.stack(rows)
+                tab = torch.from_numpy(host.view(np.uint8).reshape(len(rows), -1).copy()).to(self.device)
+                self.groups.append((tab, len(rows), max(int(r["B"]) for r in rows), hi))
+        return self
+
+    def launch(self, stream=None):
+        if self.groups is None:
+            self.finalize()
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        for tab, n, max_rows, max_ny in self.groups:
+            rc = abi.lib().fjsp_a2c_wgrad_small(C.c_void_p(tab.data_ptr()), n, max_rows, max_ny, C.c_void_p(st))
+            if rc:
+                abi.check(rc)

@@ -172,3 +172,44 @@ def test_packed_images_follow_the_weights():
     t.launch()
     for w, y in zip(ws, ys):
         _close(y, x.double() @ w.double(), (x.double().abs() @ w.double().abs()).max().item(), 1e-5)
+
+
+@pytest.mark.parametrize("B,nx,ny,transposed", [(5000, 256, 3, False), (1537, 256, 8, False), (4096, 256, 13, True), (3000, 256, 38, True),
+                                                 (2049, 128, 1, False), (700, 256, 7, True), (513, 200, 16, False)])
+def test_narrow_weight_gradients(B, nx, ny, transposed):
+    """fjsp_a2c_wgrad_small: G[i, j] += sum_b X[b, i] * Y[b, j] (slices of wider rows, either storage order of G, accumulation
+    into what G holds) against float64; plain fp32 FMAs: rtol 1e-5 of the absolute-value product."""
+    from multi_agent_rl_for_fjsp_b200 import umma
+
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(B + nx + ny)
+    xw, yw = torch.randn(B, nx + 5, device=dev, generator=g), torch.randn(B, ny + 9, device=dev, generator=g)
+    x_off, y_off = 2, 4
+    G = torch.randn(ny, nx, device=dev, generator=g) if transposed else torch.randn(nx, ny, device=dev, generator=g)
+    G0 = G.clone()
+    t = umma.WgradTable(dev)
+    t.add(xw, yw, G, B, nx, ny, ldx=nx + 5, ldy=ny + 9, gsi=(1 if transposed else ny), gsj=(nx if transposed else 1), x_off=x_off, y_off=y_off)
+    t.launch()
+    X, Y = xw[:, x_off:x_off + nx].double(), yw[:, y_off:y_off + ny].double()
+    ref = X.t() @ Y
+    ref = G0.double() + (ref.t() if transposed else ref)
+    scale = (X.abs().t() @ Y.abs()).max().item()
+    _close(G, ref, scale, 1e-5)
+
+
+def test_narrow_weight_gradients_grouped():
+    """Jobs of different widths in one table (three launches at most), different batch sizes."""
+    from multi_agent_rl_for_fjsp_b200 import umma
+
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(4)
+    shapes = [(3000, 256, 3), (3000, 256, 8), (1000, 128, 1), (3000, 256, 13), (2500, 256, 38), (3000, 256, 7)]
+    xs = [torch.randn(b, nx, device=dev, generator=g) for b, nx, ny in shapes]
+    ys = [torch.randn(b, ny, device=dev, generator=g) for b, nx, ny in shapes]
+    gs = [torch.zeros(nx, ny, device=dev) for b, nx, ny in shapes]
+    t = umma.WgradTable(dev)
+    for (b, nx, ny), x, y, G in zip(shapes, xs, ys, gs):
+        t.add(x, y, G, b, nx, ny, ldx=nx, ldy=ny, gsi=ny, gsj=1)
+    t.launch()
+    for x, y, G in zip(xs, ys, gs):
+        _close(G, x.double().t() @ y.double(), (x.double().abs().t() @ y.double().abs()).max().item(), 1e-5)

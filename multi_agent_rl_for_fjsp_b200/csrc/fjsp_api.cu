@@ -103,6 +103,17 @@ struct DeviceGuard {
     if ((h)->long_streams) { constexpr bool LONG = true; DISPATCH_K((h)->cells, __VA_ARGS__) } \
     else { constexpr bool LONG = false; DISPATCH_K((h)->cells, __VA_ARGS__) }
 
+template <class... Args>
+static void launch_ex(void (*kern)(Args...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = pdl ? 1u : 0u;
+    cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <int K, bool LONG>
 static cudaError_t set_smem_attrs() {
     using G = Geo<K, LONG>;
@@ -124,17 +135,6 @@ static cudaError_t set_smem_attrs() {
 
 // One lockstep step of `tiles` tiles starting at A.tile_begin.  K = 1: one thread per env.  K >= 2: one thread per
 // (env, cell) — unless FJSP_STEP_PER_ENV is set, which keeps the thread-per-env kernel for A/B measurements.
-template <class... Args>
-static void launch_ex(void (*kern)(Args...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = smem, cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at, cfg.numAttrs = pdl ? 1u : 0u;
-    cudaLaunchKernelEx(&cfg, kern, args...);
-}
-
 template <int K, bool WIRE, bool LONG>
 static void launch_step(const FjspHandle* h, const StepArgs& A, unsigned tiles, cudaStream_t st, bool pdl = false) {
     using G = Geo<K, LONG>;
@@ -175,8 +175,15 @@ static int launch_gemm(const void* probs, int nprob, int max_ctas, int passes, c
         CK(cudaFuncSetAttribute(umma::fjsp_gemm_kernel<AOP, BOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, umma::G_SMEM_BYTES));
         attr_dev = dev;
     }
-    umma::fjsp_gemm_kernel<AOP, BOP><<<dim3((unsigned)max_ctas, (unsigned)nprob), umma::G_THREADS, umma::G_SMEM_BYTES, st>>>(
-        static_cast<const umma::GemmProb*>(probs), passes);
+    // programmatic dependent launch: the ~100 GEMM launches of a rollout run back to back, each a single wave
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)max_ctas, (unsigned)nprob), cfg.blockDim = dim3(umma::G_THREADS);
+    cfg.dynamicSmemBytes = umma::G_SMEM_BYTES, cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, umma::fjsp_gemm_kernel<AOP, BOP>, static_cast<const umma::GemmProb*>(probs), passes));
     CK(cudaGetLastError());
     return 0;
 }

@@ -80,6 +80,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+// the same load without the wait: several can be in flight; tmem_ld_wait() then makes all of them readable.  (The empty
+// volatile asm per register after the wait keeps the compiler from moving a use of the loaded values above it.)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_pin(uint32_t* r) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) asm volatile("" : "+r"(r[i]));
+}
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -280,6 +295,9 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
     __shared__ uint32_t s_tmem;
     __shared__ float s_colsum[G_BN], s_bias[G_BN];
 
+    // Launched as a programmatic dependent (fjsp_api.cu launch_gemm): this grid may become resident while its predecessor in
+    // the stream drains; the problem table is immutable, everything else is read after griddepcontrol.wait below.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const GemmProb P = probs[blockIdx.y];
     const int mtiles = (P.M + G_BM - 1) / G_BM;
     const int splitk = P.splitk > 0 ? P.splitk : 1;
@@ -302,6 +320,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
         for (int s = 0; s < G_STAGES; s++) mbar_init(&s_full[s], G_PRODUCERS / 32), mbar_init(&s_empty[s], 1);
         mbar_init(&s_acc, 1);
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // the predecessor's writes (activations, weights) are visible from here
     if (tid == 32 && AOP != OP_MC) {
         // The pipeline reads the A tile 64 bytes per row and stage: 128 row segments 1 KB apart, a DRAM-hostile pattern
         // (ncu, first version: long-scoreboard stalls on these loads dominated, DRAM at 19 % with the tensor pipe at 18 %).
@@ -405,20 +424,37 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
         float* stage = reinterpret_cast<float*>(g_smem) + (q * 32) * G_EPI_LD;
         for (int h0 = 0; h0 < npad; h0 += 128) {
             const int ncol = min(128, npad - h0);
-            for (int n0 = 64 * half; n0 < min(ncol, 64 * half + 64); n0 += 16) {
-                float v[16];
-                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h0 + n0), v);
-                if (P.bias) {
+            // this warp's 64 columns: two TMEM loads in flight per wait (four would need 64 registers: spills)
 #pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] += s_bias[h0 + n0 + i];
+            for (int kk = 0; kk < 4; kk += 2) {
+                uint32_t raw[2][16];
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const int n0 = 64 * half + 16 * (kk + k);
+                    if (n0 < ncol) tmem_ld16_issue(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h0 + n0), raw[k]);
                 }
-                if (relu) {
+                tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f);
+                for (int k = 0; k < 2; k++) {
+                    const int n0 = 64 * half + 16 * (kk + k);
+                    if (n0 < ncol) {
+                        tmem_ld_pin(raw[k]);
+                        float v[16];
+#pragma unroll
+                        for (int i = 0; i < 16; i++) v[i] = __uint_as_float(raw[k][i]);
+                        if (P.bias) {
+#pragma unroll
+                            for (int i = 0; i < 16; i++) v[i] += s_bias[h0 + n0 + i];
+                        }
+                        if (relu) {
+#pragma unroll
+                            for (int i = 0; i < 16; i++) v[i] = fmaxf(v[i], 0.f);
+                        }
+                        float4* dst = reinterpret_cast<float4*>(stage + lane * G_EPI_LD + n0);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    }
                 }
-                float4* dst = reinterpret_cast<float4*>(stage + lane * G_EPI_LD + n0);
-#pragma unroll
-                for (int i = 0; i < 4; i++) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
             pair_sync();
             const int n = h0 + 4 * lane;         // this lane's 4 columns
@@ -429,6 +465,34 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
 #pragma unroll
                 for (int i = 0; i < 4; i++) w4[i] = n + i < P.N ? __ldg(P.rowdot_w + n + i) : 0.f;
             }
+            const int rbeg = 16 * half, rows_here = max(0, min(16, P.M - (m0 + q * 32 + rbeg)));
+            const bool fast = vec && !P.rowdot_w && n + 4 <= P.N;   // (per lane; the loop bounds are uniform)
+            if (!P.rowdot_w && __all_sync(0xffffffffu, fast || !nany)) {
+                // every active lane stores whole 16-byte pieces: two rows per iteration, the gate loads issued before the stores
+                for (int rr = 0; rr < rows_here; rr += 2) {
+                    float4 o[2], k4[2];
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const int r = rbeg + rr + u;
+                        if (nany && rr + u < rows_here) {
+                            o[u] = *reinterpret_cast<const float4*>(stage + r * G_EPI_LD + 4 * lane);
+                            if (P.mask) k4[u] = __ldg(reinterpret_cast<const float4*>(P.mask + (int64_t)(m0 + q * 32 + r) * P.csm + n));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const int r = rbeg + rr + u;
+                        if (nany && rr + u < rows_here) {
+                            if (P.mask) {
+                                o[u].x = k4[u].x > 0.f ? o[u].x : 0.f, o[u].y = k4[u].y > 0.f ? o[u].y : 0.f;
+                                o[u].z = k4[u].z > 0.f ? o[u].z : 0.f, o[u].w = k4[u].w > 0.f ? o[u].w : 0.f;
+                            }
+                            *reinterpret_cast<float4*>(P.C + (int64_t)(m0 + q * 32 + r) * P.csm + n) = o[u];
+                            cs[0] += o[u].x, cs[1] += o[u].y, cs[2] += o[u].z, cs[3] += o[u].w;
+                        }
+                    }
+                }
+            } else
             for (int r = 16 * half; r < 16 * half + 16; r++) {
                 const int m = m0 + q * 32 + r;
                 if (m >= P.M) break;              // uniform over the warp

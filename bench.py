@@ -329,6 +329,14 @@ def run_ours(args):
         env._L.fjsp_wire_decode(_C.byref(env.cfg), _p(hb["wire"]), E, _p(hb["obs"]), _p(hb["masks"]), _p(hb["rewards"]), _p(hb["flags"]),
                                 decode_threads)
     decode_only_s = max_over_ranks((time.perf_counter() - t0) / 5)
+    # the box's ceiling for the decode: streaming stores over the same pinned observation buffer, same thread count
+    _secs = _C.c_double(0.0)
+    _n = hb["obs"].numel() * 4
+    best = None
+    for i in range(4):
+        env._L.fjsp_host_stream_write_probe(_p(hb["obs"]), _n, max(1, decode_threads), _C.byref(_secs))
+        best = _secs.value if best is None else min(best, _secs.value)
+    host_stream_gbs = _n / best / 1e9
     wire_row = 4 * env.dims["wire_words"]
     # the e2e path's own roofline: this box's pinned D2H bandwidth on the wire rows (64 B/env)
     hb = env.host_buffers()
@@ -576,6 +584,7 @@ def run_ours(args):
                                                     "value": world * E * 8 * Ke / e2e_wire_s, "ms_per_step": e2e_wire_s / Ke * 1e3},
                     "decode_threads": decode_threads, "decode_only_ms": decode_only_s * 1e3,
                     "decode_only_host_gbs": E * (wire_row + 220) / decode_only_s / 1e9,
+                    "host_stream_write_gbs": host_stream_gbs,
                     "decode_only_note": "fjsp_wire_decode on the delivered rows, host only, threads spawned per call (the pipelined "
                                         "path uses the handle's persistent workers and overlaps the copies)", "pcie_d2h_gbs_measured": d2h_gbs, "host_cpus_bound": len(numa_cpus),
                     "pcie_bound_frac": (E * wire_row / (d2h_gbs * 1e9)) / (e2e_s / Ke)},

@@ -250,6 +250,10 @@ int fjsp_step_host(FjspHandle* h, const uint8_t* actions, float* obs, int8_t* ma
  * consumes the integers as they are.  Synchronised on return. */
 int fjsp_step_host_wire(FjspHandle* h, const uint8_t* actions, uint32_t* wire, int autoreset, void* stream);
 
+/* Measurement aid (bench.py e2e.host_stream_write_gbs): one pass of streaming stores over a HOST buffer from `threads`
+ * threads — the pattern fjsp_step_host's decode delivers the tensors with, i.e. the box's ceiling for it. */
+int fjsp_host_stream_write_probe(void* host_buf, size_t bytes, int threads, double* seconds);
+
 /* Host threads fjsp_step_host may use for the decode (including the caller's); 0 = every CPU the process may run on
  * (default).  Several handles / ranks on one host should share the cores out.  Call before the first fjsp_step_host. */
 int fjsp_set_decode_threads(FjspHandle* h, int threads);

@@ -87,6 +87,7 @@ EXPORTS = [
     "fjsp_state_total_bytes", "fjsp_state_save", "fjsp_state_load",
     "fjsp_a2c_sample", "fjsp_a2c_counter_add", "fjsp_a2c_gae", "fjsp_cells_pack_actions", "fjsp_cells_unpack_views",
     "fjsp_a2c_gemm", "fjsp_a2c_loss_grad", "fjsp_export_orders", "fjsp_a2c_gemm_pack", "fjsp_a2c_wgrad_small",
+    "fjsp_host_stream_write_probe",
 ]
 
 
@@ -153,6 +154,7 @@ def lib() -> C.CDLL:
     L.fjsp_a2c_gemm.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.fjsp_a2c_gemm_pack.argtypes = [vp, C.c_int, vp]
     L.fjsp_a2c_wgrad_small.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+    L.fjsp_host_stream_write_probe.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
     L.fjsp_cells_pack_actions.argtypes = [vp, vp, i64, C.c_int, vp]
     L.fjsp_cells_unpack_views.argtypes = [vp] * 8 + [i64, C.c_int, vp]
     L.fjsp_export_state.argtypes = [vp, i64, vp]

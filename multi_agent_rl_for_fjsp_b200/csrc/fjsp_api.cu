@@ -582,6 +582,13 @@ int fjsp_step_host_wire(FjspHandle* h, const uint8_t* actions, uint32_t* wire, i
     return step_host_impl(h, actions, wire, nullptr, nullptr, nullptr, nullptr, autoreset, stream);
 }
 
+int fjsp_host_stream_write_probe(void* host_buf, size_t bytes, int threads, double* seconds) {
+    if (!host_buf || !seconds || bytes == 0) return fail("host_buf / seconds is NULL or bytes == 0");
+    if (threads < 1 || threads > 256) return fail("threads must be in 1..256");
+    *seconds = host_stream_write_seconds(host_buf, bytes, threads);
+    return 0;
+}
+
 int fjsp_set_decode_threads(FjspHandle* h, int threads) {
     if (!h) return fail("handle is NULL");
     if (threads < 0 || threads > 64) return fail("threads must be in 0..64 (0 = all CPUs of the process)");

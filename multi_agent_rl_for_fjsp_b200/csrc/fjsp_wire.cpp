@@ -11,6 +11,8 @@
 
 #include "fjsp_wire.h"
 
+#include <chrono>
+
 namespace fjsp {
 
 static const int32_t kRewardLut[32] = FJSP_WIRE_REWARD_LUT;
@@ -286,6 +288,39 @@ void wire_decode(int cells, const Params& P, const u32* wire, int64_t lo, int64_
     }
 #endif
     gen[k](P, wire, lo, hi, obs, masks, rewards, flags);
+}
+
+// The decode's ceiling on a box: streaming (non-temporal) stores of `bytes` from `threads` threads, the pattern the decode
+// writes the tensors with.  Returns seconds for one pass.
+#ifdef FJSP_WIRE_X86
+__attribute__((target("avx2"))) static void stream_fill(unsigned char* p, size_t n) {
+    const __m256i v = _mm256_set1_epi32(0x3f800000);
+    size_t i = 0;
+    for (; i < n && ((reinterpret_cast<uintptr_t>(p + i)) & 31); i++) p[i] = 0;
+    for (; i + 32 <= n; i += 32) _mm256_stream_si256(reinterpret_cast<__m256i*>(p + i), v);
+    for (; i < n; i++) p[i] = 0;
+    _mm_sfence();
+}
+#endif
+double host_stream_write_seconds(void* buf, size_t bytes, int threads) {
+    if (threads < 1) threads = 1;
+    unsigned char* p = static_cast<unsigned char*>(buf);
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++) {
+        const size_t lo = bytes * t / threads, hi = bytes * (t + 1) / threads;
+        th.emplace_back([=] {
+#ifdef FJSP_WIRE_X86
+            if (have_avx2()) {
+                stream_fill(p + lo, hi - lo);
+                return;
+            }
+#endif
+            memset(p + lo, 0, hi - lo);
+        });
+    }
+    for (auto& t : th) t.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 }  // namespace fjsp

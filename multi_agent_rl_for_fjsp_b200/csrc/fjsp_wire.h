@@ -22,6 +22,8 @@ namespace fjsp {
 void wire_decode(int cells, const Params& P, const u32* wire, int64_t lo, int64_t hi, float* obs, int8_t* masks, float* rewards,
                  uint8_t* flags);
 const char* wire_decode_isa();  // "avx2" or "generic"
+// one pass of streaming stores over `bytes` from `threads` threads (the box's ceiling for the decode's writes): seconds
+double host_stream_write_seconds(void* buf, size_t bytes, int threads);
 
 inline int usable_cpus() {
     cpu_set_t set;

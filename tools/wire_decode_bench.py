@@ -19,7 +19,7 @@ def run(n):
     from multi_agent_rl_for_fjsp_b200 import abi
 
     L, cfg = abi.lib(), abi.default_config()
-    rows = np.random.randint(0, 5, size=(n, 64), dtype=np.uint8).view(np.uint32).reshape(n, 16)
+    rows = np.random.randint(0, 5, size=(n, 32), dtype=np.uint8).view(np.uint32).reshape(n, 8)   # 32-byte wire rows (K = 1)
 
     def al(shape, dt):
         nb = int(np.prod(shape)) * np.dtype(dt).itemsize

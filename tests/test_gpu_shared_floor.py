@@ -144,3 +144,69 @@ def test_gpu_shared_entry_points_and_state_round_trip():
         a.step_host(np.zeros((300, a.act_dim), np.uint8))
     with pytest.raises(Exception):
         a.export_state(0, 3)   # AGV index out of range
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("FJSP_SOAK"), reason="long run: set FJSP_SOAK=1 (evidence: profiles/r02_soak_shared_long.jsonl)")
+@pytest.mark.parametrize("mode", ["shared4", "shared2", "long4"])
+def test_gpu_soak_new_layouts_follow_the_restatement(mode):
+    """2^16 envs x 10,000 steps with auto-reset (6.6*10^8 env-steps per mode), 48 sampled envs followed by the restatement
+    at EVERY step: the shared floor (A = 4, 2) and the 4-cell shop on long order streams with Philox arrivals."""
+    import json
+    import os
+
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+    from oracle.fjsp_oracle import philox_actions
+
+    ocfg = default_config()
+    if mode.startswith("shared"):
+        ocfg.shared_agvs = int(mode[-1])
+        cells, num_orders, table_len = 1, 30, 30
+        acts_of = lambda seed, g, t: philox_actions_shared(seed, g, t, ocfg.shared_agvs)  # noqa: E731
+    else:
+        ocfg.num_cells, ocfg.long_streams, ocfg.max_episode_steps, ocfg.arrival_prob_q16, ocfg.arrival_max_orders = 4, 1, 700, 20000, 220
+        cells, num_orders, table_len = 4, 8, 220
+        acts_of = lambda seed, g, t: philox_actions(seed, g, t, 4)  # noqa: E731
+    n, steps, seed, first_env = 1 << 16, 10000, 0xC0FFEE, 123456
+    env = BatchedFJSPEnv(n, config=_abi_cfg(ocfg), first_env=first_env, seed=seed, num_orders=num_orders, autoreset=True, with_infos=True)
+    obs0, masks0 = env.reset()
+    rs = np.random.RandomState(7)
+    sample = sorted(set([0, n - 1] + rs.randint(0, n, size=46).tolist()))
+    idx = torch.as_tensor(sample, device=env.device)
+    oracles, episodes = {}, {}
+
+    def fresh(o, i, ep):
+        orders = philox_orders(seed, first_env + i, ep, table_len)
+        return o.reset_stream(orders, num_orders, seed, first_env + i, ep) if ocfg.long_streams else o.reset(orders)
+
+    for i in sample:
+        o = OracleEnv(ocfg)
+        oo, om = fresh(o, i, 0)
+        assert np.array_equal(oo, obs0[i].cpu().numpy()) and np.array_equal(om, masks0[i].cpu().numpy())
+        oracles[i], episodes[i] = o, 0
+    A = env.dims["agents"]
+    faults = ends = 0
+    for t in range(steps):
+        acts = env.random_actions(t)
+        obs, rew, term, trunc, masks = env.step(acts)
+        ho, hr, hm, hf, ha = (x[idx].cpu().numpy() for x in (obs, rew, masks, env.flags, acts))
+        for j, i in enumerate(sample):
+            o = oracles[i]
+            assert np.array_equal(ha[j], acts_of(seed, first_env + i, t))
+            oo, om, orw, of = o.step(ha[j])
+            assert tuple(of[:3]) == tuple(hf[j][:3]), (mode, i, t, of, hf[j])
+            assert np.all(np.abs(hr[j][:A] - orw[:A]) <= REL_TOL * np.abs(orw[:A])), (mode, i, t)
+            if of[0] or of[1] or of[2]:
+                ends += 1
+                faults += int(of[2] != 0)
+                episodes[i] += 1
+                oo, om = fresh(o, i, episodes[i])
+            assert np.array_equal(oo, ho[j]) and np.array_equal(om, hm[j]), (mode, i, t)
+    for i in sample[:8]:
+        for c in range(ocfg.shared_agvs if ocfg.shared_agvs >= 2 else cells):
+            assert not canon.diff(oracles[i].export(c), env.export_state(i, c)), (mode, i, c)
+    rec = {"mode": mode, "envs": n, "steps": steps, "env_steps": n * steps, "sampled_envs": len(sample), "sampled_episode_ends": ends,
+           "sampled_faults": faults, "mismatches": 0}
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "r02_soak_shared_long.jsonl"), "a") as f:
+        f.write(json.dumps(rec) + "\n")

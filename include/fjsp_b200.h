@@ -388,6 +388,25 @@ int fjsp_a2c_loss_grad(const float* logits, const int8_t* masks, const uint8_t* 
                        const float* values, const float* adv_mean, const float* adv_rstd, float entropy_coef, int64_t rows, float* dlogits,
                        float* dvalue, float* sums, void* stream);
 int fjsp_a2c_gemm_pack(const FjspPackJob* jobs_device, int njobs, void* stream);
+/* clip_grad_norm_(max_norm) per network, then Adam (a2c.py:668,686-690), over a table of parameter segments (one per
+ * (tensor, network): the six small actors are slices of stacked tensors): three launches instead of torch's ~20.  The
+ * arithmetic of torch.optim.Adam (no amsgrad / weight decay) on the optimizer's own state tensors: m, v, and a float step
+ * counter per parameter tensor (the segment with bump != 0 increments it; every segment of a tensor reads it).
+ * beta1 / beta2 / eps are doubles as in torch (1 - beta is formed in double, then the per-element arithmetic is float).
+ * norms_sq: float[16] device scratch, zero before the first call (the call leaves it zero).  max_elems = largest n. */
+typedef struct FjspOptSeg {
+    float* param;
+    float* grad;
+    float* m;
+    float* v;
+    float* step;
+    int32_t n, net;
+    float lr;
+    int32_t bump;
+    int64_t reserved;
+} FjspOptSeg;
+int fjsp_a2c_clip_adam(const FjspOptSeg* segs_device, int nseg, int max_elems, float* norms_sq, float max_norm, double beta1,
+                       double beta2, double eps, void* stream);
 /* Weight gradients with a narrow side, G[i*gsi + j*gsj] += sum_b X[b*ldx + i] * Y[b*ldy + j] for i < nx <= 256, j < ny <= 40:
  * the actors' heads, the first layers (transposed) and the critic's value head (a2c.py:647-731 backward of networks.py:22-61).
  * fp32 FMAs, X streamed once; as tensor-core GEMMs these cost as much as a 256 x 256 product each.  max_rows = max B of the

@@ -282,11 +282,13 @@ def _ptr(t):
 
 class BatchedA2C:
     def __init__(self, env, rollout_len=32, gamma=0.99, lamb=0.95, lr_actor=3e-4, lr_critic=1e-3, entropy_coef=0.01,
-                 max_grad_norm=0.5, seed=0, global_adv_norm=True, use_cuda_graph=True, fused_ops=True, impl=None, gemm_passes=3):
+                 max_grad_norm=0.5, seed=0, global_adv_norm=True, use_cuda_graph=True, fused_ops=True, impl=None, gemm_passes=3,
+                 fused_optimizer=True):
         """impl: "umma" (CUDA default) — forward and backward of the 9 networks as grouped tcgen05 GEMMs (a2c_umma.py:
         3xTF32 = fp32-level accuracy; gemm_passes=1: plain TF32), the rollout's activations reused by the update, analytic
         loss gradients, no autograd; "torch" — the same algorithm with torch ops and autograd (the fp32 reference the umma
-        path is tested against; the only path off-GPU)."""
+        path is tested against; the only path off-GPU).  fused_optimizer (umma only): per-network clipping + Adam as one
+        C-ABI call on the optimizer's own state tensors (a2c_umma.ClipAdam) instead of torch's ~30 launches."""
         self.env, self.T = env, int(rollout_len)
         self.seed = int(seed)
         self.gamma, self.lamb, self.entropy_coef, self.max_grad_norm = gamma, lamb, entropy_coef, max_grad_norm
@@ -328,11 +330,15 @@ class BatchedA2C:
         if impl not in ("umma", "torch") or (impl == "umma" and not self.fused):
             raise ValueError("impl must be 'umma' (CUDA, fused ops) or 'torch'")
         self.impl = impl
-        self.engine = None
+        self.engine, self.clip_adam = None, None
         if impl == "umma":
             from .a2c_umma import UmmaEngine
 
             self.engine = UmmaEngine(self.net, self.obs, self.masks, self.actions, self.values, N, T, passes=gemm_passes)
+            if fused_optimizer:
+                from .a2c_umma import ClipAdam
+
+                self.clip_adam = ClipAdam(self.net, self.opt, self.max_grad_norm)
         self.frames = 0
         self.stats = {}
         o, m = env.reset()
@@ -437,6 +443,9 @@ class BatchedA2C:
 
     def _update_impl(self):
         self._compute_grads()
+        if self.clip_adam is not None:
+            self.clip_adam.step()
+            return
         self._clip()
         self.opt.step()
 

@@ -174,3 +174,54 @@ class UmmaEngine:
         ent = self.sums[LS_ENT:LS_ENT + 8] * inv_b
         return {"actor_loss": self.sums[LS_ACTOR:LS_ACTOR + 8] * inv_b - entropy_coef * ent,
                 "critic_loss": self.sums[LS_CRITIC] * (inv_b / 8), "entropy": ent}
+
+
+class ClipAdam:
+    """``clip_grad_norm_(max_norm)`` per network followed by ``Adam.step()`` (/root/reference/a2c.py:668,686-690) as ONE
+    C-ABI call (``fjsp_a2c_clip_adam``: three launches) over a device table of parameter segments, on the state tensors of
+    the trainer's own ``torch.optim.Adam`` (``exp_avg``, ``exp_avg_sq``, ``step``) — ``opt.state_dict()``, checkpoints and
+    a later ``opt.step()`` see exactly what torch's step would have left there.  A segment is one (tensor, network)
+    pair: the six small actors are slices of stacked tensors; each network has its own norm."""
+
+    def __init__(self, net, opt, max_norm):
+        import numpy as np
+
+        self.max_norm = float(max_norm)
+        g0 = opt.param_groups[0]
+        self.beta1, self.beta2, self.eps = float(g0["betas"][0]), float(g0["betas"][1]), float(g0["eps"])
+        lr_of = {id(p): float(g["lr"]) for g in opt.param_groups for p in g["params"]}
+        for g in opt.param_groups:
+            assert not g.get("amsgrad") and not g.get("weight_decay") and not g.get("maximize"), "plain Adam only"
+            assert tuple(g["betas"]) == (self.beta1, self.beta2) and g["eps"] == self.eps
+        rows, net_idx, dev = [], 0, None
+        for _, params, lead in net.networks():
+            for p in params:
+                dev = p.device
+                st = opt.state[p]
+                if len(st) == 0:  # what Adam._init_group creates at the first step (capturable: the step lives on the device)
+                    st["step"] = torch.zeros((), dtype=torch.float32, device=p.device)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                assert st["step"].is_cuda and st["step"].dtype == torch.float32 and p.grad is not None and p.is_contiguous()
+                parts = 1 if lead is None else int(lead)
+                n = p.numel() // parts
+                for i in range(parts):
+                    r = np.zeros((), dtype=abi.OPT_SEG_DT)
+                    for key, t in (("param", p.data), ("grad", p.grad), ("m", st["exp_avg"]), ("v", st["exp_avg_sq"])):
+                        r[key] = t.data_ptr() + 4 * i * n
+                    r["step"], r["n"], r["net"], r["lr"], r["bump"] = st["step"].data_ptr(), n, net_idx + i, lr_of[id(p)], int(i == 0)
+                    rows.append(r)
+            net_idx += 1 if lead is None else int(lead)
+        assert net_idx <= 16
+        self.nseg, self.max_elems = len(rows), max(int(r["n"]) for r in rows)
+        self._keep = opt
+        self.table = torch.from_numpy(np.stack(rows).view(np.uint8).reshape(-1).copy()).to(dev)
+        self.norms_sq = torch.zeros(16, device=dev)
+        self._L = abi.lib()
+
+    def step(self):
+        st = C.c_void_p(torch.cuda.current_stream(self.table.device).cuda_stream)
+        rc = self._L.fjsp_a2c_clip_adam(_p(self.table), self.nseg, self.max_elems, _p(self.norms_sq), self.max_norm, self.beta1,
+                                        self.beta2, self.eps, st)
+        if rc:
+            abi.check(rc)

@@ -350,4 +350,75 @@ __global__ void __launch_bounds__(256) fjsp_a2c_wgrad_small_kernel(const WgradJo
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// clip_grad_norm_ per network + Adam (a2c.py:668,686-690: nn.utils.clip_grad_norm_(net.parameters(), 0.5) then
+// optim.Adam.step()), over a table of parameter SEGMENTS — one per (tensor, network): the six small actors are slices of
+// stacked tensors.  torch's fused multi-tensor Adam spends 0.34 ms on these 654,366 parameters in 28 tensors and the
+// clipping another dozen launches; here: one launch for the nine squared norms, one for clip + Adam, one that bumps the
+// step counters and clears the norms.  Same arithmetic as torch.optim.Adam (capturable, no amsgrad / weight decay):
+//   m = lerp(m, g, 1 - b1); v = b2 v + (1 - b2) g^2; p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// on the optimizer's OWN state tensors (exp_avg, exp_avg_sq, step), so checkpoints and a later opt.step() see them.
+// ---------------------------------------------------------------------------------------------
+struct OptSeg {            // 64 bytes; device array
+    float* param;
+    float* grad;
+    float* m;
+    float* v;
+    float* step;           // the parameter tensor's step counter (float, device); bumped by the segment with bump != 0
+    int32_t n, net;        // elements; network index (norm / clip group), < 16
+    float lr;
+    int32_t bump;
+    int64_t reserved;
+};
+static_assert(sizeof(OptSeg) == 64, "OptSeg layout is part of the ABI (include/fjsp_b200.h FjspOptSeg)");
+
+__global__ void __launch_bounds__(256) fjsp_a2c_gradnorm_kernel(const OptSeg* __restrict__ segs, float* __restrict__ norms_sq) {
+    const OptSeg S = segs[blockIdx.y];
+    float acc = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S.n; i += gridDim.x * blockDim.x) {
+        const float g = S.grad[i];
+        acc = fmaf(g, g, acc);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    __shared__ float part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) t += part[w];
+        if (t != 0.f) atomicAdd(norms_sq + S.net, t);
+    }
+}
+
+__global__ void __launch_bounds__(256) fjsp_a2c_clip_adam_kernel(const OptSeg* __restrict__ segs, const float* __restrict__ norms_sq,
+                                                                 float max_norm, double beta1, double beta2, double eps_d) {
+    const OptSeg S = segs[blockIdx.y];
+    const float coef = fminf(max_norm / (sqrtf(norms_sq[S.net]) + 1e-6f), 1.0f);   // clip_grad_norm_: clamped, always applied
+    // the scalars as torch's fused (capturable) Adam forms them: the betas rounded to float first — 1 - 0.999f is 1.3e-5 below
+    // 0.001, and measurably so in exp_avg_sq — then float per-element arithmetic
+    const float b1 = (float)beta1, b2 = (float)beta2, eps = (float)eps_d;
+    const double t = (double)S.step[0] + 1.0;
+    const float bc1 = (float)(1.0 - pow((double)b1, t)), bc2 = (float)(1.0 - pow((double)b2, t));
+    const float step_size = S.lr / bc1, bc2_sqrt = sqrtf(bc2);
+    const float w1 = 1.0f - b1, w2 = 1.0f - b2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S.n; i += gridDim.x * blockDim.x) {
+        const float g = S.grad[i] * coef;
+        S.grad[i] = g;
+        float m = S.m[i], v = S.v[i];
+        m = m + w1 * (g - m);                          // torch.lerp(m, g, 1 - beta1), weight < 0.5
+        v = b2 * v + w2 * g * g;
+        S.m[i] = m, S.v[i] = v;
+        const float denom = sqrtf(v) / bc2_sqrt + eps;
+        S.param[i] -= step_size * m / denom;
+    }
+}
+
+__global__ void fjsp_a2c_opt_finish_kernel(const OptSeg* __restrict__ segs, int nseg, float* __restrict__ norms_sq) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nseg && segs[i].bump) segs[i].step[0] += 1.0f;
+    if (i < 16) norms_sq[i] = 0.f;
+}
+
 }  // namespace fjsp

@@ -3,6 +3,7 @@
 // every entry point that advances the simulation launches a kernel from fjsp_kernels.cuh.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <new>
 #include <string>
@@ -791,6 +792,21 @@ int fjsp_a2c_wgrad_small(const FjspWgradJob* jobs, int njobs, int max_rows, int 
     if (max_ny <= 8) fjsp_a2c_wgrad_small_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(j);
     else if (max_ny <= 16) fjsp_a2c_wgrad_small_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(j);
     else fjsp_a2c_wgrad_small_kernel<40><<<grid, 256, 0, (cudaStream_t)stream>>>(j);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int fjsp_a2c_clip_adam(const FjspOptSeg* segs, int nseg, int max_elems, float* norms_sq, float max_norm, double beta1, double beta2,
+                       double eps, void* stream) {
+    if (!segs || !norms_sq) return fail("segs / norms_sq is NULL");
+    if (nseg < 1 || nseg > 65535 || max_elems < 1) return fail("nseg must be in 1..65535 and max_elems positive");
+    static_assert(sizeof(FjspOptSeg) == sizeof(OptSeg), "FjspOptSeg mirrors OptSeg");
+    const OptSeg* s = reinterpret_cast<const OptSeg*>(segs);
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned bx = (unsigned)std::min(64, (max_elems + 1023) / 1024);
+    fjsp_a2c_gradnorm_kernel<<<dim3(bx, (unsigned)nseg), 256, 0, st>>>(s, norms_sq);
+    fjsp_a2c_clip_adam_kernel<<<dim3(bx, (unsigned)nseg), 256, 0, st>>>(s, norms_sq, max_norm, beta1, beta2, eps);
+    fjsp_a2c_opt_finish_kernel<<<(unsigned)((std::max(nseg, 16) + 127) / 128), 128, 0, st>>>(s, nseg, norms_sq);
     CK(cudaGetLastError());
     return 0;
 }

@@ -278,3 +278,46 @@ def test_umma_training_with_graphs_and_tf32_variant():
         assert torch.isfinite(p1).all() and not torch.equal(p0, p1)
         assert torch.isfinite(tr.stats["critic_loss"]) and tr.frames == 5 * 8 * 512
         assert tr._ugraph is not None, tr.update_graph_error
+
+
+def test_clip_adam_call_equals_torch_clipping_and_adam():
+    """``fjsp_a2c_clip_adam`` (per-network clip_grad_norm_ 0.5 + Adam on the optimizer's own state, a2c.py:668,686-690) against
+    ``clip_grad_norm_`` + ``torch.optim.Adam.step()`` on the same gradients, five steps: some networks clipped, some not, one
+    with an all-zero gradient.  Parameters, both moments, the step counters and the clipped gradients must agree."""
+    from multi_agent_rl_for_fjsp_b200 import BatchedFJSPEnv
+    from multi_agent_rl_for_fjsp_b200.a2c_batched import BatchedA2C
+
+    a, b2 = (BatchedA2C(BatchedFJSPEnv(256, seed=3, num_orders=25, autoreset=True), rollout_len=4, seed=2, use_cuda_graph=False,
+                        impl="umma", fused_optimizer=f) for f in (True, False))
+    assert a.clip_adam is not None and b2.clip_adam is None
+    b2.net.load_state_dict(a.net.state_dict())
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    sizes = [sum(p.numel() for p in params) for _, params, _ in a.net.networks()]
+    for it in range(5):
+        g = torch.randn(a.engine.grad_flat.numel(), device="cuda", generator=gen)
+        # per-network scales: pickup station far above the clip threshold, agv below it, the six mixed, critic above
+        off = 0
+        for sz, sc in zip(sizes, (1.0, 1e-5, 1e-3 * (it + 1), 0.1)):
+            g[off:off + sz] *= sc
+            off += sz
+        a.engine.grad_flat.copy_(g), b2.engine.grad_flat.copy_(g)
+        if it == 2:  # one stacked actor with a zero gradient: the clip coefficient is max_norm / 1e-6, clamped to 1
+            for p in a.net.six:
+                p.grad[3].zero_()
+            for p in b2.net.six:
+                p.grad[3].zero_()
+        a.clip_adam.step()
+        b2._clip(), b2.opt.step()
+        assert torch.allclose(a.engine.grad_flat, b2.engine.grad_flat, rtol=1e-5, atol=1e-12), it
+        for (na, pa), (_, pb) in zip(a.net.named_parameters(), b2.net.named_parameters()):
+            sa, sb = a.opt.state[pa], b2.opt.state[pb]
+            assert float(sa["step"]) == float(sb["step"]) == it + 1, (na, sa["step"], sb["step"])
+            # (m = m + w (g - m) cancels where g ~ -m: absolute tolerances scaled to the tensor)
+            for key in ("exp_avg", "exp_avg_sq"):
+                ref = sb[key]
+                assert torch.allclose(sa[key], ref, rtol=1e-5, atol=1e-6 * ref.abs().max().item()), (na, it, key)
+            assert torch.allclose(pa, pb, rtol=1e-6, atol=2e-8), (na, it, (pa - pb).abs().max().item())
+    assert float(a.clip_adam.norms_sq.abs().max()) == 0.0
+    # the state is the optimizer's own: a torch step after ours continues from it
+    sd = a.opt.state_dict()
+    assert len(sd["state"]) == len(list(a.net.parameters()))

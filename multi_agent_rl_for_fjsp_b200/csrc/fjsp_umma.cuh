@@ -352,13 +352,18 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
         // when gradients flow through three chained GEMMs and are then summed over the batch (critic W2: 2.6e-4 of the
         // largest gradient with cut lo terms, measured against float64)
         constexpr bool ROUND_LO = true;
-        Loader<AOP, G_BM, ROUND_LO> la;
-        Loader<BOP, G_BN, ROUND_LO> lb;
+        // TWO chunks ahead in registers (two loader sets, the loop unrolled by two): with one set the loads of chunk c + 1
+        // were only issued after chunk c had been stored, so every chunk paid a full load latency in series
+        // (ncu: 60 % of the cycles no warp eligible, long scoreboard) — now a chunk's loads have a whole chunk time to land.
+        Loader<AOP, G_BM, ROUND_LO> la0, la1;
+        Loader<BOP, G_BN, ROUND_LO> lb0, lb1;
         const int pk_pieces = (three ? 2 : 1) * G_NQ * npad;   // OP_PK: 16-byte pieces of a chunk of the packed image
-        la.fetch(P.A, P.lda, m0, P.M, c_begin * G_KC, P.K, tid);
-        if (BOP == OP_PK) lb.fetch(P.B, npad, 0, pk_pieces, c_begin * G_KC, P.K, tid);
-        else lb.fetch(P.B, P.ldb, 0, P.N, c_begin * G_KC, P.K, tid);
-        for (int c = 0; c < nchunks; c++) {
+        auto fetch = [&](Loader<AOP, G_BM, ROUND_LO>& la, Loader<BOP, G_BN, ROUND_LO>& lb, int c) {
+            la.fetch(P.A, P.lda, m0, P.M, (c_begin + c) * G_KC, P.K, tid);
+            if (BOP == OP_PK) lb.fetch(P.B, npad, 0, pk_pieces, (c_begin + c) * G_KC, P.K, tid);
+            else lb.fetch(P.B, P.ldb, 0, P.N, (c_begin + c) * G_KC, P.K, tid);
+        };
+        auto stash = [&](const Loader<AOP, G_BM, ROUND_LO>& la, const Loader<BOP, G_BN, ROUND_LO>& lb, int c) {
             const int s = c % G_STAGES;
             if (c >= G_STAGES) mbar_wait_or_trap(&s_empty[s], ((c / G_STAGES) - 1) & 1);
             unsigned char* st = g_smem + s * G_STAGE_BYTES;
@@ -368,10 +373,15 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
             fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_full[s]);
+        };
+        fetch(la0, lb0, 0);
+        if (nchunks > 1) fetch(la1, lb1, 1);
+        for (int c = 0; c < nchunks; c += 2) {
+            stash(la0, lb0, c);
+            if (c + 2 < nchunks) fetch(la0, lb0, c + 2);
             if (c + 1 < nchunks) {
-                la.fetch(P.A, P.lda, m0, P.M, (c_begin + c + 1) * G_KC, P.K, tid);
-                if (BOP == OP_PK) lb.fetch(P.B, npad, 0, pk_pieces, (c_begin + c + 1) * G_KC, P.K, tid);
-                else lb.fetch(P.B, P.ldb, 0, P.N, (c_begin + c + 1) * G_KC, P.K, tid);
+                stash(la1, lb1, c + 1);
+                if (c + 3 < nchunks) fetch(la1, lb1, c + 3);
             }
         }
     } else if (lane == 0) {

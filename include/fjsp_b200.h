@@ -371,7 +371,9 @@ typedef struct FjspGemmProb {
     int32_t csm, csn;      /* C(m, n) = C[m * csm + n * csn] */
     int32_t flags;
     int32_t splitk;
-    int32_t reserved[3];
+    int32_t head_n;          /* 0: rowdot_* is the one-column head; 1..8: a fused head of that many columns, any N <= 256:      */
+    int32_t head_ld;         /*   rowdot_out[m * head_ld + j] = sum_n C(m, n) * rowdot_w[n * head_n + j] + rowdot_bias[j]   */
+    int32_t reserved;        /*   (an actor's 256 -> 3..8 logits layer in the epilogue of its second layer, fp32 FMAs)      */
     const float* rowdot_w;   /* optional fused head, N <= 128: rowdot_out[m] = sum_n C(m, n) * rowdot_w[n] + rowdot_bias[0] */
     float* rowdot_out;
     const float* rowdot_bias;

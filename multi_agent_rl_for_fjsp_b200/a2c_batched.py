@@ -356,12 +356,12 @@ class BatchedA2C:
         if self.engine is not None:
             eng = self.engine
             for t in range(T):
-                eng.forward(t)  # logits -> eng.logits[t], value -> self.values[t]; activations kept for the update
+                eng.forward_actors(t)  # logits -> eng.logits[t]; activations kept for the update
                 rc = self._L.fjsp_a2c_sample(_ptr(eng.logits[t]), _ptr(self.masks[t]), _ptr(self.actions[t]), None, env.num_envs,
                                              env.first_env, self.seed, _ptr(self._ctr), t, self._stream())
                 assert rc == 0, self._L.fjsp_last_error()
                 env.step_into(self.actions[t], self.obs[t + 1], self.masks[t + 1], self.rewards[t], self.flags[t])
-            eng.forward(T)      # bootstrap value of the last observation
+            eng.forward_critic()   # values[0..T] (incl. the bootstrap value) in one batched pass: the policy never reads them
             rc = self._L.fjsp_a2c_counter_add(_ptr(self._ctr), T, self._stream())
             assert rc == 0
             return

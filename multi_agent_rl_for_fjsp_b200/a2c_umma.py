@@ -4,8 +4,9 @@ fp32-level accuracy) plus one analytic loss-gradient kernel (``fjsp_a2c_loss_gra
 
 A2C is on-policy: the update differentiates the very networks that produced the rollout.  The rollout's forward passes
 therefore ARE the update's forward pass: every rollout step stores its hidden activations (post-ReLU) and pre-softmax
-outputs in slice ``t`` of ``[net][T+1][N][256]`` buffers, and the update only runs the backward chain over the ``T*N``
-rows:
+outputs in slice ``t`` of ``[net][T+1][N][256]`` buffers (actors: two launches per step, the logits layer fused into the
+second layer's epilogue; critic: three launches over all ``(T+1)*N`` rows once the rollout is over — the policy does not
+read it), and the update only runs the backward chain over the ``T*N`` rows:
 
     loss_grad            dlogits [B,32], dvalue [B]  (+ last-layer bias gradients, loss statistics)
     (KCS,KCS) x9         dH2 = (dlogits_i W3_i^T) * (H2 > 0)   and the critic head  dH3 = (dvalue w4^T) * (H3 > 0)
@@ -60,7 +61,9 @@ class UmmaEngine:
             off += p.numel()
         self._L = abi.lib()
         self._nets = self._describe()
-        self._fwd = [self._forward_tables(t, critic_only=False) for t in range(T)] + [self._forward_tables(T, critic_only=True)]
+        self._fwd_actors = [self._actor_tables(t) for t in range(T)]
+        self._fwd_critic = self._critic_tables(0, T + 1)
+        self._fwd_critic_step = {}
         self._bwd = self._backward_tables()
 
     # ------------------------------------------------------------------ the nine networks
@@ -87,33 +90,61 @@ class UmmaEngine:
     def _hoff(self, net, t=0):
         return ((net * (self.T + 1) + t) * self.N) * HID
 
-    # ------------------------------------------------------------------ forward (one rollout step)
-    def _forward_tables(self, t, critic_only):
+    # ------------------------------------------------------------------ forward
+    def _actor_tables(self, t):
+        """Rollout step t, the eight actors: layer 1 from the observation slices, layer 2 with the 256 -> 3..8 logits layer as
+        a fused head in its epilogue (fp32 FMAs on the values it stores) — TWO grouped launches.  As a third GEMM launch the
+        heads cost a step as much as the 256 x 256 layer: 16 K chunks of a latency-bound pipeline for 1-3 % of its flops."""
         N, dev, ps = self.N, self.dev, self.passes
-        nets = [(8, self._nets[8])] if critic_only else list(enumerate(self._nets))
         l1 = umma.GemmTable(dev, umma.OP_KCS, umma.OP_MC, ps)
         l2 = umma.GemmTable(dev, umma.OP_KC, umma.OP_MC, ps)
-        l3 = umma.GemmTable(dev, umma.OP_KC, umma.OP_MC, ps)
-        for k, d in nets:
+        for k, d in enumerate(self._nets[:8]):
             (w1, o1), (b1, ob1), (w2, o2), (b2, ob2), (w3, o3), (b3, ob3) = (self._par(d, j) for j in range(6))
             l1.add(self.obs, w1, self.h1, N, HID, d["k1"], lda=38, ldb=HID, csm=HID, a_off=t * N * 38 + d["lo"], b_off=o1,
                    c_off=self._hoff(k, t), bias=b1, bias_off=ob1, relu=True)
             l2.add(self.h1, w2, self.h2, N, HID, HID, lda=HID, ldb=HID, csm=HID, a_off=self._hoff(k, t), b_off=o2,
-                   c_off=self._hoff(k, t), bias=b2, bias_off=ob2, relu=True)
-            if k < 8:   # actor head: straight into its columns of the [N, 32] logits row
-                l3.add(self.h2, w3, self.logits, N, d["nact"], HID, lda=HID, ldb=d["nact"], csm=32, a_off=self._hoff(k, t), b_off=o3,
-                       c_off=t * N * 32 + d["zoff"], bias=b3, bias_off=ob3)
-            else:       # critic: 256 -> 128 (ReLU), and its 128 -> 1 head fused into the same epilogue
-                w4, b4 = d["p"][6], d["p"][7]
-                l3.add(self.h2, w3, self.h3, N, 128, HID, lda=HID, ldb=128, csm=128, a_off=self._hoff(k, t), b_off=o3,
-                       c_off=t * N * 128, bias=b3, bias_off=ob3, relu=True, rowdot_w=w4, rowdot_out=self.values,
-                       rowdot_out_off=t * N, rowdot_bias=b4)
+                   c_off=self._hoff(k, t), bias=b2, bias_off=ob2, relu=True, rowdot_w=w3, rowdot_w_off=o3, rowdot_bias=b3,
+                   rowdot_bias_off=ob3, rowdot_out=self.logits, rowdot_out_off=t * N * 32 + d["zoff"], head_n=d["nact"], head_ld=32)
+        return [x.finalize() for x in (l1, l2)]
+
+    def _critic_tables(self, t0, steps):
+        """The critic over the rows of rollout steps t0 .. t0 + steps - 1 as ONE problem per layer (the buffers are contiguous
+        in t): 38 -> 256 -> 256 -> 128 (ReLU) with the 128 -> 1 head fused into the third layer's epilogue."""
+        N, dev, ps = self.N, self.dev, self.passes
+        M = steps * N
+        d = self._nets[8]
+        (w1, o1), (b1, ob1), (w2, o2), (b2, ob2), (w3, o3), (b3, ob3) = (self._par(d, j) for j in range(6))
+        w4, b4 = d["p"][6], d["p"][7]
+        l1 = umma.GemmTable(dev, umma.OP_KCS, umma.OP_MC, ps)
+        l2 = umma.GemmTable(dev, umma.OP_KC, umma.OP_MC, ps)
+        l3 = umma.GemmTable(dev, umma.OP_KC, umma.OP_MC, ps)
+        l1.add(self.obs, w1, self.h1, M, HID, 38, lda=38, ldb=HID, csm=HID, a_off=t0 * N * 38, b_off=o1, c_off=self._hoff(8, t0),
+               bias=b1, bias_off=ob1, relu=True)
+        l2.add(self.h1, w2, self.h2, M, HID, HID, lda=HID, ldb=HID, csm=HID, a_off=self._hoff(8, t0), b_off=o2, c_off=self._hoff(8, t0),
+               bias=b2, bias_off=ob2, relu=True)
+        l3.add(self.h2, w3, self.h3, M, 128, HID, lda=HID, ldb=128, csm=128, a_off=self._hoff(8, t0), b_off=o3, c_off=t0 * N * 128,
+               bias=b3, bias_off=ob3, relu=True, rowdot_w=w4, rowdot_out=self.values, rowdot_out_off=t0 * N, rowdot_bias=b4)
         return [x.finalize() for x in (l1, l2, l3)]
 
+    def forward_actors(self, t):
+        """Logits of rollout step t into ``self.logits[t]`` (two grouped launches); hidden activations kept for the update."""
+        for tab in self._fwd_actors[t]:
+            tab.launch()
+
+    def forward_critic(self):
+        """Values of ALL T + 1 observations of the rollout (``values[0..T]``, the last one being the bootstrap value) in three
+        launches over (T + 1) N rows.  The policy does not read the critic, so nothing of it has to run inside the rollout's
+        step-by-step chain, where a launch is one wave of latency-bound CTAs; here the same work is 33 times as many rows."""
+        for tab in self._fwd_critic:
+            tab.launch()
+
     def forward(self, t):
-        """Actors' logits (``self.logits[t]``) and the critic value (``values[t]``) of rollout step t; t = T: the bootstrap
-        value only.  Three grouped launches (the critic's 128 -> 1 head rides in the epilogue of its third layer)."""
-        for tab in self._fwd[t]:
+        """Everything of rollout step t in one call (tests, single steps): the actors' logits (t < T) and the critic value."""
+        if t < self.T:
+            self.forward_actors(t)
+        if t not in self._fwd_critic_step:
+            self._fwd_critic_step[t] = self._critic_tables(t, 1)
+        for tab in self._fwd_critic_step[t]:
             tab.launch()
 
     # ------------------------------------------------------------------ backward (one update)

@@ -226,7 +226,7 @@ GEMM_RELU, GEMM_ATOMIC = 1, 2
 GEMM_PROB_DT = np.dtype([
     ("A", "<u8"), ("B", "<u8"), ("C", "<u8"), ("bias", "<u8"), ("mask", "<u8"), ("colsum", "<u8"),
     ("M", "<i4"), ("N", "<i4"), ("K", "<i4"), ("lda", "<i4"), ("ldb", "<i4"), ("csm", "<i4"), ("csn", "<i4"),
-    ("flags", "<i4"), ("splitk", "<i4"), ("reserved", "<i4", (3,)),
+    ("flags", "<i4"), ("splitk", "<i4"), ("head_n", "<i4"), ("head_ld", "<i4"), ("reserved", "<i4"),
     ("rowdot_w", "<u8"), ("rowdot_out", "<u8"), ("rowdot_bias", "<u8"), ("reserved2", "<i8")])
 assert GEMM_PROB_DT.itemsize == 128
 

@@ -141,9 +141,14 @@ struct GemmProb {          // 128 bytes; device array, one per problem
     int32_t csm, csn;      // C(m, n) = C[m * csm + n * csn]
     int32_t flags;         // GEMM_RELU, GEMM_ATOMIC (atomicAdd into C: split-K partial sums)
     int32_t splitk;        // >= 1: the K range is cut into this many parts, one CTA each
-    int32_t reserved[3];
-    // optional fused head (N <= 128): rowdot_out[m] = sum_n stored(m, n) * rowdot_w[n] + rowdot_bias[0] — the critic's
-    // last layer (128 -> 1, networks.py:41-61) in the epilogue of the layer before it
+    int32_t head_n;        // 0: rowdot_* is the one-column head below; 1..8: a fused head of that many columns (see below)
+    int32_t head_ld;       // head_n >= 1: row stride of rowdot_out in floats
+    int32_t reserved;
+    // optional fused head (head_n = 0, N <= 128): rowdot_out[m] = sum_n stored(m, n) * rowdot_w[n] + rowdot_bias[0] — the critic's
+    // last layer (128 -> 1, networks.py:41-61) in the epilogue of the layer before it.
+    // head_n = R in 1..8 (any N <= 256): rowdot_out[m * head_ld + j] = sum_n stored(m, n) * rowdot_w[n * R + j] + rowdot_bias[j],
+    // j < R — an actor's last layer (256 -> 3..8 logits, networks.py:22-38) as fp32 FMAs in the epilogue of its second layer:
+    // as a GEMM launch of its own it costs a rollout step as much as the 256 x 256 layer (16 K chunks, latency-bound)
     const float* rowdot_w;
     float* rowdot_out;
     const float* rowdot_bias;
@@ -162,7 +167,7 @@ constexpr int G_STAGE_BYTES = 2 * (G_A_BYTES + G_B_BYTES);
 constexpr int G_STAGES = 2;
 constexpr int G_SMEM_BYTES = G_STAGES * G_STAGE_BYTES;                   // 99,328: two CTAs per SM
 constexpr int G_EPI_LD = 132;          // floats per row of the epilogue's staging area (128 columns + 4: conflict-free)
-static_assert(G_BM * G_EPI_LD * 4 <= G_SMEM_BYTES, "the epilogue stages 128 x 128 floats in the pipeline's shared memory");
+static_assert(G_BM * G_EPI_LD * 4 + G_BM * 8 * 4 <= G_SMEM_BYTES, "the epilogue stages 128 x 128 floats in the pipeline's shared memory");
 constexpr int G_PRODUCERS = 256;      // warps 0..7 load; warps 0..3 are also the epilogue; warp 8 issues the MMAs
 constexpr int G_THREADS = G_PRODUCERS + 32;
 
@@ -294,6 +299,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
     __shared__ uint64_t s_full[G_STAGES], s_empty[G_STAGES], s_acc;
     __shared__ uint32_t s_tmem;
     __shared__ float s_colsum[G_BN], s_bias[G_BN];
+    __shared__ __align__(16) float s_head_w[G_BN * 8];   // head_n >= 1: the head's weights, [n][8] (columns >= head_n zero)
 
     // Launched as a programmatic dependent (fjsp_api.cu launch_gemm): this grid may become resident while its predecessor in
     // the stream drains; the problem table is immutable, everything else is read after griddepcontrol.wait below.
@@ -340,6 +346,13 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
         }
     }
     if (tid < G_BN) s_colsum[tid] = 0.f, s_bias[tid] = (P.bias && tid < P.N) ? __ldg(P.bias + tid) : 0.f;
+    const int head_n = P.rowdot_w ? P.head_n : 0;
+    if (head_n > 0) {
+        for (int i = tid; i < G_BN * 8; i += G_THREADS) {
+            const int n = i >> 3, j = i & 7;
+            s_head_w[i] = (n < P.N && j < head_n) ? __ldg(P.rowdot_w + n * head_n + j) : 0.f;
+        }
+    }
     if (warp == G_PRODUCERS / 32) tmem_alloc(&s_tmem, ncols);
     fence_before_sync();
     __syncthreads();
@@ -432,6 +445,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
         const bool vec = !atomic && P.csn == 1 && (P.csm & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0) &&
                          (!P.mask || (reinterpret_cast<uintptr_t>(P.mask) & 15) == 0);
         float* stage = reinterpret_cast<float*>(g_smem) + (q * 32) * G_EPI_LD;
+        float hd[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // head_n >= 1: this thread's row, its half of the columns
         for (int h0 = 0; h0 < npad; h0 += 128) {
             const int ncol = min(128, npad - h0);
             // this warp's 64 columns: two TMEM loads in flight per wait (four would need 64 registers: spills)
@@ -463,6 +477,16 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
                         float4* dst = reinterpret_cast<float4*>(stage + lane * G_EPI_LD + n0);
 #pragma unroll
                         for (int i = 0; i < 4; i++) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        if (head_n > 0) {   // warp-uniform weight reads (broadcast), eight FMAs per stored value
+                            const float4* hw = reinterpret_cast<const float4*>(s_head_w) + 2 * (h0 + n0);
+#pragma unroll
+                            for (int i = 0; i < 16; i++) {
+                                const float4 wa = hw[2 * i], wb = hw[2 * i + 1];
+                                hd[0] = fmaf(v[i], wa.x, hd[0]), hd[1] = fmaf(v[i], wa.y, hd[1]), hd[2] = fmaf(v[i], wa.z, hd[2]);
+                                hd[3] = fmaf(v[i], wa.w, hd[3]), hd[4] = fmaf(v[i], wb.x, hd[4]), hd[5] = fmaf(v[i], wb.y, hd[5]);
+                                hd[6] = fmaf(v[i], wb.z, hd[6]), hd[7] = fmaf(v[i], wb.w, hd[7]);
+                            }
+                        }
                     }
                 }
             }
@@ -471,13 +495,14 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
             const bool nany = 4 * lane < ncol && n < P.N;
             float cs[4] = {0.f, 0.f, 0.f, 0.f};
             float w4[4] = {0.f, 0.f, 0.f, 0.f};
-            if (P.rowdot_w && nany) {
+            const bool rowdot1 = P.rowdot_w && head_n == 0;
+            if (rowdot1 && nany) {
 #pragma unroll
                 for (int i = 0; i < 4; i++) w4[i] = n + i < P.N ? __ldg(P.rowdot_w + n + i) : 0.f;
             }
             const int rbeg = 16 * half, rows_here = max(0, min(16, P.M - (m0 + q * 32 + rbeg)));
-            const bool fast = vec && !P.rowdot_w && n + 4 <= P.N;   // (per lane; the loop bounds are uniform)
-            if (!P.rowdot_w && __all_sync(0xffffffffu, fast || !nany)) {
+            const bool fast = vec && !rowdot1 && n + 4 <= P.N;   // (per lane; the loop bounds are uniform)
+            if (!rowdot1 && __all_sync(0xffffffffu, fast || !nany)) {
                 // every active lane stores whole 16-byte pieces: two rows per iteration, the gate loads issued before the stores
                 for (int rr = 0; rr < rows_here; rr += 2) {
                     float4 o[2], k4[2];
@@ -506,7 +531,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
             for (int r = 16 * half; r < 16 * half + 16; r++) {
                 const int m = m0 + q * 32 + r;
                 if (m >= P.M) break;              // uniform over the warp
-                if (P.rowdot_w) {                 // fused head: every lane takes part in the row's reduction
+                if (rowdot1) {                    // fused head: every lane takes part in the row's reduction
                     float d = 0.f;
                     if (nany) {
                         const float4 o = *reinterpret_cast<const float4*>(stage + r * G_EPI_LD + 4 * lane);
@@ -546,6 +571,23 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
                     if (n + i < P.N) atomicAdd(&s_colsum[n + i], cs[i]);
             }
             pair_sync();    // the staging rows are rewritten by the next column block
+        }
+        if (head_n > 0) {   // the pair's two column halves of a row meet behind the staging area; warp q adds the bias and stores
+            float* part = reinterpret_cast<float*>(g_smem) + G_BM * G_EPI_LD + (q * 32 + lane) * 8;
+            if (half == 1) {
+                reinterpret_cast<float4*>(part)[0] = make_float4(hd[0], hd[1], hd[2], hd[3]);
+                reinterpret_cast<float4*>(part)[1] = make_float4(hd[4], hd[5], hd[6], hd[7]);
+            }
+            pair_sync();
+            const int m = m0 + q * 32 + lane;
+            if (half == 0 && m < P.M) {
+                const float4 pa = reinterpret_cast<const float4*>(part)[0], pb = reinterpret_cast<const float4*>(part)[1];
+                const float o[8] = {hd[0] + pa.x, hd[1] + pa.y, hd[2] + pa.z, hd[3] + pa.w, hd[4] + pb.x, hd[5] + pb.y, hd[6] + pb.z, hd[7] + pb.w};
+                float* out = P.rowdot_out + (int64_t)m * P.head_ld;
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (j < head_n) out[j] = o[j] + (P.rowdot_bias ? __ldg(P.rowdot_bias + j) : 0.f);
+            }
         }
         fence_before_sync();
     }

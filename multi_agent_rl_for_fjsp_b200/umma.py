@@ -37,10 +37,13 @@ class GemmTable:
 
     def add(self, A, B, Cm, M, N, K, lda, ldb, csm, csn=1, a_off=0, b_off=0, c_off=0, bias=None, bias_off=0, mask=None,
             mask_off=0, colsum=None, colsum_off=0, relu=False, atomic=False, splitk=1, rowdot_w=None, rowdot_out=None,
-            rowdot_out_off=0, rowdot_bias=None):
-        """rowdot_*: fused one-column head on the stored values: rowdot_out[m] = sum_n C[m, n] * rowdot_w[n] + rowdot_bias[0]."""
+            rowdot_out_off=0, rowdot_bias=None, rowdot_w_off=0, rowdot_bias_off=0, head_n=0, head_ld=0):
+        """rowdot_*: fused one-column head on the stored values: rowdot_out[m] = sum_n C[m, n] * rowdot_w[n] + rowdot_bias[0];
+        with head_n = R in 1..8 a head of R columns (any N): rowdot_out[m * head_ld + j] = sum_n C[m, n] * rowdot_w[n * R + j] +
+        rowdot_bias[j]."""
         assert 1 <= N <= 256 and M >= 1 and K >= 1 and splitk >= 1
-        assert rowdot_w is None or (N <= 128 and rowdot_out is not None and not atomic)
+        assert rowdot_w is None or (rowdot_out is not None and not atomic and (N <= 128 if head_n == 0 else 1 <= head_n <= 8))
+        assert head_n == 0 or (rowdot_w is not None and head_ld >= head_n)
         for t in (A, B, Cm, bias, mask, colsum, rowdot_w, rowdot_out, rowdot_bias):
             assert t is None or (t.dtype == torch.float32 and t.device == self.device), "fp32 tensors on the table's device"
         if self.a_op == OP_KC:
@@ -55,7 +58,8 @@ class GemmTable:
         r["M"], r["N"], r["K"], r["lda"], r["ldb"], r["csm"], r["csn"] = M, N, K, lda, ldb, csm, csn
         r["flags"] = (RELU if relu else 0) | (ATOMIC if atomic else 0)
         r["splitk"] = splitk
-        r["rowdot_w"], r["rowdot_out"], r["rowdot_bias"] = _addr(rowdot_w), _addr(rowdot_out, rowdot_out_off), _addr(rowdot_bias)
+        r["rowdot_w"], r["rowdot_out"], r["rowdot_bias"] = _addr(rowdot_w, rowdot_w_off), _addr(rowdot_out, rowdot_out_off), _addr(rowdot_bias, rowdot_bias_off)
+        r["head_n"], r["head_ld"] = head_n, head_ld
         self.rows.append(r)
         self.keep += [A, B, Cm, bias, mask, colsum, rowdot_w, rowdot_out, rowdot_bias]
         self.max_ctas = max(self.max_ctas, (M + BM - 1) // BM * splitk)

@@ -213,3 +213,37 @@ def test_narrow_weight_gradients_grouped():
     t.launch()
     for x, y, G in zip(xs, ys, gs):
         _close(G, x.double().t() @ y.double(), (x.double().abs().t() @ y.double().abs()).max().item(), 1e-5)
+
+
+@pytest.mark.parametrize("M,N,R", [(4096, 256, 8), (1000, 256, 3), (130, 100, 1), (257, 136, 5)])
+def test_fused_head_of_up_to_eight_columns(M, N, R):
+    """``head_n`` = R: out[m, j] = sum_n relu(x W + b)[m, n] * Wh[n, j] + bh[j] in the epilogue of the layer (an actor's
+    256 -> 3..8 logits layer, networks.py:22-38), written into columns [off, off + R) of wider rows; two problems in one
+    launch, ragged M and N; the layer's own output is stored as before.  Against float64."""
+    from multi_agent_rl_for_fjsp_b200 import umma
+
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(M + N + R)
+    K, LD = 256, 32
+    x = torch.randn(2, M, K, device=dev, generator=g)
+    w = torch.randn(2, K, N, device=dev, generator=g) / 16
+    b = torch.randn(2, N, device=dev, generator=g)
+    wh = torch.randn(2, N, R, device=dev, generator=g) / 8
+    bh = torch.randn(2, R, device=dev, generator=g)
+    y = torch.zeros(2, M, N, device=dev)
+    out = torch.full((M, LD), 7.0, device=dev)
+    t = umma.GemmTable(dev, umma.OP_KC, umma.OP_MC)
+    offs = (3, 3 + R + 2)
+    for i in range(2):
+        t.add(x, w, y, M, N, K, lda=K, ldb=N, csm=N, a_off=i * M * K, b_off=i * K * N, c_off=i * M * N, bias=b, bias_off=i * N, relu=True,
+              rowdot_w=wh, rowdot_w_off=i * N * R, rowdot_bias=bh, rowdot_bias_off=i * R, rowdot_out=out, rowdot_out_off=offs[i], head_n=R,
+              head_ld=LD)
+    t.launch()
+    touched = torch.zeros(LD, dtype=torch.bool, device=dev)
+    for i in range(2):
+        h = torch.relu(x[i].double() @ w[i].double() + b[i].double())
+        _close(y[i], h, (x[i].double().abs() @ w[i].double().abs()).max().item(), 1e-5)
+        ref = h @ wh[i].double() + bh[i].double()
+        _close(out[:, offs[i]:offs[i] + R], ref, (h.abs() @ wh[i].double().abs()).max().item(), 1e-5)
+        touched[offs[i]:offs[i] + R] = True
+    assert (out[:, ~touched] == 7.0).all()   # nothing outside the head's columns is written

@@ -409,6 +409,18 @@ typedef struct FjspOptSeg {
 } FjspOptSeg;
 int fjsp_a2c_clip_adam(const FjspOptSeg* segs_device, int nseg, int max_elems, float* norms_sq, float max_norm, double beta1,
                        double beta2, double eps, void* stream);
+/* y = relu?(x W + b) with K <= 40, N <= 256 as fp32 FMAs, one job per network: the actors' first layers in a rollout step
+ * (networks.py:22-38: Linear(3..13 -> 256) + ReLU).  The caller guarantees k <= 40 and n <= 256 (checked on the host side of
+ * the table).  max_rows / max_k = the largest `rows` / `k` of the jobs. */
+typedef struct FjspLayer1Job {
+    const float* X;        /* [rows][ldx], columns 0..k-1 */
+    const float* W;        /* [k][n] row-major */
+    const float* bias;     /* [n] or NULL */
+    float* Y;              /* [rows][ldy] */
+    int32_t rows, k, n, ldx, ldy, relu;
+    int32_t reserved[2];
+} FjspLayer1Job;
+int fjsp_a2c_layer1(const FjspLayer1Job* jobs_device, int njobs, int max_rows, int max_k, void* stream);
 /* Weight gradients with a narrow side, G[i*gsi + j*gsj] += sum_b X[b*ldx + i] * Y[b*ldy + j] for i < nx <= 256, j < ny <= 40:
  * the actors' heads, the first layers (transposed) and the critic's value head (a2c.py:647-731 backward of networks.py:22-61).
  * fp32 FMAs, X streamed once; as tensor-core GEMMs these cost as much as a 256 x 256 product each.  max_rows = max B of the

@@ -92,16 +92,16 @@ class UmmaEngine:
 
     # ------------------------------------------------------------------ forward
     def _actor_tables(self, t):
-        """Rollout step t, the eight actors: layer 1 from the observation slices, layer 2 with the 256 -> 3..8 logits layer as
+        """Rollout step t, the eight actors: layer 1 from the observation slices (K = 3..13: fp32 FMAs), layer 2 with the 256 -> 3..8 logits layer as
         a fused head in its epilogue (fp32 FMAs on the values it stores) — TWO grouped launches.  As a third GEMM launch the
         heads cost a step as much as the 256 x 256 layer: 16 K chunks of a latency-bound pipeline for 1-3 % of its flops."""
         N, dev, ps = self.N, self.dev, self.passes
-        l1 = umma.GemmTable(dev, umma.OP_KCS, umma.OP_MC, ps)
+        l1 = umma.Layer1Table(dev)   # K = 3..13: fp32 FMAs (fjsp_a2c_layer1), not a one-chunk tensor-core launch
         l2 = umma.GemmTable(dev, umma.OP_KC, umma.OP_MC, ps)
         for k, d in enumerate(self._nets[:8]):
             (w1, o1), (b1, ob1), (w2, o2), (b2, ob2), (w3, o3), (b3, ob3) = (self._par(d, j) for j in range(6))
-            l1.add(self.obs, w1, self.h1, N, HID, d["k1"], lda=38, ldb=HID, csm=HID, a_off=t * N * 38 + d["lo"], b_off=o1,
-                   c_off=self._hoff(k, t), bias=b1, bias_off=ob1, relu=True)
+            l1.add(self.obs, w1, self.h1, N, HID, d["k1"], ldx=38, ldy=HID, x_off=t * N * 38 + d["lo"], w_off=o1,
+                   y_off=self._hoff(k, t), bias=b1, bias_off=ob1, relu=True)
             l2.add(self.h1, w2, self.h2, N, HID, HID, lda=HID, ldb=HID, csm=HID, a_off=self._hoff(k, t), b_off=o2,
                    c_off=self._hoff(k, t), bias=b2, bias_off=ob2, relu=True, rowdot_w=w3, rowdot_w_off=o3, rowdot_bias=b3,
                    rowdot_bias_off=ob3, rowdot_out=self.logits, rowdot_out_off=t * N * 32 + d["zoff"], head_n=d["nact"], head_ld=32)

@@ -87,7 +87,7 @@ EXPORTS = [
     "fjsp_state_total_bytes", "fjsp_state_save", "fjsp_state_load",
     "fjsp_a2c_sample", "fjsp_a2c_counter_add", "fjsp_a2c_gae", "fjsp_cells_pack_actions", "fjsp_cells_unpack_views",
     "fjsp_a2c_gemm", "fjsp_a2c_loss_grad", "fjsp_export_orders", "fjsp_a2c_gemm_pack", "fjsp_a2c_wgrad_small",
-    "fjsp_host_stream_write_probe", "fjsp_a2c_clip_adam",
+    "fjsp_host_stream_write_probe", "fjsp_a2c_clip_adam", "fjsp_a2c_layer1",
 ]
 
 
@@ -154,6 +154,7 @@ def lib() -> C.CDLL:
     L.fjsp_a2c_gemm.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.fjsp_a2c_gemm_pack.argtypes = [vp, C.c_int, vp]
     L.fjsp_a2c_wgrad_small.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+    L.fjsp_a2c_layer1.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
     L.fjsp_a2c_clip_adam.argtypes = [vp, C.c_int, C.c_int, vp, C.c_float, C.c_double, C.c_double, C.c_double, vp]
     L.fjsp_host_stream_write_probe.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
     L.fjsp_cells_pack_actions.argtypes = [vp, vp, i64, C.c_int, vp]
@@ -215,6 +216,9 @@ WGRAD_JOB_DT = np.dtype([("X", "<u8"), ("Y", "<u8"), ("G", "<u8"), ("B", "<i4"),
                          ("ldy", "<i4"), ("gsi", "<i4"), ("gsj", "<i4"), ("reserved", "<i4", (3,))])  # FjspWgradJob (64 B)
 
 
+LAYER1_JOB_DT = np.dtype([("X", "<u8"), ("W", "<u8"), ("bias", "<u8"), ("Y", "<u8"), ("rows", "<i4"), ("k", "<i4"), ("n", "<i4"),
+                          ("ldx", "<i4"), ("ldy", "<i4"), ("relu", "<i4"), ("reserved", "<i4", (2,))])  # FjspLayer1Job (64 B)
+assert LAYER1_JOB_DT.itemsize == 64
 OPT_SEG_DT = np.dtype([("param", "<u8"), ("grad", "<u8"), ("m", "<u8"), ("v", "<u8"), ("step", "<u8"), ("n", "<i4"), ("net", "<i4"),
                        ("lr", "<f4"), ("bump", "<i4"), ("reserved", "<i8")])  # FjspOptSeg (64 B)
 assert OPT_SEG_DT.itemsize == 64

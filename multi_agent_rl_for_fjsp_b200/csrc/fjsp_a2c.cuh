@@ -326,6 +326,13 @@ __global__ void __launch_bounds__(256) fjsp_a2c_wgrad_small_kernel(const WgradJo
     for (int j = 0; j < NY; j++) acc[j] = 0.f;
     for (int rb = r0; rb < r1; rb += WG_SUB) {
         const int nr = min(WG_SUB, r1 - rb);
+        // the wide operand's 32 loads are issued first: they are in flight while the block's rows of Y go through shared memory
+        // (issued after the second barrier, every 32 rows paid the two latencies one after the other)
+        float x[WG_SUB];
+        if (act) {
+#pragma unroll
+            for (int r = 0; r < WG_SUB; r++) x[r] = r < nr ? __ldg(J.X + (int64_t)(rb + r) * J.ldx + i) : 0.f;
+        }
         __syncthreads();
         for (int e = threadIdx.x; e < WG_SUB * NY; e += 256) {
             const int r = e / NY, j = e % NY;
@@ -333,9 +340,6 @@ __global__ void __launch_bounds__(256) fjsp_a2c_wgrad_small_kernel(const WgradJo
         }
         __syncthreads();
         if (act) {
-            float x[WG_SUB];
-#pragma unroll
-            for (int r = 0; r < WG_SUB; r++) x[r] = r < nr ? __ldg(J.X + (int64_t)(rb + r) * J.ldx + i) : 0.f;
 #pragma unroll
             for (int r = 0; r < WG_SUB; r++) {
 #pragma unroll
@@ -419,6 +423,70 @@ __global__ void fjsp_a2c_opt_finish_kernel(const OptSeg* __restrict__ segs, int 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nseg && segs[i].bump) segs[i].step[0] += 1.0f;
     if (i < 16) norms_sq[i] = 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// First layers of the actors in a rollout step (networks.py:22-38: Linear(3..13 -> 256) + ReLU): y = relu(x W + b) with
+// K <= 40 as plain fp32 FMAs, one job per network.  As a tensor-core launch this layer is ONE K chunk wrapped in the
+// GEMM kernel's fixed costs (TMEM allocation, 99 KB pipeline, staged epilogue): 17 us of a 70 us rollout step for 0.04 GFLOP.
+// CTA = 32 rows x 256 columns; thread = 4 consecutive columns of 8 rows; x tile and W in shared memory; a warp stores
+// 512 contiguous bytes per row.
+// ---------------------------------------------------------------------------------------------
+struct Layer1Job {         // 64 bytes; device array
+    const float* X;        // [rows][ldx], columns 0..k-1 (an observation slice)
+    const float* W;        // [k][n] row-major
+    const float* bias;     // [n]
+    float* Y;              // [rows][ldy]
+    int32_t rows, k, n, ldx, ldy, relu;
+    int32_t reserved[2];
+};
+static_assert(sizeof(Layer1Job) == 64, "Layer1Job layout is part of the ABI (include/fjsp_b200.h FjspLayer1Job)");
+constexpr int L1_ROWS = 32, L1_KMAX = 40, L1_NMAX = 256;
+
+__global__ void __launch_bounds__(256) fjsp_a2c_layer1_kernel(const Layer1Job* __restrict__ jobs, int max_k) {
+    extern __shared__ __align__(16) float l1_smem[];   // W: [max_k][256], then the x tile: [32][41]
+    float* sw = l1_smem;
+    float (*sx)[L1_KMAX + 1] = reinterpret_cast<float (*)[L1_KMAX + 1]>(l1_smem + max_k * L1_NMAX);
+    const Layer1Job J = jobs[blockIdx.y];
+    const int r0 = blockIdx.x * L1_ROWS;
+    if (r0 >= J.rows || J.k > max_k) return;
+    const int tid = threadIdx.x, nrows = min(L1_ROWS, J.rows - r0);
+    // independent loads, several in flight: with a plain strided loop each of the k iterations paid an L2 round trip in series
+    if (tid < J.n) {
+#pragma unroll 8
+        for (int kk = 0; kk < J.k; kk++) sw[kk * L1_NMAX + tid] = __ldg(J.W + kk * J.n + tid);
+    }
+#pragma unroll 5
+    for (int i = tid; i < nrows * J.k; i += 256) sx[i / J.k][i % J.k] = __ldg(J.X + (int64_t)(r0 + i / J.k) * J.ldx + (i % J.k));
+    __syncthreads();
+    const int c = 4 * (tid & 63), rq = tid >> 6;     // columns c..c+3; rows rq, rq + 4, ...
+    if (c >= J.n) return;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (J.bias) {
+        b.x = __ldg(J.bias + c);
+        if (c + 1 < J.n) b.y = __ldg(J.bias + c + 1);
+        if (c + 2 < J.n) b.z = __ldg(J.bias + c + 2);
+        if (c + 3 < J.n) b.w = __ldg(J.bias + c + 3);
+    }
+    const bool vec = c + 4 <= J.n && (J.ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(J.Y) & 15) == 0;
+    for (int r = rq; r < nrows; r += 4) {
+        float4 a = b;
+        for (int k = 0; k < J.k; k++) {
+            const float x = sx[r][k];
+            const float4 w = *reinterpret_cast<const float4*>(sw + k * L1_NMAX + c);
+            a.x = fmaf(x, w.x, a.x), a.y = fmaf(x, w.y, a.y), a.z = fmaf(x, w.z, a.z), a.w = fmaf(x, w.w, a.w);
+        }
+        if (J.relu) a.x = fmaxf(a.x, 0.f), a.y = fmaxf(a.y, 0.f), a.z = fmaxf(a.z, 0.f), a.w = fmaxf(a.w, 0.f);
+        float* y = J.Y + (int64_t)(r0 + r) * J.ldy + c;
+        if (vec) {
+            *reinterpret_cast<float4*>(y) = a;
+        } else {
+            y[0] = a.x;
+            if (c + 1 < J.n) y[1] = a.y;
+            if (c + 2 < J.n) y[2] = a.z;
+            if (c + 3 < J.n) y[3] = a.w;
+        }
+    }
 }
 
 }  // namespace fjsp

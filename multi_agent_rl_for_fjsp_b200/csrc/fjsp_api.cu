@@ -796,6 +796,18 @@ int fjsp_a2c_wgrad_small(const FjspWgradJob* jobs, int njobs, int max_rows, int 
     return 0;
 }
 
+int fjsp_a2c_layer1(const FjspLayer1Job* jobs, int njobs, int max_rows, int max_k, void* stream) {
+    if (!jobs) return fail("jobs is NULL");
+    if (njobs < 1 || njobs > 65535 || max_rows < 1) return fail("njobs must be in 1..65535 and max_rows positive");
+    if (max_k < 1 || max_k > L1_KMAX) return fail("max_k (largest k of the jobs) must be in 1..40");
+    static_assert(sizeof(FjspLayer1Job) == sizeof(Layer1Job), "FjspLayer1Job mirrors Layer1Job");
+    const dim3 grid((unsigned)((max_rows + L1_ROWS - 1) / L1_ROWS), (unsigned)njobs);
+    const size_t smem = ((size_t)max_k * L1_NMAX + L1_ROWS * (L1_KMAX + 1)) * sizeof(float);   // <= 46,208 bytes
+    fjsp_a2c_layer1_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(reinterpret_cast<const Layer1Job*>(jobs), max_k);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int fjsp_a2c_clip_adam(const FjspOptSeg* segs, int nseg, int max_elems, float* norms_sq, float max_norm, double beta1, double beta2,
                        double eps, void* stream) {
     if (!segs || !norms_sq) return fail("segs / norms_sq is NULL");

@@ -153,3 +153,38 @@ class WgradTable:
             rc = abi.lib().fjsp_a2c_wgrad_small(C.c_void_p(tab.data_ptr()), n, max_rows, max_ny, C.c_void_p(st))
             if rc:
                 abi.check(rc)
+
+
+class Layer1Table:
+    """First layers with a short K (``fjsp_a2c_layer1``): Y = relu?(X W + b), K <= 40, N <= 256, plain fp32 FMAs, one job per
+    network, one launch."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.rows, self.keep, self.dev_table, self.max_rows, self.max_k = [], [], None, 1, 1
+
+    def add(self, X, W, Y, rows, n, k, ldx, ldy, x_off=0, w_off=0, y_off=0, bias=None, bias_off=0, relu=True):
+        assert 1 <= k <= 40 and 1 <= n <= 256 and rows >= 1
+        for t in (X, W, Y, bias):
+            assert t is None or (t.dtype == torch.float32 and t.device == self.device)
+        r = np.zeros((), dtype=abi.LAYER1_JOB_DT)
+        r["X"], r["W"], r["bias"], r["Y"] = _addr(X, x_off), _addr(W, w_off), _addr(bias, bias_off), _addr(Y, y_off)
+        r["rows"], r["k"], r["n"], r["ldx"], r["ldy"], r["relu"] = rows, k, n, ldx, ldy, int(bool(relu))
+        self.rows.append(r)
+        self.keep += [X, W, Y, bias]
+        self.max_rows, self.max_k = max(self.max_rows, int(rows)), max(self.max_k, int(k))
+        self.dev_table = None
+        return self
+
+    def finalize(self):
+        host = np.stack(self.rows)
+        self.dev_table = torch.from_numpy(host.view(np.uint8).reshape(len(self.rows), -1).copy()).to(self.device)
+        return self
+
+    def launch(self, stream=None):
+        if self.dev_table is None:
+            self.finalize()
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        rc = abi.lib().fjsp_a2c_layer1(C.c_void_p(self.dev_table.data_ptr()), len(self.rows), self.max_rows, self.max_k, C.c_void_p(st))
+        if rc:
+            abi.check(rc)

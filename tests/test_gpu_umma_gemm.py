@@ -247,3 +247,29 @@ def test_fused_head_of_up_to_eight_columns(M, N, R):
         _close(out[:, offs[i]:offs[i] + R], ref, (h.abs() @ wh[i].double().abs()).max().item(), 1e-5)
         touched[offs[i]:offs[i] + R] = True
     assert (out[:, ~touched] == 7.0).all()   # nothing outside the head's columns is written
+
+
+def test_short_k_first_layers_as_fma_kernel():
+    """``fjsp_a2c_layer1``: relu(x W + b) for K = 3 / 7 / 13 / 38 from slices of 38-wide observation rows, N = 256 and a ragged
+    N, ragged row counts, several jobs in one launch; plain fp32 FMAs against float64 (rtol 1e-6 of the absolute-value product)."""
+    from multi_agent_rl_for_fjsp_b200 import umma
+
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(9)
+    rows = 1000
+    obs = torch.randn(rows, 38, device=dev, generator=g) * 3
+    jobs = [(0, 7, 256, True), (7, 13, 256, True), (20, 3, 256, True), (0, 38, 256, True), (5, 4, 130, False)]
+    tab, outs, refs = umma.Layer1Table(dev), [], []
+    for lo, k, n, relu in jobs:
+        w = torch.randn(k, n, device=dev, generator=g)
+        b = torch.randn(n, device=dev, generator=g)
+        y = torch.full((rows + 3, 256), -7.0, device=dev)
+        r = rows if n == 256 else 333
+        tab.add(obs, w, y, r, n, k, ldx=38, ldy=256, x_off=lo, bias=b, relu=relu)
+        ref = obs[:r, lo:lo + k].double() @ w.double() + b.double()
+        outs.append((y, r, n))
+        refs.append((torch.relu(ref) if relu else ref, (obs[:r, lo:lo + k].double().abs() @ w.double().abs()).max().item()))
+    tab.launch()
+    for (y, r, n), (ref, scale) in zip(outs, refs):
+        _close(y[:r, :n], ref, scale, 1e-6)
+        assert (y[r:] == -7.0).all() and (y[:r, n:] == -7.0).all()

@@ -387,14 +387,22 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_full[s]);
         };
+        constexpr bool TWO_AHEAD = BOP != OP_PK;   // a packed B chunk is 8 float4 per thread: two sets of it would spill
         fetch(la0, lb0, 0);
-        if (nchunks > 1) fetch(la1, lb1, 1);
-        for (int c = 0; c < nchunks; c += 2) {
-            stash(la0, lb0, c);
-            if (c + 2 < nchunks) fetch(la0, lb0, c + 2);
-            if (c + 1 < nchunks) {
-                stash(la1, lb1, c + 1);
-                if (c + 3 < nchunks) fetch(la1, lb1, c + 3);
+        if (TWO_AHEAD) {
+            if (nchunks > 1) fetch(la1, lb1, 1);
+            for (int c = 0; c < nchunks; c += 2) {
+                stash(la0, lb0, c);
+                if (c + 2 < nchunks) fetch(la0, lb0, c + 2);
+                if (c + 1 < nchunks) {
+                    stash(la1, lb1, c + 1);
+                    if (c + 3 < nchunks) fetch(la1, lb1, c + 3);
+                }
+            }
+        } else {
+            for (int c = 0; c < nchunks; c++) {
+                stash(la0, lb0, c);
+                if (c + 1 < nchunks) fetch(la0, lb0, c + 1);
             }
         }
     } else if (lane == 0) {

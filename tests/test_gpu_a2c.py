@@ -321,3 +321,21 @@ def test_clip_adam_call_equals_torch_clipping_and_adam():
     # the state is the optimizer's own: a torch step after ours continues from it
     sd = a.opt.state_dict()
     assert len(sd["state"]) == len(list(a.net.parameters()))
+
+
+def test_single_step_forward_equals_the_rollout_passes():
+    """``UmmaEngine.forward(t)`` (actors of step t + the critic on that step's rows only) reproduces what the rollout computed
+    step by step (actors) and in one batched pass over all steps (critic): same kernels on the same rows, bit for bit."""
+    a, _ = _pair(1000, 4)
+    a.rollout()
+    eng = a.engine
+    for t in (0, 2, a.T):
+        z, v = eng.logits[t].clone(), a.values[t].clone()
+        if t < a.T:
+            eng.logits[t].zero_()
+        a.values[t].zero_()
+        eng.forward(t)
+        torch.cuda.synchronize()
+        assert torch.equal(a.values[t], v), t
+        if t < a.T:
+            assert torch.equal(eng.logits[t], z), t

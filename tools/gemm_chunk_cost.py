@@ -12,21 +12,30 @@ import torch
 from multi_agent_rl_for_fjsp_b200 import umma
 
 dev = torch.device("cuda", 0)
-M = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+M = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 4096
 L, KMAX = 9, 512
 x = torch.randn(L, M, KMAX, device=dev)
 w = torch.randn(L, KMAX, 256, device=dev) / 16
 y = torch.empty(L, M, 256, device=dev)
 b = torch.randn(L, 256, device=dev)
-out = {"rows": M, "problems": L, "us_per_launch": {}}
+out = {"rows": M, "problems": L, "packed_b": "--packed" in sys.argv, "us_per_launch": {}}
+PACKED = "--packed" in sys.argv   # B as packed (hi, lo) weight images (FJSP_OP_PK) instead of fp32 weights split on the fly
 for passes in (3, 1):
     for N in (256, 128, 8):
         pts = []
         for K in (16, 64, 128, 256, 512):
-            t = umma.GemmTable(dev, umma.OP_KC, umma.OP_MC, passes)
+            t = umma.GemmTable(dev, umma.OP_KC, umma.OP_PK if PACKED else umma.OP_MC, passes)
+            if PACKED:
+                pk = umma.PackTable(dev)
+                offs = [pk.add(w, umma.OP_MC, 256, N, K, i * KMAX * 256) for i in range(L)]
+                pk.finalize().launch()
             for i in range(L):
-                t.add(x, w, y, M, N, K, lda=KMAX, ldb=256, csm=256, a_off=i * M * KMAX, b_off=i * KMAX * 256, c_off=i * M * 256, bias=b,
-                      bias_off=i * 256, relu=True)
+                if PACKED:
+                    t.add(x, pk.image, y, M, N, K, lda=KMAX, ldb=0, csm=256, a_off=i * M * KMAX, b_off=offs[i], c_off=i * M * 256, bias=b,
+                          bias_off=i * 256, relu=True)
+                else:
+                    t.add(x, w, y, M, N, K, lda=KMAX, ldb=256, csm=256, a_off=i * M * KMAX, b_off=i * KMAX * 256, c_off=i * M * 256, bias=b,
+                          bias_off=i * 256, relu=True)
             t.finalize()
             for _ in range(3):
                 t.launch()

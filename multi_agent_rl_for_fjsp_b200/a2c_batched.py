@@ -355,6 +355,7 @@ class BatchedA2C:
         T, env = self.T, self.env
         if self.engine is not None:
             eng = self.engine
+            eng.repack()   # packed weight images of this cycle's weights (the optimizer step changed them)
             for t in range(T):
                 eng.forward_actors(t)  # logits -> eng.logits[t]; activations kept for the update
                 rc = self._L.fjsp_a2c_sample(_ptr(eng.logits[t]), _ptr(self.masks[t]), _ptr(self.actions[t]), None, env.num_envs,

@@ -61,6 +61,19 @@ class UmmaEngine:
             off += p.numel()
         self._L = abi.lib()
         self._nets = self._describe()
+        # The 256-wide weight matrices as PACKED (hi, lo) images (fjsp_a2c_gemm_pack, FJSP_OP_PK), one per orientation they are
+        # read in: a K chunk of an image is the B tile of a pipeline stage byte for byte, so the GEMM kernel's B loader moves it
+        # with one bulk copy (cp.async.bulk) and no thread touches the weights.  Re-packed once per cycle (``repack``: 13 us).
+        self._pk = umma.PackTable(dev)
+        self._pk_fwd2, self._pk_dx2 = [], []
+        for d in self._nets:
+            (w2, o2) = self._par(d, 2)
+            self._pk_fwd2.append(self._pk.add(w2, umma.OP_MC, HID, HID, HID, o2))    # y = h1 W2: B(n, k) = W2[k, n]
+            self._pk_dx2.append(self._pk.add(w2, umma.OP_KCS, HID, HID, HID, o2))    # dh1 = dh2 W2^T: B(n, k) = W2[n, k]
+        w3c = self._nets[8]["p"][4]
+        self._pk_fwd3c = self._pk.add(w3c, umma.OP_MC, 128, 128, HID)                # critic 256 -> 128
+        self._pk_dx3c = self._pk.add(w3c, umma.OP_KCS, 128, HID, 128)                # dh2 = dh3 W3^T
+        self._pk.finalize()
         self._fwd_actors = [self._actor_tables(t) for t in range(T)]
         self._fwd_critic = self._critic_tables(0, T + 1)
         self._fwd_critic_step = {}
@@ -97,12 +110,12 @@ class UmmaEngine:
         heads cost a step as much as the 256 x 256 layer: 16 K chunks of a latency-bound pipeline for 1-3 % of its flops."""
         N, dev, ps = self.N, self.dev, self.passes
         l1 = umma.Layer1Table(dev)   # K = 3..13: fp32 FMAs (fjsp_a2c_layer1), not a one-chunk tensor-core launch
-        l2 = umma.GemmTable(dev, umma.OP_KC, umma.OP_MC, ps)
+        l2 = umma.GemmTable(dev, umma.OP_KC, umma.OP_PK, ps)
         for k, d in enumerate(self._nets[:8]):
             (w1, o1), (b1, ob1), (w2, o2), (b2, ob2), (w3, o3), (b3, ob3) = (self._par(d, j) for j in range(6))
             l1.add(self.obs, w1, self.h1, N, HID, d["k1"], ldx=38, ldy=HID, x_off=t * N * 38 + d["lo"], w_off=o1,
                    y_off=self._hoff(k, t), bias=b1, bias_off=ob1, relu=True)
-            l2.add(self.h1, w2, self.h2, N, HID, HID, lda=HID, ldb=HID, csm=HID, a_off=self._hoff(k, t), b_off=o2,
+            l2.add(self.h1, self._pk.image, self.h2, N, HID, HID, lda=HID, ldb=0, csm=HID, a_off=self._hoff(k, t), b_off=self._pk_fwd2[k],
                    c_off=self._hoff(k, t), bias=b2, bias_off=ob2, relu=True, rowdot_w=w3, rowdot_w_off=o3, rowdot_bias=b3,
                    rowdot_bias_off=ob3, rowdot_out=self.logits, rowdot_out_off=t * N * 32 + d["zoff"], head_n=d["nact"], head_ld=32)
         return [x.finalize() for x in (l1, l2)]
@@ -116,15 +129,20 @@ class UmmaEngine:
         (w1, o1), (b1, ob1), (w2, o2), (b2, ob2), (w3, o3), (b3, ob3) = (self._par(d, j) for j in range(6))
         w4, b4 = d["p"][6], d["p"][7]
         l1 = umma.GemmTable(dev, umma.OP_KCS, umma.OP_MC, ps)
-        l2 = umma.GemmTable(dev, umma.OP_KC, umma.OP_MC, ps)
-        l3 = umma.GemmTable(dev, umma.OP_KC, umma.OP_MC, ps)
+        l2 = umma.GemmTable(dev, umma.OP_KC, umma.OP_PK, ps)
+        l3 = umma.GemmTable(dev, umma.OP_KC, umma.OP_PK, ps)
         l1.add(self.obs, w1, self.h1, M, HID, 38, lda=38, ldb=HID, csm=HID, a_off=t0 * N * 38, b_off=o1, c_off=self._hoff(8, t0),
                bias=b1, bias_off=ob1, relu=True)
-        l2.add(self.h1, w2, self.h2, M, HID, HID, lda=HID, ldb=HID, csm=HID, a_off=self._hoff(8, t0), b_off=o2, c_off=self._hoff(8, t0),
-               bias=b2, bias_off=ob2, relu=True)
-        l3.add(self.h2, w3, self.h3, M, 128, HID, lda=HID, ldb=128, csm=128, a_off=self._hoff(8, t0), b_off=o3, c_off=t0 * N * 128,
+        l2.add(self.h1, self._pk.image, self.h2, M, HID, HID, lda=HID, ldb=0, csm=HID, a_off=self._hoff(8, t0), b_off=self._pk_fwd2[8],
+               c_off=self._hoff(8, t0), bias=b2, bias_off=ob2, relu=True)
+        l3.add(self.h2, self._pk.image, self.h3, M, 128, HID, lda=HID, ldb=0, csm=128, a_off=self._hoff(8, t0), b_off=self._pk_fwd3c, c_off=t0 * N * 128,
                bias=b3, bias_off=ob3, relu=True, rowdot_w=w4, rowdot_out=self.values, rowdot_out_off=t0 * N, rowdot_bias=b4)
         return [x.finalize() for x in (l1, l2, l3)]
+
+    def repack(self):
+        """Rebuild the packed weight images from the current weights (one launch).  Call after the weights changed (optimizer
+        step, checkpoint load) and before the next forward / backward."""
+        self._pk.launch()
 
     def forward_actors(self, t):
         """Logits of rollout step t into ``self.logits[t]`` (two grouped launches); hidden activations kept for the update."""
@@ -140,6 +158,7 @@ class UmmaEngine:
 
     def forward(self, t):
         """Everything of rollout step t in one call (tests, single steps): the actors' logits (t < T) and the critic value."""
+        self.repack()
         if t < self.T:
             self.forward_actors(t)
         if t not in self._fwd_critic_step:
@@ -151,8 +170,8 @@ class UmmaEngine:
     def _backward_tables(self):
         B, dev, ps = self.B, self.dev, self.passes
         b3 = umma.GemmTable(dev, umma.OP_KCS, umma.OP_KCS, ps)
-        bc = umma.GemmTable(dev, umma.OP_KC, umma.OP_KC, ps)
-        b2 = umma.GemmTable(dev, umma.OP_KC, umma.OP_KC, ps)
+        bc = umma.GemmTable(dev, umma.OP_KC, umma.OP_PK, ps)
+        b2 = umma.GemmTable(dev, umma.OP_KC, umma.OP_PK, ps)
         dw = umma.GemmTable(dev, umma.OP_MC, umma.OP_MC, ps)
         ws = umma.WgradTable(dev)
         sk = max(1, min(64, B // 2048))
@@ -168,12 +187,12 @@ class UmmaEngine:
             else:
                 w4, gw4 = d["p"][6], d["p"][6].grad
                 b3.add(self.dvalue, w4, self.dh3, B, 128, 1, lda=1, ldb=1, csm=128, mask=self.h3, colsum=gb3, colsum_off=gb3o)
-                bc.add(self.dh3, w3, self.dh2, B, HID, 128, lda=128, ldb=128, csm=HID, b_off=o3, c_off=go, mask=self.h2, mask_off=ho,
-                       colsum=gb2, colsum_off=gb2o)
+                bc.add(self.dh3, self._pk.image, self.dh2, B, HID, 128, lda=128, ldb=0, csm=HID, b_off=self._pk_dx3c, c_off=go, mask=self.h2,
+                       mask_off=ho, colsum=gb2, colsum_off=gb2o)
                 dw.add(self.h2, self.dh3, gw3, HID, 128, B, lda=HID, ldb=128, csm=128, a_off=ho, c_off=g3, atomic=True, splitk=sk)
                 ws.add(self.h3, self.dvalue, gw4, B, 128, 1, ldx=128, ldy=1, gsi=1, gsj=1)
-            b2.add(self.dh2, w2, self.dh1, B, HID, HID, lda=HID, ldb=HID, csm=HID, a_off=go, b_off=o2, c_off=go, mask=self.h1, mask_off=ho,
-                   colsum=gb1, colsum_off=gb1o)
+            b2.add(self.dh2, self._pk.image, self.dh1, B, HID, HID, lda=HID, ldb=0, csm=HID, a_off=go, b_off=self._pk_dx2[k], c_off=go, mask=self.h1,
+                   mask_off=ho, colsum=gb1, colsum_off=gb1o)
             dw.add(self.h1, self.dh2, gw2, HID, HID, B, lda=HID, ldb=HID, csm=HID, a_off=ho, b_off=go, c_off=g2, atomic=True, splitk=sk)
             # dW1[i, j] = sum_rows obs[row, lo + i] * dH1[row, j]: X = dH1 (wide), Y = the observation slice
             ws.add(self.dh1, self.obs, gw1, B, HID, d["k1"], ldx=HID, ldy=38, gsi=1, gsj=HID, x_off=go, y_off=d["lo"], g_off=g1)
@@ -183,6 +202,7 @@ class UmmaEngine:
         """Gradients of the update's losses into ``grad_flat`` (local-batch means; the caller all-reduces and averages).
         ``adv`` / ``returns`` [T,N,8]; ``self.adv_mean`` / ``self.adv_rstd`` must hold the (global) advantage moments."""
         B = self.B
+        self.repack()   # (13 us; the rollout packed the same weights already — kept so that backward() stands on its own)
         self.grad_flat.zero_()
         self.sums.zero_()
         st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)

@@ -323,7 +323,8 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < G_STAGES; s++) mbar_init(&s_full[s], G_PRODUCERS / 32), mbar_init(&s_empty[s], 1);
+        // OP_PK: one more arrival per stage, the B loader's arrive.expect_tx (its bulk copy completes the transaction bytes)
+        for (int s = 0; s < G_STAGES; s++) mbar_init(&s_full[s], G_PRODUCERS / 32 + (BOP == OP_PK ? 1 : 0)), mbar_init(&s_empty[s], 1);
         mbar_init(&s_acc, 1);
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");   // the predecessor's writes (activations, weights) are visible from here
@@ -370,24 +371,21 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
         // (ncu: 60 % of the cycles no warp eligible, long scoreboard) — now a chunk's loads have a whole chunk time to land.
         Loader<AOP, G_BM, ROUND_LO> la0, la1;
         Loader<BOP, G_BN, ROUND_LO> lb0, lb1;
-        const int pk_pieces = (three ? 2 : 1) * G_NQ * npad;   // OP_PK: 16-byte pieces of a chunk of the packed image
         auto fetch = [&](Loader<AOP, G_BM, ROUND_LO>& la, Loader<BOP, G_BN, ROUND_LO>& lb, int c) {
             la.fetch(P.A, P.lda, m0, P.M, (c_begin + c) * G_KC, P.K, tid);
-            if (BOP == OP_PK) lb.fetch(P.B, npad, 0, pk_pieces, (c_begin + c) * G_KC, P.K, tid);
-            else lb.fetch(P.B, P.ldb, 0, P.N, (c_begin + c) * G_KC, P.K, tid);
+            if (BOP != OP_PK) lb.fetch(P.B, P.ldb, 0, P.N, (c_begin + c) * G_KC, P.K, tid);   // OP_PK: the B loader below
         };
         auto stash = [&](const Loader<AOP, G_BM, ROUND_LO>& la, const Loader<BOP, G_BN, ROUND_LO>& lb, int c) {
             const int s = c % G_STAGES;
             if (c >= G_STAGES) mbar_wait_or_trap(&s_empty[s], ((c / G_STAGES) - 1) & 1);
             unsigned char* st = g_smem + s * G_STAGE_BYTES;
             la.stash(st, st + G_A_BYTES, G_LBO_A, tid, three);
-            if (BOP == OP_PK) lb.stash(st + 2 * G_A_BYTES, nullptr, pk_pieces, tid, three);
-            else lb.stash(st + 2 * G_A_BYTES, st + 2 * G_A_BYTES + G_B_BYTES, G_LBO_B, tid, three);
+            if (BOP != OP_PK) lb.stash(st + 2 * G_A_BYTES, st + 2 * G_A_BYTES + G_B_BYTES, G_LBO_B, tid, three);
             fence_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_full[s]);
         };
-        constexpr bool TWO_AHEAD = BOP != OP_PK;   // a packed B chunk is 8 float4 per thread: two sets of it would spill
+        constexpr bool TWO_AHEAD = true;
         fetch(la0, lb0, 0);
         if (TWO_AHEAD) {
             if (nchunks > 1) fetch(la1, lb1, 1);
@@ -431,6 +429,20 @@ __global__ void __launch_bounds__(G_THREADS, 2) fjsp_gemm_kernel(const GemmProb*
             mma_commit(&s_empty[s]);  // the stage is free again once these MMAs have read it
         }
         mma_commit(&s_acc);           // accumulator complete
+    } else if (BOP == OP_PK && lane == 1) {
+        // ===== B loader (packed weight images): one thread, one bulk copy per chunk =====
+        // A chunk of the image is the stage's B tile byte for byte (hi planes, then lo planes), so the copy engine moves it:
+        // no thread touches the weights.  (Through registers — 8 + 8 vector loads / stores per producer thread — the B tile
+        // cost a chunk ~1 us whichever form the weights had: tools/gemm_chunk_cost.py.)
+        const uint32_t bytes = (uint32_t)((three ? 2 : 1) * G_NQ * npad) * 16u;
+        const size_t chunk_stride = (size_t)2 * G_NQ * npad * 16;   // bytes per chunk in the image (always hi + lo)
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(P.B) + (size_t)c_begin * chunk_stride;
+        for (int c = 0; c < nchunks; c++) {
+            const int s = c % G_STAGES;
+            if (c >= G_STAGES) mbar_wait_or_trap(&s_empty[s], ((c / G_STAGES) - 1) & 1);
+            mbar_expect_tx(&s_full[s], bytes);
+            bulk_g2s(g_smem + s * G_STAGE_BYTES + 2 * G_A_BYTES, src + (size_t)c * chunk_stride, bytes, &s_full[s]);
+        }
     }
 
     if (warp < G_PRODUCERS / 32) {

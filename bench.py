@@ -547,8 +547,8 @@ def run_ours(args):
                "envs_per_gpu": 4096, "rollout_len": 32, "updates": 20, "ms_per_update": secs / 20 * 1e3,
                "params": nparams, "impl": "umma: grouped tcgen05 GEMMs (TMEM accumulators), analytic loss gradients, rollout "
                                            "activations reused by the update, actors' logits layer fused into the second layer's "
-                                           "epilogue, critic forward batched after the rollout, per-network clipping + Adam as one "
-                                           "call, CUDA-graph rollout and update",
+                                           "epilogue, critic forward batched after the rollout, packed weight images fed by "
+                                           "cp.async.bulk, per-network clipping + Adam as one call, CUDA-graph rollout and update",
                "gemm_precision": "3xTF32 (fp32 operands split into two TF32 terms, three products, fp32 accumulate: fp32-level)",
                "cuda_graph_rollout": True,
                "gradient_allreduce": "nccl, one flat 2.62 MB buffer" if world > 1 else "none (1 GPU)",

@@ -16,10 +16,17 @@ w = torch.randn(L, 256, 256, device=dev) / 16
 b = torch.randn(L, 256, device=dev)
 y = torch.empty(L, B, 256, device=dev)
 dw = torch.zeros(L, 256, 256, device=dev)
-t = umma.GemmTable(dev, *{"fwd": (umma.OP_KC, umma.OP_MC), "dx": (umma.OP_KC, umma.OP_KC), "dw": (umma.OP_MC, umma.OP_MC)}[mode])
+t = umma.GemmTable(dev, *{"fwd": (umma.OP_KC, umma.OP_MC), "dx": (umma.OP_KC, umma.OP_KC), "dw": (umma.OP_MC, umma.OP_MC),
+                          "fwdpk": (umma.OP_KC, umma.OP_PK)}[mode])
+if mode == "fwdpk":   # what the trainer runs: the weights as packed (hi, lo) images, moved by the B loader's bulk copies
+    pk = umma.PackTable(dev)
+    offs = [pk.add(w, umma.OP_MC, 256, 256, 256, i * 65536) for i in range(L)]
+    pk.finalize().launch()
 for i in range(L):
     o = i * B * 256
-    if mode == "fwd":
+    if mode == "fwdpk":
+        t.add(x, pk.image, y, B, 256, 256, 256, 0, 256, a_off=o, b_off=offs[i], c_off=o, bias=b, bias_off=i * 256, relu=True)
+    elif mode == "fwd":
         t.add(x, w, y, B, 256, 256, 256, 256, 256, a_off=o, b_off=i * 65536, c_off=o, bias=b, bias_off=i * 256, relu=True)
     elif mode == "dx":
         t.add(x, w, y, B, 256, 256, 256, 256, 256, a_off=o, b_off=i * 65536, c_off=o, mask=x, mask_off=o)

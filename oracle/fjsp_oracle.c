@@ -24,7 +24,9 @@
  * Pinning: the reference ships no tests or golden vectors, so this restatement is
  * pinned against (a) golden trajectories generated here by executing the unmodified reference
  * (oracle/gen_golden.py -> tests/golden/, tests/test_oracle_golden.py) and (b) live differential runs
- * against the reference in this container (tests/test_oracle_vs_reference.py).
+ * against the reference in this container (tests/test_oracle_vs_reference.py).  In both, the
+ * unmodified reference runs on oracle/shims/simpy, a restatement of the SimPy 4 core from its
+ * documented semantics: SimPy itself is not vendored by the reference and not installable here.
  */
 #include <math.h>
 #include <stdint.h>

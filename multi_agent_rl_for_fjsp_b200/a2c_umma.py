@@ -12,8 +12,9 @@ read it), and the update only runs the backward chain over the ``T*N`` rows:
     (KCS,KCS) x9         dH2 = (dlogits_i W3_i^T) * (H2 > 0)   and the critic head  dH3 = (dvalue w4^T) * (H3 > 0)
     (KC,KC)   x1         critic: dH2 = (dH3 Wc3^T) * (H2 > 0)
     (KC,KC)   x9         dH1 = (dH2 W2^T) * (H1 > 0)
-    (MC,MC)   x10        the 256 x 256 (and the critic's 256 x 128) weight gradients, split-K over the batch, atomic accumulation
-    wgrad_small x18      the narrow ones (heads 256 x 3..8, first layers 3..38 x 256, value head 128 x 1): fp32 FMAs, one pass
+    (MC,MC)   x11        the 256 x 256 (and the critic's 256 x 128 and 38 x 256) weight gradients, split-K over the batch, atomic
+                         accumulation
+    wgrad_small x17      the narrow ones (heads 256 x 3..8, first layers 3..13 x 256, value head 128 x 1): fp32 FMAs, one pass
                          over the wide operand (as GEMMs each costs as much as a 256 x 256 product)
     bias gradients       column sums in the epilogues of the dH GEMMs (same pass)
 
@@ -195,7 +196,12 @@ class UmmaEngine:
                    mask_off=ho, colsum=gb1, colsum_off=gb1o)
             dw.add(self.h1, self.dh2, gw2, HID, HID, B, lda=HID, ldb=HID, csm=HID, a_off=ho, b_off=go, c_off=g2, atomic=True, splitk=sk)
             # dW1[i, j] = sum_rows obs[row, lo + i] * dH1[row, j]: X = dH1 (wide), Y = the observation slice
-            ws.add(self.dh1, self.obs, gw1, B, HID, d["k1"], ldx=HID, ldy=38, gsi=1, gsj=HID, x_off=go, y_off=d["lo"], g_off=g1)
+            if d["k1"] > 16:   # the critic's 38 x 256: 38 FMAs per streamed element make the FMA kernel compute-bound (0.21 ms);
+                #                   one 128-row tile of the tensor-core GEMM (A = the observation rows, 38 of 128 used) is cheaper
+                dw.add(self.obs, self.dh1, gw1, d["k1"], HID, B, lda=38, ldb=HID, csm=HID, a_off=d["lo"], b_off=go, c_off=g1, atomic=True,
+                       splitk=sk)
+            else:
+                ws.add(self.dh1, self.obs, gw1, B, HID, d["k1"], ldx=HID, ldy=38, gsi=1, gsj=HID, x_off=go, y_off=d["lo"], g_off=g1)
         return [x.finalize() for x in (b3, bc, b2, dw, ws)]
 
     def backward(self, adv, returns, entropy_coef):

@@ -409,6 +409,20 @@ typedef struct FjspOptSeg {
 } FjspOptSeg;
 int fjsp_a2c_clip_adam(const FjspOptSeg* segs_device, int nseg, int max_elems, float* norms_sq, float max_norm, double beta1,
                        double beta2, double eps, void* stream);
+/* Backward through a narrow head (an actor's 256 -> 3..8 logits layer, the critic's 128 -> 1 value head; a2c.py:647-731) in one
+ * pass over the head's post-ReLU input H: dH[m, n] = (sum_j dl[m, j] W[n, j]) * (H[m, n] > 0); gb[n] += sum_m dH[m, n] (the
+ * bias gradient of the layer below); gW[n, j] += sum_m H[m, n] dl[m, j].  n % 4 == 0, n <= 256, na <= 8, H / dH rows of n
+ * floats, 16-byte aligned.  gW and gb are accumulated into (zero them first).  max_rows = the largest `rows` of the jobs. */
+typedef struct FjspHeadBwdJob {
+    const float* dl;       /* [rows][ld_dl], columns 0..na-1 */
+    const float* W;        /* [n][na] row-major */
+    const float* H;        /* [rows][n] */
+    float* dH;             /* [rows][n] */
+    float* gW;             /* [n][na] */
+    float* gb;             /* [n] or NULL */
+    int32_t rows, n, na, ld_dl;
+} FjspHeadBwdJob;
+int fjsp_a2c_head_backward(const FjspHeadBwdJob* jobs_device, int njobs, int max_rows, void* stream);
 /* y = relu?(x W + b) with K <= 40, N <= 256 as fp32 FMAs, one job per network: the actors' first layers in a rollout step
  * (networks.py:22-38: Linear(3..13 -> 256) + ReLU).  The caller guarantees k <= 40 and n <= 256 (checked on the host side of
  * the table).  max_rows / max_k = the largest `rows` / `k` of the jobs. */

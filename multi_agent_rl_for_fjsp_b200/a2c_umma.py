@@ -9,12 +9,13 @@ second layer's epilogue; critic: three launches over all ``(T+1)*N`` rows once t
 read it), and the update only runs the backward chain over the ``T*N`` rows:
 
     loss_grad            dlogits [B,32], dvalue [B]  (+ last-layer bias gradients, loss statistics)
-    (KCS,KCS) x9         dH2 = (dlogits_i W3_i^T) * (H2 > 0)   and the critic head  dH3 = (dvalue w4^T) * (H3 > 0)
+    head_backward x9     dH2 = (dlogits_i W3_i^T) * (H2 > 0) with the bias gradient of layer 2 and dW3_i = H2^T dlogits_i in the same
+                         pass over H2 (fp32 FMAs); the critic's value head dH3 = (dvalue w4^T) * (H3 > 0), dw4 likewise
     (KC,KC)   x1         critic: dH2 = (dH3 Wc3^T) * (H2 > 0)
     (KC,KC)   x9         dH1 = (dH2 W2^T) * (H1 > 0)
     (MC,MC)   x11        the 256 x 256 (and the critic's 256 x 128 and 38 x 256) weight gradients, split-K over the batch, atomic
                          accumulation
-    wgrad_small x17      the narrow ones (heads 256 x 3..8, first layers 3..13 x 256, value head 128 x 1): fp32 FMAs, one pass
+    wgrad_small x8       the narrow first layers (3..13 x 256): fp32 FMAs, one pass
                          over the wide operand (as GEMMs each costs as much as a 256 x 256 product)
     bias gradients       column sums in the epilogues of the dH GEMMs (same pass)
 
@@ -170,7 +171,7 @@ class UmmaEngine:
     # ------------------------------------------------------------------ backward (one update)
     def _backward_tables(self):
         B, dev, ps = self.B, self.dev, self.passes
-        b3 = umma.GemmTable(dev, umma.OP_KCS, umma.OP_KCS, ps)
+        hb = umma.HeadBwdTable(dev)
         bc = umma.GemmTable(dev, umma.OP_KC, umma.OP_PK, ps)
         b2 = umma.GemmTable(dev, umma.OP_KC, umma.OP_PK, ps)
         dw = umma.GemmTable(dev, umma.OP_MC, umma.OP_MC, ps)
@@ -182,16 +183,16 @@ class UmmaEngine:
             ho, go = self._hoff(k), k * B * HID
             if k < 8:
                 na, zo = d["nact"], d["zoff"]
-                b3.add(self.dlogits, w3, self.dh2, B, HID, na, lda=32, ldb=na, csm=HID, a_off=zo, b_off=o3, c_off=go,
-                       mask=self.h2, mask_off=ho, colsum=gb2, colsum_off=gb2o)
-                ws.add(self.h2, self.dlogits, gw3, B, HID, na, ldx=HID, ldy=32, gsi=na, gsj=1, x_off=ho, y_off=zo, g_off=g3)
+                # backward through the logits layer in one pass over H2: dH2, the bias gradient of layer 2 and the head's own
+                # weight gradient (was: a K <= 8 tensor-core launch that is all epilogue + a narrow-gradient job, H2 read twice)
+                hb.add(self.dlogits, w3, self.h2, self.dh2, gw3, gb2, B, HID, na, 32, dl_off=zo, w_off=o3, h_off=ho, dh_off=go, gw_off=g3,
+                       gb_off=gb2o)
             else:
                 w4, gw4 = d["p"][6], d["p"][6].grad
-                b3.add(self.dvalue, w4, self.dh3, B, 128, 1, lda=1, ldb=1, csm=128, mask=self.h3, colsum=gb3, colsum_off=gb3o)
+                hb.add(self.dvalue, w4, self.h3, self.dh3, gw4, gb3, B, 128, 1, 1, gb_off=gb3o)   # the value head, the same way
                 bc.add(self.dh3, self._pk.image, self.dh2, B, HID, 128, lda=128, ldb=0, csm=HID, b_off=self._pk_dx3c, c_off=go, mask=self.h2,
                        mask_off=ho, colsum=gb2, colsum_off=gb2o)
                 dw.add(self.h2, self.dh3, gw3, HID, 128, B, lda=HID, ldb=128, csm=128, a_off=ho, c_off=g3, atomic=True, splitk=sk)
-                ws.add(self.h3, self.dvalue, gw4, B, 128, 1, ldx=128, ldy=1, gsi=1, gsj=1)
             b2.add(self.dh2, self._pk.image, self.dh1, B, HID, HID, lda=HID, ldb=0, csm=HID, a_off=go, b_off=self._pk_dx2[k], c_off=go, mask=self.h1,
                    mask_off=ho, colsum=gb1, colsum_off=gb1o)
             dw.add(self.h1, self.dh2, gw2, HID, HID, B, lda=HID, ldb=HID, csm=HID, a_off=ho, b_off=go, c_off=g2, atomic=True, splitk=sk)
@@ -202,7 +203,7 @@ class UmmaEngine:
                        splitk=sk)
             else:
                 ws.add(self.dh1, self.obs, gw1, B, HID, d["k1"], ldx=HID, ldy=38, gsi=1, gsj=HID, x_off=go, y_off=d["lo"], g_off=g1)
-        return [x.finalize() for x in (b3, bc, b2, dw, ws)]
+        return [x.finalize() for x in (hb, bc, b2, dw, ws)]
 
     def backward(self, adv, returns, entropy_coef):
         """Gradients of the update's losses into ``grad_flat`` (local-batch means; the caller all-reduces and averages).

@@ -87,7 +87,7 @@ EXPORTS = [
     "fjsp_state_total_bytes", "fjsp_state_save", "fjsp_state_load",
     "fjsp_a2c_sample", "fjsp_a2c_counter_add", "fjsp_a2c_gae", "fjsp_cells_pack_actions", "fjsp_cells_unpack_views",
     "fjsp_a2c_gemm", "fjsp_a2c_loss_grad", "fjsp_export_orders", "fjsp_a2c_gemm_pack", "fjsp_a2c_wgrad_small",
-    "fjsp_host_stream_write_probe", "fjsp_a2c_clip_adam", "fjsp_a2c_layer1",
+    "fjsp_host_stream_write_probe", "fjsp_a2c_clip_adam", "fjsp_a2c_layer1", "fjsp_a2c_head_backward",
 ]
 
 
@@ -154,6 +154,7 @@ def lib() -> C.CDLL:
     L.fjsp_a2c_gemm.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
     L.fjsp_a2c_gemm_pack.argtypes = [vp, C.c_int, vp]
     L.fjsp_a2c_wgrad_small.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+    L.fjsp_a2c_head_backward.argtypes = [vp, C.c_int, C.c_int, vp]
     L.fjsp_a2c_layer1.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
     L.fjsp_a2c_clip_adam.argtypes = [vp, C.c_int, C.c_int, vp, C.c_float, C.c_double, C.c_double, C.c_double, vp]
     L.fjsp_host_stream_write_probe.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
@@ -216,6 +217,9 @@ WGRAD_JOB_DT = np.dtype([("X", "<u8"), ("Y", "<u8"), ("G", "<u8"), ("B", "<i4"),
                          ("ldy", "<i4"), ("gsi", "<i4"), ("gsj", "<i4"), ("reserved", "<i4", (3,))])  # FjspWgradJob (64 B)
 
 
+HEAD_BWD_JOB_DT = np.dtype([("dl", "<u8"), ("W", "<u8"), ("H", "<u8"), ("dH", "<u8"), ("gW", "<u8"), ("gb", "<u8"), ("rows", "<i4"),
+                            ("n", "<i4"), ("na", "<i4"), ("ld_dl", "<i4")])  # FjspHeadBwdJob (64 B)
+assert HEAD_BWD_JOB_DT.itemsize == 64
 LAYER1_JOB_DT = np.dtype([("X", "<u8"), ("W", "<u8"), ("bias", "<u8"), ("Y", "<u8"), ("rows", "<i4"), ("k", "<i4"), ("n", "<i4"),
                           ("ldx", "<i4"), ("ldy", "<i4"), ("relu", "<i4"), ("reserved", "<i4", (2,))])  # FjspLayer1Job (64 B)
 assert LAYER1_JOB_DT.itemsize == 64

@@ -489,4 +489,95 @@ __global__ void __launch_bounds__(256) fjsp_a2c_layer1_kernel(const Layer1Job* _
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Backward through an actor's logits layer (networks.py:22-38: Linear(256 -> 3..8)) — and the critic's value head
+// (Linear(128 -> 1)) — in ONE pass over the layer's input activations H (a2c.py:647-731 backward):
+//     dH[m, n]  = (sum_j dl[m, j] * W[n, j]) * (H[m, n] > 0)      gradient into the ReLU layer below
+//     gb[n]    += sum_m dH[m, n]                                   that layer's bias gradient
+//     gW[n, j] += sum_m H[m, n] * dl[m, j]                         the head's own weight gradient
+// As two kernels (a K <= 8 tensor-core launch that is all epilogue + the narrow-gradient kernel) H was read twice;
+// here a row of H is read once: thread = 4 columns of 64 rows of a 512-row slab, the head's weights and its gradient's
+// partial sums in registers, the rows of dl broadcast from shared memory, one reduction per CTA.
+// ---------------------------------------------------------------------------------------------
+struct HeadBwdJob {        // 64 bytes; device array
+    const float* dl;       // [rows][ld_dl], columns 0..na-1 (gradient of the head's outputs)
+    const float* W;        // [n][na] row-major
+    const float* H;        // [rows][n]: post-ReLU input of the head
+    float* dH;             // [rows][n]
+    float* gW;             // [n][na], accumulated into
+    float* gb;             // [n], accumulated into
+    int32_t rows, n, na, ld_dl;
+};
+static_assert(sizeof(HeadBwdJob) == 64, "HeadBwdJob layout is part of the ABI (include/fjsp_b200.h FjspHeadBwdJob)");
+constexpr int HB_SLAB = 512, HB_SUB = 32;
+
+__global__ void __launch_bounds__(256, 2) fjsp_a2c_head_backward_kernel(const HeadBwdJob* __restrict__ jobs) {
+    __shared__ __align__(16) float sdl[HB_SUB][8];
+    __shared__ float sred[256][9];   // per column: the head's 8 weight-gradient sums and the column sum
+    const HeadBwdJob J = jobs[blockIdx.y];
+    const int r0 = blockIdx.x * HB_SLAB;
+    if (r0 >= J.rows) return;
+    const int r1 = min(J.rows, r0 + HB_SLAB), tid = threadIdx.x;
+    const int c = 4 * (tid & 63), rq = tid >> 6;
+    const bool active = c < J.n;      // (n % 4 == 0: checked by the host)
+    float w[4][8], acc[4][8], cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            w[i][j] = (active && j < J.na) ? __ldg(J.W + (int64_t)(c + i) * J.na + j) : 0.f;
+            acc[i][j] = 0.f;
+        }
+    }
+    for (int i = tid; i < 256 * 9; i += 256) (&sred[0][0])[i] = 0.f;
+    for (int rb = r0; rb < r1; rb += HB_SUB) {
+        __syncthreads();
+        {
+            const int r = tid >> 3, j = tid & 7;   // 32 rows x 8 columns = 256 threads
+            sdl[r][j] = (rb + r < r1 && j < J.na) ? __ldg(J.dl + (int64_t)(rb + r) * J.ld_dl + j) : 0.f;
+        }
+        __syncthreads();
+        if (active) {
+            const int nr = min(HB_SUB, r1 - rb);
+#pragma unroll 4
+            for (int r = rq; r < nr; r += 4) {
+                const int64_t m = rb + r;
+                const float4 h4 = __ldg(reinterpret_cast<const float4*>(J.H + m * J.n + c));
+                const float4 d0 = *reinterpret_cast<const float4*>(&sdl[r][0]), d1 = *reinterpret_cast<const float4*>(&sdl[r][4]);
+                const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+                const float h[4] = {h4.x, h4.y, h4.z, h4.w};
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) v = fmaf(d[j], w[i][j], v), acc[i][j] = fmaf(h[i], d[j], acc[i][j]);
+                    o[i] = h[i] > 0.f ? v : 0.f;
+                    cs[i] += o[i];
+                }
+                *reinterpret_cast<float4*>(J.dH + m * J.n + c) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (j < J.na) atomicAdd(&sred[c + i][j], acc[i][j]);
+            atomicAdd(&sred[c + i][8], cs[i]);
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < J.n * 9; e += 256) {
+        const int col = e / 9, j = e % 9;
+        const float v = sred[col][j];
+        if (j == 8) {
+            if (J.gb && v != 0.f) atomicAdd(J.gb + col, v);
+        } else if (j < J.na && v != 0.f) {
+            atomicAdd(J.gW + (int64_t)col * J.na + j, v);
+        }
+    }
+}
+
 }  // namespace fjsp

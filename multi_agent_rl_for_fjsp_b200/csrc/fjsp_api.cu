@@ -796,6 +796,16 @@ int fjsp_a2c_wgrad_small(const FjspWgradJob* jobs, int njobs, int max_rows, int 
     return 0;
 }
 
+int fjsp_a2c_head_backward(const FjspHeadBwdJob* jobs, int njobs, int max_rows, void* stream) {
+    if (!jobs) return fail("jobs is NULL");
+    if (njobs < 1 || njobs > 65535 || max_rows < 1) return fail("njobs must be in 1..65535 and max_rows positive");
+    static_assert(sizeof(FjspHeadBwdJob) == sizeof(HeadBwdJob), "FjspHeadBwdJob mirrors HeadBwdJob");
+    const dim3 grid((unsigned)((max_rows + HB_SLAB - 1) / HB_SLAB), (unsigned)njobs);
+    fjsp_a2c_head_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const HeadBwdJob*>(jobs));
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int fjsp_a2c_layer1(const FjspLayer1Job* jobs, int njobs, int max_rows, int max_k, void* stream) {
     if (!jobs) return fail("jobs is NULL");
     if (njobs < 1 || njobs > 65535 || max_rows < 1) return fail("njobs must be in 1..65535 and max_rows positive");

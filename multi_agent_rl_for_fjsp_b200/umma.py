@@ -188,3 +188,40 @@ class Layer1Table:
         rc = abi.lib().fjsp_a2c_layer1(C.c_void_p(self.dev_table.data_ptr()), len(self.rows), self.max_rows, self.max_k, C.c_void_p(st))
         if rc:
             abi.check(rc)
+
+
+class HeadBwdTable:
+    """Backward through narrow heads (``fjsp_a2c_head_backward``): per job dH = (dl W^T) * (H > 0), gb += column sums of dH,
+    gW += H^T dl, in one pass over H; one launch for all jobs."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.rows, self.keep, self.dev_table, self.max_rows = [], [], None, 1
+
+    def add(self, dl, W, H, dH, gW, gb, rows, n, na, ld_dl, dl_off=0, w_off=0, h_off=0, dh_off=0, gw_off=0, gb_off=0):
+        assert 1 <= na <= 8 and 4 <= n <= 256 and n % 4 == 0 and rows >= 1
+        for t in (dl, W, H, dH, gW, gb):
+            assert t is None or (t.dtype == torch.float32 and t.device == self.device)
+        assert _addr(H, h_off) % 16 == 0 and _addr(dH, dh_off) % 16 == 0
+        r = np.zeros((), dtype=abi.HEAD_BWD_JOB_DT)
+        r["dl"], r["W"], r["H"], r["dH"] = _addr(dl, dl_off), _addr(W, w_off), _addr(H, h_off), _addr(dH, dh_off)
+        r["gW"], r["gb"] = _addr(gW, gw_off), _addr(gb, gb_off)
+        r["rows"], r["n"], r["na"], r["ld_dl"] = rows, n, na, ld_dl
+        self.rows.append(r)
+        self.keep += [dl, W, H, dH, gW, gb]
+        self.max_rows = max(self.max_rows, int(rows))
+        self.dev_table = None
+        return self
+
+    def finalize(self):
+        host = np.stack(self.rows)
+        self.dev_table = torch.from_numpy(host.view(np.uint8).reshape(len(self.rows), -1).copy()).to(self.device)
+        return self
+
+    def launch(self, stream=None):
+        if self.dev_table is None:
+            self.finalize()
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        rc = abi.lib().fjsp_a2c_head_backward(C.c_void_p(self.dev_table.data_ptr()), len(self.rows), self.max_rows, C.c_void_p(st))
+        if rc:
+            abi.check(rc)

@@ -273,3 +273,30 @@ def test_short_k_first_layers_as_fma_kernel():
     for (y, r, n), (ref, scale) in zip(outs, refs):
         _close(y[:r, :n], ref, scale, 1e-6)
         assert (y[r:] == -7.0).all() and (y[:r, n:] == -7.0).all()
+
+
+@pytest.mark.parametrize("B,n,na,ld", [(5000, 256, 8, 32), (1537, 256, 3, 32), (2049, 128, 1, 1), (700, 256, 5, 32)])
+def test_head_backward_in_one_pass(B, n, na, ld):
+    """``fjsp_a2c_head_backward``: dH = (dl W^T) * (H > 0), gb += column sums of dH, gW += H^T dl in one pass over H; dl is a
+    column slice of wider rows; gW / gb are accumulated into; ragged row counts; plain fp32 FMAs against float64."""
+    from multi_agent_rl_for_fjsp_b200 import umma
+
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(B + n + na)
+    off = 3 if ld > na else 0
+    dl = torch.randn(B, ld, device=dev, generator=g)
+    W = torch.randn(n, na, device=dev, generator=g) / 4
+    H = torch.relu(torch.randn(B + 2, n, device=dev, generator=g))
+    dH = torch.full((B + 2, n), -7.0, device=dev)
+    gW0, gb0 = torch.randn(n, na, device=dev, generator=g), torch.randn(n, device=dev, generator=g)
+    gW, gb = gW0.clone(), gb0.clone()
+    t = umma.HeadBwdTable(dev)
+    t.add(dl, W, H, dH, gW, gb, B, n, na, ld, dl_off=off)
+    t.launch()
+    d = dl[:, off:off + na].double()
+    ref = (d @ W.double().t()) * (H[:B] > 0)
+    scale = (d.abs() @ W.double().abs().t()).max().item()
+    _close(dH[:B], ref, scale, 1e-6)
+    assert (dH[B:] == -7.0).all()
+    _close(gb, gb0.double() + ref.sum(0), ref.abs().sum(0).max().item() + 1.0, 1e-5)
+    _close(gW, gW0.double() + H[:B].double().t() @ d, (H[:B].double().abs().t() @ d.abs()).max().item() + 1.0, 1e-5)

@@ -509,17 +509,36 @@ struct HeadBwdJob {        // 64 bytes; device array
     int32_t rows, n, na, ld_dl;
 };
 static_assert(sizeof(HeadBwdJob) == 64, "HeadBwdJob layout is part of the ABI (include/fjsp_b200.h FjspHeadBwdJob)");
-constexpr int HB_SLAB = 512, HB_SUB = 32;
+constexpr int HB_SLAB = 512, HB_SUB = 32, HB_STAGES = 3;
+constexpr int HB_SMEM_BYTES = HB_STAGES * HB_SUB * 256 * 4;   // 98,304: the ring of H sub-blocks (32 rows x <= 256 floats each)
 
 __global__ void __launch_bounds__(256, 2) fjsp_a2c_head_backward_kernel(const HeadBwdJob* __restrict__ jobs) {
+    // The rows of H arrive by bulk copies (cp.async.bulk) into a ring of three 32-row sub-blocks — two CTAs keep 6 x 32 KB in
+    // flight per SM; with plain loads the 16 warps an SM holds (the head's weights and its gradient's partial sums take 64
+    // registers per thread) reached half of the HBM bandwidth (ncu: no warp eligible in 65 % of the cycles).
+    extern __shared__ __align__(128) unsigned char hb_smem[];
+    float* sh = reinterpret_cast<float*>(hb_smem);
+    __shared__ uint64_t bar[HB_STAGES];
     __shared__ __align__(16) float sdl[HB_SUB][8];
     __shared__ float sred[256][9];   // per column: the head's 8 weight-gradient sums and the column sum
     const HeadBwdJob J = jobs[blockIdx.y];
     const int r0 = blockIdx.x * HB_SLAB;
     if (r0 >= J.rows) return;
     const int r1 = min(J.rows, r0 + HB_SLAB), tid = threadIdx.x;
+    const int nsub = (r1 - r0 + HB_SUB - 1) / HB_SUB;
     const int c = 4 * (tid & 63), rq = tid >> 6;
     const bool active = c < J.n;      // (n % 4 == 0: checked by the host)
+    auto issue = [&](int it) {        // thread 0: sub-block `it` of the slab into stage it % HB_STAGES
+        const int rb = r0 + it * HB_SUB, nr = min(HB_SUB, r1 - rb);
+        const uint32_t bytes = (uint32_t)(nr * J.n * 4);
+        uint64_t* b = &bar[it % HB_STAGES];
+        mbar_expect_tx(b, bytes);
+        bulk_g2s(sh + (it % HB_STAGES) * HB_SUB * J.n, J.H + (int64_t)rb * J.n, bytes, b);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < HB_STAGES; s++) mbar_init(&bar[s], 1);
+    }
     float w[4][8], acc[4][8], cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -530,19 +549,30 @@ __global__ void __launch_bounds__(256, 2) fjsp_a2c_head_backward_kernel(const He
         }
     }
     for (int i = tid; i < 256 * 9; i += 256) (&sred[0][0])[i] = 0.f;
-    for (int rb = r0; rb < r1; rb += HB_SUB) {
-        __syncthreads();
+    __syncthreads();   // barriers initialised
+    if (tid == 0) {
+        for (int it = 0; it < HB_STAGES && it < nsub; it++) issue(it);
+    }
+    for (int it = 0; it < nsub; it++) {
+        const int rb = r0 + it * HB_SUB;
+        __syncthreads();   // everyone is done with sub-block it - 1: its rows of dl, and its stage of the ring
+        if (tid == 0 && it >= 1 && it - 1 + HB_STAGES < nsub) {
+            fence_async_smem();
+            issue(it - 1 + HB_STAGES);
+        }
         {
             const int r = tid >> 3, j = tid & 7;   // 32 rows x 8 columns = 256 threads
             sdl[r][j] = (rb + r < r1 && j < J.na) ? __ldg(J.dl + (int64_t)(rb + r) * J.ld_dl + j) : 0.f;
         }
         __syncthreads();
+        mbar_wait(&bar[it % HB_STAGES], (uint32_t)((it / HB_STAGES) & 1));
         if (active) {
             const int nr = min(HB_SUB, r1 - rb);
-#pragma unroll 4
+            const float* hs = sh + (it % HB_STAGES) * HB_SUB * J.n;
+#pragma unroll 2
             for (int r = rq; r < nr; r += 4) {
                 const int64_t m = rb + r;
-                const float4 h4 = __ldg(reinterpret_cast<const float4*>(J.H + m * J.n + c));
+                const float4 h4 = *reinterpret_cast<const float4*>(hs + r * J.n + c);
                 const float4 d0 = *reinterpret_cast<const float4*>(&sdl[r][0]), d1 = *reinterpret_cast<const float4*>(&sdl[r][4]);
                 const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
                 const float h[4] = {h4.x, h4.y, h4.z, h4.w};

@@ -801,7 +801,14 @@ int fjsp_a2c_head_backward(const FjspHeadBwdJob* jobs, int njobs, int max_rows, 
     if (njobs < 1 || njobs > 65535 || max_rows < 1) return fail("njobs must be in 1..65535 and max_rows positive");
     static_assert(sizeof(FjspHeadBwdJob) == sizeof(HeadBwdJob), "FjspHeadBwdJob mirrors HeadBwdJob");
     const dim3 grid((unsigned)((max_rows + HB_SLAB - 1) / HB_SLAB), (unsigned)njobs);
-    fjsp_a2c_head_backward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const HeadBwdJob*>(jobs));
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+        CK(cudaFuncSetAttribute(fjsp_a2c_head_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_SMEM_BYTES));
+        attr_dev = dev;
+    }
+    fjsp_a2c_head_backward_kernel<<<grid, 256, HB_SMEM_BYTES, (cudaStream_t)stream>>>(reinterpret_cast<const HeadBwdJob*>(jobs));
     CK(cudaGetLastError());
     return 0;
 }

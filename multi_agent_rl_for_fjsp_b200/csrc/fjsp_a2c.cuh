@@ -313,9 +313,14 @@ struct WgradJob {          // 64 bytes; device array
 static_assert(sizeof(WgradJob) == 64, "WgradJob layout is part of the ABI (include/fjsp_b200.h FjspWgradJob)");
 constexpr int WG_SLAB = 512, WG_SUB = 32;   // rows per CTA, rows per shared-memory tile of Y
 
+constexpr int WG_STAGES = 3;
+constexpr int WG_SMEM_BYTES = WG_STAGES * WG_SUB * 256 * 4;   // 98,304: ring of X sub-blocks (32 rows x <= 256 floats)
+
 template <int NY>
 __global__ void __launch_bounds__(256) fjsp_a2c_wgrad_small_kernel(const WgradJob* __restrict__ jobs) {
     __shared__ float sy[WG_SUB][NY];
+    __shared__ uint64_t bar[WG_STAGES];
+    extern __shared__ __align__(128) unsigned char wg_smem[];
     const WgradJob J = jobs[blockIdx.y];
     const int r0 = blockIdx.x * WG_SLAB;
     if (r0 >= J.B || J.ny > NY) return;
@@ -324,6 +329,56 @@ __global__ void __launch_bounds__(256) fjsp_a2c_wgrad_small_kernel(const WgradJo
     float acc[NY];
 #pragma unroll
     for (int j = 0; j < NY; j++) acc[j] = 0.f;
+    // Rows of X that are contiguous in memory (ldx == nx, 16-byte aligned: the trainer's activation gradients) arrive by
+    // cp.async.bulk into a ring of three 32-row sub-blocks, as in fjsp_a2c_head_backward_kernel; otherwise plain loads below.
+    if (J.ldx == J.nx && (J.nx & 3) == 0 && (reinterpret_cast<uintptr_t>(J.X) & 15) == 0) {
+        float* sh = reinterpret_cast<float*>(wg_smem);
+        const int nsub = (r1 - r0 + WG_SUB - 1) / WG_SUB;
+        auto issue = [&](int it) {
+            const int rb = r0 + it * WG_SUB, nr = min(WG_SUB, r1 - rb);
+            const uint32_t bytes = (uint32_t)(nr * J.nx * 4);
+            uint64_t* b = &bar[it % WG_STAGES];
+            mbar_expect_tx(b, bytes);
+            bulk_g2s(sh + (it % WG_STAGES) * WG_SUB * J.nx, J.X + (int64_t)rb * J.nx, bytes, b);
+        };
+        if (i == 0) {
+#pragma unroll
+            for (int s = 0; s < WG_STAGES; s++) mbar_init(&bar[s], 1);
+        }
+        __syncthreads();
+        if (i == 0) {
+            for (int it = 0; it < WG_STAGES && it < nsub; it++) issue(it);
+        }
+        for (int it = 0; it < nsub; it++) {
+            const int rb = r0 + it * WG_SUB, nr = min(WG_SUB, r1 - rb);
+            __syncthreads();   // everyone is done with sub-block it - 1 (its rows of Y, its stage of the ring)
+            if (i == 0 && it >= 1 && it - 1 + WG_STAGES < nsub) {
+                fence_async_smem();
+                issue(it - 1 + WG_STAGES);
+            }
+            for (int e = threadIdx.x; e < WG_SUB * NY; e += 256) {
+                const int r = e / NY, j = e % NY;
+                sy[r][j] = (r < nr && j < J.ny) ? __ldg(J.Y + (int64_t)(rb + r) * J.ldy + j) : 0.f;
+            }
+            __syncthreads();
+            mbar_wait(&bar[it % WG_STAGES], (uint32_t)((it / WG_STAGES) & 1));
+            if (act) {
+                const float* xs = sh + (it % WG_STAGES) * WG_SUB * J.nx + i;
+#pragma unroll 8
+                for (int r = 0; r < WG_SUB; r++) {
+                    const float x = r < nr ? xs[r * J.nx] : 0.f;
+#pragma unroll
+                    for (int j = 0; j < NY; j++) acc[j] = fmaf(x, sy[r][j], acc[j]);
+                }
+            }
+        }
+        if (act) {
+#pragma unroll
+            for (int j = 0; j < NY; j++)
+                if (j < J.ny) atomicAdd(J.G + (int64_t)i * J.gsi + (int64_t)j * J.gsj, acc[j]);
+        }
+        return;
+    }
     for (int rb = r0; rb < r1; rb += WG_SUB) {
         const int nr = min(WG_SUB, r1 - rb);
         // the wide operand's 32 loads are issued first: they are in flight while the block's rows of Y go through shared memory

@@ -789,9 +789,18 @@ int fjsp_a2c_wgrad_small(const FjspWgradJob* jobs, int njobs, int max_rows, int 
     static_assert(sizeof(FjspWgradJob) == sizeof(WgradJob), "FjspWgradJob mirrors WgradJob");
     const dim3 grid((unsigned)((max_rows + WG_SLAB - 1) / WG_SLAB), (unsigned)njobs);
     const WgradJob* j = reinterpret_cast<const WgradJob*>(jobs);
-    if (max_ny <= 8) fjsp_a2c_wgrad_small_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(j);
-    else if (max_ny <= 16) fjsp_a2c_wgrad_small_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(j);
-    else fjsp_a2c_wgrad_small_kernel<40><<<grid, 256, 0, (cudaStream_t)stream>>>(j);
+    static thread_local int attr_dev = -1;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (attr_dev != dev) {
+        CK(cudaFuncSetAttribute(fjsp_a2c_wgrad_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(fjsp_a2c_wgrad_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
+        CK(cudaFuncSetAttribute(fjsp_a2c_wgrad_small_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
+        attr_dev = dev;
+    }
+    if (max_ny <= 8) fjsp_a2c_wgrad_small_kernel<8><<<grid, 256, WG_SMEM_BYTES, (cudaStream_t)stream>>>(j);
+    else if (max_ny <= 16) fjsp_a2c_wgrad_small_kernel<16><<<grid, 256, WG_SMEM_BYTES, (cudaStream_t)stream>>>(j);
+    else fjsp_a2c_wgrad_small_kernel<40><<<grid, 256, WG_SMEM_BYTES, (cudaStream_t)stream>>>(j);
     CK(cudaGetLastError());
     return 0;
 }
